@@ -1,0 +1,98 @@
+// Shared host-side plumbing of libhdd_b200: status codes, error string, CUDA checks, launch counter.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/hdd_b200.h"
+
+namespace hdd {
+
+// Exception carrying the hdd_status the C-ABI function will return.  The set mirrors the exception types the
+// reference throws on this path (see include/hdd_b200.h).
+struct Error : std::runtime_error {
+  int status;
+  Error(int s, const std::string& what) : std::runtime_error(what), status(s) {}
+};
+
+void set_last_error(const std::string& msg);
+
+extern std::atomic<int64_t> g_kernel_launches;
+inline void count_launch(int n = 1) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define HDD_THROW(status, msg)                     \
+  do {                                             \
+    std::ostringstream hdd_oss_;                   \
+    hdd_oss_ << msg;                               \
+    throw ::hdd::Error((status), hdd_oss_.str());  \
+  } while (0)
+
+#define HDD_CUDA(call)                                                                              \
+  do {                                                                                              \
+    cudaError_t hdd_err_ = (call);                                                                  \
+    if (hdd_err_ != cudaSuccess)                                                                    \
+      HDD_THROW(HDD_ERR_DEVICE, "CUDA error '" << cudaGetErrorString(hdd_err_) << "' at " << __FILE__ \
+                                               << ":" << __LINE__ << " in " #call);                 \
+  } while (0)
+
+// Wraps the body of every extern "C" entry point.
+template <class F>
+int guarded(F&& f) noexcept {
+  try {
+    f();
+    return HDD_OK;
+  } catch (const Error& e) {
+    set_last_error(e.what());
+    return e.status;
+  } catch (const std::bad_alloc&) {
+    set_last_error("out of host memory");
+    return HDD_ERR_INTERNAL;
+  } catch (const std::exception& e) {
+    set_last_error(e.what());
+    return HDD_ERR_INTERNAL;
+  } catch (...) {
+    set_last_error("unknown error");
+    return HDD_ERR_INTERNAL;
+  }
+}
+
+// RAII device buffer
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void alloc(size_t count) {
+    release();
+    if (count == 0) count = 1;
+    HDD_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
+    n = count;
+  }
+  void upload(const T* host, size_t count, cudaStream_t s) {
+    if (n < count || !p) alloc(count);
+    if (count) HDD_CUDA(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void zero(cudaStream_t s) {
+    if (p) HDD_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+  }
+};
+
+}  // namespace hdd

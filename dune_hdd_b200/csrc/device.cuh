@@ -1,0 +1,208 @@
+// Device-side types and element helpers shared by the kernels (sm_100a).
+#pragma once
+#include <cstdint>
+
+#include "expr.hpp"
+#include "quadrature.hpp"
+
+namespace hdd {
+
+constexpr int kMaxParts = 8;
+
+// A data function localised for the device (see hdd_function): constant, per local cell, or postfix program.
+struct DevFn {
+  int kind;
+  int order;
+  double value;
+  const double* cell;  // indexed by LOCAL cell id
+  Program prog;
+};
+
+// sum_k theta[k] * fn[k]: a frozen affinely decomposed function (problem.with_mu(mu), estimators/swipdg.hh:134).
+struct DevCombo {
+  int n;
+  int order;
+  double theta[kMaxParts];
+  const DevFn* fn[kMaxParts];
+};
+
+// Local mesh of one rank: cells [0, n_loc) sorted by global id = [lower halo | owned | upper halo].
+struct MeshView {
+  int kind;
+  int nl;
+  int32_t n_loc;
+  int32_t own0;
+  int32_t n_own;
+  const double* cgeo;       // simplex: x0,y0,x1,y1,x2,y2 per cell; cube: x0,y0,x1,y1 (vertices 0 and 3)
+  const int32_t* neigh;     // [n_own*nf] local neighbour ids, -1 = domain boundary
+  const uint8_t* btype;     // [n_own*nf] 1 Dirichlet, 2 Neumann
+  const double* tensor;     // [n_loc*4] or nullptr (identity)
+  const int64_t* blk_start; // [n_own+1] number of matrix blocks in front of owned cell k
+  const int32_t* cgid;      // [n_loc] global cell id
+};
+
+__device__ __forceinline__ double fn_eval(const DevFn& f, int cell, double x, double y) {
+  if (f.kind == HDD_FN_CONSTANT) return f.value;
+  if (f.kind == HDD_FN_CELLWISE) return __ldg(f.cell + cell);
+  const double v[2] = {x, y};
+  return eval_program(f.prog, v);
+}
+
+__device__ __forceinline__ double combo_eval(const DevCombo& c, int cell, double x, double y) {
+  double s = 0.0;
+  for (int k = 0; k < c.n; ++k) s += c.theta[k] * fn_eval(*c.fn[k], cell, x, y);
+  return s;
+}
+
+__device__ __forceinline__ void load_tensor(const double* tensor, int cell, double K[4]) {
+  if (tensor) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(tensor + 4 * size_t(cell)));
+    const double2 b = __ldg(reinterpret_cast<const double2*>(tensor + 4 * size_t(cell)) + 1);
+    K[0] = a.x; K[1] = a.y; K[2] = b.x; K[3] = b.y;
+  } else {
+    K[0] = 1.0; K[1] = 0.0; K[2] = 0.0; K[3] = 1.0;
+  }
+}
+
+// ---- elements ------------------------------------------------------------------------------------------
+template <int KIND>
+struct Geo;
+
+// P1 on a triangle, Dune numbering: vertices (0,0),(1,0),(0,1); faces {0,1},{0,2},{1,2}.
+template <>
+struct Geo<HDD_SIMPLEX2D> {
+  static constexpr int NL = 3, NF = 3, NGEO = 6;
+  double vx[3], vy[3];
+  double i00, i01, i10, i11, detj;
+
+  __device__ __forceinline__ void load(const double* cgeo, int cell) {
+    const double2* p = reinterpret_cast<const double2*>(cgeo + size_t(NGEO) * cell);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double2 v = __ldg(p + i);
+      vx[i] = v.x;
+      vy[i] = v.y;
+    }
+    const double j00 = vx[1] - vx[0], j10 = vy[1] - vy[0], j01 = vx[2] - vx[0], j11 = vy[2] - vy[0];
+    const double det = j00 * j11 - j01 * j10;
+    detj = fabs(det);
+    i00 = j11 / det; i01 = -j01 / det; i10 = -j10 / det; i11 = j00 / det;
+  }
+  __device__ __forceinline__ void to_global(double xi, double eta, double& x, double& y) const {
+    x = vx[0] + (vx[1] - vx[0]) * xi + (vx[2] - vx[0]) * eta;
+    y = vy[0] + (vy[1] - vy[0]) * xi + (vy[2] - vy[0]) * eta;
+  }
+  __device__ __forceinline__ void to_local(double x, double y, double& xi, double& eta) const {
+    const double dx = x - vx[0], dy = y - vy[0];
+    xi = i00 * dx + i01 * dy;
+    eta = i10 * dx + i11 * dy;
+  }
+  __device__ __forceinline__ void basis(double xi, double eta, double* phi, double* gx, double* gy) const {
+    phi[0] = 1.0 - xi - eta; phi[1] = xi; phi[2] = eta;
+    gx[0] = -i00 - i10; gy[0] = -i01 - i11;
+    gx[1] = i00;        gy[1] = i01;
+    gx[2] = i10;        gy[2] = i11;
+  }
+  __device__ __forceinline__ void centroid(double& cx, double& cy) const {
+    cx = (vx[0] + vx[1] + vx[2]) / 3.0;
+    cy = (vy[0] + vy[1] + vy[2]) / 3.0;
+  }
+  __device__ __forceinline__ void face_ends(int f, double& ax, double& ay, double& bx, double& by) const {
+    const int a = f == 2 ? 1 : 0, b = f == 0 ? 1 : 2;
+    ax = vx[a]; ay = vy[a]; bx = vx[b]; by = vy[b];
+  }
+  __device__ __forceinline__ double diameter() const {
+    double h = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = i + 1; j < 3; ++j) h = fmax(h, hypot(vx[i] - vx[j], vy[i] - vy[j]));
+    return h;
+  }
+};
+
+// Q1 on an axis-parallel rectangle, Dune numbering: vertices (0,0),(1,0),(0,1),(1,1); faces {0,2},{1,3},{0,1},{2,3}.
+template <>
+struct Geo<HDD_CUBE2D> {
+  static constexpr int NL = 4, NF = 4, NGEO = 4;
+  double x0, y0, x1, y1, hx, hy, detj;
+
+  __device__ __forceinline__ void load(const double* cgeo, int cell) {
+    const double2* p = reinterpret_cast<const double2*>(cgeo + size_t(NGEO) * cell);
+    const double2 a = __ldg(p), b = __ldg(p + 1);
+    x0 = a.x; y0 = a.y; x1 = b.x; y1 = b.y;
+    hx = x1 - x0; hy = y1 - y0;
+    detj = fabs(hx * hy);
+  }
+  __device__ __forceinline__ void to_global(double xi, double eta, double& x, double& y) const {
+    x = x0 + hx * xi;
+    y = y0 + hy * eta;
+  }
+  __device__ __forceinline__ void to_local(double x, double y, double& xi, double& eta) const {
+    xi = (x - x0) / hx;
+    eta = (y - y0) / hy;
+  }
+  __device__ __forceinline__ void basis(double xi, double eta, double* phi, double* gx, double* gy) const {
+    phi[0] = (1.0 - xi) * (1.0 - eta); phi[1] = xi * (1.0 - eta);
+    phi[2] = (1.0 - xi) * eta;         phi[3] = xi * eta;
+    gx[0] = -(1.0 - eta) / hx; gx[1] = (1.0 - eta) / hx; gx[2] = -eta / hx; gx[3] = eta / hx;
+    gy[0] = -(1.0 - xi) / hy;  gy[1] = -xi / hy;         gy[2] = (1.0 - xi) / hy; gy[3] = xi / hy;
+  }
+  __device__ __forceinline__ void centroid(double& cx, double& cy) const {
+    cx = 0.5 * (x0 + x1);
+    cy = 0.5 * (y0 + y1);
+  }
+  __device__ __forceinline__ void face_ends(int f, double& ax, double& ay, double& bx, double& by) const {
+    // {0,2} left, {1,3} right, {0,1} bottom, {2,3} top
+    ax = (f == 1) ? x1 : x0;
+    ay = (f == 3) ? y1 : y0;
+    bx = (f == 0) ? x0 : x1;
+    by = (f == 2) ? y0 : y1;
+  }
+  __device__ __forceinline__ double diameter() const { return hypot(hx, hy); }
+};
+
+struct FaceGeo {
+  double ax, ay, bx, by, nx, ny, h;
+};
+
+template <class G>
+__device__ __forceinline__ FaceGeo make_face(const G& g, int f) {
+  FaceGeo e;
+  g.face_ends(f, e.ax, e.ay, e.bx, e.by);
+  const double tx = e.bx - e.ax, ty = e.by - e.ay;
+  e.h = sqrt(tx * tx + ty * ty);
+  e.nx = ty / e.h;
+  e.ny = -tx / e.h;
+  double cx, cy;
+  g.centroid(cx, cy);
+  if (e.nx * (0.5 * (e.ax + e.bx) - cx) + e.ny * (0.5 * (e.ay + e.by) - cy) < 0.0) {
+    e.nx = -e.nx;
+    e.ny = -e.ny;
+  }
+  return e;
+}
+
+// upstream GDT::LocalEvaluation::SWIPDG::internal::{inner,boundary}_sigma(polOrder)
+__host__ __device__ inline double sigma_inner(int p) { return p <= 1 ? 8.0 : p <= 2 ? 20.0 : p <= 3 ? 38.0 : 62.0; }
+__host__ __device__ inline double sigma_boundary(int p) { return p <= 1 ? 14.0 : p <= 2 ? 38.0 : p <= 3 ? 74.0 : 122.0; }
+
+// Sorted block slots of an owned cell: the row block of cell T holds one n_loc x n_loc block per member of
+// sort({T} u neighbours) (EllipticSWIPDG::pattern + SparsityPatternDefault ordering).
+template <int NF>
+__device__ __forceinline__ int block_slot(int self, const int* nb, int target) {
+  int s = self < target ? 1 : 0;
+#pragma unroll
+  for (int f = 0; f < NF; ++f) s += (nb[f] >= 0 && nb[f] < target) ? 1 : 0;
+  return s;
+}
+
+template <int NF>
+__device__ __forceinline__ int block_count(const int* nb) {
+  int s = 1;
+#pragma unroll
+  for (int f = 0; f < NF; ++f) s += nb[f] >= 0 ? 1 : 0;
+  return s;
+}
+
+}  // namespace hdd

@@ -1,0 +1,90 @@
+// Expression functions: the host compiles the strings the reference hands to
+// Stuff::Functions::Expression("x", "<expr>", order) (problems/OS2014.hh:63-74) and to
+// Pymor::ParameterFunctional("mu", 1, "<expr>") (problems/OS2014.hh:72, problems/spe10.hh:164-167,
+// discretizations/swipdg.hh:319-321) into a small postfix program that the CUDA kernels evaluate at their own
+// quadrature points - no coefficient arrays travel through HBM for analytic data.
+#pragma once
+#include <cmath>
+#include <string>
+
+#ifdef __CUDACC__
+#define HDD_HD __host__ __device__
+#else
+#define HDD_HD
+#endif
+
+namespace hdd {
+
+enum Op : unsigned char {
+  OP_CONST = 0,
+  OP_VAR0,  // x[0] or mu[0] / mu
+  OP_VAR1,  // x[1] or mu[1]
+  OP_VAR2,
+  OP_VAR3,
+  OP_ADD,
+  OP_SUB,
+  OP_MUL,
+  OP_DIV,
+  OP_NEG,
+  OP_POW,
+  OP_SIN,
+  OP_COS,
+  OP_TAN,
+  OP_EXP,
+  OP_LOG,
+  OP_SQRT,
+  OP_ABS,
+  OP_ATAN,
+  OP_MIN,
+  OP_MAX
+};
+
+constexpr int kMaxOps = 48;
+constexpr int kMaxConsts = 16;
+constexpr int kMaxStack = 16;
+
+struct Program {
+  int n_ops;
+  unsigned char op[kMaxOps];
+  unsigned char cidx[kMaxOps];  // constant slot for OP_CONST
+  double cst[kMaxConsts];
+};
+
+// Evaluates a compiled program.  vars: x[0], x[1] (functions) or mu[0..3] (parameter functionals).
+HDD_HD inline double eval_program(const Program& p, const double* vars) {
+  double st[kMaxStack];
+  int sp = 0;
+  for (int k = 0; k < p.n_ops; ++k) {
+    switch (p.op[k]) {
+      case OP_CONST: st[sp++] = p.cst[p.cidx[k]]; break;
+      case OP_VAR0: st[sp++] = vars[0]; break;
+      case OP_VAR1: st[sp++] = vars[1]; break;
+      case OP_VAR2: st[sp++] = vars[2]; break;
+      case OP_VAR3: st[sp++] = vars[3]; break;
+      case OP_ADD: --sp; st[sp - 1] = st[sp - 1] + st[sp]; break;
+      case OP_SUB: --sp; st[sp - 1] = st[sp - 1] - st[sp]; break;
+      case OP_MUL: --sp; st[sp - 1] = st[sp - 1] * st[sp]; break;
+      case OP_DIV: --sp; st[sp - 1] = st[sp - 1] / st[sp]; break;
+      case OP_POW: --sp; st[sp - 1] = pow(st[sp - 1], st[sp]); break;
+      case OP_MIN: --sp; st[sp - 1] = fmin(st[sp - 1], st[sp]); break;
+      case OP_MAX: --sp; st[sp - 1] = fmax(st[sp - 1], st[sp]); break;
+      case OP_NEG: st[sp - 1] = -st[sp - 1]; break;
+      case OP_SIN: st[sp - 1] = sin(st[sp - 1]); break;
+      case OP_COS: st[sp - 1] = cos(st[sp - 1]); break;
+      case OP_TAN: st[sp - 1] = tan(st[sp - 1]); break;
+      case OP_EXP: st[sp - 1] = exp(st[sp - 1]); break;
+      case OP_LOG: st[sp - 1] = log(st[sp - 1]); break;
+      case OP_SQRT: st[sp - 1] = sqrt(st[sp - 1]); break;
+      case OP_ABS: st[sp - 1] = fabs(st[sp - 1]); break;
+      case OP_ATAN: st[sp - 1] = atan(st[sp - 1]); break;
+      default: break;
+    }
+  }
+  return sp > 0 ? st[0] : 0.0;
+}
+
+// Compiles `text` with the (vector) variable called `var` ("x" or "mu"): var[k], and bare `var` for var[0].
+// Throws hdd::Error(HDD_ERR_WRONG_INPUT) on syntax errors or programs that are too long.
+Program compile_expression(const std::string& text, const std::string& var);
+
+}  // namespace hdd

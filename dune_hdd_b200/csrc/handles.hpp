@@ -1,0 +1,178 @@
+// Handle definitions behind the opaque hdd_mesh / hdd_swipdg pointers.
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.hpp"
+#include "kernels.hpp"
+
+struct ncclComm;
+
+namespace hdd {
+
+// thin, lazily dlopen'ed NCCL binding (libnccl.so.2 - the copy torch already loaded, if any)
+struct Nccl {
+  static Nccl& get();
+  bool available() const { return handle_ != nullptr; }
+  void unique_id(void* id128);
+  ncclComm* init_rank(const void* id128, int rank, int world);
+  void destroy(ncclComm* c);
+  void all_reduce_sum(double* buf, size_t count, ncclComm* c, cudaStream_t s);
+  void all_reduce_min(double* buf, size_t count, ncclComm* c, cudaStream_t s);
+  void group_start();
+  void group_end();
+  void send(const double* buf, size_t count, int peer, ncclComm* c, cudaStream_t s);
+  void recv(double* buf, size_t count, int peer, ncclComm* c, cudaStream_t s);
+
+ private:
+  Nccl();
+  void check(int result, const char* what);
+  void* handle_ = nullptr;
+  void* fn_[12] = {};
+};
+
+struct HaloPeer {
+  int rank;
+  int64_t send_offset, send_count;  // in DoFs, into the packed send buffer
+  int64_t recv_offset, recv_count;  // in DoFs, into the local vector (contiguous: halo sorted by global id)
+};
+
+}  // namespace hdd
+
+struct hdd_mesh {
+  int kind = 0, nl = 0, nf = 0, device = 0;
+  cudaStream_t stream = nullptr;
+  int64_t n_global = 0, cell_begin = 0, cell_end = 0;
+  int32_t n_loc = 0, own0 = 0, n_own = 0;
+  int32_t n_verts_loc = 0;
+
+  // host copies needed after creation
+  std::vector<int32_t> cgid;       // [n_loc]
+  std::vector<int32_t> h_neigh;    // [n_own*nf] local ids
+  std::vector<int32_t> h_sub;      // [n_loc] subdomain of each local cell
+  int n_subdomains = 1;
+  std::vector<int64_t> sub_cell_offsets;             // [n_subdomains+1] global cell offsets
+  std::vector<int64_t> sub_dof_offsets;              // nl * sub_cell_offsets
+  std::vector<std::vector<int32_t>> sub_neighbours;  // [n_subdomains]
+  std::vector<double> sub_diameter;                  // [n_subdomains], owned subdomains only (else 0)
+  int sub_first = 0, sub_last = 0;                   // owned subdomains [sub_first, sub_last)
+  std::vector<int64_t> seg_ptr;                      // chunked owned-cell segments for deterministic sums
+  std::vector<int32_t> seg_sub;                      // subdomain of each segment
+
+  // device
+  hdd::DevBuf<double> cgeo;
+  hdd::DevBuf<int32_t> neigh, d_cgid, cell_verts;
+  hdd::DevBuf<uint8_t> btype, vboundary;
+  hdd::DevBuf<int64_t> blk_start, vptr, d_seg_ptr;
+  hdd::DevBuf<int32_t> vdof;
+  int64_t n_blocks = 0;  // blk_start[n_own]
+  bool has_btype = false;
+
+  // multi GPU
+  int rank = 0, world = 1;
+  ncclComm* comm = nullptr;
+  std::vector<int64_t> rank_cell_offsets;  // [world+1]
+  std::vector<hdd::HaloPeer> peers;
+  hdd::DevBuf<int32_t> send_idx;  // local DoF indices to pack
+  hdd::DevBuf<double> send_buf;
+  // host scratch used while the halo plan is built
+  std::vector<int32_t> h_cell_verts_loc;  // [n_loc*nl] local vertex ids of all local cells
+
+  hdd::MeshView view(const double* tensor) const {
+    hdd::MeshView v{};
+    v.kind = kind;
+    v.nl = nl;
+    v.n_loc = n_loc;
+    v.own0 = own0;
+    v.n_own = n_own;
+    v.cgeo = cgeo.p;
+    v.neigh = neigh.p;
+    v.btype = has_btype ? btype.p : nullptr;
+    v.tensor = tensor;
+    v.blk_start = blk_start.p;
+    v.cgid = d_cgid.p;
+    return v;
+  }
+  void set_device() const { HDD_CUDA(cudaSetDevice(device)); }
+  // fills the halo part of a local vector from the owning ranks (no-op for world == 1)
+  void halo_exchange(double* v_local);
+  ~hdd_mesh();
+};
+
+namespace hdd {
+
+struct FnRef {       // index into the device function table, -1 = absent
+  int idx = -1;
+  int order = 0;
+  bool zero = false; // constant 0: contributes nothing, kernels are skipped
+};
+
+struct AffineFn {
+  std::vector<FnRef> comps;
+  std::vector<std::string> coef_expr;
+  std::vector<Program> coef_prog;
+  FnRef affine;
+  bool has_affine() const { return affine.idx >= 0; }
+  bool parametric() const { return !comps.empty(); }
+};
+
+struct RhsTerm {  // one local functional added into a rhs vector
+  int kind;       // 0 L2Volume(f), 1 DirichletBoundarySWIPDG(factor, g)
+  FnRef f, g;
+};
+
+struct VectorPart {
+  std::string coef_expr;  // empty for the affine part
+  Program coef_prog{};
+  std::vector<RhsTerm> terms;
+  DevBuf<double> values;
+};
+
+struct MatrixPart {
+  std::string coef_expr;
+  Program coef_prog{};
+  FnRef factor;
+  DevBuf<double> values;
+};
+
+}  // namespace hdd
+
+struct hdd_swipdg {
+  hdd_mesh* mesh = nullptr;
+  int polorder = 1;
+  std::string parameter_name;
+  int parameter_size = 0;
+
+  hdd::AffineFn factor, force, dirichlet, neumann;
+  std::vector<hdd::DevFn> fn_host;
+  std::vector<std::unique_ptr<hdd::DevBuf<double>>> fn_cell_storage;
+  hdd::DevBuf<hdd::DevFn> fn_dev;
+  hdd::DevBuf<double> tensor;
+  bool has_tensor = false;
+
+  bool initialized = false;
+  std::vector<hdd::MatrixPart> lhs_comps;
+  std::unique_ptr<hdd::MatrixPart> lhs_affine;
+  std::vector<hdd::VectorPart> rhs_comps;
+  std::unique_ptr<hdd::VectorPart> rhs_affine;
+  std::vector<const char*> coef_cstr_cache;
+
+  int64_t nnz = 0, n_rows = 0;
+  hdd::DevBuf<int64_t> rowptr;
+  hdd::DevBuf<int32_t> col;
+
+  // solve workspace
+  hdd::DevBuf<double> frozen, dinv, b, x, r, p, q, partial, tmp_local;
+  hdd::DevBuf<hdd::CgScalars> sc;
+  hdd::CgScalars* sc_host = nullptr;  // pinned
+  bool have_solution = false;
+
+  // estimator workspace
+  hdd::DevBuf<double> vertex_mean, ind_out, seg_out;
+
+  hdd::MeshView view() const { return mesh->view(has_tensor ? tensor.p : nullptr); }
+  const hdd::DevFn* fn(const hdd::FnRef& r) const { return fn_dev.p + r.idx; }
+  ~hdd_swipdg();
+};

@@ -1,0 +1,94 @@
+// Host-callable launchers of the sm_100a kernels (K1..K10 of SURVEY.md 8a).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "device.cuh"
+
+namespace hdd {
+
+// ---- K1: pattern ------------------------------------------------------------------------------------------
+// nblk[k] = number of blocks of owned cell k (1 + #neighbours); blk_start is its exclusive prefix sum.
+void launch_count_blocks(const MeshView& m, int64_t* nblk, cudaStream_t s);
+void exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, cudaStream_t s);
+void launch_fill_csr(const MeshView& m, int64_t* rowptr, int32_t* col, cudaStream_t s);
+
+// ---- K2/K3: assembly ----------------------------------------------------------------------------------------
+// one affine part of the system matrix: values in CSR order of the owned rows
+void launch_assemble_lhs(const MeshView& m, const DevFn* factor_dev, int factor_order, int polorder, double* values,
+                         cudaStream_t s);
+// b += L2Volume(force)
+void launch_rhs_volume(const MeshView& m, const DevFn* force_dev, int force_order, int polorder, double* b,
+                       cudaStream_t s);
+// b += DirichletBoundarySWIPDG(factor, tensor, dirichlet)
+void launch_rhs_dirichlet(const MeshView& m, const DevFn* factor_dev, int factor_order, const DevFn* dirichlet_dev,
+                          int dirichlet_order, int polorder, double* b, cudaStream_t s);
+
+// ---- K4: freeze -----------------------------------------------------------------------------------------------
+// out = sum_k theta[k] * parts[k]   (values-only AXPY over a shared pattern, discretizations/base.hh:349-361)
+struct FreezeArgs {
+  int n;
+  double theta[kMaxParts];
+  const double* part[kMaxParts];
+};
+void launch_freeze(const FreezeArgs& a, double* out, int64_t count, cudaStream_t s);
+// dinv[row] = 1 / A[row,row] (Jacobi) or 1 (identity)
+void launch_extract_dinv(const MeshView& m, const double* values, int use_diagonal, double* dinv, cudaStream_t s);
+
+// ---- K5/K6: CG ---------------------------------------------------------------------------------------------------
+struct CgScalars {     // device resident, ping-pong indexed by iteration parity
+  double rz[2];
+  int done[2];
+  int it[2];
+  double pq;           // p.Ap of the current iteration (after reduction / all-reduce)
+  double rz_new;       // r.z after the update
+  double rr;           // r.r after the update
+  double bb;           // b.b
+  double tol2;         // precision^2
+  int max_it;
+  unsigned int ticket_a, ticket_b;  // last-block tickets
+  double red[4];       // all-reduce staging: [0] pq, [1] rz_new, [2] rr
+};
+
+struct CgBuffers {
+  const double* values;  // frozen operator, CSR order
+  const double* dinv;    // owned rows
+  const double* b;       // owned rows
+  double* x;             // owned rows
+  double* r;             // owned rows
+  double* p;             // LOCAL vector (halo | owned | halo)
+  double* q;             // owned rows
+  double* partial;       // >= 3 * max_blocks
+  CgScalars* sc;
+};
+
+int cg_partial_capacity();
+// y = A x over the owned rows; x is a local vector.  If partial != nullptr also writes per-block partial sums of
+// x_owned . y and, through the last-block ticket, their total into sc->pq / sc->red[0].
+void launch_spmv(const MeshView& m, const double* values, const double* x_local, double* y, cudaStream_t s);
+void launch_cg_init(const MeshView& m, const CgBuffers& c, double precision, int max_it, cudaStream_t s);
+void launch_cg_init_finish(const MeshView& m, const CgBuffers& c, cudaStream_t s);
+void launch_cg_spmv(const MeshView& m, const CgBuffers& c, int parity, cudaStream_t s);
+void launch_cg_update(const MeshView& m, const CgBuffers& c, int parity, cudaStream_t s);
+void launch_cg_direction(const MeshView& m, const CgBuffers& c, int parity, cudaStream_t s);
+
+// ---- K7-K10: estimators ---------------------------------------------------------------------------------------
+struct IndicatorArgs {
+  DevCombo a_mu, a_hat, a_bar, a_cut, a_min, a_max;
+  const DevFn* force;
+  int force_order;
+  const double* u_local;       // local vector
+  const double* vertex_mean;   // [n_verts_local], Oswald values (0 on the boundary)
+  const int32_t* cell_verts;   // [n_own*3] local vertex ids
+  double* out;                 // [9][n_own]: nc2,res2,r2,df2,dfstar2,rstar2,amin,resstar2,esv2
+};
+void launch_oswald_vertex_means(const int64_t* vptr, const int32_t* vdof, const uint8_t* vboundary, int32_t n_verts,
+                                const double* u_local, double* vertex_mean, cudaStream_t s);
+void launch_indicators(const MeshView& m, const IndicatorArgs& a, int polorder, cudaStream_t s);
+// deterministic segmented sums: out[seg] = sum_{k in [seg_ptr[seg], seg_ptr[seg+1])} in[k]
+void launch_segment_sums(const double* in, const int64_t* seg_ptr_dev, int n_seg, double* out, cudaStream_t s);
+void launch_segment_min(const double* in, const int64_t* seg_ptr_dev, int n_seg, double* out, cudaStream_t s);
+
+// ---- K11: halo pack --------------------------------------------------------------------------------------------
+void launch_pack(const double* v_local, const int32_t* dof_idx, int64_t n, double* out, cudaStream_t s);
+
+}  // namespace hdd

@@ -1,0 +1,395 @@
+// K1 (pattern), K2 (system matrix parts), K3 (rhs parts), K4 (freeze) for sm_100a.
+//
+// Assembly is owner-computes: one thread per owned cell produces the complete row block of that cell - its
+// volume term, and for every face the en/en block (into the diagonal block) and the en/ne block (off-diagonal)
+// seen with the cell's own outward normal.  The SWIPDG face terms are symmetric under swapping the roles of the
+// two cells (omega^- <-> omega^+, n <-> -n), so this reproduces what the reference's serial walk
+// (system_assembler.walk(), discretizations/swipdg.hh:485) scatters into the rows of T from both sides, without
+// atomics, colouring or a second pass, and bit-reproducibly.  A row block is one contiguous chunk of the CSR
+// value array, written with 256-bit stores for Q1 (one full 32-byte sector per block row).
+#include <cub/device/device_scan.cuh>
+
+#include "kernels.hpp"
+
+namespace hdd {
+
+namespace {
+
+constexpr int kThreads = 128;
+
+inline int grid_for(int64_t n, int threads) { return int((n + threads - 1) / threads); }
+
+template <int NF>
+__device__ __forceinline__ void load_neigh(const int32_t* neigh, int k, int* nb) {
+  if constexpr (NF == 4) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(neigh) + k);
+    nb[0] = v.x; nb[1] = v.y; nb[2] = v.z; nb[3] = v.w;
+  } else {
+#pragma unroll
+    for (int f = 0; f < NF; ++f) nb[f] = __ldg(neigh + size_t(NF) * k + f);
+  }
+}
+
+__global__ void k_count_blocks(MeshView m, int64_t* __restrict__ nblk) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m.n_own) return;
+  const int nf = m.nl;
+  int s = 1;
+  for (int f = 0; f < nf; ++f) s += __ldg(m.neigh + size_t(nf) * k + f) >= 0 ? 1 : 0;
+  nblk[k] = s;
+}
+
+template <int KIND>
+__global__ void k_fill_csr(MeshView m, int64_t* __restrict__ rowptr, int32_t* __restrict__ col) {
+  constexpr int NL = Geo<KIND>::NL, NF = Geo<KIND>::NF;
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= int64_t(m.n_own) * NL) return;
+  const int k = int(t / NL), i = int(t % NL);
+  int nb[NF];
+  load_neigh<NF>(m.neigh, k, nb);
+  const int self = m.own0 + k;
+  const int nblk = block_count<NF>(nb);
+  const int64_t start = m.blk_start[k] * (NL * NL) + int64_t(i) * nblk * NL;
+  rowptr[t] = start;
+  if (t == int64_t(m.n_own) * NL - 1) rowptr[t + 1] = m.blk_start[m.n_own] * (NL * NL);
+  {
+    const int slot = block_slot<NF>(self, nb, self);
+    const int g = __ldg(m.cgid + self);
+#pragma unroll
+    for (int j = 0; j < NL; ++j) col[start + slot * NL + j] = NL * g + j;
+  }
+#pragma unroll
+  for (int f = 0; f < NF; ++f)
+    if (nb[f] >= 0) {
+      const int slot = block_slot<NF>(self, nb, nb[f]);
+      const int g = __ldg(m.cgid + nb[f]);
+#pragma unroll
+      for (int j = 0; j < NL; ++j) col[start + slot * NL + j] = NL * g + j;
+    }
+}
+
+template <int NL>
+__device__ __forceinline__ void store_block(double* __restrict__ row0, int row_stride, int slot, const double* B) {
+#pragma unroll
+  for (int i = 0; i < NL; ++i) {
+    double* dst = row0 + size_t(i) * row_stride + slot * NL;
+    if constexpr (NL == 4) {
+      // one full 32-byte sector per block row (Blackwell 256-bit store, STG.E.ENL2.256)
+      asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(B[i * 4 + 0]), "d"(B[i * 4 + 1]),
+                   "d"(B[i * 4 + 2]), "d"(B[i * 4 + 3])
+                   : "memory");
+    } else {
+#pragma unroll
+      for (int j = 0; j < NL; ++j) dst[j] = B[i * NL + j];
+    }
+  }
+}
+
+// K2.  SURVEY 8a rows a4 (GDT::LocalEvaluation::Elliptic), a5 (SWIPDG::Inner), a6 (SWIPDG::BoundaryLHS).
+template <int KIND>
+__global__ void __launch_bounds__(kThreads)
+    k_assemble_lhs(MeshView m, const DevFn* __restrict__ fnp, ElemRule vol, LineRule fr, double s_in, double s_bnd,
+                   double* __restrict__ vals) {
+  using G = Geo<KIND>;
+  constexpr int NL = G::NL, NF = G::NF;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m.n_own) return;
+  const int c = m.own0 + k;
+  const DevFn& fn = *fnp;
+  G g;
+  g.load(m.cgeo, c);
+  double K[4];
+  load_tensor(m.tensor, c, K);
+  int nb[NF];
+  load_neigh<NF>(m.neigh, k, nb);
+  const int nblk = block_count<NF>(nb);
+  const int rs = nblk * NL;
+  double* row0 = vals + m.blk_start[k] * (NL * NL);
+
+  double D[NL * NL];
+#pragma unroll
+  for (int t = 0; t < NL * NL; ++t) D[t] = 0.0;
+
+  // volume: sum_q w (a K grad phi_j) . grad phi_i, rule of order(a) + 2(p-1)  (no over-integration)
+  for (int q = 0; q < vol.n; ++q) {
+    double phi[NL], gx[NL], gy[NL], x, y;
+    g.basis(vol.x[q], vol.y[q], phi, gx, gy);
+    g.to_global(vol.x[q], vol.y[q], x, y);
+    const double a = fn_eval(fn, c, x, y);
+    const double w = vol.w[q] * g.detj;
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      const double fx = a * (K[0] * gx[j] + K[1] * gy[j]);
+      const double fy = a * (K[2] * gx[j] + K[3] * gy[j]);
+#pragma unroll
+      for (int i = 0; i < NL; ++i) D[i * NL + j] += w * (fx * gx[i] + fy * gy[i]);
+    }
+  }
+
+#pragma unroll 1
+  for (int f = 0; f < NF; ++f) {
+    const FaceGeo e = make_face(g, f);
+    const int n = nb[f];
+    const double dm = e.nx * (K[0] * e.nx + K[1] * e.ny) + e.ny * (K[2] * e.nx + K[3] * e.ny);
+    if (n < 0) {
+      if (m.btype && __ldg(m.btype + size_t(NF) * k + f) != 1) continue;
+      // Dirichlet face: -(A grad phi_j . n) phi_i - phi_j (A grad phi_i . n) + pen phi_j phi_i
+      for (int q = 0; q < fr.n; ++q) {
+        const double x = e.ax + fr.x[q] * (e.bx - e.ax), y = e.ay + fr.x[q] * (e.by - e.ay);
+        double xi, eta, phi[NL], gx[NL], gy[NL], fl[NL];
+        g.to_local(x, y, xi, eta);
+        g.basis(xi, eta, phi, gx, gy);
+        const double a = fn_eval(fn, c, x, y);
+        const double pen = s_bnd * dm * a / e.h;
+        const double w = fr.w[q] * e.h;
+#pragma unroll
+        for (int i = 0; i < NL; ++i)
+          fl[i] = a * ((K[0] * gx[i] + K[1] * gy[i]) * e.nx + (K[2] * gx[i] + K[3] * gy[i]) * e.ny);
+#pragma unroll
+        for (int i = 0; i < NL; ++i)
+#pragma unroll
+          for (int j = 0; j < NL; ++j) D[i * NL + j] += w * (-fl[j] * phi[i] - phi[j] * fl[i] + pen * phi[j] * phi[i]);
+      }
+    } else {
+      G gn;
+      gn.load(m.cgeo, n);
+      double Kn[4];
+      load_tensor(m.tensor, n, Kn);
+      const double dp = e.nx * (Kn[0] * e.nx + Kn[1] * e.ny) + e.ny * (Kn[2] * e.nx + Kn[3] * e.ny);
+      const double gamma = dp * dm / (dp + dm);
+      const double wm = dp / (dp + dm), wp = dm / (dp + dm);
+      double E[NL * NL];
+#pragma unroll
+      for (int t = 0; t < NL * NL; ++t) E[t] = 0.0;
+      for (int q = 0; q < fr.n; ++q) {
+        const double x = e.ax + fr.x[q] * (e.bx - e.ax), y = e.ay + fr.x[q] * (e.by - e.ay);
+        double xi, eta, phm[NL], php[NL], gx[NL], gy[NL], fm[NL], fp[NL];
+        g.to_local(x, y, xi, eta);
+        g.basis(xi, eta, phm, gx, gy);
+        const double am = fn_eval(fn, c, x, y), ap = fn_eval(fn, n, x, y);
+#pragma unroll
+        for (int i = 0; i < NL; ++i)
+          fm[i] = am * ((K[0] * gx[i] + K[1] * gy[i]) * e.nx + (K[2] * gx[i] + K[3] * gy[i]) * e.ny);
+        gn.to_local(x, y, xi, eta);
+        gn.basis(xi, eta, php, gx, gy);
+#pragma unroll
+        for (int i = 0; i < NL; ++i)
+          fp[i] = ap * ((Kn[0] * gx[i] + Kn[1] * gy[i]) * e.nx + (Kn[2] * gx[i] + Kn[3] * gy[i]) * e.ny);
+        const double pen = s_in * gamma * 0.5 * (am + ap) / e.h;
+        const double w = fr.w[q] * e.h;
+#pragma unroll
+        for (int i = 0; i < NL; ++i)
+#pragma unroll
+          for (int j = 0; j < NL; ++j) {
+            D[i * NL + j] += w * (-wm * fm[j] * phm[i] - wm * phm[j] * fm[i] + pen * phm[j] * phm[i]);  // en/en
+            E[i * NL + j] += w * (-wp * fp[j] * phm[i] + wm * php[j] * fm[i] - pen * php[j] * phm[i]);  // en/ne
+          }
+      }
+      store_block<NL>(row0, rs, block_slot<NF>(c, nb, n), E);
+    }
+  }
+  store_block<NL>(row0, rs, block_slot<NF>(c, nb, c), D);
+}
+
+// K3a.  Functionals::L2Volume(force) (discretizations/swipdg.hh:253-271): rule of order(f) + p.
+template <int KIND>
+__global__ void __launch_bounds__(kThreads)
+    k_rhs_volume(MeshView m, const DevFn* __restrict__ fnp, ElemRule vol, double* __restrict__ b) {
+  using G = Geo<KIND>;
+  constexpr int NL = G::NL;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m.n_own) return;
+  const int c = m.own0 + k;
+  G g;
+  g.load(m.cgeo, c);
+  double acc[NL];
+#pragma unroll
+  for (int i = 0; i < NL; ++i) acc[i] = 0.0;
+  for (int q = 0; q < vol.n; ++q) {
+    double phi[NL], gx[NL], gy[NL], x, y;
+    g.basis(vol.x[q], vol.y[q], phi, gx, gy);
+    g.to_global(vol.x[q], vol.y[q], x, y);
+    const double fv = fn_eval(*fnp, c, x, y) * vol.w[q] * g.detj;
+#pragma unroll
+    for (int i = 0; i < NL; ++i) acc[i] += fv * phi[i];
+  }
+#pragma unroll
+  for (int i = 0; i < NL; ++i) b[size_t(NL) * k + i] += acc[i];
+}
+
+// K3b.  Functionals::DirichletBoundarySWIPDG (discretizations/swipdg.hh:273-332; SWIPDG::BoundaryRHS):
+// b_i += int_e -g (A grad phi_i . n) + pen g phi_i
+template <int KIND>
+__global__ void __launch_bounds__(kThreads)
+    k_rhs_dirichlet(MeshView m, const DevFn* __restrict__ facp, const DevFn* __restrict__ dirp, LineRule fr,
+                    double s_bnd, double* __restrict__ b) {
+  using G = Geo<KIND>;
+  constexpr int NL = G::NL, NF = G::NF;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m.n_own) return;
+  const int c = m.own0 + k;
+  int nb[NF];
+  load_neigh<NF>(m.neigh, k, nb);
+  bool any = false;
+#pragma unroll
+  for (int f = 0; f < NF; ++f) any |= nb[f] < 0;
+  if (!any) return;
+  G g;
+  g.load(m.cgeo, c);
+  double K[4];
+  load_tensor(m.tensor, c, K);
+  double acc[NL];
+#pragma unroll
+  for (int i = 0; i < NL; ++i) acc[i] = 0.0;
+  for (int f = 0; f < NF; ++f) {
+    if (nb[f] >= 0) continue;
+    if (m.btype && __ldg(m.btype + size_t(NF) * k + f) != 1) continue;
+    const FaceGeo e = make_face(g, f);
+    const double dm = e.nx * (K[0] * e.nx + K[1] * e.ny) + e.ny * (K[2] * e.nx + K[3] * e.ny);
+    for (int q = 0; q < fr.n; ++q) {
+      const double x = e.ax + fr.x[q] * (e.bx - e.ax), y = e.ay + fr.x[q] * (e.by - e.ay);
+      double xi, eta, phi[NL], gx[NL], gy[NL];
+      g.to_local(x, y, xi, eta);
+      g.basis(xi, eta, phi, gx, gy);
+      const double a = fn_eval(*facp, c, x, y), gd = fn_eval(*dirp, c, x, y);
+      const double pen = s_bnd * dm * a / e.h;
+      const double w = fr.w[q] * e.h;
+#pragma unroll
+      for (int i = 0; i < NL; ++i) {
+        const double fl = a * ((K[0] * gx[i] + K[1] * gy[i]) * e.nx + (K[2] * gx[i] + K[3] * gy[i]) * e.ny);
+        acc[i] += w * (-gd * fl + pen * gd * phi[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NL; ++i) b[size_t(NL) * k + i] += acc[i];
+}
+
+// K4.  out = sum_k theta_k part_k, 256-bit streaming loads/stores.
+__global__ void __launch_bounds__(256) k_freeze(FreezeArgs a, double* __restrict__ out, int64_t count) {
+  const int64_t n4 = count / 4;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    for (int k = 0; k < a.n; ++k) {
+      double v0, v1, v2, v3;
+      asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                   : "=d"(v0), "=d"(v1), "=d"(v2), "=d"(v3)
+                   : "l"(a.part[k] + 4 * i));
+      s0 += a.theta[k] * v0; s1 += a.theta[k] * v1; s2 += a.theta[k] * v2; s3 += a.theta[k] * v3;
+    }
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(out + 4 * i), "d"(s0), "d"(s1), "d"(s2), "d"(s3) : "memory");
+  }
+  for (int64_t i = 4 * n4 + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
+    double s = 0;
+    for (int k = 0; k < a.n; ++k) s += a.theta[k] * a.part[k][i];
+    out[i] = s;
+  }
+}
+
+template <int KIND>
+__global__ void k_extract_dinv(MeshView m, const double* __restrict__ values, int use_diagonal,
+                               double* __restrict__ dinv) {
+  constexpr int NL = Geo<KIND>::NL, NF = Geo<KIND>::NF;
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= int64_t(m.n_own) * NL) return;
+  if (!use_diagonal) { dinv[t] = 1.0; return; }
+  const int k = int(t / NL), i = int(t % NL);
+  int nb[NF];
+  load_neigh<NF>(m.neigh, k, nb);
+  const int self = m.own0 + k;
+  const int nblk = block_count<NF>(nb);
+  const int slot = block_slot<NF>(self, nb, self);
+  const double d = values[m.blk_start[k] * (NL * NL) + int64_t(i) * nblk * NL + slot * NL + i];
+  dinv[t] = 1.0 / d;
+}
+
+}  // namespace
+
+void launch_count_blocks(const MeshView& m, int64_t* nblk, cudaStream_t s) {
+  if (m.n_own == 0) return;
+  k_count_blocks<<<grid_for(m.n_own, 256), 256, 0, s>>>(m, nblk);
+  count_launch();
+  HDD_CUDA(cudaGetLastError());
+}
+
+void exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, cudaStream_t s) {
+  size_t bytes = 0;
+  HDD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, int(n), s));
+  void* tmp = nullptr;
+  HDD_CUDA(cudaMallocAsync(&tmp, bytes, s));
+  HDD_CUDA(cub::DeviceScan::ExclusiveSum(tmp, bytes, in, out, int(n), s));
+  HDD_CUDA(cudaFreeAsync(tmp, s));
+  count_launch(2);
+}
+
+void launch_fill_csr(const MeshView& m, int64_t* rowptr, int32_t* col, cudaStream_t s) {
+  if (m.n_own == 0) return;
+  const int64_t rows = int64_t(m.n_own) * m.nl;
+  if (m.kind == HDD_SIMPLEX2D)
+    k_fill_csr<HDD_SIMPLEX2D><<<grid_for(rows, 256), 256, 0, s>>>(m, rowptr, col);
+  else
+    k_fill_csr<HDD_CUBE2D><<<grid_for(rows, 256), 256, 0, s>>>(m, rowptr, col);
+  count_launch();
+  HDD_CUDA(cudaGetLastError());
+}
+
+void launch_assemble_lhs(const MeshView& m, const DevFn* factor_dev, int factor_order, int polorder, double* values,
+                         cudaStream_t s) {
+  if (m.n_own == 0) return;
+  const ElemRule vol = element_rule(m.kind, factor_order + 2 * (polorder - 1));
+  const LineRule fr = line_rule(factor_order + 2 * polorder);
+  const double si = sigma_inner(polorder), sb = sigma_boundary(polorder);
+  if (m.kind == HDD_SIMPLEX2D)
+    k_assemble_lhs<HDD_SIMPLEX2D><<<grid_for(m.n_own, kThreads), kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+  else
+    k_assemble_lhs<HDD_CUBE2D><<<grid_for(m.n_own, kThreads), kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+  count_launch();
+  HDD_CUDA(cudaGetLastError());
+}
+
+void launch_rhs_volume(const MeshView& m, const DevFn* force_dev, int force_order, int polorder, double* b,
+                       cudaStream_t s) {
+  if (m.n_own == 0) return;
+  const ElemRule vol = element_rule(m.kind, force_order + polorder);
+  if (m.kind == HDD_SIMPLEX2D)
+    k_rhs_volume<HDD_SIMPLEX2D><<<grid_for(m.n_own, kThreads), kThreads, 0, s>>>(m, force_dev, vol, b);
+  else
+    k_rhs_volume<HDD_CUBE2D><<<grid_for(m.n_own, kThreads), kThreads, 0, s>>>(m, force_dev, vol, b);
+  count_launch();
+  HDD_CUDA(cudaGetLastError());
+}
+
+void launch_rhs_dirichlet(const MeshView& m, const DevFn* factor_dev, int factor_order, const DevFn* dirichlet_dev,
+                          int dirichlet_order, int polorder, double* b, cudaStream_t s) {
+  if (m.n_own == 0) return;
+  const LineRule fr = line_rule(factor_order + dirichlet_order + 2 * polorder);
+  const double sb = sigma_boundary(polorder);
+  if (m.kind == HDD_SIMPLEX2D)
+    k_rhs_dirichlet<HDD_SIMPLEX2D><<<grid_for(m.n_own, kThreads), kThreads, 0, s>>>(m, factor_dev, dirichlet_dev, fr, sb, b);
+  else
+    k_rhs_dirichlet<HDD_CUBE2D><<<grid_for(m.n_own, kThreads), kThreads, 0, s>>>(m, factor_dev, dirichlet_dev, fr, sb, b);
+  count_launch();
+  HDD_CUDA(cudaGetLastError());
+}
+
+void launch_freeze(const FreezeArgs& a, double* out, int64_t count, cudaStream_t s) {
+  if (count == 0) return;
+  const int blocks = int(std::min<int64_t>((count / 4 + 255) / 256 + 1, 148 * 16));
+  k_freeze<<<blocks, 256, 0, s>>>(a, out, count);
+  count_launch();
+  HDD_CUDA(cudaGetLastError());
+}
+
+void launch_extract_dinv(const MeshView& m, const double* values, int use_diagonal, double* dinv, cudaStream_t s) {
+  if (m.n_own == 0) return;
+  const int64_t rows = int64_t(m.n_own) * m.nl;
+  if (m.kind == HDD_SIMPLEX2D)
+    k_extract_dinv<HDD_SIMPLEX2D><<<grid_for(rows, 256), 256, 0, s>>>(m, values, use_diagonal, dinv);
+  else
+    k_extract_dinv<HDD_CUBE2D><<<grid_for(rows, 256), 256, 0, s>>>(m, values, use_diagonal, dinv);
+  count_launch();
+  HDD_CUDA(cudaGetLastError());
+}
+
+}  // namespace hdd

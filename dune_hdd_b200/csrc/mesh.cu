@@ -1,0 +1,496 @@
+// hdd_mesh: localisation of the host grid (owned cells + vertex-adjacent halo, sorted by global id), upload,
+// block offsets (K1 part 1), vertex incidence for the Oswald pass, halo-exchange plan and NCCL plumbing.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <unordered_map>
+
+#include "handles.hpp"
+
+namespace hdd {
+
+std::atomic<int64_t> g_kernel_launches{0};
+static thread_local std::string t_last_error;
+void set_last_error(const std::string& msg) { t_last_error = msg; }
+
+// ---- NCCL, resolved at run time ----------------------------------------------------------------------------
+enum { F_UID, F_INIT, F_DESTROY, F_ALLREDUCE, F_GSTART, F_GEND, F_SEND, F_RECV, F_ERRSTR };
+
+Nccl::Nccl() {
+  handle_ = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!handle_) return;
+  const char* names[] = {"ncclGetUniqueId", "ncclCommInitRank", "ncclCommDestroy", "ncclAllReduce", "ncclGroupStart",
+                         "ncclGroupEnd",    "ncclSend",         "ncclRecv",        "ncclGetErrorString"};
+  for (int k = 0; k < 9; ++k) {
+    fn_[k] = dlsym(handle_, names[k]);
+    if (!fn_[k]) { handle_ = nullptr; return; }
+  }
+}
+Nccl& Nccl::get() {
+  static Nccl n;
+  return n;
+}
+void Nccl::check(int result, const char* what) {
+  if (result != 0) {
+    auto errstr = reinterpret_cast<const char* (*)(ncclResult_t)>(fn_[F_ERRSTR]);
+    HDD_THROW(HDD_ERR_DEVICE, "NCCL error in " << what << ": " << errstr(ncclResult_t(result)));
+  }
+}
+void Nccl::unique_id(void* id128) {
+  if (!available()) HDD_THROW(HDD_ERR_DEVICE, "libnccl.so.2 not found");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  check(reinterpret_cast<ncclResult_t (*)(ncclUniqueId*)>(fn_[F_UID])(static_cast<ncclUniqueId*>(id128)), "ncclGetUniqueId");
+}
+ncclComm* Nccl::init_rank(const void* id128, int rank, int world) {
+  if (!available()) HDD_THROW(HDD_ERR_DEVICE, "libnccl.so.2 not found");
+  ncclComm_t c = nullptr;
+  ncclUniqueId id;
+  std::memcpy(&id, id128, sizeof(id));
+  check(reinterpret_cast<ncclResult_t (*)(ncclComm_t*, int, ncclUniqueId, int)>(fn_[F_INIT])(&c, world, id, rank),
+        "ncclCommInitRank");
+  return c;
+}
+void Nccl::destroy(ncclComm* c) {
+  if (c && available()) reinterpret_cast<ncclResult_t (*)(ncclComm_t)>(fn_[F_DESTROY])(c);
+}
+void Nccl::all_reduce_sum(double* buf, size_t count, ncclComm* c, cudaStream_t s) {
+  check(reinterpret_cast<ncclResult_t (*)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t)>(
+            fn_[F_ALLREDUCE])(buf, buf, count, ncclDouble, ncclSum, c, s),
+        "ncclAllReduce");
+}
+void Nccl::all_reduce_min(double* buf, size_t count, ncclComm* c, cudaStream_t s) {
+  check(reinterpret_cast<ncclResult_t (*)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t)>(
+            fn_[F_ALLREDUCE])(buf, buf, count, ncclDouble, ncclMin, c, s),
+        "ncclAllReduce");
+}
+void Nccl::group_start() { check(reinterpret_cast<ncclResult_t (*)()>(fn_[F_GSTART])(), "ncclGroupStart"); }
+void Nccl::group_end() { check(reinterpret_cast<ncclResult_t (*)()>(fn_[F_GEND])(), "ncclGroupEnd"); }
+void Nccl::send(const double* buf, size_t count, int peer, ncclComm* c, cudaStream_t s) {
+  check(reinterpret_cast<ncclResult_t (*)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)>(fn_[F_SEND])(
+            buf, count, ncclDouble, peer, c, s),
+        "ncclSend");
+}
+void Nccl::recv(double* buf, size_t count, int peer, ncclComm* c, cudaStream_t s) {
+  check(reinterpret_cast<ncclResult_t (*)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)>(fn_[F_RECV])(
+            buf, count, ncclDouble, peer, c, s),
+        "ncclRecv");
+}
+
+namespace {
+
+const int kFaceVertsSimplex[3][2] = {{0, 1}, {0, 2}, {1, 2}};
+const int kFaceVertsCube[4][2] = {{0, 2}, {1, 3}, {0, 1}, {2, 3}};
+
+// exact diameter of a point set: convex hull (monotone chain) + all pairs on the hull.
+// Equals the all-pairs vertex loop of LocalResidualOS2014::finalize (estimators/block-swipdg.hh:294-303).
+double point_set_diameter(std::vector<std::pair<double, double>>& pts) {
+  std::sort(pts.begin(), pts.end());
+  pts.erase(std::unique(pts.begin(), pts.end()), pts.end());
+  const size_t n = pts.size();
+  if (n < 2) return 0.0;
+  std::vector<std::pair<double, double>> h(2 * n);
+  size_t k = 0;
+  auto cross = [](const std::pair<double, double>& o, const std::pair<double, double>& a,
+                  const std::pair<double, double>& b) {
+    return (a.first - o.first) * (b.second - o.second) - (a.second - o.second) * (b.first - o.first);
+  };
+  for (size_t i = 0; i < n; ++i) {
+    while (k >= 2 && cross(h[k - 2], h[k - 1], pts[i]) <= 0) --k;
+    h[k++] = pts[i];
+  }
+  for (size_t i = n - 1, t = k + 1; i > 0; --i) {
+    while (k >= t && cross(h[k - 2], h[k - 1], pts[i - 1]) <= 0) --k;
+    h[k++] = pts[i - 1];
+  }
+  h.resize(k > 1 ? k - 1 : k);
+  double d = 0.0;
+  for (size_t i = 0; i < h.size(); ++i)
+    for (size_t j = i + 1; j < h.size(); ++j)
+      d = std::max(d, std::hypot(h[i].first - h[j].first, h[i].second - h[j].second));
+  return d;
+}
+
+}  // namespace
+}  // namespace hdd
+
+using namespace hdd;
+
+hdd_mesh::~hdd_mesh() {
+  if (comm) Nccl::get().destroy(comm);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+void hdd_mesh::halo_exchange(double* v_local) {
+  if (world == 1 || peers.empty()) return;
+  int64_t n_send = 0;
+  for (const auto& p : peers) n_send += p.send_count;
+  launch_pack(v_local, send_idx.p, n_send, send_buf.p, stream);
+  Nccl& nc = Nccl::get();
+  nc.group_start();
+  for (const auto& p : peers) {
+    if (p.send_count) nc.send(send_buf.p + p.send_offset, size_t(p.send_count), p.rank, comm, stream);
+    if (p.recv_count) nc.recv(v_local + p.recv_offset, size_t(p.recv_count), p.rank, comm, stream);
+  }
+  nc.group_end();
+}
+
+extern "C" {
+
+const char* hdd_last_error(void) { return t_last_error.c_str(); }
+const char* hdd_version(void) { return "hdd_b200 0.1 (sm_100a)"; }
+int64_t hdd_kernel_launches(void) { return g_kernel_launches.load(); }
+
+int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy, const int32_t* cell_verts,
+                    const int32_t* cell_neigh, const int32_t* cell_subdomain, const uint8_t* boundary_type,
+                    int64_t cell_begin, int64_t cell_end, int device, hdd_mesh** out) {
+  return guarded([&] {
+    if (!out) HDD_THROW(HDD_ERR_WRONG_INPUT, "out is NULL");
+    *out = nullptr;
+    if (kind != HDD_SIMPLEX2D && kind != HDD_CUBE2D) HDD_THROW(HDD_ERR_WRONG_INPUT, "unknown element kind " << kind);
+    if (n_cells < 1 || n_verts < 1 || !xy || !cell_verts || !cell_neigh)
+      HDD_THROW(HDD_ERR_WRONG_INPUT, "empty grid or NULL array");
+    if (n_cells > INT32_MAX / 8) HDD_THROW(HDD_ERR_WRONG_INPUT, "too many cells for 32-bit DoF indices");
+    if (cell_begin < 0 || cell_end > n_cells || cell_begin > cell_end)
+      HDD_THROW(HDD_ERR_WRONG_INPUT, "bad owned cell range [" << cell_begin << ", " << cell_end << ")");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+      HDD_THROW(HDD_ERR_DEVICE, "no CUDA device available (libhdd_b200 has no CPU fallback)");
+    if (device < 0 || device >= n_dev) HDD_THROW(HDD_ERR_DEVICE, "CUDA device " << device << " out of range");
+
+    std::unique_ptr<hdd_mesh> m(new hdd_mesh);
+    m->kind = kind;
+    m->nl = m->nf = (kind == HDD_SIMPLEX2D ? 3 : 4);
+    m->device = device;
+    m->n_global = n_cells;
+    m->cell_begin = cell_begin;
+    m->cell_end = cell_end;
+    m->set_device();
+    HDD_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    const int nl = m->nl, nf = m->nf;
+    const bool whole = (cell_begin == 0 && cell_end == n_cells);
+    const int64_t n_own = cell_end - cell_begin;
+
+    // ---- halo: every non-owned cell sharing a vertex with an owned cell (superset of the face neighbours the
+    // SpMV needs; the Oswald interpolation needs all cells around a vertex)
+    std::vector<int32_t> halo_lo, halo_hi;
+    if (!whole) {
+      std::vector<uint8_t> vmark(size_t(n_verts), 0);
+      for (int64_t c = cell_begin; c < cell_end; ++c)
+        for (int i = 0; i < nl; ++i) vmark[size_t(cell_verts[c * nl + i])] = 1;
+      for (int64_t c = 0; c < n_cells; ++c) {
+        if (c >= cell_begin && c < cell_end) continue;
+        bool touch = false;
+        for (int i = 0; i < nl; ++i) touch |= vmark[size_t(cell_verts[c * nl + i])] != 0;
+        if (touch) (c < cell_begin ? halo_lo : halo_hi).push_back(int32_t(c));
+      }
+    }
+    m->own0 = int32_t(halo_lo.size());
+    m->n_own = int32_t(n_own);
+    m->n_loc = int32_t(halo_lo.size() + n_own + halo_hi.size());
+    m->cgid.resize(size_t(m->n_loc));
+    {
+      size_t k = 0;
+      for (int32_t c : halo_lo) m->cgid[k++] = c;
+      for (int64_t c = cell_begin; c < cell_end; ++c) m->cgid[k++] = int32_t(c);
+      for (int32_t c : halo_hi) m->cgid[k++] = c;
+    }
+    auto to_local = [&](int32_t g) -> int32_t {
+      if (g < 0) return -1;
+      if (g >= cell_begin && g < cell_end) return int32_t(m->own0 + (g - cell_begin));
+      const std::vector<int32_t>& h = g < cell_begin ? halo_lo : halo_hi;
+      auto it = std::lower_bound(h.begin(), h.end(), g);
+      if (it == h.end() || *it != g) HDD_THROW(HDD_ERR_INTERNAL, "neighbour " << g << " missing from the halo");
+      return int32_t((g < cell_begin ? 0 : m->own0 + n_own) + (it - h.begin()));
+    };
+
+    // ---- geometry of all local cells, neighbours / boundary types of the owned ones
+    const int ngeo = kind == HDD_SIMPLEX2D ? 6 : 4;
+    std::vector<double> cgeo(size_t(m->n_loc) * ngeo);
+    for (int32_t lc = 0; lc < m->n_loc; ++lc) {
+      const int64_t g = m->cgid[size_t(lc)];
+      if (kind == HDD_SIMPLEX2D) {
+        for (int i = 0; i < 3; ++i) {
+          const int32_t v = cell_verts[g * 3 + i];
+          if (v < 0 || v >= n_verts) HDD_THROW(HDD_ERR_INDEX_OUT_OF_RANGE, "vertex id " << v << " of cell " << g);
+          cgeo[size_t(lc) * 6 + 2 * i] = xy[2 * v];
+          cgeo[size_t(lc) * 6 + 2 * i + 1] = xy[2 * v + 1];
+        }
+      } else {
+        const int32_t v0 = cell_verts[g * 4 + 0], v1 = cell_verts[g * 4 + 1], v2 = cell_verts[g * 4 + 2],
+                      v3 = cell_verts[g * 4 + 3];
+        for (int32_t v : {v0, v1, v2, v3})
+          if (v < 0 || v >= n_verts) HDD_THROW(HDD_ERR_INDEX_OUT_OF_RANGE, "vertex id " << v << " of cell " << g);
+        // axis-parallel check
+        if (xy[2 * v0] != xy[2 * v2] || xy[2 * v1] != xy[2 * v3] || xy[2 * v0 + 1] != xy[2 * v1 + 1] ||
+            xy[2 * v2 + 1] != xy[2 * v3 + 1])
+          HDD_THROW(HDD_ERR_NOT_IMPLEMENTED, "HDD_CUBE2D cells must be axis-parallel rectangles (cell " << g << ")");
+        cgeo[size_t(lc) * 4 + 0] = xy[2 * v0];
+        cgeo[size_t(lc) * 4 + 1] = xy[2 * v0 + 1];
+        cgeo[size_t(lc) * 4 + 2] = xy[2 * v3];
+        cgeo[size_t(lc) * 4 + 3] = xy[2 * v3 + 1];
+      }
+    }
+    m->h_neigh.resize(size_t(n_own) * nf);
+    for (int64_t k = 0; k < n_own; ++k)
+      for (int f = 0; f < nf; ++f) {
+        const int32_t g = cell_neigh[(cell_begin + k) * nf + f];
+        if (g >= n_cells) HDD_THROW(HDD_ERR_INDEX_OUT_OF_RANGE, "neighbour id " << g);
+        m->h_neigh[size_t(k) * nf + f] = to_local(g);
+      }
+    m->cgeo.upload(cgeo.data(), cgeo.size(), m->stream);
+    m->neigh.upload(m->h_neigh.data(), m->h_neigh.size(), m->stream);
+    m->d_cgid.upload(m->cgid.data(), m->cgid.size(), m->stream);
+    if (boundary_type) {
+      m->has_btype = true;
+      m->btype.upload(boundary_type + cell_begin * nf, size_t(n_own) * nf, m->stream);
+    }
+
+    // ---- local vertices + incidence (vertex -> local DoFs), boundary flags
+    std::vector<int32_t> cvl(size_t(m->n_loc) * nl);
+    {
+      std::unordered_map<int32_t, int32_t> vmap;
+      std::vector<int32_t> dense;
+      if (whole) dense.assign(size_t(n_verts), -1);
+      int32_t nvl = 0;
+      for (int32_t lc = 0; lc < m->n_loc; ++lc)
+        for (int i = 0; i < nl; ++i) {
+          const int32_t v = cell_verts[int64_t(m->cgid[size_t(lc)]) * nl + i];
+          int32_t id;
+          if (whole) {
+            if (dense[size_t(v)] < 0) dense[size_t(v)] = nvl++;
+            id = dense[size_t(v)];
+          } else {
+            auto it = vmap.find(v);
+            if (it == vmap.end()) it = vmap.emplace(v, nvl++).first;
+            id = it->second;
+          }
+          cvl[size_t(lc) * nl + i] = id;
+        }
+      m->n_verts_loc = nvl;
+    }
+    {
+      const int32_t nvl = m->n_verts_loc;
+      std::vector<int64_t> vptr(size_t(nvl) + 1, 0);
+      for (int32_t v : cvl) ++vptr[size_t(v) + 1];
+      for (int32_t v = 0; v < nvl; ++v) vptr[size_t(v) + 1] += vptr[size_t(v)];
+      std::vector<int32_t> vdof(cvl.size());
+      std::vector<int64_t> fill(vptr.begin(), vptr.end() - 1);
+      for (int32_t lc = 0; lc < m->n_loc; ++lc)
+        for (int i = 0; i < nl; ++i) vdof[size_t(fill[size_t(cvl[size_t(lc) * nl + i])]++)] = lc * nl + i;
+      std::vector<uint8_t> vb(size_t(nvl), 0);
+      for (int32_t lc = 0; lc < m->n_loc; ++lc) {
+        const int64_t g = m->cgid[size_t(lc)];
+        for (int f = 0; f < nf; ++f)
+          if (cell_neigh[g * nf + f] < 0) {
+            const int* fv = kind == HDD_SIMPLEX2D ? kFaceVertsSimplex[f] : kFaceVertsCube[f];
+            vb[size_t(cvl[size_t(lc) * nl + fv[0]])] = 1;
+            vb[size_t(cvl[size_t(lc) * nl + fv[1]])] = 1;
+          }
+      }
+      m->vptr.upload(vptr.data(), vptr.size(), m->stream);
+      m->vdof.upload(vdof.data(), vdof.size(), m->stream);
+      m->vboundary.upload(vb.data(), vb.size(), m->stream);
+      m->cell_verts.upload(cvl.data() + size_t(m->own0) * nl, size_t(n_own) * nl, m->stream);
+    }
+    m->h_cell_verts_loc.swap(cvl);
+
+    // ---- subdomains (grid::Multiscale view): contiguous, subdomain-major cell ranges
+    m->h_sub.assign(size_t(m->n_loc), 0);
+    if (cell_subdomain) {
+      int32_t prev = 0, mx = 0;
+      for (int64_t c = 0; c < n_cells; ++c) {
+        const int32_t s = cell_subdomain[c];
+        if (s < prev) HDD_THROW(HDD_ERR_WRONG_INPUT, "cells must be numbered subdomain-major (cell " << c << ")");
+        if (s > prev + 1) HDD_THROW(HDD_ERR_WRONG_INPUT, "empty subdomain " << prev + 1);
+        prev = s;
+        mx = std::max(mx, s);
+      }
+      if (cell_subdomain[0] != 0) HDD_THROW(HDD_ERR_WRONG_INPUT, "subdomain numbering must start at 0");
+      m->n_subdomains = mx + 1;
+      m->sub_cell_offsets.assign(size_t(m->n_subdomains) + 1, 0);
+      for (int64_t c = 0; c < n_cells; ++c) ++m->sub_cell_offsets[size_t(cell_subdomain[c]) + 1];
+      for (int s = 0; s < m->n_subdomains; ++s) m->sub_cell_offsets[size_t(s) + 1] += m->sub_cell_offsets[size_t(s)];
+      for (int32_t lc = 0; lc < m->n_loc; ++lc) m->h_sub[size_t(lc)] = cell_subdomain[m->cgid[size_t(lc)]];
+      m->sub_neighbours.assign(size_t(m->n_subdomains), {});
+      for (int64_t c = 0; c < n_cells; ++c)
+        for (int f = 0; f < nf; ++f) {
+          const int32_t g = cell_neigh[c * nf + f];
+          if (g >= 0 && cell_subdomain[g] != cell_subdomain[c])
+            m->sub_neighbours[size_t(cell_subdomain[c])].push_back(cell_subdomain[g]);
+        }
+      for (auto& v : m->sub_neighbours) {
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end()), v.end());
+      }
+    } else {
+      m->n_subdomains = 1;
+      m->sub_cell_offsets = {0, n_cells};
+      m->sub_neighbours.assign(1, {});
+    }
+    m->sub_dof_offsets.resize(m->sub_cell_offsets.size());
+    for (size_t s = 0; s < m->sub_cell_offsets.size(); ++s) m->sub_dof_offsets[s] = nl * m->sub_cell_offsets[s];
+    // owned subdomains: the owned range must consist of whole subdomains
+    m->sub_first = int(std::lower_bound(m->sub_cell_offsets.begin(), m->sub_cell_offsets.end(), cell_begin) -
+                       m->sub_cell_offsets.begin());
+    m->sub_last = int(std::lower_bound(m->sub_cell_offsets.begin(), m->sub_cell_offsets.end(), cell_end) -
+                      m->sub_cell_offsets.begin());
+    if (n_own > 0 && (m->sub_cell_offsets[size_t(m->sub_first)] != cell_begin ||
+                      m->sub_cell_offsets[size_t(m->sub_last)] != cell_end))
+      HDD_THROW(HDD_ERR_WRONG_INPUT, "the owned cell range must consist of whole subdomains");
+    if (n_own == 0) m->sub_last = m->sub_first;
+    m->sub_diameter.assign(size_t(m->n_subdomains), 0.0);
+    if (m->n_subdomains > 1 || kind == HDD_SIMPLEX2D) {
+      for (int s = m->sub_first; s < m->sub_last; ++s) {
+        std::vector<std::pair<double, double>> pts;
+        // only boundary-of-subdomain vertices matter, but collecting all is O(n) and simple
+        for (int64_t c = m->sub_cell_offsets[size_t(s)]; c < m->sub_cell_offsets[size_t(s) + 1]; ++c)
+          for (int i = 0; i < nl; ++i) {
+            const int32_t v = cell_verts[c * nl + i];
+            pts.emplace_back(xy[2 * v], xy[2 * v + 1]);
+          }
+        m->sub_diameter[size_t(s)] = point_set_diameter(pts);
+      }
+    }
+    // chunked segments of the owned cells for deterministic two-level sums
+    {
+      const int64_t chunk = 8192;
+      m->seg_ptr.clear();
+      m->seg_sub.clear();
+      for (int s = m->sub_first; s < m->sub_last; ++s) {
+        const int64_t b = m->sub_cell_offsets[size_t(s)] - cell_begin, e = m->sub_cell_offsets[size_t(s) + 1] - cell_begin;
+        for (int64_t k = b; k < e; k += chunk) {
+          m->seg_ptr.push_back(k);
+          m->seg_sub.push_back(s);
+        }
+      }
+      m->seg_ptr.push_back(n_own);
+      m->d_seg_ptr.upload(m->seg_ptr.data(), m->seg_ptr.size(), m->stream);
+    }
+
+    // ---- K1 part 1: number of blocks per owned cell and their exclusive prefix sum
+    {
+      DevBuf<int64_t> nblk;
+      nblk.alloc(size_t(n_own) + 1);
+      nblk.zero(m->stream);
+      m->blk_start.alloc(size_t(n_own) + 1);
+      const MeshView v = m->view(nullptr);
+      launch_count_blocks(v, nblk.p, m->stream);
+      exclusive_scan_i64(nblk.p, m->blk_start.p, n_own + 1, m->stream);  // nblk[n_own] = 0 => total in blk_start[n_own]
+      HDD_CUDA(cudaMemcpyAsync(&m->n_blocks, m->blk_start.p + n_own, sizeof(int64_t), cudaMemcpyDeviceToHost, m->stream));
+      HDD_CUDA(cudaStreamSynchronize(m->stream));
+    }
+    HDD_CUDA(cudaStreamSynchronize(m->stream));
+    *out = m.release();
+  });
+}
+
+int hdd_mesh_destroy(hdd_mesh* mesh) {
+  return guarded([&] {
+    if (mesh) {
+      cudaSetDevice(mesh->device);
+      delete mesh;
+    }
+  });
+}
+
+int hdd_mesh_num_cells(const hdd_mesh* mesh, int64_t* n_global, int64_t* n_owned, int64_t* n_halo) {
+  return guarded([&] {
+    if (!mesh) HDD_THROW(HDD_ERR_WRONG_INPUT, "mesh is NULL");
+    if (n_global) *n_global = mesh->n_global;
+    if (n_owned) *n_owned = mesh->n_own;
+    if (n_halo) *n_halo = mesh->n_loc - mesh->n_own;
+  });
+}
+
+int hdd_comm_unique_id(void* id128) {
+  return guarded([&] { Nccl::get().unique_id(id128); });
+}
+
+int hdd_comm_init(hdd_mesh* m, const void* id128, int rank, int world_size) {
+  return guarded([&] {
+    if (!m) HDD_THROW(HDD_ERR_WRONG_INPUT, "mesh is NULL");
+    if (world_size < 1 || rank < 0 || rank >= world_size) HDD_THROW(HDD_ERR_WRONG_INPUT, "bad rank / world size");
+    m->set_device();
+    m->rank = rank;
+    m->world = world_size;
+    if (world_size == 1) return;
+    Nccl& nc = Nccl::get();
+    m->comm = nc.init_rank(id128, rank, world_size);
+    // every rank learns every rank's owned range (2 doubles per rank through one all-reduce)
+    DevBuf<double> ranges;
+    ranges.alloc(size_t(world_size) + 1);
+    std::vector<double> h(size_t(world_size) + 1, 0.0);
+    h[size_t(rank)] = double(m->cell_begin);
+    if (rank == world_size - 1) h[size_t(world_size)] = double(m->cell_end);
+    ranges.upload(h.data(), h.size(), m->stream);
+    nc.all_reduce_sum(ranges.p, h.size(), m->comm, m->stream);
+    HDD_CUDA(cudaMemcpyAsync(h.data(), ranges.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    HDD_CUDA(cudaStreamSynchronize(m->stream));
+    m->rank_cell_offsets.resize(h.size());
+    for (size_t r = 0; r < h.size(); ++r) m->rank_cell_offsets[r] = int64_t(h[r]);
+    if (m->rank_cell_offsets[size_t(rank) + 1] != m->cell_end || m->rank_cell_offsets[0] != 0 ||
+        m->rank_cell_offsets[size_t(world_size)] != m->n_global)
+      HDD_THROW(HDD_ERR_WRONG_INPUT, "ranks must own consecutive, gap-free cell ranges in rank order");
+    {  // subdomain diameters are computed by the owning rank only (zero elsewhere): make them global once
+      DevBuf<double> dia;
+      dia.upload(m->sub_diameter.data(), m->sub_diameter.size(), m->stream);
+      nc.all_reduce_sum(dia.p, m->sub_diameter.size(), m->comm, m->stream);
+      HDD_CUDA(cudaMemcpyAsync(m->sub_diameter.data(), dia.p, m->sub_diameter.size() * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+      HDD_CUDA(cudaStreamSynchronize(m->stream));
+    }
+    // halo plan.  Receive: halo cells sorted by global id are grouped by owner => contiguous ranges of the local
+    // vector.  Send: owned cells sharing a vertex with a halo cell owned by that peer, sorted by global id - this is
+    // exactly that peer's receive range, no index exchange needed.
+    const int nl = m->nl;
+    auto owner_of = [&](int64_t g) {
+      return int(std::upper_bound(m->rank_cell_offsets.begin(), m->rank_cell_offsets.end(), g) -
+                 m->rank_cell_offsets.begin()) - 1;
+    };
+    std::map<int, HaloPeer> peers;
+    std::map<int, std::vector<int32_t>> send_cells;
+    for (int32_t lc = 0; lc < m->n_loc; ++lc) {
+      if (lc >= m->own0 && lc < m->own0 + m->n_own) continue;
+      const int r = owner_of(m->cgid[size_t(lc)]);
+      auto it = peers.find(r);
+      if (it == peers.end()) {
+        HaloPeer p{};
+        p.rank = r;
+        p.recv_offset = int64_t(lc) * nl;
+        it = peers.emplace(r, p).first;
+      }
+      it->second.recv_count += nl;
+    }
+    for (auto& kv : peers) {
+      std::vector<uint8_t> vmark(size_t(m->n_verts_loc), 0);
+      for (int32_t lc = 0; lc < m->n_loc; ++lc) {
+        if (lc >= m->own0 && lc < m->own0 + m->n_own) continue;
+        if (owner_of(m->cgid[size_t(lc)]) != kv.first) continue;
+        for (int i = 0; i < nl; ++i) vmark[size_t(m->h_cell_verts_loc[size_t(lc) * nl + i])] = 1;
+      }
+      auto& sc = send_cells[kv.first];
+      for (int32_t lc = m->own0; lc < m->own0 + m->n_own; ++lc) {
+        bool touch = false;
+        for (int i = 0; i < nl; ++i) touch |= vmark[size_t(m->h_cell_verts_loc[size_t(lc) * nl + i])] != 0;
+        if (touch) sc.push_back(lc);
+      }
+    }
+    std::vector<int32_t> idx;
+    m->peers.clear();
+    for (auto& kv : peers) {
+      HaloPeer p = kv.second;
+      p.send_offset = int64_t(idx.size());
+      for (int32_t lc : send_cells[kv.first])
+        for (int i = 0; i < nl; ++i) idx.push_back(lc * nl + i);
+      p.send_count = int64_t(idx.size()) - p.send_offset;
+      m->peers.push_back(p);
+    }
+    m->send_idx.upload(idx.data(), idx.size(), m->stream);
+    m->send_buf.alloc(idx.size());
+    HDD_CUDA(cudaStreamSynchronize(m->stream));
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,86 @@
+"""Grid providers: host-side stand-ins for ``Stuff::Grid::Providers::Cube<GridType>`` and the multiscale grid
+(``grid::Multiscale``) the reference's test cases use (testcases/ESV2007.hh:123-163, testcases/spe10.hh:262-307).
+
+A ``Grid`` is just the flat arrays the C-ABI takes; a DUNE-equipped host would fill them from its own grid view.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+SIMPLEX2D, CUBE2D = capi.HDD_SIMPLEX2D, capi.HDD_CUBE2D
+
+
+class Grid:
+    def __init__(self, kind, xy, cell_verts, cell_neigh, cell_subdomain=None, partitions=(1, 1)):
+        self.kind = kind
+        self.xy = capi.as_f64(xy)
+        self.cell_verts = capi.as_i32(cell_verts)
+        self.cell_neigh = capi.as_i32(cell_neigh)
+        self.cell_subdomain = None if cell_subdomain is None else capi.as_i32(cell_subdomain)
+        self.partitions = tuple(partitions)
+        self.n_loc = 3 if kind == SIMPLEX2D else 4
+
+    @property
+    def n_cells(self):
+        return self.cell_verts.shape[0]
+
+    @property
+    def n_verts(self):
+        return self.xy.shape[0]
+
+    @property
+    def n_dofs(self):
+        return self.n_loc * self.n_cells
+
+    @property
+    def n_subdomains(self):
+        return 1 if self.cell_subdomain is None else int(self.cell_subdomain.max()) + 1
+
+    def centers(self):
+        return self.xy[self.cell_verts].mean(axis=1)
+
+    def subdomain_cell_offsets(self):
+        if self.cell_subdomain is None:
+            return np.array([0, self.n_cells], dtype=np.int64)
+        counts = np.bincount(self.cell_subdomain, minlength=self.n_subdomains)
+        return np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+
+
+def cube(nx, ny=None, lower_left=(-1.0, -1.0), upper_right=(1.0, 1.0), partitions=(1, 1)):
+    """SGrid<2,2> via Providers::Cube(lower_left, upper_right, num_elements): nx*ny axis-parallel cells, x fastest."""
+    ny = nx if ny is None else ny
+    L = capi.lib()
+    nc, nv = C.c_int64(), C.c_int64()
+    capi.check(L.hdd_grid_cube_sizes(C.c_int64(nx), C.c_int64(ny), C.byref(nc), C.byref(nv)))
+    xy = np.empty((nv.value, 2))
+    cv = np.empty((nc.value, 4), np.int32)
+    nb = np.empty((nc.value, 4), np.int32)
+    sub = np.empty(nc.value, np.int32)
+    capi.check(L.hdd_grid_cube(C.c_int64(nx), C.c_int64(ny), C.c_double(lower_left[0]), C.c_double(upper_right[0]),
+                               C.c_double(lower_left[1]), C.c_double(upper_right[1]), int(partitions[0]),
+                               int(partitions[1]), capi.ptr(xy), capi.ptr(cv, C.c_int32), capi.ptr(nb, C.c_int32),
+                               capi.ptr(sub, C.c_int32)))
+    return Grid(CUBE2D, xy, cv, nb, sub, partitions)
+
+
+def simplex(squares_per_side, lower_left=(-1.0, -1.0), upper_right=(1.0, 1.0), partitions=(1, 1)):
+    """ALUGrid<2,2,simplex,conforming> ladder member: squares_per_side^2 squares of 8 right triangles each.
+
+    The ESV2007 ladder (testcases/ESV2007.hh:50-59,123-134; testcases/base.hh:92-103) is Cube(-1,1,4) refined by
+    2 + 2*level bisections, i.e. ``squares_per_side = 4 * 2**level`` (128, 512, 2048, 8192 cells; reference 32768).
+    """
+    L = capi.lib()
+    s = int(squares_per_side)
+    nc, nv = C.c_int64(), C.c_int64()
+    capi.check(L.hdd_grid_simplex_sizes(C.c_int64(s), C.byref(nc), C.byref(nv)))
+    xy = np.empty((nv.value, 2))
+    cv = np.empty((nc.value, 3), np.int32)
+    nb = np.empty((nc.value, 3), np.int32)
+    sub = np.empty(nc.value, np.int32)
+    capi.check(L.hdd_grid_simplex(C.c_int64(s), C.c_double(lower_left[0]), C.c_double(upper_right[0]),
+                                  C.c_double(lower_left[1]), C.c_double(upper_right[1]), int(partitions[0]),
+                                  int(partitions[1]), capi.ptr(xy), capi.ptr(cv, C.c_int32), capi.ptr(nb, C.c_int32),
+                                  capi.ptr(sub, C.c_int32)))
+    return Grid(SIMPLEX2D, xy, cv, nb, sub, partitions)

@@ -1,0 +1,233 @@
+/*
+ * hdd_b200.h - C-ABI of the B200-native SWIPDG hot path (assembly -> CG solve -> estimators).
+ *
+ * This is the drop-in boundary for dune-hdd's LinearElliptic::Discretizations::SWIPDG /
+ * BlockSWIPDG and LinearElliptic::Estimators::{SWIPDG,BlockSWIPDG}.  The reference has no
+ * FFI of its own (its seam is a C++ template API plus a pybindgen projection), so every entry
+ * point below cites the reference method it replaces; INTEGRATION.md shows the C++ facade and
+ * the Python binding a dune-hdd maintainer would put on top.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every function returns an hdd_status (0 = ok) and leaves a
+ *    message retrievable through hdd_last_error() (thread local).
+ *  - all numbers are fp64 (RangeFieldType = double, testcases/ESV2007.hh:37); cell / DoF indices are
+ *    int32 (cells) and int64 (matrix offsets).
+ *  - "host" pointers are ordinary host memory, "dev" pointers are CUDA device memory owned by
+ *    the handle they were obtained from and valid until that handle is destroyed.
+ *  - one host thread per handle; all work of a handle is ordered on the handle's CUDA stream
+ *    (the reference objects are not thread safe either: mutable cache_, discretizations/base.hh:192).
+ *  - there is no CPU fallback: without a CUDA device hdd_mesh_create fails with HDD_ERR_DEVICE.
+ *
+ * Citations `file:line` are relative to the dune-hdd tree; `dune/hdd/linearelliptic/` is omitted.
+ */
+#ifndef HDD_B200_H
+#define HDD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes: one per exception type the reference throws on this path --------------- */
+typedef enum hdd_status {
+  HDD_OK = 0,
+  HDD_ERR_WRONG_INPUT = 1,          /* Stuff::Exceptions::wrong_input_given        (discretizations/base.hh:289) */
+  HDD_ERR_USING_THIS_WRONG = 2,     /* Stuff::Exceptions::you_are_using_this_wrong (discretizations/base.hh:373, estimators/swipdg.hh:968) */
+  HDD_ERR_WRONG_PARAMETER_TYPE = 3, /* Pymor::Exceptions::wrong_parameter_type     (discretizations/base.hh:333-334) */
+  HDD_ERR_INDEX_OUT_OF_RANGE = 4,   /* Stuff::Exceptions::index_out_of_range       (discretizations/block-swipdg.hh:560-562) */
+  HDD_ERR_NOT_IMPLEMENTED = 5,      /* Dune::NotImplemented                        (discretizations/swipdg.hh:173-176) */
+  HDD_ERR_REQUIREMENTS_NOT_MET = 6, /* Stuff::Exceptions::requirements_not_met     (estimators/block-swipdg.hh:766-773) */
+  HDD_ERR_INTERNAL = 7,             /* Stuff::Exceptions::internal_error */
+  HDD_ERR_DEVICE = 8,               /* CUDA / NCCL failure, or no device */
+  HDD_ERR_NOT_CONVERGED = 9         /* Stuff::Exceptions::linear_solver_failed (upstream Stuff::LA::Solver) */
+} hdd_status;
+
+const char* hdd_last_error(void);
+const char* hdd_version(void);
+
+/* ---- grids ------------------------------------------------------------------------------- */
+/* Element kinds.  Vertex and face numbering follow the Dune reference elements
+ *   HDD_SIMPLEX2D: vertices (0,0),(1,0),(0,1);       faces {0,1},{0,2},{1,2}
+ *   HDD_CUBE2D   : vertices (0,0),(1,0),(0,1),(1,1); faces {0,2},{1,3},{0,1},{2,3}  (axis-parallel cells only)
+ * The DG space is GDT::Spaces::DiscontinuousLagrangeProvider (discretizations/swipdg.hh:94-95):
+ * global DoF = n_loc * cell + local vertex index, n_loc = 3 (P1) resp. 4 (Q1). */
+enum { HDD_SIMPLEX2D = 0, HDD_CUBE2D = 1 };
+
+typedef struct hdd_mesh hdd_mesh;
+
+/* Replaces the grid view + boundary info + (for BlockSWIPDG) the ms_grid handed to
+ * SWIPDG(grid_provider, boundary_info_cfg, problem, level) (discretizations/swipdg.hh:159-163) and
+ * BlockSWIPDG(ms_grid_provider, ...) (discretizations/block-swipdg.hh:172-176).
+ *   xy             [2*n_verts]        vertex coordinates
+ *   cell_verts     [n_loc*n_cells]    vertex ids, reference-element order
+ *   cell_neigh     [n_faces*n_cells]  neighbour cell across each face, -1 = domain boundary
+ *   cell_subdomain [n_cells] or NULL  subdomain of each cell (grid::Multiscale::subdomainOf); cells must be
+ *                                     numbered subdomain-major so that the global DoF index equals
+ *                                     Spaces::Block::mapper().mapToGlobal(ss, i) (discretizations/block-swipdg.hh:1042)
+ *   boundary_type  [n_faces*n_cells] or NULL   1 = Dirichlet (default, AllDirichlet), 2 = Neumann
+ * The arrays are copied; the caller may free them afterwards.
+ * rank / world_size: this process owns the contiguous cell range [cell_begin, cell_end) (whole subdomains);
+ * pass 0, 1, 0, n_cells for a single GPU.  device = CUDA ordinal. */
+int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy, const int32_t* cell_verts,
+                    const int32_t* cell_neigh, const int32_t* cell_subdomain, const uint8_t* boundary_type,
+                    int64_t cell_begin, int64_t cell_end, int device, hdd_mesh** out);
+int hdd_mesh_destroy(hdd_mesh* mesh);
+int hdd_mesh_num_cells(const hdd_mesh* mesh, int64_t* n_global, int64_t* n_owned, int64_t* n_halo);
+
+/* Stand-ins for Stuff::Grid::Providers::Cube<GridType>(lower_left, upper_right, num_elements) as used by the
+ * test cases (testcases/ESV2007.hh:123-127, testcases/spe10.hh:262-268): host-side generators that fill caller
+ * arrays.  hdd_grid_cube: nx*ny axis-parallel cells, x fastest (SGrid).  hdd_grid_simplex: the conforming
+ * ALUGrid<2,2,simplex,conforming> ladder obtained from n x n squares after an even number of uniform bisections:
+ * squares_per_side^2 squares, each cut into 8 right triangles around its centre (8*s^2 cells).
+ * partitions_x/y > 1 renumber the cells subdomain-major ([px py 1] partition, testcases/ESV2007.hh:150-163) and
+ * fill cell_subdomain (may be NULL otherwise). */
+int hdd_grid_cube_sizes(int64_t nx, int64_t ny, int64_t* n_cells, int64_t* n_verts);
+int hdd_grid_cube(int64_t nx, int64_t ny, double x0, double x1, double y0, double y1, int partitions_x,
+                  int partitions_y, double* xy, int32_t* cell_verts, int32_t* cell_neigh, int32_t* cell_subdomain);
+int hdd_grid_simplex_sizes(int64_t squares_per_side, int64_t* n_cells, int64_t* n_verts);
+int hdd_grid_simplex(int64_t squares_per_side, double x0, double x1, double y0, double y1, int partitions_x,
+                     int partitions_y, double* xy, int32_t* cell_verts, int32_t* cell_neigh,
+                     int32_t* cell_subdomain);
+
+/* ---- problem data (ProblemInterface, problems/interfaces.hh:84-144) ----------------------------------- */
+/* A scalar data function as the host sees it after localisation:
+ *   HDD_FN_CONSTANT   Stuff::Functions::Constant                         -> value
+ *   HDD_FN_CELLWISE   piecewise constant (Spe10::Model1, Indicator, Checkerboard evaluated per cell by the
+ *                     host from the DUNE function object)                -> cell_values[n_cells] (global numbering)
+ *   HDD_FN_EXPRESSION Stuff::Functions::Expression("x", expr, order)     -> expression in x[0], x[1], pi
+ *                     (problems/OS2014.hh:63-74); ESV2007::Testcase1Force is "0.5*pi*pi*cos(0.5*pi*x[0])*cos(0.5*pi*x[1])"
+ * `order` is the polynomial order the function reports (drives the quadrature rule exactly as in dune-gdt). */
+enum { HDD_FN_CONSTANT = 0, HDD_FN_CELLWISE = 1, HDD_FN_EXPRESSION = 2 };
+
+typedef struct hdd_function {
+  int kind;
+  int order;
+  double value;
+  const double* cell_values;
+  const char* expression;
+} hdd_function;
+
+/* Pymor::Functions::AffinelyDecomposableDefault: sum_q theta_q(mu) * component_q + affine_part.
+ * coefficients[q] is the Pymor::ParameterFunctional expression in `mu` (e.g. "mu", "-1.0*mu"). */
+typedef struct hdd_affine_function {
+  int n_components;
+  const hdd_function* components;
+  const char* const* coefficients;
+  const hdd_function* affine_part; /* NULL = none */
+} hdd_affine_function;
+
+typedef struct hdd_problem {
+  hdd_affine_function diffusion_factor;
+  const double* diffusion_tensor; /* [4*n_cells] row-major 2x2 per cell (global numbering), NULL = identity;
+                                     never parametric (discretizations/swipdg.hh:173-176) */
+  hdd_affine_function force;
+  hdd_affine_function dirichlet;
+  hdd_affine_function neumann;
+  const char* parameter_name; /* "mu" (problems/OS2014.hh:72), NULL if non-parametric */
+  int parameter_size;         /* 1 */
+} hdd_problem;
+
+/* ---- discretization ---------------------------------------------------------------------------- */
+typedef struct hdd_swipdg hdd_swipdg;
+
+enum { HDD_LHS = 0, HDD_RHS = 1 };
+
+/* SWIPDG::SWIPDG(...) (discretizations/swipdg.hh:159-177) / BlockSWIPDG::BlockSWIPDG (block-swipdg.hh:172-260).
+ * polorder must be 1 this round.  Fails with HDD_ERR_WRONG_INPUT if the tensor is empty etc. */
+int hdd_swipdg_create(hdd_mesh* mesh, int polorder, const hdd_problem* problem, hdd_swipdg** out);
+int hdd_swipdg_destroy(hdd_swipdg* h);
+
+/* SWIPDG::init() (discretizations/swipdg.hh:206-512): pattern + all affine parts of the system matrix and of
+ * the rhs, assembled on the GPU in one pass per part set.  Idempotent (container_based_initialized_, :208,:510). */
+int hdd_swipdg_init(hdd_swipdg* h);
+/* Re-runs only system_assembler.walk() (:485) on an initialised handle; used by the benchmark. seconds may be NULL. */
+int hdd_swipdg_assemble(hdd_swipdg* h, double* seconds);
+
+int hdd_num_dofs(const hdd_swipdg* h, int64_t* n_global, int64_t* n_owned);   /* space.mapper().size() */
+/* pattern() (discretizations/swipdg.hh:201-204) as CSR of the owned rows; col holds global DoF indices. */
+int hdd_pattern(hdd_swipdg* h, int64_t* n_rows, int64_t* nnz, const int64_t** rowptr_dev, const int32_t** col_dev);
+/* system_matrix()/rhs() parts (discretizations/base.hh:240-270): num_components(), component(q), coefficient(q),
+ * has_affine_part(), affine_part().  q = -1 addresses the affine part. */
+int hdd_num_components(const hdd_swipdg* h, int which, int* n_components, int* has_affine_part);
+int hdd_component_values(hdd_swipdg* h, int which, int q, const double** values_dev, int64_t* count);
+int hdd_component_coefficient(const hdd_swipdg* h, int which, int q, const char** expression);
+/* evaluates the coefficients theta_q(mu) of `which` (ParameterFunctional::evaluate). */
+int hdd_evaluate_coefficients(const hdd_swipdg* h, int which, const double* mu, int mu_size, double* theta);
+int hdd_copy_to_host(hdd_swipdg* h, void* dst_host, const void* src_dev, size_t bytes);
+int hdd_sync(hdd_swipdg* h);
+
+/* get_operator().freeze_parameter(mu).apply(x, y) - one SpMV with the frozen operator (block-swipdg.hh:741). */
+int hdd_apply(hdd_swipdg* h, const double* mu, int mu_size, const double* x_host, double* y_host);
+
+typedef struct hdd_solve_info {
+  int iterations;
+  int converged;
+  double relative_residual; /* ||r||_2 / ||b||_2 (recursive) */
+  double seconds;           /* device time of freeze + CG, CUDA events */
+  double seconds_per_iteration;
+} hdd_solve_info;
+
+/* solver_types() / solver_options(type) (discretizations/base.hh:314-322). Types: "cg.diagonal" (default,
+ * Jacobi), "cg.identity"; aliases "cg", "cg.jacobi", "cg.diagonal.lower", "cg.identity.lower". */
+int hdd_solver_types(const char* const** types, int* n_types);
+/* uncached_solve(options, vector, mu) (discretizations/base.hh:327-367): freeze lhs and rhs at mu, CG.
+ * precision / max_iter mirror Stuff::LA::Solver's option keys.  x_host[n_owned] receives the solution
+ * (NULL: keep it on the device only, see hdd_solution_dev).  mu may be NULL for non-parametric problems;
+ * a wrong mu_size gives HDD_ERR_WRONG_PARAMETER_TYPE (:333-334). */
+int hdd_solve(hdd_swipdg* h, const char* type, double precision, int max_iter, const double* mu, int mu_size,
+              double* x_host, hdd_solve_info* info);
+int hdd_solution_dev(hdd_swipdg* h, const double** x_dev);
+
+/* ---- BlockSWIPDG views (discretizations/block-swipdg.hh:553-690) --------------------------------------- */
+int hdd_num_subdomains(const hdd_swipdg* h, int* n);
+int hdd_subdomain_offsets(const hdd_swipdg* h, const int64_t** offsets_host); /* n+1 DoF offsets, mapToGlobal(ss,0) */
+int hdd_neighbouring_subdomains(const hdd_swipdg* h, int ss, const int32_t** neighbours_host, int* n);
+typedef struct hdd_csr {
+  int64_t n_rows, n_cols, nnz;
+  int64_t* rowptr;
+  int32_t* col;
+  double* val;
+} hdd_csr;
+/* get_local_operator(ss) (nn == ss) / get_coupling_operator(ss, nn): the (ss, nn) block of affine part q
+ * (q = -1: affine part) with subdomain-local indices; host copy, release with hdd_csr_free. */
+int hdd_block_extract(hdd_swipdg* h, int ss, int nn, int q, hdd_csr* out);
+int hdd_csr_free(hdd_csr* m);
+
+/* ---- estimators (estimators/swipdg.hh:824-985, estimators/block-swipdg.hh:1076-1265) ------------------- */
+typedef struct hdd_parameters { /* the ParametersMapType keys of estimators/block-swipdg.hh:756-765 */
+  const double* mu;
+  const double* mu_hat;
+  const double* mu_bar;
+  const double* parameter_range_min;
+  const double* parameter_range_max;
+  int mu_size;
+} hdd_parameters;
+
+/* available(): "eta_NC_ESV2007", "eta_R_ESV2007", "eta_R_ESV2007_*", "eta_DF_ESV2007", "eta_ESV2007",
+ * "eta_ESV2007_alt", "eta_NC_OS2014", "eta_R_OS2014", "eta_R_OS2014_*", "eta_DF_OS2014", "eta_DF_OS2014_*",
+ * "eta_OS2014", "eta_OS2014_*".  Simplex grids only, like the reference (estimators/swipdg.hh:71). */
+int hdd_estimators_available(const hdd_swipdg* h, const char* const** types, int* n_types);
+/* estimate(space, vector, problem, type[, parameters]) -> eta;  u_host = NULL uses the last solution.
+ * local_host (nullable): estimate_local(): n_cells (ESV2007 types) or n_subdomains (OS2014 types) entries. */
+int hdd_estimate(hdd_swipdg* h, const char* type, const double* u_host, const hdd_parameters* parameters,
+                 double* eta, double* local_host);
+/* all squared per-cell indicators of one pass, for tests: out[8][n_owned] = nc2,res2,r2,df2,dfstar2,rstar2,amin,resstar2 */
+int hdd_indicators(hdd_swipdg* h, const double* u_host, const hdd_parameters* parameters, double* out_host);
+
+/* ---- multi GPU: one process per GPU ------------------------------------------------------------------------ */
+/* NCCL plumbing: rank 0 calls hdd_comm_unique_id, the id is broadcast by the host program (torch.distributed),
+ * every rank calls hdd_comm_init before hdd_swipdg_create on a mesh with world_size > 1.  NCCL carries only the
+ * coupling-face halo exchange of the CG direction and the dot-product all-reduces. */
+int hdd_comm_unique_id(void* id128);
+int hdd_comm_init(hdd_mesh* mesh, const void* id128, int rank, int world_size);
+
+/* ---- counters --------------------------------------------------------------------------------------------------- */
+/* number of kernels this library launched since process start (bench.py's gpu_launches) */
+int64_t hdd_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HDD_B200_H */

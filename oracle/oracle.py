@@ -202,7 +202,7 @@ def indicators(mesh, u, force, a_mu, a_hat=None, a_bar=None, a_cut=None, a_min=N
     a_cut = a_cut or a_mu
     a_min = a_min or a_mu
     a_max = a_max or a_mu
-    names = ["nc2", "res2", "r2", "df2", "dfstar2", "rstar2", "amin"]
+    names = ["nc2", "res2", "r2", "df2", "dfstar2", "rstar2", "amin", "resstar2"]
     out = {k: np.zeros(mesh.nc) for k in names}
     t = None if tensor is None else np.ascontiguousarray(tensor, dtype=np.float64)
     u = np.ascontiguousarray(u, dtype=np.float64)

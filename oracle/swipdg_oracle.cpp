@@ -702,12 +702,13 @@ void or_oswald(int kind, int nc, int nv, const int32_t* cv, const int32_t* nb, c
 //   dfstar2[T] = int_T (A(mu) grad u + t_h).A^^-1(...)                    estimators/block-swipdg.hh:609-614,666-670
 //   rstar2[T]  = (C_P h_T^2 / c_T) int_T (f - div t_h)^2                  estimators/swipdg.hh:437-447
 //   amin[T]    = min(min a(mu_min), min a(mu_max)) * lambda_min(K)        estimators/block-swipdg.hh:272-276
+//   resstar2[T]= int_T (f - div t_h)^2                                    estimators/block-swipdg.hh:510-521
 // over_integrate = 2 (estimators/swipdg.hh:47).
 void or_indicators(int nc, int nv, const double* xy, const int32_t* cv, const int32_t* nb, const double* u,
                    const ofn_t* a_mu, const ofn_t* a_hat, const ofn_t* a_bar, const ofn_t* a_cut,
                    const ofn_t* a_min, const ofn_t* a_max, const double* tensor, const ofn_t* force,
                    double* nc2, double* res2, double* r2, double* df2, double* dfstar2, double* rstar2,
-                   double* amin) {
+                   double* amin, double* resstar2) {
   Mesh m{SIMPLEX, nc, nv, xy, cv, nb};
   const int nl = 3, p = 1, over = 2;
   std::vector<double> iu(size_t(nl) * nc);
@@ -862,7 +863,7 @@ void or_indicators(int nc, int nv, const double* xy, const int32_t* cv, const in
       if (df2) df2[c] = s;
       if (dfstar2) dfstar2[c] = ss;
     }
-    if (rstar2) {
+    if (rstar2 || resstar2) {
       const double div = (G[0] + G[1] + G[2]) / area;
       double s = 0.0;
       for (size_t q = 0; q < q_res.w.size(); ++q) {
@@ -871,7 +872,8 @@ void or_indicators(int nc, int nv, const double* xy, const int32_t* cv, const in
         const double d = fn_eval(*force, c, x, y) - div;
         s += q_res.w[q] * g.detj * d * d;
       }
-      rstar2[c] = cutoff * s;
+      if (rstar2) rstar2[c] = cutoff * s;
+      if (resstar2) resstar2[c] = s;  // estimators/block-swipdg.hh:510-521 (constant_one weight)
     }
   }
 }

@@ -1,0 +1,305 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the CPU oracle on identical grids and inputs.
+
+Bars (BASELINE.json north_star): pattern and DoF map bit-exact, assembled entries 1e-12 relative, solution /
+norms / indicators 1e-8 relative, goldens to their 3 printed digits."""
+import numpy as np
+import pytest
+
+import dune_hdd_b200 as hdd
+from dune_hdd_b200 import grids, problems
+from oracle import oracle as o
+from tests.helpers import direct_solve, oracle_mesh, oracle_system, rel
+
+pytestmark = pytest.mark.gpu
+
+ENTRY_TOL = 1e-12
+SOL_TOL = 1e-8
+
+
+def _grid(kind, n, partitions=(1, 1)):
+    return grids.simplex(n, partitions=partitions) if kind == "alu" else grids.cube(n, partitions=partitions)
+
+
+@pytest.mark.parametrize("kind,n", [("alu", 4), ("alu", 8), ("sgrid", 8), ("sgrid", 16), ("sgrid", 1), ("alu", 1)])
+def test_esv2007_pattern_and_entries(gpu, kind, n):
+    g = _grid(kind, n)
+    d = hdd.SWIPDG(g, problems.ESV2007())
+    d.init()
+    d.init()  # idempotent
+    m, rp, col, A, b = oracle_system(g, o.const(1.0), o.esv2007_force())
+    rp_g, col_g = d.pattern()
+    assert np.array_equal(rp_g, rp) and np.array_equal(col_g, col)  # bit-exact pattern + DoF map
+    M = d.system_matrix()
+    assert M.num_components() == 0 and M.has_affine_part()
+    assert rel(M.affine_part(), A) <= ENTRY_TOL
+    R = d.rhs()
+    assert R.num_components() == 0 and R.has_affine_part()
+    assert rel(R.affine_part(), b) <= ENTRY_TOL
+
+
+@pytest.mark.parametrize("kind,n", [("alu", 4), ("alu", 16), ("sgrid", 8), ("sgrid", 32)])
+def test_esv2007_solve_matches_direct_solve(gpu, kind, n):
+    g = _grid(kind, n)
+    d = hdd.SWIPDG(g, problems.ESV2007())
+    d.init()
+    m, rp, col, A, b = oracle_system(g, o.const(1.0), o.esv2007_force())
+    u_ref = direct_solve(rp, col, A, b)
+    for typ in ("cg.diagonal", "cg.identity"):
+        u, info = d.solve({"type": typ, "precision": 1e-13, "max_iter": 20000}, return_info=True)
+        assert info["converged"]
+        assert rel(u, u_ref) <= SOL_TOL
+    # operator application
+    x = np.random.default_rng(0).standard_normal(g.n_dofs)
+    assert rel(d.apply(x), o.spmv(rp, col, A, x)) <= 1e-13
+
+
+def test_cg_iterates_follow_the_oracle_cg(gpu):
+    g = grids.cube(16)
+    d = hdd.SWIPDG(g, problems.ESV2007())
+    d.init()
+    m, rp, col, A, b = oracle_system(g, o.const(1.0), o.esv2007_force())
+    for maxit in (1, 2, 5, 20):
+        x_ref, it, rr = o.cg(rp, col, A, b, precond=1, rtol=1e-30, maxit=maxit)
+        with pytest.raises(hdd.discretizations.linear_solver_failed):
+            d.uncached_solve({"type": "cg.diagonal", "precision": 1e-30, "max_iter": maxit})
+        x = np.empty(g.n_dofs)
+        import ctypes as C
+        p = C.POINTER(C.c_double)()
+        hdd.capi.check(hdd.capi.lib().hdd_solution_dev(d._h, C.byref(p)))
+        hdd.capi.check(hdd.capi.lib().hdd_copy_to_host(d._h, hdd.capi.ptr(x), p, C.c_size_t(x.nbytes)))
+        assert rel(x, x_ref) <= 1e-11
+
+
+GOLDEN_ALU = {  # test/linearelliptic-swipdg-expectations_esv2007_2daluconform.cxx:32-57
+    "L2": [1.83e-02, 4.53e-03, 1.12e-03], "H1_semi": [3.28e-01, 1.62e-01, 8.04e-02],
+    "eta_NC_ESV2007": [1.66e-1, 7.89e-2, 3.91e-2], "eta_R_ESV2007": [7.23e-2, 1.82e-2, 4.54e-3],
+    "eta_DF_ESV2007": [3.55e-1, 1.76e-1, 8.73e-2], "eta_ESV2007": [4.49e-01, 2.07e-01, 9.91e-02],
+    "eta_ESV2007_alt": [5.93e-01, 2.73e-01, 1.31e-01]}
+
+
+def _digits3(x, golden):
+    return abs(x - golden) <= 0.006 * abs(golden)
+
+
+@pytest.mark.parametrize("level", [0, 1, 2])
+def test_esv2007_estimators_and_goldens(gpu, level):
+    g = grids.simplex(4 * 2 ** level)
+    d = hdd.SWIPDG(g, problems.ESV2007())
+    d.init()
+    u = d.solve({"type": "cg.diagonal", "precision": 1e-13, "max_iter": 50000})
+    m = oracle_mesh(g)
+    ind_ref = o.indicators(m, u, o.esv2007_force(), o.const(1.0))
+    ind = d.indicators(u)
+    for k in ("nc2", "res2", "r2", "df2", "dfstar2", "rstar2", "resstar2"):
+        assert np.abs(ind[k] - ind_ref[k]).max() <= SOL_TOL * np.abs(ind_ref[k]).max(), k
+    assert rel(ind["amin"], ind_ref["amin"]) <= 1e-14
+    est = hdd.estimators.SWIPDG
+    assert est.available(d) == hdd.estimators.ESV2007_TYPES
+    for typ in est.available(d):
+        eta = est.estimate(d, u, typ)
+        if typ in GOLDEN_ALU:
+            assert _digits3(eta, GOLDEN_ALU[typ][level]), (typ, eta)
+    eta_ref = np.sqrt((ind_ref["nc2"] + (np.sqrt(ind_ref["r2"]) + np.sqrt(ind_ref["df2"])) ** 2).sum())
+    assert abs(est.estimate(d, u, "eta_ESV2007") - eta_ref) <= SOL_TOL * eta_ref
+    loc = est.estimate_local(d, u, "eta_ESV2007")
+    assert loc.shape == (g.n_cells,) and abs(loc.sum() - 1.0) < 1e-12
+    loc = est.estimate_local(d, u, "eta_ESV2007_alt")
+    assert loc.shape == (g.n_cells,)
+    err = o.error_norms(m, u, o.esv2007_exact())
+    assert _digits3(err["L2"], GOLDEN_ALU["L2"][level]) and _digits3(err["H1_semi"], GOLDEN_ALU["H1_semi"][level])
+
+
+def test_os2014_parametric_parts_and_sweep(gpu):
+    g = grids.simplex(4, partitions=(4, 4))
+    prob = problems.OS2014ParametricESV2007()
+    d = hdd.BlockSWIPDG(g, prob)
+    d.init()
+    m = oracle_mesh(g)
+    rp, col = o.pattern(m)
+    M = d.system_matrix()
+    assert M.num_components() == 1 and M.has_affine_part() and M.coefficient(0) == "mu"
+    assert rel(M.affine_part(), o.assemble_lhs(m, o.os2014_affine(), None, rp, col)) <= ENTRY_TOL
+    assert rel(M.component(0), o.assemble_lhs(m, o.os2014_component(), None, rp, col)) <= ENTRY_TOL
+    R = d.rhs()
+    assert R.num_components() == 1 and R.coefficient(0) == "mu"  # the (zero) dirichlet x factor-component vector
+    assert np.all(R.component(0) == 0.0)
+    b = o.assemble_rhs(m, o.esv2007_force())
+    assert rel(R.affine_part(), b) <= ENTRY_TOL
+    with pytest.raises(hdd.discretizations.wrong_parameter_type):
+        d.solve(mu=None)
+    with pytest.raises(hdd.discretizations.wrong_parameter_type):
+        d.solve(mu=[0.1, 0.2])
+    for mu in (0.1, 0.5, 1.0):
+        A = o.assemble_lhs(m, o.os2014_factor(mu), None, rp, col)
+        assert rel(M.freeze_parameter(mu), A) <= ENTRY_TOL
+        u_ref = direct_solve(rp, col, A, b)
+        u = d.solve({"type": "cg.diagonal", "precision": 1e-13, "max_iter": 50000}, mu=mu)
+        assert rel(u, u_ref) <= SOL_TOL
+        for mu_hat in (0.1, 1.0):
+            prm = {"mu": mu, "mu_bar": mu, "mu_hat": mu_hat, "parameter_range_min": 0.1, "parameter_range_max": 1.0}
+            ind_ref = o.indicators(m, u, o.esv2007_force(), o.os2014_factor(mu), a_hat=o.os2014_factor(mu_hat),
+                                   a_bar=o.os2014_factor(mu), a_min=o.os2014_factor(0.1), a_max=o.os2014_factor(1.0))
+            ind = d.indicators(u, prm)
+            for k in ("nc2", "res2", "df2", "dfstar2", "resstar2", "amin"):
+                assert np.abs(ind[k] - ind_ref[k]).max() <= SOL_TOL * np.abs(ind_ref[k]).max(), (k, mu, mu_hat)
+
+
+GOLDEN_OS2014_MU1 = {  # test/linearelliptic-block-swipdg-expectations_os2014_2daluconform.cxx:170-212, [4 4 1]
+    (1.0, 1.0): {"eta_DF_OS2014": [3.55e-1, 1.76e-1], "eta_OS2014": [7.74e-01, 3.82e-01]},
+    (1.0, 0.1): {"eta_DF_OS2014": [1.36, 1.33], "eta_DF_OS2014_*": [4.13e-01, 2.05e-01]},
+}
+
+
+@pytest.mark.parametrize("level", [0, 1])
+def test_os2014_goldens_mu1(gpu, level):
+    g = grids.simplex(4 * 2 ** level, partitions=(4, 4))
+    d = hdd.BlockSWIPDG(g, problems.OS2014ParametricESV2007())
+    d.init()
+    u = d.solve({"type": "cg.diagonal", "precision": 1e-13, "max_iter": 50000}, mu=1.0)
+    est = hdd.estimators.BlockSWIPDG
+    assert est.available(d) == hdd.estimators.OS2014_TYPES
+    for (mu, mu_hat), gold in GOLDEN_OS2014_MU1.items():
+        prm = {"mu": mu, "mu_bar": mu, "mu_hat": mu_hat, "parameter_range_min": 0.1, "parameter_range_max": 1.0}
+        for typ, vals in gold.items():
+            eta = est.estimate(d, u, typ, prm)
+            assert abs(eta - vals[level]) <= 0.012 * vals[level], (typ, mu, mu_hat, eta)
+    with pytest.raises(hdd.discretizations.wrong_input_given):
+        est.estimate(d, u, "eta_OS2014", {"mu": 1.0, "mu_bar": 1.0})  # missing mu_hat
+    loc = est.estimate_local(d, u, "eta_OS2014", {"mu": 1.0, "mu_bar": 1.0, "mu_hat": 1.0,
+                                                  "parameter_range_min": 0.1, "parameter_range_max": 1.0})
+    assert loc.shape == (16,)
+
+
+GOLDEN_BLOCK_ESV = {  # test/linearelliptic-block-swipdg-expectations_esv2007_2daluconform.cxx:35-134, level 0 and 1
+    (1, 1): {"eta_R_OS2014": [5.79e-01, 2.90e-01], "eta_OS2014": [1.10e+00, 5.45e-01]},
+    (2, 2): {"eta_R_OS2014": [2.89e-01, 1.45e-01], "eta_OS2014": [8.10e-01, 4.00e-01]},
+    (4, 4): {"eta_R_OS2014": [1.45e-01, 7.26e-02], "eta_OS2014": [6.65e-01, 3.27e-01]},
+    (8, 8): {"eta_R_OS2014": [7.23e-02, 3.63e-02], "eta_OS2014": [5.93e-01, 2.91e-01]},
+}
+
+
+@pytest.mark.parametrize("parts", [(1, 1), (2, 2), (4, 4), (8, 8)])
+def test_block_swipdg_esv2007(gpu, parts):
+    for level in (0, 1):
+        g = grids.simplex(4 * 2 ** level, partitions=parts)
+        d = hdd.BlockSWIPDG(g, problems.ESV2007())
+        d.init()
+        assert d.num_subdomains() == parts[0] * parts[1]
+        u = d.solve({"type": "cg.diagonal", "precision": 1e-13, "max_iter": 50000})
+        m = oracle_mesh(g)
+        err = o.error_norms(m, u, o.esv2007_exact())
+        assert _digits3(err["L2"], GOLDEN_ALU["L2"][level])  # block == non-block norms
+        for typ, vals in GOLDEN_BLOCK_ESV[parts].items():
+            eta = hdd.estimators.BlockSWIPDG.estimate(d, u, typ)
+            assert _digits3(eta, vals[level]), (parts, typ, eta)
+        assert _digits3(hdd.estimators.BlockSWIPDG.estimate(d, u, "eta_NC_OS2014"), GOLDEN_ALU["eta_NC_ESV2007"][level])
+        assert _digits3(hdd.estimators.BlockSWIPDG.estimate(d, u, "eta_DF_OS2014_*"), GOLDEN_ALU["eta_DF_ESV2007"][level])
+
+
+def test_block_views_are_sub_blocks_of_the_global_matrix(gpu):
+    g = grids.simplex(4, partitions=(2, 2))
+    d = hdd.BlockSWIPDG(g, problems.ESV2007())
+    d.init()
+    rp, col = d.pattern()
+    S = o.to_scipy(rp, col, d.system_matrix().affine_part()).tocsr()
+    off = d.subdomain_offsets()
+    assert off[-1] == g.n_dofs
+    for ss in range(4):
+        nbs = d.neighbouring_subdomains(ss)
+        assert ss not in nbs and len(nbs) >= 2
+        L = d.get_local_operator(ss)
+        assert abs(L - S[off[ss]:off[ss + 1], off[ss]:off[ss + 1]]).max() == 0.0
+        for nn in nbs:
+            Cn = d.get_coupling_operator(ss, nn)
+            assert abs(Cn - S[off[ss]:off[ss + 1], off[nn]:off[nn + 1]]).max() == 0.0
+            assert Cn.nnz > 0
+    with pytest.raises(hdd.discretizations.index_out_of_range):
+        d.neighbouring_subdomains(4)
+    far = [s for s in range(4) if s != 0 and s not in d.neighbouring_subdomains(0)]
+    for nn in far:
+        with pytest.raises(hdd.discretizations.wrong_input_given):
+            d.get_coupling_operator(0, nn)
+    u = np.arange(g.n_dofs, dtype=float)
+    assert np.array_equal(d.globalize_vectors([d.localize_vector(u, s) for s in range(4)]), u)
+
+
+def test_spe10_shaped_sgrid_with_cellwise_tensor(gpu):
+    g = grids.cube(100, 20, (0.0, 0.0), (5.0, 1.0))
+    prob = problems.Spe10Model1(g)
+    d = hdd.SWIPDG(g, prob)
+    d.init()
+    m = oracle_mesh(g)
+    rp, col = o.pattern(m)
+    A = o.assemble_lhs(m, o.const(1.0), prob.diffusion_tensor, rp, col)
+    b = o.assemble_rhs(m, o.cellwise(prob.force.affine.cell_values))
+    assert np.array_equal(d.pattern()[1], col)
+    assert rel(d.system_matrix().affine_part(), A) <= ENTRY_TOL
+    assert rel(d.rhs().affine_part(), b) <= ENTRY_TOL
+    u = d.solve({"type": "cg.diagonal", "precision": 1e-13, "max_iter": 200000})
+    assert rel(u, direct_solve(rp, col, A, b)) <= SOL_TOL
+    assert d.available_estimators() == []  # estimators exist for ALU simplices only (estimators/swipdg.hh:71)
+    with pytest.raises(hdd.discretizations.you_are_using_this_wrong):
+        d.estimate(u, "eta_ESV2007")
+
+
+def test_error_behaviour(gpu):
+    g = grids.simplex(4)
+    d = hdd.SWIPDG(g, problems.ESV2007())
+    with pytest.raises(hdd.discretizations.you_are_using_this_wrong):
+        d.pattern()  # init() not called (discretizations/base.hh:370-377)
+    with pytest.raises(hdd.discretizations.you_are_using_this_wrong):
+        d.solve()
+    d.init()
+    with pytest.raises(hdd.discretizations.wrong_input_given):
+        d.uncached_solve({"type": "bicgstab.ilut"})
+    with pytest.raises(hdd.discretizations.you_are_using_this_wrong):
+        d.estimate(d.solve(), "eta_unknown")
+    with pytest.raises(hdd.discretizations.wrong_parameter_type):
+        d.solve(mu=[1.0])
+    with pytest.raises(hdd.discretizations.NotImplemented_):
+        hdd.SWIPDG(g, problems.ESV2007(), polorder=2)
+    bad = problems.ESV2007()
+    bad.force = problems.AffinelyDecomposable(problems.Expression("cos(x[0]", 3))
+    with pytest.raises(hdd.discretizations.wrong_input_given):
+        hdd.SWIPDG(g, bad)
+    # solution cache: same (options, mu) returns the cached vector
+    u1, i1 = d.solve(return_info=True)
+    u2, i2 = d.solve(return_info=True)
+    assert np.array_equal(u1, u2) and i1 == i2
+
+
+def test_nonzero_dirichlet_and_neumann_faces(gpu):
+    g = grids.simplex(4)
+    prob = problems.ESV2007()
+    prob.dirichlet = problems.AffinelyDecomposable(problems.Expression("1+x[0]*x[1]", 2, "dirichlet"))
+    d = hdd.SWIPDG(g, prob)
+    d.init()
+    m = oracle_mesh(g)
+    gd = o.fn([(1.0, o.FN_ONE)], 2)  # oracle has no x*y term: compare with the constant part only through linearity
+    b_ref = o.assemble_rhs(m, o.esv2007_force(), o.const(1.0), gd)
+    prob2 = problems.ESV2007()
+    prob2.dirichlet = problems.AffinelyDecomposable(problems.Expression("1+0*x[0]", 2, "dirichlet"))
+    d2 = hdd.SWIPDG(g, prob2)
+    d2.init()
+    assert rel(d2.rhs().affine_part(), b_ref) <= ENTRY_TOL
+    assert np.abs(d.rhs().affine_part() - d2.rhs().affine_part()).max() > 1e-3
+
+
+def test_large_grid_properties(gpu):
+    """size-independent properties at a size the oracle does not run in seconds: symmetry through <Ax,y> = <x,Ay>,
+    row sums of the interior stiffness (constants are in the kernel of the volume + inner-face terms), CG residual."""
+    g = grids.cube(512)
+    d = hdd.SWIPDG(g, problems.ESV2007())
+    d.init()
+    rng = np.random.default_rng(1)
+    x, y = rng.standard_normal(g.n_dofs), rng.standard_normal(g.n_dofs)
+    ax, ay = d.apply(x), d.apply(y)
+    assert abs(ax @ y - x @ ay) <= 1e-11 * abs(ax @ y)
+    one = d.apply(np.ones(g.n_dofs)).reshape(-1, 4)
+    interior = (g.cell_neigh >= 0).all(axis=1)
+    assert np.abs(one[interior]).max() <= 1e-9 * np.abs(one).max()
+    u, info = d.solve({"type": "cg.diagonal", "precision": 1e-10, "max_iter": 20000}, return_info=True)
+    b = d.rhs().affine_part()
+    assert np.linalg.norm(d.apply(u) - b) <= 2e-10 * np.linalg.norm(b)
+    c = g.centers()
+    assert np.abs(u.reshape(-1, 4).mean(axis=1) - problems.esv2007_exact(c)).max() < 1e-4
