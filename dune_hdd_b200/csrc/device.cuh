@@ -86,7 +86,8 @@ struct Geo<HDD_SIMPLEX2D> {
     const double j00 = vx[1] - vx[0], j10 = vy[1] - vy[0], j01 = vx[2] - vx[0], j11 = vy[2] - vy[0];
     const double det = j00 * j11 - j01 * j10;
     detj = fabs(det);
-    i00 = j11 / det; i01 = -j01 / det; i10 = -j10 / det; i11 = j00 / det;
+    const double idet = 1.0 / det;
+    i00 = j11 * idet; i01 = -j01 * idet; i10 = -j10 * idet; i11 = j00 * idet;
   }
   __device__ __forceinline__ void to_global(double xi, double eta, double& x, double& y) const {
     x = vx[0] + (vx[1] - vx[0]) * xi + (vx[2] - vx[0]) * eta;
@@ -125,13 +126,14 @@ struct Geo<HDD_SIMPLEX2D> {
 template <>
 struct Geo<HDD_CUBE2D> {
   static constexpr int NL = 4, NF = 4, NGEO = 4;
-  double x0, y0, x1, y1, hx, hy, detj;
+  double x0, y0, x1, y1, hx, hy, ihx, ihy, detj;
 
   __device__ __forceinline__ void load(const double* cgeo, int cell) {
     const double2* p = reinterpret_cast<const double2*>(cgeo + size_t(NGEO) * cell);
     const double2 a = __ldg(p), b = __ldg(p + 1);
     x0 = a.x; y0 = a.y; x1 = b.x; y1 = b.y;
     hx = x1 - x0; hy = y1 - y0;
+    ihx = 1.0 / hx; ihy = 1.0 / hy;
     detj = fabs(hx * hy);
   }
   __device__ __forceinline__ void to_global(double xi, double eta, double& x, double& y) const {
@@ -139,14 +141,14 @@ struct Geo<HDD_CUBE2D> {
     y = y0 + hy * eta;
   }
   __device__ __forceinline__ void to_local(double x, double y, double& xi, double& eta) const {
-    xi = (x - x0) / hx;
-    eta = (y - y0) / hy;
+    xi = (x - x0) * ihx;
+    eta = (y - y0) * ihy;
   }
   __device__ __forceinline__ void basis(double xi, double eta, double* phi, double* gx, double* gy) const {
     phi[0] = (1.0 - xi) * (1.0 - eta); phi[1] = xi * (1.0 - eta);
     phi[2] = (1.0 - xi) * eta;         phi[3] = xi * eta;
-    gx[0] = -(1.0 - eta) / hx; gx[1] = (1.0 - eta) / hx; gx[2] = -eta / hx; gx[3] = eta / hx;
-    gy[0] = -(1.0 - xi) / hy;  gy[1] = -xi / hy;         gy[2] = (1.0 - xi) / hy; gy[3] = xi / hy;
+    gx[0] = -(1.0 - eta) * ihx; gx[1] = (1.0 - eta) * ihx; gx[2] = -eta * ihx; gx[3] = eta * ihx;
+    gy[0] = -(1.0 - xi) * ihy;  gy[1] = -xi * ihy;         gy[2] = (1.0 - xi) * ihy; gy[3] = xi * ihy;
   }
   __device__ __forceinline__ void centroid(double& cx, double& cy) const {
     cx = 0.5 * (x0 + x1);
@@ -163,17 +165,31 @@ struct Geo<HDD_CUBE2D> {
 };
 
 struct FaceGeo {
-  double ax, ay, bx, by, nx, ny, h;
+  double ax, ay, bx, by, nx, ny, h, ih;
 };
 
-template <class G>
-__device__ __forceinline__ FaceGeo make_face(const G& g, int f) {
+// axis-parallel rectangle: exact normals, no sqrt / division
+__device__ __forceinline__ FaceGeo make_face(const Geo<HDD_CUBE2D>& g, int f) {
+  FaceGeo e;
+  g.face_ends(f, e.ax, e.ay, e.bx, e.by);
+  const bool vertical = f < 2;  // faces 0,1 are x = const
+  e.h = vertical ? fabs(g.hy) : fabs(g.hx);
+  e.ih = vertical ? fabs(g.ihy) : fabs(g.ihx);
+  e.nx = vertical ? (f == 0 ? -1.0 : 1.0) : 0.0;
+  e.ny = vertical ? 0.0 : (f == 2 ? -1.0 : 1.0);
+  if (g.hx < 0.0) e.nx = -e.nx;
+  if (g.hy < 0.0) e.ny = -e.ny;
+  return e;
+}
+
+__device__ __forceinline__ FaceGeo make_face(const Geo<HDD_SIMPLEX2D>& g, int f) {
   FaceGeo e;
   g.face_ends(f, e.ax, e.ay, e.bx, e.by);
   const double tx = e.bx - e.ax, ty = e.by - e.ay;
   e.h = sqrt(tx * tx + ty * ty);
-  e.nx = ty / e.h;
-  e.ny = -tx / e.h;
+  e.ih = 1.0 / e.h;
+  e.nx = ty * e.ih;
+  e.ny = -tx * e.ih;
   double cx, cy;
   g.centroid(cx, cy);
   if (e.nx * (0.5 * (e.ax + e.bx) - cx) + e.ny * (0.5 * (e.ay + e.by) - cy) < 0.0) {

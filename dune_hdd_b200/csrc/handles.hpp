@@ -106,6 +106,7 @@ namespace hdd {
 struct FnRef {       // index into the device function table, -1 = absent
   int idx = -1;
   int order = 0;
+  int kind = 0;      // HDD_FN_*
   bool zero = false; // constant 0: contributes nothing, kernels are skipped
 };
 

@@ -14,8 +14,8 @@ void launch_fill_csr(const MeshView& m, int64_t* rowptr, int32_t* col, cudaStrea
 
 // ---- K2/K3: assembly ----------------------------------------------------------------------------------------
 // one affine part of the system matrix: values in CSR order of the owned rows
-void launch_assemble_lhs(const MeshView& m, const DevFn* factor_dev, int factor_order, int polorder, double* values,
-                         cudaStream_t s);
+void launch_assemble_lhs(const MeshView& m, const DevFn* factor_dev, int factor_kind, int factor_order, int polorder,
+                         double* values, cudaStream_t s);
 // b += L2Volume(force)
 void launch_rhs_volume(const MeshView& m, const DevFn* force_dev, int force_order, int polorder, double* b,
                        cudaStream_t s);

@@ -86,7 +86,20 @@ __device__ __forceinline__ void store_block(double* __restrict__ row0, int row_s
 }
 
 // K2.  SURVEY 8a rows a4 (GDT::LocalEvaluation::Elliptic), a5 (SWIPDG::Inner), a6 (SWIPDG::BoundaryLHS).
-template <int KIND>
+// FK = kind of the diffusion-factor part (HDD_FN_*), resolved at compile time so that constant and cell-wise data
+// cost no function evaluation per quadrature point.  An Expression is one global function: both sides of a face
+// see the same value at the same point, so it is evaluated once per point.
+template <int FK>
+__device__ __forceinline__ double factor_at(const DevFn& fn, double a_cell, double x, double y) {
+  if constexpr (FK == HDD_FN_EXPRESSION) {
+    const double v[2] = {x, y};
+    return eval_program(fn.prog, v);
+  } else {
+    return a_cell;
+  }
+}
+
+template <int KIND, int FK>
 __global__ void __launch_bounds__(kThreads)
     k_assemble_lhs(MeshView m, const DevFn* __restrict__ fnp, ElemRule vol, LineRule fr, double s_in, double s_bnd,
                    double* __restrict__ vals) {
@@ -105,6 +118,9 @@ __global__ void __launch_bounds__(kThreads)
   const int nblk = block_count<NF>(nb);
   const int rs = nblk * NL;
   double* row0 = vals + m.blk_start[k] * (NL * NL);
+  double a_self = 0.0;
+  if constexpr (FK == HDD_FN_CONSTANT) a_self = fn.value;
+  if constexpr (FK == HDD_FN_CELLWISE) a_self = __ldg(fn.cell + c);
 
   double D[NL * NL];
 #pragma unroll
@@ -115,14 +131,13 @@ __global__ void __launch_bounds__(kThreads)
     double phi[NL], gx[NL], gy[NL], x, y;
     g.basis(vol.x[q], vol.y[q], phi, gx, gy);
     g.to_global(vol.x[q], vol.y[q], x, y);
-    const double a = fn_eval(fn, c, x, y);
-    const double w = vol.w[q] * g.detj;
+    const double wa = vol.w[q] * g.detj * factor_at<FK>(fn, a_self, x, y);
 #pragma unroll
     for (int j = 0; j < NL; ++j) {
-      const double fx = a * (K[0] * gx[j] + K[1] * gy[j]);
-      const double fy = a * (K[2] * gx[j] + K[3] * gy[j]);
+      const double fx = wa * (K[0] * gx[j] + K[1] * gy[j]);
+      const double fy = wa * (K[2] * gx[j] + K[3] * gy[j]);
 #pragma unroll
-      for (int i = 0; i < NL; ++i) D[i * NL + j] += w * (fx * gx[i] + fy * gy[i]);
+      for (int i = 0; i < NL; ++i) D[i * NL + j] = fma(fx, gx[i], fma(fy, gy[i], D[i * NL + j]));
     }
   }
 
@@ -130,59 +145,73 @@ __global__ void __launch_bounds__(kThreads)
   for (int f = 0; f < NF; ++f) {
     const FaceGeo e = make_face(g, f);
     const int n = nb[f];
+    // K n (own side) and delta^- = n . K n
+    const double knx = K[0] * e.nx + K[2] * e.ny, kny = K[1] * e.nx + K[3] * e.ny;  // K^T n: (K grad phi).n = grad phi . K^T n
     const double dm = e.nx * (K[0] * e.nx + K[1] * e.ny) + e.ny * (K[2] * e.nx + K[3] * e.ny);
     if (n < 0) {
       if (m.btype && __ldg(m.btype + size_t(NF) * k + f) != 1) continue;
       // Dirichlet face: -(A grad phi_j . n) phi_i - phi_j (A grad phi_i . n) + pen phi_j phi_i
+      const double pen0 = s_bnd * dm * e.ih;
       for (int q = 0; q < fr.n; ++q) {
         const double x = e.ax + fr.x[q] * (e.bx - e.ax), y = e.ay + fr.x[q] * (e.by - e.ay);
-        double xi, eta, phi[NL], gx[NL], gy[NL], fl[NL];
+        double xi, eta, phi[NL], gx[NL], gy[NL], A[NL], B[NL];
         g.to_local(x, y, xi, eta);
         g.basis(xi, eta, phi, gx, gy);
-        const double a = fn_eval(fn, c, x, y);
-        const double pen = s_bnd * dm * a / e.h;
+        const double a = factor_at<FK>(fn, a_self, x, y);
         const double w = fr.w[q] * e.h;
+        const double wpen = w * pen0 * a, wa = w * a;
+#pragma unroll
+        for (int i = 0; i < NL; ++i) {
+          B[i] = wa * (gx[i] * knx + gy[i] * kny);  // w (A grad phi_i . n)
+          A[i] = wpen * phi[i] - B[i];
+        }
 #pragma unroll
         for (int i = 0; i < NL; ++i)
-          fl[i] = a * ((K[0] * gx[i] + K[1] * gy[i]) * e.nx + (K[2] * gx[i] + K[3] * gy[i]) * e.ny);
 #pragma unroll
-        for (int i = 0; i < NL; ++i)
-#pragma unroll
-          for (int j = 0; j < NL; ++j) D[i * NL + j] += w * (-fl[j] * phi[i] - phi[j] * fl[i] + pen * phi[j] * phi[i]);
+          for (int j = 0; j < NL; ++j) D[i * NL + j] = fma(phi[i], A[j], fma(-B[i], phi[j], D[i * NL + j]));
       }
     } else {
       G gn;
       gn.load(m.cgeo, n);
       double Kn[4];
       load_tensor(m.tensor, n, Kn);
+      const double knxp = Kn[0] * e.nx + Kn[2] * e.ny, knyp = Kn[1] * e.nx + Kn[3] * e.ny;
       const double dp = e.nx * (Kn[0] * e.nx + Kn[1] * e.ny) + e.ny * (Kn[2] * e.nx + Kn[3] * e.ny);
-      const double gamma = dp * dm / (dp + dm);
-      const double wm = dp / (dp + dm), wp = dm / (dp + dm);
+      const double isum = 1.0 / (dp + dm);
+      const double gamma = dp * dm * isum;
+      const double wm = dp * isum, wp = dm * isum;
+      const double pen0 = s_in * gamma * 0.5 * e.ih;
+      double a_nb = a_self;
+      if constexpr (FK == HDD_FN_CELLWISE) a_nb = __ldg(fn.cell + n);
       double E[NL * NL];
 #pragma unroll
       for (int t = 0; t < NL * NL; ++t) E[t] = 0.0;
       for (int q = 0; q < fr.n; ++q) {
         const double x = e.ax + fr.x[q] * (e.bx - e.ax), y = e.ay + fr.x[q] * (e.by - e.ay);
-        double xi, eta, phm[NL], php[NL], gx[NL], gy[NL], fm[NL], fp[NL];
+        double xi, eta, phm[NL], php[NL], gx[NL], gy[NL], A[NL], B[NL], Cc[NL];
+        const double am = factor_at<FK>(fn, a_self, x, y);
+        const double ap = (FK == HDD_FN_EXPRESSION) ? am : a_nb;
+        const double w = fr.w[q] * e.h;
+        const double wpen = w * pen0 * (am + ap);
+        const double wwm = w * wm * am, wwp = w * wp * ap;
         g.to_local(x, y, xi, eta);
         g.basis(xi, eta, phm, gx, gy);
-        const double am = fn_eval(fn, c, x, y), ap = fn_eval(fn, n, x, y);
 #pragma unroll
-        for (int i = 0; i < NL; ++i)
-          fm[i] = am * ((K[0] * gx[i] + K[1] * gy[i]) * e.nx + (K[2] * gx[i] + K[3] * gy[i]) * e.ny);
+        for (int i = 0; i < NL; ++i) {
+          B[i] = wwm * (gx[i] * knx + gy[i] * kny);  // w omega^- (A^- grad phi^-_i . n)
+          A[i] = wpen * phm[i] - B[i];
+        }
         gn.to_local(x, y, xi, eta);
         gn.basis(xi, eta, php, gx, gy);
 #pragma unroll
-        for (int i = 0; i < NL; ++i)
-          fp[i] = ap * ((Kn[0] * gx[i] + Kn[1] * gy[i]) * e.nx + (Kn[2] * gx[i] + Kn[3] * gy[i]) * e.ny);
-        const double pen = s_in * gamma * 0.5 * (am + ap) / e.h;
-        const double w = fr.w[q] * e.h;
+        for (int j = 0; j < NL; ++j)
+          Cc[j] = -wwp * (gx[j] * knxp + gy[j] * knyp) - wpen * php[j];  // -w omega^+ (A^+ grad phi^+_j . n) - w pen phi^+_j
 #pragma unroll
         for (int i = 0; i < NL; ++i)
 #pragma unroll
           for (int j = 0; j < NL; ++j) {
-            D[i * NL + j] += w * (-wm * fm[j] * phm[i] - wm * phm[j] * fm[i] + pen * phm[j] * phm[i]);  // en/en
-            E[i * NL + j] += w * (-wp * fp[j] * phm[i] + wm * php[j] * fm[i] - pen * php[j] * phm[i]);  // en/ne
+            D[i * NL + j] = fma(phm[i], A[j], fma(-B[i], phm[j], D[i * NL + j]));  // en/en
+            E[i * NL + j] = fma(phm[i], Cc[j], fma(B[i], php[j], E[i * NL + j]));  // en/ne
           }
       }
       store_block<NL>(row0, rs, block_slot<NF>(c, nb, n), E);
@@ -334,16 +363,31 @@ void launch_fill_csr(const MeshView& m, int64_t* rowptr, int32_t* col, cudaStrea
   HDD_CUDA(cudaGetLastError());
 }
 
-void launch_assemble_lhs(const MeshView& m, const DevFn* factor_dev, int factor_order, int polorder, double* values,
-                         cudaStream_t s) {
+template <int KIND>
+static void assemble_dispatch(int fk, int blocks, cudaStream_t s, const MeshView& m, const DevFn* fn, const ElemRule& vol,
+                              const LineRule& fr, double si, double sb, double* values) {
+  switch (fk) {
+    case HDD_FN_CONSTANT:
+      k_assemble_lhs<KIND, HDD_FN_CONSTANT><<<blocks, kThreads, 0, s>>>(m, fn, vol, fr, si, sb, values);
+      break;
+    case HDD_FN_CELLWISE:
+      k_assemble_lhs<KIND, HDD_FN_CELLWISE><<<blocks, kThreads, 0, s>>>(m, fn, vol, fr, si, sb, values);
+      break;
+    default:
+      k_assemble_lhs<KIND, HDD_FN_EXPRESSION><<<blocks, kThreads, 0, s>>>(m, fn, vol, fr, si, sb, values);
+  }
+}
+
+void launch_assemble_lhs(const MeshView& m, const DevFn* factor_dev, int factor_kind, int factor_order, int polorder,
+                         double* values, cudaStream_t s) {
   if (m.n_own == 0) return;
   const ElemRule vol = element_rule(m.kind, factor_order + 2 * (polorder - 1));
   const LineRule fr = line_rule(factor_order + 2 * polorder);
   const double si = sigma_inner(polorder), sb = sigma_boundary(polorder);
   if (m.kind == HDD_SIMPLEX2D)
-    k_assemble_lhs<HDD_SIMPLEX2D><<<grid_for(m.n_own, kThreads), kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+    assemble_dispatch<HDD_SIMPLEX2D>(factor_kind, grid_for(m.n_own, kThreads), s, m, factor_dev, vol, fr, si, sb, values);
   else
-    k_assemble_lhs<HDD_CUBE2D><<<grid_for(m.n_own, kThreads), kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+    assemble_dispatch<HDD_CUBE2D>(factor_kind, grid_for(m.n_own, kThreads), s, m, factor_dev, vol, fr, si, sb, values);
   count_launch();
   HDD_CUDA(cudaGetLastError());
 }

@@ -27,6 +27,7 @@ FnRef add_function(hdd_swipdg* h, const hdd_function& f, const char* what) {
   d.prog.n_ops = 0;
   FnRef r;
   r.order = f.order;
+  r.kind = f.kind;
   if (f.order < 0 || f.order > 12) HDD_THROW(HDD_ERR_WRONG_INPUT, what << ": unsupported order " << f.order);
   switch (f.kind) {
     case HDD_FN_CONSTANT:
@@ -97,9 +98,10 @@ void assemble_all(hdd_swipdg* h) {
   hdd_mesh* m = h->mesh;
   const MeshView v = h->view();
   cudaStream_t s = m->stream;
-  for (auto& part : h->lhs_comps) launch_assemble_lhs(v, h->fn(part.factor), part.factor.order, h->polorder, part.values.p, s);
+  for (auto& part : h->lhs_comps) launch_assemble_lhs(v, h->fn(part.factor), part.factor.kind, part.factor.order, h->polorder, part.values.p, s);
   if (h->lhs_affine)
-    launch_assemble_lhs(v, h->fn(h->lhs_affine->factor), h->lhs_affine->factor.order, h->polorder, h->lhs_affine->values.p, s);
+    launch_assemble_lhs(v, h->fn(h->lhs_affine->factor), h->lhs_affine->factor.kind, h->lhs_affine->factor.order, h->polorder,
+                        h->lhs_affine->values.p, s);
   auto do_vec = [&](VectorPart& part) {
     part.values.zero(s);
     for (const RhsTerm& t : part.terms) {
