@@ -249,8 +249,11 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
     }
 
     // ---- local vertices + incidence (vertex -> local DoFs), boundary flags
-    std::vector<int32_t> cvl(size_t(m->n_loc) * nl);
-    {
+    // (the incidence feeds the Oswald pass, which exists on simplices only; the local vertex ids also drive the
+    // halo plan of a distributed mesh)
+    const bool need_verts = !whole || kind == HDD_SIMPLEX2D;
+    std::vector<int32_t> cvl(need_verts ? size_t(m->n_loc) * nl : 0);
+    if (need_verts) {
       std::unordered_map<int32_t, int32_t> vmap;
       std::vector<int32_t> dense;
       if (whole) dense.assign(size_t(n_verts), -1);
@@ -271,7 +274,7 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
         }
       m->n_verts_loc = nvl;
     }
-    {
+    if (kind == HDD_SIMPLEX2D) {
       const int32_t nvl = m->n_verts_loc;
       std::vector<int64_t> vptr(size_t(nvl) + 1, 0);
       for (int32_t v : cvl) ++vptr[size_t(v) + 1];
@@ -345,11 +348,17 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
     if (m->n_subdomains > 1 || kind == HDD_SIMPLEX2D) {
       for (int s = m->sub_first; s < m->sub_last; ++s) {
         std::vector<std::pair<double, double>> pts;
-        // only boundary-of-subdomain vertices matter, but collecting all is O(n) and simple
+        // the farthest pair lies on the hull, whose vertices sit on faces leaving the subdomain
         for (int64_t c = m->sub_cell_offsets[size_t(s)]; c < m->sub_cell_offsets[size_t(s) + 1]; ++c)
-          for (int i = 0; i < nl; ++i) {
-            const int32_t v = cell_verts[c * nl + i];
-            pts.emplace_back(xy[2 * v], xy[2 * v + 1]);
+          for (int f = 0; f < nf; ++f) {
+            const int32_t g = cell_neigh[c * nf + f];
+            if (g >= 0 && cell_subdomain && cell_subdomain[g] == s) continue;
+            if (g >= 0 && !cell_subdomain) continue;
+            const int* fv = kind == HDD_SIMPLEX2D ? kFaceVertsSimplex[f] : kFaceVertsCube[f];
+            for (int e = 0; e < 2; ++e) {
+              const int32_t v = cell_verts[c * nl + fv[e]];
+              pts.emplace_back(xy[2 * v], xy[2 * v + 1]);
+            }
           }
         m->sub_diameter[size_t(s)] = point_set_diameter(pts);
       }

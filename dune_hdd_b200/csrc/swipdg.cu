@@ -903,3 +903,89 @@ int hdd_estimate(hdd_swipdg* h, const char* type_c, const double* u_host, const 
 }
 
 }  // extern "C"
+
+// ---- measurement ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+int hdd_kernel_bytes(hdd_swipdg* h, int which, double* bytes) {
+  return guarded([&] {
+    require_init(h);
+    const hdd_mesh* m = h->mesh;
+    const double cells = double(m->n_own), rows = double(h->n_rows), nnz = double(h->nnz);
+    const double geo = m->kind == HDD_SIMPLEX2D ? 48.0 : 32.0, rec = 4.0 * m->nf + 8.0;  // neighbour record + block offset
+    double b = 0.0;
+    switch (which) {
+      case 0: b = 8.0 * nnz + rec * cells + 8.0 * rows /* read p */ + 8.0 * rows /* write q */; break;
+      case 1: b = 7.0 * 8.0 * rows; break;  // read x,p,q,r,dinv; write x,r
+      case 2: b = 4.0 * 8.0 * rows; break;  // read r,dinv,p; write p
+      case 3: b = 8.0 * nnz + (geo + rec) * cells; break;
+      default: HDD_THROW(HDD_ERR_WRONG_INPUT, "unknown kernel id " << which);
+    }
+    if (bytes) *bytes = b;
+  });
+}
+
+int hdd_profile_kernel(hdd_swipdg* h, int which, int reps, double* avg_seconds) {
+  return guarded([&] {
+    require_init(h);
+    if (reps < 1) HDD_THROW(HDD_ERR_WRONG_INPUT, "reps must be positive");
+    hdd_mesh* m = h->mesh;
+    m->set_device();
+    cudaStream_t s = m->stream;
+    if (which != 3 && !h->x.p) HDD_THROW(HDD_ERR_USING_THIS_WRONG, "call hdd_solve once before profiling the CG kernels");
+    const MeshView v = h->view();
+    CgBuffers c{};
+    c.values = h->lhs_comps.empty() ? h->lhs_affine->values.p : h->frozen.p;
+    c.dinv = h->dinv.p; c.b = h->b.p; c.x = h->x.p; c.r = h->r.p; c.p = h->p.p; c.q = h->q.p;
+    c.partial = h->partial.p; c.sc = h->sc.p;
+    if (which != 3) {
+      // un-latch the convergence flag of parity 0 so that the kernels do their work; the vectors are scratch now
+      CgScalars sc = *h->sc_host;
+      sc.done[0] = 0; sc.done[1] = 0; sc.rz[0] = 1.0; sc.red[0] = 1.0; sc.red[1] = 1.0; sc.max_it = 1 << 30;
+      HDD_CUDA(cudaMemcpyAsync(h->sc.p, &sc, sizeof(sc), cudaMemcpyHostToDevice, s));
+      h->have_solution = false;
+    }
+    auto launch = [&]() {
+      switch (which) {
+        case 0: launch_cg_spmv(v, c, 0, s); break;
+        case 1: launch_cg_update(v, c, 0, s); break;
+        case 2: launch_cg_direction(v, c, 0, s); break;
+        case 3: {
+          MatrixPart& part = h->lhs_affine ? *h->lhs_affine : h->lhs_comps[0];
+          launch_assemble_lhs(v, h->fn(part.factor), part.factor.kind, part.factor.order, h->polorder, part.values.p, s);
+          break;
+        }
+        default: HDD_THROW(HDD_ERR_WRONG_INPUT, "unknown kernel id " << which);
+      }
+      if (which == 2) {  // the direction kernel flips the parity state; keep parity 0 alive
+        CgScalars sc = *h->sc_host;
+        (void)sc;
+      }
+    };
+    for (int k = 0; k < 3; ++k) launch();
+    cudaEvent_t e0, e1;
+    HDD_CUDA(cudaEventCreate(&e0));
+    HDD_CUDA(cudaEventCreate(&e1));
+    HDD_CUDA(cudaEventRecord(e0, s));
+    for (int k = 0; k < reps; ++k) launch();
+    HDD_CUDA(cudaEventRecord(e1, s));
+    HDD_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    HDD_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (avg_seconds) *avg_seconds = double(ms) * 1e-3 / reps;
+  });
+}
+
+int hdd_expression_evaluate(const char* expression, const char* variable, const double* values, int n, double* out) {
+  return guarded([&] {
+    if (!expression || !variable || !out) HDD_THROW(HDD_ERR_WRONG_INPUT, "NULL argument");
+    const Program p = compile_expression(expression, variable);
+    double v[4] = {0, 0, 0, 0};
+    for (int k = 0; k < n && k < 4; ++k) v[k] = values[k];
+    *out = eval_program(p, v);
+  });
+}
+
+}  // extern "C"

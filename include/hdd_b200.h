@@ -223,6 +223,19 @@ int hdd_indicators(hdd_swipdg* h, const double* u_host, const hdd_parameters* pa
 int hdd_comm_unique_id(void* id128);
 int hdd_comm_init(hdd_mesh* mesh, const void* id128, int rank, int world_size);
 
+/* ---- measurement ------------------------------------------------------------------------------------------------ */
+/* Times `reps` back-to-back launches of one hot kernel on the handle's stream with CUDA events (after 3 warm-up
+ * launches) and returns the average launch duration: which = 0 the CG SpMV kernel (q = A p with the fused p.Ap
+ * partial dot), 1 the fused CG update kernel, 2 the CG direction kernel, 3 the system-matrix assembly kernel of the
+ * first affine part.  Needs a previous hdd_solve (CG workspace).  Used by bench.py for the roofline numbers. */
+int hdd_profile_kernel(hdd_swipdg* h, int which, int reps, double* avg_seconds);
+/* algorithmic HBM bytes of one launch of that kernel (DESIGN.md "Kernels and rooflines") */
+int hdd_kernel_bytes(hdd_swipdg* h, int which, double* bytes);
+
+/* ParameterFunctional / Expression evaluation on the host (no device needed): value of `expression` in the vector
+ * variable `variable` ("x" or "mu") at `values[0..n)`.  HDD_ERR_WRONG_INPUT on a syntax error. */
+int hdd_expression_evaluate(const char* expression, const char* variable, const double* values, int n, double* out);
+
 /* ---- counters --------------------------------------------------------------------------------------------------- */
 /* number of kernels this library launched since process start (bench.py's gpu_launches) */
 int64_t hdd_kernel_launches(void);
