@@ -148,14 +148,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        uid = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            buf = (C.c_ubyte * 128)()
-            capi.check(capi.lib().hdd_comm_unique_id(buf))
-            uid = torch.tensor(list(buf), dtype=torch.uint8)
-        uid = uid.cuda()
-        dist.broadcast(uid, 0)
-        comm = (bytes(uid.cpu().tolist()), rank, world)
+        comm = hdd.parallel.init_comm(rank, world, local_rank)
 
     def barrier():
         torch.cuda.synchronize()
@@ -169,10 +162,8 @@ def main():
     grid = hdd.grids.cube(n, partitions=parts)
     t_grid = time.perf_counter() - t0
     problem = hdd.problems.ESV2007()
-    off = grid.subdomain_cell_offsets()
-    n_sub = len(off) - 1
-    per = [n_sub * r // world for r in range(world + 1)]
-    cell_range = (int(off[per[rank]]), int(off[per[rank + 1]]))
+    roff = hdd.parallel.rank_cell_offsets(grid, world)
+    cell_range = (int(roff[rank]), int(roff[rank + 1]))
     options = {"type": "cg.diagonal", "precision": PRECISION, "max_iter": 200000}
 
     def make():

@@ -9,6 +9,7 @@
 #include <unordered_map>
 
 #include "handles.hpp"
+#include "partition.hpp"
 
 namespace hdd {
 
@@ -176,17 +177,7 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
     // ---- halo: every non-owned cell sharing a vertex with an owned cell (superset of the face neighbours the
     // SpMV needs; the Oswald interpolation needs all cells around a vertex)
     std::vector<int32_t> halo_lo, halo_hi;
-    if (!whole) {
-      std::vector<uint8_t> vmark(size_t(n_verts), 0);
-      for (int64_t c = cell_begin; c < cell_end; ++c)
-        for (int i = 0; i < nl; ++i) vmark[size_t(cell_verts[c * nl + i])] = 1;
-      for (int64_t c = 0; c < n_cells; ++c) {
-        if (c >= cell_begin && c < cell_end) continue;
-        bool touch = false;
-        for (int i = 0; i < nl; ++i) touch |= vmark[size_t(cell_verts[c * nl + i])] != 0;
-        if (touch) (c < cell_begin ? halo_lo : halo_hi).push_back(int32_t(c));
-      }
-    }
+    compute_halo(nl, n_cells, n_verts, cell_verts, cell_begin, cell_end, halo_lo, halo_hi);
     m->own0 = int32_t(halo_lo.size());
     m->n_own = int32_t(n_own);
     m->n_loc = int32_t(halo_lo.size() + n_own + halo_hi.size());
@@ -454,15 +445,14 @@ int hdd_comm_init(hdd_mesh* m, const void* id128, int rank, int world_size) {
     // vector.  Send: owned cells sharing a vertex with a halo cell owned by that peer, sorted by global id - this is
     // exactly that peer's receive range, no index exchange needed.
     const int nl = m->nl;
-    auto owner_of = [&](int64_t g) {
-      return int(std::upper_bound(m->rank_cell_offsets.begin(), m->rank_cell_offsets.end(), g) -
-                 m->rank_cell_offsets.begin()) - 1;
-    };
     std::map<int, HaloPeer> peers;
-    std::map<int, std::vector<int32_t>> send_cells;
+    std::vector<int32_t> halo_cells;
+    std::vector<int> halo_owner;
     for (int32_t lc = 0; lc < m->n_loc; ++lc) {
       if (lc >= m->own0 && lc < m->own0 + m->n_own) continue;
-      const int r = owner_of(m->cgid[size_t(lc)]);
+      const int r = owner_of(m->rank_cell_offsets, m->cgid[size_t(lc)]);
+      halo_cells.push_back(lc);
+      halo_owner.push_back(r);
       auto it = peers.find(r);
       if (it == peers.end()) {
         HaloPeer p{};
@@ -472,20 +462,9 @@ int hdd_comm_init(hdd_mesh* m, const void* id128, int rank, int world_size) {
       }
       it->second.recv_count += nl;
     }
-    for (auto& kv : peers) {
-      std::vector<uint8_t> vmark(size_t(m->n_verts_loc), 0);
-      for (int32_t lc = 0; lc < m->n_loc; ++lc) {
-        if (lc >= m->own0 && lc < m->own0 + m->n_own) continue;
-        if (owner_of(m->cgid[size_t(lc)]) != kv.first) continue;
-        for (int i = 0; i < nl; ++i) vmark[size_t(m->h_cell_verts_loc[size_t(lc) * nl + i])] = 1;
-      }
-      auto& sc = send_cells[kv.first];
-      for (int32_t lc = m->own0; lc < m->own0 + m->n_own; ++lc) {
-        bool touch = false;
-        for (int i = 0; i < nl; ++i) touch |= vmark[size_t(m->h_cell_verts_loc[size_t(lc) * nl + i])] != 0;
-        if (touch) sc.push_back(lc);
-      }
-    }
+    std::map<int, std::vector<int32_t>> send_cells;
+    compute_send_cells(nl, m->n_verts_loc, m->h_cell_verts_loc.data(), m->own0, int64_t(m->own0) + m->n_own, halo_cells,
+                       halo_owner, send_cells);
     std::vector<int32_t> idx;
     m->peers.clear();
     for (auto& kv : peers) {

@@ -1,0 +1,98 @@
+// Host-side partition logic of the multi-GPU path (no device needed, so it is testable on a CPU-only box):
+// each rank owns a contiguous range of subdomain-major cells; its halo is every other cell sharing a vertex with an
+// owned cell (the face neighbours the SpMV needs plus the vertex neighbours the Oswald interpolation needs).
+// Because ranks own contiguous ranges and halos are sorted by global id, a rank's halo is grouped by owner and the
+// send list for a peer - owned cells sharing a vertex with a halo cell owned by that peer, sorted by global id - is
+// exactly that peer's receive range.  No index exchange is ever needed.
+#include "partition.hpp"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+namespace hdd {
+
+void compute_halo(int nl, int64_t n_cells, int64_t n_verts, const int32_t* cell_verts, int64_t cell_begin,
+                  int64_t cell_end, std::vector<int32_t>& halo_lo, std::vector<int32_t>& halo_hi) {
+  halo_lo.clear();
+  halo_hi.clear();
+  if (cell_begin == 0 && cell_end == n_cells) return;
+  std::vector<uint8_t> vmark(size_t(n_verts), 0);
+  for (int64_t c = cell_begin; c < cell_end; ++c)
+    for (int i = 0; i < nl; ++i) vmark[size_t(cell_verts[c * nl + i])] = 1;
+  for (int64_t c = 0; c < n_cells; ++c) {
+    if (c >= cell_begin && c < cell_end) continue;
+    bool touch = false;
+    for (int i = 0; i < nl; ++i) touch |= vmark[size_t(cell_verts[c * nl + i])] != 0;
+    if (touch) (c < cell_begin ? halo_lo : halo_hi).push_back(int32_t(c));
+  }
+}
+
+int owner_of(const std::vector<int64_t>& rank_cell_offsets, int64_t g) {
+  return int(std::upper_bound(rank_cell_offsets.begin(), rank_cell_offsets.end(), g) - rank_cell_offsets.begin()) - 1;
+}
+
+void compute_send_cells(int nl, int64_t n_verts, const int32_t* cell_verts, int64_t own_begin, int64_t own_end,
+                        const std::vector<int32_t>& halo_cells, const std::vector<int>& halo_owner,
+                        std::map<int, std::vector<int32_t>>& send_cells) {
+  send_cells.clear();
+  std::map<int, std::vector<int32_t>> halo_by_owner;
+  for (size_t k = 0; k < halo_cells.size(); ++k) halo_by_owner[halo_owner[k]].push_back(halo_cells[k]);
+  for (auto& kv : halo_by_owner) {
+    std::vector<uint8_t> vmark(size_t(n_verts), 0);
+    for (int32_t g : kv.second)
+      for (int i = 0; i < nl; ++i) vmark[size_t(cell_verts[int64_t(g) * nl + i])] = 1;
+    std::vector<int32_t>& out = send_cells[kv.first];
+    for (int64_t c = own_begin; c < own_end; ++c) {
+      bool touch = false;
+      for (int i = 0; i < nl; ++i) touch |= vmark[size_t(cell_verts[c * nl + i])] != 0;
+      if (touch) out.push_back(int32_t(c));
+    }
+  }
+}
+
+}  // namespace hdd
+
+extern "C" {
+
+int hdd_partition_plan(int kind, int64_t n_cells, int64_t n_verts, const int32_t* cell_verts, int world_size,
+                       const int64_t* rank_cell_offsets, int rank, int32_t** halo_cells, int64_t* n_halo,
+                       int32_t** send_cells, int64_t* send_offsets) {
+  return hdd::guarded([&] {
+    if (kind != HDD_SIMPLEX2D && kind != HDD_CUBE2D) HDD_THROW(HDD_ERR_WRONG_INPUT, "unknown element kind " << kind);
+    if (!cell_verts || !rank_cell_offsets || !halo_cells || !n_halo || !send_cells || !send_offsets)
+      HDD_THROW(HDD_ERR_WRONG_INPUT, "NULL argument");
+    if (world_size < 1 || rank < 0 || rank >= world_size) HDD_THROW(HDD_ERR_WRONG_INPUT, "bad rank / world size");
+    std::vector<int64_t> off(rank_cell_offsets, rank_cell_offsets + world_size + 1);
+    if (off.front() != 0 || off.back() != n_cells || !std::is_sorted(off.begin(), off.end()))
+      HDD_THROW(HDD_ERR_WRONG_INPUT, "ranks must own consecutive, gap-free cell ranges in rank order");
+    const int nl = kind == HDD_SIMPLEX2D ? 3 : 4;
+    std::vector<int32_t> lo, hi;
+    hdd::compute_halo(nl, n_cells, n_verts, cell_verts, off[size_t(rank)], off[size_t(rank) + 1], lo, hi);
+    std::vector<int32_t> halo(lo);
+    halo.insert(halo.end(), hi.begin(), hi.end());
+    std::vector<int> owner(halo.size());
+    for (size_t k = 0; k < halo.size(); ++k) owner[k] = hdd::owner_of(off, halo[k]);
+    std::map<int, std::vector<int32_t>> send;
+    hdd::compute_send_cells(nl, n_verts, cell_verts, off[size_t(rank)], off[size_t(rank) + 1], halo, owner, send);
+    *n_halo = int64_t(halo.size());
+    *halo_cells = static_cast<int32_t*>(std::malloc(std::max<size_t>(halo.size(), 1) * sizeof(int32_t)));
+    if (!halo.empty()) std::memcpy(*halo_cells, halo.data(), halo.size() * sizeof(int32_t));
+    std::vector<int32_t> flat;
+    send_offsets[0] = 0;
+    for (int r = 0; r < world_size; ++r) {
+      auto it = send.find(r);
+      if (it != send.end()) flat.insert(flat.end(), it->second.begin(), it->second.end());
+      send_offsets[r + 1] = int64_t(flat.size());
+    }
+    *send_cells = static_cast<int32_t*>(std::malloc(std::max<size_t>(flat.size(), 1) * sizeof(int32_t)));
+    if (!flat.empty()) std::memcpy(*send_cells, flat.data(), flat.size() * sizeof(int32_t));
+  });
+}
+
+int hdd_free(void* p) {
+  std::free(p);
+  return HDD_OK;
+}
+
+}  // extern "C"

@@ -222,6 +222,17 @@ int hdd_indicators(hdd_swipdg* h, const double* u_host, const hdd_parameters* pa
  * coupling-face halo exchange of the CG direction and the dot-product all-reduces. */
 int hdd_comm_unique_id(void* id128);
 int hdd_comm_init(hdd_mesh* mesh, const void* id128, int rank, int world_size);
+/* The host-side partition plan hdd_mesh_create / hdd_comm_init build for `rank`, without touching a device (used by
+ * the CPU tests of the N > 1 path and by hosts that want to inspect the decomposition): ranks own the consecutive
+ * cell ranges rank_cell_offsets[r] .. rank_cell_offsets[r+1] (world_size+1 entries, whole subdomains).
+ *   halo_cells   sorted global ids of every non-owned cell sharing a vertex with an owned cell (malloc'ed)
+ *   send_cells   owned cells (global ids, sorted) whose DoFs peer r keeps in its halo, CSR by peer through
+ *                send_offsets[world_size+1] (caller provided); equals peer r's halo cells owned by `rank`
+ * Release both arrays with hdd_free. */
+int hdd_partition_plan(int kind, int64_t n_cells, int64_t n_verts, const int32_t* cell_verts, int world_size,
+                       const int64_t* rank_cell_offsets, int rank, int32_t** halo_cells, int64_t* n_halo,
+                       int32_t** send_cells, int64_t* send_offsets);
+int hdd_free(void* p);
 
 /* ---- measurement ------------------------------------------------------------------------------------------------ */
 /* Times `reps` back-to-back launches of one hot kernel on the handle's stream with CUDA events (after 3 warm-up

@@ -1,0 +1,158 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, host-side logic (grid providers,
+expression compiler, partition plan, Python mirror of the reference API) behaves - no compute calls without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import dune_hdd_b200 as hdd
+from dune_hdd_b200 import capi, grids, parallel, problems
+from oracle import oracle as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_symbol_the_header_declares():
+    L = capi.lib()
+    header = open(os.path.join(ROOT, "include", "hdd_b200.h")).read()
+    declared = set(re.findall(r"\b(hdd_[a-z0-9_]+)\s*\(", header))
+    declared -= {"hdd_status"}
+    assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
+    for name in capi.SYMBOLS:
+        assert hasattr(L, name), name
+    assert b"sm_100a" in L.hdd_version()
+
+
+def test_no_cpu_fallback_without_a_device():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    g = grids.simplex(2)
+    with pytest.raises(hdd.discretizations.device_error):
+        hdd.SWIPDG(g, problems.ESV2007())
+
+
+def _tri_set(xy, cv):
+    pts = np.round(xy[cv] * 4096).astype(np.int64)
+    return {tuple(sorted(map(tuple, t))) for t in pts}
+
+
+@pytest.mark.parametrize("level", [0, 1, 2])
+def test_simplex_provider_equals_recursive_bisection(level):
+    """the closed-form union-jack generator produces exactly the triangles of ALU-style longest-edge bisection"""
+    g = grids.simplex(4 * 2 ** level)
+    m = o.mesh_bisect(4, -1.0, 1.0, 2 + 2 * level)
+    assert g.n_cells == m.nc == 128 * 4 ** level and g.n_verts == m.nv
+    assert _tri_set(g.xy, g.cell_verts) == _tri_set(m.xy, m.cv)
+
+
+@pytest.mark.parametrize("maker,n", [(grids.simplex, 4), (grids.cube, 8), (grids.simplex, 1), (grids.cube, 1)])
+@pytest.mark.parametrize("parts", [(1, 1), (2, 2), (4, 4), (8, 8)])
+def test_grid_neighbours_orientation_and_subdomains(maker, n, parts):
+    if n == 1 and parts != (1, 1):
+        pytest.skip("partition finer than the grid")
+    g = maker(n, partitions=parts)
+    nl = g.n_loc
+    fv = [(0, 1), (0, 2), (1, 2)] if g.kind == 0 else [(0, 2), (1, 3), (0, 1), (2, 3)]
+    for c in range(g.n_cells):
+        for f in range(nl):
+            nb = g.cell_neigh[c, f]
+            edge = {g.cell_verts[c, fv[f][0]], g.cell_verts[c, fv[f][1]]}
+            if nb >= 0:
+                assert c in g.cell_neigh[nb]  # symmetric
+                assert edge <= set(g.cell_verts[nb])  # shares exactly this edge
+            else:
+                p = g.xy[list(edge)]
+                assert np.any(np.all(np.abs(np.abs(p) - 1.0) < 1e-14, axis=0))  # both ends on the same domain side
+    if g.kind == 0:
+        a, b, c_ = (g.xy[g.cell_verts[:, k]] for k in range(3))
+        det = (b[:, 0] - a[:, 0]) * (c_[:, 1] - a[:, 1]) - (c_[:, 0] - a[:, 0]) * (b[:, 1] - a[:, 1])
+        assert np.all(det > 0)
+    sub = g.cell_subdomain
+    assert np.all(np.diff(sub) >= 0) and sub[0] == 0  # subdomain-major numbering
+    assert g.n_subdomains == parts[0] * parts[1]
+    cen = g.centers()
+    sx = np.clip(((cen[:, 0] + 1) / 2 * parts[0]).astype(int), 0, parts[0] - 1)
+    sy = np.clip(((cen[:, 1] + 1) / 2 * parts[1]).astype(int), 0, parts[1] - 1)
+    if n > 1:
+        assert np.array_equal(sub, sy * parts[0] + sx)
+
+
+def test_cube_provider_matches_oracle_numbering():
+    g = grids.cube(5, 3, (0.0, 0.0), (5.0, 1.0))
+    m = o.mesh_cube(5, 3, 0.0, 5.0, 0.0, 1.0)
+    assert np.array_equal(g.cell_verts, m.cv) and np.array_equal(g.cell_neigh, m.nb) and np.allclose(g.xy, m.xy)
+
+
+def _eval(expr, var, values):
+    out = C.c_double()
+    v = np.asarray(values, dtype=np.float64)
+    capi.check(capi.lib().hdd_expression_evaluate(expr.encode(), var.encode(), capi.ptr(v), len(v), C.byref(out)))
+    return out.value
+
+
+def test_expression_compiler():
+    x = [0.3, -0.7]
+    assert _eval("1+0.75*(sin(4*pi*(x[0]+0.5*x[1])))", "x", x) == pytest.approx(1 + 0.75 * np.sin(4 * np.pi * (0.3 - 0.35)), abs=1e-15)
+    f = o.esv2007_force()
+    assert _eval(problems.ESV2007_FORCE, "x", x) == pytest.approx(o.lib().or_fn_eval(C.byref(f), 0, C.c_double(0.3), C.c_double(-0.7)), rel=1e-15)
+    assert _eval("mu", "mu", [0.1]) == 0.1 and _eval("-1.0*mu", "mu", [0.5]) == -0.5
+    assert _eval("(mu)*(-1.0*mu)", "mu", [2.0]) == -4.0  # product coefficients of discretizations/swipdg.hh:319-321
+    assert _eval("2^3^2", "x", x) == 512.0 and _eval("-2^2", "x", x) == -4.0 and _eval("1-2-3", "x", x) == -4.0
+    assert _eval("pow(x[0],2)+sqrt(abs(x[1]))+exp(0)+min(1,2)*max(3,4)", "x", x) == pytest.approx(0.09 + np.sqrt(0.7) + 1 + 4)
+    for bad in ("cos(x[0]", "1+", "foo(1)", "x[7]", "1 2", ""):
+        with pytest.raises(capi.HddError) as e:
+            _eval(bad, "x", x)
+        assert e.value.status == capi.HDD_ERR_WRONG_INPUT
+
+
+def test_problem_and_api_mirror():
+    p = problems.OS2014ParametricESV2007()
+    assert p.parametric() and p.parameter_type() == {"mu": 1}
+    assert p.diffusion_factor.num_components() == 1 and p.diffusion_factor.coefficients == ["mu"]
+    assert not problems.ESV2007().parametric()
+    c = p.to_c()
+    assert c.diffusion_factor.n_components == 1 and c.parameter_size == 1
+    assert c.diffusion_factor.coefficients[0] == b"mu"
+    g = grids.cube(100, 20, (0, 0), (5, 1))
+    s = problems.Spe10Model1(g)
+    k = s.diffusion_tensor.reshape(-1, 4)
+    assert k[:, 0].min() >= problems.SPE10_MIN and k[:, 0].max() <= problems.SPE10_MAX and np.all(k[:, 1] == 0)
+    f = s.force.affine.cell_values
+    assert set(np.unique(f)) == {-1000.0, 0.0, 2000.0} and (f == 2000).sum() == 9 and (f == -1000).sum() == 18
+    assert hdd.estimators.ESV2007_TYPES[4] == "eta_ESV2007" and "eta_OS2014_*" in hdd.estimators.OS2014_TYPES
+    tc = hdd.testcases.ESV2007Multiscale((8, 8))
+    assert tc.partitioning() == "[8 8 1]" and tc.level_grid(0).n_cells == 128 and tc.reference_grid().n_cells == 32768
+
+
+@pytest.mark.parametrize("maker,n,world", [(grids.simplex, 8, 2), (grids.simplex, 8, 4), (grids.cube, 16, 3), (grids.cube, 16, 8)])
+def test_partition_plan_is_consistent_between_ranks(maker, n, world):
+    g = maker(n, partitions=(8, 8))
+    off = parallel.rank_cell_offsets(g, world)
+    assert off[0] == 0 and off[-1] == g.n_cells
+    plans = [parallel.partition_plan(g, world, r) for r in range(world)]
+    owner = np.searchsorted(off, np.arange(g.n_cells), side="right") - 1
+    # vertex adjacency, independently with numpy
+    v2c = [[] for _ in range(g.n_verts)]
+    for c in range(g.n_cells):
+        for v in g.cell_verts[c]:
+            v2c[v].append(c)
+    for r in range(world):
+        halo, send = plans[r]
+        own = set(range(off[r], off[r + 1]))
+        expect = set()
+        for c in own:
+            for v in g.cell_verts[c]:
+                expect.update(v2c[v])
+        expect -= own
+        assert list(halo) == sorted(expect)
+        face_nb = set(g.cell_neigh[off[r]:off[r + 1]].ravel()) - own - {-1}
+        assert face_nb <= set(halo)  # everything the SpMV needs is in the halo
+        for peer, cells in send.items():
+            peer_halo = plans[peer][0]
+            assert np.array_equal(cells, peer_halo[owner[peer_halo] == r])  # send list == the peer's receive range

@@ -1,0 +1,156 @@
+"""Pins the CPU oracle against every golden the reference's own tests hold for this path and that is reproducible
+offline: ESV2007 on ALU simplices and on SGrid, the block / OS2014 combinations at mu = 1.
+All goldens carry 3 significant digits."""
+import numpy as np
+import pytest
+
+from oracle import oracle as o
+from tests.helpers import direct_solve
+
+
+def digits3(x, golden, slack=0.006):
+    return abs(x - golden) <= slack * abs(golden)
+
+
+# test/linearelliptic-swipdg-expectations_esv2007_2daluconform.cxx:32-57
+ALU = {"L2": [1.83e-02, 4.53e-03, 1.12e-03, 2.78e-04], "H1_semi": [3.28e-01, 1.62e-01, 8.04e-02, 4.01e-02],
+       "energy": [3.28e-01, 1.62e-01, 8.04e-02, 4.01e-02], "eta_NC": [1.66e-1, 7.89e-2, 3.91e-2, 1.95e-2],
+       "eta_R": [7.23e-2, 1.82e-2, 4.54e-3, 1.14e-3], "eta_DF": [3.55e-1, 1.76e-1, 8.73e-2, 4.35e-2],
+       "eta": [4.49e-01, 2.07e-01, 9.91e-02, 4.85e-02], "eff": [1.37, 1.28, 1.23, 1.21],
+       "eta_alt": [5.93e-01, 2.73e-01, 1.31e-01, 6.42e-02], "eff_alt": [1.81, 1.69, 1.63, 1.60]}
+# test/linearelliptic-swipdg-expectations_esv2007_2dsgrid.cxx:31-36
+SGRID = {"L2": [1.13e-02, 2.90e-03, 7.41e-04, 1.88e-04], "H1_semi": [2.77e-01, 1.39e-01, 6.98e-02, 3.50e-02]}
+
+
+def solve_esv(mesh, factor=None):
+    rp, col = o.pattern(mesh)
+    A = o.assemble_lhs(mesh, factor or o.const(1.0), None, rp, col)
+    b = o.assemble_rhs(mesh, o.esv2007_force())
+    return direct_solve(rp, col, A, b), (rp, col, A, b)
+
+
+@pytest.mark.parametrize("level", [0, 1, 2, 3])
+def test_esv2007_alu_goldens(level):
+    m = o.mesh_bisect(4, -1.0, 1.0, 2 + 2 * level)
+    assert m.nc == 128 * 4 ** level
+    u, _ = solve_esv(m)
+    err = o.error_norms(m, u, o.esv2007_exact())
+    for k in ("L2", "H1_semi", "energy"):
+        assert digits3(err[k], ALU[k][level]), (k, err[k])
+    ind = o.indicators(m, u, o.esv2007_force(), o.const(1.0))
+    e_nc, e_r, e_df = (np.sqrt(ind[k].sum()) for k in ("nc2", "r2", "df2"))
+    eta = np.sqrt((ind["nc2"] + (np.sqrt(ind["r2"]) + np.sqrt(ind["df2"])) ** 2).sum())
+    assert digits3(e_nc, ALU["eta_NC"][level]) and digits3(e_r, ALU["eta_R"][level]) and digits3(e_df, ALU["eta_DF"][level])
+    assert digits3(eta, ALU["eta"][level]) and digits3(eta / err["energy"], ALU["eff"][level], 0.01)
+    assert digits3(e_nc + e_r + e_df, ALU["eta_alt"][level])
+    assert digits3((e_nc + e_r + e_df) / err["energy"], ALU["eff_alt"][level], 0.01)
+    # eta_R* equals eta_R up to quadrature: the scheme is locally conservative
+    assert abs(np.sqrt(ind["rstar2"].sum()) - e_r) <= 1e-6 * e_r
+
+
+@pytest.mark.parametrize("level", [0, 1, 2, 3])
+def test_esv2007_sgrid_goldens(level):
+    n = 8 * 2 ** level
+    m = o.mesh_cube(n, n, -1.0, 1.0, -1.0, 1.0)
+    u, _ = solve_esv(m)
+    err = o.error_norms(m, u, o.esv2007_exact(), order=7)
+    assert digits3(err["L2"], SGRID["L2"][level]) and digits3(err["H1_semi"], SGRID["H1_semi"][level])
+
+
+def test_q1_volume_term_is_under_integrated_like_the_reference():
+    """exact Q1 integration would give L2 1.50e-2 / H1 2.52e-1 at n = 8 instead of the goldens."""
+    m = o.mesh_cube(8, 8, -1.0, 1.0, -1.0, 1.0)
+    rp, col = o.pattern(m)
+    A = o.assemble_lhs(m, o.const(1.0), None, rp, col)
+    # the midpoint rule makes the bilinear "hourglass" mode invisible to the volume term: entry (0,3) of the
+    # diagonal block of an interior cell has no volume contribution of the xi*eta cross term
+    u, _ = solve_esv(m)
+    err = o.error_norms(m, u, o.esv2007_exact(), order=7)
+    assert abs(err["L2"] - 1.129e-2) < 2e-5 and abs(err["H1_semi"] - 2.770e-1) < 2e-4
+
+
+# test/linearelliptic-block-swipdg-expectations_esv2007_2daluconform.cxx:35-134 (level 0, 1)
+BLOCK = {1: {"eta_R_OS2014": [5.79e-01, 2.90e-01], "eta_OS2014": [1.10e+00, 5.45e-01], "eff": [3.35, 3.37]},
+         2: {"eta_R_OS2014": [2.89e-01, 1.45e-01], "eta_OS2014": [8.10e-01, 4.00e-01], "eff": [2.47, 2.47]},
+         4: {"eta_R_OS2014": [1.45e-01, 7.26e-02], "eta_OS2014": [6.65e-01, 3.27e-01], "eff": [2.03, 2.02]},
+         8: {"eta_R_OS2014": [7.23e-02, 3.63e-02], "eta_OS2014": [5.93e-01, 2.91e-01], "eff": [1.81, 1.80]}}
+
+
+def subdomain_eta_r(mesh, res2, amin, k):
+    """eta_R_OS2014 on the [k k 1] partition of [-1,1]^2 (estimators/block-swipdg.hh:209-309)"""
+    c = mesh.xy[mesh.cv].mean(axis=1)
+    sx = np.clip(((c[:, 0] + 1.0) / 2.0 * k).astype(int), 0, k - 1)
+    sy = np.clip(((c[:, 1] + 1.0) / 2.0 * k).astype(int), 0, k - 1)
+    sub = sy * k + sx
+    diam = np.sqrt(2.0) * 2.0 / k  # square subdomain of side 2/k
+    tot = 0.0
+    for s in range(k * k):
+        sel = sub == s
+        tot += diam ** 2 / np.pi ** 2 / amin[sel].min() * res2[sel].sum()
+    return np.sqrt(tot)
+
+
+@pytest.mark.parametrize("k", [1, 2, 4, 8])
+@pytest.mark.parametrize("level", [0, 1])
+def test_block_esv2007_goldens(k, level):
+    m = o.mesh_bisect(4, -1.0, 1.0, 2 + 2 * level)
+    u, _ = solve_esv(m)
+    ind = o.indicators(m, u, o.esv2007_force(), o.const(1.0))
+    e_r = subdomain_eta_r(m, ind["res2"], ind["amin"], k)
+    e_nc, e_df = np.sqrt(ind["nc2"].sum()), np.sqrt(ind["df2"].sum())
+    assert digits3(e_r, BLOCK[k]["eta_R_OS2014"][level])
+    assert digits3(e_nc + e_r + e_df, BLOCK[k]["eta_OS2014"][level])
+    err = o.error_norms(m, u, o.esv2007_exact())
+    assert digits3((e_nc + e_r + e_df) / err["energy"], BLOCK[k]["eff"][level], 0.01)
+
+
+@pytest.mark.parametrize("level", [0, 1])
+def test_os2014_parametric_goldens_mu1(level):
+    """test/linearelliptic-block-swipdg-expectations_os2014_2daluconform.cxx:170-212, [4 4 1], solve at mu = 1."""
+    m = o.mesh_bisect(4, -1.0, 1.0, 2 + 2 * level)
+    u, _ = solve_esv(m, o.os2014_factor(1.0))
+    gold = {(1.0, 1.0): {"eta_DF": [3.55e-1, 1.76e-1], "eta": [7.74e-01, 3.82e-01]},
+            (1.0, 0.1): {"eta_DF": [1.36, 1.33], "eta_DF_star": [4.13e-01, 2.05e-01], "eta_star": [5.50e-01, 2.71e-01]}}
+    for (mu, mu_hat), g in gold.items():
+        ind = o.indicators(m, u, o.esv2007_force(), o.os2014_factor(mu), a_hat=o.os2014_factor(mu_hat),
+                           a_bar=o.os2014_factor(mu), a_min=o.os2014_factor(0.1), a_max=o.os2014_factor(1.0))
+        e_nc, e_df, e_dfs = (np.sqrt(ind[k].sum()) for k in ("nc2", "df2", "dfstar2"))
+        e_r = subdomain_eta_r(m, ind["res2"], ind["amin"], 4)
+        e_rs = subdomain_eta_r(m, ind["resstar2"], ind["amin"], 4)
+        alpha_hat = gamma_hat = mu / mu_hat  # single component: alpha = gamma = theta(mu)/theta(mu_hat)
+        assert abs(e_df - g["eta_DF"][level]) <= 0.012 * g["eta_DF"][level]
+        if "eta" in g:
+            eta = e_nc + e_r + max(np.sqrt(gamma_hat), 1 / np.sqrt(alpha_hat)) * e_df
+            assert digits3(eta, g["eta"][level])
+        if "eta_DF_star" in g:
+            assert digits3(e_dfs, g["eta_DF_star"][level])
+            eta_star = e_nc + e_rs + e_dfs / np.sqrt(alpha_hat)
+            assert digits3(eta_star, g["eta_star"][level])
+    # eta_R_OS2014(parametric) = eta_R_OS2014(ESV2007) / sqrt(min a(mu_min)) = 0.145 / sqrt(0.325) = 0.254
+    if level == 0:
+        assert digits3(e_r, 0.254, 0.01)
+
+
+def test_quadrature_rules_are_exact():
+    for order in range(0, 11):
+        x, y, w = o.element_rule(o.SIMPLEX, order)
+        for a in range(order + 1):
+            for b in range(order + 1 - a):
+                from math import factorial
+                exact = factorial(a) * factorial(b) / factorial(a + b + 2)
+                assert abs((w * x ** a * y ** b).sum() - exact) < 1e-14, (order, a, b)
+        t, wt = o.line_rule(order)
+        for a in range(order + 1):
+            assert abs((wt * t ** a).sum() - 1.0 / (a + 1)) < 1e-14
+    assert len(o.element_rule(o.CUBE, 0)[0]) == 1 and len(o.element_rule(o.CUBE, 1)[0]) == 1  # midpoint rule
+    assert [len(o.element_rule(o.SIMPLEX, k)[0]) for k in range(6)] == [1, 1, 3, 4, 6, 7]
+
+
+def test_matrix_is_symmetric_positive_definite_and_cg_converges():
+    m = o.mesh_cube(16, 16, -1.0, 1.0, -1.0, 1.0)
+    u, (rp, col, A, b) = solve_esv(m)
+    S = o.to_scipy(rp, col, A)
+    assert abs(S - S.T).max() < 1e-13
+    x, it, rr = o.cg(rp, col, A, b, precond=1, rtol=1e-12)
+    assert rr <= 1e-12 and np.abs(x - u).max() <= 1e-9 * np.abs(u).max()
+    assert np.allclose(o.spmv(rp, col, A, x), S @ x, rtol=1e-13, atol=1e-15)
