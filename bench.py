@@ -3,7 +3,7 @@
 
 A step is one pass of the hot path over the workload: assemble every affine part of the system matrix and of the rhs
 (K2 + K3), then freeze and CG-solve to ||r||/||b|| <= 1e-10 (K4 - K6), on the 4096^2 structured Q1 grid with ESV2007 data
-(BASELINE.json configs[4], the configuration the metric is quoted on; --n scales it down for a quick look).
+(BASELINE.json configs[4], the configuration the metric is quoted on; --grid scales it down for a quick look).
 
     value          assembled DoFs/s over all ranks: K * N_dofs / sum of the K assembly times (device time, max over ranks)
     cg_solve_s     mean CG time-to-solution of the K steps (device time), with cg_iterations and cg_s_per_iteration
@@ -126,7 +126,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--n", type=int, default=4096, help="cells per side of the structured grid")
+    ap.add_argument("--grid", dest="n", type=int, default=4096, help="cells per side of the structured grid")
     ap.add_argument("--cpu-n", type=int, default=768)
     ap.add_argument("--cpu-cg-iters", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")

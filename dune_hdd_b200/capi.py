@@ -60,7 +60,7 @@ SYMBOLS = [
     "hdd_copy_to_host", "hdd_sync", "hdd_apply", "hdd_solver_types", "hdd_solve", "hdd_solution_dev",
     "hdd_num_subdomains", "hdd_subdomain_offsets", "hdd_neighbouring_subdomains", "hdd_block_extract",
     "hdd_csr_free", "hdd_estimators_available", "hdd_estimate", "hdd_indicators", "hdd_comm_unique_id",
-    "hdd_comm_init", "hdd_kernel_launches", "hdd_profile_kernel", "hdd_kernel_bytes", "hdd_expression_evaluate", "hdd_partition_plan", "hdd_free",
+    "hdd_comm_create", "hdd_comm_destroy", "hdd_mesh_attach_comm", "hdd_kernel_launches", "hdd_profile_kernel", "hdd_kernel_bytes", "hdd_expression_evaluate", "hdd_partition_plan", "hdd_free",
 ]
 
 _lib = None

@@ -41,6 +41,11 @@ struct HaloPeer {
 
 }  // namespace hdd
 
+struct hdd_comm {
+  int rank = 0, world = 1, device = 0;
+  ncclComm* comm = nullptr;
+};
+
 struct hdd_mesh {
   int kind = 0, nl = 0, nf = 0, device = 0;
   cudaStream_t stream = nullptr;

@@ -120,8 +120,7 @@ double point_set_diameter(std::vector<std::pair<double, double>>& pts) {
 using namespace hdd;
 
 hdd_mesh::~hdd_mesh() {
-  if (comm) Nccl::get().destroy(comm);
-  if (stream) cudaStreamDestroy(stream);
+  if (stream) cudaStreamDestroy(stream);  // the communicator belongs to its hdd_comm
 }
 
 void hdd_mesh::halo_exchange(double* v_local) {
@@ -409,16 +408,40 @@ int hdd_comm_unique_id(void* id128) {
   return guarded([&] { Nccl::get().unique_id(id128); });
 }
 
-int hdd_comm_init(hdd_mesh* m, const void* id128, int rank, int world_size) {
+int hdd_comm_create(const void* id128, int rank, int world_size, int device, hdd_comm** out) {
   return guarded([&] {
-    if (!m) HDD_THROW(HDD_ERR_WRONG_INPUT, "mesh is NULL");
+    if (!out || !id128) HDD_THROW(HDD_ERR_WRONG_INPUT, "NULL argument");
+    *out = nullptr;
     if (world_size < 1 || rank < 0 || rank >= world_size) HDD_THROW(HDD_ERR_WRONG_INPUT, "bad rank / world size");
+    HDD_CUDA(cudaSetDevice(device));
+    std::unique_ptr<hdd_comm> c(new hdd_comm);
+    c->rank = rank;
+    c->world = world_size;
+    c->device = device;
+    if (world_size > 1) c->comm = Nccl::get().init_rank(id128, rank, world_size);
+    *out = c.release();
+  });
+}
+
+int hdd_comm_destroy(hdd_comm* c) {
+  return guarded([&] {
+    if (!c) return;
+    if (c->comm) Nccl::get().destroy(c->comm);
+    delete c;
+  });
+}
+
+int hdd_mesh_attach_comm(hdd_mesh* m, hdd_comm* c) {
+  return guarded([&] {
+    if (!m || !c) HDD_THROW(HDD_ERR_WRONG_INPUT, "mesh or comm is NULL");
+    if (c->device != m->device) HDD_THROW(HDD_ERR_WRONG_INPUT, "communicator and mesh live on different devices");
+    const int rank = c->rank, world_size = c->world;
     m->set_device();
     m->rank = rank;
     m->world = world_size;
     if (world_size == 1) return;
     Nccl& nc = Nccl::get();
-    m->comm = nc.init_rank(id128, rank, world_size);
+    m->comm = c->comm;
     // every rank learns every rank's owned range (2 doubles per rank through one all-reduce)
     DevBuf<double> ranges;
     ranges.alloc(size_t(world_size) + 1);

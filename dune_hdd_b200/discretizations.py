@@ -117,9 +117,9 @@ class SWIPDG:
                                  capi.ptr(grid.cell_verts, C.c_int32), capi.ptr(grid.cell_neigh, C.c_int32),
                                  capi.ptr(grid.cell_subdomain, C.c_int32), capi.ptr(bt, C.c_uint8), C.c_int64(cb),
                                  C.c_int64(ce), device, C.byref(self._mesh)))
+        self._comm = comm  # keep the communicator alive as long as the mesh
         if comm is not None:
-            uid, rank, world = comm
-            _check(L.hdd_comm_init(self._mesh, uid, rank, world))
+            _check(L.hdd_mesh_attach_comm(self._mesh, comm.handle))
         self._cproblem = problem.to_c()
         h = C.c_void_p()
         try:

@@ -42,9 +42,25 @@ def partition_plan(grid, world_size, rank, offsets=None):
     return halo, send
 
 
-def init_comm(rank, world_size, device=None):
+class Comm:
+    """one NCCL communicator per process (hdd_comm); pass it to every discretization of this process"""
+
+    def __init__(self, uid, rank, world_size, device):
+        self.rank, self.world_size, self.device = rank, world_size, device
+        self.handle = C.c_void_p()
+        capi.check(capi.lib().hdd_comm_create(uid, rank, world_size, device, C.byref(self.handle)))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                capi.lib().hdd_comm_destroy(self.handle)
+        except Exception:
+            pass
+
+
+def init_comm(rank, world_size, device=0):
     """NCCL unique id from rank 0, broadcast over the already initialised torch.distributed group.
-    Returns the ``comm`` tuple the discretization constructors take, or None for a single process."""
+    Returns the Comm the discretization constructors take, or None for a single process."""
     if world_size == 1:
         return None
     import torch
@@ -57,4 +73,4 @@ def init_comm(rank, world_size, device=None):
     if dist.get_backend() == "nccl":
         uid = uid.cuda(device)
     dist.broadcast(uid, 0)
-    return (bytes(uid.cpu().tolist()), rank, world_size)
+    return Comm(bytes(uid.cpu().tolist()), rank, world_size, device)

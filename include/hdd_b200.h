@@ -217,11 +217,16 @@ int hdd_estimate(hdd_swipdg* h, const char* type, const double* u_host, const hd
 int hdd_indicators(hdd_swipdg* h, const double* u_host, const hdd_parameters* parameters, double* out_host);
 
 /* ---- multi GPU: one process per GPU ------------------------------------------------------------------------ */
-/* NCCL plumbing: rank 0 calls hdd_comm_unique_id, the id is broadcast by the host program (torch.distributed),
- * every rank calls hdd_comm_init before hdd_swipdg_create on a mesh with world_size > 1.  NCCL carries only the
- * coupling-face halo exchange of the CG direction and the dot-product all-reduces. */
+/* NCCL plumbing: rank 0 calls hdd_comm_unique_id, the 128-byte id is broadcast by the host program
+ * (torch.distributed), every rank creates ONE communicator per process with hdd_comm_create and attaches it to each
+ * mesh whose owned range is a proper slab (hdd_mesh_attach_comm builds the halo-exchange plan).  NCCL carries only the
+ * coupling-face halo exchange of the CG direction and the dot-product all-reduces.  All ranks must attach / solve /
+ * estimate collectively. */
+typedef struct hdd_comm hdd_comm;
 int hdd_comm_unique_id(void* id128);
-int hdd_comm_init(hdd_mesh* mesh, const void* id128, int rank, int world_size);
+int hdd_comm_create(const void* id128, int rank, int world_size, int device, hdd_comm** out);
+int hdd_comm_destroy(hdd_comm* comm);
+int hdd_mesh_attach_comm(hdd_mesh* mesh, hdd_comm* comm);
 /* The host-side partition plan hdd_mesh_create / hdd_comm_init build for `rank`, without touching a device (used by
  * the CPU tests of the N > 1 path and by hosts that want to inspect the decomposition): ranks own the consecutive
  * cell ranges rank_cell_offsets[r] .. rank_cell_offsets[r+1] (world_size+1 entries, whole subdomains).
