@@ -131,6 +131,7 @@ def main():
     ap.add_argument("--cpu-cg-iters", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--solver", default="cg.diagonal", help="cg.blockdiagonal | cg.diagonal | cg.identity")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -164,7 +165,7 @@ def main():
     problem = hdd.problems.ESV2007()
     roff = hdd.parallel.rank_cell_offsets(grid, world)
     cell_range = (int(roff[rank]), int(roff[rank + 1]))
-    options = {"type": "cg.diagonal", "precision": PRECISION, "max_iter": 200000}
+    options = {"type": args.solver, "precision": PRECISION, "max_iter": 200000}
 
     def make():
         d = hdd.BlockSWIPDG(grid, problem, device=local_rank, cell_range=cell_range, comm=comm)
@@ -251,7 +252,7 @@ def main():
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "config5: SWIPDG p1 (Q1) on the %dx%d structured grid [-1,1]^2, ESV2007 data, "
                                        "8x8 BlockSWIPDG partition" % (n, n), "cells": n * n, "dofs": n_dofs,
-                           "cg": "Jacobi-preconditioned CG to ||r||/||b|| <= 1e-10", "l2_flush": "inputs >> L2 (matrix "
+                           "cg": "%s to ||r||/||b|| <= 1e-10" % args.solver, "l2_flush": "inputs >> L2 (matrix "
                            "%.1f GB per part)" % (8.0 * 16 * (n * n + 2 * 2 * n * (n - 1)) / 1e9),
                            "parallelism": "subdomain slabs x%d" % world},
                 "assemble_ms": 1e3 * t_asm / args.steps, "cg_solve_s": t_cg / args.steps, "cg_iterations": iters,

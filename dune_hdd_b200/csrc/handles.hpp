@@ -170,7 +170,8 @@ struct hdd_swipdg {
   hdd::DevBuf<int32_t> col;
 
   // solve workspace
-  hdd::DevBuf<double> frozen, dinv, b, x, r, p, q, partial, tmp_local;
+  hdd::DevBuf<double> frozen, dinv, dinv_block, z, b, x, r, p, q, partial, tmp_local;
+  int last_precond = 1;  // 0 identity, 1 diagonal, 2 cell-block diagonal
   hdd::DevBuf<hdd::CgScalars> sc;
   hdd::CgScalars* sc_host = nullptr;  // pinned
   bool have_solution = false;

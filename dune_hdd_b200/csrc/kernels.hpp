@@ -33,6 +33,7 @@ struct FreezeArgs {
 void launch_freeze(const FreezeArgs& a, double* out, int64_t count, cudaStream_t s);
 // dinv[row] = 1 / A[row,row] (Jacobi) or 1 (identity)
 void launch_extract_dinv(const MeshView& m, const double* values, int use_diagonal, double* dinv, cudaStream_t s);
+void launch_invert_diag_blocks(const MeshView& m, const double* values, double* dinv_block, cudaStream_t s);
 
 // ---- K5/K6: CG ---------------------------------------------------------------------------------------------------
 struct CgScalars {     // device resident, ping-pong indexed by iteration parity
@@ -51,7 +52,9 @@ struct CgScalars {     // device resident, ping-pong indexed by iteration parity
 
 struct CgBuffers {
   const double* values;  // frozen operator, CSR order
-  const double* dinv;    // owned rows
+  const double* dinv;    // owned rows (identity / diagonal preconditioner)
+  const double* dinv_block;  // [n_own * nl * nl] inverted diagonal blocks (block Jacobi) or nullptr
+  double* z;             // owned rows, preconditioned residual (block Jacobi only) or nullptr
   const double* b;       // owned rows
   double* x;             // owned rows
   double* r;             // owned rows

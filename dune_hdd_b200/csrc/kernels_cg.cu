@@ -6,10 +6,21 @@
 // from the 16-byte neighbour record of the cell and one 8-byte block offset per cell.  That removes the 4 B/nnz
 // index stream of textbook CSR: 8.05 B/nnz instead of 12 B/nnz of HBM traffic for Q1.
 //
+// Two SpMV kernels:
+//   k_cg_spmv      generic (P1 and Q1): one thread per row, 256-bit loads for Q1.
+//   k_cg_spmv_tma  Q1: the matrix stream (88 % of the bytes) is moved by the TMA engine.  The row blocks of
+//                  consecutive cells are one contiguous byte range, so a producer warp issues 1-D bulk copies
+//                  (cp.async.bulk, UBLKCP) of 8-cell tiles into a 32-stage shared-memory ring guarded by mbarriers;
+//                  16 consumer warps read their rows from shared memory, gather x through L1/L2 and write q.
+//                  The copy engine keeps ~160 KB per SM in flight independent of what the consumer warps wait on.
+//
 // CG is the classic Hestenes-Stiefel recurrence (same algebra as oracle/or_cg) with device-resident scalars:
 // no host synchronisation inside the iteration, dot products reduced deterministically (fixed per-block partials,
 // last-arriving block sums them in a fixed order), convergence latched in a ping-pong flag so that iterations
-// launched after convergence are no-ops.
+// launched after convergence are no-ops.  Preconditioners: identity, diagonal (Jacobi), and the cell-block diagonal
+// (block Jacobi with the n_loc x n_loc diagonal blocks, the natural choice for DG).
+#include <cstdlib>
+
 #include "kernels.hpp"
 
 namespace hdd {
@@ -36,10 +47,10 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// Block-level sum of up to 3 values; result valid in thread 0.
+// Block-level sum of N values; result valid in thread 0.  Works for up to 32 warps.
 template <int N>
 __device__ __forceinline__ void block_sum(double (&v)[N], double* smem /* [N*32] */) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
 #pragma unroll
   for (int k = 0; k < N; ++k) v[k] = warp_sum(v[k]);
   __syncthreads();
@@ -83,20 +94,15 @@ __device__ __forceinline__ void grid_sum(double (&v)[N], double* partial, unsign
   if (threadIdx.x == 0) finish(w);
 }
 
-// Row kernel shared by SpMV and the CG step: y_t = sum over the blocks of row t, ascending column order.
-template <int KIND>
-__device__ __forceinline__ double row_times_x(const MeshView& m, const double* __restrict__ vals,
-                                              const double* __restrict__ x, int64_t t) {
-  constexpr int NL = Geo<KIND>::NL, NF = Geo<KIND>::NF;
-  const int k = int(t / NL), i = int(t % NL);
+// cells of the row block of owned cell k in ascending (= column) order; returns the number of blocks
+template <int NF>
+__device__ __forceinline__ int sorted_blocks(const MeshView& m, int k, int* cells) {
   int nb[NF];
   load_neigh<NF>(m.neigh, k, nb);
   const int self = m.own0 + k;
-  int cells[NF + 1];
   int nblk = 1;
 #pragma unroll
   for (int f = 0; f < NF; ++f) nblk += nb[f] >= 0 ? 1 : 0;
-  // scatter cells into their sorted slots
 #pragma unroll
   for (int s = 0; s < NF + 1; ++s) cells[s] = 0;
   {
@@ -113,6 +119,31 @@ __device__ __forceinline__ double row_times_x(const MeshView& m, const double* _
       for (int s = 0; s < NF + 1; ++s)
         if (s == slot) cells[s] = nb[f];
     }
+  return nblk;
+}
+
+__device__ __forceinline__ void ld256_stream(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ void ld256(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+// read-modify-write streams (x, r, p) must not use the non-coherent path
+__device__ __forceinline__ void ld256_rw(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st256(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+// Row kernel shared by SpMV and the CG step: y_t = sum over the blocks of row t, ascending column order.
+template <int KIND>
+__device__ __forceinline__ double row_times_x(const MeshView& m, const double* __restrict__ vals,
+                                              const double* __restrict__ x, int64_t t) {
+  constexpr int NL = Geo<KIND>::NL, NF = Geo<KIND>::NF;
+  const int k = int(t / NL), i = int(t % NL);
+  int cells[NF + 1];
+  const int nblk = sorted_blocks<NF>(m, k, cells);
   const double* row = vals + m.blk_start[k] * (NL * NL) + int64_t(i) * nblk * NL;
   double sum = 0.0;
 #pragma unroll
@@ -121,14 +152,12 @@ __device__ __forceinline__ double row_times_x(const MeshView& m, const double* _
       const double* xs = x + size_t(NL) * cells[s];
       if constexpr (NL == 4) {
         double a0, a1, a2, a3, x0, x1, x2, x3;
-        asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
-                     : "=d"(a0), "=d"(a1), "=d"(a2), "=d"(a3)
-                     : "l"(row + s * 4));
-        asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x0), "=d"(x1), "=d"(x2), "=d"(x3) : "l"(xs));
+        ld256_stream(row + s * 4, a0, a1, a2, a3);
+        ld256(xs, x0, x1, x2, x3);
         sum = fma(a0, x0, sum); sum = fma(a1, x1, sum); sum = fma(a2, x2, sum); sum = fma(a3, x3, sum);
       } else {
 #pragma unroll
-        for (int j = 0; j < NL; ++j) sum = fma(row[s * NL + j], xs[j], sum);
+        for (int j = 0; j < NL; ++j) sum = fma(__ldg(row + s * NL + j), __ldg(xs + j), sum);
       }
     }
   }
@@ -143,33 +172,6 @@ __global__ void __launch_bounds__(kCgThreads)
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
   for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < rows; t += stride)
     y[t] = row_times_x<KIND>(m, vals, x, t);
-}
-
-__global__ void __launch_bounds__(kCgThreads) k_cg_init(int64_t rows, int64_t own_off, CgBuffers c) {
-  double v[2] = {0.0, 0.0};
-  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
-  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < rows; t += stride) {
-    const double b = c.b[t], z = c.dinv[t] * b;
-    c.x[t] = 0.0;
-    c.r[t] = b;
-    c.p[own_off + t] = z;
-    v[0] += b * z;
-    v[1] += b * b;
-  }
-  CgScalars* sc = c.sc;
-  grid_sum<2>(v, c.partial, &sc->ticket_a, [sc](const double(&w)[2]) {
-    sc->red[1] = w[0];  // local r.z
-    sc->red[2] = w[1];  // local b.b
-  });
-}
-
-// after the (optional) all-reduce of red[1..2]
-__global__ void k_cg_init_finish(CgScalars* sc) {
-  sc->rz[0] = sc->red[1];
-  sc->bb = sc->red[2];
-  sc->rr = sc->red[2];
-  sc->it[0] = 0;
-  sc->done[0] = (sc->red[2] == 0.0 || sc->max_it <= 0) ? 1 : 0;
 }
 
 template <int KIND>
@@ -188,19 +190,220 @@ __global__ void __launch_bounds__(kCgThreads) k_cg_spmv(MeshView m, CgBuffers c,
   grid_sum<1>(v, c.partial, &sc->ticket_a, [sc](const double(&w)[1]) { sc->red[0] = w[0]; });
 }
 
+// ---- TMA-staged Q1 SpMV -----------------------------------------------------------------------------------------
+constexpr int kTmaStages = 32;
+constexpr int kTmaTileCells = 8;                           // one warp: 8 cells x 4 rows
+constexpr int kTmaStageBytes = kTmaTileCells * 5 * 128;    // 8 cells x <= 5 blocks x 16 doubles
+constexpr int kTmaConsumerWarps = 16;
+constexpr int kTmaThreads = (kTmaConsumerWarps + 1) * 32;
+constexpr int kTmaSmemBytes = kTmaStages * kTmaStageBytes + 2 * kTmaStages * 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kTmaThreads, 1) k_cg_spmv_tma(MeshView m, CgBuffers c, int par, int cells_per_cta) {
+  constexpr int NL = 4, NF = 4;
+  extern __shared__ __align__(128) unsigned char smem[];
+  CgScalars* sc = c.sc;
+  if (sc->done[par]) return;
+  unsigned char* stage_base = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTmaStages * kTmaStageBytes);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kTmaStages);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTmaStages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int c0 = blockIdx.x * cells_per_cta;
+  const int c1 = min(c0 + cells_per_cta, m.n_own);
+  const int n_tiles = c1 > c0 ? (c1 - c0 + kTmaTileCells - 1) / kTmaTileCells : 0;
+  double v[1] = {0.0};
+  if (warp == kTmaConsumerWarps) {
+    // producer: lane l owns stage l and feeds tiles l, l+32, ...
+    for (int t = lane; t < n_tiles; t += kTmaStages) {
+      const int n = t / kTmaStages;
+      if (n > 0) mbar_wait(empty0 + 8 * lane, (n - 1) & 1);
+      const int k0 = c0 + t * kTmaTileCells, k1 = min(k0 + kTmaTileCells, c1);
+      const int64_t b0 = __ldg(m.blk_start + k0), b1 = __ldg(m.blk_start + k1);
+      const uint32_t bytes = uint32_t(b1 - b0) * (NL * NL * 8);
+      mbar_expect_tx(full0 + 8 * lane, bytes);
+      bulk_g2s(smem_u32(stage_base + lane * kTmaStageBytes), c.values + b0 * (NL * NL), bytes, full0 + 8 * lane);
+    }
+  } else {
+    const int64_t own_off = int64_t(m.own0) * NL;
+    const int i = lane & 3;
+    for (int t = warp; t < n_tiles; t += kTmaConsumerWarps) {
+      const int stage = t % kTmaStages, n = t / kTmaStages;
+      const int k0 = c0 + t * kTmaTileCells;
+      const int k = k0 + (lane >> 2);
+      const bool active = k < c1;
+      int cells[NF + 1];
+      int nblk = 0;
+      int64_t off = 0;
+      double xv[NF + 1][4];
+      if (active) {
+        nblk = sorted_blocks<NF>(m, k, cells);
+        off = (__ldg(m.blk_start + k) - __ldg(m.blk_start + k0)) * (NL * NL) + int64_t(i) * nblk * NL;
+#pragma unroll
+        for (int s = 0; s < NF + 1; ++s)
+          if (s < nblk) ld256(c.p + size_t(NL) * cells[s], xv[s][0], xv[s][1], xv[s][2], xv[s][3]);
+      }
+      mbar_wait(full0 + 8 * stage, n & 1);
+      double sum = 0.0;
+      if (active) {
+        const double* row = reinterpret_cast<const double*>(stage_base + stage * kTmaStageBytes) + off;
+#pragma unroll
+        for (int s = 0; s < NF + 1; ++s)
+          if (s < nblk) {
+            const double2 a = *reinterpret_cast<const double2*>(row + s * 4);
+            const double2 b = *reinterpret_cast<const double2*>(row + s * 4 + 2);
+            sum = fma(a.x, xv[s][0], sum); sum = fma(a.y, xv[s][1], sum);
+            sum = fma(b.x, xv[s][2], sum); sum = fma(b.y, xv[s][3], sum);
+          }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + 8 * stage);
+      if (active) {
+        const int64_t r = int64_t(NL) * k + i;
+        c.q[r] = sum;
+        v[0] = fma(__ldg(c.p + own_off + r), sum, v[0]);
+      }
+    }
+  }
+  grid_sum<1>(v, c.partial, &sc->ticket_a, [sc](const double(&w)[1]) { sc->red[0] = w[0]; });
+}
+
+// ---- vector kernels ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCgThreads) k_cg_init(int64_t rows, int64_t own_off, CgBuffers c) {
+  double v[2] = {0.0, 0.0};
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < rows; t += stride) {
+    const double b = c.b[t], z = c.dinv[t] * b;
+    c.x[t] = 0.0;
+    c.r[t] = b;
+    c.p[own_off + t] = z;
+    v[0] += b * z;
+    v[1] += b * b;
+  }
+  CgScalars* sc = c.sc;
+  grid_sum<2>(v, c.partial, &sc->ticket_a, [sc](const double(&w)[2]) {
+    sc->red[1] = w[0];  // local r.z
+    sc->red[2] = w[1];  // local b.b
+  });
+}
+
+// block-Jacobi variant: one thread per cell, z = Dinv_T r_T with the inverted n_loc x n_loc diagonal block
+template <int NL>
+__global__ void __launch_bounds__(kCgThreads) k_cg_init_block(int64_t cells, int64_t own_off, CgBuffers c) {
+  double v[2] = {0.0, 0.0};
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; k < cells; k += stride) {
+    double b[NL], z[NL];
+#pragma unroll
+    for (int i = 0; i < NL; ++i) b[i] = c.b[NL * k + i];
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < NL; ++j) s = fma(__ldg(c.dinv_block + (NL * NL) * k + i * NL + j), b[j], s);
+      z[i] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      c.x[NL * k + i] = 0.0;
+      c.r[NL * k + i] = b[i];
+      c.z[NL * k + i] = z[i];
+      c.p[own_off + NL * k + i] = z[i];
+      v[0] = fma(b[i], z[i], v[0]);
+      v[1] = fma(b[i], b[i], v[1]);
+    }
+  }
+  CgScalars* sc = c.sc;
+  grid_sum<2>(v, c.partial, &sc->ticket_a, [sc](const double(&w)[2]) {
+    sc->red[1] = w[0];
+    sc->red[2] = w[1];
+  });
+}
+
+// after the (optional) all-reduce of red[1..2]
+__global__ void k_cg_init_finish(CgScalars* sc) {
+  sc->rz[0] = sc->red[1];
+  sc->bb = sc->red[2];
+  sc->rr = sc->red[2];
+  sc->it[0] = 0;
+  sc->done[0] = (sc->red[2] == 0.0 || sc->max_it <= 0) ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(kCgThreads) k_cg_update(int64_t rows, int64_t own_off, CgBuffers c, int par) {
   CgScalars* sc = c.sc;
   if (sc->done[par]) return;
   const double alpha = sc->rz[par] / sc->red[0];
   double v[2] = {0.0, 0.0};
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
-  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < rows; t += stride) {
-    c.x[t] = fma(alpha, c.p[own_off + t], c.x[t]);
-    const double r = fma(-alpha, c.q[t], c.r[t]);
-    c.r[t] = r;
-    const double z = c.dinv[t] * r;
-    v[0] = fma(r, z, v[0]);
-    v[1] = fma(r, r, v[1]);
+  if ((rows & 3) == 0 && (own_off & 3) == 0) {
+    // four rows per thread, 256-bit accesses
+    const int64_t n4 = rows >> 2;
+    for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < n4; t += stride) {
+      double p[4], q[4], x[4], r[4], d[4];
+      ld256_rw(c.p + own_off + 4 * t, p[0], p[1], p[2], p[3]);
+      ld256_stream(c.q + 4 * t, q[0], q[1], q[2], q[3]);
+      ld256_rw(c.x + 4 * t, x[0], x[1], x[2], x[3]);
+      ld256_rw(c.r + 4 * t, r[0], r[1], r[2], r[3]);
+      ld256_stream(c.dinv + 4 * t, d[0], d[1], d[2], d[3]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        x[j] = fma(alpha, p[j], x[j]);
+        r[j] = fma(-alpha, q[j], r[j]);
+        const double z = d[j] * r[j];
+        v[0] = fma(r[j], z, v[0]);
+        v[1] = fma(r[j], r[j], v[1]);
+      }
+      st256(c.x + 4 * t, x[0], x[1], x[2], x[3]);
+      st256(c.r + 4 * t, r[0], r[1], r[2], r[3]);
+    }
+  } else {
+    for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < rows; t += stride) {
+      c.x[t] = fma(alpha, c.p[own_off + t], c.x[t]);
+      const double r = fma(-alpha, c.q[t], c.r[t]);
+      c.r[t] = r;
+      const double z = c.dinv[t] * r;
+      v[0] = fma(r, z, v[0]);
+      v[1] = fma(r, r, v[1]);
+    }
   }
   grid_sum<2>(v, c.partial, &sc->ticket_b, [sc](const double(&w)[2]) {
     sc->red[1] = w[0];
@@ -208,14 +411,91 @@ __global__ void __launch_bounds__(kCgThreads) k_cg_update(int64_t rows, int64_t 
   });
 }
 
+template <int NL>
+__global__ void __launch_bounds__(kCgThreads) k_cg_update_block(int64_t cells, int64_t own_off, CgBuffers c, int par) {
+  CgScalars* sc = c.sc;
+  if (sc->done[par]) return;
+  const double alpha = sc->rz[par] / sc->red[0];
+  double v[2] = {0.0, 0.0};
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; k < cells; k += stride) {
+    double p[NL], q[NL], x[NL], r[NL], z[NL], D[NL * NL];
+    if constexpr (NL == 4) {
+      ld256_rw(c.p + own_off + 4 * k, p[0], p[1], p[2], p[3]);
+      ld256_stream(c.q + 4 * k, q[0], q[1], q[2], q[3]);
+      ld256_rw(c.x + 4 * k, x[0], x[1], x[2], x[3]);
+      ld256_rw(c.r + 4 * k, r[0], r[1], r[2], r[3]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ld256_stream(c.dinv_block + 16 * k + 4 * i, D[4 * i], D[4 * i + 1], D[4 * i + 2], D[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NL; ++i) {
+        p[i] = c.p[own_off + NL * k + i]; q[i] = c.q[NL * k + i]; x[i] = c.x[NL * k + i]; r[i] = c.r[NL * k + i];
+      }
+#pragma unroll
+      for (int i = 0; i < NL * NL; ++i) D[i] = __ldg(c.dinv_block + (NL * NL) * k + i);
+    }
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      x[i] = fma(alpha, p[i], x[i]);
+      r[i] = fma(-alpha, q[i], r[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < NL; ++j) s = fma(D[i * NL + j], r[j], s);
+      z[i] = s;
+      v[0] = fma(r[i], s, v[0]);
+      v[1] = fma(r[i], r[i], v[1]);
+    }
+    if constexpr (NL == 4) {
+      st256(c.x + 4 * k, x[0], x[1], x[2], x[3]);
+      st256(c.r + 4 * k, r[0], r[1], r[2], r[3]);
+      st256(c.z + 4 * k, z[0], z[1], z[2], z[3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NL; ++i) { c.x[NL * k + i] = x[i]; c.r[NL * k + i] = r[i]; c.z[NL * k + i] = z[i]; }
+    }
+  }
+  grid_sum<2>(v, c.partial, &sc->ticket_b, [sc](const double(&w)[2]) {
+    sc->red[1] = w[0];
+    sc->red[2] = w[1];
+  });
+}
+
+// p = z + beta p with z = dinv r (diagonal / identity) or the stored z (block Jacobi); also advances the CG state
 __global__ void __launch_bounds__(kCgThreads) k_cg_direction(int64_t rows, int64_t own_off, CgBuffers c, int par) {
   CgScalars* sc = c.sc;
   const int done = sc->done[par];
   if (!done) {
     const double beta = sc->red[1] / sc->rz[par];
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
-    for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < rows; t += stride)
-      c.p[own_off + t] = fma(beta, c.p[own_off + t], c.dinv[t] * c.r[t]);
+    const bool stored_z = c.z != nullptr;
+    if ((rows & 3) == 0 && (own_off & 3) == 0) {
+      const int64_t n4 = rows >> 2;
+      for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < n4; t += stride) {
+        double p[4], z[4];
+        ld256_rw(c.p + own_off + 4 * t, p[0], p[1], p[2], p[3]);
+        if (stored_z) {
+          ld256_rw(c.z + 4 * t, z[0], z[1], z[2], z[3]);
+        } else {
+          double r[4];
+          ld256_rw(c.r + 4 * t, r[0], r[1], r[2], r[3]);
+          ld256_stream(c.dinv + 4 * t, z[0], z[1], z[2], z[3]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) z[j] *= r[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) p[j] = fma(beta, p[j], z[j]);
+        st256(c.p + own_off + 4 * t, p[0], p[1], p[2], p[3]);
+      }
+    } else {
+      for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < rows; t += stride) {
+        const double z = stored_z ? c.z[t] : c.dinv[t] * c.r[t];
+        c.p[own_off + t] = fma(beta, c.p[own_off + t], z);
+      }
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     if (done) {
@@ -232,15 +512,62 @@ __global__ void __launch_bounds__(kCgThreads) k_cg_direction(int64_t rows, int64
   }
 }
 
+// inverse of the n_loc x n_loc diagonal block of every owned cell (Gauss-Jordan, the blocks are s.p.d.)
+template <int KIND>
+__global__ void k_invert_diag_blocks(MeshView m, const double* __restrict__ values, double* __restrict__ dinv_block) {
+  constexpr int NL = Geo<KIND>::NL, NF = Geo<KIND>::NF;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m.n_own) return;
+  int nb[NF];
+  load_neigh<NF>(m.neigh, k, nb);
+  const int self = m.own0 + k;
+  const int nblk = block_count<NF>(nb);
+  const int slot = block_slot<NF>(self, nb, self);
+  const double* row0 = values + m.blk_start[k] * (NL * NL);
+  double A[NL][NL], I[NL][NL];
+#pragma unroll
+  for (int i = 0; i < NL; ++i)
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      A[i][j] = row0[size_t(i) * nblk * NL + slot * NL + j];
+      I[i][j] = i == j ? 1.0 : 0.0;
+    }
+#pragma unroll
+  for (int c = 0; c < NL; ++c) {
+    const double ip = 1.0 / A[c][c];
+#pragma unroll
+    for (int j = 0; j < NL; ++j) { A[c][j] *= ip; I[c][j] *= ip; }
+#pragma unroll
+    for (int i = 0; i < NL; ++i)
+      if (i != c) {
+        const double f = A[i][c];
+#pragma unroll
+        for (int j = 0; j < NL; ++j) { A[i][j] = fma(-f, A[c][j], A[i][j]); I[i][j] = fma(-f, I[c][j], I[i][j]); }
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < NL; ++i)
+#pragma unroll
+    for (int j = 0; j < NL; ++j) dinv_block[size_t(NL * NL) * k + i * NL + j] = 0.5 * (I[i][j] + I[j][i]);
+}
+
 __global__ void k_pack(const double* __restrict__ v, const int32_t* __restrict__ idx, int64_t n,
                        double* __restrict__ out) {
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
   for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += stride) out[t] = v[idx[t]];
 }
 
-inline int cg_grid(int64_t rows) {
-  const int64_t need = (rows + kCgThreads - 1) / kCgThreads;
+inline int cg_grid(int64_t items) {
+  const int64_t need = (items + kCgThreads - 1) / kCgThreads;
   return int(std::max<int64_t>(1, std::min<int64_t>(need, kMaxBlocks)));
+}
+
+bool use_tma() {
+  static const bool on = [] {
+    const char* e = std::getenv("HDD_SPMV_TMA");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 
 }  // namespace
@@ -258,13 +585,30 @@ void launch_spmv(const MeshView& m, const double* values, const double* x_local,
   HDD_CUDA(cudaGetLastError());
 }
 
+void launch_invert_diag_blocks(const MeshView& m, const double* values, double* dinv_block, cudaStream_t s) {
+  if (m.n_own == 0) return;
+  if (m.kind == HDD_SIMPLEX2D)
+    k_invert_diag_blocks<HDD_SIMPLEX2D><<<(m.n_own + 127) / 128, 128, 0, s>>>(m, values, dinv_block);
+  else
+    k_invert_diag_blocks<HDD_CUBE2D><<<(m.n_own + 127) / 128, 128, 0, s>>>(m, values, dinv_block);
+  count_launch();
+  HDD_CUDA(cudaGetLastError());
+}
+
 void launch_cg_init(const MeshView& m, const CgBuffers& c, double precision, int max_it, cudaStream_t s) {
   const int64_t rows = int64_t(m.n_own) * m.nl;
   CgScalars h{};
   h.tol2 = precision * precision;
   h.max_it = max_it;
   HDD_CUDA(cudaMemcpyAsync(c.sc, &h, sizeof(h), cudaMemcpyHostToDevice, s));
-  k_cg_init<<<cg_grid(rows), kCgThreads, 0, s>>>(rows, int64_t(m.own0) * m.nl, c);
+  if (c.dinv_block) {
+    if (m.nl == 3)
+      k_cg_init_block<3><<<cg_grid(m.n_own), kCgThreads, 0, s>>>(m.n_own, int64_t(m.own0) * m.nl, c);
+    else
+      k_cg_init_block<4><<<cg_grid(m.n_own), kCgThreads, 0, s>>>(m.n_own, int64_t(m.own0) * m.nl, c);
+  } else {
+    k_cg_init<<<cg_grid(rows), kCgThreads, 0, s>>>(rows, int64_t(m.own0) * m.nl, c);
+  }
   count_launch();
   HDD_CUDA(cudaGetLastError());
 }
@@ -277,24 +621,45 @@ void launch_cg_init_finish(const MeshView&, const CgBuffers& c, cudaStream_t s) 
 
 void launch_cg_spmv(const MeshView& m, const CgBuffers& c, int parity, cudaStream_t s) {
   const int64_t rows = int64_t(m.n_own) * m.nl;
-  if (m.kind == HDD_SIMPLEX2D)
+  if (m.kind == HDD_SIMPLEX2D) {
     k_cg_spmv<HDD_SIMPLEX2D><<<cg_grid(rows), kCgThreads, 0, s>>>(m, c, parity);
-  else
+  } else if (use_tma() && m.n_own >= 148 * kTmaTileCells) {
+    static bool configured = false;
+    if (!configured) {
+      HDD_CUDA(cudaFuncSetAttribute(k_cg_spmv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes));
+      configured = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int cells_per_cta = (m.n_own + sms - 1) / sms;
+    cells_per_cta = (cells_per_cta + kTmaTileCells - 1) / kTmaTileCells * kTmaTileCells;
+    const int grid = (m.n_own + cells_per_cta - 1) / cells_per_cta;
+    k_cg_spmv_tma<<<grid, kTmaThreads, kTmaSmemBytes, s>>>(m, c, parity, cells_per_cta);
+  } else {
     k_cg_spmv<HDD_CUBE2D><<<cg_grid(rows), kCgThreads, 0, s>>>(m, c, parity);
+  }
   count_launch();
   HDD_CUDA(cudaGetLastError());
 }
 
 void launch_cg_update(const MeshView& m, const CgBuffers& c, int parity, cudaStream_t s) {
   const int64_t rows = int64_t(m.n_own) * m.nl;
-  k_cg_update<<<cg_grid(rows), kCgThreads, 0, s>>>(rows, int64_t(m.own0) * m.nl, c, parity);
+  if (c.dinv_block) {
+    if (m.nl == 3)
+      k_cg_update_block<3><<<cg_grid(m.n_own), kCgThreads, 0, s>>>(m.n_own, int64_t(m.own0) * m.nl, c, parity);
+    else
+      k_cg_update_block<4><<<cg_grid(m.n_own), kCgThreads, 0, s>>>(m.n_own, int64_t(m.own0) * m.nl, c, parity);
+  } else {
+    k_cg_update<<<cg_grid((rows + 3) / 4), kCgThreads, 0, s>>>(rows, int64_t(m.own0) * m.nl, c, parity);
+  }
   count_launch();
   HDD_CUDA(cudaGetLastError());
 }
 
 void launch_cg_direction(const MeshView& m, const CgBuffers& c, int parity, cudaStream_t s) {
   const int64_t rows = int64_t(m.n_own) * m.nl;
-  k_cg_direction<<<cg_grid(rows), kCgThreads, 0, s>>>(rows, int64_t(m.own0) * m.nl, c, parity);
+  k_cg_direction<<<cg_grid((rows + 3) / 4), kCgThreads, 0, s>>>(rows, int64_t(m.own0) * m.nl, c, parity);
   count_launch();
   HDD_CUDA(cudaGetLastError());
 }

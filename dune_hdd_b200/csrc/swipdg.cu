@@ -173,6 +173,7 @@ int parse_solver_type(const char* type) {
   if (t.empty() || t == "cg.diagonal" || t == "cg.jacobi" || t == "cg" || t == "cg.diagonal.lower" || t == "cg.diagonal.upper")
     return 1;
   if (t == "cg.identity" || t == "cg.identity.lower" || t == "cg.identity.upper") return 0;
+  if (t == "cg.blockdiagonal" || t == "cg.blockjacobi") return 2;
   HDD_THROW(HDD_ERR_WRONG_INPUT, "solver type '" << t << "' is not one of solver_types()");
 }
 
@@ -298,7 +299,7 @@ double total(const std::vector<double>& v) {
 const char* const kEstimatorTypes[] = {"eta_NC_ESV2007", "eta_R_ESV2007",  "eta_R_ESV2007_*", "eta_DF_ESV2007", "eta_ESV2007",
                                        "eta_ESV2007_alt", "eta_NC_OS2014", "eta_R_OS2014",    "eta_R_OS2014_*", "eta_DF_OS2014",
                                        "eta_DF_OS2014_*", "eta_OS2014",    "eta_OS2014_*"};
-const char* const kSolverTypes[] = {"cg.diagonal", "cg.identity"};
+const char* const kSolverTypes[] = {"cg.diagonal", "cg.blockdiagonal", "cg.identity"};
 
 }  // namespace
 
@@ -571,7 +572,7 @@ int hdd_apply(hdd_swipdg* h, const double* mu, int mu_size, const double* x_host
 int hdd_solver_types(const char* const** types, int* n_types) {
   return guarded([&] {
     if (types) *types = kSolverTypes;
-    if (n_types) *n_types = 2;
+    if (n_types) *n_types = 3;
   });
 }
 
@@ -593,10 +594,21 @@ int hdd_solve(hdd_swipdg* h, const char* type, double precision, int max_iter, c
     const double* vals = freeze_lhs(h, mu, mu_size);
     freeze_rhs(h, mu, mu_size);
     const MeshView v = h->view();
-    launch_extract_dinv(v, vals, use_diag, h->dinv.p, s);
     CgBuffers c{};
     c.values = vals;
     c.dinv = h->dinv.p;
+    h->last_precond = use_diag;
+    if (use_diag == 2) {
+      if (!h->dinv_block.p) {
+        h->dinv_block.alloc(size_t(m->n_own) * m->nl * m->nl);
+        h->z.alloc(size_t(h->n_rows));
+      }
+      launch_invert_diag_blocks(v, vals, h->dinv_block.p, s);
+      c.dinv_block = h->dinv_block.p;
+      c.z = h->z.p;
+    } else {
+      launch_extract_dinv(v, vals, use_diag, h->dinv.p, s);
+    }
     c.b = h->b.p;
     c.x = h->x.p;
     c.r = h->r.p;
@@ -916,8 +928,12 @@ int hdd_kernel_bytes(hdd_swipdg* h, int which, double* bytes) {
     double b = 0.0;
     switch (which) {
       case 0: b = 8.0 * nnz + rec * cells + 8.0 * rows /* read p */ + 8.0 * rows /* write q */; break;
-      case 1: b = 7.0 * 8.0 * rows; break;  // read x,p,q,r,dinv; write x,r
-      case 2: b = 4.0 * 8.0 * rows; break;  // read r,dinv,p; write p
+      case 1:  // diagonal: read x,p,q,r,dinv, write x,r; block: read x,p,q,r + n_loc^2 block per cell, write x,r,z
+        b = h->last_precond == 2 ? 7.0 * 8.0 * rows + 8.0 * m->nl * rows : 7.0 * 8.0 * rows;
+        break;
+      case 2:  // diagonal: read r,dinv,p, write p; block: read z,p, write p
+        b = h->last_precond == 2 ? 3.0 * 8.0 * rows : 4.0 * 8.0 * rows;
+        break;
       case 3: b = 8.0 * nnz + (geo + rec) * cells; break;
       default: HDD_THROW(HDD_ERR_WRONG_INPUT, "unknown kernel id " << which);
     }
@@ -938,6 +954,7 @@ int hdd_profile_kernel(hdd_swipdg* h, int which, int reps, double* avg_seconds) 
     c.values = h->lhs_comps.empty() ? h->lhs_affine->values.p : h->frozen.p;
     c.dinv = h->dinv.p; c.b = h->b.p; c.x = h->x.p; c.r = h->r.p; c.p = h->p.p; c.q = h->q.p;
     c.partial = h->partial.p; c.sc = h->sc.p;
+    if (h->last_precond == 2) { c.dinv_block = h->dinv_block.p; c.z = h->z.p; }
     if (which != 3) {
       // un-latch the convergence flag of parity 0 so that the kernels do their work; the vectors are scratch now
       CgScalars sc = *h->sc_host;

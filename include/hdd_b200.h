@@ -170,7 +170,8 @@ typedef struct hdd_solve_info {
 } hdd_solve_info;
 
 /* solver_types() / solver_options(type) (discretizations/base.hh:314-322). Types: "cg.diagonal" (default,
- * Jacobi), "cg.identity"; aliases "cg", "cg.jacobi", "cg.diagonal.lower", "cg.identity.lower". */
+ * Jacobi), "cg.blockdiagonal" (block Jacobi with the n_loc x n_loc cell blocks), "cg.identity"; aliases "cg",
+ * "cg.jacobi", "cg.diagonal.lower", "cg.identity.lower", "cg.blockjacobi". */
 int hdd_solver_types(const char* const** types, int* n_types);
 /* uncached_solve(options, vector, mu) (discretizations/base.hh:327-367): freeze lhs and rhs at mu, CG.
  * precision / max_iter mirror Stuff::LA::Solver's option keys.  x_host[n_owned] receives the solution

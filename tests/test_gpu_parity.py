@@ -44,7 +44,7 @@ def test_esv2007_solve_matches_direct_solve(gpu, kind, n):
     d.init()
     m, rp, col, A, b = oracle_system(g, o.const(1.0), o.esv2007_force())
     u_ref = direct_solve(rp, col, A, b)
-    for typ in ("cg.diagonal", "cg.identity"):
+    for typ in ("cg.diagonal", "cg.identity", "cg.blockdiagonal"):
         u, info = d.solve({"type": typ, "precision": 1e-13, "max_iter": 20000}, return_info=True)
         assert info["converged"]
         assert rel(u, u_ref) <= SOL_TOL
