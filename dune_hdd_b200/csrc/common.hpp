@@ -8,6 +8,8 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/hdd_b200.h"
 
@@ -59,6 +61,33 @@ int guarded(F&& f) noexcept {
     set_last_error("unknown error");
     return HDD_ERR_INTERNAL;
   }
+}
+
+// ---- host threading for the O(n_cells) passes over the caller's arrays -----------------------------------------
+inline int worker_count(int64_t n) {
+  const unsigned hw = std::thread::hardware_concurrency();
+  int t = int(hw == 0 ? 4 : (hw > 32 ? 32 : hw));
+  const int64_t by_size = n / 65536 + 1;  // do not spawn threads for small grids
+  return int(by_size < t ? by_size : t);
+}
+
+template <class F>
+void parallel_for_indexed(int64_t n, int nt, F&& f) {  // f(thread, begin, end), contiguous chunks in order
+  if (n <= 0) return;
+  if (nt <= 1) { f(0, int64_t(0), n); return; }
+  std::vector<std::thread> th;
+  const int64_t chunk = (n + nt - 1) / nt;
+  for (int t = 0; t < nt; ++t) {
+    const int64_t a = t * chunk, b = a + chunk < n ? a + chunk : n;
+    if (a >= b) break;
+    th.emplace_back([&f, t, a, b] { f(t, a, b); });
+  }
+  for (auto& x : th) x.join();
+}
+
+template <class F>
+void parallel_for(int64_t n, F&& f) {  // f(begin, end)
+  parallel_for_indexed(n, worker_count(n), [&f](int, int64_t a, int64_t b) { f(a, b); });
 }
 
 // RAII device buffer

@@ -16,6 +16,8 @@ struct DevFn {
   double value;
   const double* cell;  // indexed by LOCAL cell id
   Program prog;
+  int separable;       // expression == px(x[0]) * py(x[1])
+  Program px, py;
 };
 
 // sum_k theta[k] * fn[k]: a frozen affinely decomposed function (problem.with_mu(mu), estimators/swipdg.hh:134).

@@ -87,4 +87,8 @@ HDD_HD inline double eval_program(const Program& p, const double* vars) {
 // Throws hdd::Error(HDD_ERR_WRONG_INPUT) on syntax errors or programs that are too long.
 Program compile_expression(const std::string& text, const std::string& var);
 
+// Tries to write the expression as fx(var[0]) * fy(var[1]) (top-level product whose factors depend on one coordinate
+// each).  Returns false if it is not of that form.  Used for tensor-product quadrature on axis-parallel cells.
+bool compile_separable(const std::string& text, const std::string& var, Program& fx, Program& fy);
+
 }  // namespace hdd

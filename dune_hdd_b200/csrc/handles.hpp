@@ -55,8 +55,6 @@ struct hdd_mesh {
 
   // host copies needed after creation
   std::vector<int32_t> cgid;       // [n_loc]
-  std::vector<int32_t> h_neigh;    // [n_own*nf] local ids
-  std::vector<int32_t> h_sub;      // [n_loc] subdomain of each local cell
   int n_subdomains = 1;
   std::vector<int64_t> sub_cell_offsets;             // [n_subdomains+1] global cell offsets
   std::vector<int64_t> sub_dof_offsets;              // nl * sub_cell_offsets
@@ -112,6 +110,7 @@ struct FnRef {       // index into the device function table, -1 = absent
   int idx = -1;
   int order = 0;
   int kind = 0;      // HDD_FN_*
+  bool separable = false;  // expression of the form g(x[0]) * h(x[1])
   bool zero = false; // constant 0: contributes nothing, kernels are skipped
 };
 

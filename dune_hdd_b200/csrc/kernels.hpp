@@ -6,6 +6,14 @@
 
 namespace hdd {
 
+// ---- K0: device-side localisation of the host grid -------------------------------------------------------------------
+// cgeo[c] from (xy, cell_verts); flag |= 1 if a cube cell is not an axis-parallel rectangle
+void launch_build_geometry(int kind, int32_t n_loc, const double* xy, const int32_t* cell_verts_local, double* cgeo,
+                           int32_t* flag, cudaStream_t s);
+// in place: global neighbour ids of the owned cells -> local ids ([lower halo | owned | upper halo]); flag |= 2 if missing
+void launch_localize_neighbours(int32_t* neigh, int64_t count, int32_t cell_begin, int32_t cell_end, const int32_t* halo,
+                                int32_t n_lo, int32_t n_hi, int32_t* flag, cudaStream_t s);
+
 // ---- K1: pattern ------------------------------------------------------------------------------------------
 // nblk[k] = number of blocks of owned cell k (1 + #neighbours); blk_start is its exclusive prefix sum.
 void launch_count_blocks(const MeshView& m, int64_t* nblk, cudaStream_t s);
@@ -17,8 +25,8 @@ void launch_fill_csr(const MeshView& m, int64_t* rowptr, int32_t* col, cudaStrea
 void launch_assemble_lhs(const MeshView& m, const DevFn* factor_dev, int factor_kind, int factor_order, int polorder,
                          double* values, cudaStream_t s);
 // b += L2Volume(force)
-void launch_rhs_volume(const MeshView& m, const DevFn* force_dev, int force_order, int polorder, double* b,
-                       cudaStream_t s);
+void launch_rhs_volume(const MeshView& m, const DevFn* force_dev, int force_order, bool separable, int polorder,
+                       double* b, cudaStream_t s);
 // b += DirichletBoundarySWIPDG(factor, tensor, dirichlet)
 void launch_rhs_dirichlet(const MeshView& m, const DevFn* factor_dev, int factor_order, const DevFn* dirichlet_dev,
                           int dirichlet_order, int polorder, double* b, cudaStream_t s);

@@ -30,6 +30,44 @@ __device__ __forceinline__ void load_neigh(const int32_t* neigh, int k, int* nb)
   }
 }
 
+__global__ void k_build_geometry(int kind, int32_t n_loc, const double* __restrict__ xy, const int32_t* __restrict__ cv,
+                                 double* __restrict__ cgeo, int32_t* flag) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_loc) return;
+  const double2* p = reinterpret_cast<const double2*>(xy);
+  if (kind == HDD_SIMPLEX2D) {
+    double2* out = reinterpret_cast<double2*>(cgeo + size_t(6) * c);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) out[i] = __ldg(p + cv[size_t(3) * c + i]);
+  } else {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(cv) + c);
+    const double2 a = __ldg(p + v.x), b = __ldg(p + v.y), d = __ldg(p + v.z), e = __ldg(p + v.w);
+    if (a.x != d.x || b.x != e.x || a.y != b.y || d.y != e.y) atomicOr(flag, 1);
+    double2* out = reinterpret_cast<double2*>(cgeo + size_t(4) * c);
+    out[0] = a;
+    out[1] = e;
+  }
+}
+
+__global__ void k_localize_neighbours(int32_t* __restrict__ neigh, int64_t count, int32_t cb, int32_t ce,
+                                      const int32_t* __restrict__ halo, int32_t n_lo, int32_t n_hi, int32_t* flag) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const int32_t g = neigh[t];
+  if (g < 0) return;
+  if (g >= cb && g < ce) { neigh[t] = n_lo + (g - cb); return; }
+  // binary search in the sorted lower / upper halo list
+  int lo = g < cb ? 0 : n_lo, hi = g < cb ? n_lo : n_lo + n_hi;
+  const int base = lo, end = hi;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (halo[mid] < g) lo = mid + 1; else hi = mid;
+  }
+  if (lo >= end || halo[lo] != g) { atomicOr(flag, 2); return; }
+  neigh[t] = g < cb ? lo : (ce - cb) + lo;  // upper halo follows the owned cells: n_lo + n_own + (lo - n_lo)
+  (void)base;
+}
+
 __global__ void k_count_blocks(MeshView m, int64_t* __restrict__ nblk) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= m.n_own) return;
@@ -246,6 +284,35 @@ __global__ void __launch_bounds__(kThreads)
   for (int i = 0; i < NL; ++i) b[size_t(NL) * k + i] += acc[i];
 }
 
+// K3a', Q1 on axis-parallel cells with a separable force f(x,y) = g(x) h(y): the tensor Gauss rule needs only
+// n + n evaluations of the (transcendental) factors per cell instead of n * n of the full expression.
+__global__ void __launch_bounds__(kThreads)
+    k_rhs_volume_cube_separable(MeshView m, const DevFn* __restrict__ fnp, LineRule g1, double* __restrict__ b) {
+  using G = Geo<HDD_CUBE2D>;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m.n_own) return;
+  const int c = m.own0 + k;
+  G g;
+  g.load(m.cgeo, c);
+  double fx[kMaxLinePts], fy[kMaxLinePts];
+  for (int i = 0; i < g1.n; ++i) {
+    const double vx[2] = {g.x0 + g.hx * g1.x[i], 0.0}, vy[2] = {0.0, g.y0 + g.hy * g1.x[i]};
+    fx[i] = eval_program(fnp->px, vx) * g1.w[i];
+    fy[i] = eval_program(fnp->py, vy) * g1.w[i];
+  }
+  // b_i = detj * sum_{q,r} w_q w_r g(x_q) h(y_r) phi_i(xi_q, xi_r), phi tensor: (1-xi | xi) x (1-eta | eta)
+  double sx0 = 0.0, sx1 = 0.0, sy0 = 0.0, sy1 = 0.0;
+  for (int i = 0; i < g1.n; ++i) {
+    sx0 = fma(fx[i], 1.0 - g1.x[i], sx0); sx1 = fma(fx[i], g1.x[i], sx1);
+    sy0 = fma(fy[i], 1.0 - g1.x[i], sy0); sy1 = fma(fy[i], g1.x[i], sy1);
+  }
+  double* dst = b + size_t(4) * k;
+  dst[0] += g.detj * sx0 * sy0;
+  dst[1] += g.detj * sx1 * sy0;
+  dst[2] += g.detj * sx0 * sy1;
+  dst[3] += g.detj * sx1 * sy1;
+}
+
 // K3b.  Functionals::DirichletBoundarySWIPDG (discretizations/swipdg.hh:273-332; SWIPDG::BoundaryRHS):
 // b_i += int_e -g (A grad phi_i . n) + pen g phi_i
 template <int KIND>
@@ -335,6 +402,22 @@ __global__ void k_extract_dinv(MeshView m, const double* __restrict__ values, in
 
 }  // namespace
 
+void launch_build_geometry(int kind, int32_t n_loc, const double* xy, const int32_t* cell_verts_local, double* cgeo,
+                           int32_t* flag, cudaStream_t s) {
+  if (n_loc == 0) return;
+  k_build_geometry<<<grid_for(n_loc, 256), 256, 0, s>>>(kind, n_loc, xy, cell_verts_local, cgeo, flag);
+  count_launch();
+  HDD_CUDA(cudaGetLastError());
+}
+
+void launch_localize_neighbours(int32_t* neigh, int64_t count, int32_t cell_begin, int32_t cell_end, const int32_t* halo,
+                                int32_t n_lo, int32_t n_hi, int32_t* flag, cudaStream_t s) {
+  if (count == 0) return;
+  k_localize_neighbours<<<grid_for(count, 256), 256, 0, s>>>(neigh, count, cell_begin, cell_end, halo, n_lo, n_hi, flag);
+  count_launch();
+  HDD_CUDA(cudaGetLastError());
+}
+
 void launch_count_blocks(const MeshView& m, int64_t* nblk, cudaStream_t s) {
   if (m.n_own == 0) return;
   k_count_blocks<<<grid_for(m.n_own, 256), 256, 0, s>>>(m, nblk);
@@ -392,9 +475,15 @@ void launch_assemble_lhs(const MeshView& m, const DevFn* factor_dev, int factor_
   HDD_CUDA(cudaGetLastError());
 }
 
-void launch_rhs_volume(const MeshView& m, const DevFn* force_dev, int force_order, int polorder, double* b,
-                       cudaStream_t s) {
+void launch_rhs_volume(const MeshView& m, const DevFn* force_dev, int force_order, bool separable, int polorder,
+                       double* b, cudaStream_t s) {
   if (m.n_own == 0) return;
+  if (m.kind == HDD_CUBE2D && separable) {
+    k_rhs_volume_cube_separable<<<grid_for(m.n_own, kThreads), kThreads, 0, s>>>(m, force_dev, line_rule(force_order + polorder), b);
+    count_launch();
+    HDD_CUDA(cudaGetLastError());
+    return;
+  }
   const ElemRule vol = element_rule(m.kind, force_order + polorder);
   if (m.kind == HDD_SIMPLEX2D)
     k_rhs_volume<HDD_SIMPLEX2D><<<grid_for(m.n_own, kThreads), kThreads, 0, s>>>(m, force_dev, vol, b);

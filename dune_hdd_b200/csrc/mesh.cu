@@ -172,6 +172,22 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
     const int nl = m->nl, nf = m->nf;
     const bool whole = (cell_begin == 0 && cell_end == n_cells);
     const int64_t n_own = cell_end - cell_begin;
+    cudaStream_t s = m->stream;
+
+    // ---- validate indices (threaded: these are the only full passes over the host arrays) -------------------
+    {
+      std::atomic<int64_t> bad_vertex{-1}, bad_neigh{-1};
+      parallel_for(n_cells, [&](int64_t c0, int64_t c1) {
+        for (int64_t c = c0; c < c1; ++c)
+          for (int i = 0; i < nl; ++i) {
+            const int32_t v = cell_verts[c * nl + i], g = cell_neigh[c * nf + i];
+            if (v < 0 || v >= n_verts) bad_vertex = c;
+            if (g >= n_cells) bad_neigh = c;
+          }
+      });
+      if (bad_vertex >= 0) HDD_THROW(HDD_ERR_INDEX_OUT_OF_RANGE, "vertex id out of range in cell " << bad_vertex.load());
+      if (bad_neigh >= 0) HDD_THROW(HDD_ERR_INDEX_OUT_OF_RANGE, "neighbour id out of range in cell " << bad_neigh.load());
+    }
 
     // ---- halo: every non-owned cell sharing a vertex with an owned cell (superset of the face neighbours the
     // SpMV needs; the Oswald interpolation needs all cells around a vertex)
@@ -182,60 +198,62 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
     m->n_loc = int32_t(halo_lo.size() + n_own + halo_hi.size());
     m->cgid.resize(size_t(m->n_loc));
     {
-      size_t k = 0;
-      for (int32_t c : halo_lo) m->cgid[k++] = c;
-      for (int64_t c = cell_begin; c < cell_end; ++c) m->cgid[k++] = int32_t(c);
-      for (int32_t c : halo_hi) m->cgid[k++] = c;
+      std::copy(halo_lo.begin(), halo_lo.end(), m->cgid.begin());
+      int32_t* own = m->cgid.data() + halo_lo.size();
+      parallel_for(n_own, [&](int64_t a, int64_t b) {
+        for (int64_t k = a; k < b; ++k) own[k] = int32_t(cell_begin + k);
+      });
+      std::copy(halo_hi.begin(), halo_hi.end(), m->cgid.begin() + halo_lo.size() + n_own);
     }
-    auto to_local = [&](int32_t g) -> int32_t {
-      if (g < 0) return -1;
-      if (g >= cell_begin && g < cell_end) return int32_t(m->own0 + (g - cell_begin));
-      const std::vector<int32_t>& h = g < cell_begin ? halo_lo : halo_hi;
-      auto it = std::lower_bound(h.begin(), h.end(), g);
-      if (it == h.end() || *it != g) HDD_THROW(HDD_ERR_INTERNAL, "neighbour " << g << " missing from the halo");
-      return int32_t((g < cell_begin ? 0 : m->own0 + n_own) + (it - h.begin()));
-    };
 
-    // ---- geometry of all local cells, neighbours / boundary types of the owned ones
-    const int ngeo = kind == HDD_SIMPLEX2D ? 6 : 4;
-    std::vector<double> cgeo(size_t(m->n_loc) * ngeo);
-    for (int32_t lc = 0; lc < m->n_loc; ++lc) {
-      const int64_t g = m->cgid[size_t(lc)];
-      if (kind == HDD_SIMPLEX2D) {
-        for (int i = 0; i < 3; ++i) {
-          const int32_t v = cell_verts[g * 3 + i];
-          if (v < 0 || v >= n_verts) HDD_THROW(HDD_ERR_INDEX_OUT_OF_RANGE, "vertex id " << v << " of cell " << g);
-          cgeo[size_t(lc) * 6 + 2 * i] = xy[2 * v];
-          cgeo[size_t(lc) * 6 + 2 * i + 1] = xy[2 * v + 1];
-        }
-      } else {
-        const int32_t v0 = cell_verts[g * 4 + 0], v1 = cell_verts[g * 4 + 1], v2 = cell_verts[g * 4 + 2],
-                      v3 = cell_verts[g * 4 + 3];
-        for (int32_t v : {v0, v1, v2, v3})
-          if (v < 0 || v >= n_verts) HDD_THROW(HDD_ERR_INDEX_OUT_OF_RANGE, "vertex id " << v << " of cell " << g);
-        // axis-parallel check
-        if (xy[2 * v0] != xy[2 * v2] || xy[2 * v1] != xy[2 * v3] || xy[2 * v0 + 1] != xy[2 * v1 + 1] ||
-            xy[2 * v2 + 1] != xy[2 * v3 + 1])
-          HDD_THROW(HDD_ERR_NOT_IMPLEMENTED, "HDD_CUBE2D cells must be axis-parallel rectangles (cell " << g << ")");
-        cgeo[size_t(lc) * 4 + 0] = xy[2 * v0];
-        cgeo[size_t(lc) * 4 + 1] = xy[2 * v0 + 1];
-        cgeo[size_t(lc) * 4 + 2] = xy[2 * v3];
-        cgeo[size_t(lc) * 4 + 3] = xy[2 * v3 + 1];
+    // ---- device-side localisation: the owned slices of the host arrays are uploaded as they are (no host copy);
+    // kernels build the per-cell geometry records and translate neighbour ids to local numbering
+    {
+      DevBuf<double> d_xy;
+      d_xy.upload(xy, size_t(2) * n_verts, s);
+      DevBuf<int32_t> d_cv;
+      d_cv.alloc(size_t(m->n_loc) * nl);
+      std::vector<int32_t> halo_cv((halo_lo.size() + halo_hi.size()) * nl);
+      for (size_t h = 0; h < halo_lo.size(); ++h)
+        std::memcpy(&halo_cv[h * nl], cell_verts + int64_t(halo_lo[h]) * nl, nl * sizeof(int32_t));
+      for (size_t h = 0; h < halo_hi.size(); ++h)
+        std::memcpy(&halo_cv[(halo_lo.size() + h) * nl], cell_verts + int64_t(halo_hi[h]) * nl, nl * sizeof(int32_t));
+      if (!halo_lo.empty())
+        HDD_CUDA(cudaMemcpyAsync(d_cv.p, halo_cv.data(), halo_lo.size() * nl * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+      if (n_own)
+        HDD_CUDA(cudaMemcpyAsync(d_cv.p + halo_lo.size() * nl, cell_verts + cell_begin * nl, size_t(n_own) * nl * sizeof(int32_t),
+                                 cudaMemcpyHostToDevice, s));
+      if (!halo_hi.empty())
+        HDD_CUDA(cudaMemcpyAsync(d_cv.p + (halo_lo.size() + n_own) * nl, halo_cv.data() + halo_lo.size() * nl,
+                                 halo_hi.size() * nl * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+      const int ngeo = kind == HDD_SIMPLEX2D ? 6 : 4;
+      m->cgeo.alloc(size_t(m->n_loc) * ngeo);
+      DevBuf<int32_t> d_flag;
+      d_flag.alloc(1);
+      d_flag.zero(s);
+      launch_build_geometry(kind, m->n_loc, d_xy.p, d_cv.p, m->cgeo.p, d_flag.p, s);
+      m->neigh.alloc(size_t(n_own) * nf);
+      if (n_own)
+        HDD_CUDA(cudaMemcpyAsync(m->neigh.p, cell_neigh + cell_begin * nf, size_t(n_own) * nf * sizeof(int32_t),
+                                 cudaMemcpyHostToDevice, s));
+      DevBuf<int32_t> d_halo;
+      if (!whole) {
+        std::vector<int32_t> halo(halo_lo);
+        halo.insert(halo.end(), halo_hi.begin(), halo_hi.end());
+        d_halo.upload(halo.data(), halo.size(), s);
+        launch_localize_neighbours(m->neigh.p, int64_t(n_own) * nf, int32_t(cell_begin), int32_t(cell_end), d_halo.p,
+                                   int32_t(halo_lo.size()), int32_t(halo_hi.size()), d_flag.p, s);
       }
-    }
-    m->h_neigh.resize(size_t(n_own) * nf);
-    for (int64_t k = 0; k < n_own; ++k)
-      for (int f = 0; f < nf; ++f) {
-        const int32_t g = cell_neigh[(cell_begin + k) * nf + f];
-        if (g >= n_cells) HDD_THROW(HDD_ERR_INDEX_OUT_OF_RANGE, "neighbour id " << g);
-        m->h_neigh[size_t(k) * nf + f] = to_local(g);
+      m->d_cgid.upload(m->cgid.data(), m->cgid.size(), s);
+      if (boundary_type) {
+        m->has_btype = true;
+        m->btype.upload(boundary_type + cell_begin * nf, size_t(n_own) * nf, s);
       }
-    m->cgeo.upload(cgeo.data(), cgeo.size(), m->stream);
-    m->neigh.upload(m->h_neigh.data(), m->h_neigh.size(), m->stream);
-    m->d_cgid.upload(m->cgid.data(), m->cgid.size(), m->stream);
-    if (boundary_type) {
-      m->has_btype = true;
-      m->btype.upload(boundary_type + cell_begin * nf, size_t(n_own) * nf, m->stream);
+      int32_t flag = 0;
+      HDD_CUDA(cudaMemcpyAsync(&flag, d_flag.p, sizeof(flag), cudaMemcpyDeviceToHost, s));
+      HDD_CUDA(cudaStreamSynchronize(s));
+      if (flag & 1) HDD_THROW(HDD_ERR_NOT_IMPLEMENTED, "HDD_CUBE2D cells must be axis-parallel rectangles");
+      if (flag & 2) HDD_THROW(HDD_ERR_INTERNAL, "a neighbour of an owned cell is missing from the halo");
     }
 
     // ---- local vertices + incidence (vertex -> local DoFs), boundary flags
@@ -278,42 +296,56 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
         const int64_t g = m->cgid[size_t(lc)];
         for (int f = 0; f < nf; ++f)
           if (cell_neigh[g * nf + f] < 0) {
-            const int* fv = kind == HDD_SIMPLEX2D ? kFaceVertsSimplex[f] : kFaceVertsCube[f];
+            const int* fv = kFaceVertsSimplex[f];
             vb[size_t(cvl[size_t(lc) * nl + fv[0]])] = 1;
             vb[size_t(cvl[size_t(lc) * nl + fv[1]])] = 1;
           }
       }
-      m->vptr.upload(vptr.data(), vptr.size(), m->stream);
-      m->vdof.upload(vdof.data(), vdof.size(), m->stream);
-      m->vboundary.upload(vb.data(), vb.size(), m->stream);
-      m->cell_verts.upload(cvl.data() + size_t(m->own0) * nl, size_t(n_own) * nl, m->stream);
+      m->vptr.upload(vptr.data(), vptr.size(), s);
+      m->vdof.upload(vdof.data(), vdof.size(), s);
+      m->vboundary.upload(vb.data(), vb.size(), s);
+      m->cell_verts.upload(cvl.data() + size_t(m->own0) * nl, size_t(n_own) * nl, s);
+      HDD_CUDA(cudaStreamSynchronize(s));
     }
     m->h_cell_verts_loc.swap(cvl);
 
     // ---- subdomains (grid::Multiscale view): contiguous, subdomain-major cell ranges
-    m->h_sub.assign(size_t(m->n_loc), 0);
     if (cell_subdomain) {
-      int32_t prev = 0, mx = 0;
-      for (int64_t c = 0; c < n_cells; ++c) {
-        const int32_t s = cell_subdomain[c];
-        if (s < prev) HDD_THROW(HDD_ERR_WRONG_INPUT, "cells must be numbered subdomain-major (cell " << c << ")");
-        if (s > prev + 1) HDD_THROW(HDD_ERR_WRONG_INPUT, "empty subdomain " << prev + 1);
-        prev = s;
-        mx = std::max(mx, s);
-      }
       if (cell_subdomain[0] != 0) HDD_THROW(HDD_ERR_WRONG_INPUT, "subdomain numbering must start at 0");
-      m->n_subdomains = mx + 1;
-      m->sub_cell_offsets.assign(size_t(m->n_subdomains) + 1, 0);
-      for (int64_t c = 0; c < n_cells; ++c) ++m->sub_cell_offsets[size_t(cell_subdomain[c]) + 1];
-      for (int s = 0; s < m->n_subdomains; ++s) m->sub_cell_offsets[size_t(s) + 1] += m->sub_cell_offsets[size_t(s)];
-      for (int32_t lc = 0; lc < m->n_loc; ++lc) m->h_sub[size_t(lc)] = cell_subdomain[m->cgid[size_t(lc)]];
-      m->sub_neighbours.assign(size_t(m->n_subdomains), {});
-      for (int64_t c = 0; c < n_cells; ++c)
-        for (int f = 0; f < nf; ++f) {
-          const int32_t g = cell_neigh[c * nf + f];
-          if (g >= 0 && cell_subdomain[g] != cell_subdomain[c])
-            m->sub_neighbours[size_t(cell_subdomain[c])].push_back(cell_subdomain[g]);
+      std::atomic<int64_t> bad{-1};
+      parallel_for(n_cells - 1, [&](int64_t a, int64_t b) {
+        for (int64_t c = a; c < b; ++c) {
+          const int32_t d = cell_subdomain[c + 1] - cell_subdomain[c];
+          if (d < 0 || d > 1) bad = c + 1;
         }
+      });
+      if (bad >= 0)
+        HDD_THROW(HDD_ERR_WRONG_INPUT, "cells must be numbered subdomain-major without empty subdomains (cell " << bad.load() << ")");
+      m->n_subdomains = cell_subdomain[n_cells - 1] + 1;
+      m->sub_cell_offsets.assign(size_t(m->n_subdomains) + 1, 0);
+      m->sub_cell_offsets[size_t(m->n_subdomains)] = n_cells;
+      parallel_for(n_cells - 1, [&](int64_t a, int64_t b) {
+        for (int64_t c = a; c < b; ++c)
+          if (cell_subdomain[c + 1] != cell_subdomain[c]) m->sub_cell_offsets[size_t(cell_subdomain[c + 1])] = c + 1;
+      });
+      // neighbouring subdomains: per-thread pair lists, merged
+      const int nt = hdd::worker_count(n_cells);
+      std::vector<std::vector<std::pair<int32_t, int32_t>>> pairs;
+      pairs.resize(size_t(nt));
+      parallel_for_indexed(n_cells, nt, [&](int t, int64_t a, int64_t b) {
+        auto& out = pairs[size_t(t)];
+        for (int64_t c = a; c < b; ++c)
+          for (int f = 0; f < nf; ++f) {
+            const int32_t g = cell_neigh[c * nf + f];
+            if (g >= 0 && cell_subdomain[g] != cell_subdomain[c]) {
+              const std::pair<int32_t, int32_t> pr(cell_subdomain[c], cell_subdomain[g]);
+              if (out.empty() || out.back() != pr) out.push_back(pr);
+            }
+          }
+      });
+      m->sub_neighbours.assign(size_t(m->n_subdomains), {});
+      for (auto& v : pairs)
+        for (auto& pr : v) m->sub_neighbours[size_t(pr.first)].push_back(pr.second);
       for (auto& v : m->sub_neighbours) {
         std::sort(v.begin(), v.end());
         v.erase(std::unique(v.begin(), v.end()), v.end());
@@ -324,7 +356,7 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
       m->sub_neighbours.assign(1, {});
     }
     m->sub_dof_offsets.resize(m->sub_cell_offsets.size());
-    for (size_t s = 0; s < m->sub_cell_offsets.size(); ++s) m->sub_dof_offsets[s] = nl * m->sub_cell_offsets[s];
+    for (size_t k = 0; k < m->sub_cell_offsets.size(); ++k) m->sub_dof_offsets[k] = nl * m->sub_cell_offsets[k];
     // owned subdomains: the owned range must consist of whole subdomains
     m->sub_first = int(std::lower_bound(m->sub_cell_offsets.begin(), m->sub_cell_offsets.end(), cell_begin) -
                        m->sub_cell_offsets.begin());
@@ -335,22 +367,22 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
       HDD_THROW(HDD_ERR_WRONG_INPUT, "the owned cell range must consist of whole subdomains");
     if (n_own == 0) m->sub_last = m->sub_first;
     m->sub_diameter.assign(size_t(m->n_subdomains), 0.0);
-    if (m->n_subdomains > 1 || kind == HDD_SIMPLEX2D) {
-      for (int s = m->sub_first; s < m->sub_last; ++s) {
+    if (kind == HDD_SIMPLEX2D) {  // only the OS2014 estimators (simplex grids) use the diameters
+      for (int sd = m->sub_first; sd < m->sub_last; ++sd) {
         std::vector<std::pair<double, double>> pts;
         // the farthest pair lies on the hull, whose vertices sit on faces leaving the subdomain
-        for (int64_t c = m->sub_cell_offsets[size_t(s)]; c < m->sub_cell_offsets[size_t(s) + 1]; ++c)
+        for (int64_t c = m->sub_cell_offsets[size_t(sd)]; c < m->sub_cell_offsets[size_t(sd) + 1]; ++c)
           for (int f = 0; f < nf; ++f) {
             const int32_t g = cell_neigh[c * nf + f];
-            if (g >= 0 && cell_subdomain && cell_subdomain[g] == s) continue;
+            if (g >= 0 && cell_subdomain && cell_subdomain[g] == sd) continue;
             if (g >= 0 && !cell_subdomain) continue;
-            const int* fv = kind == HDD_SIMPLEX2D ? kFaceVertsSimplex[f] : kFaceVertsCube[f];
+            const int* fv = kFaceVertsSimplex[f];
             for (int e = 0; e < 2; ++e) {
               const int32_t v = cell_verts[c * nl + fv[e]];
               pts.emplace_back(xy[2 * v], xy[2 * v + 1]);
             }
           }
-        m->sub_diameter[size_t(s)] = point_set_diameter(pts);
+        m->sub_diameter[size_t(sd)] = point_set_diameter(pts);
       }
     }
     // chunked segments of the owned cells for deterministic two-level sums
@@ -358,30 +390,29 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
       const int64_t chunk = 8192;
       m->seg_ptr.clear();
       m->seg_sub.clear();
-      for (int s = m->sub_first; s < m->sub_last; ++s) {
-        const int64_t b = m->sub_cell_offsets[size_t(s)] - cell_begin, e = m->sub_cell_offsets[size_t(s) + 1] - cell_begin;
+      for (int sd = m->sub_first; sd < m->sub_last; ++sd) {
+        const int64_t b = m->sub_cell_offsets[size_t(sd)] - cell_begin, e = m->sub_cell_offsets[size_t(sd) + 1] - cell_begin;
         for (int64_t k = b; k < e; k += chunk) {
           m->seg_ptr.push_back(k);
-          m->seg_sub.push_back(s);
+          m->seg_sub.push_back(sd);
         }
       }
       m->seg_ptr.push_back(n_own);
-      m->d_seg_ptr.upload(m->seg_ptr.data(), m->seg_ptr.size(), m->stream);
+      m->d_seg_ptr.upload(m->seg_ptr.data(), m->seg_ptr.size(), s);
     }
 
     // ---- K1 part 1: number of blocks per owned cell and their exclusive prefix sum
     {
       DevBuf<int64_t> nblk;
       nblk.alloc(size_t(n_own) + 1);
-      nblk.zero(m->stream);
+      nblk.zero(s);
       m->blk_start.alloc(size_t(n_own) + 1);
       const MeshView v = m->view(nullptr);
-      launch_count_blocks(v, nblk.p, m->stream);
-      exclusive_scan_i64(nblk.p, m->blk_start.p, n_own + 1, m->stream);  // nblk[n_own] = 0 => total in blk_start[n_own]
-      HDD_CUDA(cudaMemcpyAsync(&m->n_blocks, m->blk_start.p + n_own, sizeof(int64_t), cudaMemcpyDeviceToHost, m->stream));
-      HDD_CUDA(cudaStreamSynchronize(m->stream));
+      launch_count_blocks(v, nblk.p, s);
+      exclusive_scan_i64(nblk.p, m->blk_start.p, n_own + 1, s);  // nblk[n_own] = 0 => total in blk_start[n_own]
+      HDD_CUDA(cudaMemcpyAsync(&m->n_blocks, m->blk_start.p + n_own, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+      HDD_CUDA(cudaStreamSynchronize(s));
     }
-    HDD_CUDA(cudaStreamSynchronize(m->stream));
     *out = m.release();
   });
 }

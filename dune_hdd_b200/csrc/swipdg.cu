@@ -25,6 +25,9 @@ FnRef add_function(hdd_swipdg* h, const hdd_function& f, const char* what) {
   d.value = f.value;
   d.cell = nullptr;
   d.prog.n_ops = 0;
+  d.separable = 0;
+  d.px.n_ops = 0;
+  d.py.n_ops = 0;
   FnRef r;
   r.order = f.order;
   r.kind = f.kind;
@@ -46,11 +49,13 @@ FnRef add_function(hdd_swipdg* h, const hdd_function& f, const char* what) {
     case HDD_FN_EXPRESSION:
       if (!f.expression) HDD_THROW(HDD_ERR_WRONG_INPUT, what << ": expression is NULL");
       d.prog = compile_expression(f.expression, "x");
+      d.separable = compile_separable(f.expression, "x", d.px, d.py) ? 1 : 0;
       break;
     default:
       HDD_THROW(HDD_ERR_WRONG_INPUT, what << ": unknown function kind " << f.kind);
   }
   r.idx = int(h->fn_host.size());
+  r.separable = d.separable != 0;
   h->fn_host.push_back(d);
   return r;
 }
@@ -106,7 +111,7 @@ void assemble_all(hdd_swipdg* h) {
     part.values.zero(s);
     for (const RhsTerm& t : part.terms) {
       if (t.kind == 0) {
-        if (!t.f.zero) launch_rhs_volume(v, h->fn(t.f), t.f.order, h->polorder, part.values.p, s);
+        if (!t.f.zero) launch_rhs_volume(v, h->fn(t.f), t.f.order, t.f.separable, h->polorder, part.values.p, s);
       } else {
         if (!t.f.zero && !t.g.zero)
           launch_rhs_dirichlet(v, h->fn(t.f), t.f.order, h->fn(t.g), t.g.order, h->polorder, part.values.p, s);
@@ -733,7 +738,10 @@ int hdd_block_extract(hdd_swipdg* h, int ss, int nn, int q, hdd_csr* out) {
     std::vector<double> vals(size_t(v1 - v0));
     HDD_CUDA(cudaMemcpyAsync(vals.data(), vals_dev + v0, vals.size() * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
     HDD_CUDA(cudaStreamSynchronize(m->stream));
-    const int64_t col0 = m->sub_cell_offsets[size_t(nn)];
+    std::vector<int32_t> nbr(size_t(k1 - k0) * nf);  // local neighbour ids of the subdomain's cells
+    HDD_CUDA(cudaMemcpyAsync(nbr.data(), m->neigh.p + k0 * nf, nbr.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
+    HDD_CUDA(cudaStreamSynchronize(m->stream));
+    const int64_t col0 = m->sub_cell_offsets[size_t(nn)], col1 = m->sub_cell_offsets[size_t(nn) + 1];
     out->n_rows = (k1 - k0) * nl;
     out->n_cols = (m->sub_cell_offsets[size_t(nn) + 1] - col0) * nl;
     std::vector<int64_t> rowptr(size_t(out->n_rows) + 1, 0);
@@ -745,13 +753,13 @@ int hdd_block_extract(hdd_swipdg* h, int ss, int nn, int q, hdd_csr* out) {
       int nb = 0;
       cells[nb++] = self;
       for (int f = 0; f < nf; ++f)
-        if (m->h_neigh[size_t(k) * nf + f] >= 0) cells[nb++] = m->h_neigh[size_t(k) * nf + f];
+        if (nbr[size_t(k - k0) * nf + f] >= 0) cells[nb++] = nbr[size_t(k - k0) * nf + f];
       std::sort(cells, cells + nb);
       const int64_t base = bs[size_t(k - k0)] * nl * nl - v0;
       for (int i = 0; i < nl; ++i) {
         for (int b = 0; b < nb; ++b) {
-          if (m->h_sub[size_t(cells[b])] != nn) continue;
           const int64_t gc = m->cgid[size_t(cells[b])];
+          if (gc < col0 || gc >= col1) continue;  // not a cell of subdomain nn
           for (int j = 0; j < nl; ++j) {
             col.push_back(int32_t((gc - col0) * nl + j));
             val.push_back(vals[size_t(base + int64_t(i) * nb * nl + b * nl + j)]);
