@@ -9,6 +9,8 @@
 // value array, written with 256-bit stores for Q1 (one full 32-byte sector per block row).
 #include <cub/device/device_scan.cuh>
 
+#include <cstdlib>
+
 #include "kernels.hpp"
 
 namespace hdd {
@@ -258,6 +260,165 @@ __global__ void __launch_bounds__(kThreads)
   store_block<NL>(row0, rs, block_slot<NF>(c, nb, c), D);
 }
 
+// K2 for Q1 on axis-parallel rectangles.  Same integrals as k_assemble_lhs, with two structural facts used at compile
+// time per face F: only the two basis functions of the face's own nodes are non-zero on it (and only the two nodes of
+// the neighbour's opposite face), and normals are +-e_x / +-e_y.  That halves the fp64 work (16 instead of 32 fused
+// multiply-adds per block and quadrature point) and drops every sqrt / division from the face loop.
+template <int F>
+struct CubeFace {
+  static constexpr bool vertical = F < 2;                 // faces 0,1: x = const; faces 2,3: y = const
+  static constexpr double sgn = (F == 0 || F == 2) ? -1.0 : 1.0;
+  static constexpr int a0 = F == 0 ? 0 : F == 1 ? 1 : F == 2 ? 0 : 2;  // own nodes on the face, in the direction of t
+  static constexpr int a1 = F == 0 ? 2 : F == 1 ? 3 : F == 2 ? 1 : 3;
+  static constexpr int b0 = F == 0 ? 1 : F == 1 ? 0 : F == 2 ? 2 : 0;  // neighbour's nodes on its opposite face
+  static constexpr int b1 = F == 0 ? 3 : F == 1 ? 2 : F == 2 ? 3 : 1;
+};
+
+// reference gradients of Q1 at (xi, eta), scaled to physical: gx = d/dxi * ihx, gy = d/deta * ihy
+__device__ __forceinline__ void q1_grads(double xi, double eta, double ihx, double ihy, double* gx, double* gy) {
+  gx[0] = -(1.0 - eta) * ihx; gx[1] = (1.0 - eta) * ihx; gx[2] = -eta * ihx; gx[3] = eta * ihx;
+  gy[0] = -(1.0 - xi) * ihy;  gy[1] = -xi * ihy;         gy[2] = (1.0 - xi) * ihy; gy[3] = xi * ihy;
+}
+
+template <int F, int FK>
+__device__ __forceinline__ void cube_face(const MeshView& m, const DevFn& fn, const Geo<HDD_CUBE2D>& g, const double* K,
+                                          int k, int c, int n, double a_self, const LineRule& fr, double s_in,
+                                          double s_bnd, double* D, double* row0, int rs, const int* nb) {
+  using CF = CubeFace<F>;
+  constexpr int NL = 4;
+  const double h = CF::vertical ? fabs(g.hy) : fabs(g.hx);
+  const double ih = CF::vertical ? fabs(g.ihy) : fabs(g.ihx);
+  const double knx = CF::sgn * (CF::vertical ? K[0] : K[2]);  // (K^T n)_x
+  const double kny = CF::sgn * (CF::vertical ? K[1] : K[3]);
+  const double dm = CF::vertical ? K[0] : K[3];              // n . K n
+  const double xi_own = CF::vertical ? (F == 1 ? 1.0 : 0.0) : 0.0, eta_own = CF::vertical ? 0.0 : (F == 3 ? 1.0 : 0.0);
+  if (n < 0) {
+    if (m.btype && __ldg(m.btype + size_t(4) * k + F) != 1) return;
+    const double pen0 = s_bnd * dm * ih;
+    for (int q = 0; q < fr.n; ++q) {
+      const double t = fr.x[q];
+      const double xi = CF::vertical ? xi_own : t, eta = CF::vertical ? t : eta_own;
+      double gx[NL], gy[NL], B[NL];
+      q1_grads(xi, eta, g.ihx, g.ihy, gx, gy);
+      double a = a_self;
+      if constexpr (FK == HDD_FN_EXPRESSION) a = factor_at<FK>(fn, a_self, g.x0 + g.hx * xi, g.y0 + g.hy * eta);
+      const double w = fr.w[q] * h, wa = w * a, wpen = w * pen0 * a;
+      const double p0 = 1.0 - t, p1 = t;
+#pragma unroll
+      for (int i = 0; i < NL; ++i) B[i] = wa * (gx[i] * knx + gy[i] * kny);
+      // D[i][j] += phi_i A_j - B_i phi_j with A_j = wpen phi_j - B_j; phi is non-zero at a0, a1 only
+#pragma unroll
+      for (int j = 0; j < NL; ++j) {
+        const double Aj = (j == CF::a0 ? wpen * p0 : j == CF::a1 ? wpen * p1 : 0.0) - B[j];
+        D[CF::a0 * NL + j] = fma(p0, Aj, D[CF::a0 * NL + j]);
+        D[CF::a1 * NL + j] = fma(p1, Aj, D[CF::a1 * NL + j]);
+      }
+#pragma unroll
+      for (int i = 0; i < NL; ++i) {
+        D[i * NL + CF::a0] = fma(-B[i], p0, D[i * NL + CF::a0]);
+        D[i * NL + CF::a1] = fma(-B[i], p1, D[i * NL + CF::a1]);
+      }
+    }
+    return;
+  }
+  Geo<HDD_CUBE2D> gn;
+  gn.load(m.cgeo, n);
+  double Kn[4];
+  load_tensor(m.tensor, n, Kn);
+  const double knxp = CF::sgn * (CF::vertical ? Kn[0] : Kn[2]);
+  const double knyp = CF::sgn * (CF::vertical ? Kn[1] : Kn[3]);
+  const double dp = CF::vertical ? Kn[0] : Kn[3];
+  const double isum = 1.0 / (dp + dm);
+  const double gamma = dp * dm * isum, wm = dp * isum, wp = dm * isum;
+  const double pen0 = s_in * gamma * 0.5 * ih;
+  double a_nb = a_self;
+  if constexpr (FK == HDD_FN_CELLWISE) a_nb = __ldg(fn.cell + n);
+  // the neighbour sees the face from its opposite side
+  const double xi_nb = CF::vertical ? (F == 0 ? 1.0 : 0.0) : 0.0, eta_nb = CF::vertical ? 0.0 : (F == 2 ? 1.0 : 0.0);
+  double E[NL * NL];
+#pragma unroll
+  for (int t2 = 0; t2 < NL * NL; ++t2) E[t2] = 0.0;
+  for (int q = 0; q < fr.n; ++q) {
+    const double t = fr.x[q];
+    const double xi = CF::vertical ? xi_own : t, eta = CF::vertical ? t : eta_own;
+    double gx[NL], gy[NL], B[NL], Cc[NL];
+    double am = a_self;
+    if constexpr (FK == HDD_FN_EXPRESSION) am = factor_at<FK>(fn, a_self, g.x0 + g.hx * xi, g.y0 + g.hy * eta);
+    const double ap = (FK == HDD_FN_EXPRESSION) ? am : a_nb;
+    const double w = fr.w[q] * h;
+    const double wpen = w * pen0 * (am + ap), wwm = w * wm * am, wwp = w * wp * ap;
+    const double p0 = 1.0 - t, p1 = t;
+    q1_grads(xi, eta, g.ihx, g.ihy, gx, gy);
+#pragma unroll
+    for (int i = 0; i < NL; ++i) B[i] = wwm * (gx[i] * knx + gy[i] * kny);
+    q1_grads(CF::vertical ? xi_nb : t, CF::vertical ? t : eta_nb, gn.ihx, gn.ihy, gx, gy);
+#pragma unroll
+    for (int j = 0; j < NL; ++j)
+      Cc[j] = -wwp * (gx[j] * knxp + gy[j] * knyp) - (j == CF::b0 ? wpen * p0 : j == CF::b1 ? wpen * p1 : 0.0);
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      const double Aj = (j == CF::a0 ? wpen * p0 : j == CF::a1 ? wpen * p1 : 0.0) - B[j];
+      D[CF::a0 * NL + j] = fma(p0, Aj, D[CF::a0 * NL + j]);      // en/en: phi^-_i A_j
+      D[CF::a1 * NL + j] = fma(p1, Aj, D[CF::a1 * NL + j]);
+      E[CF::a0 * NL + j] = fma(p0, Cc[j], E[CF::a0 * NL + j]);   // en/ne: phi^-_i C_j
+      E[CF::a1 * NL + j] = fma(p1, Cc[j], E[CF::a1 * NL + j]);
+    }
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      D[i * NL + CF::a0] = fma(-B[i], p0, D[i * NL + CF::a0]);   // en/en: -B_i phi^-_j
+      D[i * NL + CF::a1] = fma(-B[i], p1, D[i * NL + CF::a1]);
+      E[i * NL + CF::b0] = fma(B[i], p0, E[i * NL + CF::b0]);    // en/ne: +B_i phi^+_j
+      E[i * NL + CF::b1] = fma(B[i], p1, E[i * NL + CF::b1]);
+    }
+  }
+  store_block<NL>(row0, rs, block_slot<4>(c, nb, n), E);
+}
+
+template <int FK>
+__global__ void __launch_bounds__(kThreads, 3)
+    k_assemble_lhs_cube(MeshView m, const DevFn* __restrict__ fnp, ElemRule vol, LineRule fr, double s_in, double s_bnd,
+                        double* __restrict__ vals) {
+  using G = Geo<HDD_CUBE2D>;
+  constexpr int NL = 4, NF = 4;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m.n_own) return;
+  const int c = m.own0 + k;
+  const DevFn& fn = *fnp;
+  G g;
+  g.load(m.cgeo, c);
+  double K[4];
+  load_tensor(m.tensor, c, K);
+  int nb[NF];
+  load_neigh<NF>(m.neigh, k, nb);
+  const int nblk = block_count<NF>(nb);
+  const int rs = nblk * NL;
+  double* row0 = vals + m.blk_start[k] * (NL * NL);
+  double a_self = 0.0;
+  if constexpr (FK == HDD_FN_CONSTANT) a_self = fn.value;
+  if constexpr (FK == HDD_FN_CELLWISE) a_self = __ldg(fn.cell + c);
+  double D[NL * NL];
+#pragma unroll
+  for (int t = 0; t < NL * NL; ++t) D[t] = 0.0;
+  for (int q = 0; q < vol.n; ++q) {
+    double gx[NL], gy[NL];
+    q1_grads(vol.x[q], vol.y[q], g.ihx, g.ihy, gx, gy);
+    const double wa = vol.w[q] * g.detj *
+                      factor_at<FK>(fn, a_self, g.x0 + g.hx * vol.x[q], g.y0 + g.hy * vol.y[q]);
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      const double fx = wa * (K[0] * gx[j] + K[1] * gy[j]);
+      const double fy = wa * (K[2] * gx[j] + K[3] * gy[j]);
+#pragma unroll
+      for (int i = 0; i < NL; ++i) D[i * NL + j] = fma(fx, gx[i], fma(fy, gy[i], D[i * NL + j]));
+    }
+  }
+  cube_face<0, FK>(m, fn, g, K, k, c, nb[0], a_self, fr, s_in, s_bnd, D, row0, rs, nb);
+  cube_face<1, FK>(m, fn, g, K, k, c, nb[1], a_self, fr, s_in, s_bnd, D, row0, rs, nb);
+  cube_face<2, FK>(m, fn, g, K, k, c, nb[2], a_self, fr, s_in, s_bnd, D, row0, rs, nb);
+  cube_face<3, FK>(m, fn, g, K, k, c, nb[3], a_self, fr, s_in, s_bnd, D, row0, rs, nb);
+  store_block<NL>(row0, rs, block_slot<NF>(c, nb, c), D);
+}
+
 // K3a.  Functionals::L2Volume(force) (discretizations/swipdg.hh:253-271): rule of order(f) + p.
 template <int KIND>
 __global__ void __launch_bounds__(kThreads)
@@ -467,10 +628,24 @@ void launch_assemble_lhs(const MeshView& m, const DevFn* factor_dev, int factor_
   const ElemRule vol = element_rule(m.kind, factor_order + 2 * (polorder - 1));
   const LineRule fr = line_rule(factor_order + 2 * polorder);
   const double si = sigma_inner(polorder), sb = sigma_boundary(polorder);
-  if (m.kind == HDD_SIMPLEX2D)
-    assemble_dispatch<HDD_SIMPLEX2D>(factor_kind, grid_for(m.n_own, kThreads), s, m, factor_dev, vol, fr, si, sb, values);
-  else
-    assemble_dispatch<HDD_CUBE2D>(factor_kind, grid_for(m.n_own, kThreads), s, m, factor_dev, vol, fr, si, sb, values);
+  const int blocks = grid_for(m.n_own, kThreads);
+  static const bool generic_cube = [] { const char* e = std::getenv("HDD_ASSEMBLY_GENERIC"); return e && e[0] == '1'; }();
+  if (m.kind == HDD_SIMPLEX2D) {
+    assemble_dispatch<HDD_SIMPLEX2D>(factor_kind, blocks, s, m, factor_dev, vol, fr, si, sb, values);
+  } else if (generic_cube) {
+    assemble_dispatch<HDD_CUBE2D>(factor_kind, blocks, s, m, factor_dev, vol, fr, si, sb, values);
+  } else {
+    switch (factor_kind) {
+      case HDD_FN_CONSTANT:
+        k_assemble_lhs_cube<HDD_FN_CONSTANT><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+        break;
+      case HDD_FN_CELLWISE:
+        k_assemble_lhs_cube<HDD_FN_CELLWISE><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+        break;
+      default:
+        k_assemble_lhs_cube<HDD_FN_EXPRESSION><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+    }
+  }
   count_launch();
   HDD_CUDA(cudaGetLastError());
 }
