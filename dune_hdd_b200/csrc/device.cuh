@@ -25,7 +25,7 @@ struct DevCombo {
   int n;
   int order;
   double theta[kMaxParts];
-  const DevFn* fn[kMaxParts];
+  int idx[kMaxParts];  // indices into the handle's function table
 };
 
 // Local mesh of one rank: cells [0, n_loc) sorted by global id = [lower halo | owned | upper halo].
@@ -50,9 +50,9 @@ __device__ __forceinline__ double fn_eval(const DevFn& f, int cell, double x, do
   return eval_program(f.prog, v);
 }
 
-__device__ __forceinline__ double combo_eval(const DevCombo& c, int cell, double x, double y) {
+__device__ __forceinline__ double combo_eval(const DevCombo& c, const DevFn* table, int cell, double x, double y) {
   double s = 0.0;
-  for (int k = 0; k < c.n; ++k) s += c.theta[k] * fn_eval(*c.fn[k], cell, x, y);
+  for (int k = 0; k < c.n; ++k) s += c.theta[k] * fn_eval(table[c.idx[k]], cell, x, y);
   return s;
 }
 

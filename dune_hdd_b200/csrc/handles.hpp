@@ -180,5 +180,6 @@ struct hdd_swipdg {
 
   hdd::MeshView view() const { return mesh->view(has_tensor ? tensor.p : nullptr); }
   const hdd::DevFn* fn(const hdd::FnRef& r) const { return fn_dev.p + r.idx; }
+  const hdd::DevFn& fn_h(const hdd::FnRef& r) const { return fn_host[size_t(r.idx)]; }
   ~hdd_swipdg();
 };

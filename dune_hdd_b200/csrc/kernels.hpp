@@ -21,14 +21,15 @@ void exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, cudaStream_t
 void launch_fill_csr(const MeshView& m, int64_t* rowptr, int32_t* col, cudaStream_t s);
 
 // ---- K2/K3: assembly ----------------------------------------------------------------------------------------
-// one affine part of the system matrix: values in CSR order of the owned rows
-void launch_assemble_lhs(const MeshView& m, const DevFn* factor_dev, int factor_kind, int factor_order, int polorder,
+// one affine part of the system matrix: values in CSR order of the owned rows.  Function descriptors travel by value
+// (kernel parameter space = constant bank), so the expression programs are never fetched from global memory.
+void launch_assemble_lhs(const MeshView& m, const DevFn& factor_dev, int factor_kind, int factor_order, int polorder,
                          double* values, cudaStream_t s);
 // b += L2Volume(force)
-void launch_rhs_volume(const MeshView& m, const DevFn* force_dev, int force_order, bool separable, int polorder,
+void launch_rhs_volume(const MeshView& m, const DevFn& force_dev, int force_order, bool separable, int polorder,
                        double* b, cudaStream_t s);
 // b += DirichletBoundarySWIPDG(factor, tensor, dirichlet)
-void launch_rhs_dirichlet(const MeshView& m, const DevFn* factor_dev, int factor_order, const DevFn* dirichlet_dev,
+void launch_rhs_dirichlet(const MeshView& m, const DevFn& factor_dev, int factor_order, const DevFn& dirichlet_dev,
                           int dirichlet_order, int polorder, double* b, cudaStream_t s);
 
 // ---- K4: freeze -----------------------------------------------------------------------------------------------
@@ -85,7 +86,9 @@ void launch_cg_direction(const MeshView& m, const CgBuffers& c, int parity, cuda
 // ---- K7-K10: estimators ---------------------------------------------------------------------------------------
 struct IndicatorArgs {
   DevCombo a_mu, a_hat, a_bar, a_cut, a_min, a_max;
-  const DevFn* force;
+  const DevFn* fn_table;       // the handle's function table (global memory); staged in shared memory by the kernel
+  int n_fn;
+  int force_idx;
   int force_order;
   const double* u_local;       // local vector
   const double* vertex_mean;   // [n_verts_local], Oswald values (0 on the boundary)

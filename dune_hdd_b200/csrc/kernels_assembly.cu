@@ -141,14 +141,13 @@ __device__ __forceinline__ double factor_at(const DevFn& fn, double a_cell, doub
 
 template <int KIND, int FK>
 __global__ void __launch_bounds__(kThreads)
-    k_assemble_lhs(MeshView m, const DevFn* __restrict__ fnp, ElemRule vol, LineRule fr, double s_in, double s_bnd,
+    k_assemble_lhs(MeshView m, const __grid_constant__ DevFn fn, ElemRule vol, LineRule fr, double s_in, double s_bnd,
                    double* __restrict__ vals) {
   using G = Geo<KIND>;
   constexpr int NL = G::NL, NF = G::NF;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= m.n_own) return;
   const int c = m.own0 + k;
-  const DevFn& fn = *fnp;
   G g;
   g.load(m.cgeo, c);
   double K[4];
@@ -282,8 +281,9 @@ __device__ __forceinline__ void q1_grads(double xi, double eta, double ihx, doub
 
 template <int F, int FK>
 __device__ __forceinline__ void cube_face(const MeshView& m, const DevFn& fn, const Geo<HDD_CUBE2D>& g, const double* K,
-                                          int k, int c, int n, double a_self, const LineRule& fr, double s_in,
-                                          double s_bnd, double* D, double* row0, int rs, const int* nb) {
+                                          int k, int c, int n, double nb_ihx, double nb_ihy, double a_self,
+                                          const LineRule& fr, double s_in, double s_bnd, double* D, double* row0, int rs,
+                                          const int* nb) {
   using CF = CubeFace<F>;
   constexpr int NL = 4;
   const double h = CF::vertical ? fabs(g.hy) : fabs(g.hx);
@@ -321,8 +321,6 @@ __device__ __forceinline__ void cube_face(const MeshView& m, const DevFn& fn, co
     }
     return;
   }
-  Geo<HDD_CUBE2D> gn;
-  gn.load(m.cgeo, n);
   double Kn[4];
   load_tensor(m.tensor, n, Kn);
   const double knxp = CF::sgn * (CF::vertical ? Kn[0] : Kn[2]);
@@ -351,7 +349,7 @@ __device__ __forceinline__ void cube_face(const MeshView& m, const DevFn& fn, co
     q1_grads(xi, eta, g.ihx, g.ihy, gx, gy);
 #pragma unroll
     for (int i = 0; i < NL; ++i) B[i] = wwm * (gx[i] * knx + gy[i] * kny);
-    q1_grads(CF::vertical ? xi_nb : t, CF::vertical ? t : eta_nb, gn.ihx, gn.ihy, gx, gy);
+    q1_grads(CF::vertical ? xi_nb : t, CF::vertical ? t : eta_nb, nb_ihx, nb_ihy, gx, gy);
 #pragma unroll
     for (int j = 0; j < NL; ++j)
       Cc[j] = -wwp * (gx[j] * knxp + gy[j] * knyp) - (j == CF::b0 ? wpen * p0 : j == CF::b1 ? wpen * p1 : 0.0);
@@ -376,14 +374,13 @@ __device__ __forceinline__ void cube_face(const MeshView& m, const DevFn& fn, co
 
 template <int FK>
 __global__ void __launch_bounds__(kThreads, 3)
-    k_assemble_lhs_cube(MeshView m, const DevFn* __restrict__ fnp, ElemRule vol, LineRule fr, double s_in, double s_bnd,
+    k_assemble_lhs_cube(MeshView m, const __grid_constant__ DevFn fn, ElemRule vol, LineRule fr, double s_in, double s_bnd,
                         double* __restrict__ vals) {
   using G = Geo<HDD_CUBE2D>;
   constexpr int NL = 4, NF = 4;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= m.n_own) return;
   const int c = m.own0 + k;
-  const DevFn& fn = *fnp;
   G g;
   g.load(m.cgeo, c);
   double K[4];
@@ -396,6 +393,22 @@ __global__ void __launch_bounds__(kThreads, 3)
   double a_self = 0.0;
   if constexpr (FK == HDD_FN_CONSTANT) a_self = fn.value;
   if constexpr (FK == HDD_FN_CELLWISE) a_self = __ldg(fn.cell + c);
+  // all four neighbour records are requested up front: one memory latency instead of four in the face loop
+  double nihx[NF], nihy[NF];
+  {
+    double2 lo[NF], hi[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      const double2* p = reinterpret_cast<const double2*>(m.cgeo + size_t(4) * (nb[f] >= 0 ? nb[f] : c));
+      lo[f] = __ldg(p);
+      hi[f] = __ldg(p + 1);
+    }
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      nihx[f] = 1.0 / (hi[f].x - lo[f].x);
+      nihy[f] = 1.0 / (hi[f].y - lo[f].y);
+    }
+  }
   double D[NL * NL];
 #pragma unroll
   for (int t = 0; t < NL * NL; ++t) D[t] = 0.0;
@@ -412,17 +425,17 @@ __global__ void __launch_bounds__(kThreads, 3)
       for (int i = 0; i < NL; ++i) D[i * NL + j] = fma(fx, gx[i], fma(fy, gy[i], D[i * NL + j]));
     }
   }
-  cube_face<0, FK>(m, fn, g, K, k, c, nb[0], a_self, fr, s_in, s_bnd, D, row0, rs, nb);
-  cube_face<1, FK>(m, fn, g, K, k, c, nb[1], a_self, fr, s_in, s_bnd, D, row0, rs, nb);
-  cube_face<2, FK>(m, fn, g, K, k, c, nb[2], a_self, fr, s_in, s_bnd, D, row0, rs, nb);
-  cube_face<3, FK>(m, fn, g, K, k, c, nb[3], a_self, fr, s_in, s_bnd, D, row0, rs, nb);
+  cube_face<0, FK>(m, fn, g, K, k, c, nb[0], nihx[0], nihy[0], a_self, fr, s_in, s_bnd, D, row0, rs, nb);
+  cube_face<1, FK>(m, fn, g, K, k, c, nb[1], nihx[1], nihy[1], a_self, fr, s_in, s_bnd, D, row0, rs, nb);
+  cube_face<2, FK>(m, fn, g, K, k, c, nb[2], nihx[2], nihy[2], a_self, fr, s_in, s_bnd, D, row0, rs, nb);
+  cube_face<3, FK>(m, fn, g, K, k, c, nb[3], nihx[3], nihy[3], a_self, fr, s_in, s_bnd, D, row0, rs, nb);
   store_block<NL>(row0, rs, block_slot<NF>(c, nb, c), D);
 }
 
 // K3a.  Functionals::L2Volume(force) (discretizations/swipdg.hh:253-271): rule of order(f) + p.
 template <int KIND>
 __global__ void __launch_bounds__(kThreads)
-    k_rhs_volume(MeshView m, const DevFn* __restrict__ fnp, ElemRule vol, double* __restrict__ b) {
+    k_rhs_volume(MeshView m, const __grid_constant__ DevFn fn, ElemRule vol, double* __restrict__ b) {
   using G = Geo<KIND>;
   constexpr int NL = G::NL;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -437,7 +450,7 @@ __global__ void __launch_bounds__(kThreads)
     double phi[NL], gx[NL], gy[NL], x, y;
     g.basis(vol.x[q], vol.y[q], phi, gx, gy);
     g.to_global(vol.x[q], vol.y[q], x, y);
-    const double fv = fn_eval(*fnp, c, x, y) * vol.w[q] * g.detj;
+    const double fv = fn_eval(fn, c, x, y) * vol.w[q] * g.detj;
 #pragma unroll
     for (int i = 0; i < NL; ++i) acc[i] += fv * phi[i];
   }
@@ -448,7 +461,7 @@ __global__ void __launch_bounds__(kThreads)
 // K3a', Q1 on axis-parallel cells with a separable force f(x,y) = g(x) h(y): the tensor Gauss rule needs only
 // n + n evaluations of the (transcendental) factors per cell instead of n * n of the full expression.
 __global__ void __launch_bounds__(kThreads)
-    k_rhs_volume_cube_separable(MeshView m, const DevFn* __restrict__ fnp, LineRule g1, double* __restrict__ b) {
+    k_rhs_volume_cube_separable(MeshView m, const __grid_constant__ DevFn fn, LineRule g1, double* __restrict__ b) {
   using G = Geo<HDD_CUBE2D>;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= m.n_own) return;
@@ -458,8 +471,8 @@ __global__ void __launch_bounds__(kThreads)
   double fx[kMaxLinePts], fy[kMaxLinePts];
   for (int i = 0; i < g1.n; ++i) {
     const double vx[2] = {g.x0 + g.hx * g1.x[i], 0.0}, vy[2] = {0.0, g.y0 + g.hy * g1.x[i]};
-    fx[i] = eval_program(fnp->px, vx) * g1.w[i];
-    fy[i] = eval_program(fnp->py, vy) * g1.w[i];
+    fx[i] = eval_program(fn.px, vx) * g1.w[i];
+    fy[i] = eval_program(fn.py, vy) * g1.w[i];
   }
   // b_i = detj * sum_{q,r} w_q w_r g(x_q) h(y_r) phi_i(xi_q, xi_r), phi tensor: (1-xi | xi) x (1-eta | eta)
   double sx0 = 0.0, sx1 = 0.0, sy0 = 0.0, sy1 = 0.0;
@@ -478,7 +491,7 @@ __global__ void __launch_bounds__(kThreads)
 // b_i += int_e -g (A grad phi_i . n) + pen g phi_i
 template <int KIND>
 __global__ void __launch_bounds__(kThreads)
-    k_rhs_dirichlet(MeshView m, const DevFn* __restrict__ facp, const DevFn* __restrict__ dirp, LineRule fr,
+    k_rhs_dirichlet(MeshView m, const __grid_constant__ DevFn fac, const __grid_constant__ DevFn dir, LineRule fr,
                     double s_bnd, double* __restrict__ b) {
   using G = Geo<KIND>;
   constexpr int NL = G::NL, NF = G::NF;
@@ -508,7 +521,7 @@ __global__ void __launch_bounds__(kThreads)
       double xi, eta, phi[NL], gx[NL], gy[NL];
       g.to_local(x, y, xi, eta);
       g.basis(xi, eta, phi, gx, gy);
-      const double a = fn_eval(*facp, c, x, y), gd = fn_eval(*dirp, c, x, y);
+      const double a = fn_eval(fac, c, x, y), gd = fn_eval(dir, c, x, y);
       const double pen = s_bnd * dm * a / e.h;
       const double w = fr.w[q] * e.h;
 #pragma unroll
@@ -608,7 +621,7 @@ void launch_fill_csr(const MeshView& m, int64_t* rowptr, int32_t* col, cudaStrea
 }
 
 template <int KIND>
-static void assemble_dispatch(int fk, int blocks, cudaStream_t s, const MeshView& m, const DevFn* fn, const ElemRule& vol,
+static void assemble_dispatch(int fk, int blocks, cudaStream_t s, const MeshView& m, const DevFn& fn, const ElemRule& vol,
                               const LineRule& fr, double si, double sb, double* values) {
   switch (fk) {
     case HDD_FN_CONSTANT:
@@ -622,7 +635,7 @@ static void assemble_dispatch(int fk, int blocks, cudaStream_t s, const MeshView
   }
 }
 
-void launch_assemble_lhs(const MeshView& m, const DevFn* factor_dev, int factor_kind, int factor_order, int polorder,
+void launch_assemble_lhs(const MeshView& m, const DevFn& factor_dev, int factor_kind, int factor_order, int polorder,
                          double* values, cudaStream_t s) {
   if (m.n_own == 0) return;
   const ElemRule vol = element_rule(m.kind, factor_order + 2 * (polorder - 1));
@@ -650,7 +663,7 @@ void launch_assemble_lhs(const MeshView& m, const DevFn* factor_dev, int factor_
   HDD_CUDA(cudaGetLastError());
 }
 
-void launch_rhs_volume(const MeshView& m, const DevFn* force_dev, int force_order, bool separable, int polorder,
+void launch_rhs_volume(const MeshView& m, const DevFn& force_dev, int force_order, bool separable, int polorder,
                        double* b, cudaStream_t s) {
   if (m.n_own == 0) return;
   if (m.kind == HDD_CUBE2D && separable) {
@@ -668,7 +681,7 @@ void launch_rhs_volume(const MeshView& m, const DevFn* force_dev, int force_orde
   HDD_CUDA(cudaGetLastError());
 }
 
-void launch_rhs_dirichlet(const MeshView& m, const DevFn* factor_dev, int factor_order, const DevFn* dirichlet_dev,
+void launch_rhs_dirichlet(const MeshView& m, const DevFn& factor_dev, int factor_order, const DevFn& dirichlet_dev,
                           int dirichlet_order, int polorder, double* b, cudaStream_t s) {
   if (m.n_own == 0) return;
   const LineRule fr = line_rule(factor_order + dirichlet_order + 2 * polorder);

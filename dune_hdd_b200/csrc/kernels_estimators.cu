@@ -37,6 +37,17 @@ __global__ void __launch_bounds__(128)
     k_indicators(MeshView m, IndicatorArgs a, const IndicatorRules* __restrict__ rules, double s_in, double s_bnd) {
   using G = Geo<HDD_SIMPLEX2D>;
   constexpr int NL = 3;
+  // the data functions (expression programs included) are staged in shared memory once per block
+  extern __shared__ __align__(16) unsigned char fn_smem[];
+  DevFn* table = reinterpret_cast<DevFn*>(fn_smem);
+  {
+    const int words = a.n_fn * int(sizeof(DevFn) / 4);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.fn_table);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(fn_smem);
+    for (int w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
+  }
+  __syncthreads();
+  const DevFn& force = table[a.force_idx];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= m.n_own) return;
   const int c = m.own0 + k;
@@ -66,7 +77,7 @@ __global__ void __launch_bounds__(128)
     for (int q = 0; q < R.nc.n; ++q) {
       double x, y;
       g.to_global(R.nc.x[q], R.nc.y[q], x, y);
-      s += R.nc.w[q] * g.detj * combo_eval(a.a_bar, c, x, y) * e;
+      s += R.nc.w[q] * g.detj * combo_eval(a.a_bar, table, c, x, y) * e;
     }
     a.out[0 * n + k] = s;
     v_nc = s;
@@ -76,7 +87,7 @@ __global__ void __launch_bounds__(128)
   for (int q = 0; q < R.p0.n; ++q) {
     double x, y;
     g.to_global(R.p0.x[q], R.p0.y[q], x, y);
-    f0 += R.p0.w[q] * fn_eval(*a.force, c, x, y);
+    f0 += R.p0.w[q] * fn_eval(force, c, x, y);
   }
   f0 /= 0.5;
   const double hT = g.diameter();
@@ -84,7 +95,7 @@ __global__ void __launch_bounds__(128)
   for (int q = 0; q < R.cut.n; ++q) {
     double x, y;
     g.to_global(R.cut.x[q], R.cut.y[q], x, y);
-    cT = fmin(cT, combo_eval(a.a_cut, c, x, y) * lam_min);
+    cT = fmin(cT, combo_eval(a.a_cut, table, c, x, y) * lam_min);
   }
   const double cutoff = hT * hT / (kPi * kPi * cT);
   {
@@ -92,7 +103,7 @@ __global__ void __launch_bounds__(128)
     for (int q = 0; q < R.res.n; ++q) {
       double x, y;
       g.to_global(R.res.x[q], R.res.y[q], x, y);
-      const double d = fn_eval(*a.force, c, x, y) - f0;
+      const double d = fn_eval(force, c, x, y) - f0;
       rs += R.res.w[q] * g.detj * d * d;
     }
     a.out[1 * n + k] = rs;
@@ -104,12 +115,12 @@ __global__ void __launch_bounds__(128)
     for (int q = 0; q < R.amin.n; ++q) {
       double x, y;
       g.to_global(R.amin.x[q], R.amin.y[q], x, y);
-      mn = fmin(mn, combo_eval(a.a_min, c, x, y));
+      mn = fmin(mn, combo_eval(a.a_min, table, c, x, y));
     }
     for (int q = 0; q < R.amax.n; ++q) {
       double x, y;
       g.to_global(R.amax.x[q], R.amax.y[q], x, y);
-      mn = fmin(mn, combo_eval(a.a_max, c, x, y));
+      mn = fmin(mn, combo_eval(a.a_max, table, c, x, y));
     }
     a.out[6 * n + k] = mn * lam_min;
   }
@@ -128,7 +139,7 @@ __global__ void __launch_bounds__(128)
         g.to_local(x, y, xi, eta);
         g.basis(xi, eta, ph, hx, hy);
         const double uv = u[0] * ph[0] + u[1] * ph[1] + u[2] * ph[2];
-        const double am = combo_eval(a.a_mu, c, x, y);
+        const double am = combo_eval(a.a_mu, table, c, x, y);
         const double pen = s_bnd * dm * am / e.h;
         const double flux = am * ((K[0] * ux + K[1] * uy) * e.nx + (K[2] * ux + K[3] * uy) * e.ny);
         s += R.face.w[q] * e.h * (-flux + pen * uv);
@@ -156,7 +167,7 @@ __global__ void __launch_bounds__(128)
         gn.basis(xi, eta, qh, hx, hy);
         const double um = u[0] * ph[0] + u[1] * ph[1] + u[2] * ph[2];
         const double up = un[0] * qh[0] + un[1] * qh[1] + un[2] * qh[2];
-        const double am = combo_eval(a.a_mu, c, x, y), ap = combo_eval(a.a_mu, nbc, x, y);
+        const double am = combo_eval(a.a_mu, table, c, x, y), ap = combo_eval(a.a_mu, table, nbc, x, y);
         const double pen = s_in * gamma * 0.5 * (am + ap) / e.h;
         const double fm = am * ((K[0] * ux + K[1] * uy) * e.nx + (K[2] * ux + K[3] * uy) * e.ny);
         const double fp = ap * ((Kn[0] * vx + Kn[1] * vy) * e.nx + (Kn[2] * vx + Kn[3] * vy) * e.ny);
@@ -176,7 +187,7 @@ __global__ void __launch_bounds__(128)
       g.to_global(R.df.x[q], R.df.y[q], x, y);
       const double t0 = (Gf[0] * (x - g.vx[2]) + Gf[1] * (x - g.vx[1]) + Gf[2] * (x - g.vx[0])) / (2.0 * area);
       const double t1 = (Gf[0] * (y - g.vy[2]) + Gf[1] * (y - g.vy[1]) + Gf[2] * (y - g.vy[0])) / (2.0 * area);
-      const double ah = combo_eval(a.a_hat, c, x, y), am = combo_eval(a.a_mu, c, x, y);
+      const double ah = combo_eval(a.a_hat, table, c, x, y), am = combo_eval(a.a_mu, table, c, x, y);
       const double w = R.df.w[q] * g.detj;
       double v0 = ah * kux + t0, v1 = ah * kuy + t1;
       s += w * (v0 * (k00 * v0 + k01 * v1) + v1 * (k10 * v0 + k11 * v1)) / ah;
@@ -194,7 +205,7 @@ __global__ void __launch_bounds__(128)
     for (int q = 0; q < R.res.n; ++q) {
       double x, y;
       g.to_global(R.res.x[q], R.res.y[q], x, y);
-      const double d = fn_eval(*a.force, c, x, y) - div;
+      const double d = fn_eval(force, c, x, y) - div;
       s += R.res.w[q] * g.detj * d * d;
     }
     a.out[5 * n + k] = cutoff * s;
@@ -249,7 +260,10 @@ void launch_indicators(const MeshView& m, const IndicatorArgs& a, int polorder, 
   IndicatorRules* dR = nullptr;
   HDD_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dR), sizeof(R), s));
   HDD_CUDA(cudaMemcpyAsync(dR, &R, sizeof(R), cudaMemcpyHostToDevice, s));
-  k_indicators<<<(m.n_own + 127) / 128, 128, 0, s>>>(m, a, dR, sigma_inner(p), sigma_boundary(p));
+  static_assert(sizeof(DevFn) % 4 == 0, "DevFn must be word sized");
+  const size_t fn_bytes = size_t(a.n_fn) * sizeof(DevFn);
+  if (fn_bytes > 48 * 1024) HDD_THROW(HDD_ERR_NOT_IMPLEMENTED, "too many data functions for the estimator kernel");
+  k_indicators<<<(m.n_own + 127) / 128, 128, fn_bytes, s>>>(m, a, dR, sigma_inner(p), sigma_boundary(p));
   count_launch();
   HDD_CUDA(cudaGetLastError());
   HDD_CUDA(cudaStreamSynchronize(s));  // R lives on this stack frame until the copy has happened

@@ -6,7 +6,6 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
-#include <unordered_map>
 
 #include "handles.hpp"
 #include "partition.hpp"
@@ -262,24 +261,16 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
     const bool need_verts = !whole || kind == HDD_SIMPLEX2D;
     std::vector<int32_t> cvl(need_verts ? size_t(m->n_loc) * nl : 0);
     if (need_verts) {
-      std::unordered_map<int32_t, int32_t> vmap;
-      std::vector<int32_t> dense;
-      if (whole) dense.assign(size_t(n_verts), -1);
+      std::vector<int32_t> dense(size_t(n_verts), -1);  // global vertex -> local vertex, first-touch order
       int32_t nvl = 0;
-      for (int32_t lc = 0; lc < m->n_loc; ++lc)
+      for (int32_t lc = 0; lc < m->n_loc; ++lc) {
+        const int32_t* gv = cell_verts + int64_t(m->cgid[size_t(lc)]) * nl;
         for (int i = 0; i < nl; ++i) {
-          const int32_t v = cell_verts[int64_t(m->cgid[size_t(lc)]) * nl + i];
-          int32_t id;
-          if (whole) {
-            if (dense[size_t(v)] < 0) dense[size_t(v)] = nvl++;
-            id = dense[size_t(v)];
-          } else {
-            auto it = vmap.find(v);
-            if (it == vmap.end()) it = vmap.emplace(v, nvl++).first;
-            id = it->second;
-          }
+          int32_t& id = dense[size_t(gv[i])];
+          if (id < 0) id = nvl++;
           cvl[size_t(lc) * nl + i] = id;
         }
+      }
       m->n_verts_loc = nvl;
     }
     if (kind == HDD_SIMPLEX2D) {

@@ -103,18 +103,18 @@ void assemble_all(hdd_swipdg* h) {
   hdd_mesh* m = h->mesh;
   const MeshView v = h->view();
   cudaStream_t s = m->stream;
-  for (auto& part : h->lhs_comps) launch_assemble_lhs(v, h->fn(part.factor), part.factor.kind, part.factor.order, h->polorder, part.values.p, s);
+  for (auto& part : h->lhs_comps) launch_assemble_lhs(v, h->fn_h(part.factor), part.factor.kind, part.factor.order, h->polorder, part.values.p, s);
   if (h->lhs_affine)
-    launch_assemble_lhs(v, h->fn(h->lhs_affine->factor), h->lhs_affine->factor.kind, h->lhs_affine->factor.order, h->polorder,
+    launch_assemble_lhs(v, h->fn_h(h->lhs_affine->factor), h->lhs_affine->factor.kind, h->lhs_affine->factor.order, h->polorder,
                         h->lhs_affine->values.p, s);
   auto do_vec = [&](VectorPart& part) {
     part.values.zero(s);
     for (const RhsTerm& t : part.terms) {
       if (t.kind == 0) {
-        if (!t.f.zero) launch_rhs_volume(v, h->fn(t.f), t.f.order, t.f.separable, h->polorder, part.values.p, s);
+        if (!t.f.zero) launch_rhs_volume(v, h->fn_h(t.f), t.f.order, t.f.separable, h->polorder, part.values.p, s);
       } else {
         if (!t.f.zero && !t.g.zero)
-          launch_rhs_dirichlet(v, h->fn(t.f), t.f.order, h->fn(t.g), t.g.order, h->polorder, part.values.p, s);
+          launch_rhs_dirichlet(v, h->fn_h(t.f), t.f.order, h->fn_h(t.g), t.g.order, h->polorder, part.values.p, s);
       }
     }
   };
@@ -187,12 +187,12 @@ DevCombo make_combo(const hdd_swipdg* h, const AffineFn& f, const double* mu, in
   int order = 0;
   for (size_t q = 0; q < f.comps.size(); ++q) {
     c.theta[c.n] = eval_coef(f.coef_prog[q], mu, mu_size);
-    c.fn[c.n++] = h->fn(f.comps[q]);
+    c.idx[c.n++] = f.comps[q].idx;
     order = std::max(order, f.comps[q].order);
   }
   if (f.has_affine()) {
     c.theta[c.n] = 1.0;
-    c.fn[c.n++] = h->fn(f.affine);
+    c.idx[c.n++] = f.affine.idx;
     order = std::max(order, f.affine.order);
   }
   c.order = order;
@@ -251,7 +251,9 @@ void run_indicators(hdd_swipdg* h, const double* u_host, const hdd_parameters* p
   a.a_min = make_combo(h, h->factor, mu_min, ms);
   a.a_max = make_combo(h, h->factor, mu_max, ms);
   if (!h->force.has_affine()) HDD_THROW(HDD_ERR_REQUIREMENTS_NOT_MET, "the force needs an affine part");
-  a.force = h->fn(h->force.affine);
+  a.fn_table = h->fn_dev.p;
+  a.n_fn = int(h->fn_host.size());
+  a.force_idx = h->force.affine.idx;
   a.force_order = h->force.affine.order;
   a.u_local = h->tmp_local.p;
   a.vertex_mean = h->vertex_mean.p;
@@ -977,7 +979,7 @@ int hdd_profile_kernel(hdd_swipdg* h, int which, int reps, double* avg_seconds) 
         case 2: launch_cg_direction(v, c, 0, s); break;
         case 3: {
           MatrixPart& part = h->lhs_affine ? *h->lhs_affine : h->lhs_comps[0];
-          launch_assemble_lhs(v, h->fn(part.factor), part.factor.kind, part.factor.order, h->polorder, part.values.p, s);
+          launch_assemble_lhs(v, h->fn_h(part.factor), part.factor.kind, part.factor.order, h->polorder, part.values.p, s);
           break;
         }
         default: HDD_THROW(HDD_ERR_WRONG_INPUT, "unknown kernel id " << which);
