@@ -207,12 +207,23 @@ def main():
     L = capi.lib()
     roof = {}
     peak, peak_kind = measured_peak_gbs()
+    # DRAM traffic per launch from the committed `ncu --set full` capture of this workload (profiles/), if it matches
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01c_traffic_n4096.json")) as f:
+            tj = json.load(f)
+        if tj.get("cells") == n * n and world == 1:
+            kmap = {"spmv": "k_cg_spmv_tma", "cg_update": "k_cg_update", "cg_direction": "k_cg_direction",
+                    "assembly": "k_assemble_lhs_cube<0>"}
+            traffic = {k: tj["kernels"][v]["dram_bytes"] for k, v in kmap.items() if v in tj["kernels"]}
+    except Exception:
+        pass
     for which, name in ((0, "spmv"), (1, "cg_update"), (2, "cg_direction"), (3, "assembly")):
         sec, byt = C.c_double(), C.c_double()
         capi.check(L.hdd_profile_kernel(d._h, which, 20 if which != 3 else 5, C.byref(sec)))
         capi.check(L.hdd_kernel_bytes(d._h, which, C.byref(byt)))
         roof[name] = {"bound": "hbm", "achieved": byt.value / sec.value / 1e9, "peak": peak, "unit": "GB/s",
-                      "frac": byt.value / sec.value / 1e9 / peak, "traffic": None, "ms": sec.value * 1e3,
+                      "frac": byt.value / sec.value / 1e9 / peak, "traffic": traffic.get(name), "ms": sec.value * 1e3,
                       "algorithmic_bytes": byt.value, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)"}
 
     # end to end through the public API from host buffers (H2D of the grid + problem, D2H of the solution), every step

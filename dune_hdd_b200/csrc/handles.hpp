@@ -21,6 +21,7 @@ struct Nccl {
   void destroy(ncclComm* c);
   void all_reduce_sum(double* buf, size_t count, ncclComm* c, cudaStream_t s);
   void all_reduce_min(double* buf, size_t count, ncclComm* c, cudaStream_t s);
+  void all_gather_bytes(const void* send, void* recv, size_t bytes_per_rank, ncclComm* c, cudaStream_t s);
   void group_start();
   void group_end();
   void send(const double* buf, size_t count, int peer, ncclComm* c, cudaStream_t s);
@@ -80,6 +81,8 @@ struct hdd_mesh {
   std::vector<hdd::HaloPeer> peers;
   hdd::DevBuf<int32_t> send_idx;  // local DoF indices to pack
   hdd::DevBuf<double> send_buf;
+  hdd::DevBuf<int32_t> halo_peer, halo_rcell;  // per halo cell: owner rank, cell offset inside the owner's owned range
+  std::vector<int32_t> rank_own0;              // own0 of every rank
   // host scratch used while the halo plan is built
   std::vector<int32_t> h_cell_verts_loc;  // [n_loc*nl] local vertex ids of all local cells
 
@@ -170,6 +173,11 @@ struct hdd_swipdg {
 
   // solve workspace
   hdd::DevBuf<double> frozen, dinv, dinv_block, z, b, x, r, p, q, partial, tmp_local;
+  // peer-memory SpMV (multi GPU): ping-pong direction, dinv with halo, peers' r / p buffers mapped through CUDA IPC
+  hdd::DevBuf<double> p_alt, dinv_local;
+  bool p2p_ready = false, p2p_failed = false;
+  hdd::PeerView peer_view{};
+  std::vector<void*> ipc_opened;
   int last_precond = 1;  // 0 identity, 1 diagonal, 2 cell-block diagonal
   hdd::DevBuf<hdd::CgScalars> sc;
   hdd::CgScalars* sc_host = nullptr;  // pinned

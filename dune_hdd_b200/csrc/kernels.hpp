@@ -67,19 +67,36 @@ struct CgBuffers {
   const double* b;       // owned rows
   double* x;             // owned rows
   double* r;             // owned rows
-  double* p;             // LOCAL vector (halo | owned | halo)
+  double* p;             // LOCAL vector (halo | owned | halo); parity-0 buffer when p_alt != nullptr
+  double* p_alt;         // parity-1 direction buffer (ping-pong, peer-memory mode) or nullptr
   double* q;             // owned rows
   double* partial;       // >= 3 * max_blocks
   CgScalars* sc;
 };
 
+// Peer-memory view for the fused SpMV + halo read (multi GPU, Q1): the halo part of the CG direction is never
+// exchanged; the kernel reads the owner's r and previous direction through NVLink and forms p = D^-1 r + beta p_old on
+// the fly.  The two all-reduces of the CG iteration are the only synchronisation.
+constexpr int kMaxPeers = 16;
+struct PeerView {
+  int enabled;
+  int own0, n_own;               // of this rank
+  const int32_t* halo_peer;      // [n_halo] owner rank
+  const int32_t* halo_rcell;     // [n_halo] cell offset inside the owner's owned range
+  const double* dinv_local;      // [n_loc * nl] Jacobi diagonal inverse including the halo
+  const double* r[kMaxPeers];    // owners' residuals (owned rows)
+  const double* p[2][kMaxPeers]; // owners' direction buffers (local vectors) by parity
+  int own0_of[kMaxPeers];        // owners' own0
+};
+
 int cg_partial_capacity();
+bool cg_spmv_uses_tma(const MeshView& m);  // the peer-memory halo read lives in the TMA SpMV kernel
 // y = A x over the owned rows; x is a local vector.  If partial != nullptr also writes per-block partial sums of
 // x_owned . y and, through the last-block ticket, their total into sc->pq / sc->red[0].
 void launch_spmv(const MeshView& m, const double* values, const double* x_local, double* y, cudaStream_t s);
 void launch_cg_init(const MeshView& m, const CgBuffers& c, double precision, int max_it, cudaStream_t s);
 void launch_cg_init_finish(const MeshView& m, const CgBuffers& c, cudaStream_t s);
-void launch_cg_spmv(const MeshView& m, const CgBuffers& c, int parity, cudaStream_t s);
+void launch_cg_spmv(const MeshView& m, const CgBuffers& c, int parity, cudaStream_t s, const PeerView* peer = nullptr);
 void launch_cg_update(const MeshView& m, const CgBuffers& c, int parity, cudaStream_t s);
 void launch_cg_direction(const MeshView& m, const CgBuffers& c, int parity, cudaStream_t s);
 

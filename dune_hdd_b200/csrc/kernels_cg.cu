@@ -136,6 +136,11 @@ __device__ __forceinline__ void st256(double* p, double a, double b, double c, d
   asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
 
+__device__ __forceinline__ double* dir_in(const CgBuffers& c, int par) { return (c.p_alt && par) ? c.p_alt : c.p; }
+__device__ __forceinline__ double* dir_out(const CgBuffers& c, int par) {
+  return c.p_alt ? (par ? c.p : c.p_alt) : c.p;  // ping-pong: iteration `par` writes the other buffer
+}
+
 // Row kernel shared by SpMV and the CG step: y_t = sum over the blocks of row t, ascending column order.
 template <int KIND>
 __device__ __forceinline__ double row_times_x(const MeshView& m, const double* __restrict__ vals,
@@ -183,9 +188,10 @@ __global__ void __launch_bounds__(kCgThreads) k_cg_spmv(MeshView m, CgBuffers c,
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
   double v[1] = {0.0};
   for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < rows; t += stride) {
-    const double y = row_times_x<KIND>(m, c.values, c.p, t);
+    const double* pc = dir_in(c, par);
+    const double y = row_times_x<KIND>(m, c.values, pc, t);
     c.q[t] = y;
-    v[0] = fma(c.p[own_off + t], y, v[0]);
+    v[0] = fma(pc[own_off + t], y, v[0]);
   }
   grid_sum<1>(v, c.partial, &sc->ticket_a, [sc](const double(&w)[1]) { sc->red[0] = w[0]; });
 }
@@ -231,7 +237,31 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
-__global__ void __launch_bounds__(kTmaThreads, 1) k_cg_spmv_tma(MeshView m, CgBuffers c, int par, int cells_per_cta) {
+// direction entries of one cell: owned cells come from this rank's buffer; in peer-memory mode halo cells are formed on
+// the fly from the owner's residual and previous direction, read through NVLink (p = D^-1 r + beta p_old)
+__device__ __forceinline__ void load_direction(const double* p_cur, const PeerView& pv, int par, double beta, bool first,
+                                               int cell, double* v) {
+  if (!pv.enabled || (cell >= pv.own0 && cell < pv.own0 + pv.n_own)) {
+    ld256(p_cur + size_t(4) * cell, v[0], v[1], v[2], v[3]);
+    return;
+  }
+  const int h = cell < pv.own0 ? cell : cell - pv.n_own;
+  const int peer = __ldg(pv.halo_peer + h), rc = __ldg(pv.halo_rcell + h);
+  double r[4], d[4];
+  ld256_rw(pv.r[peer] + size_t(4) * rc, r[0], r[1], r[2], r[3]);
+  ld256(pv.dinv_local + size_t(4) * cell, d[0], d[1], d[2], d[3]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] = d[j] * r[j];
+  if (!first) {
+    double po[4];
+    ld256_rw(pv.p[par ^ 1][peer] + size_t(4) * (pv.own0_of[peer] + rc), po[0], po[1], po[2], po[3]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = fma(beta, po[j], v[j]);
+  }
+}
+
+__global__ void __launch_bounds__(kTmaThreads, 1)
+    k_cg_spmv_tma(MeshView m, CgBuffers c, int par, int cells_per_cta, const __grid_constant__ PeerView pv) {
   constexpr int NL = 4, NF = 4;
   extern __shared__ __align__(128) unsigned char smem[];
   CgScalars* sc = c.sc;
@@ -266,6 +296,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_cg_spmv_tma(MeshView m, CgBu
   } else {
     const int64_t own_off = int64_t(m.own0) * NL;
     const int i = lane & 3;
+    const double* p_cur = dir_in(c, par);
+    const bool first = sc->it[par] == 0;
+    const double beta = (pv.enabled && !first) ? sc->rz[par] / sc->rz[par ^ 1] : 0.0;
     for (int t = warp; t < n_tiles; t += kTmaConsumerWarps) {
       const int stage = t % kTmaStages, n = t / kTmaStages;
       const int k0 = c0 + t * kTmaTileCells;
@@ -280,7 +313,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_cg_spmv_tma(MeshView m, CgBu
         off = (__ldg(m.blk_start + k) - __ldg(m.blk_start + k0)) * (NL * NL) + int64_t(i) * nblk * NL;
 #pragma unroll
         for (int s = 0; s < NF + 1; ++s)
-          if (s < nblk) ld256(c.p + size_t(NL) * cells[s], xv[s][0], xv[s][1], xv[s][2], xv[s][3]);
+          if (s < nblk) load_direction(p_cur, pv, par, beta, first, cells[s], xv[s]);
       }
       mbar_wait(full0 + 8 * stage, n & 1);
       double sum = 0.0;
@@ -300,7 +333,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_cg_spmv_tma(MeshView m, CgBu
       if (active) {
         const int64_t r = int64_t(NL) * k + i;
         c.q[r] = sum;
-        v[0] = fma(__ldg(c.p + own_off + r), sum, v[0]);
+        v[0] = fma(__ldg(p_cur + own_off + r), sum, v[0]);
       }
     }
   }
@@ -379,7 +412,7 @@ __global__ void __launch_bounds__(kCgThreads) k_cg_update(int64_t rows, int64_t 
     const int64_t n4 = rows >> 2;
     for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < n4; t += stride) {
       double p[4], q[4], x[4], r[4], d[4];
-      ld256_rw(c.p + own_off + 4 * t, p[0], p[1], p[2], p[3]);
+      ld256_rw(dir_in(c, par) + own_off + 4 * t, p[0], p[1], p[2], p[3]);
       ld256_stream(c.q + 4 * t, q[0], q[1], q[2], q[3]);
       ld256_rw(c.x + 4 * t, x[0], x[1], x[2], x[3]);
       ld256_rw(c.r + 4 * t, r[0], r[1], r[2], r[3]);
@@ -397,7 +430,7 @@ __global__ void __launch_bounds__(kCgThreads) k_cg_update(int64_t rows, int64_t 
     }
   } else {
     for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < rows; t += stride) {
-      c.x[t] = fma(alpha, c.p[own_off + t], c.x[t]);
+      c.x[t] = fma(alpha, dir_in(c, par)[own_off + t], c.x[t]);
       const double r = fma(-alpha, c.q[t], c.r[t]);
       c.r[t] = r;
       const double z = c.dinv[t] * r;
@@ -421,7 +454,7 @@ __global__ void __launch_bounds__(kCgThreads) k_cg_update_block(int64_t cells, i
   for (int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; k < cells; k += stride) {
     double p[NL], q[NL], x[NL], r[NL], z[NL], D[NL * NL];
     if constexpr (NL == 4) {
-      ld256_rw(c.p + own_off + 4 * k, p[0], p[1], p[2], p[3]);
+      ld256_rw(dir_in(c, par) + own_off + 4 * k, p[0], p[1], p[2], p[3]);
       ld256_stream(c.q + 4 * k, q[0], q[1], q[2], q[3]);
       ld256_rw(c.x + 4 * k, x[0], x[1], x[2], x[3]);
       ld256_rw(c.r + 4 * k, r[0], r[1], r[2], r[3]);
@@ -430,7 +463,7 @@ __global__ void __launch_bounds__(kCgThreads) k_cg_update_block(int64_t cells, i
     } else {
 #pragma unroll
       for (int i = 0; i < NL; ++i) {
-        p[i] = c.p[own_off + NL * k + i]; q[i] = c.q[NL * k + i]; x[i] = c.x[NL * k + i]; r[i] = c.r[NL * k + i];
+        p[i] = dir_in(c, par)[own_off + NL * k + i]; q[i] = c.q[NL * k + i]; x[i] = c.x[NL * k + i]; r[i] = c.r[NL * k + i];
       }
 #pragma unroll
       for (int i = 0; i < NL * NL; ++i) D[i] = __ldg(c.dinv_block + (NL * NL) * k + i);
@@ -472,11 +505,13 @@ __global__ void __launch_bounds__(kCgThreads) k_cg_direction(int64_t rows, int64
     const double beta = sc->red[1] / sc->rz[par];
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
     const bool stored_z = c.z != nullptr;
+    const double* pin = dir_in(c, par);
+    double* pout = dir_out(c, par);
     if ((rows & 3) == 0 && (own_off & 3) == 0) {
       const int64_t n4 = rows >> 2;
       for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < n4; t += stride) {
         double p[4], z[4];
-        ld256_rw(c.p + own_off + 4 * t, p[0], p[1], p[2], p[3]);
+        ld256_rw(pin + own_off + 4 * t, p[0], p[1], p[2], p[3]);
         if (stored_z) {
           ld256_rw(c.z + 4 * t, z[0], z[1], z[2], z[3]);
         } else {
@@ -488,12 +523,12 @@ __global__ void __launch_bounds__(kCgThreads) k_cg_direction(int64_t rows, int64
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) p[j] = fma(beta, p[j], z[j]);
-        st256(c.p + own_off + 4 * t, p[0], p[1], p[2], p[3]);
+        st256(pout + own_off + 4 * t, p[0], p[1], p[2], p[3]);
       }
     } else {
       for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < rows; t += stride) {
         const double z = stored_z ? c.z[t] : c.dinv[t] * c.r[t];
-        c.p[own_off + t] = fma(beta, c.p[own_off + t], z);
+        pout[own_off + t] = fma(beta, pin[own_off + t], z);
       }
     }
   }
@@ -562,7 +597,7 @@ inline int cg_grid(int64_t items) {
   return int(std::max<int64_t>(1, std::min<int64_t>(need, kMaxBlocks)));
 }
 
-bool use_tma() {
+bool use_tma_impl() {
   static const bool on = [] {
     const char* e = std::getenv("HDD_SPMV_TMA");
     return !(e && e[0] == '0');
@@ -571,6 +606,8 @@ bool use_tma() {
 }
 
 }  // namespace
+
+bool cg_spmv_uses_tma(const MeshView& m) { return m.kind == HDD_CUBE2D && use_tma_impl() && m.n_own >= 148 * kTmaTileCells; }
 
 int cg_partial_capacity() { return 3 * kMaxBlocks; }
 
@@ -619,11 +656,11 @@ void launch_cg_init_finish(const MeshView&, const CgBuffers& c, cudaStream_t s) 
   HDD_CUDA(cudaGetLastError());
 }
 
-void launch_cg_spmv(const MeshView& m, const CgBuffers& c, int parity, cudaStream_t s) {
+void launch_cg_spmv(const MeshView& m, const CgBuffers& c, int parity, cudaStream_t s, const PeerView* peer) {
   const int64_t rows = int64_t(m.n_own) * m.nl;
   if (m.kind == HDD_SIMPLEX2D) {
     k_cg_spmv<HDD_SIMPLEX2D><<<cg_grid(rows), kCgThreads, 0, s>>>(m, c, parity);
-  } else if (use_tma() && m.n_own >= 148 * kTmaTileCells) {
+  } else if (cg_spmv_uses_tma(m)) {
     static bool configured = false;
     if (!configured) {
       HDD_CUDA(cudaFuncSetAttribute(k_cg_spmv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes));
@@ -635,7 +672,9 @@ void launch_cg_spmv(const MeshView& m, const CgBuffers& c, int parity, cudaStrea
     int cells_per_cta = (m.n_own + sms - 1) / sms;
     cells_per_cta = (cells_per_cta + kTmaTileCells - 1) / kTmaTileCells * kTmaTileCells;
     const int grid = (m.n_own + cells_per_cta - 1) / cells_per_cta;
-    k_cg_spmv_tma<<<grid, kTmaThreads, kTmaSmemBytes, s>>>(m, c, parity, cells_per_cta);
+    PeerView pv{};
+    if (peer) pv = *peer;
+    k_cg_spmv_tma<<<grid, kTmaThreads, kTmaSmemBytes, s>>>(m, c, parity, cells_per_cta, pv);
   } else {
     k_cg_spmv<HDD_CUBE2D><<<cg_grid(rows), kCgThreads, 0, s>>>(m, c, parity);
   }

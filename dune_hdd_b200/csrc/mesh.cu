@@ -17,14 +17,15 @@ static thread_local std::string t_last_error;
 void set_last_error(const std::string& msg) { t_last_error = msg; }
 
 // ---- NCCL, resolved at run time ----------------------------------------------------------------------------
-enum { F_UID, F_INIT, F_DESTROY, F_ALLREDUCE, F_GSTART, F_GEND, F_SEND, F_RECV, F_ERRSTR };
+enum { F_UID, F_INIT, F_DESTROY, F_ALLREDUCE, F_GSTART, F_GEND, F_SEND, F_RECV, F_ERRSTR, F_ALLGATHER };
 
 Nccl::Nccl() {
   handle_ = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
   if (!handle_) return;
   const char* names[] = {"ncclGetUniqueId", "ncclCommInitRank", "ncclCommDestroy", "ncclAllReduce", "ncclGroupStart",
-                         "ncclGroupEnd",    "ncclSend",         "ncclRecv",        "ncclGetErrorString"};
-  for (int k = 0; k < 9; ++k) {
+                         "ncclGroupEnd",    "ncclSend",         "ncclRecv",        "ncclGetErrorString",
+                         "ncclAllGather"};
+  for (int k = 0; k < 10; ++k) {
     fn_[k] = dlsym(handle_, names[k]);
     if (!fn_[k]) { handle_ = nullptr; return; }
   }
@@ -65,6 +66,11 @@ void Nccl::all_reduce_min(double* buf, size_t count, ncclComm* c, cudaStream_t s
   check(reinterpret_cast<ncclResult_t (*)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t)>(
             fn_[F_ALLREDUCE])(buf, buf, count, ncclDouble, ncclMin, c, s),
         "ncclAllReduce");
+}
+void Nccl::all_gather_bytes(const void* send, void* recv, size_t bytes_per_rank, ncclComm* c, cudaStream_t s) {
+  check(reinterpret_cast<ncclResult_t (*)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t)>(fn_[F_ALLGATHER])(
+            send, recv, bytes_per_rank, ncclUint8, c, s),
+        "ncclAllGather");
 }
 void Nccl::group_start() { check(reinterpret_cast<ncclResult_t (*)()>(fn_[F_GSTART])(), "ncclGroupStart"); }
 void Nccl::group_end() { check(reinterpret_cast<ncclResult_t (*)()>(fn_[F_GEND])(), "ncclGroupEnd"); }
@@ -522,6 +528,25 @@ int hdd_mesh_attach_comm(hdd_mesh* m, hdd_comm* c) {
     }
     m->send_idx.upload(idx.data(), idx.size(), m->stream);
     m->send_buf.alloc(idx.size());
+    // tables for the peer-memory SpMV: owner rank and the owner's row offset (in cells) of every halo cell
+    {
+      std::vector<int32_t> hp(halo_cells.size()), hr(halo_cells.size());
+      for (size_t k = 0; k < halo_cells.size(); ++k) {
+        hp[k] = halo_owner[k];
+        hr[k] = int32_t(m->cgid[size_t(halo_cells[k])] - m->rank_cell_offsets[size_t(halo_owner[k])]);
+      }
+      m->halo_peer.upload(hp.data(), hp.size(), m->stream);
+      m->halo_rcell.upload(hr.data(), hr.size(), m->stream);
+      // every rank's own0 (offset of its owned cells inside its local vectors)
+      DevBuf<int32_t> own0_all;
+      own0_all.alloc(size_t(world_size));
+      DevBuf<int32_t> mine;
+      mine.upload(&m->own0, 1, m->stream);
+      nc.all_gather_bytes(mine.p, own0_all.p, sizeof(int32_t), m->comm, m->stream);
+      m->rank_own0.resize(size_t(world_size));
+      HDD_CUDA(cudaMemcpyAsync(m->rank_own0.data(), own0_all.p, size_t(world_size) * sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
+      HDD_CUDA(cudaStreamSynchronize(m->stream));
+    }
     HDD_CUDA(cudaStreamSynchronize(m->stream));
   });
 }

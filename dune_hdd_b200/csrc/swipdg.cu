@@ -5,11 +5,14 @@
 #include <cmath>
 #include <cstring>
 
+#include <dlfcn.h>
+
 #include "handles.hpp"
 
 using namespace hdd;
 
 hdd_swipdg::~hdd_swipdg() {
+  for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
   if (sc_host) cudaFreeHost(sc_host);
 }
 
@@ -171,6 +174,106 @@ void ensure_solve_workspace(hdd_swipdg* h) {
     h->sc.alloc(1);
     HDD_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->sc_host), sizeof(CgScalars)));
   }
+}
+
+// ---- peer-memory SpMV set-up ------------------------------------------------------------------------------------
+// Each rank publishes its residual and its two direction buffers through CUDA IPC; neighbours map them and the SpMV
+// kernel reads halo entries straight from the owner's HBM over NVLink.  Collective: every rank must call it, and the
+// outcome (all ranks succeeded?) is agreed on with an all-reduce so that nobody falls back alone.
+struct IpcRecord {
+  cudaIpcMemHandle_t handle[3];
+  uint64_t offset[3];  // pointer - allocation base (cudaMalloc may sub-allocate)
+};
+
+uint64_t allocation_offset(const void* ptr) {
+  typedef int (*get_range_t)(unsigned long long*, size_t*, unsigned long long);
+  static get_range_t fn = [] {
+    void* lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    return lib ? reinterpret_cast<get_range_t>(dlsym(lib, "cuMemGetAddressRange_v2")) : nullptr;
+  }();
+  if (!fn) HDD_THROW(HDD_ERR_DEVICE, "libcuda.so.1 / cuMemGetAddressRange_v2 not available");
+  unsigned long long base = 0;
+  size_t size = 0;
+  if (fn(&base, &size, reinterpret_cast<unsigned long long>(ptr)) != 0) HDD_THROW(HDD_ERR_DEVICE, "cuMemGetAddressRange failed");
+  return uint64_t(reinterpret_cast<unsigned long long>(ptr) - base);
+}
+
+bool p2p_wanted() {
+  static const bool on = [] { const char* e = std::getenv("HDD_P2P"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+bool setup_p2p(hdd_swipdg* h) {
+  hdd_mesh* m = h->mesh;
+  if (h->p2p_ready) return true;
+  if (h->p2p_failed) return false;
+  cudaStream_t s = m->stream;
+  Nccl& nc = Nccl::get();
+  const size_t loc = size_t(m->n_loc) * m->nl;
+  int ok = 1;
+  std::vector<IpcRecord> all(size_t(m->world));
+  try {
+    if (m->world > kMaxPeers) HDD_THROW(HDD_ERR_NOT_IMPLEMENTED, "peer-memory SpMV supports at most " << kMaxPeers << " ranks");
+    h->p_alt.alloc(loc);
+    h->p_alt.zero(s);
+    h->dinv_local.alloc(loc);
+    h->dinv_local.zero(s);
+    IpcRecord mine{};
+    const void* ptrs[3] = {h->r.p, h->p.p, h->p_alt.p};
+    for (int k = 0; k < 3; ++k) {
+      HDD_CUDA(cudaIpcGetMemHandle(&mine.handle[k], const_cast<void*>(ptrs[k])));
+      mine.offset[k] = allocation_offset(ptrs[k]);
+    }
+    DevBuf<unsigned char> send, recv;
+    send.upload(reinterpret_cast<const unsigned char*>(&mine), sizeof(mine), s);
+    recv.alloc(sizeof(IpcRecord) * size_t(m->world));
+    nc.all_gather_bytes(send.p, recv.p, sizeof(IpcRecord), m->comm, s);
+    HDD_CUDA(cudaMemcpyAsync(all.data(), recv.p, sizeof(IpcRecord) * size_t(m->world), cudaMemcpyDeviceToHost, s));
+    HDD_CUDA(cudaStreamSynchronize(s));
+  } catch (const Error& e) {
+    set_last_error(e.what());
+    ok = 0;
+  }
+  PeerView pv{};
+  if (ok) {
+    pv.own0 = m->own0;
+    pv.n_own = m->n_own;
+    pv.halo_peer = m->halo_peer.p;
+    pv.halo_rcell = m->halo_rcell.p;
+    pv.dinv_local = h->dinv_local.p;
+    for (const HaloPeer& peer : m->peers) {
+      void* opened[3] = {nullptr, nullptr, nullptr};
+      for (int k = 0; k < 3 && ok; ++k) {
+        if (cudaIpcOpenMemHandle(&opened[k], all[size_t(peer.rank)].handle[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          cudaGetLastError();
+          ok = 0;
+          break;
+        }
+        h->ipc_opened.push_back(opened[k]);
+      }
+      if (!ok) break;
+      pv.r[peer.rank] = reinterpret_cast<const double*>(static_cast<char*>(opened[0]) + all[size_t(peer.rank)].offset[0]);
+      pv.p[0][peer.rank] = reinterpret_cast<const double*>(static_cast<char*>(opened[1]) + all[size_t(peer.rank)].offset[1]);
+      pv.p[1][peer.rank] = reinterpret_cast<const double*>(static_cast<char*>(opened[2]) + all[size_t(peer.rank)].offset[2]);
+      pv.own0_of[peer.rank] = m->rank_own0[size_t(peer.rank)];
+    }
+  }
+  // agree on the outcome
+  DevBuf<double> flag;
+  double f = ok ? 0.0 : 1.0;
+  flag.upload(&f, 1, s);
+  nc.all_reduce_sum(flag.p, 1, m->comm, s);
+  HDD_CUDA(cudaMemcpyAsync(&f, flag.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+  HDD_CUDA(cudaStreamSynchronize(s));
+  if (f != 0.0) {
+    h->p2p_failed = true;
+    h->p_alt.release();
+    return false;
+  }
+  pv.enabled = 1;
+  h->peer_view = pv;
+  h->p2p_ready = true;
+  return true;
 }
 
 int parse_solver_type(const char* type) {
@@ -625,14 +728,35 @@ int hdd_solve(hdd_swipdg* h, const char* type, double precision, int max_iter, c
     c.sc = h->sc.p;
     Nccl& nc = Nccl::get();
     const bool multi = m->world > 1;
+    // multi GPU, Q1, Jacobi / identity: fused SpMV + halo read over peer memory instead of pack + send/recv
+    bool p2p = multi && p2p_wanted() && use_diag != 2 && cg_spmv_uses_tma(v);
+    if (multi) {  // the decision must be collective: a rank without owned cells large enough would disagree
+      DevBuf<double> vote;
+      double want = p2p ? 0.0 : 1.0;
+      vote.upload(&want, 1, s);
+      nc.all_reduce_sum(vote.p, 1, m->comm, s);
+      HDD_CUDA(cudaMemcpyAsync(&want, vote.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+      HDD_CUDA(cudaStreamSynchronize(s));
+      p2p = (want == 0.0);
+    }
+    if (p2p) p2p = setup_p2p(h);
+    const PeerView* peer = nullptr;
+    if (p2p) {
+      // Jacobi diagonal including the halo (static during the solve): owned part computed here, halo exchanged once
+      double* dl = h->dinv_local.p;
+      HDD_CUDA(cudaMemcpyAsync(dl + size_t(m->own0) * m->nl, h->dinv.p, size_t(h->n_rows) * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      m->halo_exchange(dl);
+      c.p_alt = h->p_alt.p;
+      peer = &h->peer_view;
+    }
     launch_cg_init(v, c, precision, max_iter, s);
     if (multi) nc.all_reduce_sum(&c.sc->red[1], 2, m->comm, s);
     launch_cg_init_finish(v, c, s);
     int par = 0, launched = 0, batch = 16;
     for (;;) {
       for (int k = 0; k < batch; ++k) {
-        if (multi) m->halo_exchange(c.p);
-        launch_cg_spmv(v, c, par, s);
+        if (multi && !p2p) m->halo_exchange(c.p);
+        launch_cg_spmv(v, c, par, s, peer);
         if (multi) nc.all_reduce_sum(&c.sc->red[0], 1, m->comm, s);
         launch_cg_update(v, c, par, s);
         if (multi) nc.all_reduce_sum(&c.sc->red[1], 2, m->comm, s);

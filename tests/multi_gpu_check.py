@@ -18,8 +18,9 @@ def main():
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     comm = hdd.parallel.init_comm(rank, world, lr)
-    for kind, n in (("alu", 8), ("sgrid", 32)):
-        g = (hdd.grids.simplex if kind == "alu" else hdd.grids.cube)(n, partitions=(4, 4))
+    # the last case is large enough for the TMA SpMV and therefore for the peer-memory (CUDA IPC / NVLink) halo read
+    for kind, n in (("alu", 8), ("sgrid", 32), ("sgrid", 256)):
+        g = (hdd.grids.simplex if kind == "alu" else hdd.grids.cube)(n, partitions=(8, 8) if n == 256 else (4, 4))
         roff = hdd.parallel.rank_cell_offsets(g, world)
         rng = (int(roff[rank]), int(roff[rank + 1]))
         prob = hdd.problems.OS2014ParametricESV2007() if kind == "alu" else hdd.problems.ESV2007()
