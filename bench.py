@@ -265,7 +265,9 @@ def main():
                                        "8x8 BlockSWIPDG partition" % (n, n), "cells": n * n, "dofs": n_dofs,
                            "cg": "%s to ||r||/||b|| <= 1e-10" % args.solver, "l2_flush": "inputs >> L2 (matrix "
                            "%.1f GB per part)" % (8.0 * 16 * (n * n + 2 * 2 * n * (n - 1)) / 1e9),
-                           "parallelism": "subdomain slabs x%d" % world},
+                           "parallelism": "subdomain slabs x%d" % world,
+                           "halo": ("peer-memory SpMV (CUDA IPC over NVLink)" if results[-1][1].get("peer_memory") else
+                                    "NCCL send/recv") if world > 1 else "none"},
                 "assemble_ms": 1e3 * t_asm / args.steps, "cg_solve_s": t_cg / args.steps, "cg_iterations": iters,
                 "cg_s_per_iteration": t_cg / args.steps / max(iters, 1),
                 "roofline": roof["spmv"], "roofline_assembly": roof["assembly"], "roofline_cg_update": roof["cg_update"],

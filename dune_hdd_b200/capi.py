@@ -37,7 +37,7 @@ class hdd_problem(C.Structure):
 
 class hdd_solve_info(C.Structure):
     _fields_ = [("iterations", C.c_int), ("converged", C.c_int), ("relative_residual", C.c_double),
-                ("seconds", C.c_double), ("seconds_per_iteration", C.c_double)]
+                ("seconds", C.c_double), ("seconds_per_iteration", C.c_double), ("peer_memory", C.c_int)]
 
 
 class hdd_csr(C.Structure):

@@ -786,6 +786,7 @@ int hdd_solve(hdd_swipdg* h, const char* type, double precision, int max_iter, c
       info->relative_residual = relres;
       info->seconds = double(ms) * 1e-3;
       info->seconds_per_iteration = sc.it[par] > 0 ? double(ms) * 1e-3 / sc.it[par] : 0.0;
+      info->peer_memory = p2p ? 1 : 0;
     }
     if (x_host) {
       HDD_CUDA(cudaMemcpyAsync(x_host, h->x.p, size_t(h->n_rows) * sizeof(double), cudaMemcpyDeviceToHost, s));

@@ -238,7 +238,7 @@ class SWIPDG:
                                     C.byref(info)))
         d = {"iterations": info.iterations, "converged": bool(info.converged),
              "relative_residual": info.relative_residual, "seconds": info.seconds,
-             "seconds_per_iteration": info.seconds_per_iteration}
+             "seconds_per_iteration": info.seconds_per_iteration, "peer_memory": bool(info.peer_memory)}
         return (x, d) if return_info else x
 
     # ---- estimators ---------------------------------------------------------------------------------------

@@ -167,6 +167,7 @@ typedef struct hdd_solve_info {
   double relative_residual; /* ||r||_2 / ||b||_2 (recursive) */
   double seconds;           /* device time of freeze + CG, CUDA events */
   double seconds_per_iteration;
+  int peer_memory;          /* multi GPU: 1 = fused SpMV + halo read over peer memory (NVLink), 0 = NCCL send/recv */
 } hdd_solve_info;
 
 /* solver_types() / solver_options(type) (discretizations/base.hh:314-322). Types: "cg.diagonal" (default,
