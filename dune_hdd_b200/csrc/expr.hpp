@@ -9,8 +9,10 @@
 
 #ifdef __CUDACC__
 #define HDD_HD __host__ __device__
+#define HDD_FORCEINLINE __forceinline__
 #else
 #define HDD_HD
+#define HDD_FORCEINLINE inline
 #endif
 
 namespace hdd {
@@ -51,7 +53,7 @@ struct Program {
 };
 
 // Evaluates a compiled program.  vars: x[0], x[1] (functions) or mu[0..3] (parameter functionals).
-HDD_HD inline double eval_program(const Program& p, const double* vars) {
+HDD_HD HDD_FORCEINLINE double eval_program(const Program& p, const double* vars) {
   double st[kMaxStack];
   int sp = 0;
   for (int k = 0; k < p.n_ops; ++k) {

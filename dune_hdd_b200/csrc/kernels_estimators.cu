@@ -34,7 +34,8 @@ struct IndicatorRules {
 };
 
 __global__ void __launch_bounds__(128)
-    k_indicators(MeshView m, IndicatorArgs a, const IndicatorRules* __restrict__ rules, double s_in, double s_bnd) {
+    k_indicators(MeshView m, const __grid_constant__ IndicatorArgs a, const IndicatorRules* __restrict__ rules, double s_in,
+                 double s_bnd) {
   using G = Geo<HDD_SIMPLEX2D>;
   constexpr int NL = 3;
   // the data functions (expression programs included) are staged in shared memory once per block
@@ -98,12 +99,14 @@ __global__ void __launch_bounds__(128)
     cT = fmin(cT, combo_eval(a.a_cut, table, c, x, y) * lam_min);
   }
   const double cutoff = hT * hT / (kPi * kPi * cT);
+  double f_res[kMaxElemPts];  // force at the residual rule's points: evaluated once, used for eta_R and eta_R*
   {
     double rs = 0.0;
     for (int q = 0; q < R.res.n; ++q) {
       double x, y;
       g.to_global(R.res.x[q], R.res.y[q], x, y);
-      const double d = fn_eval(force, c, x, y) - f0;
+      f_res[q] = fn_eval(force, c, x, y);
+      const double d = f_res[q] - f0;
       rs += R.res.w[q] * g.detj * d * d;
     }
     a.out[1 * n + k] = rs;
@@ -203,9 +206,7 @@ __global__ void __launch_bounds__(128)
     const double div = (Gf[0] + Gf[1] + Gf[2]) / area;
     double s = 0.0;
     for (int q = 0; q < R.res.n; ++q) {
-      double x, y;
-      g.to_global(R.res.x[q], R.res.y[q], x, y);
-      const double d = fn_eval(force, c, x, y) - div;
+      const double d = f_res[q] - div;
       s += R.res.w[q] * g.detj * d * d;
     }
     a.out[5 * n + k] = cutoff * s;
