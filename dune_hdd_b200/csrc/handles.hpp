@@ -73,6 +73,7 @@ struct hdd_mesh {
   hdd::DevBuf<int32_t> vdof;
   int64_t n_blocks = 0;  // blk_start[n_own]
   bool has_btype = false;
+  bool purely_neumann = false;  // no Dirichlet face anywhere (DirichletDetector, discretizations/swipdg.hh:219-220,488-489)
 
   // multi GPU
   int rank = 0, world = 1;

@@ -100,6 +100,10 @@ void launch_cg_spmv(const MeshView& m, const CgBuffers& c, int parity, cudaStrea
 void launch_cg_update(const MeshView& m, const CgBuffers& c, int parity, cudaStream_t s);
 void launch_cg_direction(const MeshView& m, const CgBuffers& c, int parity, cudaStream_t s);
 
+// a15 (pure Neumann): symmetric unit row/column 0 + rhs[0] = 0, and x -= mean(x) after the solve
+void launch_unit_row_col0(const MeshView& m, double* values, double* b, cudaStream_t s);
+void launch_subtract_mean(double* x, int64_t n, double* partial, CgScalars* sc, cudaStream_t s);
+
 // ---- K7-K10: estimators ---------------------------------------------------------------------------------------
 struct IndicatorArgs {
   DevCombo a_mu, a_hat, a_bar, a_cut, a_min, a_max;

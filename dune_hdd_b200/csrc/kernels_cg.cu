@@ -586,6 +586,48 @@ __global__ void k_invert_diag_blocks(MeshView m, const double* __restrict__ valu
     for (int j = 0; j < NL; ++j) dinv_block[size_t(NL * NL) * k + i * NL + j] = 0.5 * (I[i][j] + I[j][i]);
 }
 
+// a15: pure-Neumann fix of ContainerBasedDefault::uncached_solve (discretizations/base.hh:337-345): unit_row(0) and
+// rhs[0] = 0.  Done symmetrically (row and column 0) so that CG stays applicable; with rhs[0] = 0 both give x_0 = 0
+// and the same remaining system.  One warp, cell 0 and its neighbours only.
+template <int KIND>
+__global__ void k_unit_row_col0(MeshView m, double* __restrict__ vals, double* __restrict__ b) {
+  constexpr int NL = Geo<KIND>::NL, NF = Geo<KIND>::NF;
+  if (threadIdx.x != 0 || blockIdx.x != 0 || m.n_own == 0 || m.own0 != 0) return;
+  int nb[NF];
+  load_neigh<NF>(m.neigh, 0, nb);
+  const int nblk = block_count<NF>(nb);
+  double* row0 = vals + m.blk_start[0] * (NL * NL);
+  const int self_slot = block_slot<NF>(0, nb, 0);
+  for (int t = 0; t < nblk * NL; ++t) row0[t] = 0.0;                                  // row 0
+  for (int i = 0; i < NL; ++i) row0[size_t(i) * nblk * NL + self_slot * NL + 0] = 0.0;  // column 0 inside cell 0
+  row0[self_slot * NL] = 1.0;
+  for (int f = 0; f < NF; ++f) {
+    const int n = nb[f];
+    if (n < 0 || n >= m.n_own) continue;
+    int nn[NF];
+    load_neigh<NF>(m.neigh, n, nn);
+    const int cnt = block_count<NF>(nn);
+    const int slot = block_slot<NF>(n, nn, 0);
+    double* r = vals + m.blk_start[n] * (NL * NL);
+    for (int i = 0; i < NL; ++i) r[size_t(i) * cnt * NL + slot * NL + 0] = 0.0;        // column 0 in the neighbour's rows
+  }
+  b[0] = 0.0;
+}
+
+__global__ void __launch_bounds__(kCgThreads) k_sum(const double* __restrict__ x, int64_t n, double* partial,
+                                                    unsigned int* ticket, double* out) {
+  double v[1] = {0.0};
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += stride) v[0] += x[t];
+  grid_sum<1>(v, partial, ticket, [out](const double(&w)[1]) { *out = w[0]; });
+}
+
+__global__ void k_shift(double* __restrict__ x, int64_t n, const double* __restrict__ sum, double inv_count) {
+  const double mean = *sum * inv_count;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += stride) x[t] -= mean;
+}
+
 __global__ void k_pack(const double* __restrict__ v, const int32_t* __restrict__ idx, int64_t n,
                        double* __restrict__ out) {
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
@@ -700,6 +742,23 @@ void launch_cg_direction(const MeshView& m, const CgBuffers& c, int parity, cuda
   const int64_t rows = int64_t(m.n_own) * m.nl;
   k_cg_direction<<<cg_grid((rows + 3) / 4), kCgThreads, 0, s>>>(rows, int64_t(m.own0) * m.nl, c, parity);
   count_launch();
+  HDD_CUDA(cudaGetLastError());
+}
+
+void launch_unit_row_col0(const MeshView& m, double* values, double* b, cudaStream_t s) {
+  if (m.kind == HDD_SIMPLEX2D)
+    k_unit_row_col0<HDD_SIMPLEX2D><<<1, 32, 0, s>>>(m, values, b);
+  else
+    k_unit_row_col0<HDD_CUBE2D><<<1, 32, 0, s>>>(m, values, b);
+  count_launch();
+  HDD_CUDA(cudaGetLastError());
+}
+
+void launch_subtract_mean(double* x, int64_t n, double* partial, CgScalars* sc, cudaStream_t s) {
+  if (n == 0) return;
+  k_sum<<<cg_grid(n), kCgThreads, 0, s>>>(x, n, partial, &sc->ticket_a, &sc->red[3]);
+  k_shift<<<cg_grid(n), kCgThreads, 0, s>>>(x, n, &sc->red[3], 1.0 / double(n));
+  count_launch(2);
   HDD_CUDA(cudaGetLastError());
 }
 

@@ -253,6 +253,13 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
       if (boundary_type) {
         m->has_btype = true;
         m->btype.upload(boundary_type + cell_begin * nf, size_t(n_own) * nf, s);
+        std::atomic<int> dirichlet_found{0};
+        parallel_for(n_cells, [&](int64_t a, int64_t b) {
+          for (int64_t c = a; c < b; ++c)
+            for (int f = 0; f < nf; ++f)
+              if (cell_neigh[c * nf + f] < 0 && boundary_type[c * nf + f] == 1) dirichlet_found = 1;
+        });
+        m->purely_neumann = dirichlet_found == 0;
       }
       int32_t flag = 0;
       HDD_CUDA(cudaMemcpyAsync(&flag, d_flag.p, sizeof(flag), cudaMemcpyDeviceToHost, s));

@@ -704,6 +704,15 @@ int hdd_solve(hdd_swipdg* h, const char* type, double precision, int max_iter, c
     const double* vals = freeze_lhs(h, mu, mu_size);
     freeze_rhs(h, mu, mu_size);
     const MeshView v = h->view();
+    if (m->purely_neumann) {
+      // discretizations/base.hh:337-345: unit_row(0), rhs[0] = 0, solve, subtract the mean
+      if (m->world > 1) HDD_THROW(HDD_ERR_NOT_IMPLEMENTED, "pure Neumann problems on more than one GPU");
+      if (!h->frozen.p) h->frozen.alloc(size_t(h->nnz));
+      if (vals != h->frozen.p)
+        HDD_CUDA(cudaMemcpyAsync(h->frozen.p, vals, size_t(h->nnz) * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      launch_unit_row_col0(v, h->frozen.p, h->b.p, s);
+      vals = h->frozen.p;
+    }
     CgBuffers c{};
     c.values = vals;
     c.dinv = h->dinv.p;
@@ -770,6 +779,7 @@ int hdd_solve(hdd_swipdg* h, const char* type, double precision, int max_iter, c
       if (launched > max_iter + batch) break;  // cannot happen: done latches at max_it
       if (batch < 256) batch *= 2;
     }
+    if (m->purely_neumann) launch_subtract_mean(h->x.p, h->n_rows, h->partial.p, h->sc.p, s);
     HDD_CUDA(cudaEventRecord(e1, s));
     HDD_CUDA(cudaEventSynchronize(e1));
     float ms = 0.f;

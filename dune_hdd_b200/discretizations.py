@@ -338,6 +338,16 @@ class BlockSWIPDG(SWIPDG):
         """off-diagonal coupling block (ss, nn) (discretizations/block-swipdg.hh:634-660)"""
         return self._block(ss, nn, q)
 
+    def get_local_functional(self, ss, q=-1):
+        """rhs part q restricted to subdomain ss (discretizations/block-swipdg.hh:662-669)"""
+        off = self.subdomain_offsets()
+        if ss < 0 or ss >= len(off) - 1:
+            raise index_out_of_range(capi.HDD_ERR_INDEX_OUT_OF_RANGE,
+                                     "0 <= ss < num_subdomains() = %d is not true for ss = %d!" % (len(off) - 1, ss))
+        part = self.rhs().affine_part() if q == -1 else self.rhs().component(q)
+        r0 = self.cell_range[0] * self.grid.n_loc
+        return np.array(part[off[ss] - r0:off[ss + 1] - r0])
+
     def localize_vector(self, global_vector, ss):
         """discretizations/block-swipdg.hh:567-583"""
         off = self.subdomain_offsets()
