@@ -6,7 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libhdd_b200.so")
-SOURCES = ["mesh.cu", "swipdg.cu", "kernels_assembly.cu", "kernels_cg.cu", "kernels_estimators.cu", "expr.cpp",
+SOURCES = ["mesh.cu", "swipdg.cu", "products.cu", "kernels_assembly.cu", "kernels_cg.cu", "kernels_estimators.cu",
+           "kernels_products.cu", "expr.cpp",
            "grids.cpp", "partition.cpp"]
 HEADERS = ["common.hpp", "expr.hpp", "quadrature.hpp", "device.cuh", "kernels.hpp", "handles.hpp", "partition.hpp",
            os.path.join("..", "..", "include", "hdd_b200.h")]

@@ -60,7 +60,10 @@ SYMBOLS = [
     "hdd_copy_to_host", "hdd_sync", "hdd_apply", "hdd_solver_types", "hdd_solve", "hdd_solution_dev",
     "hdd_num_subdomains", "hdd_subdomain_offsets", "hdd_neighbouring_subdomains", "hdd_block_extract",
     "hdd_csr_free", "hdd_estimators_available", "hdd_estimate", "hdd_indicators", "hdd_comm_unique_id",
-    "hdd_comm_create", "hdd_comm_destroy", "hdd_mesh_attach_comm", "hdd_kernel_launches", "hdd_profile_kernel", "hdd_kernel_bytes", "hdd_expression_evaluate", "hdd_partition_plan", "hdd_free",
+    "hdd_comm_create", "hdd_comm_destroy", "hdd_mesh_attach_comm", "hdd_kernel_launches", "hdd_profile_kernel",
+    "hdd_kernel_bytes", "hdd_expression_evaluate", "hdd_partition_plan", "hdd_free",
+    "hdd_swipdg_only_these_products", "hdd_products_available", "hdd_product_num_components", "hdd_product_values",
+    "hdd_product_coefficient", "hdd_pattern_volume", "hdd_product_apply2", "hdd_error_norms",
 ]
 
 _lib = None

@@ -31,7 +31,8 @@ struct DevCombo {
 // Local mesh of one rank: cells [0, n_loc) sorted by global id = [lower halo | owned | upper halo].
 struct MeshView {
   int kind;
-  int nl;
+  int nl;                   // local DoFs per cell: P1 3, Q1 4, P2 6, Q2 9
+  int nf;                   // faces per cell
   int32_t n_loc;
   int32_t own0;
   int32_t n_own;
@@ -165,6 +166,59 @@ struct Geo<HDD_CUBE2D> {
   }
   __device__ __forceinline__ double diameter() const { return hypot(hx, hy); }
 };
+
+// Geometry + nodal Lagrange basis of order P.  P = 1 is Geo<KIND> itself (nodes = vertices in Dune order).  P = 2: P2 / Q2
+// with the nodes in lexicographic order - (0,0),(1/2,0),(1,0),(0,1/2),(1/2,1/2),(0,1) on the triangle, i + 3 j on the
+// square - which is what the generic Lagrange point sets of the reference's space backend produce (dune-fem,
+// discretizations/swipdg.hh:67-71); no reference test instantiates polOrder = 2, so this numbering is unpinned.
+template <int KIND, int P>
+struct Elem : Geo<KIND> {};
+
+template <>
+struct Elem<HDD_SIMPLEX2D, 2> : Geo<HDD_SIMPLEX2D> {
+  static constexpr int NL = 6;
+  __device__ __forceinline__ void basis(double xi, double eta, double* phi, double* gx, double* gy) const {
+    const double l0 = 1.0 - xi - eta, l1 = xi, l2 = eta;
+    // physical gradients of the barycentric coordinates
+    const double g1x = i00, g1y = i01, g2x = i10, g2y = i11, g0x = -i00 - i10, g0y = -i01 - i11;
+    phi[0] = l0 * (2.0 * l0 - 1.0); phi[1] = 4.0 * l0 * l1; phi[2] = l1 * (2.0 * l1 - 1.0);
+    phi[3] = 4.0 * l0 * l2;         phi[4] = 4.0 * l1 * l2; phi[5] = l2 * (2.0 * l2 - 1.0);
+    const double d0 = 4.0 * l0 - 1.0, d1 = 4.0 * l1 - 1.0, d2 = 4.0 * l2 - 1.0;
+    gx[0] = d0 * g0x;                     gy[0] = d0 * g0y;
+    gx[1] = 4.0 * (l1 * g0x + l0 * g1x);  gy[1] = 4.0 * (l1 * g0y + l0 * g1y);
+    gx[2] = d1 * g1x;                     gy[2] = d1 * g1y;
+    gx[3] = 4.0 * (l2 * g0x + l0 * g2x);  gy[3] = 4.0 * (l2 * g0y + l0 * g2y);
+    gx[4] = 4.0 * (l2 * g1x + l1 * g2x);  gy[4] = 4.0 * (l2 * g1y + l1 * g2y);
+    gx[5] = d2 * g2x;                     gy[5] = d2 * g2y;
+  }
+};
+
+template <>
+struct Elem<HDD_CUBE2D, 2> : Geo<HDD_CUBE2D> {
+  static constexpr int NL = 9;
+  __device__ __forceinline__ static void lagrange3(double t, double* l, double* d) {
+    l[0] = (1.0 - t) * (1.0 - 2.0 * t); l[1] = 4.0 * t * (1.0 - t); l[2] = t * (2.0 * t - 1.0);
+    d[0] = 4.0 * t - 3.0;               d[1] = 4.0 - 8.0 * t;       d[2] = 4.0 * t - 1.0;
+  }
+  __device__ __forceinline__ void basis(double xi, double eta, double* phi, double* gx, double* gy) const {
+    double lx[3], dx[3], ly[3], dy[3];
+    lagrange3(xi, lx, dx);
+    lagrange3(eta, ly, dy);
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        phi[i + 3 * j] = lx[i] * ly[j];
+        gx[i + 3 * j] = dx[i] * ly[j] * ihx;
+        gy[i + 3 * j] = lx[i] * dy[j] * ihy;
+      }
+  }
+};
+
+// local DoFs of the nodal Lagrange space of order p
+__host__ __device__ inline int n_local_dofs(int kind, int p) {
+  return kind == HDD_SIMPLEX2D ? (p + 1) * (p + 2) / 2 : (p + 1) * (p + 1);
+}
 
 struct FaceGeo {
   double ax, ay, bx, by, nx, ny, h, ih;

@@ -36,8 +36,8 @@ struct Nccl {
 
 struct HaloPeer {
   int rank;
-  int64_t send_offset, send_count;  // in DoFs, into the packed send buffer
-  int64_t recv_offset, recv_count;  // in DoFs, into the local vector (contiguous: halo sorted by global id)
+  int64_t send_offset, send_count;  // in cells, into the list of cells to pack
+  int64_t recv_offset, recv_count;  // in cells: a contiguous range of local cells (halo sorted by global id)
 };
 
 }  // namespace hdd
@@ -80,8 +80,9 @@ struct hdd_mesh {
   ncclComm* comm = nullptr;
   std::vector<int64_t> rank_cell_offsets;  // [world+1]
   std::vector<hdd::HaloPeer> peers;
-  hdd::DevBuf<int32_t> send_idx;  // local DoF indices to pack
+  hdd::DevBuf<int32_t> send_idx;  // local cells whose DoFs are packed, grouped by peer
   hdd::DevBuf<double> send_buf;
+  int64_t n_send_cells = 0, send_buf_capacity = 0;
   hdd::DevBuf<int32_t> halo_peer, halo_rcell;  // per halo cell: owner rank, cell offset inside the owner's owned range
   std::vector<int32_t> rank_own0;              // own0 of every rank
   // host scratch used while the halo plan is built
@@ -91,6 +92,7 @@ struct hdd_mesh {
     hdd::MeshView v{};
     v.kind = kind;
     v.nl = nl;
+    v.nf = nf;
     v.n_loc = n_loc;
     v.own0 = own0;
     v.n_own = n_own;
@@ -103,8 +105,8 @@ struct hdd_mesh {
     return v;
   }
   void set_device() const { HDD_CUDA(cudaSetDevice(device)); }
-  // fills the halo part of a local vector from the owning ranks (no-op for world == 1)
-  void halo_exchange(double* v_local);
+  // fills the halo part of a local vector (nd DoFs per cell) from the owning ranks (no-op for world == 1)
+  void halo_exchange(double* v_local, int nd);
   ~hdd_mesh();
 };
 
@@ -128,7 +130,7 @@ struct AffineFn {
 };
 
 struct RhsTerm {  // one local functional added into a rhs vector
-  int kind;       // 0 L2Volume(f), 1 DirichletBoundarySWIPDG(factor, g)
+  int kind;       // 0 L2Volume(f), 1 DirichletBoundarySWIPDG(factor f, g), 2 L2Face(f) on the Neumann faces
   FnRef f, g;
 };
 
@@ -146,11 +148,24 @@ struct MatrixPart {
   DevBuf<double> values;
 };
 
+// One entry of products_ (discretizations/base.hh:272-291): an affinely decomposed matrix over the system pattern
+// ("penalty", "energy") or over the volume pattern ("l2", "h1_semi", "elliptic", "boundary_l2").
+struct Product {
+  std::string id;
+  int which = 0;           // 0 l2, 1 h1_semi, 2 elliptic, 3 boundary_l2, 4 penalty, 5 energy
+  bool volume_pattern = true;
+  bool assembled = false;
+  std::vector<MatrixPart> comps;
+  std::unique_ptr<MatrixPart> affine;
+};
+
 }  // namespace hdd
 
 struct hdd_swipdg {
   hdd_mesh* mesh = nullptr;
   int polorder = 1;
+  int nl = 0;  // local DoFs per cell of the DG space: P1 3, Q1 4, P2 6, Q2 9
+  std::vector<int64_t> sub_dof_offsets;  // [n_subdomains+1], mapToGlobal(ss, 0)
   std::string parameter_name;
   int parameter_size = 0;
 
@@ -171,6 +186,12 @@ struct hdd_swipdg {
   int64_t nnz = 0, n_rows = 0;
   hdd::DevBuf<int64_t> rowptr;
   hdd::DevBuf<int32_t> col;
+  // products (only_these_products, discretizations/swipdg.hh:159-163)
+  std::vector<std::unique_ptr<hdd::Product>> products;
+  std::vector<const char*> product_ids;
+  hdd::DevBuf<int64_t> vol_rowptr;
+  hdd::DevBuf<int32_t> vol_col;
+  hdd::DevBuf<double> prod_frozen, prod_tmp;
 
   // solve workspace
   hdd::DevBuf<double> frozen, dinv, dinv_block, z, b, x, r, p, q, partial, tmp_local;
@@ -187,8 +208,21 @@ struct hdd_swipdg {
   // estimator workspace
   hdd::DevBuf<double> vertex_mean, ind_out, seg_out;
 
-  hdd::MeshView view() const { return mesh->view(has_tensor ? tensor.p : nullptr); }
+  hdd::MeshView view() const {
+    hdd::MeshView v = mesh->view(has_tensor ? tensor.p : nullptr);
+    v.nl = nl;
+    return v;
+  }
   const hdd::DevFn* fn(const hdd::FnRef& r) const { return fn_dev.p + r.idx; }
   const hdd::DevFn& fn_h(const hdd::FnRef& r) const { return fn_host[size_t(r.idx)]; }
   ~hdd_swipdg();
 };
+
+namespace hdd {
+// shared by swipdg.cu and products.cu
+void require_init(const hdd_swipdg* h);                                          // assert_everything_is_ready (base.hh:370-377)
+void check_mu(const hdd_swipdg* h, const double* mu, int mu_size, const char* name);  // base.hh:333-334
+double eval_coef(const Program& p, const double* mu, int mu_size);
+void assemble_products(hdd_swipdg* h);  // the product assemblers added to system_assembler (discretizations/swipdg.hh:359-479)
+DevCombo make_combo(const hdd_swipdg* h, const AffineFn& f, const double* mu, int mu_size);  // f frozen at mu
+}  // namespace hdd

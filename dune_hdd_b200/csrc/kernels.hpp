@@ -25,12 +25,23 @@ void launch_fill_csr(const MeshView& m, int64_t* rowptr, int32_t* col, cudaStrea
 // (kernel parameter space = constant bank), so the expression programs are never fetched from global memory.
 void launch_assemble_lhs(const MeshView& m, const DevFn& factor_dev, int factor_kind, int factor_order, int polorder,
                          double* values, cudaStream_t s);
+// the penalty terms only (Products::SwipdgPenaltyAssemblable, over_integrate = 2), same pattern as the system matrix
+void launch_assemble_penalty(const MeshView& m, const DevFn& factor_dev, int factor_kind, int factor_order, int polorder,
+                             double* values, cudaStream_t s);
+// volume-pattern products, values [n_own * nl * nl] (one dense block per cell): which = 0 l2, 1 h1_semi, 2 elliptic,
+// 3 boundary_l2 (discretizations/swipdg.hh:359-443)
+void launch_assemble_block_product(const MeshView& m, int which, const DevFn& factor_dev, int factor_order, int polorder,
+                                   double* values, cudaStream_t s);
 // b += L2Volume(force)
 void launch_rhs_volume(const MeshView& m, const DevFn& force_dev, int force_order, bool separable, int polorder,
                        double* b, cudaStream_t s);
 // b += DirichletBoundarySWIPDG(factor, tensor, dirichlet)
 void launch_rhs_dirichlet(const MeshView& m, const DevFn& factor_dev, int factor_order, const DevFn& dirichlet_dev,
                           int dirichlet_order, int polorder, double* b, cudaStream_t s);
+
+// b += L2Face(neumann) on the Neumann faces
+void launch_rhs_neumann(const MeshView& m, const DevFn& neumann_dev, int neumann_order, int polorder, double* b,
+                        cudaStream_t s);
 
 // ---- K4: freeze -----------------------------------------------------------------------------------------------
 // out = sum_k theta[k] * parts[k]   (values-only AXPY over a shared pattern, discretizations/base.hh:349-361)
@@ -123,7 +134,20 @@ void launch_indicators(const MeshView& m, const IndicatorArgs& a, int polorder, 
 void launch_segment_sums(const double* in, const int64_t* seg_ptr_dev, int n_seg, double* out, cudaStream_t s);
 void launch_segment_min(const double* in, const int64_t* seg_ptr_dev, int n_seg, double* out, cudaStream_t s);
 
+// ---- K12/K13: products in use, error norms ---------------------------------------------------------------------
+void launch_fill_volume_csr(const MeshView& m, int64_t* rowptr, int32_t* col, cudaStream_t s);
+// y = P x for a volume-pattern (block diagonal) product; x and y over the owned rows
+void launch_block_spmv(const MeshView& m, const double* values, const double* x_own, double* y, cudaStream_t s);
+// out[3][n_own]: per cell int (u_h-u)^2, int |grad(u_h-u)|^2, int a K grad(u_h-u).grad(u_h-u) with a rule of `order`
+void launch_error_norms(const MeshView& m, int polorder, const DevFn& exact, const DevFn& exact_dx, const DevFn& exact_dy,
+                        const DevCombo& factor, const DevFn* fn_table, int order, const double* u_own, double* out,
+                        cudaStream_t s);
+// out[seg] = sum over the DoFs of the cells [seg_ptr[seg], seg_ptr[seg+1]) of x * y
+void launch_segment_dot(const double* x, const double* y, const int64_t* seg_ptr_dev, int n_seg, int nd, double* out,
+                        cudaStream_t s);
+
 // ---- K11: halo pack --------------------------------------------------------------------------------------------
-void launch_pack(const double* v_local, const int32_t* dof_idx, int64_t n, double* out, cudaStream_t s);
+// out[k * nd + i] = v_local[cells[k] * nd + i]: the DoFs of the listed local cells, nd DoFs per cell
+void launch_pack(const double* v_local, const int32_t* cells, int64_t n_cells, int nd, double* out, cudaStream_t s);
 
 }  // namespace hdd

@@ -10,6 +10,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "kernels.hpp"
 
@@ -73,15 +74,14 @@ __global__ void k_localize_neighbours(int32_t* __restrict__ neigh, int64_t count
 __global__ void k_count_blocks(MeshView m, int64_t* __restrict__ nblk) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= m.n_own) return;
-  const int nf = m.nl;
+  const int nf = m.nf;
   int s = 1;
   for (int f = 0; f < nf; ++f) s += __ldg(m.neigh + size_t(nf) * k + f) >= 0 ? 1 : 0;
   nblk[k] = s;
 }
 
-template <int KIND>
+template <int NF, int NL>
 __global__ void k_fill_csr(MeshView m, int64_t* __restrict__ rowptr, int32_t* __restrict__ col) {
-  constexpr int NL = Geo<KIND>::NL, NF = Geo<KIND>::NF;
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= int64_t(m.n_own) * NL) return;
   const int k = int(t / NL), i = int(t % NL);
@@ -432,11 +432,218 @@ __global__ void __launch_bounds__(kThreads, 3)
   store_block<NL>(row0, rs, block_slot<NF>(c, nb, c), D);
 }
 
+// select v[i] for a run-time i without dynamic register indexing
+template <int N>
+__device__ __forceinline__ double pick(const double* v, int i) {
+  double r = v[0];
+#pragma unroll
+  for (int k = 1; k < N; ++k) r = (k == i) ? v[k] : r;
+  return r;
+}
+
+// K2, generic in the polynomial order: one thread per matrix ROW (cell k, test function i).  Used for p = 2, where a
+// whole n_loc x n_loc block pair per thread (162 doubles for Q2) would not fit the register file, and for the penalty
+// product.  Same integrals and the same owner-computes argument as k_assemble_lhs; the n_loc threads of a cell repeat
+// the basis evaluation (cheap next to the 8 B/nnz they have to write).
+//   MODE 0: the SWIPDG bilinear form (volume + inner + Dirichlet faces)
+//   MODE 1: only its penalty terms - Products::SwipdgPenaltyAssemblable (discretizations/swipdg.hh:444-479)
+template <int KIND, int P, int FK, int MODE>
+__global__ void __launch_bounds__(kThreads)
+    k_assemble_rows(MeshView m, const __grid_constant__ DevFn fn, ElemRule vol, LineRule fr, double s_in, double s_bnd,
+                    double* __restrict__ vals) {
+  using G = Elem<KIND, P>;
+  constexpr int NL = G::NL, NF = G::NF;
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= int64_t(m.n_own) * NL) return;
+  const int k = int(t / NL), i = int(t % NL);
+  const int c = m.own0 + k;
+  G g;
+  g.load(m.cgeo, c);
+  double K[4];
+  load_tensor(m.tensor, c, K);
+  int nb[NF];
+  load_neigh<NF>(m.neigh, k, nb);
+  const int nblk = block_count<NF>(nb);
+  double* row = vals + m.blk_start[k] * (NL * NL) + int64_t(i) * nblk * NL;
+  double a_self = 0.0;
+  if constexpr (FK == HDD_FN_CONSTANT) a_self = fn.value;
+  if constexpr (FK == HDD_FN_CELLWISE) a_self = __ldg(fn.cell + c);
+
+  double D[NL];
+#pragma unroll
+  for (int j = 0; j < NL; ++j) D[j] = 0.0;
+
+  if constexpr (MODE == 0) {
+    for (int q = 0; q < vol.n; ++q) {
+      double phi[NL], gx[NL], gy[NL], x, y;
+      g.basis(vol.x[q], vol.y[q], phi, gx, gy);
+      g.to_global(vol.x[q], vol.y[q], x, y);
+      const double wa = vol.w[q] * g.detj * factor_at<FK>(fn, a_self, x, y);
+      const double gxi = wa * pick<NL>(gx, i), gyi = wa * pick<NL>(gy, i);
+#pragma unroll
+      for (int j = 0; j < NL; ++j)
+        D[j] = fma(K[0] * gx[j] + K[1] * gy[j], gxi, fma(K[2] * gx[j] + K[3] * gy[j], gyi, D[j]));
+    }
+  }
+
+#pragma unroll 1
+  for (int f = 0; f < NF; ++f) {
+    const FaceGeo e = make_face(g, f);
+    const int n = nb[f];
+    const double knx = K[0] * e.nx + K[2] * e.ny, kny = K[1] * e.nx + K[3] * e.ny;
+    const double dm = e.nx * (K[0] * e.nx + K[1] * e.ny) + e.ny * (K[2] * e.nx + K[3] * e.ny);
+    if (n < 0) {
+      if (m.btype && __ldg(m.btype + size_t(NF) * k + f) != 1) continue;
+      const double pen0 = s_bnd * dm * e.ih;
+      for (int q = 0; q < fr.n; ++q) {
+        const double x = e.ax + fr.x[q] * (e.bx - e.ax), y = e.ay + fr.x[q] * (e.by - e.ay);
+        double xi, eta, phi[NL], gx[NL], gy[NL];
+        g.to_local(x, y, xi, eta);
+        g.basis(xi, eta, phi, gx, gy);
+        const double a = factor_at<FK>(fn, a_self, x, y);
+        const double w = fr.w[q] * e.h;
+        const double wpen = w * pen0 * a, wa = w * a;
+        const double phii = pick<NL>(phi, i);
+        if constexpr (MODE == 0) {
+          const double Bi = wa * (pick<NL>(gx, i) * knx + pick<NL>(gy, i) * kny);
+#pragma unroll
+          for (int j = 0; j < NL; ++j) {
+            const double Aj = wpen * phi[j] - wa * (gx[j] * knx + gy[j] * kny);
+            D[j] = fma(phii, Aj, fma(-Bi, phi[j], D[j]));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < NL; ++j) D[j] = fma(phii * wpen, phi[j], D[j]);
+        }
+      }
+    } else {
+      G gn;
+      gn.load(m.cgeo, n);
+      double Kn[4];
+      load_tensor(m.tensor, n, Kn);
+      const double knxp = Kn[0] * e.nx + Kn[2] * e.ny, knyp = Kn[1] * e.nx + Kn[3] * e.ny;
+      const double dp = e.nx * (Kn[0] * e.nx + Kn[1] * e.ny) + e.ny * (Kn[2] * e.nx + Kn[3] * e.ny);
+      const double isum = 1.0 / (dp + dm);
+      const double gamma = dp * dm * isum;
+      const double wm = dp * isum, wp = dm * isum;
+      const double pen0 = s_in * gamma * 0.5 * e.ih;
+      double a_nb = a_self;
+      if constexpr (FK == HDD_FN_CELLWISE) a_nb = __ldg(fn.cell + n);
+      double E[NL];
+#pragma unroll
+      for (int j = 0; j < NL; ++j) E[j] = 0.0;
+      for (int q = 0; q < fr.n; ++q) {
+        const double x = e.ax + fr.x[q] * (e.bx - e.ax), y = e.ay + fr.x[q] * (e.by - e.ay);
+        double xi, eta, ph[NL], gx[NL], gy[NL];
+        const double am = factor_at<FK>(fn, a_self, x, y);
+        const double ap = (FK == HDD_FN_EXPRESSION) ? am : a_nb;
+        const double w = fr.w[q] * e.h;
+        const double wpen = w * pen0 * (am + ap);
+        const double wwm = w * wm * am, wwp = w * wp * ap;
+        g.to_local(x, y, xi, eta);
+        g.basis(xi, eta, ph, gx, gy);
+        const double phii = pick<NL>(ph, i);
+        double Bi = 0.0;
+        if constexpr (MODE == 0) {
+          Bi = wwm * (pick<NL>(gx, i) * knx + pick<NL>(gy, i) * kny);
+#pragma unroll
+          for (int j = 0; j < NL; ++j) {
+            const double Aj = wpen * ph[j] - wwm * (gx[j] * knx + gy[j] * kny);
+            D[j] = fma(phii, Aj, fma(-Bi, ph[j], D[j]));                       // en/en
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < NL; ++j) D[j] = fma(phii * wpen, ph[j], D[j]);
+        }
+        gn.to_local(x, y, xi, eta);
+        gn.basis(xi, eta, ph, gx, gy);
+        if constexpr (MODE == 0) {
+#pragma unroll
+          for (int j = 0; j < NL; ++j) {
+            const double Cj = -wwp * (gx[j] * knxp + gy[j] * knyp) - wpen * ph[j];
+            E[j] = fma(phii, Cj, fma(Bi, ph[j], E[j]));                         // en/ne
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < NL; ++j) E[j] = fma(-phii * wpen, ph[j], E[j]);
+        }
+      }
+      double* dst = row + block_slot<NF>(c, nb, n) * NL;
+#pragma unroll
+      for (int j = 0; j < NL; ++j) dst[j] = E[j];
+    }
+  }
+  double* dst = row + block_slot<NF>(c, nb, c) * NL;
+#pragma unroll
+  for (int j = 0; j < NL; ++j) dst[j] = D[j];
+}
+
+// Volume-pattern products (discretizations/swipdg.hh:359-443): one dense n_loc x n_loc block per cell, one thread per
+// row.  WHICH 0 "l2" int phi_i phi_j, 1 "h1_semi" int grad phi_j . grad phi_i, 2 "elliptic" int a K grad phi_j . grad
+// phi_i, 3 "boundary_l2" int_{dT on dOmega} phi_i phi_j.  over_integrate = 2 is folded into the rules by the launcher.
+template <int KIND, int P, int WHICH>
+__global__ void __launch_bounds__(kThreads)
+    k_assemble_block_product(MeshView m, const __grid_constant__ DevFn fn, ElemRule vol, LineRule fr,
+                             double* __restrict__ vals) {
+  using G = Elem<KIND, P>;
+  constexpr int NL = G::NL, NF = G::NF;
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= int64_t(m.n_own) * NL) return;
+  const int k = int(t / NL), i = int(t % NL);
+  const int c = m.own0 + k;
+  G g;
+  g.load(m.cgeo, c);
+  double D[NL];
+#pragma unroll
+  for (int j = 0; j < NL; ++j) D[j] = 0.0;
+  if constexpr (WHICH <= 2) {
+    double K[4] = {1.0, 0.0, 0.0, 1.0};
+    if constexpr (WHICH == 2) load_tensor(m.tensor, c, K);
+    for (int q = 0; q < vol.n; ++q) {
+      double phi[NL], gx[NL], gy[NL], x, y;
+      g.basis(vol.x[q], vol.y[q], phi, gx, gy);
+      g.to_global(vol.x[q], vol.y[q], x, y);
+      double w = vol.w[q] * g.detj;
+      if constexpr (WHICH == 2) w *= fn_eval(fn, c, x, y);
+      if constexpr (WHICH == 0) {
+        const double pi = w * pick<NL>(phi, i);
+#pragma unroll
+        for (int j = 0; j < NL; ++j) D[j] = fma(pi, phi[j], D[j]);
+      } else {
+        const double gxi = w * pick<NL>(gx, i), gyi = w * pick<NL>(gy, i);
+#pragma unroll
+        for (int j = 0; j < NL; ++j)
+          D[j] = fma(K[0] * gx[j] + K[1] * gy[j], gxi, fma(K[2] * gx[j] + K[3] * gy[j], gyi, D[j]));
+      }
+    }
+  } else {
+    int nb[NF];
+    load_neigh<NF>(m.neigh, k, nb);
+#pragma unroll 1
+    for (int f = 0; f < NF; ++f) {
+      if (nb[f] >= 0) continue;
+      const FaceGeo e = make_face(g, f);
+      for (int q = 0; q < fr.n; ++q) {
+        const double x = e.ax + fr.x[q] * (e.bx - e.ax), y = e.ay + fr.x[q] * (e.by - e.ay);
+        double xi, eta, phi[NL], gx[NL], gy[NL];
+        g.to_local(x, y, xi, eta);
+        g.basis(xi, eta, phi, gx, gy);
+        const double pi = fr.w[q] * e.h * pick<NL>(phi, i);
+#pragma unroll
+        for (int j = 0; j < NL; ++j) D[j] = fma(pi, phi[j], D[j]);
+      }
+    }
+  }
+  double* dst = vals + size_t(t) * NL;
+#pragma unroll
+  for (int j = 0; j < NL; ++j) dst[j] = D[j];
+}
+
 // K3a.  Functionals::L2Volume(force) (discretizations/swipdg.hh:253-271): rule of order(f) + p.
-template <int KIND>
+template <int KIND, int P>
 __global__ void __launch_bounds__(kThreads)
     k_rhs_volume(MeshView m, const __grid_constant__ DevFn fn, ElemRule vol, double* __restrict__ b) {
-  using G = Geo<KIND>;
+  using G = Elem<KIND, P>;
   constexpr int NL = G::NL;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= m.n_own) return;
@@ -489,11 +696,11 @@ __global__ void __launch_bounds__(kThreads)
 
 // K3b.  Functionals::DirichletBoundarySWIPDG (discretizations/swipdg.hh:273-332; SWIPDG::BoundaryRHS):
 // b_i += int_e -g (A grad phi_i . n) + pen g phi_i
-template <int KIND>
+template <int KIND, int P>
 __global__ void __launch_bounds__(kThreads)
     k_rhs_dirichlet(MeshView m, const __grid_constant__ DevFn fac, const __grid_constant__ DevFn dir, LineRule fr,
                     double s_bnd, double* __restrict__ b) {
-  using G = Geo<KIND>;
+  using G = Elem<KIND, P>;
   constexpr int NL = G::NL, NF = G::NF;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= m.n_own) return;
@@ -535,6 +742,43 @@ __global__ void __launch_bounds__(kThreads)
   for (int i = 0; i < NL; ++i) b[size_t(NL) * k + i] += acc[i];
 }
 
+// K3c.  Functionals::L2Face(neumann) on the Neumann faces (discretizations/swipdg.hh:335-356): b_i += int_e g_N phi_i
+template <int KIND, int P>
+__global__ void __launch_bounds__(kThreads)
+    k_rhs_neumann(MeshView m, const __grid_constant__ DevFn neu, LineRule fr, double* __restrict__ b) {
+  using G = Elem<KIND, P>;
+  constexpr int NL = G::NL, NF = G::NF;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m.n_own || !m.btype) return;
+  const int c = m.own0 + k;
+  int nb[NF];
+  load_neigh<NF>(m.neigh, k, nb);
+  bool any = false;
+#pragma unroll
+  for (int f = 0; f < NF; ++f) any |= nb[f] < 0 && __ldg(m.btype + size_t(NF) * k + f) == 2;
+  if (!any) return;
+  G g;
+  g.load(m.cgeo, c);
+  double acc[NL];
+#pragma unroll
+  for (int i = 0; i < NL; ++i) acc[i] = 0.0;
+  for (int f = 0; f < NF; ++f) {
+    if (nb[f] >= 0 || __ldg(m.btype + size_t(NF) * k + f) != 2) continue;
+    const FaceGeo e = make_face(g, f);
+    for (int q = 0; q < fr.n; ++q) {
+      const double x = e.ax + fr.x[q] * (e.bx - e.ax), y = e.ay + fr.x[q] * (e.by - e.ay);
+      double xi, eta, phi[NL], gx[NL], gy[NL];
+      g.to_local(x, y, xi, eta);
+      g.basis(xi, eta, phi, gx, gy);
+      const double gn = fn_eval(neu, c, x, y) * fr.w[q] * e.h;
+#pragma unroll
+      for (int i = 0; i < NL; ++i) acc[i] = fma(gn, phi[i], acc[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NL; ++i) b[size_t(NL) * k + i] += acc[i];
+}
+
 // K4.  out = sum_k theta_k part_k, 256-bit streaming loads/stores.
 __global__ void __launch_bounds__(256) k_freeze(FreezeArgs a, double* __restrict__ out, int64_t count) {
   const int64_t n4 = count / 4;
@@ -557,10 +801,9 @@ __global__ void __launch_bounds__(256) k_freeze(FreezeArgs a, double* __restrict
   }
 }
 
-template <int KIND>
+template <int NF, int NL>
 __global__ void k_extract_dinv(MeshView m, const double* __restrict__ values, int use_diagonal,
                                double* __restrict__ dinv) {
-  constexpr int NL = Geo<KIND>::NL, NF = Geo<KIND>::NF;
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= int64_t(m.n_own) * NL) return;
   if (!use_diagonal) { dinv[t] = 1.0; return; }
@@ -609,13 +852,42 @@ void exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, cudaStream_t
   count_launch(2);
 }
 
+// compile-time dispatch helpers: (element kind, polynomial order) and (faces, local DoFs)
+template <int V>
+using ic = std::integral_constant<int, V>;
+
+template <class F>
+static void dispatch_elem(int kind, int polorder, F&& f) {
+  if (polorder != 1 && polorder != 2) HDD_THROW(HDD_ERR_NOT_IMPLEMENTED, "polorder " << polorder);
+  if (kind == HDD_SIMPLEX2D) {
+    if (polorder == 1) f(ic<HDD_SIMPLEX2D>{}, ic<1>{}); else f(ic<HDD_SIMPLEX2D>{}, ic<2>{});
+  } else {
+    if (polorder == 1) f(ic<HDD_CUBE2D>{}, ic<1>{}); else f(ic<HDD_CUBE2D>{}, ic<2>{});
+  }
+}
+
+template <class F>
+static void dispatch_block(const MeshView& m, F&& f) {
+  if (m.nf == 3 && m.nl == 3) f(ic<3>{}, ic<3>{});
+  else if (m.nf == 3 && m.nl == 6) f(ic<3>{}, ic<6>{});
+  else if (m.nf == 4 && m.nl == 4) f(ic<4>{}, ic<4>{});
+  else if (m.nf == 4 && m.nl == 9) f(ic<4>{}, ic<9>{});
+  else HDD_THROW(HDD_ERR_INTERNAL, "unsupported block shape nf = " << m.nf << ", nl = " << m.nl);
+}
+
+template <class F>
+static void dispatch_fk(int fk, F&& f) {
+  if (fk == HDD_FN_CONSTANT) f(ic<HDD_FN_CONSTANT>{});
+  else if (fk == HDD_FN_CELLWISE) f(ic<HDD_FN_CELLWISE>{});
+  else f(ic<HDD_FN_EXPRESSION>{});
+}
+
 void launch_fill_csr(const MeshView& m, int64_t* rowptr, int32_t* col, cudaStream_t s) {
   if (m.n_own == 0) return;
   const int64_t rows = int64_t(m.n_own) * m.nl;
-  if (m.kind == HDD_SIMPLEX2D)
-    k_fill_csr<HDD_SIMPLEX2D><<<grid_for(rows, 256), 256, 0, s>>>(m, rowptr, col);
-  else
-    k_fill_csr<HDD_CUBE2D><<<grid_for(rows, 256), 256, 0, s>>>(m, rowptr, col);
+  dispatch_block(m, [&](auto nf, auto nl) {
+    k_fill_csr<decltype(nf)::value, decltype(nl)::value><<<grid_for(rows, 256), 256, 0, s>>>(m, rowptr, col);
+  });
   count_launch();
   HDD_CUDA(cudaGetLastError());
 }
@@ -623,16 +895,9 @@ void launch_fill_csr(const MeshView& m, int64_t* rowptr, int32_t* col, cudaStrea
 template <int KIND>
 static void assemble_dispatch(int fk, int blocks, cudaStream_t s, const MeshView& m, const DevFn& fn, const ElemRule& vol,
                               const LineRule& fr, double si, double sb, double* values) {
-  switch (fk) {
-    case HDD_FN_CONSTANT:
-      k_assemble_lhs<KIND, HDD_FN_CONSTANT><<<blocks, kThreads, 0, s>>>(m, fn, vol, fr, si, sb, values);
-      break;
-    case HDD_FN_CELLWISE:
-      k_assemble_lhs<KIND, HDD_FN_CELLWISE><<<blocks, kThreads, 0, s>>>(m, fn, vol, fr, si, sb, values);
-      break;
-    default:
-      k_assemble_lhs<KIND, HDD_FN_EXPRESSION><<<blocks, kThreads, 0, s>>>(m, fn, vol, fr, si, sb, values);
-  }
+  dispatch_fk(fk, [&](auto k) {
+    k_assemble_lhs<KIND, decltype(k)::value><<<blocks, kThreads, 0, s>>>(m, fn, vol, fr, si, sb, values);
+  });
 }
 
 void launch_assemble_lhs(const MeshView& m, const DevFn& factor_dev, int factor_kind, int factor_order, int polorder,
@@ -643,22 +908,69 @@ void launch_assemble_lhs(const MeshView& m, const DevFn& factor_dev, int factor_
   const double si = sigma_inner(polorder), sb = sigma_boundary(polorder);
   const int blocks = grid_for(m.n_own, kThreads);
   static const bool generic_cube = [] { const char* e = std::getenv("HDD_ASSEMBLY_GENERIC"); return e && e[0] == '1'; }();
-  if (m.kind == HDD_SIMPLEX2D) {
+  if (polorder != 1) {
+    // p = 2: one thread per row
+    const int64_t rows = int64_t(m.n_own) * m.nl;
+    dispatch_elem(m.kind, polorder, [&](auto kind, auto p) {
+      if constexpr (decltype(p)::value == 2)
+        dispatch_fk(factor_kind, [&](auto k) {
+          k_assemble_rows<decltype(kind)::value, 2, decltype(k)::value, 0>
+              <<<grid_for(rows, kThreads), kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+        });
+    });
+  } else if (m.kind == HDD_SIMPLEX2D) {
     assemble_dispatch<HDD_SIMPLEX2D>(factor_kind, blocks, s, m, factor_dev, vol, fr, si, sb, values);
   } else if (generic_cube) {
     assemble_dispatch<HDD_CUBE2D>(factor_kind, blocks, s, m, factor_dev, vol, fr, si, sb, values);
   } else {
-    switch (factor_kind) {
-      case HDD_FN_CONSTANT:
-        k_assemble_lhs_cube<HDD_FN_CONSTANT><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
-        break;
-      case HDD_FN_CELLWISE:
-        k_assemble_lhs_cube<HDD_FN_CELLWISE><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
-        break;
-      default:
-        k_assemble_lhs_cube<HDD_FN_EXPRESSION><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
-    }
+    dispatch_fk(factor_kind, [&](auto k) {
+      k_assemble_lhs_cube<decltype(k)::value><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+    });
   }
+  count_launch();
+  HDD_CUDA(cudaGetLastError());
+}
+
+// over_integrate of the product assemblers (discretizations/swipdg.hh:359, block-swipdg.hh:399)
+constexpr int kOverIntegrate = 2;
+
+void launch_assemble_penalty(const MeshView& m, const DevFn& factor_dev, int factor_kind, int factor_order, int polorder,
+                             double* values, cudaStream_t s) {
+  if (m.n_own == 0) return;
+  const ElemRule vol = element_rule(m.kind, 0);  // unused
+  const LineRule fr = line_rule(factor_order + 2 * polorder + kOverIntegrate);
+  const double si = sigma_inner(polorder), sb = sigma_boundary(polorder);
+  const int64_t rows = int64_t(m.n_own) * m.nl;
+  dispatch_elem(m.kind, polorder, [&](auto kind, auto p) {
+    dispatch_fk(factor_kind, [&](auto k) {
+      k_assemble_rows<decltype(kind)::value, decltype(p)::value, decltype(k)::value, 1>
+          <<<grid_for(rows, kThreads), kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+    });
+  });
+  count_launch();
+  HDD_CUDA(cudaGetLastError());
+}
+
+void launch_assemble_block_product(const MeshView& m, int which, const DevFn& factor_dev, int factor_order, int polorder,
+                                   double* values, cudaStream_t s) {
+  if (m.n_own == 0) return;
+  const int p = polorder;
+  const int vorder = which == 0 ? 2 * p + kOverIntegrate
+                                : which == 1 ? 2 * (p - 1) + kOverIntegrate : factor_order + 2 * (p - 1) + kOverIntegrate;
+  const ElemRule vol = element_rule(m.kind, vorder);
+  const LineRule fr = line_rule(2 * p + kOverIntegrate);
+  const int64_t rows = int64_t(m.n_own) * m.nl;
+  const int blocks = grid_for(rows, kThreads);
+  dispatch_elem(m.kind, polorder, [&](auto kind, auto pp) {
+    constexpr int KD = decltype(kind)::value, PP = decltype(pp)::value;
+    switch (which) {
+      case 0: k_assemble_block_product<KD, PP, 0><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, values); break;
+      case 1: k_assemble_block_product<KD, PP, 1><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, values); break;
+      case 2: k_assemble_block_product<KD, PP, 2><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, values); break;
+      case 3: k_assemble_block_product<KD, PP, 3><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, values); break;
+      default: HDD_THROW(HDD_ERR_INTERNAL, "unknown block product " << which);
+    }
+  });
   count_launch();
   HDD_CUDA(cudaGetLastError());
 }
@@ -666,17 +978,16 @@ void launch_assemble_lhs(const MeshView& m, const DevFn& factor_dev, int factor_
 void launch_rhs_volume(const MeshView& m, const DevFn& force_dev, int force_order, bool separable, int polorder,
                        double* b, cudaStream_t s) {
   if (m.n_own == 0) return;
-  if (m.kind == HDD_CUBE2D && separable) {
+  if (m.kind == HDD_CUBE2D && separable && polorder == 1) {
     k_rhs_volume_cube_separable<<<grid_for(m.n_own, kThreads), kThreads, 0, s>>>(m, force_dev, line_rule(force_order + polorder), b);
     count_launch();
     HDD_CUDA(cudaGetLastError());
     return;
   }
   const ElemRule vol = element_rule(m.kind, force_order + polorder);
-  if (m.kind == HDD_SIMPLEX2D)
-    k_rhs_volume<HDD_SIMPLEX2D><<<grid_for(m.n_own, kThreads), kThreads, 0, s>>>(m, force_dev, vol, b);
-  else
-    k_rhs_volume<HDD_CUBE2D><<<grid_for(m.n_own, kThreads), kThreads, 0, s>>>(m, force_dev, vol, b);
+  dispatch_elem(m.kind, polorder, [&](auto kind, auto p) {
+    k_rhs_volume<decltype(kind)::value, decltype(p)::value><<<grid_for(m.n_own, kThreads), kThreads, 0, s>>>(m, force_dev, vol, b);
+  });
   count_launch();
   HDD_CUDA(cudaGetLastError());
 }
@@ -686,10 +997,21 @@ void launch_rhs_dirichlet(const MeshView& m, const DevFn& factor_dev, int factor
   if (m.n_own == 0) return;
   const LineRule fr = line_rule(factor_order + dirichlet_order + 2 * polorder);
   const double sb = sigma_boundary(polorder);
-  if (m.kind == HDD_SIMPLEX2D)
-    k_rhs_dirichlet<HDD_SIMPLEX2D><<<grid_for(m.n_own, kThreads), kThreads, 0, s>>>(m, factor_dev, dirichlet_dev, fr, sb, b);
-  else
-    k_rhs_dirichlet<HDD_CUBE2D><<<grid_for(m.n_own, kThreads), kThreads, 0, s>>>(m, factor_dev, dirichlet_dev, fr, sb, b);
+  dispatch_elem(m.kind, polorder, [&](auto kind, auto p) {
+    k_rhs_dirichlet<decltype(kind)::value, decltype(p)::value>
+        <<<grid_for(m.n_own, kThreads), kThreads, 0, s>>>(m, factor_dev, dirichlet_dev, fr, sb, b);
+  });
+  count_launch();
+  HDD_CUDA(cudaGetLastError());
+}
+
+void launch_rhs_neumann(const MeshView& m, const DevFn& neumann_dev, int neumann_order, int polorder, double* b,
+                        cudaStream_t s) {
+  if (m.n_own == 0 || !m.btype) return;
+  const LineRule fr = line_rule(neumann_order + polorder);
+  dispatch_elem(m.kind, polorder, [&](auto kind, auto p) {
+    k_rhs_neumann<decltype(kind)::value, decltype(p)::value><<<grid_for(m.n_own, kThreads), kThreads, 0, s>>>(m, neumann_dev, fr, b);
+  });
   count_launch();
   HDD_CUDA(cudaGetLastError());
 }
@@ -705,10 +1027,9 @@ void launch_freeze(const FreezeArgs& a, double* out, int64_t count, cudaStream_t
 void launch_extract_dinv(const MeshView& m, const double* values, int use_diagonal, double* dinv, cudaStream_t s) {
   if (m.n_own == 0) return;
   const int64_t rows = int64_t(m.n_own) * m.nl;
-  if (m.kind == HDD_SIMPLEX2D)
-    k_extract_dinv<HDD_SIMPLEX2D><<<grid_for(rows, 256), 256, 0, s>>>(m, values, use_diagonal, dinv);
-  else
-    k_extract_dinv<HDD_CUBE2D><<<grid_for(rows, 256), 256, 0, s>>>(m, values, use_diagonal, dinv);
+  dispatch_block(m, [&](auto nf, auto nl) {
+    k_extract_dinv<decltype(nf)::value, decltype(nl)::value><<<grid_for(rows, 256), 256, 0, s>>>(m, values, use_diagonal, dinv);
+  });
   count_launch();
   HDD_CUDA(cudaGetLastError());
 }

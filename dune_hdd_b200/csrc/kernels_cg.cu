@@ -20,6 +20,7 @@
 // launched after convergence are no-ops.  Preconditioners: identity, diagonal (Jacobi), and the cell-block diagonal
 // (block Jacobi with the n_loc x n_loc diagonal blocks, the natural choice for DG).
 #include <cstdlib>
+#include <type_traits>
 
 #include "kernels.hpp"
 
@@ -142,10 +143,9 @@ __device__ __forceinline__ double* dir_out(const CgBuffers& c, int par) {
 }
 
 // Row kernel shared by SpMV and the CG step: y_t = sum over the blocks of row t, ascending column order.
-template <int KIND>
+template <int NF, int NL>
 __device__ __forceinline__ double row_times_x(const MeshView& m, const double* __restrict__ vals,
                                               const double* __restrict__ x, int64_t t) {
-  constexpr int NL = Geo<KIND>::NL, NF = Geo<KIND>::NF;
   const int k = int(t / NL), i = int(t % NL);
   int cells[NF + 1];
   const int nblk = sorted_blocks<NF>(m, k, cells);
@@ -169,19 +169,17 @@ __device__ __forceinline__ double row_times_x(const MeshView& m, const double* _
   return sum;
 }
 
-template <int KIND>
+template <int NF, int NL>
 __global__ void __launch_bounds__(kCgThreads)
     k_spmv(MeshView m, const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y) {
-  constexpr int NL = Geo<KIND>::NL;
   const int64_t rows = int64_t(m.n_own) * NL;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
   for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < rows; t += stride)
-    y[t] = row_times_x<KIND>(m, vals, x, t);
+    y[t] = row_times_x<NF, NL>(m, vals, x, t);
 }
 
-template <int KIND>
+template <int NF, int NL>
 __global__ void __launch_bounds__(kCgThreads) k_cg_spmv(MeshView m, CgBuffers c, int par) {
-  constexpr int NL = Geo<KIND>::NL;
   CgScalars* sc = c.sc;
   if (sc->done[par]) return;
   const int64_t rows = int64_t(m.n_own) * NL, own_off = int64_t(m.own0) * NL;
@@ -189,7 +187,7 @@ __global__ void __launch_bounds__(kCgThreads) k_cg_spmv(MeshView m, CgBuffers c,
   double v[1] = {0.0};
   for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < rows; t += stride) {
     const double* pc = dir_in(c, par);
-    const double y = row_times_x<KIND>(m, c.values, pc, t);
+    const double y = row_times_x<NF, NL>(m, c.values, pc, t);
     c.q[t] = y;
     v[0] = fma(pc[own_off + t], y, v[0]);
   }
@@ -548,9 +546,8 @@ __global__ void __launch_bounds__(kCgThreads) k_cg_direction(int64_t rows, int64
 }
 
 // inverse of the n_loc x n_loc diagonal block of every owned cell (Gauss-Jordan, the blocks are s.p.d.)
-template <int KIND>
+template <int NF, int NL>
 __global__ void k_invert_diag_blocks(MeshView m, const double* __restrict__ values, double* __restrict__ dinv_block) {
-  constexpr int NL = Geo<KIND>::NL, NF = Geo<KIND>::NF;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= m.n_own) return;
   int nb[NF];
@@ -589,9 +586,8 @@ __global__ void k_invert_diag_blocks(MeshView m, const double* __restrict__ valu
 // a15: pure-Neumann fix of ContainerBasedDefault::uncached_solve (discretizations/base.hh:337-345): unit_row(0) and
 // rhs[0] = 0.  Done symmetrically (row and column 0) so that CG stays applicable; with rhs[0] = 0 both give x_0 = 0
 // and the same remaining system.  One warp, cell 0 and its neighbours only.
-template <int KIND>
+template <int NF, int NL>
 __global__ void k_unit_row_col0(MeshView m, double* __restrict__ vals, double* __restrict__ b) {
-  constexpr int NL = Geo<KIND>::NL, NF = Geo<KIND>::NF;
   if (threadIdx.x != 0 || blockIdx.x != 0 || m.n_own == 0 || m.own0 != 0) return;
   int nb[NF];
   load_neigh<NF>(m.neigh, 0, nb);
@@ -628,10 +624,36 @@ __global__ void k_shift(double* __restrict__ x, int64_t n, const double* __restr
   for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += stride) x[t] -= mean;
 }
 
-__global__ void k_pack(const double* __restrict__ v, const int32_t* __restrict__ idx, int64_t n,
+__global__ void k_pack(const double* __restrict__ v, const int32_t* __restrict__ cells, int64_t n, int nd,
                        double* __restrict__ out) {
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
-  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += stride) out[t] = v[idx[t]];
+  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += stride) {
+    const int64_t k = t / nd;
+    out[t] = v[int64_t(cells[k]) * nd + (t - k * nd)];
+  }
+}
+
+template <int V>
+using ic = std::integral_constant<int, V>;
+
+template <class F>
+void dispatch_block(const MeshView& m, F&& f) {
+  if (m.nf == 3 && m.nl == 3) f(ic<3>{}, ic<3>{});
+  else if (m.nf == 3 && m.nl == 6) f(ic<3>{}, ic<6>{});
+  else if (m.nf == 4 && m.nl == 4) f(ic<4>{}, ic<4>{});
+  else if (m.nf == 4 && m.nl == 9) f(ic<4>{}, ic<9>{});
+  else HDD_THROW(HDD_ERR_INTERNAL, "unsupported block shape nf = " << m.nf << ", nl = " << m.nl);
+}
+
+template <class F>
+void dispatch_nl(int nl, F&& f) {
+  switch (nl) {
+    case 3: f(ic<3>{}); break;
+    case 4: f(ic<4>{}); break;
+    case 6: f(ic<6>{}); break;
+    case 9: f(ic<9>{}); break;
+    default: HDD_THROW(HDD_ERR_INTERNAL, "unsupported n_loc " << nl);
+  }
 }
 
 inline int cg_grid(int64_t items) {
@@ -649,27 +671,27 @@ bool use_tma_impl() {
 
 }  // namespace
 
-bool cg_spmv_uses_tma(const MeshView& m) { return m.kind == HDD_CUBE2D && use_tma_impl() && m.n_own >= 148 * kTmaTileCells; }
+bool cg_spmv_uses_tma(const MeshView& m) {
+  return m.kind == HDD_CUBE2D && m.nl == 4 && use_tma_impl() && m.n_own >= 148 * kTmaTileCells;
+}
 
 int cg_partial_capacity() { return 3 * kMaxBlocks; }
 
 void launch_spmv(const MeshView& m, const double* values, const double* x_local, double* y, cudaStream_t s) {
   const int64_t rows = int64_t(m.n_own) * m.nl;
   if (rows == 0) return;
-  if (m.kind == HDD_SIMPLEX2D)
-    k_spmv<HDD_SIMPLEX2D><<<cg_grid(rows), kCgThreads, 0, s>>>(m, values, x_local, y);
-  else
-    k_spmv<HDD_CUBE2D><<<cg_grid(rows), kCgThreads, 0, s>>>(m, values, x_local, y);
+  dispatch_block(m, [&](auto nf, auto nl) {
+    k_spmv<decltype(nf)::value, decltype(nl)::value><<<cg_grid(rows), kCgThreads, 0, s>>>(m, values, x_local, y);
+  });
   count_launch();
   HDD_CUDA(cudaGetLastError());
 }
 
 void launch_invert_diag_blocks(const MeshView& m, const double* values, double* dinv_block, cudaStream_t s) {
   if (m.n_own == 0) return;
-  if (m.kind == HDD_SIMPLEX2D)
-    k_invert_diag_blocks<HDD_SIMPLEX2D><<<(m.n_own + 127) / 128, 128, 0, s>>>(m, values, dinv_block);
-  else
-    k_invert_diag_blocks<HDD_CUBE2D><<<(m.n_own + 127) / 128, 128, 0, s>>>(m, values, dinv_block);
+  dispatch_block(m, [&](auto nf, auto nl) {
+    k_invert_diag_blocks<decltype(nf)::value, decltype(nl)::value><<<(m.n_own + 127) / 128, 128, 0, s>>>(m, values, dinv_block);
+  });
   count_launch();
   HDD_CUDA(cudaGetLastError());
 }
@@ -681,10 +703,9 @@ void launch_cg_init(const MeshView& m, const CgBuffers& c, double precision, int
   h.max_it = max_it;
   HDD_CUDA(cudaMemcpyAsync(c.sc, &h, sizeof(h), cudaMemcpyHostToDevice, s));
   if (c.dinv_block) {
-    if (m.nl == 3)
-      k_cg_init_block<3><<<cg_grid(m.n_own), kCgThreads, 0, s>>>(m.n_own, int64_t(m.own0) * m.nl, c);
-    else
-      k_cg_init_block<4><<<cg_grid(m.n_own), kCgThreads, 0, s>>>(m.n_own, int64_t(m.own0) * m.nl, c);
+    dispatch_nl(m.nl, [&](auto nl) {
+      k_cg_init_block<decltype(nl)::value><<<cg_grid(m.n_own), kCgThreads, 0, s>>>(m.n_own, int64_t(m.own0) * m.nl, c);
+    });
   } else {
     k_cg_init<<<cg_grid(rows), kCgThreads, 0, s>>>(rows, int64_t(m.own0) * m.nl, c);
   }
@@ -700,9 +721,7 @@ void launch_cg_init_finish(const MeshView&, const CgBuffers& c, cudaStream_t s) 
 
 void launch_cg_spmv(const MeshView& m, const CgBuffers& c, int parity, cudaStream_t s, const PeerView* peer) {
   const int64_t rows = int64_t(m.n_own) * m.nl;
-  if (m.kind == HDD_SIMPLEX2D) {
-    k_cg_spmv<HDD_SIMPLEX2D><<<cg_grid(rows), kCgThreads, 0, s>>>(m, c, parity);
-  } else if (cg_spmv_uses_tma(m)) {
+  if (cg_spmv_uses_tma(m)) {
     static bool configured = false;
     if (!configured) {
       HDD_CUDA(cudaFuncSetAttribute(k_cg_spmv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes));
@@ -718,7 +737,9 @@ void launch_cg_spmv(const MeshView& m, const CgBuffers& c, int parity, cudaStrea
     if (peer) pv = *peer;
     k_cg_spmv_tma<<<grid, kTmaThreads, kTmaSmemBytes, s>>>(m, c, parity, cells_per_cta, pv);
   } else {
-    k_cg_spmv<HDD_CUBE2D><<<cg_grid(rows), kCgThreads, 0, s>>>(m, c, parity);
+    dispatch_block(m, [&](auto nf, auto nl) {
+      k_cg_spmv<decltype(nf)::value, decltype(nl)::value><<<cg_grid(rows), kCgThreads, 0, s>>>(m, c, parity);
+    });
   }
   count_launch();
   HDD_CUDA(cudaGetLastError());
@@ -727,10 +748,9 @@ void launch_cg_spmv(const MeshView& m, const CgBuffers& c, int parity, cudaStrea
 void launch_cg_update(const MeshView& m, const CgBuffers& c, int parity, cudaStream_t s) {
   const int64_t rows = int64_t(m.n_own) * m.nl;
   if (c.dinv_block) {
-    if (m.nl == 3)
-      k_cg_update_block<3><<<cg_grid(m.n_own), kCgThreads, 0, s>>>(m.n_own, int64_t(m.own0) * m.nl, c, parity);
-    else
-      k_cg_update_block<4><<<cg_grid(m.n_own), kCgThreads, 0, s>>>(m.n_own, int64_t(m.own0) * m.nl, c, parity);
+    dispatch_nl(m.nl, [&](auto nl) {
+      k_cg_update_block<decltype(nl)::value><<<cg_grid(m.n_own), kCgThreads, 0, s>>>(m.n_own, int64_t(m.own0) * m.nl, c, parity);
+    });
   } else {
     k_cg_update<<<cg_grid((rows + 3) / 4), kCgThreads, 0, s>>>(rows, int64_t(m.own0) * m.nl, c, parity);
   }
@@ -746,10 +766,9 @@ void launch_cg_direction(const MeshView& m, const CgBuffers& c, int parity, cuda
 }
 
 void launch_unit_row_col0(const MeshView& m, double* values, double* b, cudaStream_t s) {
-  if (m.kind == HDD_SIMPLEX2D)
-    k_unit_row_col0<HDD_SIMPLEX2D><<<1, 32, 0, s>>>(m, values, b);
-  else
-    k_unit_row_col0<HDD_CUBE2D><<<1, 32, 0, s>>>(m, values, b);
+  dispatch_block(m, [&](auto nf, auto nl) {
+    k_unit_row_col0<decltype(nf)::value, decltype(nl)::value><<<1, 32, 0, s>>>(m, values, b);
+  });
   count_launch();
   HDD_CUDA(cudaGetLastError());
 }
@@ -762,9 +781,10 @@ void launch_subtract_mean(double* x, int64_t n, double* partial, CgScalars* sc, 
   HDD_CUDA(cudaGetLastError());
 }
 
-void launch_pack(const double* v_local, const int32_t* dof_idx, int64_t n, double* out, cudaStream_t s) {
+void launch_pack(const double* v_local, const int32_t* cells, int64_t n_cells, int nd, double* out, cudaStream_t s) {
+  const int64_t n = n_cells * nd;
   if (n == 0) return;
-  k_pack<<<int(std::min<int64_t>((n + 255) / 256, 1024)), 256, 0, s>>>(v_local, dof_idx, n, out);
+  k_pack<<<int(std::min<int64_t>((n + 255) / 256, 1024)), 256, 0, s>>>(v_local, cells, n, nd, out);
   count_launch();
   HDD_CUDA(cudaGetLastError());
 }

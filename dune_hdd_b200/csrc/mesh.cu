@@ -128,16 +128,20 @@ hdd_mesh::~hdd_mesh() {
   if (stream) cudaStreamDestroy(stream);  // the communicator belongs to its hdd_comm
 }
 
-void hdd_mesh::halo_exchange(double* v_local) {
+void hdd_mesh::halo_exchange(double* v_local, int nd) {
   if (world == 1 || peers.empty()) return;
-  int64_t n_send = 0;
-  for (const auto& p : peers) n_send += p.send_count;
-  launch_pack(v_local, send_idx.p, n_send, send_buf.p, stream);
+  if (send_buf_capacity < n_send_cells * nd) {
+    HDD_CUDA(cudaStreamSynchronize(stream));
+    send_buf.release();
+    send_buf.alloc(size_t(n_send_cells) * nd);
+    send_buf_capacity = n_send_cells * nd;
+  }
+  launch_pack(v_local, send_idx.p, n_send_cells, nd, send_buf.p, stream);
   Nccl& nc = Nccl::get();
   nc.group_start();
   for (const auto& p : peers) {
-    if (p.send_count) nc.send(send_buf.p + p.send_offset, size_t(p.send_count), p.rank, comm, stream);
-    if (p.recv_count) nc.recv(v_local + p.recv_offset, size_t(p.recv_count), p.rank, comm, stream);
+    if (p.send_count) nc.send(send_buf.p + p.send_offset * nd, size_t(p.send_count) * nd, p.rank, comm, stream);
+    if (p.recv_count) nc.recv(v_local + p.recv_offset * nd, size_t(p.recv_count) * nd, p.rank, comm, stream);
   }
   nc.group_end();
 }
@@ -515,10 +519,10 @@ int hdd_mesh_attach_comm(hdd_mesh* m, hdd_comm* c) {
       if (it == peers.end()) {
         HaloPeer p{};
         p.rank = r;
-        p.recv_offset = int64_t(lc) * nl;
+        p.recv_offset = int64_t(lc);
         it = peers.emplace(r, p).first;
       }
-      it->second.recv_count += nl;
+      it->second.recv_count += 1;
     }
     std::map<int, std::vector<int32_t>> send_cells;
     compute_send_cells(nl, m->n_verts_loc, m->h_cell_verts_loc.data(), m->own0, int64_t(m->own0) + m->n_own, halo_cells,
@@ -528,13 +532,14 @@ int hdd_mesh_attach_comm(hdd_mesh* m, hdd_comm* c) {
     for (auto& kv : peers) {
       HaloPeer p = kv.second;
       p.send_offset = int64_t(idx.size());
-      for (int32_t lc : send_cells[kv.first])
-        for (int i = 0; i < nl; ++i) idx.push_back(lc * nl + i);
+      for (int32_t lc : send_cells[kv.first]) idx.push_back(lc);
       p.send_count = int64_t(idx.size()) - p.send_offset;
       m->peers.push_back(p);
     }
     m->send_idx.upload(idx.data(), idx.size(), m->stream);
-    m->send_buf.alloc(idx.size());
+    m->n_send_cells = int64_t(idx.size());
+    m->send_buf.alloc(idx.size() * size_t(nl));
+    m->send_buf_capacity = int64_t(idx.size()) * nl;
     // tables for the peer-memory SpMV: owner rank and the owner's row offset (in cells) of every halo cell
     {
       std::vector<int32_t> hp(halo_cells.size()), hr(halo_cells.size());

@@ -16,6 +16,51 @@ hdd_swipdg::~hdd_swipdg() {
   if (sc_host) cudaFreeHost(sc_host);
 }
 
+namespace hdd {
+
+void require_init(const hdd_swipdg* h) {
+  if (!h) HDD_THROW(HDD_ERR_WRONG_INPUT, "discretization handle is NULL");
+  if (!h->initialized)
+    HDD_THROW(HDD_ERR_USING_THIS_WRONG, "The user has to call init() before calling any other method!");
+}
+
+// map_parameter + type check of uncached_solve (discretizations/base.hh:333-334)
+void check_mu(const hdd_swipdg* h, const double* mu, int mu_size, const char* name) {
+  const bool parametric = h->factor.parametric() || h->force.parametric() || h->dirichlet.parametric() || h->neumann.parametric();
+  if (parametric) {
+    if (!mu || mu_size != h->parameter_size)
+      HDD_THROW(HDD_ERR_WRONG_PARAMETER_TYPE, name << " has size " << (mu ? mu_size : 0) << " vs. parameter type {"
+                                                   << h->parameter_name << ": " << h->parameter_size << "}");
+  } else if (mu && mu_size != 0) {
+    HDD_THROW(HDD_ERR_WRONG_PARAMETER_TYPE, name << " has size " << mu_size << " vs. empty parameter type");
+  }
+}
+
+double eval_coef(const Program& p, const double* mu, int mu_size) {
+  double v[4] = {0, 0, 0, 0};
+  for (int k = 0; k < mu_size && k < 4; ++k) v[k] = mu[k];
+  return eval_program(p, v);
+}
+
+DevCombo make_combo(const hdd_swipdg* h, const AffineFn& f, const double* mu, int mu_size) {
+  DevCombo c{};
+  int order = 0;
+  for (size_t q = 0; q < f.comps.size(); ++q) {
+    c.theta[c.n] = eval_coef(f.coef_prog[q], mu, mu_size);
+    c.idx[c.n++] = f.comps[q].idx;
+    order = std::max(order, f.comps[q].order);
+  }
+  if (f.has_affine()) {
+    c.theta[c.n] = 1.0;
+    c.idx[c.n++] = f.affine.idx;
+    order = std::max(order, f.affine.order);
+  }
+  c.order = order;
+  return c;
+}
+
+}  // namespace hdd
+
 namespace {
 
 constexpr double kPi = 3.14159265358979323846264338327950288;
@@ -78,30 +123,6 @@ AffineFn add_affine(hdd_swipdg* h, const hdd_affine_function& a, const char* wha
   return out;
 }
 
-void require_init(const hdd_swipdg* h) {
-  if (!h) HDD_THROW(HDD_ERR_WRONG_INPUT, "discretization handle is NULL");
-  if (!h->initialized)
-    HDD_THROW(HDD_ERR_USING_THIS_WRONG, "The user has to call init() before calling any other method!");
-}
-
-// map_parameter + type check of uncached_solve (discretizations/base.hh:333-334)
-void check_mu(const hdd_swipdg* h, const double* mu, int mu_size, const char* name) {
-  const bool parametric = h->factor.parametric() || h->force.parametric() || h->dirichlet.parametric();
-  if (parametric) {
-    if (!mu || mu_size != h->parameter_size)
-      HDD_THROW(HDD_ERR_WRONG_PARAMETER_TYPE, name << " has size " << (mu ? mu_size : 0) << " vs. parameter type {"
-                                                   << h->parameter_name << ": " << h->parameter_size << "}");
-  } else if (mu && mu_size != 0) {
-    HDD_THROW(HDD_ERR_WRONG_PARAMETER_TYPE, name << " has size " << mu_size << " vs. empty parameter type");
-  }
-}
-
-double eval_coef(const Program& p, const double* mu, int mu_size) {
-  double v[4] = {0, 0, 0, 0};
-  for (int k = 0; k < mu_size && k < 4; ++k) v[k] = mu[k];
-  return eval_program(p, v);
-}
-
 void assemble_all(hdd_swipdg* h) {
   hdd_mesh* m = h->mesh;
   const MeshView v = h->view();
@@ -115,6 +136,8 @@ void assemble_all(hdd_swipdg* h) {
     for (const RhsTerm& t : part.terms) {
       if (t.kind == 0) {
         if (!t.f.zero) launch_rhs_volume(v, h->fn_h(t.f), t.f.order, t.f.separable, h->polorder, part.values.p, s);
+      } else if (t.kind == 2) {
+        if (!t.f.zero) launch_rhs_neumann(v, h->fn_h(t.f), t.f.order, h->polorder, part.values.p, s);
       } else {
         if (!t.f.zero && !t.g.zero)
           launch_rhs_dirichlet(v, h->fn_h(t.f), t.f.order, h->fn_h(t.g), t.g.order, h->polorder, part.values.p, s);
@@ -162,7 +185,7 @@ void freeze_rhs(hdd_swipdg* h, const double* mu, int mu_size) {
 
 void ensure_solve_workspace(hdd_swipdg* h) {
   hdd_mesh* m = h->mesh;
-  const size_t rows = size_t(h->n_rows), loc = size_t(m->n_loc) * m->nl;
+  const size_t rows = size_t(h->n_rows), loc = size_t(m->n_loc) * h->nl;
   if (!h->x.p) {
     h->dinv.alloc(rows);
     h->x.alloc(rows);
@@ -209,7 +232,7 @@ bool setup_p2p(hdd_swipdg* h) {
   if (h->p2p_failed) return false;
   cudaStream_t s = m->stream;
   Nccl& nc = Nccl::get();
-  const size_t loc = size_t(m->n_loc) * m->nl;
+  const size_t loc = size_t(m->n_loc) * h->nl;
   int ok = 1;
   std::vector<IpcRecord> all(size_t(m->world));
   try {
@@ -285,23 +308,6 @@ int parse_solver_type(const char* type) {
   HDD_THROW(HDD_ERR_WRONG_INPUT, "solver type '" << t << "' is not one of solver_types()");
 }
 
-DevCombo make_combo(const hdd_swipdg* h, const AffineFn& f, const double* mu, int mu_size) {
-  DevCombo c{};
-  int order = 0;
-  for (size_t q = 0; q < f.comps.size(); ++q) {
-    c.theta[c.n] = eval_coef(f.coef_prog[q], mu, mu_size);
-    c.idx[c.n++] = f.comps[q].idx;
-    order = std::max(order, f.comps[q].order);
-  }
-  if (f.has_affine()) {
-    c.theta[c.n] = 1.0;
-    c.idx[c.n++] = f.affine.idx;
-    order = std::max(order, f.affine.order);
-  }
-  c.order = order;
-  return c;
-}
-
 // Pymor::AffinelyDecomposableFunctionInterface::alpha / gamma (call sites estimators/block-swipdg.hh:778-781):
 // min / max over the components of theta_q(mu1) / theta_q(mu2); 1 for non-parametric functions.
 void alpha_gamma(const hdd_swipdg* h, const double* mu1, const double* mu2, int mu_size, double& alpha, double& gamma) {
@@ -327,7 +333,9 @@ void run_indicators(hdd_swipdg* h, const double* u_host, const hdd_parameters* p
   cudaStream_t s = m->stream;
   if (m->kind != HDD_SIMPLEX2D)
     HDD_THROW(HDD_ERR_USING_THIS_WRONG, "the estimators are only available on 2d simplex grids (estimators/swipdg.hh:71)");
-  const int nl = m->nl;
+  if (h->polorder != 1)
+    HDD_THROW(HDD_ERR_NOT_IMPLEMENTED, "the estimators need polOrder 1 (Oswald interpolation and RT0 reconstruction, estimators/swipdg.hh:149,359)");
+  const int nl = h->nl;
   const size_t loc = size_t(m->n_loc) * nl, rows = size_t(h->n_rows);
   if (!h->tmp_local.p) { h->tmp_local.alloc(loc); h->tmp_local.zero(s); }
   if (u_host) {
@@ -336,7 +344,7 @@ void run_indicators(hdd_swipdg* h, const double* u_host, const hdd_parameters* p
     if (!h->have_solution) HDD_THROW(HDD_ERR_USING_THIS_WRONG, "no vector given and no solution available");
     HDD_CUDA(cudaMemcpyAsync(h->tmp_local.p + size_t(m->own0) * nl, h->x.p, rows * sizeof(double), cudaMemcpyDeviceToDevice, s));
   }
-  m->halo_exchange(h->tmp_local.p);
+  m->halo_exchange(h->tmp_local.p, nl);
   if (!h->vertex_mean.p) h->vertex_mean.alloc(size_t(m->n_verts_loc));
   launch_oswald_vertex_means(m->vptr.p, m->vdof.p, m->vboundary.p, m->n_verts_loc, h->tmp_local.p, h->vertex_mean.p, s);
 
@@ -420,11 +428,15 @@ int hdd_swipdg_create(hdd_mesh* mesh, int polorder, const hdd_problem* problem, 
     if (!out) HDD_THROW(HDD_ERR_WRONG_INPUT, "out is NULL");
     *out = nullptr;
     if (!mesh || !problem) HDD_THROW(HDD_ERR_WRONG_INPUT, "mesh or problem is NULL");
-    if (polorder != 1) HDD_THROW(HDD_ERR_NOT_IMPLEMENTED, "polorder " << polorder << " (only p = 1 so far)");
+    if (polorder != 1 && polorder != 2) HDD_THROW(HDD_ERR_NOT_IMPLEMENTED, "polorder " << polorder << " (p = 1 and p = 2 only)");
     mesh->set_device();
     std::unique_ptr<hdd_swipdg> h(new hdd_swipdg);
     h->mesh = mesh;
     h->polorder = polorder;
+    h->nl = n_local_dofs(mesh->kind, polorder);
+    if (mesh->n_global * h->nl > int64_t(INT32_MAX)) HDD_THROW(HDD_ERR_WRONG_INPUT, "too many DoFs for 32-bit column indices");
+    h->sub_dof_offsets.resize(mesh->sub_cell_offsets.size());
+    for (size_t k = 0; k < mesh->sub_cell_offsets.size(); ++k) h->sub_dof_offsets[k] = h->nl * mesh->sub_cell_offsets[k];
     h->parameter_name = problem->parameter_name ? problem->parameter_name : "";
     h->parameter_size = problem->parameter_name ? problem->parameter_size : 0;
     if (h->parameter_size < 0 || h->parameter_size > 4) HDD_THROW(HDD_ERR_WRONG_INPUT, "parameter_size must be in [0,4]");
@@ -437,11 +449,6 @@ int hdd_swipdg_create(hdd_mesh* mesh, int polorder, const hdd_problem* problem, 
     const bool parametric = h->factor.parametric() || h->force.parametric() || h->dirichlet.parametric() || h->neumann.parametric();
     if (parametric && h->parameter_size == 0)
       HDD_THROW(HDD_ERR_WRONG_INPUT, "parametric data functions but no parameter_name / parameter_size given");
-    // Neumann data: no BASELINE config has Neumann faces (AllDirichlet everywhere); non-zero data is not implemented
-    for (const FnRef& r : h->neumann.comps)
-      if (!r.zero) HDD_THROW(HDD_ERR_NOT_IMPLEMENTED, "non-zero Neumann data (Functionals::L2Face, discretizations/swipdg.hh:335-356)");
-    if (h->neumann.has_affine() && !h->neumann.affine.zero)
-      HDD_THROW(HDD_ERR_NOT_IMPLEMENTED, "non-zero Neumann data (Functionals::L2Face, discretizations/swipdg.hh:335-356)");
     if (problem->diffusion_tensor) {
       h->has_tensor = true;
       std::vector<double> loc(size_t(mesh->n_loc) * 4);
@@ -451,8 +458,8 @@ int hdd_swipdg_create(hdd_mesh* mesh, int polorder, const hdd_problem* problem, 
     }
     h->fn_dev.upload(h->fn_host.data(), h->fn_host.size(), mesh->stream);
     HDD_CUDA(cudaStreamSynchronize(mesh->stream));
-    h->n_rows = int64_t(mesh->n_own) * mesh->nl;
-    h->nnz = mesh->n_blocks * mesh->nl * mesh->nl;
+    h->n_rows = int64_t(mesh->n_own) * h->nl;
+    h->nnz = mesh->n_blocks * h->nl * h->nl;
 
     // affine structure of the system matrix (discretizations/swipdg.hh:228-247) ...
     for (size_t q = 0; q < h->factor.comps.size(); ++q) {
@@ -506,6 +513,15 @@ int hdd_swipdg_create(hdd_mesh* mesh, int polorder, const hdd_problem* problem, 
         p.terms.push_back({1, h->factor.comps[pp], h->dirichlet.comps[qq]});
         h->rhs_comps.push_back(std::move(p));
       }
+    // ... Neumann parts (:335-356): L2Face on the Neumann intersections
+    for (size_t q = 0; q < h->neumann.comps.size(); ++q) {
+      VectorPart p;
+      p.coef_expr = h->neumann.coef_expr[q];
+      p.coef_prog = h->neumann.coef_prog[q];
+      p.terms.push_back({2, h->neumann.comps[q], FnRef{}});
+      h->rhs_comps.push_back(std::move(p));
+    }
+    if (h->neumann.has_affine() && !h->neumann.affine.zero) affine_rhs().terms.push_back({2, h->neumann.affine, FnRef{}});
     if (h->lhs_comps.size() + 1 > size_t(kMaxParts) || h->rhs_comps.size() + 1 > size_t(kMaxParts))
       HDD_THROW(HDD_ERR_NOT_IMPLEMENTED, "more than " << kMaxParts - 1 << " affine components");
     *out = h.release();
@@ -538,6 +554,7 @@ int hdd_swipdg_init(hdd_swipdg* h) {
     for (auto& p : h->rhs_comps) p.values.alloc(size_t(h->n_rows));
     if (h->rhs_affine) h->rhs_affine->values.alloc(size_t(h->n_rows));
     assemble_all(h);
+    assemble_products(h);
     HDD_CUDA(cudaStreamSynchronize(s));
     h->initialized = true;
   });
@@ -566,7 +583,7 @@ int hdd_swipdg_assemble(hdd_swipdg* h, double* seconds) {
 int hdd_num_dofs(const hdd_swipdg* h, int64_t* n_global, int64_t* n_owned) {
   return guarded([&] {
     if (!h) HDD_THROW(HDD_ERR_WRONG_INPUT, "discretization handle is NULL");
-    if (n_global) *n_global = h->mesh->n_global * h->mesh->nl;
+    if (n_global) *n_global = h->mesh->n_global * h->nl;
     if (n_owned) *n_owned = h->n_rows;
   });
 }
@@ -667,12 +684,12 @@ int hdd_apply(hdd_swipdg* h, const double* mu, int mu_size, const double* x_host
     m->set_device();
     cudaStream_t s = m->stream;
     const double* vals = freeze_lhs(h, mu, mu_size);
-    const size_t loc = size_t(m->n_loc) * m->nl, rows = size_t(h->n_rows);
+    const size_t loc = size_t(m->n_loc) * h->nl, rows = size_t(h->n_rows);
     if (!h->tmp_local.p) { h->tmp_local.alloc(loc); h->tmp_local.zero(s); }
     DevBuf<double> y;
     y.alloc(rows);
-    HDD_CUDA(cudaMemcpyAsync(h->tmp_local.p + size_t(m->own0) * m->nl, x_host, rows * sizeof(double), cudaMemcpyHostToDevice, s));
-    m->halo_exchange(h->tmp_local.p);
+    HDD_CUDA(cudaMemcpyAsync(h->tmp_local.p + size_t(m->own0) * h->nl, x_host, rows * sizeof(double), cudaMemcpyHostToDevice, s));
+    m->halo_exchange(h->tmp_local.p, h->nl);
     launch_spmv(h->view(), vals, h->tmp_local.p, y.p, s);
     HDD_CUDA(cudaMemcpyAsync(y_host, y.p, rows * sizeof(double), cudaMemcpyDeviceToHost, s));
     HDD_CUDA(cudaStreamSynchronize(s));
@@ -719,7 +736,7 @@ int hdd_solve(hdd_swipdg* h, const char* type, double precision, int max_iter, c
     h->last_precond = use_diag;
     if (use_diag == 2) {
       if (!h->dinv_block.p) {
-        h->dinv_block.alloc(size_t(m->n_own) * m->nl * m->nl);
+        h->dinv_block.alloc(size_t(m->n_own) * h->nl * h->nl);
         h->z.alloc(size_t(h->n_rows));
       }
       launch_invert_diag_blocks(v, vals, h->dinv_block.p, s);
@@ -753,8 +770,8 @@ int hdd_solve(hdd_swipdg* h, const char* type, double precision, int max_iter, c
     if (p2p) {
       // Jacobi diagonal including the halo (static during the solve): owned part computed here, halo exchanged once
       double* dl = h->dinv_local.p;
-      HDD_CUDA(cudaMemcpyAsync(dl + size_t(m->own0) * m->nl, h->dinv.p, size_t(h->n_rows) * sizeof(double), cudaMemcpyDeviceToDevice, s));
-      m->halo_exchange(dl);
+      HDD_CUDA(cudaMemcpyAsync(dl + size_t(m->own0) * h->nl, h->dinv.p, size_t(h->n_rows) * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      m->halo_exchange(dl, h->nl);
       c.p_alt = h->p_alt.p;
       peer = &h->peer_view;
     }
@@ -764,7 +781,7 @@ int hdd_solve(hdd_swipdg* h, const char* type, double precision, int max_iter, c
     int par = 0, launched = 0, batch = 16;
     for (;;) {
       for (int k = 0; k < batch; ++k) {
-        if (multi && !p2p) m->halo_exchange(c.p);
+        if (multi && !p2p) m->halo_exchange(c.p, h->nl);
         launch_cg_spmv(v, c, par, s, peer);
         if (multi) nc.all_reduce_sum(&c.sc->red[0], 1, m->comm, s);
         launch_cg_update(v, c, par, s);
@@ -827,7 +844,7 @@ int hdd_num_subdomains(const hdd_swipdg* h, int* n) {
 int hdd_subdomain_offsets(const hdd_swipdg* h, const int64_t** offsets_host) {
   return guarded([&] {
     if (!h) HDD_THROW(HDD_ERR_WRONG_INPUT, "discretization handle is NULL");
-    if (offsets_host) *offsets_host = h->mesh->sub_dof_offsets.data();
+    if (offsets_host) *offsets_host = h->sub_dof_offsets.data();
   });
 }
 
@@ -848,7 +865,7 @@ int hdd_block_extract(hdd_swipdg* h, int ss, int nn, int q, hdd_csr* out) {
     if (!out) HDD_THROW(HDD_ERR_WRONG_INPUT, "out is NULL");
     std::memset(out, 0, sizeof(*out));
     hdd_mesh* m = h->mesh;
-    const int ns = m->n_subdomains, nl = m->nl, nf = m->nf;
+    const int ns = m->n_subdomains, nl = h->nl, nf = m->nf;
     if (ss < 0 || ss >= ns) HDD_THROW(HDD_ERR_INDEX_OUT_OF_RANGE, "0 <= ss < num_subdomains() = " << ns << " is not true for ss = " << ss << "!");
     if (nn < 0 || nn >= ns) HDD_THROW(HDD_ERR_INDEX_OUT_OF_RANGE, "0 <= nn < num_subdomains() = " << ns << " is not true for nn = " << nn << "!");
     if (nn != ss) {
@@ -1070,11 +1087,12 @@ int hdd_kernel_bytes(hdd_swipdg* h, int which, double* bytes) {
     const hdd_mesh* m = h->mesh;
     const double cells = double(m->n_own), rows = double(h->n_rows), nnz = double(h->nnz);
     const double geo = m->kind == HDD_SIMPLEX2D ? 48.0 : 32.0, rec = 4.0 * m->nf + 8.0;  // neighbour record + block offset
+    const int nl = h->nl;
     double b = 0.0;
     switch (which) {
       case 0: b = 8.0 * nnz + rec * cells + 8.0 * rows /* read p */ + 8.0 * rows /* write q */; break;
       case 1:  // diagonal: read x,p,q,r,dinv, write x,r; block: read x,p,q,r + n_loc^2 block per cell, write x,r,z
-        b = h->last_precond == 2 ? 7.0 * 8.0 * rows + 8.0 * m->nl * rows : 7.0 * 8.0 * rows;
+        b = h->last_precond == 2 ? 7.0 * 8.0 * rows + 8.0 * nl * rows : 7.0 * 8.0 * rows;
         break;
       case 2:  // diagonal: read r,dinv,p, write p; block: read z,p, write p
         b = h->last_precond == 2 ? 3.0 * 8.0 * rows : 4.0 * 8.0 * rows;

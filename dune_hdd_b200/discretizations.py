@@ -102,12 +102,76 @@ class _Parts:
         return out
 
 
+class _ProductParts(_Parts):
+    """get_product(id): the affinely decomposed product matrix (discretizations/base.hh:281-291)."""
+
+    def __init__(self, disc, pid):
+        self._d, self._id = disc, pid.encode()
+
+    def _info(self):
+        n, a, v = C.c_int(), C.c_int(), C.c_int()
+        _check(capi.lib().hdd_product_num_components(self._d._h, self._id, C.byref(n), C.byref(a), C.byref(v)))
+        return n.value, bool(a.value), bool(v.value)
+
+    def num_components(self):
+        return self._info()[0]
+
+    def has_affine_part(self):
+        return self._info()[1]
+
+    def volume_pattern(self):
+        """True: values follow SWIPDG.pattern_volume() (one dense block per cell), False: SWIPDG.pattern()"""
+        return self._info()[2]
+
+    def coefficient(self, q):
+        s = C.c_char_p()
+        _check(capi.lib().hdd_product_coefficient(self._d._h, self._id, q, C.byref(s)))
+        return s.value.decode()
+
+    def _values(self, q):
+        p, n = C.POINTER(C.c_double)(), C.c_int64()
+        _check(capi.lib().hdd_product_values(self._d._h, self._id, q, C.byref(p), C.byref(n)))
+        out = np.empty(n.value)
+        _check(capi.lib().hdd_copy_to_host(self._d._h, capi.ptr(out), p, C.c_size_t(out.nbytes)))
+        return out
+
+    def device_pointer(self, q):
+        p, n = C.POINTER(C.c_double)(), C.c_int64()
+        _check(capi.lib().hdd_product_values(self._d._h, self._id, q, C.byref(p), C.byref(n)))
+        return C.cast(p, C.c_void_p).value, n.value
+
+    def freeze_parameter(self, mu=None):
+        mu_a, ms = _mu_array(mu)
+        out = self.affine_part().copy() if self.has_affine_part() else 0.0
+        for q in range(self.num_components()):
+            theta = np.zeros(1)
+            _check(capi.lib().hdd_expression_evaluate(self.coefficient(q).encode(),
+                                                      (self._d.problem.parameter_name or "mu").encode(),
+                                                      capi.ptr(mu_a), ms, capi.ptr(theta)))
+            out = out + theta[0] * self.component(q)
+        return out
+
+    def apply2(self, u, v, mu=None):
+        """u^T P(mu) v on the device"""
+        mu_a, ms = _mu_array(mu)
+        r = C.c_double()
+        _check(capi.lib().hdd_product_apply2(self._d._h, self._id, capi.ptr(mu_a), ms, capi.ptr(capi.as_f64(u)),
+                                             capi.ptr(capi.as_f64(v)), C.byref(r)))
+        return r.value
+
+    def induced_norm(self, u, mu=None):
+        return float(np.sqrt(max(self.apply2(u, u, mu), 0.0)))
+
+
 class SWIPDG:
     """Discretizations::SWIPDG(grid_provider, boundary_info_cfg, problem, level, only_these_products)."""
 
-    def __init__(self, grid, problem, boundary_info=None, polorder=1, device=0, cell_range=None, comm=None):
+    def __init__(self, grid, problem, boundary_info=None, polorder=1, device=0, cell_range=None, comm=None,
+                 only_these_products=()):
         L = capi.lib()
         self.grid, self.problem = grid, problem
+        self.polorder = polorder
+        self.n_loc = ((polorder + 1) * (polorder + 2) // 2) if grid.kind == capi.HDD_SIMPLEX2D else (polorder + 1) ** 2
         self._h = None
         self._mesh = C.c_void_p()
         self._cache = {}
@@ -130,6 +194,9 @@ class SWIPDG:
             raise
         self._h = h
         self.cell_range = (cb, ce)
+        if only_these_products:
+            ids = (C.c_char_p * len(only_these_products))(*[p.encode() for p in only_these_products])
+            _check(L.hdd_swipdg_only_these_products(self._h, ids, len(only_these_products)))
 
     def __del__(self):
         try:
@@ -189,6 +256,38 @@ class SWIPDG:
 
     get_operator = system_matrix
     get_rhs = rhs
+
+    # ---- products (discretizations/base.hh:272-291) ---------------------------------------------------
+    def available_products(self):
+        t, n = C.POINTER(C.c_char_p)(), C.c_int()
+        _check(capi.lib().hdd_products_available(self._h, C.byref(t), C.byref(n)))
+        return [t[i].decode() for i in range(n.value)]
+
+    def get_product(self, id):
+        p = _ProductParts(self, id)
+        p._info()  # raises like the reference: no products at all / unknown id
+        return p
+
+    def pattern_volume(self):
+        """(rowptr, col) of the volume-pattern products: one dense n_loc x n_loc block per owned cell"""
+        L = capi.lib()
+        n, nnz = C.c_int64(), C.c_int64()
+        rp, cl = C.POINTER(C.c_int64)(), C.POINTER(C.c_int32)()
+        _check(L.hdd_pattern_volume(self._h, C.byref(n), C.byref(nnz), C.byref(rp), C.byref(cl)))
+        rowptr = np.empty(n.value + 1, np.int64)
+        col = np.empty(nnz.value, np.int32)
+        _check(L.hdd_copy_to_host(self._h, capi.ptr(rowptr, C.c_int64), rp, C.c_size_t(rowptr.nbytes)))
+        _check(L.hdd_copy_to_host(self._h, capi.ptr(col, C.c_int32), cl, C.c_size_t(col.nbytes)))
+        return rowptr, col
+
+    def error_norms(self, exact, exact_dx, exact_dy, vector=None, order=5, mu=None):
+        """{L2, H1_semi, energy} norms of vector - exact (test/linearelliptic-swipdg.hh:267-290), on the device"""
+        mu_a, ms = _mu_array(mu)
+        out = np.zeros(3)
+        v = None if vector is None else capi.as_f64(vector)
+        _check(capi.lib().hdd_error_norms(self._h, capi.ptr(v), exact.encode(), exact_dx.encode(), exact_dy.encode(),
+                                          int(order), capi.ptr(mu_a), ms, capi.ptr(out)))
+        return {"L2": out[0], "H1_semi": out[1], "energy": out[2]}
 
     def parametric(self):
         return self.problem.parametric()
@@ -272,7 +371,7 @@ class SWIPDG:
         p = self._parameters(parameters)
         eta = C.c_double()
         v = None if vector is None else capi.as_f64(vector)
-        n = self.num_subdomains() if "OS2014" in type else self.num_owned_dofs() // self.grid.n_loc
+        n = self.num_subdomains() if "OS2014" in type else self.num_owned_dofs() // self.n_loc
         out = np.zeros(n)
         _check(capi.lib().hdd_estimate(self._h, type.encode(), capi.ptr(v), C.byref(p), C.byref(eta), capi.ptr(out)))
         return out
@@ -281,7 +380,7 @@ class SWIPDG:
         """all squared per-cell indicators of one device pass (dict of arrays), for parity tests"""
         p = self._parameters(parameters)
         v = None if vector is None else capi.as_f64(vector)
-        n = self.num_owned_dofs() // self.grid.n_loc
+        n = self.num_owned_dofs() // self.n_loc
         out = np.zeros((8, n))
         _check(capi.lib().hdd_indicators(self._h, capi.ptr(v), C.byref(p), capi.ptr(out)))
         names = ["nc2", "res2", "r2", "df2", "dfstar2", "rstar2", "amin", "resstar2"]
@@ -320,10 +419,10 @@ class BlockSWIPDG(SWIPDG):
     """Discretizations::BlockSWIPDG(ms_grid_provider, cfg, problem): the grid carries cell_subdomain (subdomain-major
     numbering), boundary info is forced to AllDirichlet (discretizations/block-swipdg.hh:110,237)."""
 
-    def __init__(self, grid, problem, polorder=1, device=0, cell_range=None, comm=None):
+    def __init__(self, grid, problem, polorder=1, device=0, cell_range=None, comm=None, only_these_products=()):
         if grid.cell_subdomain is None:
             raise wrong_input_given(capi.HDD_ERR_WRONG_INPUT, "BlockSWIPDG needs a grid with subdomains")
-        super().__init__(grid, problem, None, polorder, device, cell_range, comm)
+        super().__init__(grid, problem, None, polorder, device, cell_range, comm, only_these_products)
 
     @staticmethod
     def static_id():
@@ -345,8 +444,26 @@ class BlockSWIPDG(SWIPDG):
             raise index_out_of_range(capi.HDD_ERR_INDEX_OUT_OF_RANGE,
                                      "0 <= ss < num_subdomains() = %d is not true for ss = %d!" % (len(off) - 1, ss))
         part = self.rhs().affine_part() if q == -1 else self.rhs().component(q)
-        r0 = self.cell_range[0] * self.grid.n_loc
+        r0 = self.cell_range[0] * self.n_loc
         return np.array(part[off[ss] - r0:off[ss + 1] - r0])
+
+    def get_local_product(self, ss, id, q=-1):
+        """product of the local discretization on subdomain ss (discretizations/block-swipdg.hh:612-618) for the
+        volume-pattern products l2 / h1_semi / elliptic, whose local matrix is the diagonal sub-block of the global
+        one: scipy CSR with subdomain-local indices"""
+        import scipy.sparse as sp
+        off = self.subdomain_offsets()
+        if ss < 0 or ss >= len(off) - 1:
+            raise index_out_of_range(capi.HDD_ERR_INDEX_OUT_OF_RANGE,
+                                     "0 <= ss < num_subdomains() = %d is not true for ss = %d!" % (len(off) - 1, ss))
+        if id not in ("l2", "h1_semi", "elliptic"):
+            raise wrong_input_given(capi.HDD_ERR_WRONG_INPUT, id)
+        P = self.get_product(id)
+        vals = P.affine_part() if q == -1 else P.component(q)
+        nl, r0 = self.n_loc, self.cell_range[0] * self.n_loc
+        a, b = off[ss] - r0, off[ss + 1] - r0
+        blocks = vals.reshape(-1, nl, nl)[a // nl:b // nl]
+        return sp.block_diag(list(blocks), format="csr") if len(blocks) else sp.csr_matrix((0, 0))
 
     def localize_vector(self, global_vector, ss):
         """discretizations/block-swipdg.hh:567-583"""

@@ -118,6 +118,11 @@ def ESV2007(integration_order=3):
                    AffinelyDecomposable(Expression(ESV2007_FORCE, integration_order, "force")), name="ESV2007")
 
 
+# Stuff::Functions::ESV2007::Testcase1ExactSolution and its gradient as Expression strings (u, du/dx, du/dy)
+ESV2007_EXACT = ("cos(0.5*pi*x[0])*cos(0.5*pi*x[1])", "-0.5*pi*sin(0.5*pi*x[0])*cos(0.5*pi*x[1])",
+                 "-0.5*pi*cos(0.5*pi*x[0])*sin(0.5*pi*x[1])")
+
+
 def esv2007_exact(xy):
     """Stuff::Functions::ESV2007::Testcase1ExactSolution (testcases/ESV2007.hh:41)"""
     return np.cos(0.5 * np.pi * xy[..., 0]) * np.cos(0.5 * np.pi * xy[..., 1])

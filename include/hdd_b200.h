@@ -135,7 +135,10 @@ typedef struct hdd_swipdg hdd_swipdg;
 enum { HDD_LHS = 0, HDD_RHS = 1 };
 
 /* SWIPDG::SWIPDG(...) (discretizations/swipdg.hh:159-177) / BlockSWIPDG::BlockSWIPDG (block-swipdg.hh:172-260).
- * polorder must be 1 this round.  Fails with HDD_ERR_WRONG_INPUT if the tensor is empty etc. */
+ * polorder = 1 (P1 / Q1, n_loc = 3 / 4) or 2 (P2 / Q2, n_loc = 6 / 9; nodes in lexicographic order - (0,0),(1/2,0),(1,0),
+ * (0,1/2),(1/2,1/2),(0,1) on the triangle, i + 3 j on the square; unpinned: every reference test instantiates polOrder 1,
+ * test/linearelliptic-swipdg.cc:45).  The estimators need polorder 1.  Fails with HDD_ERR_WRONG_INPUT if the factor is
+ * empty etc. */
 int hdd_swipdg_create(hdd_mesh* mesh, int polorder, const hdd_problem* problem, hdd_swipdg** out);
 int hdd_swipdg_destroy(hdd_swipdg* h);
 
@@ -181,6 +184,38 @@ int hdd_solver_types(const char* const** types, int* n_types);
 int hdd_solve(hdd_swipdg* h, const char* type, double precision, int max_iter, const double* mu, int mu_size,
               double* x_host, hdd_solve_info* info);
 int hdd_solution_dev(hdd_swipdg* h, const double** x_dev);
+
+/* ---- products (discretizations/swipdg.hh:359-508, block-swipdg.hh:392-548, base.hh:272-291) ---------------- */
+/* The `only_these_products` constructor argument (discretizations/swipdg.hh:159-163): ids out of "l2", "h1_semi",
+ * "elliptic", "boundary_l2", "penalty", "energy" (others are ignored, like the std::find tests of :364-505).  Call
+ * before hdd_swipdg_init (they are then assembled by init() together with the system, like in system_assembler.walk());
+ * on an initialised handle they are assembled at once.  Default: none, as in the reference.
+ *   l2           int_T phi_i phi_j                             volume pattern (one dense n_loc x n_loc block per cell)
+ *   h1_semi      int_T grad phi_j . grad phi_i                 volume pattern
+ *   elliptic     int_T a_q K grad phi_j . grad phi_i           volume pattern, one part per diffusion-factor part
+ *   boundary_l2  int_{dT on dOmega} phi_i phi_j                volume pattern
+ *   penalty      the penalty terms of the SWIPDG form only     system pattern (hdd_pattern), one part per factor part
+ *   energy       copy of the system matrix                     system pattern (aliases hdd_component_values(HDD_LHS))
+ * all with over_integrate = 2 (:359). */
+int hdd_swipdg_only_these_products(hdd_swipdg* h, const char* const* ids, int n);
+/* available_products() (discretizations/base.hh:272-280), sorted like the std::map. */
+int hdd_products_available(const hdd_swipdg* h, const char* const** ids, int* n);
+/* get_product(id) (base.hh:281-291): HDD_ERR_USING_THIS_WRONG if there are no products, HDD_ERR_WRONG_INPUT for an
+ * unknown id.  volume_pattern: 1 = values follow hdd_pattern_volume, 0 = hdd_pattern.  q = -1 is the affine part. */
+int hdd_product_num_components(hdd_swipdg* h, const char* id, int* n_components, int* has_affine_part, int* volume_pattern);
+int hdd_product_values(hdd_swipdg* h, const char* id, int q, const double** values_dev, int64_t* count);
+int hdd_product_coefficient(hdd_swipdg* h, const char* id, int q, const char** expression);
+int hdd_pattern_volume(hdd_swipdg* h, int64_t* n_rows, int64_t* nnz, const int64_t** rowptr_dev, const int32_t** col_dev);
+/* get_product(id).freeze_parameter(mu).apply2(u, v) = u^T P(mu) v on the device (u, v: owned rows; all ranks call it
+ * collectively and receive the global value).  The induced norm is sqrt(apply2(u, u)). */
+int hdd_product_apply2(hdd_swipdg* h, const char* id, const double* mu, int mu_size, const double* u_host,
+                       const double* v_host, double* result);
+/* Error norms of the convergence studies (test/linearelliptic-swipdg.hh:267-290: Products::L2 / H1Semi / Elliptic induced
+ * norms of the difference) against an analytic solution given as Expression strings in x[0], x[1] for u, du/dx, du/dy;
+ * evaluated on this grid with the element rule exact for `order`; out3 = {L2, H1_semi, energy}, global over all ranks.
+ * u_host = NULL uses the last solution. */
+int hdd_error_norms(hdd_swipdg* h, const double* u_host, const char* exact, const char* exact_dx, const char* exact_dy,
+                    int order, const double* mu, int mu_size, double* out3);
 
 /* ---- BlockSWIPDG views (discretizations/block-swipdg.hh:553-690) --------------------------------------- */
 int hdd_num_subdomains(const hdd_swipdg* h, int* n);

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 SIMPLEX, CUBE = 0, 1
-FN_ONE, FN_CELLWISE, FN_ESV_FORCE, FN_OS_SIN, FN_ESV_EXACT = range(5)
+FN_ONE, FN_CELLWISE, FN_ESV_FORCE, FN_OS_SIN, FN_ESV_EXACT, FN_X, FN_Y, FN_XY = range(8)
 
 
 class OFn(C.Structure):
@@ -94,22 +94,30 @@ def _pf(f):
     return None if f is None else C.byref(f)
 
 
+def n_local(kind, polorder):
+    return (polorder + 1) * (polorder + 2) // 2 if kind == SIMPLEX else (polorder + 1) ** 2
+
+
 class Mesh:
-    def __init__(self, kind, xy, cv, nb):
+    def __init__(self, kind, xy, cv, nb, polorder=1):
         self.kind = kind
+        self.p = polorder
         self.xy = np.ascontiguousarray(xy, dtype=np.float64)
         self.cv = np.ascontiguousarray(cv, dtype=np.int32)
         self.nb = np.ascontiguousarray(nb, dtype=np.int32)
-        self.nl = 3 if kind == SIMPLEX else 4
+        self.nl = n_local(kind, polorder)
         self.nc = self.cv.shape[0]
         self.nv = self.xy.shape[0]
+
+    def with_polorder(self, polorder):
+        return Mesh(self.kind, self.xy, self.cv, self.nb, polorder)
 
     @property
     def n_dofs(self):
         return self.nl * self.nc
 
     def args(self):
-        return (self.kind, self.nc, self.nv, _p(self.xy), _p(self.cv, C.c_int32), _p(self.nb, C.c_int32))
+        return (self.kind, self.p, self.nc, self.nv, _p(self.xy), _p(self.cv, C.c_int32), _p(self.nb, C.c_int32))
 
 
 def mesh_cube(nx, ny, x0, x1, y0, y1):
@@ -148,10 +156,32 @@ def element_rule(kind, order):
 def pattern(mesh):
     n = mesh.n_dofs
     rowptr = np.empty(n + 1, np.int64)
-    lib().or_pattern(mesh.kind, mesh.nc, _p(mesh.nb, C.c_int32), _p(rowptr, C.c_int64), None)
+    lib().or_pattern(mesh.kind, mesh.p, mesh.nc, _p(mesh.nb, C.c_int32), _p(rowptr, C.c_int64), None)
     col = np.empty(rowptr[-1], np.int32)
-    lib().or_pattern(mesh.kind, mesh.nc, _p(mesh.nb, C.c_int32), _p(rowptr, C.c_int64), _p(col, C.c_int32))
+    lib().or_pattern(mesh.kind, mesh.p, mesh.nc, _p(mesh.nb, C.c_int32), _p(rowptr, C.c_int64), _p(col, C.c_int32))
     return rowptr, col
+
+
+def pattern_volume(mesh):
+    """block-diagonal pattern of the volume-only products (l2, h1_semi, elliptic, boundary_l2)"""
+    n = mesh.n_dofs
+    rowptr = np.empty(n + 1, np.int64)
+    col = np.empty(n * mesh.nl, np.int32)
+    lib().or_pattern_volume(mesh.kind, mesh.p, mesh.nc, _p(rowptr, C.c_int64), _p(col, C.c_int32))
+    return rowptr, col
+
+
+PRODUCTS = {"l2": 0, "h1_semi": 1, "elliptic": 2, "boundary_l2": 3, "penalty": 4}
+
+
+def assemble_product(mesh, which, rowptr, col, factor=None, tensor=None, bnd_dirichlet=None):
+    val = np.zeros(col.shape[0])
+    t = None if tensor is None else np.ascontiguousarray(tensor, dtype=np.float64)
+    bd = None if bnd_dirichlet is None else np.ascontiguousarray(bnd_dirichlet, dtype=np.uint8)
+    factor = factor or const(1.0)
+    lib().or_assemble_product(*mesh.args(), PRODUCTS[which], _pf(factor), _p(t), _p(bd, C.c_uint8),
+                              _p(rowptr, C.c_int64), _p(col, C.c_int32), _p(val))
+    return val
 
 
 def assemble_lhs(mesh, factor, tensor, rowptr, col, bnd_dirichlet=None):
@@ -163,10 +193,13 @@ def assemble_lhs(mesh, factor, tensor, rowptr, col, bnd_dirichlet=None):
     return val
 
 
-def assemble_rhs(mesh, force, factor=None, dirichlet=None, tensor=None):
+def assemble_rhs(mesh, force, factor=None, dirichlet=None, tensor=None, neumann=None, bnd_type=None):
+    """bnd_type: uint8 [nc, nf], 1 Dirichlet / 2 Neumann; None = AllDirichlet"""
     b = np.zeros(mesh.n_dofs)
     t = None if tensor is None else np.ascontiguousarray(tensor, dtype=np.float64)
-    lib().or_assemble_rhs(*mesh.args(), _pf(force), _pf(factor), _pf(dirichlet), _p(t), _p(b))
+    bt = None if bnd_type is None else np.ascontiguousarray(bnd_type, dtype=np.uint8)
+    lib().or_assemble_rhs(*mesh.args(), _pf(force), _pf(factor), _pf(dirichlet), _pf(neumann), _p(t),
+                          _p(bt, C.c_uint8), _p(b))
     return b
 
 
@@ -216,7 +249,7 @@ def error_norms(mesh, u, exact, factor=None, tensor=None, order=5):
     out = np.zeros(3)
     t = None if tensor is None else np.ascontiguousarray(tensor, dtype=np.float64)
     u = np.ascontiguousarray(u, dtype=np.float64)
-    lib().or_error_norms(mesh.kind, mesh.nc, mesh.nv, _p(mesh.xy), _p(mesh.cv, C.c_int32), _p(u), _pf(exact),
+    lib().or_error_norms(mesh.kind, mesh.p, mesh.nc, mesh.nv, _p(mesh.xy), _p(mesh.cv, C.c_int32), _p(u), _pf(exact),
                          _pf(factor), _p(t), order, _p(out))
     return {"L2": out[0], "H1_semi": out[1], "energy": out[2]}
 

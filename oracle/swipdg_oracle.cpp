@@ -153,7 +153,10 @@ enum FnKind {
   FN_CELLWISE = 1,   // value[cell]                        (Spe10::Model1 / Indicator, problems/spe10.hh:74-80,154-157)
   FN_ESV_FORCE = 2,  // 1/2 pi^2 cos(pi x/2) cos(pi y/2)   (problems/ESV2007.hh:78; testcases/ESV2007.hh:75-79)
   FN_OS_SIN = 3,     // sin(4 pi (x + y/2))                (problems/OS2014.hh:65-74)
-  FN_ESV_EXACT = 4   // cos(pi x/2) cos(pi y/2)            (testcases/ESV2007.hh:41,65)
+  FN_ESV_EXACT = 4,  // cos(pi x/2) cos(pi y/2)            (testcases/ESV2007.hh:41,65)
+  FN_X = 5,          // x        } monomials: stand-ins for Stuff::Functions::Expression data in the
+  FN_Y = 6,          // y        } parity tests of non-constant Dirichlet / Neumann values
+  FN_XY = 7          // x * y    }
 };
 
 extern "C" struct ofn_t {
@@ -174,6 +177,9 @@ double fn_eval(const ofn_t& f, int cell, double x, double y) {
       case FN_ESV_FORCE: v = 0.5 * kPi * kPi * std::cos(0.5 * kPi * x) * std::cos(0.5 * kPi * y); break;
       case FN_OS_SIN: v = std::sin(4.0 * kPi * (x + 0.5 * y)); break;
       case FN_ESV_EXACT: v = std::cos(0.5 * kPi * x) * std::cos(0.5 * kPi * y); break;
+      case FN_X: v = x; break;
+      case FN_Y: v = y; break;
+      case FN_XY: v = x * y; break;
     }
     s += f.coef[k] * v;
   }
@@ -198,12 +204,19 @@ void fn_exact_grad(const ofn_t& f, double x, double y, double g[2]) {
 // ------------------------------------------------------------------------------------
 enum { SIMPLEX = 0, CUBE = 1 };
 
+constexpr int kMaxLoc = 9;  // Q2
+
+// local DoFs of the nodal Lagrange space of order p: P1 3, Q1 4, P2 6, Q2 9
+int n_local(int kind, int p) { return kind == SIMPLEX ? (p + 1) * (p + 2) / 2 : (p + 1) * (p + 1); }
+
 struct Mesh {
   int kind, nc, nv;
   const double* xy;
   const int32_t* cv;
   const int32_t* nb;
-  int nl() const { return kind == SIMPLEX ? 3 : 4; }
+  int p = 1;
+  int nl() const { return n_local(kind, p); }          // local DoFs
+  int nvc() const { return kind == SIMPLEX ? 3 : 4; }  // vertices per cell
   int nf() const { return kind == SIMPLEX ? 3 : 4; }
 };
 
@@ -211,7 +224,7 @@ const int kFaceVertsSimplex[3][2] = {{0, 1}, {0, 2}, {1, 2}};
 const int kFaceVertsCube[4][2] = {{0, 2}, {1, 3}, {0, 1}, {2, 3}};
 
 struct Cell {
-  int kind, nl;
+  int kind, nl, nvc, p;
   double vx[4], vy[4];
   double j00, j01, j10, j11;  // J = d x / d xi
   double i00, i01, i10, i11;  // J^-1
@@ -223,13 +236,15 @@ Cell load_cell(const Mesh& m, int c) {
   Cell g;
   g.kind = m.kind;
   g.nl = m.nl();
+  g.nvc = m.nvc();
+  g.p = m.p;
   g.cx = g.cy = 0.0;
-  for (int i = 0; i < g.nl; ++i) {
-    const int v = m.cv[c * g.nl + i];
+  for (int i = 0; i < g.nvc; ++i) {
+    const int v = m.cv[c * g.nvc + i];
     g.vx[i] = m.xy[2 * v];
     g.vy[i] = m.xy[2 * v + 1];
-    g.cx += g.vx[i] / g.nl;
-    g.cy += g.vy[i] / g.nl;
+    g.cx += g.vx[i] / g.nvc;
+    g.cy += g.vy[i] / g.nvc;
   }
   g.j00 = g.vx[1] - g.vx[0];
   g.j10 = g.vy[1] - g.vy[0];
@@ -255,18 +270,46 @@ void to_global(const Cell& g, double xi, double eta, double& x, double& y) {
   y = g.vy[0] + g.j10 * xi + g.j11 * eta;
 }
 
-// nodal Lagrange basis, p = 1: P1 on simplices, Q1 (not P1) on cubes.
-void basis(const Cell& g, double xi, double eta, double phi[4], double gx[4], double gy[4]) {
-  double dxi[4], deta[4];
-  if (g.kind == SIMPLEX) {
+// nodal Lagrange basis.  p = 1: P1 on simplices, Q1 (not P1) on cubes, nodes = vertices in Dune
+// reference-element order.  p = 2: P2 / Q2 with the nodes in lexicographic order - (0,0),(1/2,0),(1,0),(0,1/2),
+// (1/2,1/2),(0,1) on the triangle, i + 3 j on the square - which is what the generic Lagrange point sets of the
+// space backend (dune-fem, discretizations/swipdg.hh:67-71) produce; no reference test runs p = 2, so this
+// numbering is unpinned.
+void basis(const Cell& g, double xi, double eta, double phi[kMaxLoc], double gx[kMaxLoc], double gy[kMaxLoc]) {
+  double dxi[kMaxLoc], deta[kMaxLoc];
+  if (g.kind == SIMPLEX && g.p == 1) {
     phi[0] = 1.0 - xi - eta; phi[1] = xi; phi[2] = eta;
     dxi[0] = -1.0; dxi[1] = 1.0; dxi[2] = 0.0;
     deta[0] = -1.0; deta[1] = 0.0; deta[2] = 1.0;
-  } else {
+  } else if (g.kind == SIMPLEX) {
+    const double l0 = 1.0 - xi - eta, l1 = xi, l2 = eta;
+    phi[0] = l0 * (2.0 * l0 - 1.0); phi[1] = 4.0 * l0 * l1; phi[2] = l1 * (2.0 * l1 - 1.0);
+    phi[3] = 4.0 * l0 * l2;         phi[4] = 4.0 * l1 * l2; phi[5] = l2 * (2.0 * l2 - 1.0);
+    dxi[0] = -(4.0 * l0 - 1.0); deta[0] = -(4.0 * l0 - 1.0);
+    dxi[1] = 4.0 * (l0 - l1);   deta[1] = -4.0 * l1;
+    dxi[2] = 4.0 * l1 - 1.0;    deta[2] = 0.0;
+    dxi[3] = -4.0 * l2;         deta[3] = 4.0 * (l0 - l2);
+    dxi[4] = 4.0 * l2;          deta[4] = 4.0 * l1;
+    dxi[5] = 0.0;               deta[5] = 4.0 * l2 - 1.0;
+  } else if (g.p == 1) {
     phi[0] = (1.0 - xi) * (1.0 - eta); phi[1] = xi * (1.0 - eta);
     phi[2] = (1.0 - xi) * eta;         phi[3] = xi * eta;
     dxi[0] = -(1.0 - eta); dxi[1] = (1.0 - eta); dxi[2] = -eta; dxi[3] = eta;
     deta[0] = -(1.0 - xi); deta[1] = -xi; deta[2] = (1.0 - xi); deta[3] = xi;
+  } else {
+    auto lag = [](double t, double l[3], double d[3]) {
+      l[0] = (1.0 - t) * (1.0 - 2.0 * t); l[1] = 4.0 * t * (1.0 - t); l[2] = t * (2.0 * t - 1.0);
+      d[0] = 4.0 * t - 3.0;               d[1] = 4.0 - 8.0 * t;       d[2] = 4.0 * t - 1.0;
+    };
+    double lx[3], dx[3], ly[3], dy[3];
+    lag(xi, lx, dx);
+    lag(eta, ly, dy);
+    for (int j = 0; j < 3; ++j)
+      for (int i = 0; i < 3; ++i) {
+        phi[i + 3 * j] = lx[i] * ly[j];
+        dxi[i + 3 * j] = dx[i] * ly[j];
+        deta[i + 3 * j] = lx[i] * dy[j];
+      }
   }
   for (int i = 0; i < g.nl; ++i) {  // grad = J^-T grad_ref
     gx[i] = g.i00 * dxi[i] + g.i10 * deta[i];
@@ -274,7 +317,7 @@ void basis(const Cell& g, double xi, double eta, double phi[4], double gx[4], do
   }
 }
 
-void basis_at(const Cell& g, double x, double y, double phi[4], double gx[4], double gy[4]) {
+void basis_at(const Cell& g, double x, double y, double phi[kMaxLoc], double gx[kMaxLoc], double gy[kMaxLoc]) {
   double xi, eta;
   to_local(g, x, y, xi, eta);
   basis(g, xi, eta, phi, gx, gy);
@@ -452,8 +495,8 @@ int or_mesh_bisect(int n, double x0, double x1, int bisections, double* xy_out, 
 // couples with all DoFs of T and of each face neighbour; column sets are sorted
 // (Stuff::LA::SparsityPatternDefault; block version sorts explicitly,
 // discretizations/block-swipdg.hh:389).  Two calls: col == NULL fills rowptr only.
-void or_pattern(int kind, int nc, const int32_t* nb, int64_t* rowptr, int32_t* col) {
-  const int nl = kind == SIMPLEX ? 3 : 4, nf = nl;
+void or_pattern(int kind, int polorder, int nc, const int32_t* nb, int64_t* rowptr, int32_t* col) {
+  const int nl = n_local(kind, polorder), nf = kind == SIMPLEX ? 3 : 4;
   rowptr[0] = 0;
   for (int c = 0; c < nc; ++c) {
     int blocks[16];  // >= 5; oversized to keep -Warray-bounds quiet
@@ -482,12 +525,12 @@ void or_pattern(int kind, int nc, const int32_t* nb, int64_t* rowptr, int32_t* c
 // all boundary faces are Dirichlet (testcases/ESV2007.hh:63, OS2014.hh:80, spe10.hh:311;
 // forced in the block case, discretizations/block-swipdg.hh:110,237) unless bnd_dirichlet[c*nf+f]==0.
 // Formulas: SURVEY 8a rows a4 (LocalEvaluation::Elliptic), a5 (SWIPDG::Inner), a6 (SWIPDG::BoundaryLHS).
-void or_assemble_lhs(int kind, int nc, int nv, const double* xy, const int32_t* cv, const int32_t* nb,
+void or_assemble_lhs(int kind, int polorder, int nc, int nv, const double* xy, const int32_t* cv, const int32_t* nb,
                      const ofn_t* factor, const double* tensor, const uint8_t* bnd_dirichlet,
                      const int64_t* rowptr, const int32_t* col, double* val) {
   (void)nv;
-  Mesh m{kind, nc, nv, xy, cv, nb};
-  const int nl = m.nl(), nf = m.nf(), p = 1;
+  Mesh m{kind, nc, nv, xy, cv, nb, polorder};
+  const int nl = m.nl(), nf = m.nf(), p = polorder;
   Csr A{rowptr, col, val};
   const double beta = 1.0;  // default_beta(dimDomain) = 1/(d-1), discretizations/swipdg.hh:168
   const Rule2 vol = kind == SIMPLEX ? triangle_rule(factor->order + 2 * (p - 1)) : square_rule(factor->order + 2 * (p - 1));
@@ -498,7 +541,7 @@ void or_assemble_lhs(int kind, int nc, int nv, const double* xy, const int32_t* 
     tensor_of(tensor, c, K);
     // volume
     for (size_t q = 0; q < vol.w.size(); ++q) {
-      double phi[4], gx[4], gy[4], x, y;
+      double phi[kMaxLoc], gx[kMaxLoc], gy[kMaxLoc], x, y;
       basis(g, vol.x[q], vol.y[q], phi, gx, gy);
       to_global(g, vol.x[q], vol.y[q], x, y);
       const double a = fn_eval(*factor, c, x, y);
@@ -519,12 +562,12 @@ void or_assemble_lhs(int kind, int nc, int nv, const double* xy, const int32_t* 
         const double delta = e.nx * (K[0] * e.nx + K[1] * e.ny) + e.ny * (K[2] * e.nx + K[3] * e.ny);
         for (size_t q = 0; q < fr.w.size(); ++q) {
           const double x = e.ax + fr.x[q] * (e.bx - e.ax), y = e.ay + fr.x[q] * (e.by - e.ay);
-          double phi[4], gx[4], gy[4];
+          double phi[kMaxLoc], gx[kMaxLoc], gy[kMaxLoc];
           basis_at(g, x, y, phi, gx, gy);
           const double a = fn_eval(*factor, c, x, y);
           const double pen = sigma_boundary(p) * delta * a / std::pow(e.h, beta);
           const double w = fr.w[q] * e.h;
-          double flux[4];
+          double flux[kMaxLoc];
           for (int i = 0; i < nl; ++i)
             flux[i] = a * ((K[0] * gx[i] + K[1] * gy[i]) * e.nx + (K[2] * gx[i] + K[3] * gy[i]) * e.ny);
           for (int i = 0; i < nl; ++i)
@@ -541,13 +584,13 @@ void or_assemble_lhs(int kind, int nc, int nv, const double* xy, const int32_t* 
         const double wm = dp / (dp + dm), wp = dm / (dp + dm);
         for (size_t q = 0; q < fr.w.size(); ++q) {
           const double x = e.ax + fr.x[q] * (e.bx - e.ax), y = e.ay + fr.x[q] * (e.by - e.ay);
-          double phm[4], gxm[4], gym[4], php[4], gxp[4], gyp[4];
+          double phm[kMaxLoc], gxm[kMaxLoc], gym[kMaxLoc], php[kMaxLoc], gxp[kMaxLoc], gyp[kMaxLoc];
           basis_at(g, x, y, phm, gxm, gym);
           basis_at(gn, x, y, php, gxp, gyp);
           const double am = fn_eval(*factor, c, x, y), ap = fn_eval(*factor, n, x, y);
           const double pen = sigma_inner(p) * gamma * 0.5 * (am + ap) / std::pow(e.h, beta);
           const double w = fr.w[q] * e.h;
-          double fm[4], fp[4];
+          double fm[kMaxLoc], fp[kMaxLoc];
           for (int i = 0; i < nl; ++i) {
             fm[i] = am * ((K[0] * gxm[i] + K[1] * gym[i]) * e.nx + (K[2] * gxm[i] + K[3] * gym[i]) * e.ny);
             fp[i] = ap * ((Kn[0] * gxp[i] + Kn[1] * gyp[i]) * e.nx + (Kn[2] * gxp[i] + Kn[3] * gyp[i]) * e.ny);
@@ -567,20 +610,22 @@ void or_assemble_lhs(int kind, int nc, int nv, const double* xy, const int32_t* 
   }
 }
 
-// ---- a7/a8: rhs ----------------------------------------------------------------------------
-// Functionals::L2Volume(force) (discretizations/swipdg.hh:253-271) and, if `dirichlet` != NULL,
-// Functionals::DirichletBoundarySWIPDG(factor, tensor, dirichlet) (:273-332).
-void or_assemble_rhs(int kind, int nc, int nv, const double* xy, const int32_t* cv, const int32_t* nb,
-                     const ofn_t* force, const ofn_t* factor, const ofn_t* dirichlet, const double* tensor,
-                     double* b) {
-  Mesh m{kind, nc, nv, xy, cv, nb};
-  const int nl = m.nl(), nf = m.nf(), p = 1;
+// ---- a7/a8/a9: rhs ---------------------------------------------------------------------------
+// Functionals::L2Volume(force) (discretizations/swipdg.hh:253-271), if `dirichlet` != NULL
+// Functionals::DirichletBoundarySWIPDG(factor, tensor, dirichlet) on the Dirichlet faces (:273-332), and if
+// `neumann` != NULL Functionals::L2Face(neumann) on the Neumann faces (:335-356).
+// bnd_type[c*nf+f]: 1 Dirichlet, 2 Neumann (Stuff::Grid::BoundaryInfo); NULL = AllDirichlet.
+void or_assemble_rhs(int kind, int polorder, int nc, int nv, const double* xy, const int32_t* cv, const int32_t* nb,
+                     const ofn_t* force, const ofn_t* factor, const ofn_t* dirichlet, const ofn_t* neumann,
+                     const double* tensor, const uint8_t* bnd_type, double* b) {
+  Mesh m{kind, nc, nv, xy, cv, nb, polorder};
+  const int nl = m.nl(), nf = m.nf(), p = polorder;
   for (int c = 0; c < nc; ++c) {
     const Cell g = load_cell(m, c);
     if (force) {
       const Rule2 vol = kind == SIMPLEX ? triangle_rule(force->order + p) : square_rule(force->order + p);
       for (size_t q = 0; q < vol.w.size(); ++q) {
-        double phi[4], gx[4], gy[4], x, y;
+        double phi[kMaxLoc], gx[kMaxLoc], gy[kMaxLoc], x, y;
         basis(g, vol.x[q], vol.y[q], phi, gx, gy);
         to_global(g, vol.x[q], vol.y[q], x, y);
         const double fv = fn_eval(*force, c, x, y) * vol.w[q] * g.detj;
@@ -593,11 +638,12 @@ void or_assemble_rhs(int kind, int nc, int nv, const double* xy, const int32_t* 
       const Rule1 fr = line_rule(factor->order + dirichlet->order + 2 * p);
       for (int f = 0; f < nf; ++f) {
         if (nb[nf * c + f] >= 0) continue;
+        if (bnd_type && bnd_type[nf * c + f] != 1) continue;
         const Face e = load_face(g, f);
         const double delta = e.nx * (K[0] * e.nx + K[1] * e.ny) + e.ny * (K[2] * e.nx + K[3] * e.ny);
         for (size_t q = 0; q < fr.w.size(); ++q) {
           const double x = e.ax + fr.x[q] * (e.bx - e.ax), y = e.ay + fr.x[q] * (e.by - e.ay);
-          double phi[4], gx[4], gy[4];
+          double phi[kMaxLoc], gx[kMaxLoc], gy[kMaxLoc];
           basis_at(g, x, y, phi, gx, gy);
           const double a = fn_eval(*factor, c, x, y), gd = fn_eval(*dirichlet, c, x, y);
           const double pen = sigma_boundary(p) * delta * a / e.h;
@@ -606,6 +652,127 @@ void or_assemble_rhs(int kind, int nc, int nv, const double* xy, const int32_t* 
             const double flux = a * ((K[0] * gx[i] + K[1] * gy[i]) * e.nx + (K[2] * gx[i] + K[3] * gy[i]) * e.ny);
             b[nl * c + i] += w * (-gd * flux + pen * gd * phi[i]);
           }
+        }
+      }
+    }
+    if (neumann && bnd_type) {
+      const Rule1 fr = line_rule(neumann->order + p);
+      for (int f = 0; f < nf; ++f) {
+        if (nb[nf * c + f] >= 0 || bnd_type[nf * c + f] != 2) continue;
+        const Face e = load_face(g, f);
+        for (size_t q = 0; q < fr.w.size(); ++q) {
+          const double x = e.ax + fr.x[q] * (e.bx - e.ax), y = e.ay + fr.x[q] * (e.by - e.ay);
+          double phi[kMaxLoc], gx[kMaxLoc], gy[kMaxLoc];
+          basis_at(g, x, y, phi, gx, gy);
+          const double gn = fn_eval(*neumann, c, x, y) * fr.w[q] * e.h;
+          for (int i = 0; i < nl; ++i) b[nl * c + i] += gn * phi[i];
+        }
+      }
+    }
+  }
+}
+
+// ---- products (8f rank 1; discretizations/swipdg.hh:359-479, block-swipdg.hh:392-548) ----------------------
+// Pattern of the volume-only products: one dense n_loc x n_loc block per cell (Products::L2Assemblable::pattern =
+// the space's volume pattern).
+void or_pattern_volume(int kind, int polorder, int nc, int64_t* rowptr, int32_t* col) {
+  const int nl = n_local(kind, polorder);
+  rowptr[0] = 0;
+  for (int c = 0; c < nc; ++c)
+    for (int i = 0; i < nl; ++i) {
+      const int64_t row = int64_t(nl) * c + i;
+      rowptr[row + 1] = rowptr[row] + nl;
+      if (col)
+        for (int j = 0; j < nl; ++j) col[rowptr[row] + j] = nl * c + j;
+    }
+}
+
+// which: 0 "l2"          Products::L2Assemblable           int_T phi_i phi_j                  rule 2p + over
+//        1 "h1_semi"     Products::H1SemiAssemblable       int_T grad phi_j . grad phi_i      rule 2(p-1) + over
+//        2 "elliptic"    Products::EllipticAssemblable     int_T a K grad phi_j . grad phi_i  rule order(a) + 2(p-1) + over
+//        3 "boundary_l2" Products::BoundaryL2Assemblable   int_{dT on dOmega} phi_i phi_j     rule 2p + over
+//        4 "penalty"     Products::SwipdgPenaltyAssemblable: the penalty terms of SWIPDG::Inner / BoundaryLHS only,
+//                        sigma gamma {a} / h^beta [phi_i][phi_j] resp. sigma_b delta a / h^beta phi_i phi_j (Dirichlet
+//                        faces), rule order(a) + 2p + over
+// over_integrate = 2 (discretizations/swipdg.hh:359).  The arithmetic lives upstream in dune-gdt and no reference test
+// prints product entries: parity unpinned.  (rowptr, col) must contain the entries touched (volume pattern for 0-3,
+// system pattern for 4).
+void or_assemble_product(int kind, int polorder, int nc, int nv, const double* xy, const int32_t* cv, const int32_t* nb,
+                         int which, const ofn_t* factor, const double* tensor, const uint8_t* bnd_dirichlet,
+                         const int64_t* rowptr, const int32_t* col, double* val) {
+  Mesh m{kind, nc, nv, xy, cv, nb, polorder};
+  const int nl = m.nl(), nf = m.nf(), p = polorder, over = 2;
+  Csr A{rowptr, col, val};
+  const int fo = factor ? factor->order : 0;
+  const int vorder = which == 0 ? 2 * p + over : which == 1 ? 2 * (p - 1) + over : fo + 2 * (p - 1) + over;
+  const Rule2 vol = kind == SIMPLEX ? triangle_rule(vorder) : square_rule(vorder);
+  const Rule1 fr = line_rule(which == 3 ? 2 * p + over : fo + 2 * p + over);
+  for (int c = 0; c < nc; ++c) {
+    const Cell g = load_cell(m, c);
+    double K[4];
+    tensor_of(which == 2 || which == 4 ? tensor : nullptr, c, K);
+    if (which <= 2) {
+      for (size_t q = 0; q < vol.w.size(); ++q) {
+        double phi[kMaxLoc], gx[kMaxLoc], gy[kMaxLoc], x, y;
+        basis(g, vol.x[q], vol.y[q], phi, gx, gy);
+        to_global(g, vol.x[q], vol.y[q], x, y);
+        const double a = which == 2 ? fn_eval(*factor, c, x, y) : 1.0;
+        const double w = vol.w[q] * g.detj;
+        for (int i = 0; i < nl; ++i)
+          for (int j = 0; j < nl; ++j) {
+            double v;
+            if (which == 0) v = phi[i] * phi[j];
+            else v = a * ((K[0] * gx[j] + K[1] * gy[j]) * gx[i] + (K[2] * gx[j] + K[3] * gy[j]) * gy[i]);
+            A.add(int64_t(nl) * c + i, nl * c + j, w * v);
+          }
+      }
+      continue;
+    }
+    for (int f = 0; f < nf; ++f) {
+      const int n = nb[nf * c + f];
+      const Face e = load_face(g, f);
+      if (which == 3) {
+        if (n >= 0) continue;
+        for (size_t q = 0; q < fr.w.size(); ++q) {
+          const double x = e.ax + fr.x[q] * (e.bx - e.ax), y = e.ay + fr.x[q] * (e.by - e.ay);
+          double phi[kMaxLoc], gx[kMaxLoc], gy[kMaxLoc];
+          basis_at(g, x, y, phi, gx, gy);
+          for (int i = 0; i < nl; ++i)
+            for (int j = 0; j < nl; ++j) A.add(int64_t(nl) * c + i, nl * c + j, fr.w[q] * e.h * phi[i] * phi[j]);
+        }
+        continue;
+      }
+      const double dm = e.nx * (K[0] * e.nx + K[1] * e.ny) + e.ny * (K[2] * e.nx + K[3] * e.ny);
+      if (n < 0) {
+        if (bnd_dirichlet && !bnd_dirichlet[nf * c + f]) continue;
+        for (size_t q = 0; q < fr.w.size(); ++q) {
+          const double x = e.ax + fr.x[q] * (e.bx - e.ax), y = e.ay + fr.x[q] * (e.by - e.ay);
+          double phi[kMaxLoc], gx[kMaxLoc], gy[kMaxLoc];
+          basis_at(g, x, y, phi, gx, gy);
+          const double pen = sigma_boundary(p) * dm * fn_eval(*factor, c, x, y) / e.h;
+          for (int i = 0; i < nl; ++i)
+            for (int j = 0; j < nl; ++j) A.add(int64_t(nl) * c + i, nl * c + j, fr.w[q] * e.h * pen * phi[i] * phi[j]);
+        }
+      } else if (c < n) {
+        const Cell gn = load_cell(m, n);
+        double Kn[4];
+        tensor_of(tensor, n, Kn);
+        const double dp = e.nx * (Kn[0] * e.nx + Kn[1] * e.ny) + e.ny * (Kn[2] * e.nx + Kn[3] * e.ny);
+        const double gamma = dp * dm / (dp + dm);
+        for (size_t q = 0; q < fr.w.size(); ++q) {
+          const double x = e.ax + fr.x[q] * (e.bx - e.ax), y = e.ay + fr.x[q] * (e.by - e.ay);
+          double phm[kMaxLoc], php[kMaxLoc], gx[kMaxLoc], gy[kMaxLoc];
+          basis_at(g, x, y, phm, gx, gy);
+          basis_at(gn, x, y, php, gx, gy);
+          const double pen = sigma_inner(p) * gamma * 0.5 * (fn_eval(*factor, c, x, y) + fn_eval(*factor, n, x, y)) / e.h;
+          const double w = fr.w[q] * e.h * pen;
+          for (int i = 0; i < nl; ++i)
+            for (int j = 0; j < nl; ++j) {
+              A.add(int64_t(nl) * c + i, nl * c + j, w * phm[j] * phm[i]);
+              A.add(int64_t(nl) * c + i, nl * n + j, -w * php[j] * phm[i]);
+              A.add(int64_t(nl) * n + i, nl * c + j, -w * phm[j] * php[i]);
+              A.add(int64_t(nl) * n + i, nl * n + j, w * php[j] * php[i]);
+            }
         }
       }
     }
@@ -725,7 +892,7 @@ void or_indicators(int nc, int nv, const double* xy, const int32_t* cv, const in
     tensor_of(tensor, c, K);
     const double tr = K[0] + K[3], dt = K[0] * K[3] - K[1] * K[2];
     const double lam_min = 0.5 * tr - std::sqrt(std::max(0.0, 0.25 * tr * tr - dt));
-    double phi[4], gx[4], gy[4];
+    double phi[kMaxLoc], gx[kMaxLoc], gy[kMaxLoc];
     basis(g, 1.0 / 3.0, 1.0 / 3.0, phi, gx, gy);  // P1 gradients are constant
     double ux = 0, uy = 0, dx = 0, dy = 0;
     for (int i = 0; i < nl; ++i) {
@@ -798,7 +965,7 @@ void or_indicators(int nc, int nv, const double* xy, const int32_t* cv, const in
         const double delta = e.nx * (K[0] * e.nx + K[1] * e.ny) + e.ny * (K[2] * e.nx + K[3] * e.ny);
         for (size_t q = 0; q < q_face.w.size(); ++q) {
           const double x = e.ax + q_face.x[q] * (e.bx - e.ax), y = e.ay + q_face.x[q] * (e.by - e.ay);
-          double ph[4], hx[4], hy[4];
+          double ph[kMaxLoc], hx[kMaxLoc], hy[kMaxLoc];
           basis_at(g, x, y, ph, hx, hy);
           double uv = 0.0;
           for (int i = 0; i < nl; ++i) uv += u[nl * c + i] * ph[i];
@@ -811,7 +978,7 @@ void or_indicators(int nc, int nv, const double* xy, const int32_t* cv, const in
         const Cell gn = load_cell(m, n);
         double Kn[4];
         tensor_of(tensor, n, Kn);
-        double pn[4], nx_[4], ny_[4];
+        double pn[kMaxLoc], nx_[kMaxLoc], ny_[kMaxLoc];
         basis(gn, 1.0 / 3.0, 1.0 / 3.0, pn, nx_, ny_);
         double vx = 0, vy = 0;
         for (int i = 0; i < nl; ++i) { vx += u[nl * n + i] * nx_[i]; vy += u[nl * n + i] * ny_[i]; }
@@ -820,7 +987,7 @@ void or_indicators(int nc, int nv, const double* xy, const int32_t* cv, const in
         const double gamma = dp * dm / (dp + dm), wm = dp / (dp + dm), wp = dm / (dp + dm);
         for (size_t q = 0; q < q_face.w.size(); ++q) {
           const double x = e.ax + q_face.x[q] * (e.bx - e.ax), y = e.ay + q_face.x[q] * (e.by - e.ay);
-          double ph[4], hx[4], hy[4], qh[4];
+          double ph[kMaxLoc], hx[kMaxLoc], hy[kMaxLoc], qh[kMaxLoc];
           basis_at(g, x, y, ph, hx, hy);
           basis_at(gn, x, y, qh, hx, hy);
           double um = 0.0, up = 0.0;
@@ -880,9 +1047,9 @@ void or_indicators(int nc, int nv, const double* xy, const int32_t* cv, const in
 
 // ---- error norms (test/linearelliptic-swipdg.hh:267-290: Products::L2 / H1Semi / Elliptic induced norms)
 // against an analytic solution (FN_ESV_EXACT terms), evaluated on the same grid with a rule of `order`.
-void or_error_norms(int kind, int nc, int nv, const double* xy, const int32_t* cv, const double* u,
+void or_error_norms(int kind, int polorder, int nc, int nv, const double* xy, const int32_t* cv, const double* u,
                     const ofn_t* exact, const ofn_t* factor, const double* tensor, int order, double out[3]) {
-  Mesh m{kind, nc, nv, xy, cv, nullptr};
+  Mesh m{kind, nc, nv, xy, cv, nullptr, polorder};
   const int nl = m.nl();
   const Rule2 r = kind == SIMPLEX ? triangle_rule(order) : square_rule(order);
   double l2 = 0, h1 = 0, en = 0;
@@ -891,7 +1058,7 @@ void or_error_norms(int kind, int nc, int nv, const double* xy, const int32_t* c
     double K[4];
     tensor_of(tensor, c, K);
     for (size_t q = 0; q < r.w.size(); ++q) {
-      double phi[4], gx[4], gy[4], x, y, ge[2];
+      double phi[kMaxLoc], gx[kMaxLoc], gy[kMaxLoc], x, y, ge[2];
       basis(g, r.x[q], r.y[q], phi, gx, gy);
       to_global(g, r.x[q], r.y[q], x, y);
       double uv = 0, ux = 0, uy = 0;

@@ -257,7 +257,7 @@ def test_error_behaviour(gpu):
     with pytest.raises(hdd.discretizations.wrong_parameter_type):
         d.solve(mu=[1.0])
     with pytest.raises(hdd.discretizations.NotImplemented_):
-        hdd.SWIPDG(g, problems.ESV2007(), polorder=2)
+        hdd.SWIPDG(g, problems.ESV2007(), polorder=3)
     bad = problems.ESV2007()
     bad.force = problems.AffinelyDecomposable(problems.Expression("cos(x[0]", 3))
     with pytest.raises(hdd.discretizations.wrong_input_given):
@@ -346,3 +346,191 @@ def test_neumann_faces_and_pure_neumann_fix(gpu):
         u = d.solve({"type": "cg.diagonal", "precision": 1e-13, "max_iter": 50000})
         assert abs(u.mean()) <= 1e-12 * np.abs(u).max()
         assert rel(u, x) <= 1e-7
+
+
+# ---- polOrder 2 (BASELINE config 5: "SWIPDG p1 and p2"): P2 / Q2, GPU vs oracle -----------------------------------
+def _oracle_system_p(g, polorder, factor, force, tensor=None):
+    m = oracle_mesh(g).with_polorder(polorder)
+    rp, col = o.pattern(m)
+    return m, rp, col, o.assemble_lhs(m, factor, tensor, rp, col), o.assemble_rhs(m, force)
+
+
+@pytest.mark.parametrize("kind,n", [("alu", 2), ("alu", 4), ("sgrid", 6), ("sgrid", 1), ("alu", 1)])
+def test_p2_pattern_entries_and_solve(gpu, kind, n):
+    g = _grid(kind, n)
+    d = hdd.SWIPDG(g, problems.ESV2007(), polorder=2)
+    d.init()
+    m, rp, col, A, b = _oracle_system_p(g, 2, o.const(1.0), o.esv2007_force())
+    assert d.num_dofs() == m.n_dofs == g.n_cells * (6 if kind == "alu" else 9)
+    rp_g, col_g = d.pattern()
+    assert np.array_equal(rp_g, rp) and np.array_equal(col_g, col)
+    assert rel(d.system_matrix().affine_part(), A) <= ENTRY_TOL
+    assert rel(d.rhs().affine_part(), b) <= ENTRY_TOL
+    x = np.random.default_rng(0).standard_normal(m.n_dofs)
+    assert rel(d.apply(x), o.spmv(rp, col, A, x)) <= 1e-13
+    u_ref = direct_solve(rp, col, A, b)
+    for typ in ("cg.diagonal", "cg.blockdiagonal", "cg.identity"):
+        u, info = d.solve({"type": typ, "precision": 1e-13, "max_iter": 50000}, return_info=True)
+        assert info["converged"]
+        assert rel(u, u_ref) <= SOL_TOL
+    # device error norms against the oracle's
+    e_ref = o.error_norms(m, u_ref, o.esv2007_exact(), order=8)
+    e = d.error_norms(*problems.ESV2007_EXACT, vector=u_ref, order=8)
+    for key in ("L2", "H1_semi", "energy"):
+        assert abs(e[key] - e_ref[key]) <= SOL_TOL * e_ref[key]
+
+
+def test_p2_parametric_cellwise_and_block_views(gpu):
+    """OS2014 (expression factor, two affine parts) and a cell-wise tensor on p2; block views on a 2x2 partition"""
+    g = grids.simplex(4, partitions=(2, 2))
+    prob = problems.OS2014ParametricESV2007()
+    d = hdd.BlockSWIPDG(g, prob, polorder=2)
+    d.init()
+    m = oracle_mesh(g).with_polorder(2)
+    rp, col = o.pattern(m)
+    M = d.system_matrix()
+    assert M.num_components() == 1 and M.has_affine_part()
+    assert rel(M.affine_part(), o.assemble_lhs(m, o.os2014_affine(), None, rp, col)) <= ENTRY_TOL
+    assert rel(M.component(0), o.assemble_lhs(m, o.os2014_component(), None, rp, col)) <= ENTRY_TOL
+    A = o.assemble_lhs(m, o.os2014_factor(0.3), None, rp, col)
+    assert rel(M.freeze_parameter(0.3), A) <= ENTRY_TOL
+    b = o.assemble_rhs(m, o.esv2007_force())
+    u = d.solve({"type": "cg.blockdiagonal", "precision": 1e-13, "max_iter": 50000}, mu=0.3)
+    assert rel(u, direct_solve(rp, col, A, b)) <= SOL_TOL
+    S = o.to_scipy(rp, col, o.assemble_lhs(m, o.os2014_affine(), None, rp, col))
+    off = d.subdomain_offsets()
+    assert off[-1] == m.n_dofs
+    for ss in range(d.num_subdomains()):
+        B = d.get_local_operator(ss)
+        assert abs(B - S[off[ss]:off[ss + 1], off[ss]:off[ss + 1]]).max() <= ENTRY_TOL * abs(S).max()
+        for nn in d.neighbouring_subdomains(ss):
+            Cb = d.get_coupling_operator(ss, nn)
+            assert abs(Cb - S[off[ss]:off[ss + 1], off[nn]:off[nn + 1]]).max() <= ENTRY_TOL * abs(S).max()
+    # cell-wise tensor on Q2
+    g2 = grids.cube(6)
+    k = np.random.default_rng(3).uniform(0.1, 10.0, g2.n_cells)
+    tensor = np.zeros((g2.n_cells, 4))
+    tensor[:, 0] = tensor[:, 3] = k
+    prob2 = problems.ESV2007()
+    prob2.diffusion_tensor = tensor
+    d2 = hdd.SWIPDG(g2, prob2, polorder=2)
+    d2.init()
+    m2, rp2, col2, A2, b2 = _oracle_system_p(g2, 2, o.const(1.0), o.esv2007_force(), tensor)
+    assert rel(d2.system_matrix().affine_part(), A2) <= ENTRY_TOL
+    with pytest.raises(hdd.discretizations.NotImplemented_):
+        hdd.SWIPDG(grids.simplex(2), problems.ESV2007(), polorder=2).estimate(None, "eta_ESV2007")
+    with pytest.raises(hdd.discretizations.NotImplemented_):
+        hdd.SWIPDG(g2, problems.ESV2007(), polorder=3)
+
+
+# ---- a9: non-zero Neumann data (Functionals::L2Face, discretizations/swipdg.hh:335-356) --------------------------
+@pytest.mark.parametrize("kind,n,polorder", [("alu", 4, 1), ("sgrid", 8, 1), ("alu", 2, 2), ("sgrid", 4, 2)])
+def test_nonzero_neumann_and_dirichlet_data(gpu, kind, n, polorder):
+    g = _grid(kind, n)
+    cen = g.centers()
+    bt = np.ones((g.n_cells, g.n_loc), np.uint8)
+    bt[(cen[:, 0] < 0)[:, None] & (g.cell_neigh < 0)] = 2
+    prob = problems.ESV2007()
+    prob.neumann = problems.AffinelyDecomposable(problems.Expression("0.5+x[0]*x[1]-2*x[1]", 2, "neumann"))
+    prob.dirichlet = problems.AffinelyDecomposable(problems.Expression("1+x[0]*x[1]", 2, "dirichlet"))
+    d = hdd.SWIPDG(g, prob, boundary_info=bt, polorder=polorder)
+    d.init()
+    m = oracle_mesh(g).with_polorder(polorder)
+    rp, col = o.pattern(m)
+    gn = o.fn([(0.5, o.FN_ONE), (1.0, o.FN_XY), (-2.0, o.FN_Y)], 2)
+    gd = o.fn([(1.0, o.FN_ONE), (1.0, o.FN_XY)], 2)
+    b = o.assemble_rhs(m, o.esv2007_force(), o.const(1.0), gd, neumann=gn, bnd_type=bt)
+    assert rel(d.rhs().affine_part(), b) <= ENTRY_TOL
+    b0 = o.assemble_rhs(m, o.esv2007_force(), o.const(1.0), gd, bnd_type=bt)
+    assert np.abs(b - b0).max() > 1e-3  # the Neumann term is really there
+    A = o.assemble_lhs(m, o.const(1.0), None, rp, col, bnd_dirichlet=(bt == 1))
+    u = d.solve({"type": "cg.diagonal", "precision": 1e-13, "max_iter": 50000})
+    assert rel(u, direct_solve(rp, col, A, b)) <= SOL_TOL
+    # parametric Neumann data: one rhs component per part, coefficient string preserved
+    prob.neumann = problems.AffinelyDecomposable(problems.Constant(0.0, "neumann"),
+                                                 [problems.Expression("x[1]", 1, "neumann_0")], ["2*mu"])
+    prob.parameter_name, prob.parameter_size = "mu", 1
+    dp = hdd.SWIPDG(g, prob, boundary_info=bt, polorder=polorder)
+    dp.init()
+    R = dp.rhs()
+    assert R.num_components() == 1 and R.coefficient(0) == "2*mu"
+    comp = o.assemble_rhs(m, None, neumann=o.fn([(1.0, o.FN_Y)], 1), bnd_type=bt)
+    assert rel(R.component(0), comp) <= ENTRY_TOL
+
+
+# ---- 8f rank 1: product matrices ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,n,polorder", [("alu", 4, 1), ("sgrid", 8, 1), ("alu", 2, 2), ("sgrid", 4, 2)])
+def test_products(gpu, kind, n, polorder):
+    g = _grid(kind, n)
+    ids = ["l2", "h1_semi", "elliptic", "boundary_l2", "penalty", "energy", "not_a_product"]
+    d = hdd.SWIPDG(g, problems.OS2014ParametricESV2007(), polorder=polorder, only_these_products=ids)
+    assert d.available_products() == sorted(ids[:-1])
+    d.init()
+    m = oracle_mesh(g).with_polorder(polorder)
+    rp, col = o.pattern(m)
+    rpv, colv = o.pattern_volume(m)
+    rp_g, col_g = d.pattern_volume()
+    assert np.array_equal(rp_g, rpv) and np.array_equal(col_g, colv)
+    rng = np.random.default_rng(5)
+    u, v = rng.standard_normal(m.n_dofs), rng.standard_normal(m.n_dofs)
+    for pid in ("l2", "h1_semi", "boundary_l2"):
+        P = d.get_product(pid)
+        assert P.num_components() == 0 and P.has_affine_part() and P.volume_pattern()
+        ref = o.assemble_product(m, pid, rpv, colv)
+        assert rel(P.affine_part(), ref) <= ENTRY_TOL
+        S = o.to_scipy(rpv, colv, ref)
+        assert abs(P.apply2(u, v) - u @ (S @ v)) <= 1e-12 * np.abs(S).sum()
+    for pid, (r, c) in (("elliptic", (rpv, colv)), ("penalty", (rp, col))):
+        P = d.get_product(pid)
+        assert P.num_components() == 1 and P.has_affine_part() and P.coefficient(0) == d.system_matrix().coefficient(0)
+        assert P.volume_pattern() == (pid == "elliptic")
+        assert rel(P.affine_part(), o.assemble_product(m, pid, r, c, factor=o.os2014_affine())) <= ENTRY_TOL
+        assert rel(P.component(0), o.assemble_product(m, pid, r, c, factor=o.os2014_component())) <= ENTRY_TOL
+        ref = o.assemble_product(m, pid, r, c, factor=o.os2014_factor(0.4))
+        assert rel(P.freeze_parameter(0.4), ref) <= ENTRY_TOL
+        S = o.to_scipy(r, c, ref)
+        assert abs(P.apply2(u, v, mu=0.4) - u @ (S @ v)) <= 1e-12 * np.abs(S).sum()
+        assert abs(P.induced_norm(u, mu=0.4) - np.sqrt(u @ (S @ u))) <= 1e-10 * np.sqrt(u @ (S @ u))
+    E = d.get_product("energy")
+    assert not E.volume_pattern() and E.num_components() == 1
+    assert np.array_equal(E.affine_part(), d.system_matrix().affine_part())
+    with pytest.raises(hdd.discretizations.wrong_input_given):
+        d.get_product("h1")
+    d0 = hdd.SWIPDG(g, problems.ESV2007(), polorder=polorder)
+    d0.init()
+    assert d0.available_products() == []
+    with pytest.raises(hdd.discretizations.you_are_using_this_wrong):
+        d0.get_product("l2")
+    # products requested after init() are assembled at once; l2 norm of the constant 1 is sqrt(|Omega|)
+    d1 = hdd.BlockSWIPDG(_grid(kind, n, (2, 2)), problems.ESV2007(), polorder=polorder)
+    d1.init()
+    L = capi_products(d1, ["l2", "elliptic"])
+    one = np.ones(d1.num_dofs())
+    assert abs(L["l2"].induced_norm(one) - 2.0) <= 1e-12
+    assert abs(L["elliptic"].induced_norm(one)) <= 1e-6
+    M = o.to_scipy(rpv, colv, o.assemble_product(m, "l2", rpv, colv))
+    off = d1.subdomain_offsets()
+    loc = d1.get_local_product(1, "l2")
+    assert loc.shape == (off[2] - off[1],) * 2 and abs(loc.sum() - 1.0) <= 1e-12  # |subdomain| = 1
+
+
+def capi_products(d, ids):
+    import ctypes as C
+    from dune_hdd_b200 import capi
+    arr = (C.c_char_p * len(ids))(*[i.encode() for i in ids])
+    capi.check(capi.lib().hdd_swipdg_only_these_products(d._h, arr, len(ids)))
+    return {i: d.get_product(i) for i in ids}
+
+
+def test_error_norms_on_the_device(gpu):
+    for kind, n in (("alu", 8), ("sgrid", 16)):
+        g = _grid(kind, n)
+        d = hdd.SWIPDG(g, problems.ESV2007())
+        d.init()
+        u = d.solve({"type": "cg.diagonal", "precision": 1e-13, "max_iter": 50000})
+        m = oracle_mesh(g)
+        e_ref = o.error_norms(m, u, o.esv2007_exact(), order=5)
+        for vec in (u, None):  # None: the last solution, resident on the device
+            e = d.error_norms(*problems.ESV2007_EXACT, vector=vec, order=5)
+            for key in ("L2", "H1_semi", "energy"):
+                assert abs(e[key] - e_ref[key]) <= SOL_TOL * e_ref[key]
