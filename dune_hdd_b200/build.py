@@ -7,9 +7,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libhdd_b200.so")
 SOURCES = ["mesh.cu", "swipdg.cu", "products.cu", "kernels_assembly.cu", "kernels_cg.cu", "kernels_estimators.cu",
-           "kernels_products.cu", "expr.cpp",
+           "kernels_products.cu", "multigrid.cu", "expr.cpp",
            "grids.cpp", "partition.cpp"]
-HEADERS = ["common.hpp", "expr.hpp", "quadrature.hpp", "device.cuh", "kernels.hpp", "handles.hpp", "partition.hpp",
+HEADERS = ["common.hpp", "expr.hpp", "quadrature.hpp", "device.cuh", "reduce.cuh", "kernels.hpp", "handles.hpp",
+           "partition.hpp",
            os.path.join("..", "..", "include", "hdd_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",

@@ -73,6 +73,10 @@ struct hdd_mesh {
   hdd::DevBuf<int32_t> vdof;
   int64_t n_blocks = 0;  // blk_start[n_own]
   bool has_btype = false;
+  // logically structured cube grid (vertices x-fastest): cells per direction (0 = not structured / not one GPU), the
+  // vertex 0 of every cell and the map lexicographic cell -> cell; feeds the multigrid preconditioner ("cg.mg")
+  int sx = 0, sy = 0;
+  hdd::DevBuf<int32_t> cell_v0, lex_cell;
   bool purely_neumann = false;  // no Dirichlet face anywhere (DirichletDetector, discretizations/swipdg.hh:219-220,488-489)
 
   // multi GPU
@@ -128,6 +132,8 @@ struct AffineFn {
   bool has_affine() const { return affine.idx >= 0; }
   bool parametric() const { return !comps.empty(); }
 };
+
+struct MgState;  // multigrid.cu
 
 struct RhsTerm {  // one local functional added into a rhs vector
   int kind;       // 0 L2Volume(f), 1 DirichletBoundarySWIPDG(factor f, g), 2 L2Face(f) on the Neumann faces
@@ -200,7 +206,8 @@ struct hdd_swipdg {
   bool p2p_ready = false, p2p_failed = false;
   hdd::PeerView peer_view{};
   std::vector<void*> ipc_opened;
-  int last_precond = 1;  // 0 identity, 1 diagonal, 2 cell-block diagonal
+  int last_precond = 1;  // 0 identity, 1 diagonal, 2 cell-block diagonal, 3 two-level multigrid (cg.mg)
+  hdd::MgState* mg = nullptr;
   hdd::DevBuf<hdd::CgScalars> sc;
   hdd::CgScalars* sc_host = nullptr;  // pinned
   bool have_solution = false;
@@ -223,6 +230,12 @@ namespace hdd {
 void require_init(const hdd_swipdg* h);                                          // assert_everything_is_ready (base.hh:370-377)
 void check_mu(const hdd_swipdg* h, const double* mu, int mu_size, const char* name);  // base.hh:333-334
 double eval_coef(const Program& p, const double* mu, int mu_size);
-void assemble_products(hdd_swipdg* h);  // the product assemblers added to system_assembler (discretizations/swipdg.hh:359-479)
+void assemble_products(hdd_swipdg* h);
+// multigrid.cu ("cg.mg")
+void mg_detect_structure(hdd_mesh* m, const double* xy_host, const double* xy_dev, const int32_t* cv_dev, int64_t n_verts);
+void mg_setup(hdd_swipdg* h, const double* frozen_values);
+void mg_apply(hdd_swipdg* h, const int* done, const double* r, double* z, double* p_init, double* partial, CgScalars* sc);
+void mg_release(MgState* st);
+int mg_num_levels(const hdd_swipdg* h);  // the product assemblers added to system_assembler (discretizations/swipdg.hh:359-479)
 DevCombo make_combo(const hdd_swipdg* h, const AffineFn& f, const double* mu, int mu_size);  // f frozen at mu
 }  // namespace hdd

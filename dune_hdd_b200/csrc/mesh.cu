@@ -254,6 +254,7 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
                                    int32_t(halo_lo.size()), int32_t(halo_hi.size()), d_flag.p, s);
       }
       m->d_cgid.upload(m->cgid.data(), m->cgid.size(), s);
+      mg_detect_structure(m.get(), xy, d_xy.p, d_cv.p, n_verts);
       if (boundary_type) {
         m->has_btype = true;
         m->btype.upload(boundary_type + cell_begin * nf, size_t(n_own) * nf, s);

@@ -1,0 +1,505 @@
+// "cg.mg": CG preconditioned by a two-level method for the SWIPDG matrix on logically structured Q1 grids.
+//
+//   M^-1 r = D_blk^-1 r  +  P V(P^T r)  +  P C V_C(C P^T r)
+//
+// D_blk   the 4 x 4 cell blocks of A (block Jacobi, the DG-level smoother),
+// P       the injection of the conforming Q1 space into the DG space (DG DoF (T, i) = value at vertex i of T); the
+//         auxiliary operator A_c = P^T A P is a 9-point vertex stencil (for continuous functions every inner-face jump
+//         vanishes, what remains is the volume term and the Dirichlet-face terms),
+// V       one geometric multigrid V(1,1)-cycle for A_c on the (nx+1) x (ny+1) vertex grid: damped Jacobi, bilinear
+//         interpolation, full weighting, Galerkin coarse operators, dense inverse on the coarsest grid,
+// C       the checkerboard sign (-1)^(ix+iy).  The reference under-integrates the Q1 volume term with the midpoint rule
+//         (SURVEY 0.4), which makes the element hourglass mode energy-free: A_c has a second family of low-energy modes,
+//         checkerboard x smooth, invisible to standard coarse grids.  The twisted hierarchy V_C built from C A_c C
+//         removes exactly that family (measured: CG iterations 188 -> 42 at 128^2, flat in h).
+//
+// The reference's default solver is BiCGSTAB with an algebraic-multigrid / ILU preconditioner
+// (Stuff::LA::Solver defaults, discretizations/base.hh:314-322); this is the same idea specialised to the
+// structured grids of BASELINE configs 2 and 5.  Everything is additive and symmetric, so CG stays applicable; all
+// reductions are deterministic.  Single GPU only (hdd_solve falls back loudly otherwise).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "handles.hpp"
+#include "reduce.cuh"
+
+namespace hdd {
+
+namespace {
+
+constexpr int kMgThreads = 256;
+constexpr int kMaxCoarse = 400;   // dense coarsest solve up to this many vertices
+constexpr double kOmega = 0.8;    // Jacobi damping on the vertex levels
+
+inline int blocks_for(int64_t n) { return int((n + kMgThreads - 1) / kMgThreads); }
+
+__device__ __forceinline__ void load_neigh4(const int32_t* neigh, int k, int* nb) {
+  const int4 v = __ldg(reinterpret_cast<const int4*>(neigh) + k);
+  nb[0] = v.x; nb[1] = v.y; nb[2] = v.z; nb[3] = v.w;
+}
+
+// ---- structure detection -------------------------------------------------------------------------------------
+// cells: vertices must be (v0, v0+1, v0+nx1, v0+nx1+1); records v0 per cell and the map lexicographic cell -> cell
+__global__ void k_struct_cells(const int32_t* __restrict__ cv, int32_t n_cells, int nx, int ny, int32_t* __restrict__ cell_v0,
+                               int32_t* __restrict__ lex_cell, int32_t* flag) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cells) return;
+  const int4 v = __ldg(reinterpret_cast<const int4*>(cv) + c);
+  const int nx1 = nx + 1;
+  const int cx = v.x % nx1, cy = v.x / nx1;
+  if (v.x < 0 || cx >= nx || cy >= ny || v.y != v.x + 1 || v.z != v.x + nx1 || v.w != v.x + nx1 + 1) {
+    atomicOr(flag, 1);
+    return;
+  }
+  cell_v0[c] = v.x;
+  lex_cell[cx + nx * cy] = c;
+}
+
+// vertices: tensor-product coordinates
+__global__ void k_struct_verts(const double* __restrict__ xy, int32_t n_verts, int nx, int32_t* flag) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n_verts) return;
+  const int nx1 = nx + 1;
+  const double2 p = __ldg(reinterpret_cast<const double2*>(xy) + v);
+  const double2 px = __ldg(reinterpret_cast<const double2*>(xy) + v % nx1);
+  const double2 py = __ldg(reinterpret_cast<const double2*>(xy) + (v / nx1) * nx1);
+  if (p.x != px.x || p.y != py.y) atomicOr(flag, 2);
+}
+
+// ---- level-0 operator: A_c = P^T A P gathered per vertex (no atomics) ------------------------------------------
+// S[e][v], e = (dy+1)*3 + (dx+1): coupling of vertex v = (ix, iy) to vertex (ix+dx, iy+dy).  Entries of P^T A P at
+// index distance 2 cancel analytically (inner-face jumps of continuous functions) and are dropped.
+__global__ void __launch_bounds__(kMgThreads)
+    k_vertex_galerkin(MeshView m, const double* __restrict__ vals, const int32_t* __restrict__ cell_v0,
+                      const int32_t* __restrict__ lex_cell, int nx, int ny, double* __restrict__ S, double* __restrict__ SC) {
+  const int64_t nv = int64_t(nx + 1) * (ny + 1);
+  const int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  const int nx1 = nx + 1;
+  const int ix = int(v % nx1), iy = int(v / nx1);
+  double acc[9];
+#pragma unroll
+  for (int e = 0; e < 9; ++e) acc[e] = 0.0;
+#pragma unroll
+  for (int b = 0; b < 2; ++b)
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int cx = ix - 1 + a, cy = iy - 1 + b;
+      if (cx < 0 || cy < 0 || cx >= nx || cy >= ny) continue;
+      const int c = __ldg(lex_cell + cx + nx * cy);
+      const int i = (1 - a) + 2 * (1 - b);  // local index of v in that cell
+      int nb[4];
+      load_neigh4(m.neigh, c, nb);
+      const int nblk = block_count<4>(nb);
+      const double* row = vals + __ldg(m.blk_start + c) * 16 + int64_t(i) * nblk * 4;
+#pragma unroll
+      for (int t = 0; t < 5; ++t) {
+        const int cell = t == 0 ? c : nb[t - 1];
+        if (cell < 0) continue;
+        const int slot = block_slot<4>(c, nb, cell);
+        const int v0 = __ldg(cell_v0 + cell);
+        const int jx = v0 % nx1 - ix, jy = v0 / nx1 - iy;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int dx = jx + (j & 1), dy = jy + (j >> 1);
+          if (dx < -1 || dx > 1 || dy < -1 || dy > 1) continue;
+          acc[(dy + 1) * 3 + dx + 1] += __ldg(row + slot * 4 + j);
+        }
+      }
+    }
+#pragma unroll
+  for (int e = 0; e < 9; ++e) {
+    S[e * nv + v] = acc[e];
+    SC[e * nv + v] = (e & 1) ? -acc[e] : acc[e];  // e odd <=> |dx| + |dy| odd: C A_c C flips the edge neighbours
+  }
+}
+
+// ---- Galerkin coarse operator with bilinear interpolation: 9-point -> 9-point ---------------------------------
+__global__ void __launch_bounds__(kMgThreads)
+    k_rap(const double* __restrict__ Sf, int nxf, int nyf, double* __restrict__ Sc) {
+  const int nxc = nxf / 2, nyc = nyf / 2;
+  const int64_t nvc = int64_t(nxc + 1) * (nyc + 1), nvf = int64_t(nxf + 1) * (nyf + 1);
+  const int64_t I = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (I >= nvc) return;
+  const int IX = int(I % (nxc + 1)), IY = int(I / (nxc + 1));
+  double acc[9];
+#pragma unroll
+  for (int e = 0; e < 9; ++e) acc[e] = 0.0;
+  for (int dy = -1; dy <= 1; ++dy)
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int fx = 2 * IX + dx, fy = 2 * IY + dy;
+      if (fx < 0 || fy < 0 || fx > nxf || fy > nyf) continue;
+      const double wd = (dx == 0 ? 1.0 : 0.5) * (dy == 0 ? 1.0 : 0.5);
+      const int64_t i = fx + int64_t(nxf + 1) * fy;
+      for (int ey = -1; ey <= 1; ++ey)
+        for (int ex = -1; ex <= 1; ++ex) {
+          const int jx = fx + ex, jy = fy + ey;
+          if (jx < 0 || jy < 0 || jx > nxf || jy > nyf) continue;
+          const double s = wd * __ldg(Sf + ((ey + 1) * 3 + ex + 1) * nvf + i);
+          // coarse vertices J = I + D whose interpolation stencil touches j: |j - 2J| <= 1
+#pragma unroll
+          for (int Dy = -1; Dy <= 1; ++Dy) {
+            const int py = dy + ey - 2 * Dy;
+            if (py < -1 || py > 1 || IY + Dy < 0 || IY + Dy > nyc) continue;
+#pragma unroll
+            for (int Dx = -1; Dx <= 1; ++Dx) {
+              const int px = dx + ex - 2 * Dx;
+              if (px < -1 || px > 1 || IX + Dx < 0 || IX + Dx > nxc) continue;
+              acc[(Dy + 1) * 3 + Dx + 1] += s * (px == 0 ? 1.0 : 0.5) * (py == 0 ? 1.0 : 0.5);
+            }
+          }
+        }
+    }
+#pragma unroll
+  for (int e = 0; e < 9; ++e) Sc[e * nvc + I] = acc[e];
+}
+
+// ---- V-cycle kernels.  done: convergence latch of the CG iteration that owns this application (see k_cg_*) ----------
+// pre-smoothing from a zero guess, x = w D^-1 b, fused with the residual r = b - A x
+__global__ void __launch_bounds__(kMgThreads)
+    k_mg_pre(const int* done, const double* __restrict__ S, int nx, int ny, const double* __restrict__ b,
+             double* __restrict__ x, double* __restrict__ r) {
+  if (done && *done) return;
+  const int nx1 = nx + 1;
+  const int64_t nv = int64_t(nx1) * (ny + 1);
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= nv) return;
+  const int ix = int(i % nx1), iy = int(i / nx1);
+  double ax = 0.0;
+#pragma unroll
+  for (int ey = -1; ey <= 1; ++ey)
+#pragma unroll
+    for (int ex = -1; ex <= 1; ++ex) {
+      const int jx = ix + ex, jy = iy + ey;
+      if (jx < 0 || jy < 0 || jx > nx || jy > ny) continue;
+      const int64_t j = i + ex + int64_t(ey) * nx1;
+      const double xj = kOmega * __ldg(b + j) / __ldg(S + 4 * nv + j);
+      ax = fma(__ldg(S + ((ey + 1) * 3 + ex + 1) * nv + i), xj, ax);
+      if (ex == 0 && ey == 0) x[i] = xj;
+    }
+  r[i] = b[i] - ax;
+}
+
+// full weighting: b_H = P^T r
+__global__ void __launch_bounds__(kMgThreads)
+    k_mg_restrict(const int* done, const double* __restrict__ r, int nxf, int nyf, double* __restrict__ bc) {
+  if (done && *done) return;
+  const int nxc = nxf / 2, nyc = nyf / 2;
+  const int64_t nvc = int64_t(nxc + 1) * (nyc + 1);
+  const int64_t I = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (I >= nvc) return;
+  const int IX = int(I % (nxc + 1)), IY = int(I / (nxc + 1));
+  double s = 0.0;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int fx = 2 * IX + dx, fy = 2 * IY + dy;
+      if (fx < 0 || fy < 0 || fx > nxf || fy > nyf) continue;
+      s = fma((dx == 0 ? 1.0 : 0.5) * (dy == 0 ? 1.0 : 0.5), __ldg(r + fx + int64_t(nxf + 1) * fy), s);
+    }
+  bc[I] = s;
+}
+
+// x += P x_H (bilinear interpolation)
+__global__ void __launch_bounds__(kMgThreads)
+    k_mg_prolong_add(const int* done, const double* __restrict__ xc, int nxf, int nyf, double* __restrict__ x) {
+  if (done && *done) return;
+  const int nxc = nxf / 2;
+  const int64_t nvf = int64_t(nxf + 1) * (nyf + 1);
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= nvf) return;
+  const int fx = int(i % (nxf + 1)), fy = int(i / (nxf + 1));
+  const int cx = fx >> 1, cy = fy >> 1;
+  const int ox = fx & 1, oy = fy & 1;
+  const int64_t I = cx + int64_t(nxc + 1) * cy;
+  double v = __ldg(xc + I);
+  if (ox) v += __ldg(xc + I + 1);
+  if (oy) {
+    v += __ldg(xc + I + nxc + 1);
+    if (ox) v += __ldg(xc + I + nxc + 2);
+  }
+  x[i] += v * (ox ? 0.5 : 1.0) * (oy ? 0.5 : 1.0);
+}
+
+// post-smoothing: y = x + w D^-1 (b - A x)
+__global__ void __launch_bounds__(kMgThreads)
+    k_mg_post(const int* done, const double* __restrict__ S, int nx, int ny, const double* __restrict__ b,
+              const double* __restrict__ x, double* __restrict__ y) {
+  if (done && *done) return;
+  const int nx1 = nx + 1;
+  const int64_t nv = int64_t(nx1) * (ny + 1);
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= nv) return;
+  const int ix = int(i % nx1), iy = int(i / nx1);
+  double ax = 0.0;
+#pragma unroll
+  for (int ey = -1; ey <= 1; ++ey)
+#pragma unroll
+    for (int ex = -1; ex <= 1; ++ex) {
+      const int jx = ix + ex, jy = iy + ey;
+      if (jx < 0 || jy < 0 || jx > nx || jy > ny) continue;
+      ax = fma(__ldg(S + ((ey + 1) * 3 + ex + 1) * nv + i), __ldg(x + i + ex + int64_t(ey) * nx1), ax);
+    }
+  y[i] = x[i] + kOmega * (b[i] - ax) / __ldg(S + 4 * nv + i);
+}
+
+// coarsest grid: x = A^-1 b with the dense inverse, one thread per row
+__global__ void k_mg_dense(const int* done, const double* __restrict__ Ainv, int n, const double* __restrict__ b,
+                           double* __restrict__ x) {
+  if (done && *done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int j = 0; j < n; ++j) s = fma(__ldg(Ainv + size_t(i) * n + j), __ldg(b + j), s);
+  x[i] = s;
+}
+
+// ---- DG level ---------------------------------------------------------------------------------------------------
+// rc = P^T r (sum of the DG residual entries sitting on each vertex) and its checkerboard-signed copy
+__global__ void __launch_bounds__(kMgThreads)
+    k_dg_restrict(const int* done, const double* __restrict__ r, const int32_t* __restrict__ lex_cell, int nx, int ny,
+                  double* __restrict__ b0, double* __restrict__ b1) {
+  if (done && *done) return;
+  const int nx1 = nx + 1;
+  const int64_t nv = int64_t(nx1) * (ny + 1);
+  const int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  const int ix = int(v % nx1), iy = int(v / nx1);
+  double s = 0.0;
+#pragma unroll
+  for (int b = 0; b < 2; ++b)
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int cx = ix - 1 + a, cy = iy - 1 + b;
+      if (cx < 0 || cy < 0 || cx >= nx || cy >= ny) continue;
+      const int c = __ldg(lex_cell + cx + nx * cy);
+      s += __ldg(r + size_t(4) * c + (1 - a) + 2 * (1 - b));
+    }
+  b0[v] = s;
+  b1[v] = ((ix + iy) & 1) ? -s : s;
+}
+
+// z += P (x0 + C x1), r.z recomputed; optionally p = z (first direction).  One thread per cell, 256-bit accesses.
+__global__ void __launch_bounds__(kMgThreads)
+    k_dg_prolong_dot(const int* done, int32_t n_cells, const int32_t* __restrict__ cell_v0, int nx,
+                     const double* __restrict__ x0, const double* __restrict__ x1, const double* __restrict__ r,
+                     double* __restrict__ z, double* __restrict__ p_init, double* partial, CgScalars* sc) {
+  if (done && *done) return;
+  const int nx1 = nx + 1;
+  double v[1] = {0.0};
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; c < n_cells; c += stride) {
+    const int v0 = __ldg(cell_v0 + c);
+    const double sg = ((v0 % nx1 + v0 / nx1) & 1) ? -1.0 : 1.0;  // parity of vertex 0; vertices 1, 2 flip, 3 agrees
+    const double4 zz = *reinterpret_cast<const double4*>(z + 4 * c);
+    const double4 rr = *reinterpret_cast<const double4*>(r + 4 * c);
+    double4 o;
+    o.x = zz.x + __ldg(x0 + v0) + sg * __ldg(x1 + v0);
+    o.y = zz.y + __ldg(x0 + v0 + 1) - sg * __ldg(x1 + v0 + 1);
+    o.z = zz.z + __ldg(x0 + v0 + nx1) - sg * __ldg(x1 + v0 + nx1);
+    o.w = zz.w + __ldg(x0 + v0 + nx1 + 1) + sg * __ldg(x1 + v0 + nx1 + 1);
+    *reinterpret_cast<double4*>(z + 4 * c) = o;
+    if (p_init) *reinterpret_cast<double4*>(p_init + 4 * c) = o;
+    v[0] = fma(rr.x, o.x, fma(rr.y, o.y, fma(rr.z, o.z, fma(rr.w, o.w, v[0]))));
+  }
+  grid_sum<1>(v, partial, &sc->ticket_a, [sc](const double(&w)[1]) { sc->red[1] = w[0]; });
+}
+
+}  // namespace
+
+// ---- host side ------------------------------------------------------------------------------------------------
+struct MgLevel {
+  int nx = 0, ny = 0;
+  int64_t nv = 0;
+  DevBuf<double> S, b, x, r, y;
+};
+
+struct MgHierarchy {
+  std::vector<std::unique_ptr<MgLevel>> levels;
+  DevBuf<double> coarse_inv;
+};
+
+struct MgState {
+  MgHierarchy h[2];  // plain and checkerboard-twisted
+  int nx = 0, ny = 0;
+};
+
+void mg_detect_structure(hdd_mesh* m, const double* xy_host, const double* xy_dev, const int32_t* cv_dev, int64_t n_verts) {
+  m->sx = m->sy = 0;
+  if (m->kind != HDD_CUBE2D || m->n_own != m->n_global || m->n_loc != m->n_own) return;
+  int64_t nx1 = 1;
+  while (nx1 < n_verts && xy_host[2 * nx1 + 1] == xy_host[1]) ++nx1;
+  if (nx1 < 2 || n_verts % nx1 != 0) return;
+  const int64_t nx = nx1 - 1, ny = n_verts / nx1 - 1;
+  if (ny < 1 || nx * ny != m->n_global) return;
+  cudaStream_t s = m->stream;
+  m->cell_v0.alloc(size_t(m->n_own));
+  m->lex_cell.alloc(size_t(m->n_own));
+  DevBuf<int32_t> flag;
+  flag.alloc(1);
+  flag.zero(s);
+  k_struct_cells<<<blocks_for(m->n_own), kMgThreads, 0, s>>>(cv_dev, m->n_own, int(nx), int(ny), m->cell_v0.p, m->lex_cell.p, flag.p);
+  k_struct_verts<<<blocks_for(n_verts), kMgThreads, 0, s>>>(xy_dev, int32_t(n_verts), int(nx), flag.p);
+  count_launch(2);
+  int32_t f = 0;
+  HDD_CUDA(cudaMemcpyAsync(&f, flag.p, sizeof(f), cudaMemcpyDeviceToHost, s));
+  HDD_CUDA(cudaStreamSynchronize(s));
+  if (f != 0) {
+    m->cell_v0.release();
+    m->lex_cell.release();
+    return;
+  }
+  m->sx = int(nx);
+  m->sy = int(ny);
+}
+
+static void build_hierarchy(hdd_swipdg* h, MgHierarchy& H, std::unique_ptr<MgLevel> fine) {
+  cudaStream_t s = h->mesh->stream;
+  H.levels.clear();
+  H.levels.push_back(std::move(fine));
+  for (;;) {
+    MgLevel& f = *H.levels.back();
+    if (f.nv <= kMaxCoarse || (f.nx & 1) || (f.ny & 1) || f.nx < 2 || f.ny < 2) break;
+    std::unique_ptr<MgLevel> c(new MgLevel);
+    c->nx = f.nx / 2;
+    c->ny = f.ny / 2;
+    c->nv = int64_t(c->nx + 1) * (c->ny + 1);
+    c->S.alloc(size_t(9) * c->nv);
+    k_rap<<<blocks_for(c->nv), kMgThreads, 0, s>>>(f.S.p, f.nx, f.ny, c->S.p);
+    count_launch();
+    H.levels.push_back(std::move(c));
+  }
+  for (auto& L : H.levels) {
+    if (!L->b.p) L->b.alloc(size_t(L->nv));
+    L->x.alloc(size_t(L->nv));
+    L->r.alloc(size_t(L->nv));
+    L->y.alloc(size_t(L->nv));
+  }
+  // dense inverse of the coarsest operator (s.p.d.), Gauss-Jordan on the host
+  MgLevel& C = *H.levels.back();
+  if (C.nv > kMaxCoarse)
+    HDD_THROW(HDD_ERR_REQUIREMENTS_NOT_MET, "cg.mg: the " << H.levels.front()->nx << " x " << H.levels.front()->ny
+                                                           << " grid cannot be coarsened by halving down to at most "
+                                                           << kMaxCoarse << " vertices (stuck at " << C.nx << " x " << C.ny << ")");
+  const int n = int(C.nv);
+  std::vector<double> S(size_t(9) * n);
+  HDD_CUDA(cudaMemcpyAsync(S.data(), C.S.p, S.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+  HDD_CUDA(cudaStreamSynchronize(s));
+  std::vector<double> A(size_t(n) * n, 0.0), I(size_t(n) * n, 0.0);
+  const int nx1 = C.nx + 1;
+  for (int i = 0; i < n; ++i) {
+    const int ix = i % nx1, iy = i / nx1;
+    for (int ey = -1; ey <= 1; ++ey)
+      for (int ex = -1; ex <= 1; ++ex) {
+        const int jx = ix + ex, jy = iy + ey;
+        if (jx < 0 || jy < 0 || jx > C.nx || jy > C.ny) continue;
+        A[size_t(i) * n + (jx + nx1 * jy)] = S[size_t((ey + 1) * 3 + ex + 1) * n + i];
+      }
+    I[size_t(i) * n + i] = 1.0;
+  }
+  for (int c = 0; c < n; ++c) {
+    const double piv = A[size_t(c) * n + c];
+    if (!(piv > 0.0)) HDD_THROW(HDD_ERR_REQUIREMENTS_NOT_MET, "cg.mg: the coarsest operator is not positive definite");
+    const double ip = 1.0 / piv;
+    for (int j = 0; j < n; ++j) { A[size_t(c) * n + j] *= ip; I[size_t(c) * n + j] *= ip; }
+    for (int i = 0; i < n; ++i) {
+      if (i == c) continue;
+      const double f = A[size_t(i) * n + c];
+      if (f == 0.0) continue;
+      for (int j = 0; j < n; ++j) { A[size_t(i) * n + j] -= f * A[size_t(c) * n + j]; I[size_t(i) * n + j] -= f * I[size_t(c) * n + j]; }
+    }
+  }
+  H.coarse_inv.upload(I.data(), I.size(), s);
+  HDD_CUDA(cudaStreamSynchronize(s));
+}
+
+static void vcycle(MgHierarchy& H, const int* done, cudaStream_t s) {
+  const int nl = int(H.levels.size());
+  for (int l = 0; l + 1 < nl; ++l) {
+    MgLevel& L = *H.levels[size_t(l)];
+    MgLevel& Cn = *H.levels[size_t(l) + 1];
+    k_mg_pre<<<blocks_for(L.nv), kMgThreads, 0, s>>>(done, L.S.p, L.nx, L.ny, L.b.p, L.x.p, L.r.p);
+    k_mg_restrict<<<blocks_for(Cn.nv), kMgThreads, 0, s>>>(done, L.r.p, L.nx, L.ny, Cn.b.p);
+    count_launch(2);
+  }
+  MgLevel& C = *H.levels.back();
+  k_mg_dense<<<(int(C.nv) + 127) / 128, 128, 0, s>>>(done, H.coarse_inv.p, int(C.nv), C.b.p, C.x.p);
+  count_launch();
+  for (int l = nl - 2; l >= 0; --l) {
+    MgLevel& L = *H.levels[size_t(l)];
+    MgLevel& Cn = *H.levels[size_t(l) + 1];
+    k_mg_prolong_add<<<blocks_for(L.nv), kMgThreads, 0, s>>>(done, Cn.x.p, L.nx, L.ny, L.x.p);
+    k_mg_post<<<blocks_for(L.nv), kMgThreads, 0, s>>>(done, L.S.p, L.nx, L.ny, L.b.p, L.x.p, L.y.p);
+    count_launch(2);
+    std::swap(L.x.p, L.y.p);  // the smoothed iterate is the level's x from here on
+  }
+}
+
+void mg_release(MgState* st) { delete st; }
+
+// (re)builds both hierarchies for the frozen operator `vals`
+void mg_setup(hdd_swipdg* h, const double* vals) {
+  hdd_mesh* m = h->mesh;
+  if (m->sx == 0 || h->polorder != 1)
+    HDD_THROW(HDD_ERR_REQUIREMENTS_NOT_MET,
+              "solver type 'cg.mg' needs polOrder 1 on a logically structured HDD_CUBE2D grid owned by one GPU (vertices numbered "
+              "x-fastest as by Stuff::Grid::Providers::Cube / hdd_grid_cube); use 'cg.diagonal' or 'cg.blockdiagonal'");
+  cudaStream_t s = m->stream;
+  if (!h->mg) h->mg = new MgState;
+  MgState& st = *h->mg;
+  st.nx = m->sx;
+  st.ny = m->sy;
+  const int64_t nv = int64_t(m->sx + 1) * (m->sy + 1);
+  std::unique_ptr<MgLevel> f0(new MgLevel), f1(new MgLevel);
+  for (MgLevel* L : {f0.get(), f1.get()}) {
+    L->nx = m->sx;
+    L->ny = m->sy;
+    L->nv = nv;
+  }
+  // reuse the level-0 storage of a previous solve
+  if (!st.h[0].levels.empty() && st.h[0].levels[0]->nv == nv) {
+    f0->S = std::move(st.h[0].levels[0]->S);
+    f1->S = std::move(st.h[1].levels[0]->S);
+    f0->b = std::move(st.h[0].levels[0]->b);
+    f1->b = std::move(st.h[1].levels[0]->b);
+  } else {
+    f0->S.alloc(size_t(9) * nv);
+    f1->S.alloc(size_t(9) * nv);
+  }
+  k_vertex_galerkin<<<blocks_for(nv), kMgThreads, 0, s>>>(h->view(), vals, m->cell_v0.p, m->lex_cell.p, m->sx, m->sy, f0->S.p, f1->S.p);
+  count_launch();
+  HDD_CUDA(cudaGetLastError());
+  build_hierarchy(h, st.h[0], std::move(f0));
+  build_hierarchy(h, st.h[1], std::move(f1));
+  HDD_CUDA(cudaGetLastError());
+}
+
+// z += P V(P^T r) + P C V_C(C P^T r), red[1] = r.z; p_init != nullptr also stores z as the first direction
+void mg_apply(hdd_swipdg* h, const int* done, const double* r, double* z, double* p_init, double* partial, CgScalars* sc) {
+  hdd_mesh* m = h->mesh;
+  MgState& st = *h->mg;
+  cudaStream_t s = m->stream;
+  MgLevel& a = *st.h[0].levels[0];
+  MgLevel& b = *st.h[1].levels[0];
+  k_dg_restrict<<<blocks_for(a.nv), kMgThreads, 0, s>>>(done, r, m->lex_cell.p, st.nx, st.ny, a.b.p, b.b.p);
+  count_launch();
+  if (st.h[0].levels.size() == 1) {
+    // the fine vertex grid is already small enough for the dense solve
+    k_mg_dense<<<(int(a.nv) + 127) / 128, 128, 0, s>>>(done, st.h[0].coarse_inv.p, int(a.nv), a.b.p, a.x.p);
+    k_mg_dense<<<(int(b.nv) + 127) / 128, 128, 0, s>>>(done, st.h[1].coarse_inv.p, int(b.nv), b.b.p, b.x.p);
+    count_launch(2);
+  } else {
+    vcycle(st.h[0], done, s);
+    vcycle(st.h[1], done, s);
+  }
+  const int grid = int(std::min<int64_t>((m->n_own + kMgThreads - 1) / kMgThreads, kMaxBlocks));
+  k_dg_prolong_dot<<<grid, kMgThreads, 0, s>>>(done, m->n_own, m->cell_v0.p, st.nx, a.x.p, b.x.p, r, z, p_init, partial, sc);
+  count_launch();
+  HDD_CUDA(cudaGetLastError());
+}
+
+int mg_num_levels(const hdd_swipdg* h) { return h->mg ? int(h->mg->h[0].levels.size()) : 0; }
+
+}  // namespace hdd

@@ -14,6 +14,7 @@ using namespace hdd;
 hdd_swipdg::~hdd_swipdg() {
   for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
   if (sc_host) cudaFreeHost(sc_host);
+  if (mg) hdd::mg_release(mg);
 }
 
 namespace hdd {
@@ -305,6 +306,7 @@ int parse_solver_type(const char* type) {
     return 1;
   if (t == "cg.identity" || t == "cg.identity.lower" || t == "cg.identity.upper") return 0;
   if (t == "cg.blockdiagonal" || t == "cg.blockjacobi") return 2;
+  if (t == "cg.mg" || t == "cg.multigrid") return 3;
   HDD_THROW(HDD_ERR_WRONG_INPUT, "solver type '" << t << "' is not one of solver_types()");
 }
 
@@ -417,7 +419,7 @@ double total(const std::vector<double>& v) {
 const char* const kEstimatorTypes[] = {"eta_NC_ESV2007", "eta_R_ESV2007",  "eta_R_ESV2007_*", "eta_DF_ESV2007", "eta_ESV2007",
                                        "eta_ESV2007_alt", "eta_NC_OS2014", "eta_R_OS2014",    "eta_R_OS2014_*", "eta_DF_OS2014",
                                        "eta_DF_OS2014_*", "eta_OS2014",    "eta_OS2014_*"};
-const char* const kSolverTypes[] = {"cg.diagonal", "cg.blockdiagonal", "cg.identity"};
+const char* const kSolverTypes[] = {"cg.diagonal", "cg.blockdiagonal", "cg.identity", "cg.mg"};
 
 }  // namespace
 
@@ -699,7 +701,7 @@ int hdd_apply(hdd_swipdg* h, const double* mu, int mu_size, const double* x_host
 int hdd_solver_types(const char* const** types, int* n_types) {
   return guarded([&] {
     if (types) *types = kSolverTypes;
-    if (n_types) *n_types = 3;
+    if (n_types) *n_types = 4;
   });
 }
 
@@ -734,7 +736,9 @@ int hdd_solve(hdd_swipdg* h, const char* type, double precision, int max_iter, c
     c.values = vals;
     c.dinv = h->dinv.p;
     h->last_precond = use_diag;
-    if (use_diag == 2) {
+    if (use_diag == 3 && m->world > 1)
+      HDD_THROW(HDD_ERR_NOT_IMPLEMENTED, "solver type 'cg.mg' on more than one GPU");
+    if (use_diag >= 2) {
       if (!h->dinv_block.p) {
         h->dinv_block.alloc(size_t(m->n_own) * h->nl * h->nl);
         h->z.alloc(size_t(h->n_rows));
@@ -742,6 +746,7 @@ int hdd_solve(hdd_swipdg* h, const char* type, double precision, int max_iter, c
       launch_invert_diag_blocks(v, vals, h->dinv_block.p, s);
       c.dinv_block = h->dinv_block.p;
       c.z = h->z.p;
+      if (use_diag == 3) mg_setup(h, vals);
     } else {
       launch_extract_dinv(v, vals, use_diag, h->dinv.p, s);
     }
@@ -755,7 +760,7 @@ int hdd_solve(hdd_swipdg* h, const char* type, double precision, int max_iter, c
     Nccl& nc = Nccl::get();
     const bool multi = m->world > 1;
     // multi GPU, Q1, Jacobi / identity: fused SpMV + halo read over peer memory instead of pack + send/recv
-    bool p2p = multi && p2p_wanted() && use_diag != 2 && cg_spmv_uses_tma(v);
+    bool p2p = multi && p2p_wanted() && use_diag < 2 && cg_spmv_uses_tma(v);
     if (multi) {  // the decision must be collective: a rank without owned cells large enough would disagree
       DevBuf<double> vote;
       double want = p2p ? 0.0 : 1.0;
@@ -776,15 +781,17 @@ int hdd_solve(hdd_swipdg* h, const char* type, double precision, int max_iter, c
       peer = &h->peer_view;
     }
     launch_cg_init(v, c, precision, max_iter, s);
+    if (use_diag == 3) mg_apply(h, nullptr, c.r, c.z, c.p + size_t(m->own0) * h->nl, c.partial, c.sc);
     if (multi) nc.all_reduce_sum(&c.sc->red[1], 2, m->comm, s);
     launch_cg_init_finish(v, c, s);
-    int par = 0, launched = 0, batch = 16;
+    int par = 0, launched = 0, batch = use_diag == 3 ? 8 : 16;
     for (;;) {
       for (int k = 0; k < batch; ++k) {
         if (multi && !p2p) m->halo_exchange(c.p, h->nl);
         launch_cg_spmv(v, c, par, s, peer);
         if (multi) nc.all_reduce_sum(&c.sc->red[0], 1, m->comm, s);
         launch_cg_update(v, c, par, s);
+        if (use_diag == 3) mg_apply(h, &c.sc->done[par], c.r, c.z, nullptr, c.partial, c.sc);
         if (multi) nc.all_reduce_sum(&c.sc->red[1], 2, m->comm, s);
         launch_cg_direction(v, c, par, s);
         par ^= 1;
@@ -794,7 +801,7 @@ int hdd_solve(hdd_swipdg* h, const char* type, double precision, int max_iter, c
       HDD_CUDA(cudaStreamSynchronize(s));
       if (h->sc_host->done[par]) break;
       if (launched > max_iter + batch) break;  // cannot happen: done latches at max_it
-      if (batch < 256) batch *= 2;
+      if (batch < 256 && use_diag != 3) batch *= 2;
     }
     if (m->purely_neumann) launch_subtract_mean(h->x.p, h->n_rows, h->partial.p, h->sc.p, s);
     HDD_CUDA(cudaEventRecord(e1, s));
@@ -1092,10 +1099,10 @@ int hdd_kernel_bytes(hdd_swipdg* h, int which, double* bytes) {
     switch (which) {
       case 0: b = 8.0 * nnz + rec * cells + 8.0 * rows /* read p */ + 8.0 * rows /* write q */; break;
       case 1:  // diagonal: read x,p,q,r,dinv, write x,r; block: read x,p,q,r + n_loc^2 block per cell, write x,r,z
-        b = h->last_precond == 2 ? 7.0 * 8.0 * rows + 8.0 * nl * rows : 7.0 * 8.0 * rows;
+        b = h->last_precond >= 2 ? 7.0 * 8.0 * rows + 8.0 * nl * rows : 7.0 * 8.0 * rows;
         break;
       case 2:  // diagonal: read r,dinv,p, write p; block: read z,p, write p
-        b = h->last_precond == 2 ? 3.0 * 8.0 * rows : 4.0 * 8.0 * rows;
+        b = h->last_precond >= 2 ? 3.0 * 8.0 * rows : 4.0 * 8.0 * rows;
         break;
       case 3: b = 8.0 * nnz + (geo + rec) * cells; break;
       default: HDD_THROW(HDD_ERR_WRONG_INPUT, "unknown kernel id " << which);
@@ -1117,7 +1124,7 @@ int hdd_profile_kernel(hdd_swipdg* h, int which, int reps, double* avg_seconds) 
     c.values = h->lhs_comps.empty() ? h->lhs_affine->values.p : h->frozen.p;
     c.dinv = h->dinv.p; c.b = h->b.p; c.x = h->x.p; c.r = h->r.p; c.p = h->p.p; c.q = h->q.p;
     c.partial = h->partial.p; c.sc = h->sc.p;
-    if (h->last_precond == 2) { c.dinv_block = h->dinv_block.p; c.z = h->z.p; }
+    if (h->last_precond >= 2) { c.dinv_block = h->dinv_block.p; c.z = h->z.p; }
     if (which != 3) {
       // un-latch the convergence flag of parity 0 so that the kernels do their work; the vectors are scratch now
       CgScalars sc = *h->sc_host;

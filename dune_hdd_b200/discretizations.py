@@ -311,7 +311,7 @@ class SWIPDG:
 
     def solver_options(self, type=""):
         type = type or self.solver_types()[0]
-        if type.split(".lower")[0].split(".upper")[0] not in ("cg", "cg.jacobi", "cg.diagonal", "cg.identity"):
+        if type.split(".lower")[0].split(".upper")[0] not in ["cg", "cg.jacobi", "cg.blockjacobi"] + self.solver_types():
             raise wrong_input_given(capi.HDD_ERR_WRONG_INPUT, "solver type '%s' is not one of solver_types()" % type)
         return {"type": type, "precision": 1e-10, "max_iter": 100000}
 

@@ -534,3 +534,53 @@ def test_error_norms_on_the_device(gpu):
             e = d.error_norms(*problems.ESV2007_EXACT, vector=vec, order=5)
             for key in ("L2", "H1_semi", "energy"):
                 assert abs(e[key] - e_ref[key]) <= SOL_TOL * e_ref[key]
+
+
+# ---- "cg.mg": two-level multigrid preconditioner on structured Q1 grids ---------------------------------------------
+@pytest.mark.parametrize("n,parts", [(8, (1, 1)), (16, (2, 2)), (32, (1, 1)), (48, (4, 4)), (3, (1, 1))])
+def test_cg_mg_matches_direct_solve(gpu, n, parts):
+    g = grids.cube(n, partitions=parts)  # the partitioned grids have subdomain-major cell numbering
+    d = hdd.SWIPDG(g, problems.ESV2007())
+    d.init()
+    assert "cg.mg" in d.solver_types()
+    m, rp, col, A, b = oracle_system(g, o.const(1.0), o.esv2007_force())
+    u_ref = direct_solve(rp, col, A, b)
+    u, info = d.solve({"type": "cg.mg", "precision": 1e-13, "max_iter": 500}, return_info=True)
+    assert info["converged"] and rel(u, u_ref) <= SOL_TOL
+    _, ij = d.solve({"type": "cg.diagonal", "precision": 1e-13, "max_iter": 50000}, return_info=True)
+    assert info["iterations"] <= 70 and (n < 16 or info["iterations"] < ij["iterations"] / 2)
+
+
+def test_cg_mg_spe10_shape_parametric_and_requirements(gpu):
+    g = grids.cube(100, 20, (0.0, 0.0), (5.0, 1.0))
+    prob = problems.Spe10Model1(g)
+    d = hdd.SWIPDG(g, prob)
+    d.init()
+    m = oracle_mesh(g)
+    rp, col = o.pattern(m)
+    A = o.assemble_lhs(m, o.const(1.0), prob.diffusion_tensor, rp, col)
+    b = d.rhs().affine_part()
+    u, info = d.solve({"type": "cg.mg", "precision": 1e-12, "max_iter": 2000}, return_info=True)
+    assert info["converged"]
+    assert np.linalg.norm(o.spmv(rp, col, A, u) - b) <= 1e-9 * np.linalg.norm(b)
+    _, ij = d.solve({"type": "cg.blockdiagonal", "precision": 1e-12, "max_iter": 200000}, return_info=True)
+    assert info["iterations"] < ij["iterations"] / 4
+    # parametric operator: the hierarchy is rebuilt for every frozen A(mu)
+    g2 = grids.cube(32)
+    fac = problems.AffinelyDecomposable(problems.Constant(1.0), [problems.Expression("x[0]*x[0]+0.1", 2)], ["mu"])
+    p2 = problems.Problem(fac, problems.ESV2007().force, parameter_name="mu", parameter_size=1)
+    d2 = hdd.SWIPDG(g2, p2)
+    d2.init()
+    for mu in (0.1, 10.0):
+        um = d2.solve({"type": "cg.mg", "precision": 1e-13, "max_iter": 1000}, mu=mu)
+        ud = d2.solve({"type": "cg.diagonal", "precision": 1e-13, "max_iter": 100000}, mu=mu)
+        assert rel(um, ud) <= SOL_TOL
+    # needs a structured cube grid with p = 1
+    ds = hdd.SWIPDG(grids.simplex(4), problems.ESV2007())
+    ds.init()
+    with pytest.raises(hdd.discretizations.requirements_not_met):
+        ds.solve({"type": "cg.mg", "precision": 1e-10, "max_iter": 100})
+    dq = hdd.SWIPDG(grids.cube(8), problems.ESV2007(), polorder=2)
+    dq.init()
+    with pytest.raises(hdd.discretizations.requirements_not_met):
+        dq.solve({"type": "cg.mg", "precision": 1e-10, "max_iter": 100})
