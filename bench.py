@@ -6,7 +6,9 @@ A step is one pass of the hot path over the workload: assemble every affine part
 (BASELINE.json configs[4], the configuration the metric is quoted on; --grid scales it down for a quick look).
 
     value          assembled DoFs/s over all ranks: K * N_dofs / sum of the K assembly times (device time, max over ranks)
-    cg_solve_s     mean CG time-to-solution of the K steps (device time), with cg_iterations and cg_s_per_iteration
+    cg_solve_s     mean CG time-to-solution of the K steps (device time), with cg_iterations and cg_s_per_iteration;
+                   default solver "cg.mg" (CG with the two-level multigrid preconditioner); cg_diagonal holds the plain
+                   Jacobi-CG solve of the same system, run once after the timed steps
     ms_per_step    whole step (assembly + solve), wall clock between barriers / K
     e2e            the same through the public API from HOST buffers: grid arrays -> hdd_mesh_create (H2D) -> init -> solve
                    -> solution back on the host (D2H), every step
@@ -131,7 +133,8 @@ def main():
     ap.add_argument("--cpu-cg-iters", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--solver", default="cg.diagonal", help="cg.blockdiagonal | cg.diagonal | cg.identity")
+    ap.add_argument("--solver", default="cg.mg", help="cg.mg | cg.blockdiagonal | cg.diagonal | cg.identity")
+    ap.add_argument("--no-jacobi", action="store_true", help="skip the extra Jacobi-CG solve reported next to --solver")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -203,6 +206,26 @@ def main():
         torch.distributed.all_reduce(stats, op=torch.distributed.ReduceOp.MAX)
     t_asm, t_cg, wall = [float(v) for v in stats.cpu()]
 
+    # the plain Jacobi-preconditioned CG on the same system, once, outside the timed steps: its SpMV / update / direction
+    # kernels are the ones the roofline numbers below are taken from
+    jacobi = None
+    if not args.no_jacobi or args.solver != "cg.diagonal":
+        jopt = dict(options, type="cg.diagonal")
+        if args.no_jacobi:
+            jopt["max_iter"] = 50
+        try:
+            _, ji = d.uncached_solve(jopt, return_info=True, copy_to_host=False)
+        except hdd.discretizations.linear_solver_failed:
+            ji = None
+        if ji is not None:
+            js = torch.tensor([ji["seconds"]], dtype=torch.float64, device="cuda")
+            if world > 1:
+                torch.distributed.all_reduce(js, op=torch.distributed.ReduceOp.MAX)
+            jacobi = {"solve_s": float(js.cpu()[0]), "iterations": ji["iterations"],
+                      "s_per_iteration": float(js.cpu()[0]) / max(ji["iterations"], 1),
+                      "halo": ("peer-memory SpMV (CUDA IPC over NVLink)" if ji.get("peer_memory") else "NCCL send/recv")
+                      if world > 1 else "none"}
+
     # roofline of the dominant kernel: CG SpMV, timed alone with CUDA events on the library's stream
     L = capi.lib()
     roof = {}
@@ -267,9 +290,11 @@ def main():
                            "%.1f GB per part)" % (8.0 * 16 * (n * n + 2 * 2 * n * (n - 1)) / 1e9),
                            "parallelism": "subdomain slabs x%d" % world,
                            "halo": ("peer-memory SpMV (CUDA IPC over NVLink)" if results[-1][1].get("peer_memory") else
-                                    "NCCL send/recv") if world > 1 else "none"},
+                                    "NCCL send/recv of the CG direction" + (", all-reduce of the restricted residual (cg.mg)"
+                                                                           if args.solver == "cg.mg" else ""))
+                           if world > 1 else "none"},
                 "assemble_ms": 1e3 * t_asm / args.steps, "cg_solve_s": t_cg / args.steps, "cg_iterations": iters,
-                "cg_s_per_iteration": t_cg / args.steps / max(iters, 1),
+                "cg_s_per_iteration": t_cg / args.steps / max(iters, 1), "cg_diagonal": jacobi,
                 "roofline": roof["spmv"], "roofline_assembly": roof["assembly"], "roofline_cg_update": roof["cg_update"],
                 "roofline_cg_direction": roof["cg_direction"],
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "grid_generation_s": t_grid}

@@ -16,10 +16,19 @@
 // The reference's default solver is BiCGSTAB with an algebraic-multigrid / ILU preconditioner
 // (Stuff::LA::Solver defaults, discretizations/base.hh:314-322); this is the same idea specialised to the
 // structured grids of BASELINE configs 2 and 5.  Everything is additive and symmetric, so CG stays applicable; all
-// reductions are deterministic.  Single GPU only (hdd_solve falls back loudly otherwise).
+// reductions are deterministic.
+//
+// Multi GPU: the DG level (SpMV, block Jacobi, restriction, prolongation) is distributed like the rest of the solve; the
+// vertex hierarchy is replicated - every rank assembles the rows of A_c its cells contribute to, one all-reduce makes
+// the level-0 stencil global (once per solve), and per application one all-reduce of the restricted residual (8 B per
+// vertex) feeds identical V-cycles on every rank.  No halo exchange inside the V-cycle; the coarse work does not scale
+// with the GPU count, the 85 % of the iteration that lives on the DG level does.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
 
 #include "handles.hpp"
 #include "reduce.cuh"
@@ -43,7 +52,7 @@ __device__ __forceinline__ void load_neigh4(const int32_t* neigh, int k, int* nb
 // cells: vertices must be (v0, v0+1, v0+nx1, v0+nx1+1); records v0 per cell and the map lexicographic cell -> cell
 __global__ void k_struct_cells(const int32_t* __restrict__ cv, int32_t n_cells, int nx, int ny, int32_t* __restrict__ cell_v0,
                                int32_t* __restrict__ lex_cell, int32_t* flag) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;  // local cell id
   if (c >= n_cells) return;
   const int4 v = __ldg(reinterpret_cast<const int4*>(cv) + c);
   const int nx1 = nx + 1;
@@ -87,12 +96,14 @@ __global__ void __launch_bounds__(kMgThreads)
     for (int a = 0; a < 2; ++a) {
       const int cx = ix - 1 + a, cy = iy - 1 + b;
       if (cx < 0 || cy < 0 || cx >= nx || cy >= ny) continue;
-      const int c = __ldg(lex_cell + cx + nx * cy);
+      const int c = __ldg(lex_cell + cx + nx * cy);  // local cell id, -1 = not on this rank
+      const int k = c - m.own0;
+      if (c < 0 || k < 0 || k >= m.n_own) continue;  // rows of cells owned elsewhere are added by the all-reduce
       const int i = (1 - a) + 2 * (1 - b);  // local index of v in that cell
       int nb[4];
-      load_neigh4(m.neigh, c, nb);
+      load_neigh4(m.neigh, k, nb);
       const int nblk = block_count<4>(nb);
-      const double* row = vals + __ldg(m.blk_start + c) * 16 + int64_t(i) * nblk * 4;
+      const double* row = vals + __ldg(m.blk_start + k) * 16 + int64_t(i) * nblk * 4;
 #pragma unroll
       for (int t = 0; t < 5; ++t) {
         const int cell = t == 0 ? c : nb[t - 1];
@@ -111,8 +122,25 @@ __global__ void __launch_bounds__(kMgThreads)
 #pragma unroll
   for (int e = 0; e < 9; ++e) {
     S[e * nv + v] = acc[e];
-    SC[e * nv + v] = (e & 1) ? -acc[e] : acc[e];  // e odd <=> |dx| + |dy| odd: C A_c C flips the edge neighbours
+    if (SC) SC[e * nv + v] = (e & 1) ? -acc[e] : acc[e];  // e odd <=> |dx| + |dy| odd: C A_c C flips the edge neighbours
   }
+}
+
+// SC = C S C after the all-reduce of S (multi GPU)
+__global__ void k_twist_stencil(const double* __restrict__ S, int64_t nv, double* __restrict__ SC) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= 9 * nv) return;
+  const int e = int(t / nv);
+  SC[t] = (e & 1) ? -S[t] : S[t];
+}
+
+// b1 = C b0 after the all-reduce of b0 (multi GPU)
+__global__ void k_twist_vector(const int* done, const double* __restrict__ b0, int nx, int64_t nv, double* __restrict__ b1) {
+  if (done && *done) return;
+  const int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  const int nx1 = nx + 1;
+  b1[v] = ((int(v % nx1) + int(v / nx1)) & 1) ? -b0[v] : b0[v];
 }
 
 // ---- Galerkin coarse operator with bilinear interpolation: 9-point -> 9-point ---------------------------------
@@ -259,8 +287,8 @@ __global__ void k_mg_dense(const int* done, const double* __restrict__ Ainv, int
 // ---- DG level ---------------------------------------------------------------------------------------------------
 // rc = P^T r (sum of the DG residual entries sitting on each vertex) and its checkerboard-signed copy
 __global__ void __launch_bounds__(kMgThreads)
-    k_dg_restrict(const int* done, const double* __restrict__ r, const int32_t* __restrict__ lex_cell, int nx, int ny,
-                  double* __restrict__ b0, double* __restrict__ b1) {
+    k_dg_restrict(const int* done, const double* __restrict__ r, const int32_t* __restrict__ lex_cell, int own0,
+                  int n_own, int nx, int ny, double* __restrict__ b0, double* __restrict__ b1) {
   if (done && *done) return;
   const int nx1 = nx + 1;
   const int64_t nv = int64_t(nx1) * (ny + 1);
@@ -274,16 +302,17 @@ __global__ void __launch_bounds__(kMgThreads)
     for (int a = 0; a < 2; ++a) {
       const int cx = ix - 1 + a, cy = iy - 1 + b;
       if (cx < 0 || cy < 0 || cx >= nx || cy >= ny) continue;
-      const int c = __ldg(lex_cell + cx + nx * cy);
-      s += __ldg(r + size_t(4) * c + (1 - a) + 2 * (1 - b));
+      const int k = __ldg(lex_cell + cx + nx * cy) - own0;
+      if (k < 0 || k >= n_own) continue;
+      s += __ldg(r + size_t(4) * k + (1 - a) + 2 * (1 - b));
     }
   b0[v] = s;
-  b1[v] = ((ix + iy) & 1) ? -s : s;
+  if (b1) b1[v] = ((ix + iy) & 1) ? -s : s;
 }
 
 // z += P (x0 + C x1), r.z recomputed; optionally p = z (first direction).  One thread per cell, 256-bit accesses.
 __global__ void __launch_bounds__(kMgThreads)
-    k_dg_prolong_dot(const int* done, int32_t n_cells, const int32_t* __restrict__ cell_v0, int nx,
+    k_dg_prolong_dot(const int* done, int32_t n_cells, const int32_t* __restrict__ cell_v0 /* of the owned cells */, int nx,
                      const double* __restrict__ x0, const double* __restrict__ x1, const double* __restrict__ r,
                      double* __restrict__ z, double* __restrict__ p_init, double* partial, CgScalars* sc) {
   if (done && *done) return;
@@ -328,19 +357,20 @@ struct MgState {
 
 void mg_detect_structure(hdd_mesh* m, const double* xy_host, const double* xy_dev, const int32_t* cv_dev, int64_t n_verts) {
   m->sx = m->sy = 0;
-  if (m->kind != HDD_CUBE2D || m->n_own != m->n_global || m->n_loc != m->n_own) return;
+  if (m->kind != HDD_CUBE2D) return;
   int64_t nx1 = 1;
   while (nx1 < n_verts && xy_host[2 * nx1 + 1] == xy_host[1]) ++nx1;
   if (nx1 < 2 || n_verts % nx1 != 0) return;
   const int64_t nx = nx1 - 1, ny = n_verts / nx1 - 1;
   if (ny < 1 || nx * ny != m->n_global) return;
   cudaStream_t s = m->stream;
-  m->cell_v0.alloc(size_t(m->n_own));
-  m->lex_cell.alloc(size_t(m->n_own));
+  m->cell_v0.alloc(size_t(m->n_loc));
+  m->lex_cell.alloc(size_t(m->n_global));
+  HDD_CUDA(cudaMemsetAsync(m->lex_cell.p, 0xFF, size_t(m->n_global) * sizeof(int32_t), s));  // -1: not on this rank
   DevBuf<int32_t> flag;
   flag.alloc(1);
   flag.zero(s);
-  k_struct_cells<<<blocks_for(m->n_own), kMgThreads, 0, s>>>(cv_dev, m->n_own, int(nx), int(ny), m->cell_v0.p, m->lex_cell.p, flag.p);
+  k_struct_cells<<<blocks_for(m->n_loc), kMgThreads, 0, s>>>(cv_dev, m->n_loc, int(nx), int(ny), m->cell_v0.p, m->lex_cell.p, flag.p);
   k_struct_verts<<<blocks_for(n_verts), kMgThreads, 0, s>>>(xy_dev, int32_t(n_verts), int(nx), flag.p);
   count_launch(2);
   int32_t f = 0;
@@ -444,8 +474,8 @@ void mg_setup(hdd_swipdg* h, const double* vals) {
   hdd_mesh* m = h->mesh;
   if (m->sx == 0 || h->polorder != 1)
     HDD_THROW(HDD_ERR_REQUIREMENTS_NOT_MET,
-              "solver type 'cg.mg' needs polOrder 1 on a logically structured HDD_CUBE2D grid owned by one GPU (vertices numbered "
-              "x-fastest as by Stuff::Grid::Providers::Cube / hdd_grid_cube); use 'cg.diagonal' or 'cg.blockdiagonal'");
+              "solver type 'cg.mg' needs polOrder 1 on a logically structured HDD_CUBE2D grid (vertices numbered x-fastest as by "
+              "Stuff::Grid::Providers::Cube / hdd_grid_cube); use 'cg.diagonal' or 'cg.blockdiagonal'");
   cudaStream_t s = m->stream;
   if (!h->mg) h->mg = new MgState;
   MgState& st = *h->mg;
@@ -468,8 +498,15 @@ void mg_setup(hdd_swipdg* h, const double* vals) {
     f0->S.alloc(size_t(9) * nv);
     f1->S.alloc(size_t(9) * nv);
   }
-  k_vertex_galerkin<<<blocks_for(nv), kMgThreads, 0, s>>>(h->view(), vals, m->cell_v0.p, m->lex_cell.p, m->sx, m->sy, f0->S.p, f1->S.p);
+  const bool multi = m->world > 1;
+  k_vertex_galerkin<<<blocks_for(nv), kMgThreads, 0, s>>>(h->view(), vals, m->cell_v0.p, m->lex_cell.p, m->sx, m->sy, f0->S.p,
+                                                           multi ? nullptr : f1->S.p);
   count_launch();
+  if (multi) {
+    Nccl::get().all_reduce_sum(f0->S.p, size_t(9) * nv, m->comm, s);
+    k_twist_stencil<<<blocks_for(9 * nv), kMgThreads, 0, s>>>(f0->S.p, nv, f1->S.p);
+    count_launch();
+  }
   HDD_CUDA(cudaGetLastError());
   build_hierarchy(h, st.h[0], std::move(f0));
   build_hierarchy(h, st.h[1], std::move(f1));
@@ -481,10 +518,34 @@ void mg_apply(hdd_swipdg* h, const int* done, const double* r, double* z, double
   hdd_mesh* m = h->mesh;
   MgState& st = *h->mg;
   cudaStream_t s = m->stream;
+  // HDD_MG_TIMING=1: wall-clock phases of the first applications (synchronising; diagnostics only)
+  static const bool timing = [] { const char* e = std::getenv("HDD_MG_TIMING"); return e && e[0] == '1'; }();
+  static int timed_calls = 0;
+  const bool tt = timing && timed_calls < 6;
+  double t_mark = 0.0;
+  auto lap = [&](const char* what) {
+    if (!tt) return;
+    cudaStreamSynchronize(s);
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    const double now = ts.tv_sec + 1e-9 * ts.tv_nsec;
+    if (what) std::fprintf(stderr, "[hdd mg rank %d call %d] %-12s %.3f ms\n", m->rank, timed_calls, what, 1e3 * (now - t_mark));
+    t_mark = now;
+  };
+  lap(nullptr);
   MgLevel& a = *st.h[0].levels[0];
   MgLevel& b = *st.h[1].levels[0];
-  k_dg_restrict<<<blocks_for(a.nv), kMgThreads, 0, s>>>(done, r, m->lex_cell.p, st.nx, st.ny, a.b.p, b.b.p);
+  const bool multi = m->world > 1;
+  k_dg_restrict<<<blocks_for(a.nv), kMgThreads, 0, s>>>(done, r, m->lex_cell.p, m->own0, m->n_own, st.nx, st.ny, a.b.p,
+                                                         multi ? nullptr : b.b.p);
   count_launch();
+  lap("restrict");
+  if (multi) {
+    Nccl::get().all_reduce_sum(a.b.p, size_t(a.nv), m->comm, s);
+    lap("all-reduce");
+    k_twist_vector<<<blocks_for(a.nv), kMgThreads, 0, s>>>(done, a.b.p, st.nx, a.nv, b.b.p);
+    count_launch();
+  }
   if (st.h[0].levels.size() == 1) {
     // the fine vertex grid is already small enough for the dense solve
     k_mg_dense<<<(int(a.nv) + 127) / 128, 128, 0, s>>>(done, st.h[0].coarse_inv.p, int(a.nv), a.b.p, a.x.p);
@@ -492,12 +553,16 @@ void mg_apply(hdd_swipdg* h, const int* done, const double* r, double* z, double
     count_launch(2);
   } else {
     vcycle(st.h[0], done, s);
+    lap("v-cycle");
     vcycle(st.h[1], done, s);
+    lap("v-cycle C");
   }
   const int grid = int(std::min<int64_t>((m->n_own + kMgThreads - 1) / kMgThreads, kMaxBlocks));
-  k_dg_prolong_dot<<<grid, kMgThreads, 0, s>>>(done, m->n_own, m->cell_v0.p, st.nx, a.x.p, b.x.p, r, z, p_init, partial, sc);
+  k_dg_prolong_dot<<<grid, kMgThreads, 0, s>>>(done, m->n_own, m->cell_v0.p + m->own0, st.nx, a.x.p, b.x.p, r, z, p_init, partial, sc);
   count_launch();
   HDD_CUDA(cudaGetLastError());
+  lap("prolong+dot");
+  if (tt) ++timed_calls;
 }
 
 int mg_num_levels(const hdd_swipdg* h) { return h->mg ? int(h->mg->h[0].levels.size()) : 0; }

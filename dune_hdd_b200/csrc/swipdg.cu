@@ -736,8 +736,6 @@ int hdd_solve(hdd_swipdg* h, const char* type, double precision, int max_iter, c
     c.values = vals;
     c.dinv = h->dinv.p;
     h->last_precond = use_diag;
-    if (use_diag == 3 && m->world > 1)
-      HDD_THROW(HDD_ERR_NOT_IMPLEMENTED, "solver type 'cg.mg' on more than one GPU");
     if (use_diag >= 2) {
       if (!h->dinv_block.p) {
         h->dinv_block.alloc(size_t(m->n_own) * h->nl * h->nl);

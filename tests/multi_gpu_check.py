@@ -47,6 +47,40 @@ def main():
         u_ref = spla.spsolve(o.to_scipy(rp, col, A).tocsc(), b)
         u, info = d.solve({"type": "cg.diagonal", "precision": 1e-13, "max_iter": 50000}, mu=mu, return_info=True)
         assert np.abs(u - u_ref[r0:r1]).max() <= 1e-8 * np.abs(u_ref).max(), "solution"
+        if kind == "sgrid":
+            # multigrid-preconditioned CG: distributed DG level, replicated vertex hierarchy
+            um, im = d.solve({"type": "cg.mg", "precision": 1e-13, "max_iter": 500}, return_info=True)
+            assert np.abs(um - u_ref[r0:r1]).max() <= 1e-8 * np.abs(u_ref).max(), "cg.mg solution"
+            assert im["iterations"] <= 70, "cg.mg iterations"
+            ub, ib = d.solve({"type": "cg.blockdiagonal", "precision": 1e-13, "max_iter": 50000}, return_info=True)
+            assert np.abs(ub - u_ref[r0:r1]).max() <= 1e-8 * np.abs(u_ref).max(), "cg.blockdiagonal solution"
+            # products and error norms are global over the ranks
+            import ctypes as C
+            from dune_hdd_b200 import capi
+            ids = ["l2", "penalty"]
+            capi.check(capi.lib().hdd_swipdg_only_these_products(d._h, (C.c_char_p * 2)(*[i.encode() for i in ids]), 2))
+            one = np.ones(r1 - r0)
+            assert abs(d.get_product("l2").apply2(one, one) - 4.0) <= 1e-11, "l2 product over all ranks"
+            Pm = o.to_scipy(rp, col, o.assemble_product(m, "penalty", rp, col))
+            assert abs(d.get_product("penalty").apply2(x[r0:r1], x[r0:r1]) - x @ (Pm @ x)) <= 1e-10 * abs(x @ (Pm @ x)), "penalty"
+            e = d.error_norms(*hdd.problems.ESV2007_EXACT, vector=u_ref[r0:r1], order=5)
+            e_ref = o.error_norms(m, u_ref, o.esv2007_exact(), order=5)
+            assert abs(e["L2"] - e_ref["L2"]) <= 1e-8 * e_ref["L2"], "L2 error over all ranks"
+            if rank == 0:
+                print("cg.mg iterations", im["iterations"], "cg.blockdiagonal", ib["iterations"])
+            if n == 32:  # p = 2 on the distributed mesh (generic halo exchange with 9 DoFs per cell)
+                d2 = hdd.BlockSWIPDG(g, prob, polorder=2, device=lr, cell_range=rng, comm=comm)
+                d2.init()
+                m2 = m.with_polorder(2)
+                rp2, col2 = o.pattern(m2)
+                A2 = o.assemble_lhs(m2, fac, None, rp2, col2)
+                b2 = o.assemble_rhs(m2, o.esv2007_force())
+                q0, q1 = rng[0] * 9, rng[1] * 9
+                assert np.abs(d2.system_matrix().affine_part() - A2[rp2[q0]:rp2[q1]]).max() <= 1e-12 * np.abs(A2).max(), "p2 entries"
+                u2_ref = spla.spsolve(o.to_scipy(rp2, col2, A2).tocsc(), b2)
+                u2 = d2.solve({"type": "cg.diagonal", "precision": 1e-13, "max_iter": 50000})
+                assert np.abs(u2 - u2_ref[q0:q1]).max() <= 1e-8 * np.abs(u2_ref).max(), "p2 solution"
+                del d2
         if kind == "alu":
             prm = {"mu": 0.5, "mu_bar": 0.5, "mu_hat": 1.0, "parameter_range_min": 0.1, "parameter_range_max": 1.0}
             ind_ref = o.indicators(m, u_ref, o.esv2007_force(), o.os2014_factor(0.5), a_hat=o.os2014_factor(1.0),
