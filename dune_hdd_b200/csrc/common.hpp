@@ -5,6 +5,8 @@
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <ctime>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -63,6 +65,31 @@ int guarded(F&& f) noexcept {
   }
 }
 
+// HDD_TIMING=1: wall-clock phases of the set-up entry points on stderr (diagnostics; synchronises the stream)
+struct PhaseTimer {
+  const char* scope;
+  cudaStream_t stream;
+  bool on;
+  double last;
+  static double now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+  }
+  PhaseTimer(const char* sc, cudaStream_t s) : scope(sc), stream(s), last(0.0) {
+    static const bool enabled = [] { const char* e = std::getenv("HDD_TIMING"); return e && e[0] == '1'; }();
+    on = enabled;
+    if (on) last = now();
+  }
+  void lap(const char* what) {
+    if (!on) return;
+    if (stream) cudaStreamSynchronize(stream);
+    const double t = now();
+    std::fprintf(stderr, "[hdd timing] %-18s %-28s %8.3f ms\n", scope, what, 1e3 * (t - last));
+    last = t;
+  }
+};
+
 // ---- host threading for the O(n_cells) passes over the caller's arrays -----------------------------------------
 inline int worker_count(int64_t n) {
   const unsigned hw = std::thread::hardware_concurrency();
@@ -112,7 +139,8 @@ struct DevBuf {
   void alloc(size_t count) {
     release();
     if (count == 0) count = 1;
-    HDD_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
+    // 32 bytes of slack: the bulk-copy SpMV rounds its 8-byte aligned row blocks out to 16-byte boundaries
+    HDD_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T) + 32));
     n = count;
   }
   void upload(const T* host, size_t count, cudaStream_t s) {

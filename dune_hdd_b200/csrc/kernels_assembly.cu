@@ -372,8 +372,8 @@ __device__ __forceinline__ void cube_face(const MeshView& m, const DevFn& fn, co
   store_block<NL>(row0, rs, block_slot<4>(c, nb, n), E);
 }
 
-template <int FK>
-__global__ void __launch_bounds__(kThreads, 3)
+template <int FK, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
     k_assemble_lhs_cube(MeshView m, const __grid_constant__ DevFn fn, ElemRule vol, LineRule fr, double s_in, double s_bnd,
                         double* __restrict__ vals) {
   using G = Geo<HDD_CUBE2D>;
@@ -447,8 +447,8 @@ __device__ __forceinline__ double pick(const double* v, int i) {
 // the basis evaluation (cheap next to the 8 B/nnz they have to write).
 //   MODE 0: the SWIPDG bilinear form (volume + inner + Dirichlet faces)
 //   MODE 1: only its penalty terms - Products::SwipdgPenaltyAssemblable (discretizations/swipdg.hh:444-479)
-template <int KIND, int P, int FK, int MODE>
-__global__ void __launch_bounds__(kThreads)
+template <int KIND, int P, int FK, int MODE, int MINB = 2>
+__global__ void __launch_bounds__(kThreads, MINB)
     k_assemble_rows(MeshView m, const __grid_constant__ DevFn fn, ElemRule vol, LineRule fr, double s_in, double s_bnd,
                     double* __restrict__ vals) {
   using G = Elem<KIND, P>;
@@ -912,10 +912,14 @@ void launch_assemble_lhs(const MeshView& m, const DevFn& factor_dev, int factor_
     // p = 2: one thread per row
     const int64_t rows = int64_t(m.n_own) * m.nl;
     dispatch_elem(m.kind, polorder, [&](auto kind, auto p) {
+      static const int minb = [] { const char* e = std::getenv("HDD_ASM_ROWS_MINB"); return e ? std::atoi(e) : 2; }();
       if constexpr (decltype(p)::value == 2)
         dispatch_fk(factor_kind, [&](auto k) {
-          k_assemble_rows<decltype(kind)::value, 2, decltype(k)::value, 0>
-              <<<grid_for(rows, kThreads), kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+          constexpr int KD = decltype(kind)::value, FKV = decltype(k)::value;
+          const int g = grid_for(rows, kThreads);
+          if (minb == 3) k_assemble_rows<KD, 2, FKV, 0, 3><<<g, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+          else if (minb == 4) k_assemble_rows<KD, 2, FKV, 0, 4><<<g, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+          else k_assemble_rows<KD, 2, FKV, 0, 2><<<g, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
         });
     });
   } else if (m.kind == HDD_SIMPLEX2D) {
@@ -923,8 +927,13 @@ void launch_assemble_lhs(const MeshView& m, const DevFn& factor_dev, int factor_
   } else if (generic_cube) {
     assemble_dispatch<HDD_CUBE2D>(factor_kind, blocks, s, m, factor_dev, vol, fr, si, sb, values);
   } else {
+    static const int minb = [] { const char* e = std::getenv("HDD_ASM_MINB"); return e ? std::atoi(e) : 3; }();
     dispatch_fk(factor_kind, [&](auto k) {
-      k_assemble_lhs_cube<decltype(k)::value><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+      constexpr int FKV = decltype(k)::value;
+      if (minb == 4) k_assemble_lhs_cube<FKV, 4><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+      else if (minb == 5) k_assemble_lhs_cube<FKV, 5><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+      else if (minb == 6) k_assemble_lhs_cube<FKV, 6><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+      else k_assemble_lhs_cube<FKV, 3><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
     });
   }
   count_launch();

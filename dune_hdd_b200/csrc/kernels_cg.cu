@@ -285,6 +285,123 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   grid_sum<1>(v, c.partial, &sc->ticket_a, [sc](const double(&w)[1]) { sc->red[0] = w[0]; });
 }
 
+// ---- TMA-staged SpMV, generic block size (P1 / P2 / Q2) ----------------------------------------------------------------
+// Same pipeline as k_cg_spmv_tma with TC cells (TC * NL <= 32 rows) per warp tile.  Row blocks of NL = 3 and NL = 9 are
+// only 8-byte aligned (72 / 648 bytes per block), so the producer copies from the enclosing 16-byte aligned range and the
+// consumers skip the leading double.
+template <int NF, int NL, int TC>
+struct TmaCfg {
+  static constexpr int kTileBytes = ((TC * (NF + 1) * NL * NL * 8 + 16 + 127) / 128) * 128;
+  static constexpr int kStages = (200 * 1024 / kTileBytes) < 32 ? (200 * 1024 / kTileBytes) : 32;
+  static constexpr int kConsumerWarps = NL >= 9 ? 12 : 16;
+  static constexpr int kThreads = (kConsumerWarps + 1) * 32;
+  static constexpr int kSmemBytes = kStages * kTileBytes + 2 * kStages * 8;
+};
+
+template <int NF, int NL, int TC>
+__global__ void __launch_bounds__((TmaCfg<NF, NL, TC>::kThreads), 1)
+    k_cg_spmv_tma_g(MeshView m, CgBuffers c, int par, int cells_per_cta) {
+  using Cfg = TmaCfg<NF, NL, TC>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ __align__(128) unsigned char smem[];
+  CgScalars* sc = c.sc;
+  if (sc->done[par]) return;
+  unsigned char* stage_base = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kTileBytes);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int c0 = blockIdx.x * cells_per_cta;
+  const int c1 = min(c0 + cells_per_cta, m.n_own);
+  const int n_tiles = c1 > c0 ? (c1 - c0 + TC - 1) / TC : 0;
+  double v[1] = {0.0};
+  if (warp == Cfg::kConsumerWarps) {
+    // producer warp: in round n lane l (< S) feeds tile n * S + l into stage l.  All lanes walk the same rounds and meet
+    // at the end of each one, so the warp reaches the final reduction converged.
+    const int rounds = (n_tiles + S - 1) / S;
+    for (int n = 0; n < rounds; ++n) {
+      const int t = n * S + lane;
+      if (lane < S && t < n_tiles) {
+        if (n > 0) mbar_wait(empty0 + 8 * lane, (n - 1) & 1);
+        const int k0 = c0 + t * TC, k1 = min(k0 + TC, c1);
+        const int64_t e0 = __ldg(m.blk_start + k0) * (NL * NL), e1 = __ldg(m.blk_start + k1) * (NL * NL);
+        const int64_t a0 = e0 & ~int64_t(1), a1 = (e1 + 1) & ~int64_t(1);  // 16-byte aligned element range
+        const uint32_t bytes = uint32_t(a1 - a0) * 8;
+        mbar_expect_tx(full0 + 8 * lane, bytes);
+        bulk_g2s(smem_u32(stage_base + lane * Cfg::kTileBytes), c.values + a0, bytes, full0 + 8 * lane);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int64_t own_off = int64_t(m.own0) * NL;
+    const int ci = lane / NL, i = lane - ci * NL;
+    const double* p_cur = dir_in(c, par);
+    for (int t = warp; t < n_tiles; t += Cfg::kConsumerWarps) {
+      const int stage = t % S, n = t / S;
+      const int k0 = c0 + t * TC;
+      const int k = k0 + ci;
+      const bool active = ci < TC && k < c1;
+      int cells[NF + 1];
+      int nblk = 0;
+      int64_t off = 0;
+      if (active) {
+        nblk = sorted_blocks<NF>(m, k, cells);
+        const int64_t e0 = __ldg(m.blk_start + k0) * (NL * NL);
+        off = __ldg(m.blk_start + k) * (NL * NL) - (e0 & ~int64_t(1)) + int64_t(i) * nblk * NL;
+        // touch the direction entries before waiting for the matrix tile: the gather then hits L1
+#pragma unroll
+        for (int s = 0; s < NF + 1; ++s)
+          if (s < nblk) asm volatile("prefetch.global.L1 [%0];" ::"l"(p_cur + size_t(NL) * cells[s]));
+      }
+      mbar_wait(full0 + 8 * stage, n & 1);
+      double sum = 0.0;
+      if (active) {
+        const double* row = reinterpret_cast<const double*>(stage_base + stage * Cfg::kTileBytes) + off;
+#pragma unroll
+        for (int s = 0; s < NF + 1; ++s)
+          if (s < nblk) {
+            const double* xs = p_cur + size_t(NL) * cells[s];
+#pragma unroll
+            for (int j = 0; j < NL; ++j) sum = fma(row[s * NL + j], __ldg(xs + j), sum);
+          }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + 8 * stage);
+      if (active) {
+        const int64_t r = int64_t(NL) * k + i;
+        c.q[r] = sum;
+        v[0] = fma(__ldg(p_cur + own_off + r), sum, v[0]);
+      }
+    }
+  }
+  grid_sum<1>(v, c.partial, &sc->ticket_a, [sc](const double(&w)[1]) { sc->red[0] = w[0]; });
+}
+
+template <int NF, int NL, int TC>
+void launch_cg_spmv_tma_g(const MeshView& m, const CgBuffers& c, int parity, cudaStream_t s) {
+  using Cfg = TmaCfg<NF, NL, TC>;
+  static bool configured = false;
+  if (!configured) {
+    HDD_CUDA(cudaFuncSetAttribute(k_cg_spmv_tma_g<NF, NL, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (const char* e = std::getenv("HDD_SPMV_CTAS")) sms = std::max(1, std::atoi(e));  // tests: few CTAs => the ring wraps
+  int cells_per_cta = (m.n_own + sms - 1) / sms;
+  cells_per_cta = (cells_per_cta + TC - 1) / TC * TC;
+  const int grid = (m.n_own + cells_per_cta - 1) / cells_per_cta;
+  k_cg_spmv_tma_g<NF, NL, TC><<<grid, Cfg::kThreads, Cfg::kSmemBytes, s>>>(m, c, parity, cells_per_cta);
+}
+
 // ---- vector kernels ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kCgThreads) k_cg_init(int64_t rows, int64_t own_off, CgBuffers c) {
   double v[2] = {0.0, 0.0};
@@ -677,12 +794,18 @@ void launch_cg_spmv(const MeshView& m, const CgBuffers& c, int parity, cudaStrea
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (const char* e = std::getenv("HDD_SPMV_CTAS")) sms = std::max(1, std::atoi(e));  // tests: few CTAs => the ring wraps
     int cells_per_cta = (m.n_own + sms - 1) / sms;
     cells_per_cta = (cells_per_cta + kTmaTileCells - 1) / kTmaTileCells * kTmaTileCells;
     const int grid = (m.n_own + cells_per_cta - 1) / cells_per_cta;
     PeerView pv{};
     if (peer) pv = *peer;
     k_cg_spmv_tma<<<grid, kTmaThreads, kTmaSmemBytes, s>>>(m, c, parity, cells_per_cta, pv);
+  } else if (use_tma_impl() && !peer && m.n_own >= 1024 && !(m.nf == 4 && m.nl == 4)) {
+    if (m.nf == 3 && m.nl == 3) launch_cg_spmv_tma_g<3, 3, 10>(m, c, parity, s);
+    else if (m.nf == 3 && m.nl == 6) launch_cg_spmv_tma_g<3, 6, 5>(m, c, parity, s);
+    else if (m.nf == 4 && m.nl == 9) launch_cg_spmv_tma_g<4, 9, 3>(m, c, parity, s);
+    else HDD_THROW(HDD_ERR_INTERNAL, "unsupported block shape nf = " << m.nf << ", nl = " << m.nl);
   } else {
     dispatch_block(m, [&](auto nf, auto nl) {
       k_cg_spmv<decltype(nf)::value, decltype(nl)::value><<<cg_grid(rows), kCgThreads, 0, s>>>(m, c, parity);

@@ -182,6 +182,7 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
     const bool whole = (cell_begin == 0 && cell_end == n_cells);
     const int64_t n_own = cell_end - cell_begin;
     cudaStream_t s = m->stream;
+    PhaseTimer pt("hdd_mesh_create", s);
 
     // ---- validate indices (threaded: these are the only full passes over the host arrays) -------------------
     {
@@ -198,6 +199,7 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
       if (bad_neigh >= 0) HDD_THROW(HDD_ERR_INDEX_OUT_OF_RANGE, "neighbour id out of range in cell " << bad_neigh.load());
     }
 
+    pt.lap("validate indices");
     // ---- halo: every non-owned cell sharing a vertex with an owned cell (superset of the face neighbours the
     // SpMV needs; the Oswald interpolation needs all cells around a vertex)
     std::vector<int32_t> halo_lo, halo_hi;
@@ -215,6 +217,7 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
       std::copy(halo_hi.begin(), halo_hi.end(), m->cgid.begin() + halo_lo.size() + n_own);
     }
 
+    pt.lap("halo + cell ids");
     // ---- device-side localisation: the owned slices of the host arrays are uploaded as they are (no host copy);
     // kernels build the per-cell geometry records and translate neighbour ids to local numbering
     {
@@ -273,6 +276,7 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
       if (flag & 2) HDD_THROW(HDD_ERR_INTERNAL, "a neighbour of an owned cell is missing from the halo");
     }
 
+    pt.lap("upload + geometry kernels");
     // ---- local vertices + incidence (vertex -> local DoFs), boundary flags
     // (the incidence feeds the Oswald pass, which exists on simplices only; the local vertex ids also drive the
     // halo plan of a distributed mesh)
@@ -318,6 +322,7 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
     }
     m->h_cell_verts_loc.swap(cvl);
 
+    pt.lap("vertex incidence");
     // ---- subdomains (grid::Multiscale view): contiguous, subdomain-major cell ranges
     if (cell_subdomain) {
       if (cell_subdomain[0] != 0) HDD_THROW(HDD_ERR_WRONG_INPUT, "subdomain numbering must start at 0");
@@ -410,6 +415,7 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
       m->d_seg_ptr.upload(m->seg_ptr.data(), m->seg_ptr.size(), s);
     }
 
+    pt.lap("subdomains");
     // ---- K1 part 1: number of blocks per owned cell and their exclusive prefix sum
     {
       DevBuf<int64_t> nblk;
@@ -422,6 +428,7 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
       HDD_CUDA(cudaMemcpyAsync(&m->n_blocks, m->blk_start.p + n_own, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
       HDD_CUDA(cudaStreamSynchronize(s));
     }
+    pt.lap("block offsets");
     *out = m.release();
   });
 }

@@ -546,18 +546,22 @@ int hdd_swipdg_init(hdd_swipdg* h) {
     hdd_mesh* m = h->mesh;
     m->set_device();
     cudaStream_t s = m->stream;
+    PhaseTimer pt("hdd_swipdg_init", s);
     // K1 part 2: the CSR pattern handed out by pattern()
     h->rowptr.alloc(size_t(h->n_rows) + 1);
     h->col.alloc(size_t(h->nnz));
-    if (h->n_rows == 0) HDD_CUDA(cudaMemsetAsync(h->rowptr.p, 0, sizeof(int64_t), s));
-    launch_fill_csr(h->view(), h->rowptr.p, h->col.p, s);
     for (auto& p : h->lhs_comps) p.values.alloc(size_t(h->nnz));
     if (h->lhs_affine) h->lhs_affine->values.alloc(size_t(h->nnz));
     for (auto& p : h->rhs_comps) p.values.alloc(size_t(h->n_rows));
     if (h->rhs_affine) h->rhs_affine->values.alloc(size_t(h->n_rows));
+    pt.lap("allocate");
+    if (h->n_rows == 0) HDD_CUDA(cudaMemsetAsync(h->rowptr.p, 0, sizeof(int64_t), s));
+    launch_fill_csr(h->view(), h->rowptr.p, h->col.p, s);
+    pt.lap("pattern");
     assemble_all(h);
     assemble_products(h);
     HDD_CUDA(cudaStreamSynchronize(s));
+    pt.lap("assemble");
     h->initialized = true;
   });
 }

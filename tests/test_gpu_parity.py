@@ -2,6 +2,8 @@
 
 Bars (BASELINE.json north_star): pattern and DoF map bit-exact, assembled entries 1e-12 relative, solution /
 norms / indicators 1e-8 relative, goldens to their 3 printed digits."""
+import os
+
 import numpy as np
 import pytest
 
@@ -417,8 +419,10 @@ def test_p2_parametric_cellwise_and_block_views(gpu):
     d2.init()
     m2, rp2, col2, A2, b2 = _oracle_system_p(g2, 2, o.const(1.0), o.esv2007_force(), tensor)
     assert rel(d2.system_matrix().affine_part(), A2) <= ENTRY_TOL
+    ds = hdd.SWIPDG(grids.simplex(2), problems.ESV2007(), polorder=2)
+    ds.init()
     with pytest.raises(hdd.discretizations.NotImplemented_):
-        hdd.SWIPDG(grids.simplex(2), problems.ESV2007(), polorder=2).estimate(None, "eta_ESV2007")
+        ds.estimate(np.zeros(ds.num_dofs()), "eta_ESV2007")
     with pytest.raises(hdd.discretizations.NotImplemented_):
         hdd.SWIPDG(g2, problems.ESV2007(), polorder=3)
 
@@ -584,3 +588,42 @@ def test_cg_mg_spe10_shape_parametric_and_requirements(gpu):
     dq.init()
     with pytest.raises(hdd.discretizations.requirements_not_met):
         dq.solve({"type": "cg.mg", "precision": 1e-10, "max_iter": 100})
+
+
+@pytest.mark.parametrize("kind,n,polorder", [("alu", 16, 1), ("alu", 32, 1), ("alu", 16, 2), ("sgrid", 32, 2), ("sgrid", 40, 1)])
+def test_bulk_copy_spmv_paths(gpu, kind, n, polorder):
+    """grids large enough (>= 1024 cells) for the TMA-staged CG SpMV kernels of every block size, against the direct
+    solve and against the generic kernels (HDD_SPMV_TMA=0 is read once per process, so compare through the oracle)"""
+    g = _grid(kind, n)
+    assert g.n_cells >= 1024
+    os.environ["HDD_SPMV_CTAS"] = "3"  # few CTAs: every CTA walks its shared-memory ring several times
+    try:
+        _bulk_copy_case(g, polorder)
+    finally:
+        del os.environ["HDD_SPMV_CTAS"]
+    _bulk_copy_case(g, polorder)
+
+
+def _bulk_copy_case(g, polorder):
+    d = hdd.SWIPDG(g, problems.ESV2007(), polorder=polorder)
+    d.init()
+    m = oracle_mesh(g).with_polorder(polorder)
+    rp, col = o.pattern(m)
+    A = o.assemble_lhs(m, o.const(1.0), None, rp, col)
+    b = o.assemble_rhs(m, o.esv2007_force())
+    u_ref = direct_solve(rp, col, A, b)
+    u, info = d.solve({"type": "cg.diagonal", "precision": 1e-13, "max_iter": 100000}, return_info=True)
+    assert info["converged"] and rel(u, u_ref) <= SOL_TOL
+    # iterates: 10 iterations from the same start follow the oracle CG to rounding
+    x10, it, _ = o.cg(rp, col, A, b, precond=1, rtol=1e-30, maxit=10)
+    try:
+        d.uncached_solve({"type": "cg.diagonal", "precision": 1e-30, "max_iter": 10})
+    except hdd.discretizations.linear_solver_failed:
+        pass
+    import ctypes as C
+    from dune_hdd_b200 import capi
+    xp = C.POINTER(C.c_double)()
+    capi.check(capi.lib().hdd_solution_dev(d._h, C.byref(xp)))
+    xg = np.empty(d.num_dofs())
+    capi.check(capi.lib().hdd_copy_to_host(d._h, capi.ptr(xg), xp, C.c_size_t(xg.nbytes)))
+    assert rel(xg, x10) <= 1e-11
