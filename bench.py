@@ -45,36 +45,72 @@ def measured_peak_gbs():
 
 
 class ClockSampler(threading.Thread):
-    """samples nvidia-smi clocks and throttle reasons during the timed region"""
+    """samples SM clocks and throttle reasons during the timed region: through NVML in-process (no fork, no driver
+    re-initialisation next to a launch-bound step), falling back to spawning nvidia-smi"""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self._halt = index, [], threading.Event()
+        self.index, self.samples, self._halt, self._was_started = index, [], threading.Event(), False
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # LOCAL_RANK -> physical device: respect CUDA_VISIBLE_DEVICES when it lists plain indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
 
-    def run(self):
+    def _sample_nvml(self):
+        n = self._nvml
+        sm = n.nvmlDeviceGetClockInfo(self._handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self._handle, n.NVML_CLOCK_SM)
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        r = get(self._handle)
+        bits = [getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8), getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20), getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)]
+        return [str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b in bits]
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        return [x.strip() for x in out.strip().split(",")]
+
+    def start(self):
+        self._was_started = True
+        super().start()
+
+    def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
+                f = self._sample_nvml() if self._nvml else self._sample_smi()
                 if len(f) >= 6:
                     self.samples.append(f)
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.05 if self._nvml else 0.2)
 
     def stop(self):
         self._halt.set()
-        self.join(timeout=3)
+        if self._was_started:
+            self.join(timeout=3)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
+        reasons = [n for k, n in enumerate(self.NAMES) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
         mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples), "source": "nvml" if self._nvml else "nvidia-smi"}
 
 
 def cpu_baseline(n_cpu, cg_iters):
@@ -163,7 +199,7 @@ def main():
     n = args.n
     parts = (8, 8) if n % 8 == 0 else (1, 1)
     t0 = time.perf_counter()
-    grid = hdd.grids.cube(n, partitions=parts)
+    grid = hdd.grids.cube(n, partitions=parts, pinned=True)  # page-locked host arrays (hdd_host_alloc)
     t_grid = time.perf_counter() - t0
     problem = hdd.problems.ESV2007()
     roff = hdd.parallel.rank_cell_offsets(grid, world)
@@ -255,6 +291,8 @@ def main():
         del d
         torch.cuda.empty_cache()
         e_asm, e_cg = [], []
+        own_dofs = (cell_range[1] - cell_range[0]) * 4
+        x_host = capi.pinned_empty((own_dofs,), np.float64)  # page-locked result buffer, reused by every step
         for k in range(1 + args.steps):  # one warm-up
             barrier()
             t0 = time.perf_counter()
@@ -262,7 +300,7 @@ def main():
             d2.init()
             d2._sync = capi.check(L.hdd_sync(d2._h))
             t1 = time.perf_counter()
-            u, info = d2.uncached_solve(options, return_info=True, copy_to_host=True)
+            u, info = d2.uncached_solve(options, return_info=True, copy_to_host=True, out=x_host)
             t2 = time.perf_counter()
             del d2
             if k > 0:
@@ -277,8 +315,8 @@ def main():
         e2e = {"value": args.steps * n_dofs / ea, "unit": "DoFs/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(own_cells * 4 * 8), "cg_solve_s": ec / args.steps,
                "setup_s": ea / args.steps,
-               "note": "value = DoFs / (hdd_mesh_create from host arrays + hdd_swipdg_create + init), incl. host-side "
-                       "localisation of the grid; cg_solve_s includes the D2H copy of the solution"}
+               "note": "value = DoFs / (hdd_mesh_create from page-locked host arrays + hdd_swipdg_create + init), incl. "
+                       "host-side localisation of the grid; cg_solve_s includes the D2H copy of the solution"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": args.steps * n_dofs / t_asm, "unit": "DoFs/s", "n_gpus": world,

@@ -64,6 +64,7 @@ SYMBOLS = [
     "hdd_kernel_bytes", "hdd_expression_evaluate", "hdd_partition_plan", "hdd_free",
     "hdd_swipdg_only_these_products", "hdd_products_available", "hdd_product_num_components", "hdd_product_values",
     "hdd_product_coefficient", "hdd_pattern_volume", "hdd_product_apply2", "hdd_error_norms",
+    "hdd_host_alloc", "hdd_host_free",
 ]
 
 _lib = None
@@ -113,6 +114,35 @@ def as_f64(a):
 
 def as_i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class _PinnedBlock:
+    """page-locked host allocation (hdd_host_alloc) kept alive by the numpy arrays carved out of it"""
+
+    def __init__(self, nbytes):
+        self.ptr = C.c_void_p()
+        self.nbytes = int(nbytes)
+        check(lib().hdd_host_alloc(C.c_size_t(self.nbytes), C.byref(self.ptr)))
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().hdd_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """numpy array in page-locked host memory; falls back to ordinary memory if the allocation fails (no device)"""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    try:
+        blk = _PinnedBlock(max(n * dtype.itemsize, 1))
+    except Exception:
+        return np.empty(shape, dtype)
+    buf = (C.c_char * blk.nbytes).from_address(blk.ptr.value)
+    buf._hdd_owner = blk  # the ctypes buffer is the array's base object: the block lives as long as any view
+    return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
 
 
 def kernel_launches():

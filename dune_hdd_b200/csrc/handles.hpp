@@ -208,6 +208,14 @@ struct hdd_swipdg {
   std::vector<void*> ipc_opened;
   int last_precond = 1;  // 0 identity, 1 diagonal, 2 cell-block diagonal, 3 two-level multigrid (cg.mg)
   hdd::MgState* mg = nullptr;
+  // CUDA graph of two CG iterations, cached per solver type; valid while the operator / workspace pointers it was
+  // captured with are the ones in use (cg_graph_key)
+  struct CgGraph {
+    cudaGraphExec_t exec = nullptr;
+    const void* key[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    int64_t launches = 0;
+  };
+  CgGraph cg_graph[4];
   hdd::DevBuf<hdd::CgScalars> sc;
   hdd::CgScalars* sc_host = nullptr;  // pinned
   bool have_solution = false;

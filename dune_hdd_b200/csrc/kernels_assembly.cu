@@ -145,8 +145,15 @@ __global__ void __launch_bounds__(kThreads)
                    double* __restrict__ vals) {
   using G = Geo<KIND>;
   constexpr int NL = G::NL, NF = G::NF;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= m.n_own) return;
+  // P1 row blocks are 3 doubles wide: written straight from the registers every store instruction would touch 32
+  // different sectors for 24 bytes each.  The row blocks of the CTA's cells are one contiguous range of the value array,
+  // so they are staged in shared memory and written out fully coalesced.
+  constexpr bool kStaged = (NL == 3);
+  __shared__ double stage[kStaged ? kThreads * (NF + 1) * NL * NL : 1];
+  const int k_first = blockIdx.x * blockDim.x;
+  const bool live = k_first + int(threadIdx.x) < m.n_own;
+  if (!kStaged && !live) return;
+  const int k = live ? k_first + threadIdx.x : m.n_own - 1;  // idle threads of the last CTA recompute its last cell
   const int c = m.own0 + k;
   G g;
   g.load(m.cgeo, c);
@@ -156,7 +163,8 @@ __global__ void __launch_bounds__(kThreads)
   load_neigh<NF>(m.neigh, k, nb);
   const int nblk = block_count<NF>(nb);
   const int rs = nblk * NL;
-  double* row0 = vals + m.blk_start[k] * (NL * NL);
+  const int64_t base_blk = kStaged ? __ldg(m.blk_start + k_first) : 0;
+  double* row0 = kStaged ? stage + (m.blk_start[k] - base_blk) * (NL * NL) : vals + m.blk_start[k] * (NL * NL);
   double a_self = 0.0;
   if constexpr (FK == HDD_FN_CONSTANT) a_self = fn.value;
   if constexpr (FK == HDD_FN_CELLWISE) a_self = __ldg(fn.cell + c);
@@ -253,10 +261,17 @@ __global__ void __launch_bounds__(kThreads)
             E[i * NL + j] = fma(phm[i], Cc[j], fma(B[i], php[j], E[i * NL + j]));  // en/ne
           }
       }
-      store_block<NL>(row0, rs, block_slot<NF>(c, nb, n), E);
+      if (live) store_block<NL>(row0, rs, block_slot<NF>(c, nb, n), E);
     }
   }
-  store_block<NL>(row0, rs, block_slot<NF>(c, nb, c), D);
+  if (live) store_block<NL>(row0, rs, block_slot<NF>(c, nb, c), D);
+  if constexpr (kStaged) {
+    __syncthreads();
+    const int k_end = min(k_first + int(blockDim.x), m.n_own);
+    const int64_t total = (__ldg(m.blk_start + k_end) - base_blk) * (NL * NL);
+    double* dst = vals + base_blk * (NL * NL);
+    for (int64_t t = threadIdx.x; t < total; t += blockDim.x) dst[t] = stage[t];
+  }
 }
 
 // K2 for Q1 on axis-parallel rectangles.  Same integrals as k_assemble_lhs, with two structural facts used at compile
@@ -912,7 +927,7 @@ void launch_assemble_lhs(const MeshView& m, const DevFn& factor_dev, int factor_
     // p = 2: one thread per row
     const int64_t rows = int64_t(m.n_own) * m.nl;
     dispatch_elem(m.kind, polorder, [&](auto kind, auto p) {
-      static const int minb = [] { const char* e = std::getenv("HDD_ASM_ROWS_MINB"); return e ? std::atoi(e) : 2; }();
+      static const int minb = [] { const char* e = std::getenv("HDD_ASM_ROWS_MINB"); return e ? std::atoi(e) : 3; }();
       if constexpr (decltype(p)::value == 2)
         dispatch_fk(factor_kind, [&](auto k) {
           constexpr int KD = decltype(kind)::value, FKV = decltype(k)::value;

@@ -433,6 +433,20 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
   });
 }
 
+int hdd_host_alloc(size_t bytes, void** ptr) {
+  return guarded([&] {
+    if (!ptr) HDD_THROW(HDD_ERR_WRONG_INPUT, "ptr is NULL");
+    *ptr = nullptr;
+    HDD_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
+  });
+}
+
+int hdd_host_free(void* ptr) {
+  return guarded([&] {
+    if (ptr) HDD_CUDA(cudaFreeHost(ptr));
+  });
+}
+
 int hdd_mesh_destroy(hdd_mesh* mesh) {
   return guarded([&] {
     if (mesh) {

@@ -385,27 +385,17 @@ void mg_detect_structure(hdd_mesh* m, const double* xy_host, const double* xy_de
   m->sy = int(ny);
 }
 
-static void build_hierarchy(hdd_swipdg* h, MgHierarchy& H, std::unique_ptr<MgLevel> fine) {
+// recomputes the Galerkin operators below the finest level and the dense coarsest inverse; the level buffers are
+// allocated once per mesh by mg_setup and persist across solves, so a captured CUDA graph of the iteration stays valid
+static void build_hierarchy(hdd_swipdg* h, MgHierarchy& H, int nx, int ny) {
   cudaStream_t s = h->mesh->stream;
-  H.levels.clear();
-  H.levels.push_back(std::move(fine));
-  for (;;) {
-    MgLevel& f = *H.levels.back();
-    if (f.nv <= kMaxCoarse || (f.nx & 1) || (f.ny & 1) || f.nx < 2 || f.ny < 2) break;
-    std::unique_ptr<MgLevel> c(new MgLevel);
-    c->nx = f.nx / 2;
-    c->ny = f.ny / 2;
-    c->nv = int64_t(c->nx + 1) * (c->ny + 1);
-    c->S.alloc(size_t(9) * c->nv);
-    k_rap<<<blocks_for(c->nv), kMgThreads, 0, s>>>(f.S.p, f.nx, f.ny, c->S.p);
+  (void)nx;
+  (void)ny;
+  for (size_t l = 0; l + 1 < H.levels.size(); ++l) {
+    MgLevel& f = *H.levels[l];
+    MgLevel& c = *H.levels[l + 1];
+    k_rap<<<blocks_for(c.nv), kMgThreads, 0, s>>>(f.S.p, f.nx, f.ny, c.S.p);
     count_launch();
-    H.levels.push_back(std::move(c));
-  }
-  for (auto& L : H.levels) {
-    if (!L->b.p) L->b.alloc(size_t(L->nv));
-    L->x.alloc(size_t(L->nv));
-    L->r.alloc(size_t(L->nv));
-    L->y.alloc(size_t(L->nv));
   }
   // dense inverse of the coarsest operator (s.p.d.), Gauss-Jordan on the host
   MgLevel& C = *H.levels.back();
@@ -482,34 +472,57 @@ void mg_setup(hdd_swipdg* h, const double* vals) {
   st.nx = m->sx;
   st.ny = m->sy;
   const int64_t nv = int64_t(m->sx + 1) * (m->sy + 1);
-  std::unique_ptr<MgLevel> f0(new MgLevel), f1(new MgLevel);
-  for (MgLevel* L : {f0.get(), f1.get()}) {
-    L->nx = m->sx;
-    L->ny = m->sy;
-    L->nv = nv;
+  if (!st.h[0].levels.empty() && (st.h[0].levels[0]->nx != m->sx || st.h[0].levels[0]->ny != m->sy)) {
+    st.h[0].levels.clear();
+    st.h[1].levels.clear();
   }
-  // reuse the level-0 storage of a previous solve
-  if (!st.h[0].levels.empty() && st.h[0].levels[0]->nv == nv) {
-    f0->S = std::move(st.h[0].levels[0]->S);
-    f1->S = std::move(st.h[1].levels[0]->S);
-    f0->b = std::move(st.h[0].levels[0]->b);
-    f1->b = std::move(st.h[1].levels[0]->b);
-  } else {
-    f0->S.alloc(size_t(9) * nv);
-    f1->S.alloc(size_t(9) * nv);
+  // level structure first (allocation only), then the level-0 operators, then the Galerkin products
+  const bool fresh = st.h[0].levels.empty();
+  if (fresh) {
+    for (int t = 0; t < 2; ++t) {
+      std::unique_ptr<MgLevel> L(new MgLevel);
+      L->nx = m->sx;
+      L->ny = m->sy;
+      L->nv = nv;
+      L->S.alloc(size_t(9) * nv);
+      L->b.alloc(size_t(nv));
+      L->x.alloc(size_t(nv));
+      L->r.alloc(size_t(nv));
+      L->y.alloc(size_t(nv));
+      st.h[t].levels.push_back(std::move(L));
+      int lx = m->sx, ly = m->sy;
+      int64_t lv = nv;
+      while (!(lv <= kMaxCoarse || (lx & 1) || (ly & 1) || lx < 2 || ly < 2)) {
+        lx /= 2;
+        ly /= 2;
+        lv = int64_t(lx + 1) * (ly + 1);
+        std::unique_ptr<MgLevel> C(new MgLevel);
+        C->nx = lx;
+        C->ny = ly;
+        C->nv = lv;
+        C->S.alloc(size_t(9) * lv);
+        C->b.alloc(size_t(lv));
+        C->x.alloc(size_t(lv));
+        C->r.alloc(size_t(lv));
+        C->y.alloc(size_t(lv));
+        st.h[t].levels.push_back(std::move(C));
+      }
+    }
   }
+  MgLevel& f0 = *st.h[0].levels[0];
+  MgLevel& f1 = *st.h[1].levels[0];
   const bool multi = m->world > 1;
-  k_vertex_galerkin<<<blocks_for(nv), kMgThreads, 0, s>>>(h->view(), vals, m->cell_v0.p, m->lex_cell.p, m->sx, m->sy, f0->S.p,
-                                                           multi ? nullptr : f1->S.p);
+  k_vertex_galerkin<<<blocks_for(nv), kMgThreads, 0, s>>>(h->view(), vals, m->cell_v0.p, m->lex_cell.p, m->sx, m->sy, f0.S.p,
+                                                           multi ? nullptr : f1.S.p);
   count_launch();
   if (multi) {
-    Nccl::get().all_reduce_sum(f0->S.p, size_t(9) * nv, m->comm, s);
-    k_twist_stencil<<<blocks_for(9 * nv), kMgThreads, 0, s>>>(f0->S.p, nv, f1->S.p);
+    Nccl::get().all_reduce_sum(f0.S.p, size_t(9) * nv, m->comm, s);
+    k_twist_stencil<<<blocks_for(9 * nv), kMgThreads, 0, s>>>(f0.S.p, nv, f1.S.p);
     count_launch();
   }
   HDD_CUDA(cudaGetLastError());
-  build_hierarchy(h, st.h[0], std::move(f0));
-  build_hierarchy(h, st.h[1], std::move(f1));
+  build_hierarchy(h, st.h[0], m->sx, m->sy);
+  build_hierarchy(h, st.h[1], m->sx, m->sy);
   HDD_CUDA(cudaGetLastError());
 }
 

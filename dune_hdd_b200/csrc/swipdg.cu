@@ -15,6 +15,8 @@ hdd_swipdg::~hdd_swipdg() {
   for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
   if (sc_host) cudaFreeHost(sc_host);
   if (mg) hdd::mg_release(mg);
+  for (auto& g : cg_graph)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
 }
 
 namespace hdd {
@@ -786,19 +788,72 @@ int hdd_solve(hdd_swipdg* h, const char* type, double precision, int max_iter, c
     if (use_diag == 3) mg_apply(h, nullptr, c.r, c.z, c.p + size_t(m->own0) * h->nl, c.partial, c.sc);
     if (multi) nc.all_reduce_sum(&c.sc->red[1], 2, m->comm, s);
     launch_cg_init_finish(v, c, s);
+    // One CG iteration = 3 kernels (+ 2 all-reduces, + ~100 small multigrid kernels for cg.mg).  The first batch is
+    // launched directly (one-time attribute / buffer set-up happens there); after that two iterations (parity 0 and 1)
+    // are captured into a CUDA graph and replayed, so a launch-bound iteration costs one graph launch instead of up to
+    // a hundred kernel launches and does not stall the GPU when the host thread is delayed.  HDD_CG_GRAPH=0 disables it.
+    auto iteration = [&](int parity) {
+      if (multi && !p2p) m->halo_exchange(c.p, h->nl);
+      launch_cg_spmv(v, c, parity, s, peer);
+      if (multi) nc.all_reduce_sum(&c.sc->red[0], 1, m->comm, s);
+      launch_cg_update(v, c, parity, s);
+      if (use_diag == 3) mg_apply(h, &c.sc->done[parity], c.r, c.z, nullptr, c.partial, c.sc);
+      if (multi) nc.all_reduce_sum(&c.sc->red[1], 2, m->comm, s);
+      launch_cg_direction(v, c, parity, s);
+    };
+    static const bool graphs_wanted = [] {
+      const char* e = std::getenv("HDD_CG_GRAPH");
+      const char* t = std::getenv("HDD_MG_TIMING");
+      return !(e && e[0] == '0') && !(t && t[0] == '1');
+    }();
+    hdd_swipdg::CgGraph& cached = h->cg_graph[use_diag];
+    const void* key[5] = {vals, c.p_alt, peer, c.dinv_block, m->send_buf.p};
+    if (cached.exec && std::memcmp(cached.key, key, sizeof(key)) != 0) {
+      cudaGraphExecDestroy(cached.exec);
+      cached.exec = nullptr;
+    }
+    bool capture_failed = false;
     int par = 0, launched = 0, batch = use_diag == 3 ? 8 : 16;
+    bool first_batch = !cached.exec;  // a cached graph means every one-time set-up has already happened
     for (;;) {
-      for (int k = 0; k < batch; ++k) {
-        if (multi && !p2p) m->halo_exchange(c.p, h->nl);
-        launch_cg_spmv(v, c, par, s, peer);
-        if (multi) nc.all_reduce_sum(&c.sc->red[0], 1, m->comm, s);
-        launch_cg_update(v, c, par, s);
-        if (use_diag == 3) mg_apply(h, &c.sc->done[par], c.r, c.z, nullptr, c.partial, c.sc);
-        if (multi) nc.all_reduce_sum(&c.sc->red[1], 2, m->comm, s);
-        launch_cg_direction(v, c, par, s);
-        par ^= 1;
-        ++launched;
+      if (!first_batch && graphs_wanted && !cached.exec && !capture_failed) {
+        const int64_t before = hdd_kernel_launches();
+        cudaGraph_t g = nullptr;
+        bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+          try {
+            iteration(0);
+            iteration(1);
+          } catch (const Error&) {
+            ok = false;
+          }
+          if (cudaStreamEndCapture(s, &g) != cudaSuccess || !g) ok = false;
+          if (ok && cudaGraphInstantiate(&cached.exec, g, 0) != cudaSuccess) ok = false;
+          if (g) cudaGraphDestroy(g);
+        }
+        cached.launches = hdd_kernel_launches() - before;
+        g_kernel_launches.fetch_sub(cached.launches);  // captured, not launched yet
+        if (ok) {
+          std::memcpy(cached.key, key, sizeof(key));
+        } else {
+          cudaGetLastError();
+          if (cached.exec) cudaGraphExecDestroy(cached.exec);
+          cached.exec = nullptr;
+          capture_failed = true;
+        }
       }
+      if (cached.exec && graphs_wanted) {
+        for (int k = 0; k < batch; k += 2) HDD_CUDA(cudaGraphLaunch(cached.exec, s));
+        count_launch(int(cached.launches) * (batch / 2));
+        launched += batch;  // batch is even: the parity is back at its value from the start of the batch
+      } else {
+        for (int k = 0; k < batch; ++k) {
+          iteration(par);
+          par ^= 1;
+          ++launched;
+        }
+      }
+      first_batch = false;
       HDD_CUDA(cudaMemcpyAsync(h->sc_host, h->sc.p, sizeof(CgScalars), cudaMemcpyDeviceToHost, s));
       HDD_CUDA(cudaStreamSynchronize(s));
       if (h->sc_host->done[par]) break;

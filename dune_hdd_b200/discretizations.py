@@ -327,10 +327,11 @@ class SWIPDG:
         x, info = self._cache[key]
         return (x.copy(), dict(info)) if return_info else x.copy()
 
-    def uncached_solve(self, options=None, mu=None, return_info=False, copy_to_host=True):
+    def uncached_solve(self, options=None, mu=None, return_info=False, copy_to_host=True, out=None):
+        """out: optional preallocated float64 array of num_owned_dofs() entries (e.g. page-locked, capi.pinned_empty)"""
         options = dict(self.solver_options() if options is None else options)
         mu_a, ms = _mu_array(mu)
-        x = self.create_vector() if copy_to_host else None
+        x = (self.create_vector() if out is None else out) if copy_to_host else None
         info = capi.hdd_solve_info()
         _check(capi.lib().hdd_solve(self._h, options.get("type", "").encode(), C.c_double(options.get("precision", 1e-10)),
                                     int(options.get("max_iter", 100000)), capi.ptr(mu_a), ms, capi.ptr(x),

@@ -15,6 +15,7 @@ SIMPLEX2D, CUBE2D = capi.HDD_SIMPLEX2D, capi.HDD_CUBE2D
 class Grid:
     def __init__(self, kind, xy, cell_verts, cell_neigh, cell_subdomain=None, partitions=(1, 1)):
         self.kind = kind
+        # np.ascontiguousarray keeps arrays that already have the right type and layout (e.g. page-locked ones) as they are
         self.xy = capi.as_f64(xy)
         self.cell_verts = capi.as_i32(cell_verts)
         self.cell_neigh = capi.as_i32(cell_neigh)
@@ -48,16 +49,18 @@ class Grid:
         return np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
 
 
-def cube(nx, ny=None, lower_left=(-1.0, -1.0), upper_right=(1.0, 1.0), partitions=(1, 1)):
-    """SGrid<2,2> via Providers::Cube(lower_left, upper_right, num_elements): nx*ny axis-parallel cells, x fastest."""
+def cube(nx, ny=None, lower_left=(-1.0, -1.0), upper_right=(1.0, 1.0), partitions=(1, 1), pinned=False):
+    """SGrid<2,2> via Providers::Cube(lower_left, upper_right, num_elements): nx*ny axis-parallel cells, x fastest.
+    pinned: allocate the arrays in page-locked host memory (hdd_host_alloc) so that the upload runs at link speed."""
     ny = nx if ny is None else ny
     L = capi.lib()
     nc, nv = C.c_int64(), C.c_int64()
     capi.check(L.hdd_grid_cube_sizes(C.c_int64(nx), C.c_int64(ny), C.byref(nc), C.byref(nv)))
-    xy = np.empty((nv.value, 2))
-    cv = np.empty((nc.value, 4), np.int32)
-    nb = np.empty((nc.value, 4), np.int32)
-    sub = np.empty(nc.value, np.int32)
+    empty = capi.pinned_empty if pinned else np.empty
+    xy = empty((nv.value, 2), np.float64)
+    cv = empty((nc.value, 4), np.int32)
+    nb = empty((nc.value, 4), np.int32)
+    sub = empty((nc.value,), np.int32)
     capi.check(L.hdd_grid_cube(C.c_int64(nx), C.c_int64(ny), C.c_double(lower_left[0]), C.c_double(upper_right[0]),
                                C.c_double(lower_left[1]), C.c_double(upper_right[1]), int(partitions[0]),
                                int(partitions[1]), capi.ptr(xy), capi.ptr(cv, C.c_int32), capi.ptr(nb, C.c_int32),

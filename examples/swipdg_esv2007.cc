@@ -42,6 +42,30 @@ int main(int argc, char** argv) {
         std::printf("  %-16s %.3e   expected %.2e   %s\n", type.c_str(), eta, expected, ok ? "ok" : "MISMATCH");
       }
     }
+    // ESV2007 on SGrid (test/linearelliptic-swipdg-expectations_esv2007_2dsgrid.cxx:31-36): Q1, solved with the
+    // multigrid-preconditioned CG, error norms evaluated on the device, products requested through only_these_products
+    const double l2_golden[4] = {1.13e-02, 2.90e-03, 7.41e-04, 1.88e-04}, h1_golden[4] = {2.77e-01, 1.39e-01, 6.98e-02, 3.50e-02};
+    for (int level = 0; level < levels; ++level) {
+      const int n = 8 << level;
+      const Grid grid = Grid::cube(n, n, -1.0, 1.0, -1.0, 1.0);
+      SWIPDG discretization(grid, problem, 1, 0, nullptr, 0, -1, {"l2", "h1_semi", "elliptic"});
+      discretization.init();
+      Vector solution = discretization.create_vector();
+      LinearElliptic::Discretizations::SolveInfo info;
+      discretization.uncached_solve({{"type", "cg.mg"}, {"precision", "1e-12"}, {"max_iter", "1000"}}, solution, Parameter(), &info);
+      const auto err = discretization.error_norms(solution, "cos(0.5*pi*x[0])*cos(0.5*pi*x[1])",
+                                                  "-0.5*pi*sin(0.5*pi*x[0])*cos(0.5*pi*x[1])",
+                                                  "-0.5*pi*cos(0.5*pi*x[0])*sin(0.5*pi*x[1])", 7);
+      const bool ok = std::fabs(err.at("L2") - l2_golden[level]) <= 0.006 * l2_golden[level] &&
+                      std::fabs(err.at("H1_semi") - h1_golden[level]) <= 0.006 * h1_golden[level];
+      failures += ok ? 0 : 1;
+      const Vector one(solution.size(), 1.0);
+      const double area = discretization.get_product("l2").apply2(one, one);
+      failures += std::fabs(area - 4.0) <= 1e-10 ? 0 : 1;
+      std::printf("sgrid level %d: %dx%d cells, cg.mg %d iterations, L2 %.3e (expected %.2e), H1_semi %.3e (expected %.2e), "
+                  "|Omega| via l2 product %.12f  %s\n", level, n, n, info.iterations, err.at("L2"), l2_golden[level],
+                  err.at("H1_semi"), h1_golden[level], area, ok ? "ok" : "MISMATCH");
+    }
     // error behaviour of the reference: init() not called (discretizations/base.hh:370-377)
     try {
       const Grid grid = Grid::simplex(4, -1.0, 1.0, -1.0, 1.0);

@@ -9,6 +9,7 @@
 #ifndef HDD_B200_HPP
 #define HDD_B200_HPP
 
+#include <cmath>
 #include <cstdint>
 #include <map>
 #include <memory>
@@ -197,7 +198,40 @@ class AffinelyDecomposedContainer {
   int which_;
 };
 
-// Discretizations::SWIPDG< GridType, layer, double, 1, polOrder = 1 > and BlockSWIPDG share this class: a grid with
+// get_product(id) (discretizations/base.hh:281-291): the affinely decomposed product matrix
+class Product {
+ public:
+  Product(hdd_swipdg* h, std::string id) : h_(h), id_(std::move(id)) { info(nullptr, nullptr, nullptr); }
+  int num_components() const { int n = 0; info(&n, nullptr, nullptr); return n; }
+  bool has_affine_part() const { int a = 0; info(nullptr, &a, nullptr); return a != 0; }
+  // true: values follow SWIPDG::pattern_volume() (one dense n_loc x n_loc block per cell), false: SWIPDG::pattern()
+  bool volume_pattern() const { int v = 0; info(nullptr, nullptr, &v); return v != 0; }
+  std::string coefficient(int q) const { const char* s = nullptr; check(hdd_product_coefficient(h_, id_.c_str(), q, &s)); return s; }
+  const double* component_dev(int q, int64_t* count = nullptr) const {
+    const double* p = nullptr; check(hdd_product_values(h_, id_.c_str(), q, &p, count)); return p;
+  }
+  Vector component(int q) const {
+    int64_t n = 0; const double* p = component_dev(q, &n);
+    Vector v(static_cast<size_t>(n)); check(hdd_copy_to_host(h_, v.data(), p, v.size() * sizeof(double))); return v;
+  }
+  Vector affine_part() const { return component(-1); }
+  // freeze_parameter(mu).apply2(u, v) = u^T P(mu) v, evaluated on the device
+  double apply2(const Vector& u, const Vector& v, const Parameter& mu = Parameter()) const {
+    double r = 0.0;
+    check(hdd_product_apply2(h_, id_.c_str(), mu.empty() ? nullptr : mu.data(), int(mu.size()), u.data(), v.data(), &r));
+    return r;
+  }
+  double induced_norm(const Vector& u, const Parameter& mu = Parameter()) const {
+    const double s = apply2(u, u, mu);
+    return s > 0.0 ? std::sqrt(s) : 0.0;
+  }
+ private:
+  void info(int* n, int* a, int* v) const { check(hdd_product_num_components(h_, id_.c_str(), n, a, v)); }
+  hdd_swipdg* h_;
+  std::string id_;
+};
+
+// Discretizations::SWIPDG< GridType, layer, double, 1, polOrder > and BlockSWIPDG share this class: a grid with
 // cell_subdomain is the multiscale grid of BlockSWIPDG (boundary info forced to AllDirichlet there,
 // discretizations/block-swipdg.hh:110,237).
 class SWIPDG {
@@ -205,8 +239,8 @@ class SWIPDG {
   static std::string static_id() { return "hdd.linearelliptic.discretizations.swipdg"; }
 
   SWIPDG(const Grid& grid, const Problem& problem, int polorder = 1, int device = 0, hdd_comm* comm = nullptr,
-         int64_t cell_begin = 0, int64_t cell_end = -1)
-      : n_loc_(grid.n_loc()) {
+         int64_t cell_begin = 0, int64_t cell_end = -1, const std::vector<std::string>& only_these_products = {})
+      : n_loc_(grid.kind == HDD_SIMPLEX2D ? (polorder + 1) * (polorder + 2) / 2 : (polorder + 1) * (polorder + 1)) {
     if (cell_end < 0) cell_end = grid.n_cells();
     check(hdd_mesh_create(grid.kind, grid.n_cells(), grid.n_verts(), grid.xy.data(), grid.cell_verts.data(),
                           grid.cell_neigh.data(), grid.cell_subdomain.empty() ? nullptr : grid.cell_subdomain.data(),
@@ -221,7 +255,13 @@ class SWIPDG {
       p.parameter_name = problem.parameter_name.empty() ? nullptr : problem.parameter_name.c_str();
       p.parameter_size = problem.parameter_size;
       check(hdd_swipdg_create(mesh_, polorder, &p, &h_));
+      if (!only_these_products.empty()) {
+        std::vector<const char*> ids;
+        for (const auto& id : only_these_products) ids.push_back(id.c_str());
+        check(hdd_swipdg_only_these_products(h_, ids.data(), int(ids.size())));
+      }
     } catch (...) {
+      if (h_) hdd_swipdg_destroy(h_);
       hdd_mesh_destroy(mesh_);
       throw;
     }
@@ -254,6 +294,30 @@ class SWIPDG {
     Vector y(x.size());
     check(hdd_apply(h_, mu.empty() ? nullptr : mu.data(), int(mu.size()), x.data(), y.data()));
     return y;
+  }
+
+  // products (discretizations/base.hh:272-291)
+  std::vector<std::string> available_products() const {
+    const char* const* t = nullptr; int n = 0; check(hdd_products_available(h_, &t, &n));
+    return std::vector<std::string>(t, t + n);
+  }
+  Product get_product(const std::string& id) const { return Product(h_, id); }
+  void pattern_volume(std::vector<int64_t>& rowptr, std::vector<int32_t>& col) const {
+    int64_t n = 0, nnz = 0; const int64_t* rp = nullptr; const int32_t* cl = nullptr;
+    check(hdd_pattern_volume(h_, &n, &nnz, &rp, &cl));
+    rowptr.resize(size_t(n) + 1); col.resize(size_t(nnz));
+    check(hdd_copy_to_host(h_, rowptr.data(), rp, rowptr.size() * sizeof(int64_t)));
+    check(hdd_copy_to_host(h_, col.data(), cl, col.size() * sizeof(int32_t)));
+  }
+  // {L2, H1_semi, energy} norms of vector - exact (test/linearelliptic-swipdg.hh:267-290); exact solution and its
+  // gradient as Expression strings in x[0], x[1]
+  std::map<std::string, double> error_norms(const Vector& vector, const std::string& exact, const std::string& exact_dx,
+                                            const std::string& exact_dy, int order = 5,
+                                            const Parameter& mu = Parameter()) const {
+    double out[3] = {0.0, 0.0, 0.0};
+    check(hdd_error_norms(h_, vector.data(), exact.c_str(), exact_dx.c_str(), exact_dy.c_str(), order,
+                          mu.empty() ? nullptr : mu.data(), int(mu.size()), out));
+    return {{"L2", out[0]}, {"H1_semi", out[1]}, {"energy", out[2]}};
   }
 
   // solve (CachedDefault::solve + ContainerBasedDefault::uncached_solve, discretizations/base.hh:151-178,327-367)

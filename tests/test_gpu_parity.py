@@ -627,3 +627,28 @@ def _bulk_copy_case(g, polorder):
     xg = np.empty(d.num_dofs())
     capi.check(capi.lib().hdd_copy_to_host(d._h, capi.ptr(xg), xp, C.c_size_t(xg.nbytes)))
     assert rel(xg, x10) <= 1e-11
+
+
+@pytest.mark.parametrize("level", [0, 1, 2, 3])
+def test_sgrid_goldens_entirely_on_the_device(gpu, level):
+    """the committed SGrid expectations (test/linearelliptic-swipdg-expectations_esv2007_2dsgrid.cxx:31-36) reproduced
+    without the oracle: assembly, multigrid-preconditioned CG and the error norms all run on the GPU"""
+    n = 8 * 2 ** level
+    d = hdd.SWIPDG(grids.cube(n), problems.ESV2007())
+    d.init()
+    d.solve({"type": "cg.mg", "precision": 1e-12, "max_iter": 1000})
+    e = d.error_norms(*problems.ESV2007_EXACT, order=7)
+    assert abs(e["L2"] - [1.13e-02, 2.90e-03, 7.41e-04, 1.88e-04][level]) <= 0.006 * e["L2"]
+    assert abs(e["H1_semi"] - [2.77e-01, 1.39e-01, 6.98e-02, 3.50e-02][level]) <= 0.006 * e["H1_semi"]
+
+
+@pytest.mark.parametrize("level", [0, 1, 2])
+def test_alu_error_goldens_on_the_device(gpu, level):
+    """test/linearelliptic-swipdg-expectations_esv2007_2daluconform.cxx:32-41 (L2, H1_semi, energy) with device norms"""
+    d = hdd.SWIPDG(grids.simplex(4 * 2 ** level), problems.ESV2007())
+    d.init()
+    d.solve({"type": "cg.blockdiagonal", "precision": 1e-12, "max_iter": 100000})
+    e = d.error_norms(*problems.ESV2007_EXACT, order=5)
+    gold = {"L2": [1.83e-02, 4.53e-03, 1.12e-03], "H1_semi": [3.28e-01, 1.62e-01, 8.04e-02], "energy": [3.28e-01, 1.62e-01, 8.04e-02]}
+    for key in gold:
+        assert abs(e[key] - gold[key][level]) <= 0.006 * gold[key][level]
