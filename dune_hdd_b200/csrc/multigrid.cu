@@ -186,8 +186,8 @@ __global__ void __launch_bounds__(kMgThreads)
 // ---- V-cycle kernels.  done: convergence latch of the CG iteration that owns this application (see k_cg_*) ----------
 // pre-smoothing from a zero guess, x = w D^-1 b, fused with the residual r = b - A x
 __global__ void __launch_bounds__(kMgThreads)
-    k_mg_pre(const int* done, const double* __restrict__ S, int nx, int ny, const double* __restrict__ b,
-             double* __restrict__ x, double* __restrict__ r) {
+    k_mg_pre(const int* done, const double* __restrict__ S, const double* __restrict__ dinv, int nx, int ny,
+             const double* __restrict__ b, double* __restrict__ x, double* __restrict__ r) {
   if (done && *done) return;
   const int nx1 = nx + 1;
   const int64_t nv = int64_t(nx1) * (ny + 1);
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kMgThreads)
       const int jx = ix + ex, jy = iy + ey;
       if (jx < 0 || jy < 0 || jx > nx || jy > ny) continue;
       const int64_t j = i + ex + int64_t(ey) * nx1;
-      const double xj = kOmega * __ldg(b + j) / __ldg(S + 4 * nv + j);
+      const double xj = __ldg(dinv + j) * __ldg(b + j);  // dinv = w / diagonal: no division in the sweep
       ax = fma(__ldg(S + ((ey + 1) * 3 + ex + 1) * nv + i), xj, ax);
       if (ex == 0 && ey == 0) x[i] = xj;
     }
@@ -253,8 +253,8 @@ __global__ void __launch_bounds__(kMgThreads)
 
 // post-smoothing: y = x + w D^-1 (b - A x)
 __global__ void __launch_bounds__(kMgThreads)
-    k_mg_post(const int* done, const double* __restrict__ S, int nx, int ny, const double* __restrict__ b,
-              const double* __restrict__ x, double* __restrict__ y) {
+    k_mg_post(const int* done, const double* __restrict__ S, const double* __restrict__ dinv, int nx, int ny,
+              const double* __restrict__ b, const double* __restrict__ x, double* __restrict__ y) {
   if (done && *done) return;
   const int nx1 = nx + 1;
   const int64_t nv = int64_t(nx1) * (ny + 1);
@@ -270,7 +270,13 @@ __global__ void __launch_bounds__(kMgThreads)
       if (jx < 0 || jy < 0 || jx > nx || jy > ny) continue;
       ax = fma(__ldg(S + ((ey + 1) * 3 + ex + 1) * nv + i), __ldg(x + i + ex + int64_t(ey) * nx1), ax);
     }
-  y[i] = x[i] + kOmega * (b[i] - ax) / __ldg(S + 4 * nv + i);
+  y[i] = fma(__ldg(dinv + i), b[i] - ax, x[i]);
+}
+
+// dinv = w / diagonal of the level operator
+__global__ void k_mg_dinv(const double* __restrict__ S, int64_t nv, double* __restrict__ dinv) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < nv) dinv[i] = kOmega / S[4 * nv + i];
 }
 
 // coarsest grid: x = A^-1 b with the dense inverse, one thread per row
@@ -342,7 +348,7 @@ __global__ void __launch_bounds__(kMgThreads)
 struct MgLevel {
   int nx = 0, ny = 0;
   int64_t nv = 0;
-  DevBuf<double> S, b, x, r, y;
+  DevBuf<double> S, dinv, b, x, r, y;
 };
 
 struct MgHierarchy {
@@ -397,6 +403,10 @@ static void build_hierarchy(hdd_swipdg* h, MgHierarchy& H, int nx, int ny) {
     k_rap<<<blocks_for(c.nv), kMgThreads, 0, s>>>(f.S.p, f.nx, f.ny, c.S.p);
     count_launch();
   }
+  for (auto& L : H.levels) {
+    k_mg_dinv<<<blocks_for(L->nv), kMgThreads, 0, s>>>(L->S.p, L->nv, L->dinv.p);
+    count_launch();
+  }
   // dense inverse of the coarsest operator (s.p.d.), Gauss-Jordan on the host
   MgLevel& C = *H.levels.back();
   if (C.nv > kMaxCoarse)
@@ -440,7 +450,7 @@ static void vcycle(MgHierarchy& H, const int* done, cudaStream_t s) {
   for (int l = 0; l + 1 < nl; ++l) {
     MgLevel& L = *H.levels[size_t(l)];
     MgLevel& Cn = *H.levels[size_t(l) + 1];
-    k_mg_pre<<<blocks_for(L.nv), kMgThreads, 0, s>>>(done, L.S.p, L.nx, L.ny, L.b.p, L.x.p, L.r.p);
+    k_mg_pre<<<blocks_for(L.nv), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, L.b.p, L.x.p, L.r.p);
     k_mg_restrict<<<blocks_for(Cn.nv), kMgThreads, 0, s>>>(done, L.r.p, L.nx, L.ny, Cn.b.p);
     count_launch(2);
   }
@@ -451,7 +461,7 @@ static void vcycle(MgHierarchy& H, const int* done, cudaStream_t s) {
     MgLevel& L = *H.levels[size_t(l)];
     MgLevel& Cn = *H.levels[size_t(l) + 1];
     k_mg_prolong_add<<<blocks_for(L.nv), kMgThreads, 0, s>>>(done, Cn.x.p, L.nx, L.ny, L.x.p);
-    k_mg_post<<<blocks_for(L.nv), kMgThreads, 0, s>>>(done, L.S.p, L.nx, L.ny, L.b.p, L.x.p, L.y.p);
+    k_mg_post<<<blocks_for(L.nv), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, L.b.p, L.x.p, L.y.p);
     count_launch(2);
     std::swap(L.x.p, L.y.p);  // the smoothed iterate is the level's x from here on
   }
@@ -485,6 +495,7 @@ void mg_setup(hdd_swipdg* h, const double* vals) {
       L->ny = m->sy;
       L->nv = nv;
       L->S.alloc(size_t(9) * nv);
+      L->dinv.alloc(size_t(nv));
       L->b.alloc(size_t(nv));
       L->x.alloc(size_t(nv));
       L->r.alloc(size_t(nv));
@@ -501,6 +512,7 @@ void mg_setup(hdd_swipdg* h, const double* vals) {
         C->ny = ly;
         C->nv = lv;
         C->S.alloc(size_t(9) * lv);
+        C->dinv.alloc(size_t(lv));
         C->b.alloc(size_t(lv));
         C->x.alloc(size_t(lv));
         C->r.alloc(size_t(lv));
