@@ -10,6 +10,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 #include "kernels.hpp"
@@ -468,8 +469,14 @@ __global__ void __launch_bounds__(kThreads, MINB)
                     double* __restrict__ vals) {
   using G = Elem<KIND, P>;
   constexpr int NL = G::NL, NF = G::NF;
-  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (t >= int64_t(m.n_own) * NL) return;
+  // The rows of the CTA are one contiguous range of the value array.  Written straight from the registers every store
+  // instruction would touch 32 sectors for 8 bytes each (four partial writes per sector: the L2 request rate, not the
+  // fp64 pipe, bounded the first version); the rows are staged in shared memory and written out coalesced instead.
+  __shared__ double stage[kThreads * (NF + 1) * NL];
+  const int64_t n_rows = int64_t(m.n_own) * NL;
+  const int64_t t_first = int64_t(blockIdx.x) * blockDim.x;
+  const bool live = t_first + threadIdx.x < n_rows;
+  const int64_t t = live ? t_first + threadIdx.x : n_rows - 1;  // idle threads of the last CTA recompute its last row
   const int k = int(t / NL), i = int(t % NL);
   const int c = m.own0 + k;
   G g;
@@ -479,7 +486,15 @@ __global__ void __launch_bounds__(kThreads, MINB)
   int nb[NF];
   load_neigh<NF>(m.neigh, k, nb);
   const int nblk = block_count<NF>(nb);
-  double* row = vals + m.blk_start[k] * (NL * NL) + int64_t(i) * nblk * NL;
+  int64_t base;  // first value of the CTA's first row
+  {
+    const int kf = int(t_first / NL), jf = int(t_first % NL);
+    int nbf[NF];
+    load_neigh<NF>(m.neigh, kf, nbf);
+    base = __ldg(m.blk_start + kf) * (NL * NL) + int64_t(jf) * block_count<NF>(nbf) * NL;
+  }
+  const int64_t row_off = m.blk_start[k] * (NL * NL) + int64_t(i) * nblk * NL;
+  double* row = stage + (row_off - base);
   double a_self = 0.0;
   if constexpr (FK == HDD_FN_CONSTANT) a_self = fn.value;
   if constexpr (FK == HDD_FN_CELLWISE) a_self = __ldg(fn.cell + c);
@@ -583,14 +598,28 @@ __global__ void __launch_bounds__(kThreads, MINB)
           for (int j = 0; j < NL; ++j) E[j] = fma(-phii * wpen, ph[j], E[j]);
         }
       }
-      double* dst = row + block_slot<NF>(c, nb, n) * NL;
+      if (live) {
+        double* dst = row + block_slot<NF>(c, nb, n) * NL;
 #pragma unroll
-      for (int j = 0; j < NL; ++j) dst[j] = E[j];
+        for (int j = 0; j < NL; ++j) dst[j] = E[j];
+      }
     }
   }
-  double* dst = row + block_slot<NF>(c, nb, c) * NL;
+  if (live) {
+    double* dst = row + block_slot<NF>(c, nb, c) * NL;
 #pragma unroll
-  for (int j = 0; j < NL; ++j) dst[j] = D[j];
+    for (int j = 0; j < NL; ++j) dst[j] = D[j];
+  }
+  __syncthreads();
+  // end of the CTA's last row
+  const int64_t t_last = min(t_first + int64_t(blockDim.x), n_rows) - 1;
+  const int kl = int(t_last / NL), il = int(t_last % NL);
+  int nbl[NF];
+  load_neigh<NF>(m.neigh, kl, nbl);
+  const int nblkl = block_count<NF>(nbl);
+  const int64_t total = __ldg(m.blk_start + kl) * (NL * NL) + int64_t(il + 1) * nblkl * NL - base;
+  double* out = vals + base;
+  for (int64_t q = threadIdx.x; q < total; q += blockDim.x) out[q] = stage[q];
 }
 
 // Volume-pattern products (discretizations/swipdg.hh:359-443): one dense n_loc x n_loc block per cell, one thread per

@@ -283,16 +283,28 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
     const bool need_verts = !whole || kind == HDD_SIMPLEX2D;
     std::vector<int32_t> cvl(need_verts ? size_t(m->n_loc) * nl : 0);
     if (need_verts) {
-      std::vector<int32_t> dense(size_t(n_verts), -1);  // global vertex -> local vertex, first-touch order
-      int32_t nvl = 0;
-      for (int32_t lc = 0; lc < m->n_loc; ++lc) {
-        const int32_t* gv = cell_verts + int64_t(m->cgid[size_t(lc)]) * nl;
-        for (int i = 0; i < nl; ++i) {
-          int32_t& id = dense[size_t(gv[i])];
-          if (id < 0) id = nvl++;
-          cvl[size_t(lc) * nl + i] = id;
+      // global vertex -> local vertex: ascending global id over the vertices the local cells touch (threaded mark,
+      // serial prefix sum over the vertices, threaded map)
+      std::vector<int32_t> dense(size_t(n_verts), 0);
+      int32_t* dn = dense.data();
+      parallel_for(m->n_loc, [&](int64_t a, int64_t b) {
+        for (int64_t lc = a; lc < b; ++lc) {
+          const int32_t* gv = cell_verts + int64_t(m->cgid[size_t(lc)]) * nl;
+          for (int i = 0; i < nl; ++i) dn[size_t(gv[i])] = 1;  // same value from every thread
         }
+      });
+      int32_t nvl = 0;
+      for (int64_t v = 0; v < n_verts; ++v) {
+        const int32_t touched = dn[v];
+        dn[v] = touched ? nvl : -1;
+        nvl += touched;
       }
+      parallel_for(m->n_loc, [&](int64_t a, int64_t b) {
+        for (int64_t lc = a; lc < b; ++lc) {
+          const int32_t* gv = cell_verts + int64_t(m->cgid[size_t(lc)]) * nl;
+          for (int i = 0; i < nl; ++i) cvl[size_t(lc) * nl + i] = dn[size_t(gv[i])];
+        }
+      });
       m->n_verts_loc = nvl;
     }
     if (kind == HDD_SIMPLEX2D) {

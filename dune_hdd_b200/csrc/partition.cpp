@@ -17,14 +17,28 @@ void compute_halo(int nl, int64_t n_cells, int64_t n_verts, const int32_t* cell_
   halo_lo.clear();
   halo_hi.clear();
   if (cell_begin == 0 && cell_end == n_cells) return;
+  // threaded: both passes are full sweeps over the caller's arrays.  Marking stores the same value from every thread.
   std::vector<uint8_t> vmark(size_t(n_verts), 0);
-  for (int64_t c = cell_begin; c < cell_end; ++c)
-    for (int i = 0; i < nl; ++i) vmark[size_t(cell_verts[c * nl + i])] = 1;
-  for (int64_t c = 0; c < n_cells; ++c) {
-    if (c >= cell_begin && c < cell_end) continue;
-    bool touch = false;
-    for (int i = 0; i < nl; ++i) touch |= vmark[size_t(cell_verts[c * nl + i])] != 0;
-    if (touch) (c < cell_begin ? halo_lo : halo_hi).push_back(int32_t(c));
+  uint8_t* mark = vmark.data();
+  parallel_for(cell_end - cell_begin, [&](int64_t a, int64_t b) {
+    for (int64_t c = cell_begin + a; c < cell_begin + b; ++c)
+      for (int i = 0; i < nl; ++i) mark[size_t(cell_verts[c * nl + i])] = 1;
+  });
+  const int nt = worker_count(n_cells);
+  std::vector<std::vector<int32_t>> lo, hi;
+  lo.resize(size_t(nt));
+  hi.resize(size_t(nt));
+  parallel_for_indexed(n_cells, nt, [&](int t, int64_t a, int64_t b) {  // contiguous chunks in order => sorted output
+    for (int64_t c = a; c < b; ++c) {
+      if (c >= cell_begin && c < cell_end) continue;
+      bool touch = false;
+      for (int i = 0; i < nl; ++i) touch |= mark[size_t(cell_verts[c * nl + i])] != 0;
+      if (touch) (c < cell_begin ? lo : hi)[size_t(t)].push_back(int32_t(c));
+    }
+  });
+  for (int t = 0; t < nt; ++t) {
+    halo_lo.insert(halo_lo.end(), lo[size_t(t)].begin(), lo[size_t(t)].end());
+    halo_hi.insert(halo_hi.end(), hi[size_t(t)].begin(), hi[size_t(t)].end());
   }
 }
 
@@ -43,11 +57,17 @@ void compute_send_cells(int nl, int64_t n_verts, const int32_t* cell_verts, int6
     for (int32_t g : kv.second)
       for (int i = 0; i < nl; ++i) vmark[size_t(cell_verts[int64_t(g) * nl + i])] = 1;
     std::vector<int32_t>& out = send_cells[kv.first];
-    for (int64_t c = own_begin; c < own_end; ++c) {
-      bool touch = false;
-      for (int i = 0; i < nl; ++i) touch |= vmark[size_t(cell_verts[c * nl + i])] != 0;
-      if (touch) out.push_back(int32_t(c));
-    }
+    const int nt = worker_count(own_end - own_begin);
+    std::vector<std::vector<int32_t>> part;
+    part.resize(size_t(nt));
+    parallel_for_indexed(own_end - own_begin, nt, [&](int t, int64_t a, int64_t b) {
+      for (int64_t c = own_begin + a; c < own_begin + b; ++c) {
+        bool touch = false;
+        for (int i = 0; i < nl; ++i) touch |= vmark[size_t(cell_verts[c * nl + i])] != 0;
+        if (touch) part[size_t(t)].push_back(int32_t(c));
+      }
+    });
+    for (int t = 0; t < nt; ++t) out.insert(out.end(), part[size_t(t)].begin(), part[size_t(t)].end());
   }
 }
 
