@@ -198,6 +198,7 @@ struct hdd_swipdg {
   hdd::DevBuf<int64_t> vol_rowptr;
   hdd::DevBuf<int32_t> vol_col;
   hdd::DevBuf<double> prod_frozen, prod_tmp;
+  hdd::DevBuf<double> rhs_scratch;  // tables of the tensor-grid rhs path
 
   // solve workspace
   hdd::DevBuf<double> frozen, dinv, dinv_block, z, b, x, r, p, q, partial, tmp_local;

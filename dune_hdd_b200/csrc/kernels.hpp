@@ -32,9 +32,17 @@ void launch_assemble_penalty(const MeshView& m, const DevFn& factor_dev, int fac
 // 3 boundary_l2 (discretizations/swipdg.hh:359-443)
 void launch_assemble_block_product(const MeshView& m, int which, const DevFn& factor_dev, int factor_order, int polorder,
                                    double* values, cudaStream_t s);
-// b += L2Volume(force)
+// A logically structured (tensor-product) cube grid as the mesh detected it: cells per direction, vertex 0 of every
+// local cell, and scratch for the per-column / per-row tables of the separable-force fast path
+// (>= (nx + ny) * (2 + p + 1) doubles).
+struct TensorGridView {
+  int nx = 0, ny = 0;
+  const int32_t* cell_v0 = nullptr;
+  double* scratch = nullptr;
+};
+// b (+)= L2Volume(force).  accumulate = false overwrites b (no memset, no read-modify-write for the first term)
 void launch_rhs_volume(const MeshView& m, const DevFn& force_dev, int force_order, bool separable, int polorder,
-                       double* b, cudaStream_t s);
+                       bool accumulate, const TensorGridView* tg, double* b, cudaStream_t s);
 // b += DirichletBoundarySWIPDG(factor, tensor, dirichlet)
 void launch_rhs_dirichlet(const MeshView& m, const DevFn& factor_dev, int factor_order, const DevFn& dirichlet_dev,
                           int dirichlet_order, int polorder, double* b, cudaStream_t s);

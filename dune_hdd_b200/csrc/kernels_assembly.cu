@@ -686,7 +686,7 @@ __global__ void __launch_bounds__(kThreads)
 // K3a.  Functionals::L2Volume(force) (discretizations/swipdg.hh:253-271): rule of order(f) + p.
 template <int KIND, int P>
 __global__ void __launch_bounds__(kThreads)
-    k_rhs_volume(MeshView m, const __grid_constant__ DevFn fn, ElemRule vol, double* __restrict__ b) {
+    k_rhs_volume(MeshView m, const __grid_constant__ DevFn fn, ElemRule vol, int accumulate, double* __restrict__ b) {
   using G = Elem<KIND, P>;
   constexpr int NL = G::NL;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -706,13 +706,14 @@ __global__ void __launch_bounds__(kThreads)
     for (int i = 0; i < NL; ++i) acc[i] += fv * phi[i];
   }
 #pragma unroll
-  for (int i = 0; i < NL; ++i) b[size_t(NL) * k + i] += acc[i];
+  for (int i = 0; i < NL; ++i) b[size_t(NL) * k + i] = accumulate ? b[size_t(NL) * k + i] + acc[i] : acc[i];
 }
 
 // K3a', Q1 on axis-parallel cells with a separable force f(x,y) = g(x) h(y): the tensor Gauss rule needs only
 // n + n evaluations of the (transcendental) factors per cell instead of n * n of the full expression.
 __global__ void __launch_bounds__(kThreads)
-    k_rhs_volume_cube_separable(MeshView m, const __grid_constant__ DevFn fn, LineRule g1, double* __restrict__ b) {
+    k_rhs_volume_cube_separable(MeshView m, const __grid_constant__ DevFn fn, LineRule g1, int accumulate,
+                                double* __restrict__ b) {
   using G = Geo<HDD_CUBE2D>;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= m.n_own) return;
@@ -732,10 +733,87 @@ __global__ void __launch_bounds__(kThreads)
     sy0 = fma(fy[i], 1.0 - g1.x[i], sy0); sy1 = fma(fy[i], g1.x[i], sy1);
   }
   double* dst = b + size_t(4) * k;
-  dst[0] += g.detj * sx0 * sy0;
-  dst[1] += g.detj * sx1 * sy0;
-  dst[2] += g.detj * sx0 * sy1;
-  dst[3] += g.detj * sx1 * sy1;
+  double o0 = g.detj * sx0 * sy0, o1 = g.detj * sx1 * sy0, o2 = g.detj * sx0 * sy1, o3 = g.detj * sx1 * sy1;
+  if (accumulate) { o0 += dst[0]; o1 += dst[1]; o2 += dst[2]; o3 += dst[3]; }
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(o0), "d"(o1), "d"(o2), "d"(o3) : "memory");
+}
+
+// K3a'', tensor-product grid + separable force f = g(x) h(y): the one-dimensional moments
+//   SX[cx][a] = h_x sum_q w_q g(x_q) l_a(xi_q),  SY[cy][b] = h_y sum_q w_q h(y_q) l_b(eta_q)
+// depend on the column / row of the cell only, so they are evaluated once per column and row (nx + ny instead of
+// nx * ny evaluations of the transcendental factors) and the cell kernel is a pure stream: b_(a + (p+1) b) = SX_a SY_b.
+// Step 1 records x0 / hx per column and y0 / hy per row from the owned cells (every writer stores the same value).
+__global__ void k_rhs_tensor_geometry(MeshView m, const int32_t* __restrict__ cell_v0, int nx, double* __restrict__ tab) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m.n_own) return;
+  const int c = m.own0 + k;
+  const int v0 = __ldg(cell_v0 + c);
+  const int cx = v0 % (nx + 1), cy = v0 / (nx + 1);
+  const double2 lo = __ldg(reinterpret_cast<const double2*>(m.cgeo + size_t(4) * c));
+  const double2 hi = __ldg(reinterpret_cast<const double2*>(m.cgeo + size_t(4) * c) + 1);
+  double2* gx = reinterpret_cast<double2*>(tab);             // [nx]: x0, hx
+  double2* gy = reinterpret_cast<double2*>(tab) + nx;        // [ny]: y0, hy
+  gx[cx] = make_double2(lo.x, hi.x - lo.x);
+  gy[cy] = make_double2(lo.y, hi.y - lo.y);
+}
+
+template <int P>
+__global__ void k_rhs_tensor_moments(const __grid_constant__ DevFn fn, LineRule g1, int nx, int ny,
+                                     const double* __restrict__ geo, double* __restrict__ mom) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nx + ny) return;
+  const bool is_x = t < nx;
+  const double2 oh = reinterpret_cast<const double2*>(geo)[t];
+  double acc[P + 1];
+#pragma unroll
+  for (int a = 0; a <= P; ++a) acc[a] = 0.0;
+  for (int q = 0; q < g1.n; ++q) {
+    const double xi = g1.x[q];
+    const double pos = oh.x + oh.y * xi;
+    const double v[2] = {is_x ? pos : 0.0, is_x ? 0.0 : pos};
+    const double f = eval_program(is_x ? fn.px : fn.py, v) * g1.w[q];
+    if constexpr (P == 1) {
+      acc[0] = fma(f, 1.0 - xi, acc[0]);
+      acc[1] = fma(f, xi, acc[1]);
+    } else {
+      acc[0] = fma(f, (1.0 - xi) * (1.0 - 2.0 * xi), acc[0]);
+      acc[1] = fma(f, 4.0 * xi * (1.0 - xi), acc[1]);
+      acc[2] = fma(f, xi * (2.0 * xi - 1.0), acc[2]);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a <= P; ++a) mom[size_t(t) * (P + 1) + a] = fabs(oh.y) * acc[a];
+}
+
+template <int P>
+__global__ void __launch_bounds__(256)
+    k_rhs_tensor_cells(int32_t n_own, int32_t own0, const int32_t* __restrict__ cell_v0, int nx,
+                       const double* __restrict__ mom, int accumulate, double* __restrict__ b) {
+  constexpr int N1 = P + 1, NL = N1 * N1;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_own) return;
+  const int v0 = __ldg(cell_v0 + own0 + k);
+  const int cx = v0 % (nx + 1), cy = v0 / (nx + 1);
+  double sx[N1], sy[N1];
+#pragma unroll
+  for (int a = 0; a < N1; ++a) {
+    sx[a] = __ldg(mom + size_t(cx) * N1 + a);
+    sy[a] = __ldg(mom + size_t(nx + cy) * N1 + a);
+  }
+  double* dst = b + size_t(NL) * k;
+  if constexpr (P == 1) {
+    double o0 = sx[0] * sy[0], o1 = sx[1] * sy[0], o2 = sx[0] * sy[1], o3 = sx[1] * sy[1];
+    if (accumulate) { o0 += dst[0]; o1 += dst[1]; o2 += dst[2]; o3 += dst[3]; }
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(o0), "d"(o1), "d"(o2), "d"(o3) : "memory");
+  } else {
+#pragma unroll
+    for (int bb = 0; bb < N1; ++bb)
+#pragma unroll
+      for (int a = 0; a < N1; ++a) {
+        const double o = sx[a] * sy[bb];
+        dst[a + N1 * bb] = accumulate ? dst[a + N1 * bb] + o : o;
+      }
+  }
 }
 
 // K3b.  Functionals::DirichletBoundarySWIPDG (discretizations/swipdg.hh:273-332; SWIPDG::BoundaryRHS):
@@ -1029,17 +1107,37 @@ void launch_assemble_block_product(const MeshView& m, int which, const DevFn& fa
 }
 
 void launch_rhs_volume(const MeshView& m, const DevFn& force_dev, int force_order, bool separable, int polorder,
-                       double* b, cudaStream_t s) {
+                       bool accumulate, const TensorGridView* tg, double* b, cudaStream_t s) {
   if (m.n_own == 0) return;
+  const int acc = accumulate ? 1 : 0;
+  if (m.kind == HDD_CUBE2D && separable && tg && tg->nx > 0 && tg->scratch) {
+    // tensor-product grid: 1-d moments per column / row, then a pure streaming kernel
+    const LineRule g1 = line_rule(force_order + polorder);
+    const int nx = tg->nx, ny = tg->ny, n1 = polorder + 1;
+    double* geo = tg->scratch;                       // [2 * (nx + ny)]
+    double* mom = tg->scratch + 2 * size_t(nx + ny);  // [(nx + ny) * (p + 1)]
+    k_rhs_tensor_geometry<<<grid_for(m.n_own, 256), 256, 0, s>>>(m, tg->cell_v0, nx, geo);
+    if (polorder == 1) {
+      k_rhs_tensor_moments<1><<<grid_for(nx + ny, 128), 128, 0, s>>>(force_dev, g1, nx, ny, geo, mom);
+      k_rhs_tensor_cells<1><<<grid_for(m.n_own, 256), 256, 0, s>>>(m.n_own, m.own0, tg->cell_v0, nx, mom, acc, b);
+    } else {
+      k_rhs_tensor_moments<2><<<grid_for(nx + ny, 128), 128, 0, s>>>(force_dev, g1, nx, ny, geo, mom);
+      k_rhs_tensor_cells<2><<<grid_for(m.n_own, 256), 256, 0, s>>>(m.n_own, m.own0, tg->cell_v0, nx, mom, acc, b);
+    }
+    (void)n1;
+    count_launch(3);
+    HDD_CUDA(cudaGetLastError());
+    return;
+  }
   if (m.kind == HDD_CUBE2D && separable && polorder == 1) {
-    k_rhs_volume_cube_separable<<<grid_for(m.n_own, kThreads), kThreads, 0, s>>>(m, force_dev, line_rule(force_order + polorder), b);
+    k_rhs_volume_cube_separable<<<grid_for(m.n_own, kThreads), kThreads, 0, s>>>(m, force_dev, line_rule(force_order + polorder), acc, b);
     count_launch();
     HDD_CUDA(cudaGetLastError());
     return;
   }
   const ElemRule vol = element_rule(m.kind, force_order + polorder);
   dispatch_elem(m.kind, polorder, [&](auto kind, auto p) {
-    k_rhs_volume<decltype(kind)::value, decltype(p)::value><<<grid_for(m.n_own, kThreads), kThreads, 0, s>>>(m, force_dev, vol, b);
+    k_rhs_volume<decltype(kind)::value, decltype(p)::value><<<grid_for(m.n_own, kThreads), kThreads, 0, s>>>(m, force_dev, vol, acc, b);
   });
   count_launch();
   HDD_CUDA(cudaGetLastError());

@@ -134,11 +134,29 @@ void assemble_all(hdd_swipdg* h) {
   if (h->lhs_affine)
     launch_assemble_lhs(v, h->fn_h(h->lhs_affine->factor), h->lhs_affine->factor.kind, h->lhs_affine->factor.order, h->polorder,
                         h->lhs_affine->values.p, s);
+  TensorGridView tg;
+  if (m->sx > 0) {
+    tg.nx = m->sx;
+    tg.ny = m->sy;
+    tg.cell_v0 = m->cell_v0.p;
+    const size_t need = size_t(m->sx + m->sy) * (2 + h->polorder + 1);
+    if (h->rhs_scratch.n < need) h->rhs_scratch.alloc(need);
+    tg.scratch = h->rhs_scratch.p;
+  }
   auto do_vec = [&](VectorPart& part) {
-    part.values.zero(s);
+    // the first volume term overwrites the vector; only parts without one need the memset
+    bool written = false;
+    for (const RhsTerm& t : part.terms) written |= (t.kind == 0 && !t.f.zero);
+    if (!written) part.values.zero(s);
+    bool first = true;
+    for (const RhsTerm& t : part.terms)
+      if (t.kind == 0 && !t.f.zero) {
+        launch_rhs_volume(v, h->fn_h(t.f), t.f.order, t.f.separable, h->polorder, !first, &tg, part.values.p, s);
+        first = false;
+      }
     for (const RhsTerm& t : part.terms) {
       if (t.kind == 0) {
-        if (!t.f.zero) launch_rhs_volume(v, h->fn_h(t.f), t.f.order, t.f.separable, h->polorder, part.values.p, s);
+        continue;
       } else if (t.kind == 2) {
         if (!t.f.zero) launch_rhs_neumann(v, h->fn_h(t.f), t.f.order, h->polorder, part.values.p, s);
       } else {
@@ -813,6 +831,7 @@ int hdd_solve(hdd_swipdg* h, const char* type, double precision, int max_iter, c
       cached.exec = nullptr;
     }
     bool capture_failed = false;
+    double rr_prev = 1e300;
     int par = 0, launched = 0, batch = use_diag == 3 ? 8 : 16;
     bool first_batch = !cached.exec;  // a cached graph means every one-time set-up has already happened
     for (;;) {
@@ -858,7 +877,19 @@ int hdd_solve(hdd_swipdg* h, const char* type, double precision, int max_iter, c
       HDD_CUDA(cudaStreamSynchronize(s));
       if (h->sc_host->done[par]) break;
       if (launched > max_iter + batch) break;  // cannot happen: done latches at max_it
-      if (batch < 256 && use_diag != 3) batch *= 2;
+      // next batch: the iterations still needed at the convergence rate seen so far (iterations launched after
+      // convergence are no-ops, but they still cost their launch), at most twice the last batch and at most 256
+      {
+        const double rr = h->sc_host->rr, target = h->sc_host->tol2 * h->sc_host->bb;
+        int next = 2 * batch;
+        if (rr > 0.0 && rr < rr_prev && target > 0.0 && rr > target) {
+          const double per_it = std::log(rr / rr_prev) / batch;  // < 0
+          const double need = std::log(target / rr) / per_it;
+          if (need < double(next)) next = int(need) + 1;
+        }
+        rr_prev = rr;
+        batch = std::max(2, std::min(256, (next + 1) & ~1));
+      }
     }
     if (m->purely_neumann) launch_subtract_mean(h->x.p, h->n_rows, h->partial.p, h->sc.p, s);
     HDD_CUDA(cudaEventRecord(e1, s));
