@@ -282,7 +282,15 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
     // halo plan of a distributed mesh)
     const bool need_verts = !whole || kind == HDD_SIMPLEX2D;
     std::vector<int32_t> cvl(need_verts ? size_t(m->n_loc) * nl : 0);
-    if (need_verts) {
+    if (need_verts && kind == HDD_CUBE2D) {
+      // cubes have no vertex incidence (the Oswald pass exists on simplices only): the halo plan works on the global
+      // vertex ids of the local cells directly
+      parallel_for(m->n_loc, [&](int64_t a, int64_t b) {
+        for (int64_t lc = a; lc < b; ++lc)
+          std::memcpy(&cvl[size_t(lc) * nl], cell_verts + int64_t(m->cgid[size_t(lc)]) * nl, nl * sizeof(int32_t));
+      });
+      m->n_verts_loc = int32_t(n_verts);
+    } else if (need_verts) {
       // global vertex -> local vertex: ascending global id over the vertices the local cells touch (threaded mark,
       // serial prefix sum over the vertices, threaded map)
       std::vector<int32_t> dense(size_t(n_verts), 0);
@@ -515,6 +523,7 @@ int hdd_mesh_attach_comm(hdd_mesh* m, hdd_comm* c) {
     if (world_size == 1) return;
     Nccl& nc = Nccl::get();
     m->comm = c->comm;
+    PhaseTimer pt("hdd_mesh_attach", m->stream);
     // every rank learns every rank's owned range (2 doubles per rank through one all-reduce)
     DevBuf<double> ranges;
     ranges.alloc(size_t(world_size) + 1);
@@ -537,6 +546,7 @@ int hdd_mesh_attach_comm(hdd_mesh* m, hdd_comm* c) {
       HDD_CUDA(cudaMemcpyAsync(m->sub_diameter.data(), dia.p, m->sub_diameter.size() * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
       HDD_CUDA(cudaStreamSynchronize(m->stream));
     }
+    pt.lap("ranges + diameters");
     // halo plan.  Receive: halo cells sorted by global id are grouped by owner => contiguous ranges of the local
     // vector.  Send: owned cells sharing a vertex with a halo cell owned by that peer, sorted by global id - this is
     // exactly that peer's receive range, no index exchange needed.
@@ -570,6 +580,7 @@ int hdd_mesh_attach_comm(hdd_mesh* m, hdd_comm* c) {
       p.send_count = int64_t(idx.size()) - p.send_offset;
       m->peers.push_back(p);
     }
+    pt.lap("halo plan");
     m->send_idx.upload(idx.data(), idx.size(), m->stream);
     m->n_send_cells = int64_t(idx.size());
     m->send_buf.alloc(idx.size() * size_t(nl));
@@ -594,6 +605,7 @@ int hdd_mesh_attach_comm(hdd_mesh* m, hdd_comm* c) {
       HDD_CUDA(cudaStreamSynchronize(m->stream));
     }
     HDD_CUDA(cudaStreamSynchronize(m->stream));
+    pt.lap("peer tables");
   });
 }
 

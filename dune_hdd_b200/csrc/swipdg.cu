@@ -452,6 +452,7 @@ int hdd_swipdg_create(hdd_mesh* mesh, int polorder, const hdd_problem* problem, 
     if (!mesh || !problem) HDD_THROW(HDD_ERR_WRONG_INPUT, "mesh or problem is NULL");
     if (polorder != 1 && polorder != 2) HDD_THROW(HDD_ERR_NOT_IMPLEMENTED, "polorder " << polorder << " (p = 1 and p = 2 only)");
     mesh->set_device();
+    PhaseTimer pt("hdd_swipdg_create", mesh->stream);
     std::unique_ptr<hdd_swipdg> h(new hdd_swipdg);
     h->mesh = mesh;
     h->polorder = polorder;
@@ -546,6 +547,7 @@ int hdd_swipdg_create(hdd_mesh* mesh, int polorder, const hdd_problem* problem, 
     if (h->neumann.has_affine() && !h->neumann.affine.zero) affine_rhs().terms.push_back({2, h->neumann.affine, FnRef{}});
     if (h->lhs_comps.size() + 1 > size_t(kMaxParts) || h->rhs_comps.size() + 1 > size_t(kMaxParts))
       HDD_THROW(HDD_ERR_NOT_IMPLEMENTED, "more than " << kMaxParts - 1 << " affine components");
+    pt.lap("all");
     *out = h.release();
   });
 }
