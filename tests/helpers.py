@@ -1,7 +1,22 @@
 """Shared helpers of the parity tests: the same problem stated for the product (dune_hdd_b200) and for the oracle."""
+import json
+import os
+
 import numpy as np
 
 from oracle import oracle as o
+
+_GOLDEN = None
+
+
+def golden(stem, type, partitioning="-", mus="-"):
+    """A golden vector of the reference's own tests (tests/golden/reference_expectations.json, transcribed from the
+    reference's test/<stem>.cxx by tests/golden/extract_expectations.py): one value per refinement level."""
+    global _GOLDEN
+    if _GOLDEN is None:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_expectations.json")) as f:
+            _GOLDEN = json.load(f)
+    return _GOLDEN[stem][partitioning][mus][type]["values"]
 
 
 def oracle_mesh(grid):

@@ -10,7 +10,7 @@ import pytest
 import dune_hdd_b200 as hdd
 from dune_hdd_b200 import grids, problems
 from oracle import oracle as o
-from tests.helpers import direct_solve, oracle_mesh, oracle_system, rel
+from tests.helpers import direct_solve, golden, oracle_mesh, oracle_system, rel
 
 pytestmark = pytest.mark.gpu
 
@@ -72,15 +72,13 @@ def test_cg_iterates_follow_the_oracle_cg(gpu):
         assert rel(x, x_ref) <= 1e-11
 
 
-GOLDEN_ALU = {  # test/linearelliptic-swipdg-expectations_esv2007_2daluconform.cxx:32-57
-    "L2": [1.83e-02, 4.53e-03, 1.12e-03], "H1_semi": [3.28e-01, 1.62e-01, 8.04e-02],
-    "eta_NC_ESV2007": [1.66e-1, 7.89e-2, 3.91e-2], "eta_R_ESV2007": [7.23e-2, 1.82e-2, 4.54e-3],
-    "eta_DF_ESV2007": [3.55e-1, 1.76e-1, 8.73e-2], "eta_ESV2007": [4.49e-01, 2.07e-01, 9.91e-02],
-    "eta_ESV2007_alt": [5.93e-01, 2.73e-01, 1.31e-01]}
+_ALU_STEM = "linearelliptic-swipdg-expectations_esv2007_2daluconform"
+GOLDEN_ALU = {k: golden(_ALU_STEM, k) for k in ("L2", "H1_semi", "energy", "eta_NC_ESV2007", "eta_R_ESV2007",
+                                                  "eta_DF_ESV2007", "eta_ESV2007", "eta_ESV2007_alt")}
 
 
-def _digits3(x, golden):
-    return abs(x - golden) <= 0.006 * abs(golden)
+def _digits3(x, gold):
+    return abs(x - gold) <= 0.006 * abs(gold)
 
 
 @pytest.mark.parametrize("level", [0, 1, 2])
@@ -638,8 +636,9 @@ def test_sgrid_goldens_entirely_on_the_device(gpu, level):
     d.init()
     d.solve({"type": "cg.mg", "precision": 1e-12, "max_iter": 1000})
     e = d.error_norms(*problems.ESV2007_EXACT, order=7)
-    assert abs(e["L2"] - [1.13e-02, 2.90e-03, 7.41e-04, 1.88e-04][level]) <= 0.006 * e["L2"]
-    assert abs(e["H1_semi"] - [2.77e-01, 1.39e-01, 6.98e-02, 3.50e-02][level]) <= 0.006 * e["H1_semi"]
+    stem = "linearelliptic-swipdg-expectations_esv2007_2dsgrid"
+    assert abs(e["L2"] - golden(stem, "L2")[level]) <= 0.006 * e["L2"]
+    assert abs(e["H1_semi"] - golden(stem, "H1_semi")[level]) <= 0.006 * e["H1_semi"]
 
 
 @pytest.mark.parametrize("level", [0, 1, 2])
@@ -649,6 +648,6 @@ def test_alu_error_goldens_on_the_device(gpu, level):
     d.init()
     d.solve({"type": "cg.blockdiagonal", "precision": 1e-12, "max_iter": 100000})
     e = d.error_norms(*problems.ESV2007_EXACT, order=5)
-    gold = {"L2": [1.83e-02, 4.53e-03, 1.12e-03], "H1_semi": [3.28e-01, 1.62e-01, 8.04e-02], "energy": [3.28e-01, 1.62e-01, 8.04e-02]}
-    for key in gold:
-        assert abs(e[key] - gold[key][level]) <= 0.006 * gold[key][level]
+    stem = "linearelliptic-swipdg-expectations_esv2007_2daluconform"
+    for key in ("L2", "H1_semi", "energy"):
+        assert abs(e[key] - golden(stem, key)[level]) <= 0.006 * golden(stem, key)[level]

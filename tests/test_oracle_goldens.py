@@ -5,21 +5,23 @@ import numpy as np
 import pytest
 
 from oracle import oracle as o
-from tests.helpers import direct_solve
+from tests.helpers import direct_solve, golden
 
 
 def digits3(x, golden, slack=0.006):
     return abs(x - golden) <= slack * abs(golden)
 
 
+# the reference's committed expectations, read from tests/golden/reference_expectations.json
 # test/linearelliptic-swipdg-expectations_esv2007_2daluconform.cxx:32-57
-ALU = {"L2": [1.83e-02, 4.53e-03, 1.12e-03, 2.78e-04], "H1_semi": [3.28e-01, 1.62e-01, 8.04e-02, 4.01e-02],
-       "energy": [3.28e-01, 1.62e-01, 8.04e-02, 4.01e-02], "eta_NC": [1.66e-1, 7.89e-2, 3.91e-2, 1.95e-2],
-       "eta_R": [7.23e-2, 1.82e-2, 4.54e-3, 1.14e-3], "eta_DF": [3.55e-1, 1.76e-1, 8.73e-2, 4.35e-2],
-       "eta": [4.49e-01, 2.07e-01, 9.91e-02, 4.85e-02], "eff": [1.37, 1.28, 1.23, 1.21],
-       "eta_alt": [5.93e-01, 2.73e-01, 1.31e-01, 6.42e-02], "eff_alt": [1.81, 1.69, 1.63, 1.60]}
+_ALU = "linearelliptic-swipdg-expectations_esv2007_2daluconform"
+ALU = {key: golden(_ALU, name) for key, name in (
+    ("L2", "L2"), ("H1_semi", "H1_semi"), ("energy", "energy"), ("eta_NC", "eta_NC_ESV2007"), ("eta_R", "eta_R_ESV2007"),
+    ("eta_DF", "eta_DF_ESV2007"), ("eta", "eta_ESV2007"), ("eff", "eff_ESV2007"), ("eta_alt", "eta_ESV2007_alt"),
+    ("eff_alt", "eff_ESV2007_alt"))}
 # test/linearelliptic-swipdg-expectations_esv2007_2dsgrid.cxx:31-36
-SGRID = {"L2": [1.13e-02, 2.90e-03, 7.41e-04, 1.88e-04], "H1_semi": [2.77e-01, 1.39e-01, 6.98e-02, 3.50e-02]}
+_SG = "linearelliptic-swipdg-expectations_esv2007_2dsgrid"
+SGRID = {"L2": golden(_SG, "L2"), "H1_semi": golden(_SG, "H1_semi")}
 
 
 def solve_esv(mesh, factor=None):
@@ -69,11 +71,11 @@ def test_q1_volume_term_is_under_integrated_like_the_reference():
     assert abs(err["L2"] - 1.129e-2) < 2e-5 and abs(err["H1_semi"] - 2.770e-1) < 2e-4
 
 
-# test/linearelliptic-block-swipdg-expectations_esv2007_2daluconform.cxx:35-134 (level 0, 1)
-BLOCK = {1: {"eta_R_OS2014": [5.79e-01, 2.90e-01], "eta_OS2014": [1.10e+00, 5.45e-01], "eff": [3.35, 3.37]},
-         2: {"eta_R_OS2014": [2.89e-01, 1.45e-01], "eta_OS2014": [8.10e-01, 4.00e-01], "eff": [2.47, 2.47]},
-         4: {"eta_R_OS2014": [1.45e-01, 7.26e-02], "eta_OS2014": [6.65e-01, 3.27e-01], "eff": [2.03, 2.02]},
-         8: {"eta_R_OS2014": [7.23e-02, 3.63e-02], "eta_OS2014": [5.93e-01, 2.91e-01], "eff": [1.81, 1.80]}}
+# test/linearelliptic-block-swipdg-expectations_esv2007_2daluconform.cxx:35-134
+_BLK = "linearelliptic-block-swipdg-expectations_esv2007_2daluconform"
+BLOCK = {k: {"eta_R_OS2014": golden(_BLK, "eta_R_OS2014", "[%d %d 1]" % (k, k)),
+             "eta_OS2014": golden(_BLK, "eta_OS2014", "[%d %d 1]" % (k, k)),
+             "eff": golden(_BLK, "eff_OS2014", "[%d %d 1]" % (k, k))} for k in (1, 2, 4, 8)}
 
 
 def subdomain_eta_r(mesh, res2, amin, k):
@@ -109,8 +111,12 @@ def test_os2014_parametric_goldens_mu1(level):
     """test/linearelliptic-block-swipdg-expectations_os2014_2daluconform.cxx:170-212, [4 4 1], solve at mu = 1."""
     m = o.mesh_bisect(4, -1.0, 1.0, 2 + 2 * level)
     u, _ = solve_esv(m, o.os2014_factor(1.0))
-    gold = {(1.0, 1.0): {"eta_DF": [3.55e-1, 1.76e-1], "eta": [7.74e-01, 3.82e-01]},
-            (1.0, 0.1): {"eta_DF": [1.36, 1.33], "eta_DF_star": [4.13e-01, 2.05e-01], "eta_star": [5.50e-01, 2.71e-01]}}
+    os14 = "linearelliptic-block-swipdg-expectations_os2014_2daluconform"
+    gold = {(1.0, 1.0): {"eta_DF": golden(os14, "eta_DF_OS2014", "[4 4 1]", "1,1,1"),
+                         "eta": golden(os14, "eta_OS2014", "[4 4 1]", "1,1,1")},
+            (1.0, 0.1): {"eta_DF": golden(os14, "eta_DF_OS2014", "[4 4 1]", "1,1,0.1"),
+                         "eta_DF_star": golden(os14, "eta_DF_OS2014_*", "[4 4 1]", "1,1,0.1"),
+                         "eta_star": golden(os14, "eta_OS2014_*", "[4 4 1]", "1,1,0.1")}}
     for (mu, mu_hat), g in gold.items():
         ind = o.indicators(m, u, o.esv2007_force(), o.os2014_factor(mu), a_hat=o.os2014_factor(mu_hat),
                            a_bar=o.os2014_factor(mu), a_min=o.os2014_factor(0.1), a_max=o.os2014_factor(1.0))
