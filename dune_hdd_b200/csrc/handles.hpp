@@ -55,7 +55,9 @@ struct hdd_mesh {
   int32_t n_verts_loc = 0;
 
   // host copies needed after creation
-  std::vector<int32_t> cgid;       // [n_loc]
+  std::vector<int32_t> cgid;       // [n_loc] global id of every local cell; empty for a whole mesh (identity)
+  bool whole = true;               // this rank owns every cell
+  int32_t gid(int32_t lc) const { return whole ? lc : cgid[size_t(lc)]; }
   int n_subdomains = 1;
   std::vector<int64_t> sub_cell_offsets;             // [n_subdomains+1] global cell offsets
   std::vector<int64_t> sub_dof_offsets;              // nl * sub_cell_offsets

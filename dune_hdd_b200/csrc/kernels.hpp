@@ -8,8 +8,15 @@ namespace hdd {
 
 // ---- K0: device-side localisation of the host grid -------------------------------------------------------------------
 // cgeo[c] from (xy, cell_verts); flag |= 1 if a cube cell is not an axis-parallel rectangle
-void launch_build_geometry(int kind, int32_t n_loc, const double* xy, const int32_t* cell_verts_local, double* cgeo,
-                           int32_t* flag, cudaStream_t s);
+// (also validates the vertex ids: flag |= 4 if one is out of range)
+void launch_build_geometry(int kind, int32_t n_loc, int32_t n_verts, const double* xy, const int32_t* cell_verts_local,
+                           double* cgeo, int32_t* flag, cudaStream_t s);
+// whole mesh on one GPU: flag |= 8 if a neighbour id is out of range; out[i] = i
+void launch_validate_neighbours(const int32_t* neigh, int64_t count, int32_t n_cells, int32_t* flag, cudaStream_t s);
+void launch_iota(int32_t* out, int32_t n, cudaStream_t s);
+// subdomain offsets and neighbouring-subdomain byte matrix of a whole mesh; flag |= 16 if not subdomain-major
+void launch_subdomain_structure(const int32_t* sub, const int32_t* neigh, int nf, int32_t n_cells, int n_sub,
+                                int64_t* offsets, uint8_t* adj, int32_t* flag, cudaStream_t s);
 // in place: global neighbour ids of the owned cells -> local ids ([lower halo | owned | upper halo]); flag |= 2 if missing
 void launch_localize_neighbours(int32_t* neigh, int64_t count, int32_t cell_begin, int32_t cell_end, const int32_t* halo,
                                 int32_t n_lo, int32_t n_hi, int32_t* flag, cudaStream_t s);

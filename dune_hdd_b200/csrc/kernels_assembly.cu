@@ -34,22 +34,65 @@ __device__ __forceinline__ void load_neigh(const int32_t* neigh, int k, int* nb)
   }
 }
 
-__global__ void k_build_geometry(int kind, int32_t n_loc, const double* __restrict__ xy, const int32_t* __restrict__ cv,
-                                 double* __restrict__ cgeo, int32_t* flag) {
+__global__ void k_build_geometry(int kind, int32_t n_loc, int32_t n_verts, const double* __restrict__ xy,
+                                 const int32_t* __restrict__ cv, double* __restrict__ cgeo, int32_t* flag) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_loc) return;
   const double2* p = reinterpret_cast<const double2*>(xy);
   if (kind == HDD_SIMPLEX2D) {
     double2* out = reinterpret_cast<double2*>(cgeo + size_t(6) * c);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) out[i] = __ldg(p + cv[size_t(3) * c + i]);
+    for (int i = 0; i < 3; ++i) {
+      const int v = cv[size_t(3) * c + i];
+      if (v < 0 || v >= n_verts) { atomicOr(flag, 4); return; }  // index validation happens here, not on the host
+      out[i] = __ldg(p + v);
+    }
   } else {
     const int4 v = __ldg(reinterpret_cast<const int4*>(cv) + c);
+    if (v.x < 0 || v.y < 0 || v.z < 0 || v.w < 0 || v.x >= n_verts || v.y >= n_verts || v.z >= n_verts || v.w >= n_verts) {
+      atomicOr(flag, 4);
+      return;
+    }
     const double2 a = __ldg(p + v.x), b = __ldg(p + v.y), d = __ldg(p + v.z), e = __ldg(p + v.w);
     if (a.x != d.x || b.x != e.x || a.y != b.y || d.y != e.y) atomicOr(flag, 1);
     double2* out = reinterpret_cast<double2*>(cgeo + size_t(4) * c);
     out[0] = a;
     out[1] = e;
+  }
+}
+
+// whole mesh on one GPU: neighbour ids are used as they are; range check and global ids = identity
+__global__ void k_validate_neighbours(const int32_t* __restrict__ neigh, int64_t count, int32_t n_cells, int32_t* flag) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const int32_t g = neigh[t];
+  if (g < -1 || g >= n_cells) atomicOr(flag, 8);
+}
+
+__global__ void k_iota(int32_t* __restrict__ out, int32_t n) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = t;
+}
+
+// subdomain structure of a whole mesh (grid::Multiscale view): offsets of the subdomain-major cell ranges, the
+// neighbouring-subdomain relation as a byte matrix; flag |= 16 if the numbering is not subdomain-major
+__global__ void k_subdomain_structure(const int32_t* __restrict__ sub, const int32_t* __restrict__ neigh, int nf,
+                                      int32_t n_cells, int n_sub, int64_t* __restrict__ offsets, uint8_t* __restrict__ adj,
+                                      int32_t* flag) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cells) return;
+  const int s = sub[c];
+  if (s < 0 || s >= n_sub) { atomicOr(flag, 16); return; }
+  if (c + 1 < n_cells) {
+    const int d = sub[c + 1] - s;
+    if (d < 0 || d > 1) atomicOr(flag, 16);
+    if (d == 1) offsets[s + 1] = c + 1;
+  }
+  for (int f = 0; f < nf; ++f) {
+    const int g = neigh[size_t(nf) * c + f];
+    if (g < 0 || g >= n_cells) continue;
+    const int t = sub[g];
+    if (t != s && t >= 0 && t < n_sub) adj[size_t(s) * n_sub + t] = 1;
   }
 }
 
@@ -93,20 +136,18 @@ __global__ void k_fill_csr(MeshView m, int64_t* __restrict__ rowptr, int32_t* __
   const int64_t start = m.blk_start[k] * (NL * NL) + int64_t(i) * nblk * NL;
   rowptr[t] = start;
   if (t == int64_t(m.n_own) * NL - 1) rowptr[t + 1] = m.blk_start[m.n_own] * (NL * NL);
-  {
-    const int slot = block_slot<NF>(self, nb, self);
-    const int g = __ldg(m.cgid + self);
-#pragma unroll
-    for (int j = 0; j < NL; ++j) col[start + slot * NL + j] = NL * g + j;
-  }
-#pragma unroll
-  for (int f = 0; f < NF; ++f)
-    if (nb[f] >= 0) {
-      const int slot = block_slot<NF>(self, nb, nb[f]);
-      const int g = __ldg(m.cgid + nb[f]);
+  auto write_block = [&](int slot, int g) {
+    if constexpr (NL == 4) {  // one 16-byte store per block instead of four 4-byte ones
+      *reinterpret_cast<int4*>(col + start + slot * 4) = make_int4(4 * g, 4 * g + 1, 4 * g + 2, 4 * g + 3);
+    } else {
 #pragma unroll
       for (int j = 0; j < NL; ++j) col[start + slot * NL + j] = NL * g + j;
     }
+  };
+  write_block(block_slot<NF>(self, nb, self), __ldg(m.cgid + self));
+#pragma unroll
+  for (int f = 0; f < NF; ++f)
+    if (nb[f] >= 0) write_block(block_slot<NF>(self, nb, nb[f]), __ldg(m.cgid + nb[f]));
 }
 
 template <int NL>
@@ -941,10 +982,31 @@ __global__ void k_extract_dinv(MeshView m, const double* __restrict__ values, in
 
 }  // namespace
 
-void launch_build_geometry(int kind, int32_t n_loc, const double* xy, const int32_t* cell_verts_local, double* cgeo,
-                           int32_t* flag, cudaStream_t s) {
+void launch_build_geometry(int kind, int32_t n_loc, int32_t n_verts, const double* xy, const int32_t* cell_verts_local,
+                           double* cgeo, int32_t* flag, cudaStream_t s) {
   if (n_loc == 0) return;
-  k_build_geometry<<<grid_for(n_loc, 256), 256, 0, s>>>(kind, n_loc, xy, cell_verts_local, cgeo, flag);
+  k_build_geometry<<<grid_for(n_loc, 256), 256, 0, s>>>(kind, n_loc, n_verts, xy, cell_verts_local, cgeo, flag);
+  count_launch();
+  HDD_CUDA(cudaGetLastError());
+}
+
+void launch_validate_neighbours(const int32_t* neigh, int64_t count, int32_t n_cells, int32_t* flag, cudaStream_t s) {
+  if (count == 0) return;
+  k_validate_neighbours<<<grid_for(count, 256), 256, 0, s>>>(neigh, count, n_cells, flag);
+  count_launch();
+  HDD_CUDA(cudaGetLastError());
+}
+
+void launch_iota(int32_t* out, int32_t n, cudaStream_t s) {
+  if (n == 0) return;
+  k_iota<<<grid_for(n, 256), 256, 0, s>>>(out, n);
+  count_launch();
+  HDD_CUDA(cudaGetLastError());
+}
+
+void launch_subdomain_structure(const int32_t* sub, const int32_t* neigh, int nf, int32_t n_cells, int n_sub,
+                                int64_t* offsets, uint8_t* adj, int32_t* flag, cudaStream_t s) {
+  k_subdomain_structure<<<grid_for(n_cells, 256), 256, 0, s>>>(sub, neigh, nf, n_cells, n_sub, offsets, adj, flag);
   count_launch();
   HDD_CUDA(cudaGetLastError());
 }

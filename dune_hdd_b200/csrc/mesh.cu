@@ -184,8 +184,9 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
     cudaStream_t s = m->stream;
     PhaseTimer pt("hdd_mesh_create", s);
 
-    // ---- validate indices (threaded: these are the only full passes over the host arrays) -------------------
-    {
+    // ---- index validation: on the device for a whole mesh (inside the geometry / neighbour kernels); a distributed
+    // mesh walks the caller's arrays on the host below (halo search), so those are checked here first
+    if (!whole) {
       std::atomic<int64_t> bad_vertex{-1}, bad_neigh{-1};
       parallel_for(n_cells, [&](int64_t c0, int64_t c1) {
         for (int64_t c = c0; c < c1; ++c)
@@ -198,7 +199,6 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
       if (bad_vertex >= 0) HDD_THROW(HDD_ERR_INDEX_OUT_OF_RANGE, "vertex id out of range in cell " << bad_vertex.load());
       if (bad_neigh >= 0) HDD_THROW(HDD_ERR_INDEX_OUT_OF_RANGE, "neighbour id out of range in cell " << bad_neigh.load());
     }
-
     pt.lap("validate indices");
     // ---- halo: every non-owned cell sharing a vertex with an owned cell (superset of the face neighbours the
     // SpMV needs; the Oswald interpolation needs all cells around a vertex)
@@ -207,8 +207,9 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
     m->own0 = int32_t(halo_lo.size());
     m->n_own = int32_t(n_own);
     m->n_loc = int32_t(halo_lo.size() + n_own + halo_hi.size());
-    m->cgid.resize(size_t(m->n_loc));
-    {
+    m->whole = whole;
+    if (!whole) {
+      m->cgid.resize(size_t(m->n_loc));
       std::copy(halo_lo.begin(), halo_lo.end(), m->cgid.begin());
       int32_t* own = m->cgid.data() + halo_lo.size();
       parallel_for(n_own, [&](int64_t a, int64_t b) {
@@ -243,7 +244,7 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
       DevBuf<int32_t> d_flag;
       d_flag.alloc(1);
       d_flag.zero(s);
-      launch_build_geometry(kind, m->n_loc, d_xy.p, d_cv.p, m->cgeo.p, d_flag.p, s);
+      launch_build_geometry(kind, m->n_loc, int32_t(n_verts), d_xy.p, d_cv.p, m->cgeo.p, d_flag.p, s);
       m->neigh.alloc(size_t(n_own) * nf);
       if (n_own)
         HDD_CUDA(cudaMemcpyAsync(m->neigh.p, cell_neigh + cell_begin * nf, size_t(n_own) * nf * sizeof(int32_t),
@@ -255,8 +256,12 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
         d_halo.upload(halo.data(), halo.size(), s);
         launch_localize_neighbours(m->neigh.p, int64_t(n_own) * nf, int32_t(cell_begin), int32_t(cell_end), d_halo.p,
                                    int32_t(halo_lo.size()), int32_t(halo_hi.size()), d_flag.p, s);
+        m->d_cgid.upload(m->cgid.data(), m->cgid.size(), s);
+      } else {
+        launch_validate_neighbours(m->neigh.p, int64_t(n_own) * nf, int32_t(n_cells), d_flag.p, s);
+        m->d_cgid.alloc(size_t(m->n_loc));
+        launch_iota(m->d_cgid.p, m->n_loc, s);
       }
-      m->d_cgid.upload(m->cgid.data(), m->cgid.size(), s);
       mg_detect_structure(m.get(), xy, d_xy.p, d_cv.p, n_verts);
       if (boundary_type) {
         m->has_btype = true;
@@ -272,6 +277,8 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
       int32_t flag = 0;
       HDD_CUDA(cudaMemcpyAsync(&flag, d_flag.p, sizeof(flag), cudaMemcpyDeviceToHost, s));
       HDD_CUDA(cudaStreamSynchronize(s));
+      if (flag & 4) HDD_THROW(HDD_ERR_INDEX_OUT_OF_RANGE, "a vertex id of a cell is out of range");
+      if (flag & 8) HDD_THROW(HDD_ERR_INDEX_OUT_OF_RANGE, "a neighbour id of a cell is out of range");
       if (flag & 1) HDD_THROW(HDD_ERR_NOT_IMPLEMENTED, "HDD_CUBE2D cells must be axis-parallel rectangles");
       if (flag & 2) HDD_THROW(HDD_ERR_INTERNAL, "a neighbour of an owned cell is missing from the halo");
     }
@@ -287,7 +294,7 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
       // vertex ids of the local cells directly
       parallel_for(m->n_loc, [&](int64_t a, int64_t b) {
         for (int64_t lc = a; lc < b; ++lc)
-          std::memcpy(&cvl[size_t(lc) * nl], cell_verts + int64_t(m->cgid[size_t(lc)]) * nl, nl * sizeof(int32_t));
+          std::memcpy(&cvl[size_t(lc) * nl], cell_verts + int64_t(m->gid(int32_t(lc))) * nl, nl * sizeof(int32_t));
       });
       m->n_verts_loc = int32_t(n_verts);
     } else if (need_verts) {
@@ -297,7 +304,7 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
       int32_t* dn = dense.data();
       parallel_for(m->n_loc, [&](int64_t a, int64_t b) {
         for (int64_t lc = a; lc < b; ++lc) {
-          const int32_t* gv = cell_verts + int64_t(m->cgid[size_t(lc)]) * nl;
+          const int32_t* gv = cell_verts + int64_t(m->gid(int32_t(lc))) * nl;
           for (int i = 0; i < nl; ++i) dn[size_t(gv[i])] = 1;  // same value from every thread
         }
       });
@@ -309,7 +316,7 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
       }
       parallel_for(m->n_loc, [&](int64_t a, int64_t b) {
         for (int64_t lc = a; lc < b; ++lc) {
-          const int32_t* gv = cell_verts + int64_t(m->cgid[size_t(lc)]) * nl;
+          const int32_t* gv = cell_verts + int64_t(m->gid(int32_t(lc))) * nl;
           for (int i = 0; i < nl; ++i) cvl[size_t(lc) * nl + i] = dn[size_t(gv[i])];
         }
       });
@@ -326,7 +333,7 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
         for (int i = 0; i < nl; ++i) vdof[size_t(fill[size_t(cvl[size_t(lc) * nl + i])]++)] = lc * nl + i;
       std::vector<uint8_t> vb(size_t(nvl), 0);
       for (int32_t lc = 0; lc < m->n_loc; ++lc) {
-        const int64_t g = m->cgid[size_t(lc)];
+        const int64_t g = m->gid(lc);
         for (int f = 0; f < nf; ++f)
           if (cell_neigh[g * nf + f] < 0) {
             const int* fv = kFaceVertsSimplex[f];
@@ -344,7 +351,40 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
 
     pt.lap("vertex incidence");
     // ---- subdomains (grid::Multiscale view): contiguous, subdomain-major cell ranges
-    if (cell_subdomain) {
+    const int n_sub_hint = cell_subdomain ? cell_subdomain[n_cells - 1] + 1 : 1;
+    if (cell_subdomain && whole && n_sub_hint >= 1 && n_sub_hint <= 2048) {
+      // one GPU owns every cell: offsets and the neighbouring-subdomain relation come from one kernel over the cells
+      if (cell_subdomain[0] != 0) HDD_THROW(HDD_ERR_WRONG_INPUT, "subdomain numbering must start at 0");
+      const int ns = n_sub_hint;
+      m->n_subdomains = ns;
+      DevBuf<int32_t> d_sub, d_flag2;
+      DevBuf<int64_t> d_off;
+      DevBuf<uint8_t> d_adj;
+      d_sub.upload(cell_subdomain, size_t(n_cells), s);
+      d_off.alloc(size_t(ns) + 1);
+      d_off.zero(s);
+      d_adj.alloc(size_t(ns) * ns);
+      d_adj.zero(s);
+      d_flag2.alloc(1);
+      d_flag2.zero(s);
+      launch_subdomain_structure(d_sub.p, m->neigh.p, nf, int32_t(n_cells), ns, d_off.p, d_adj.p, d_flag2.p, s);
+      std::vector<uint8_t> adj(size_t(ns) * ns);
+      m->sub_cell_offsets.assign(size_t(ns) + 1, 0);
+      int32_t f2 = 0;
+      HDD_CUDA(cudaMemcpyAsync(adj.data(), d_adj.p, adj.size(), cudaMemcpyDeviceToHost, s));
+      HDD_CUDA(cudaMemcpyAsync(m->sub_cell_offsets.data(), d_off.p, (size_t(ns) + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+      HDD_CUDA(cudaMemcpyAsync(&f2, d_flag2.p, sizeof(f2), cudaMemcpyDeviceToHost, s));
+      HDD_CUDA(cudaStreamSynchronize(s));
+      m->sub_cell_offsets[size_t(ns)] = n_cells;
+      bool empty_sub = false;
+      for (int k = 1; k < ns; ++k) empty_sub |= m->sub_cell_offsets[size_t(k)] == 0;
+      if (f2 != 0 || empty_sub)
+        HDD_THROW(HDD_ERR_WRONG_INPUT, "cells must be numbered subdomain-major without empty subdomains");
+      m->sub_neighbours.assign(size_t(ns), {});
+      for (int a = 0; a < ns; ++a)
+        for (int b = 0; b < ns; ++b)
+          if (adj[size_t(a) * ns + b]) m->sub_neighbours[size_t(a)].push_back(b);
+    } else if (cell_subdomain) {
       if (cell_subdomain[0] != 0) HDD_THROW(HDD_ERR_WRONG_INPUT, "subdomain numbering must start at 0");
       std::atomic<int64_t> bad{-1};
       parallel_for(n_cells - 1, [&](int64_t a, int64_t b) {
@@ -371,7 +411,7 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
         for (int64_t c = a; c < b; ++c)
           for (int f = 0; f < nf; ++f) {
             const int32_t g = cell_neigh[c * nf + f];
-            if (g >= 0 && cell_subdomain[g] != cell_subdomain[c]) {
+            if (g >= 0 && g < n_cells && cell_subdomain[g] != cell_subdomain[c]) {
               const std::pair<int32_t, int32_t> pr(cell_subdomain[c], cell_subdomain[g]);
               if (out.empty() || out.back() != pr) out.push_back(pr);
             }
@@ -556,7 +596,7 @@ int hdd_mesh_attach_comm(hdd_mesh* m, hdd_comm* c) {
     std::vector<int> halo_owner;
     for (int32_t lc = 0; lc < m->n_loc; ++lc) {
       if (lc >= m->own0 && lc < m->own0 + m->n_own) continue;
-      const int r = owner_of(m->rank_cell_offsets, m->cgid[size_t(lc)]);
+      const int r = owner_of(m->rank_cell_offsets, m->gid(lc));
       halo_cells.push_back(lc);
       halo_owner.push_back(r);
       auto it = peers.find(r);
@@ -590,7 +630,7 @@ int hdd_mesh_attach_comm(hdd_mesh* m, hdd_comm* c) {
       std::vector<int32_t> hp(halo_cells.size()), hr(halo_cells.size());
       for (size_t k = 0; k < halo_cells.size(); ++k) {
         hp[k] = halo_owner[k];
-        hr[k] = int32_t(m->cgid[size_t(halo_cells[k])] - m->rank_cell_offsets[size_t(halo_owner[k])]);
+        hr[k] = int32_t(m->gid(halo_cells[k]) - m->rank_cell_offsets[size_t(halo_owner[k])]);
       }
       m->halo_peer.upload(hp.data(), hp.size(), m->stream);
       m->halo_rcell.upload(hr.data(), hr.size(), m->stream);

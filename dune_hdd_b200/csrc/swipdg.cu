@@ -89,10 +89,14 @@ FnRef add_function(hdd_swipdg* h, const hdd_function& f, const char* what) {
       break;
     case HDD_FN_CELLWISE: {
       if (!f.cell_values) HDD_THROW(HDD_ERR_WRONG_INPUT, what << ": cell_values is NULL");
-      std::vector<double> loc(size_t(m->n_loc));
-      for (int32_t lc = 0; lc < m->n_loc; ++lc) loc[size_t(lc)] = f.cell_values[m->cgid[size_t(lc)]];
       h->fn_cell_storage.emplace_back(new DevBuf<double>);
-      h->fn_cell_storage.back()->upload(loc.data(), loc.size(), m->stream);
+      if (m->whole) {  // local numbering = global numbering: upload the caller's array as it is
+        h->fn_cell_storage.back()->upload(f.cell_values, size_t(m->n_loc), m->stream);
+      } else {
+        std::vector<double> loc(size_t(m->n_loc));
+        for (int32_t lc = 0; lc < m->n_loc; ++lc) loc[size_t(lc)] = f.cell_values[m->gid(lc)];
+        h->fn_cell_storage.back()->upload(loc.data(), loc.size(), m->stream);
+      }
       HDD_CUDA(cudaStreamSynchronize(m->stream));
       d.cell = h->fn_cell_storage.back()->p;
       break;
@@ -474,10 +478,15 @@ int hdd_swipdg_create(hdd_mesh* mesh, int polorder, const hdd_problem* problem, 
       HDD_THROW(HDD_ERR_WRONG_INPUT, "parametric data functions but no parameter_name / parameter_size given");
     if (problem->diffusion_tensor) {
       h->has_tensor = true;
-      std::vector<double> loc(size_t(mesh->n_loc) * 4);
-      for (int32_t lc = 0; lc < mesh->n_loc; ++lc)
-        for (int k = 0; k < 4; ++k) loc[size_t(lc) * 4 + k] = problem->diffusion_tensor[int64_t(mesh->cgid[size_t(lc)]) * 4 + k];
-      h->tensor.upload(loc.data(), loc.size(), mesh->stream);
+      if (mesh->whole) {
+        h->tensor.upload(problem->diffusion_tensor, size_t(mesh->n_loc) * 4, mesh->stream);
+      } else {
+        std::vector<double> loc(size_t(mesh->n_loc) * 4);
+        for (int32_t lc = 0; lc < mesh->n_loc; ++lc)
+          for (int k = 0; k < 4; ++k) loc[size_t(lc) * 4 + k] = problem->diffusion_tensor[int64_t(mesh->gid(lc)) * 4 + k];
+        h->tensor.upload(loc.data(), loc.size(), mesh->stream);
+        HDD_CUDA(cudaStreamSynchronize(mesh->stream));  // loc dies with this scope
+      }
     }
     h->fn_dev.upload(h->fn_host.data(), h->fn_host.size(), mesh->stream);
     HDD_CUDA(cudaStreamSynchronize(mesh->stream));
@@ -1009,7 +1018,7 @@ int hdd_block_extract(hdd_swipdg* h, int ss, int nn, int q, hdd_csr* out) {
       const int64_t base = bs[size_t(k - k0)] * nl * nl - v0;
       for (int i = 0; i < nl; ++i) {
         for (int b = 0; b < nb; ++b) {
-          const int64_t gc = m->cgid[size_t(cells[b])];
+          const int64_t gc = m->gid(cells[b]);
           if (gc < col0 || gc >= col1) continue;  // not a cell of subdomain nn
           for (int j = 0; j < nl; ++j) {
             col.push_back(int32_t((gc - col0) * nl + j));

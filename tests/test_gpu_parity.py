@@ -258,6 +258,17 @@ def test_error_behaviour(gpu):
         d.solve(mu=[1.0])
     with pytest.raises(hdd.discretizations.NotImplemented_):
         hdd.SWIPDG(g, problems.ESV2007(), polorder=3)
+    # index validation happens on the device (geometry / neighbour kernels of hdd_mesh_create)
+    import copy
+    for field, value in (("cell_verts", g.n_verts), ("cell_verts", -1), ("cell_neigh", g.n_cells), ("cell_neigh", -2)):
+        gb = copy.deepcopy(g)
+        getattr(gb, field)[5, 1] = value
+        with pytest.raises(hdd.discretizations.index_out_of_range):
+            hdd.SWIPDG(gb, problems.ESV2007())
+    gp = grids.simplex(4, partitions=(2, 2))
+    gp.cell_subdomain[3], gp.cell_subdomain[4] = gp.cell_subdomain[-1], gp.cell_subdomain[-1]  # not subdomain-major
+    with pytest.raises(hdd.discretizations.wrong_input_given):
+        hdd.BlockSWIPDG(gp, problems.ESV2007())
     bad = problems.ESV2007()
     bad.force = problems.AffinelyDecomposable(problems.Expression("cos(x[0]", 3))
     with pytest.raises(hdd.discretizations.wrong_input_given):
