@@ -81,7 +81,7 @@ __global__ void k_struct_verts(const double* __restrict__ xy, int32_t n_verts, i
 // index distance 2 cancel analytically (inner-face jumps of continuous functions) and are dropped.
 __global__ void __launch_bounds__(kMgThreads)
     k_vertex_galerkin(MeshView m, const double* __restrict__ vals, const int32_t* __restrict__ cell_v0,
-                      const int32_t* __restrict__ lex_cell, int nx, int ny, double* __restrict__ S, double* __restrict__ SC) {
+                      const int32_t* __restrict__ lex_cell, int nx, int ny, double* __restrict__ S) {
   const int64_t nv = int64_t(nx + 1) * (ny + 1);
   const int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (v >= nv) return;
@@ -120,18 +120,7 @@ __global__ void __launch_bounds__(kMgThreads)
       }
     }
 #pragma unroll
-  for (int e = 0; e < 9; ++e) {
-    S[e * nv + v] = acc[e];
-    if (SC) SC[e * nv + v] = (e & 1) ? -acc[e] : acc[e];  // e odd <=> |dx| + |dy| odd: C A_c C flips the edge neighbours
-  }
-}
-
-// SC = C S C after the all-reduce of S (multi GPU)
-__global__ void k_twist_stencil(const double* __restrict__ S, int64_t nv, double* __restrict__ SC) {
-  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (t >= 9 * nv) return;
-  const int e = int(t / nv);
-  SC[t] = (e & 1) ? -S[t] : S[t];
+  for (int e = 0; e < 9; ++e) S[e * nv + v] = acc[e];
 }
 
 // b1 = C b0 after the all-reduce of b0 (multi GPU)
@@ -145,7 +134,7 @@ __global__ void k_twist_vector(const int* done, const double* __restrict__ b0, i
 
 // ---- Galerkin coarse operator with bilinear interpolation: 9-point -> 9-point ---------------------------------
 __global__ void __launch_bounds__(kMgThreads)
-    k_rap(const double* __restrict__ Sf, int nxf, int nyf, double* __restrict__ Sc) {
+    k_rap(const double* __restrict__ Sf, int nxf, int nyf, int twist, double* __restrict__ Sc) {
   const int nxc = nxf / 2, nyc = nyf / 2;
   const int64_t nvc = int64_t(nxc + 1) * (nyc + 1), nvf = int64_t(nxf + 1) * (nyf + 1);
   const int64_t I = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -164,7 +153,8 @@ __global__ void __launch_bounds__(kMgThreads)
         for (int ex = -1; ex <= 1; ++ex) {
           const int jx = fx + ex, jy = fy + ey;
           if (jx < 0 || jy < 0 || jx > nxf || jy > nyf) continue;
-          const double s = wd * __ldg(Sf + ((ey + 1) * 3 + ex + 1) * nvf + i);
+          double s = wd * __ldg(Sf + ((ey + 1) * 3 + ex + 1) * nvf + i);
+          if (twist && ((ex + ey) & 1)) s = -s;  // fine operator C A C, read from the arrays of A
           // coarse vertices J = I + D whose interpolation stencil touches j: |j - 2J| <= 1
 #pragma unroll
           for (int Dy = -1; Dy <= 1; ++Dy) {
@@ -271,6 +261,65 @@ __global__ void __launch_bounds__(kMgThreads)
       ax = fma(__ldg(S + ((ey + 1) * 3 + ex + 1) * nv + i), __ldg(x + i + ex + int64_t(ey) * nx1), ax);
     }
   y[i] = fma(__ldg(dinv + i), b[i] - ax, x[i]);
+}
+
+// Level 0, both hierarchies in one sweep: C A_c C differs from A_c only by the sign of the edge-neighbour entries
+// (e odd), so the nine coefficient arrays - three quarters of the bytes of a smoothing sweep - are read once for
+// the plain and the twisted hierarchy.
+__global__ void __launch_bounds__(kMgThreads)
+    k_mg_pre2(const int* done, const double* __restrict__ S, const double* __restrict__ dinv, int nx, int ny,
+              const double* __restrict__ b0, const double* __restrict__ b1, double* __restrict__ x0, double* __restrict__ x1,
+              double* __restrict__ r0, double* __restrict__ r1) {
+  if (done && *done) return;
+  const int nx1 = nx + 1;
+  const int64_t nv = int64_t(nx1) * (ny + 1);
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= nv) return;
+  const int ix = int(i % nx1), iy = int(i / nx1);
+  double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+  for (int ey = -1; ey <= 1; ++ey)
+#pragma unroll
+    for (int ex = -1; ex <= 1; ++ex) {
+      const int jx = ix + ex, jy = iy + ey;
+      if (jx < 0 || jy < 0 || jx > nx || jy > ny) continue;
+      const int64_t j = i + ex + int64_t(ey) * nx1;
+      const double dj = __ldg(dinv + j);
+      const double xj0 = dj * __ldg(b0 + j), xj1 = dj * __ldg(b1 + j);
+      const double se = __ldg(S + ((ey + 1) * 3 + ex + 1) * nv + i);
+      a0 = fma(se, xj0, a0);
+      a1 = fma(((ex + ey) & 1) ? -se : se, xj1, a1);
+      if (ex == 0 && ey == 0) { x0[i] = xj0; x1[i] = xj1; }
+    }
+  r0[i] = b0[i] - a0;
+  r1[i] = b1[i] - a1;
+}
+
+__global__ void __launch_bounds__(kMgThreads)
+    k_mg_post2(const int* done, const double* __restrict__ S, const double* __restrict__ dinv, int nx, int ny,
+               const double* __restrict__ b0, const double* __restrict__ b1, const double* __restrict__ x0,
+               const double* __restrict__ x1, double* __restrict__ y0, double* __restrict__ y1) {
+  if (done && *done) return;
+  const int nx1 = nx + 1;
+  const int64_t nv = int64_t(nx1) * (ny + 1);
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= nv) return;
+  const int ix = int(i % nx1), iy = int(i / nx1);
+  double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+  for (int ey = -1; ey <= 1; ++ey)
+#pragma unroll
+    for (int ex = -1; ex <= 1; ++ex) {
+      const int jx = ix + ex, jy = iy + ey;
+      if (jx < 0 || jy < 0 || jx > nx || jy > ny) continue;
+      const int64_t j = i + ex + int64_t(ey) * nx1;
+      const double se = __ldg(S + ((ey + 1) * 3 + ex + 1) * nv + i);
+      a0 = fma(se, __ldg(x0 + j), a0);
+      a1 = fma(((ex + ey) & 1) ? -se : se, __ldg(x1 + j), a1);
+    }
+  const double d = __ldg(dinv + i);
+  y0[i] = fma(d, b0[i] - a0, x0[i]);
+  y1[i] = fma(d, b1[i] - a1, x1[i]);
 }
 
 // dinv = w / diagonal of the level operator
@@ -392,19 +441,20 @@ void mg_detect_structure(hdd_mesh* m, const double* xy_host, const double* xy_de
 }
 
 // recomputes the Galerkin operators below the finest level and the dense coarsest inverse; the level buffers are
-// allocated once per mesh by mg_setup and persist across solves, so a captured CUDA graph of the iteration stays valid
-static void build_hierarchy(hdd_swipdg* h, MgHierarchy& H, int nx, int ny) {
+// allocated once per mesh by mg_setup and persist across solves, so a captured CUDA graph of the iteration stays valid.
+// The twisted hierarchy has no level-0 arrays of its own: its finest operator is C A_c C, read from `S0` with the sign
+// of the edge-neighbour entries flipped.
+static void build_hierarchy(hdd_swipdg* h, MgHierarchy& H, const double* S0, bool twisted) {
   cudaStream_t s = h->mesh->stream;
-  (void)nx;
-  (void)ny;
   for (size_t l = 0; l + 1 < H.levels.size(); ++l) {
     MgLevel& f = *H.levels[l];
     MgLevel& c = *H.levels[l + 1];
-    k_rap<<<blocks_for(c.nv), kMgThreads, 0, s>>>(f.S.p, f.nx, f.ny, c.S.p);
+    k_rap<<<blocks_for(c.nv), kMgThreads, 0, s>>>(l == 0 ? S0 : f.S.p, f.nx, f.ny, (l == 0 && twisted) ? 1 : 0, c.S.p);
     count_launch();
   }
-  for (auto& L : H.levels) {
-    k_mg_dinv<<<blocks_for(L->nv), kMgThreads, 0, s>>>(L->S.p, L->nv, L->dinv.p);
+  for (size_t l = twisted ? 1 : 0; l < H.levels.size(); ++l) {
+    MgLevel& L = *H.levels[l];
+    k_mg_dinv<<<blocks_for(L.nv), kMgThreads, 0, s>>>(L.S.p, L.nv, L.dinv.p);
     count_launch();
   }
   // dense inverse of the coarsest operator (s.p.d.), Gauss-Jordan on the host
@@ -414,9 +464,13 @@ static void build_hierarchy(hdd_swipdg* h, MgHierarchy& H, int nx, int ny) {
                                                            << " grid cannot be coarsened by halving down to at most "
                                                            << kMaxCoarse << " vertices (stuck at " << C.nx << " x " << C.ny << ")");
   const int n = int(C.nv);
+  const bool coarsest_is_finest = H.levels.size() == 1;
   std::vector<double> S(size_t(9) * n);
-  HDD_CUDA(cudaMemcpyAsync(S.data(), C.S.p, S.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+  HDD_CUDA(cudaMemcpyAsync(S.data(), coarsest_is_finest ? S0 : C.S.p, S.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
   HDD_CUDA(cudaStreamSynchronize(s));
+  if (coarsest_is_finest && twisted)
+    for (int e = 1; e < 9; e += 2)
+      for (int i = 0; i < n; ++i) S[size_t(e) * n + i] = -S[size_t(e) * n + i];
   std::vector<double> A(size_t(n) * n, 0.0), I(size_t(n) * n, 0.0);
   const int nx1 = C.nx + 1;
   for (int i = 0; i < n; ++i) {
@@ -445,9 +499,10 @@ static void build_hierarchy(hdd_swipdg* h, MgHierarchy& H, int nx, int ny) {
   HDD_CUDA(cudaStreamSynchronize(s));
 }
 
-static void vcycle(MgHierarchy& H, const int* done, cudaStream_t s) {
+// levels l0 .. coarsest of one hierarchy: down, dense solve, up; leaves the result in levels[l0]->x
+static void vcycle_from(MgHierarchy& H, int l0, const int* done, cudaStream_t s) {
   const int nl = int(H.levels.size());
-  for (int l = 0; l + 1 < nl; ++l) {
+  for (int l = l0; l + 1 < nl; ++l) {
     MgLevel& L = *H.levels[size_t(l)];
     MgLevel& Cn = *H.levels[size_t(l) + 1];
     k_mg_pre<<<blocks_for(L.nv), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, L.b.p, L.x.p, L.r.p);
@@ -457,7 +512,7 @@ static void vcycle(MgHierarchy& H, const int* done, cudaStream_t s) {
   MgLevel& C = *H.levels.back();
   k_mg_dense<<<(int(C.nv) + 127) / 128, 128, 0, s>>>(done, H.coarse_inv.p, int(C.nv), C.b.p, C.x.p);
   count_launch();
-  for (int l = nl - 2; l >= 0; --l) {
+  for (int l = nl - 2; l >= l0; --l) {
     MgLevel& L = *H.levels[size_t(l)];
     MgLevel& Cn = *H.levels[size_t(l) + 1];
     k_mg_prolong_add<<<blocks_for(L.nv), kMgThreads, 0, s>>>(done, Cn.x.p, L.nx, L.ny, L.x.p);
@@ -465,6 +520,26 @@ static void vcycle(MgHierarchy& H, const int* done, cudaStream_t s) {
     count_launch(2);
     std::swap(L.x.p, L.y.p);  // the smoothed iterate is the level's x from here on
   }
+}
+
+// one V(1,1)-cycle of both hierarchies; level 0 is swept once for the two of them (k_mg_pre2 / k_mg_post2)
+static void vcycle_pair(MgState& st, const int* done, cudaStream_t s) {
+  MgLevel& a = *st.h[0].levels[0];
+  MgLevel& b = *st.h[1].levels[0];
+  MgLevel& a1 = *st.h[0].levels[1];
+  MgLevel& b1 = *st.h[1].levels[1];
+  k_mg_pre2<<<blocks_for(a.nv), kMgThreads, 0, s>>>(done, a.S.p, a.dinv.p, a.nx, a.ny, a.b.p, b.b.p, a.x.p, b.x.p, a.r.p, b.r.p);
+  k_mg_restrict<<<blocks_for(a1.nv), kMgThreads, 0, s>>>(done, a.r.p, a.nx, a.ny, a1.b.p);
+  k_mg_restrict<<<blocks_for(b1.nv), kMgThreads, 0, s>>>(done, b.r.p, b.nx, b.ny, b1.b.p);
+  count_launch(3);
+  vcycle_from(st.h[0], 1, done, s);
+  vcycle_from(st.h[1], 1, done, s);
+  k_mg_prolong_add<<<blocks_for(a.nv), kMgThreads, 0, s>>>(done, a1.x.p, a.nx, a.ny, a.x.p);
+  k_mg_prolong_add<<<blocks_for(b.nv), kMgThreads, 0, s>>>(done, b1.x.p, b.nx, b.ny, b.x.p);
+  k_mg_post2<<<blocks_for(a.nv), kMgThreads, 0, s>>>(done, a.S.p, a.dinv.p, a.nx, a.ny, a.b.p, b.b.p, a.x.p, b.x.p, a.y.p, b.y.p);
+  count_launch(3);
+  std::swap(a.x.p, a.y.p);
+  std::swap(b.x.p, b.y.p);
 }
 
 void mg_release(MgState* st) { delete st; }
@@ -486,55 +561,37 @@ void mg_setup(hdd_swipdg* h, const double* vals) {
     st.h[0].levels.clear();
     st.h[1].levels.clear();
   }
-  // level structure first (allocation only), then the level-0 operators, then the Galerkin products
-  const bool fresh = st.h[0].levels.empty();
-  if (fresh) {
+  if (st.h[0].levels.empty()) {  // level structure, allocation only
     for (int t = 0; t < 2; ++t) {
-      std::unique_ptr<MgLevel> L(new MgLevel);
-      L->nx = m->sx;
-      L->ny = m->sy;
-      L->nv = nv;
-      L->S.alloc(size_t(9) * nv);
-      L->dinv.alloc(size_t(nv));
-      L->b.alloc(size_t(nv));
-      L->x.alloc(size_t(nv));
-      L->r.alloc(size_t(nv));
-      L->y.alloc(size_t(nv));
-      st.h[t].levels.push_back(std::move(L));
       int lx = m->sx, ly = m->sy;
-      int64_t lv = nv;
-      while (!(lv <= kMaxCoarse || (lx & 1) || (ly & 1) || lx < 2 || ly < 2)) {
+      for (int l = 0;; ++l) {
+        std::unique_ptr<MgLevel> L(new MgLevel);
+        L->nx = lx;
+        L->ny = ly;
+        L->nv = int64_t(lx + 1) * (ly + 1);
+        if (!(t == 1 && l == 0)) {  // the twisted hierarchy shares the level-0 operator of the plain one
+          L->S.alloc(size_t(9) * L->nv);
+          L->dinv.alloc(size_t(L->nv));
+        }
+        L->b.alloc(size_t(L->nv));
+        L->x.alloc(size_t(L->nv));
+        L->r.alloc(size_t(L->nv));
+        L->y.alloc(size_t(L->nv));
+        const bool last = L->nv <= kMaxCoarse || (lx & 1) || (ly & 1) || lx < 2 || ly < 2;
+        st.h[t].levels.push_back(std::move(L));
+        if (last) break;
         lx /= 2;
         ly /= 2;
-        lv = int64_t(lx + 1) * (ly + 1);
-        std::unique_ptr<MgLevel> C(new MgLevel);
-        C->nx = lx;
-        C->ny = ly;
-        C->nv = lv;
-        C->S.alloc(size_t(9) * lv);
-        C->dinv.alloc(size_t(lv));
-        C->b.alloc(size_t(lv));
-        C->x.alloc(size_t(lv));
-        C->r.alloc(size_t(lv));
-        C->y.alloc(size_t(lv));
-        st.h[t].levels.push_back(std::move(C));
       }
     }
   }
   MgLevel& f0 = *st.h[0].levels[0];
-  MgLevel& f1 = *st.h[1].levels[0];
-  const bool multi = m->world > 1;
-  k_vertex_galerkin<<<blocks_for(nv), kMgThreads, 0, s>>>(h->view(), vals, m->cell_v0.p, m->lex_cell.p, m->sx, m->sy, f0.S.p,
-                                                           multi ? nullptr : f1.S.p);
+  k_vertex_galerkin<<<blocks_for(nv), kMgThreads, 0, s>>>(h->view(), vals, m->cell_v0.p, m->lex_cell.p, m->sx, m->sy, f0.S.p);
   count_launch();
-  if (multi) {
-    Nccl::get().all_reduce_sum(f0.S.p, size_t(9) * nv, m->comm, s);
-    k_twist_stencil<<<blocks_for(9 * nv), kMgThreads, 0, s>>>(f0.S.p, nv, f1.S.p);
-    count_launch();
-  }
+  if (m->world > 1) Nccl::get().all_reduce_sum(f0.S.p, size_t(9) * nv, m->comm, s);
   HDD_CUDA(cudaGetLastError());
-  build_hierarchy(h, st.h[0], m->sx, m->sy);
-  build_hierarchy(h, st.h[1], m->sx, m->sy);
+  build_hierarchy(h, st.h[0], f0.S.p, false);
+  build_hierarchy(h, st.h[1], f0.S.p, true);
   HDD_CUDA(cudaGetLastError());
 }
 
@@ -577,10 +634,8 @@ void mg_apply(hdd_swipdg* h, const int* done, const double* r, double* z, double
     k_mg_dense<<<(int(b.nv) + 127) / 128, 128, 0, s>>>(done, st.h[1].coarse_inv.p, int(b.nv), b.b.p, b.x.p);
     count_launch(2);
   } else {
-    vcycle(st.h[0], done, s);
-    lap("v-cycle");
-    vcycle(st.h[1], done, s);
-    lap("v-cycle C");
+    vcycle_pair(st, done, s);
+    lap("v-cycles");
   }
   const int grid = int(std::min<int64_t>((m->n_own + kMgThreads - 1) / kMgThreads, kMaxBlocks));
   k_dg_prolong_dot<<<grid, kMgThreads, 0, s>>>(done, m->n_own, m->cell_v0.p + m->own0, st.nx, a.x.p, b.x.p, r, z, p_init, partial, sc);
