@@ -79,6 +79,7 @@ struct hdd_mesh {
   // vertex 0 of every cell and the map lexicographic cell -> cell; feeds the multigrid preconditioner ("cg.mg")
   int sx = 0, sy = 0;
   hdd::DevBuf<int32_t> cell_v0, lex_cell;
+  hdd::DevBuf<double> tgeo;  // {x0, hx} per column, {y0, hy} per row
   bool purely_neumann = false;  // no Dirichlet face anywhere (DirichletDetector, discretizations/swipdg.hh:219-220,488-489)
 
   // multi GPU
@@ -108,6 +109,10 @@ struct hdd_mesh {
     v.tensor = tensor;
     v.blk_start = blk_start.p;
     v.cgid = d_cgid.p;
+    v.cell_v0 = sx > 0 ? cell_v0.p : nullptr;
+    v.tgeo = sx > 0 ? tgeo.p : nullptr;
+    v.tnx = sx;
+    v.tny = sy;
     return v;
   }
   void set_device() const { HDD_CUDA(cudaSetDevice(device)); }

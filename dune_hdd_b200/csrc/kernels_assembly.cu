@@ -429,7 +429,10 @@ __device__ __forceinline__ void cube_face(const MeshView& m, const DevFn& fn, co
   store_block<NL>(row0, rs, block_slot<4>(c, nb, n), E);
 }
 
-template <int FK, int MINB>
+// TENSOR: the mesh is a logically structured tensor grid (MeshView::tgeo): the cell sizes of the cell and of its four
+// neighbours come from the one-dimensional column / row tables (a few KB, cache resident) instead of the per-cell
+// geometry records - no dependent neigh -> cgeo[neighbour] round trip, 160 bytes less gather traffic per cell.
+template <int FK, int MINB, bool TENSOR>
 __global__ void __launch_bounds__(kThreads, MINB)
     k_assemble_lhs_cube(MeshView m, const __grid_constant__ DevFn fn, ElemRule vol, LineRule fr, double s_in, double s_bnd,
                         double* __restrict__ vals) {
@@ -439,20 +442,39 @@ __global__ void __launch_bounds__(kThreads, MINB)
   if (k >= m.n_own) return;
   const int c = m.own0 + k;
   G g;
-  g.load(m.cgeo, c);
-  double K[4];
-  load_tensor(m.tensor, c, K);
+  double nihx[NF], nihy[NF];
   int nb[NF];
   load_neigh<NF>(m.neigh, k, nb);
+  if constexpr (TENSOR) {
+    const int v0 = __ldg(m.cell_v0 + c);
+    const int cx = v0 % (m.tnx + 1), cy = v0 / (m.tnx + 1);
+    const double2* tx = reinterpret_cast<const double2*>(m.tgeo);
+    const double2* ty = tx + m.tnx;
+    const double2 ox = __ldg(tx + cx), oy = __ldg(ty + cy);
+    g.x0 = ox.x; g.hx = ox.y; g.x1 = ox.x + ox.y;
+    g.y0 = oy.x; g.hy = oy.y; g.y1 = oy.x + oy.y;
+    g.ihx = 1.0 / g.hx; g.ihy = 1.0 / g.hy;
+    g.detj = fabs(g.hx * g.hy);
+    // left / right neighbours share the row, bottom / top neighbours the column
+    nihx[0] = 1.0 / __ldg(tx + max(cx - 1, 0)).y;
+    nihx[1] = 1.0 / __ldg(tx + min(cx + 1, m.tnx - 1)).y;
+    nihx[2] = nihx[3] = g.ihx;
+    nihy[0] = nihy[1] = g.ihy;
+    nihy[2] = 1.0 / __ldg(ty + max(cy - 1, 0)).y;
+    nihy[3] = 1.0 / __ldg(ty + min(cy + 1, m.tny - 1)).y;
+  } else {
+    g.load(m.cgeo, c);
+  }
+  double K[4];
+  load_tensor(m.tensor, c, K);
   const int nblk = block_count<NF>(nb);
   const int rs = nblk * NL;
   double* row0 = vals + m.blk_start[k] * (NL * NL);
   double a_self = 0.0;
   if constexpr (FK == HDD_FN_CONSTANT) a_self = fn.value;
   if constexpr (FK == HDD_FN_CELLWISE) a_self = __ldg(fn.cell + c);
-  // all four neighbour records are requested up front: one memory latency instead of four in the face loop
-  double nihx[NF], nihy[NF];
-  {
+  if constexpr (!TENSOR) {
+    // all four neighbour records are requested up front: one memory latency instead of four in the face loop
     double2 lo[NF], hi[NF];
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
@@ -783,21 +805,7 @@ __global__ void __launch_bounds__(kThreads)
 //   SX[cx][a] = h_x sum_q w_q g(x_q) l_a(xi_q),  SY[cy][b] = h_y sum_q w_q h(y_q) l_b(eta_q)
 // depend on the column / row of the cell only, so they are evaluated once per column and row (nx + ny instead of
 // nx * ny evaluations of the transcendental factors) and the cell kernel is a pure stream: b_(a + (p+1) b) = SX_a SY_b.
-// Step 1 records x0 / hx per column and y0 / hy per row from the owned cells (every writer stores the same value).
-__global__ void k_rhs_tensor_geometry(MeshView m, const int32_t* __restrict__ cell_v0, int nx, double* __restrict__ tab) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= m.n_own) return;
-  const int c = m.own0 + k;
-  const int v0 = __ldg(cell_v0 + c);
-  const int cx = v0 % (nx + 1), cy = v0 / (nx + 1);
-  const double2 lo = __ldg(reinterpret_cast<const double2*>(m.cgeo + size_t(4) * c));
-  const double2 hi = __ldg(reinterpret_cast<const double2*>(m.cgeo + size_t(4) * c) + 1);
-  double2* gx = reinterpret_cast<double2*>(tab);             // [nx]: x0, hx
-  double2* gy = reinterpret_cast<double2*>(tab) + nx;        // [ny]: y0, hy
-  gx[cx] = make_double2(lo.x, hi.x - lo.x);
-  gy[cy] = make_double2(lo.y, hi.y - lo.y);
-}
-
+// The column / row geometry comes from MeshView::tgeo.
 template <int P>
 __global__ void k_rhs_tensor_moments(const __grid_constant__ DevFn fn, LineRule g1, int nx, int ny,
                                      const double* __restrict__ geo, double* __restrict__ mom) {
@@ -1111,13 +1119,22 @@ void launch_assemble_lhs(const MeshView& m, const DevFn& factor_dev, int factor_
   } else if (generic_cube) {
     assemble_dispatch<HDD_CUBE2D>(factor_kind, blocks, s, m, factor_dev, vol, fr, si, sb, values);
   } else {
-    static const int minb = [] { const char* e = std::getenv("HDD_ASM_MINB"); return e ? std::atoi(e) : 3; }();
+    // resident CTAs per SM the kernel is compiled for: 3 (160 registers) for the general kernel, 4 (128) for the tensor
+    // grid variant, which keeps no neighbour geometry records alive (measured 2.15 -> 2.03 ms at 4096^2)
+    static const int minb_env = [] { const char* e = std::getenv("HDD_ASM_MINB"); return e ? std::atoi(e) : 0; }();
     dispatch_fk(factor_kind, [&](auto k) {
       constexpr int FKV = decltype(k)::value;
-      if (minb == 4) k_assemble_lhs_cube<FKV, 4><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
-      else if (minb == 5) k_assemble_lhs_cube<FKV, 5><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
-      else if (minb == 6) k_assemble_lhs_cube<FKV, 6><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
-      else k_assemble_lhs_cube<FKV, 3><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+      static const bool tensor_ok = [] { const char* e = std::getenv("HDD_ASM_TENSOR"); return !(e && e[0] == '0'); }();
+      const int minb = minb_env ? minb_env : ((m.tgeo && tensor_ok) ? 4 : 3);
+      if (m.tgeo && tensor_ok) {
+        if (minb == 3) k_assemble_lhs_cube<FKV, 3, true><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+        else if (minb == 5) k_assemble_lhs_cube<FKV, 5, true><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+        else k_assemble_lhs_cube<FKV, 4, true><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+      } else if (minb == 4) {
+        k_assemble_lhs_cube<FKV, 4, false><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+      } else {
+        k_assemble_lhs_cube<FKV, 3, false><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+      }
     });
   }
   count_launch();
@@ -1172,13 +1189,12 @@ void launch_rhs_volume(const MeshView& m, const DevFn& force_dev, int force_orde
                        bool accumulate, const TensorGridView* tg, double* b, cudaStream_t s) {
   if (m.n_own == 0) return;
   const int acc = accumulate ? 1 : 0;
-  if (m.kind == HDD_CUBE2D && separable && tg && tg->nx > 0 && tg->scratch) {
+  if (m.kind == HDD_CUBE2D && separable && tg && tg->nx > 0 && tg->scratch && m.tgeo) {
     // tensor-product grid: 1-d moments per column / row, then a pure streaming kernel
     const LineRule g1 = line_rule(force_order + polorder);
     const int nx = tg->nx, ny = tg->ny, n1 = polorder + 1;
-    double* geo = tg->scratch;                       // [2 * (nx + ny)]
-    double* mom = tg->scratch + 2 * size_t(nx + ny);  // [(nx + ny) * (p + 1)]
-    k_rhs_tensor_geometry<<<grid_for(m.n_own, 256), 256, 0, s>>>(m, tg->cell_v0, nx, geo);
+    const double* geo = m.tgeo;  // {x0, hx} per column, {y0, hy} per row (built at mesh creation)
+    double* mom = tg->scratch;   // [(nx + ny) * (p + 1)]
     if (polorder == 1) {
       k_rhs_tensor_moments<1><<<grid_for(nx + ny, 128), 128, 0, s>>>(force_dev, g1, nx, ny, geo, mom);
       k_rhs_tensor_cells<1><<<grid_for(m.n_own, 256), 256, 0, s>>>(m.n_own, m.own0, tg->cell_v0, nx, mom, acc, b);
@@ -1187,7 +1203,7 @@ void launch_rhs_volume(const MeshView& m, const DevFn& force_dev, int force_orde
       k_rhs_tensor_cells<2><<<grid_for(m.n_own, 256), 256, 0, s>>>(m.n_own, m.own0, tg->cell_v0, nx, mom, acc, b);
     }
     (void)n1;
-    count_launch(3);
+    count_launch(2);
     HDD_CUDA(cudaGetLastError());
     return;
   }
