@@ -429,24 +429,20 @@ __device__ __forceinline__ void cube_face(const MeshView& m, const DevFn& fn, co
   store_block<NL>(row0, rs, block_slot<4>(c, nb, n), E);
 }
 
+// The row block of one Q1 cell from its already loaded records (neighbour ids, block offset, vertex 0).
 // TENSOR: the mesh is a logically structured tensor grid (MeshView::tgeo): the cell sizes of the cell and of its four
 // neighbours come from the one-dimensional column / row tables (a few KB, cache resident) instead of the per-cell
 // geometry records - no dependent neigh -> cgeo[neighbour] round trip, 160 bytes less gather traffic per cell.
-template <int FK, int MINB, bool TENSOR>
-__global__ void __launch_bounds__(kThreads, MINB)
-    k_assemble_lhs_cube(MeshView m, const __grid_constant__ DevFn fn, ElemRule vol, LineRule fr, double s_in, double s_bnd,
-                        double* __restrict__ vals) {
+template <int FK, bool TENSOR>
+__device__ __forceinline__ void assemble_cube_cell(const MeshView& m, const DevFn& fn, const ElemRule& vol, const LineRule& fr,
+                                                   double s_in, double s_bnd, double* __restrict__ vals, int k, const int* nb,
+                                                   int64_t blk, int v0) {
   using G = Geo<HDD_CUBE2D>;
   constexpr int NL = 4, NF = 4;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= m.n_own) return;
   const int c = m.own0 + k;
   G g;
   double nihx[NF], nihy[NF];
-  int nb[NF];
-  load_neigh<NF>(m.neigh, k, nb);
   if constexpr (TENSOR) {
-    const int v0 = __ldg(m.cell_v0 + c);
     const int cx = v0 % (m.tnx + 1), cy = v0 / (m.tnx + 1);
     const double2* tx = reinterpret_cast<const double2*>(m.tgeo);
     const double2* ty = tx + m.tnx;
@@ -469,7 +465,7 @@ __global__ void __launch_bounds__(kThreads, MINB)
   load_tensor(m.tensor, c, K);
   const int nblk = block_count<NF>(nb);
   const int rs = nblk * NL;
-  double* row0 = vals + m.blk_start[k] * (NL * NL);
+  double* row0 = vals + blk * (NL * NL);
   double a_self = 0.0;
   if constexpr (FK == HDD_FN_CONSTANT) a_self = fn.value;
   if constexpr (FK == HDD_FN_CELLWISE) a_self = __ldg(fn.cell + c);
@@ -509,6 +505,18 @@ __global__ void __launch_bounds__(kThreads, MINB)
   cube_face<2, FK>(m, fn, g, K, k, c, nb[2], nihx[2], nihy[2], a_self, fr, s_in, s_bnd, D, row0, rs, nb);
   cube_face<3, FK>(m, fn, g, K, k, c, nb[3], nihx[3], nihy[3], a_self, fr, s_in, s_bnd, D, row0, rs, nb);
   store_block<NL>(row0, rs, block_slot<NF>(c, nb, c), D);
+}
+
+template <int FK, int MINB, bool TENSOR>
+__global__ void __launch_bounds__(kThreads, MINB)
+    k_assemble_lhs_cube(MeshView m, const __grid_constant__ DevFn fn, ElemRule vol, LineRule fr, double s_in, double s_bnd,
+                        double* __restrict__ vals) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m.n_own) return;
+  int nb[4];
+  load_neigh<4>(m.neigh, k, nb);
+  const int v0 = TENSOR ? __ldg(m.cell_v0 + m.own0 + k) : 0;
+  assemble_cube_cell<FK, TENSOR>(m, fn, vol, fr, s_in, s_bnd, vals, k, nb, m.blk_start[k], v0);
 }
 
 // select v[i] for a run-time i without dynamic register indexing
