@@ -268,15 +268,15 @@ def main():
     peak, peak_kind = measured_peak_gbs()
     # DRAM traffic per launch from the committed `ncu --set full` capture of this workload (profiles/), if it matches
     traffic = {}
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01c_traffic_n4096.json")) as f:
-            tj = json.load(f)
-        if tj.get("cells") == n * n and world == 1:
-            kmap = {"spmv": "k_cg_spmv_tma", "cg_update": "k_cg_update", "cg_direction": "k_cg_direction",
-                    "assembly": "k_assemble_lhs_cube<0>"}
-            traffic = {k: tj["kernels"][v]["dram_bytes"] for k, v in kmap.items() if v in tj["kernels"]}
-    except Exception:
-        pass
+    for fname, kmap in (("r01c_traffic_n4096.json", {"cg_update": "k_cg_update", "cg_direction": "k_cg_direction"}),
+                        ("r01f_traffic_n4096.json", {"spmv": "k_cg_spmv_tma", "assembly": "k_assemble_lhs_cube<0, 4, 1>"})):
+        try:
+            with open(os.path.join(ROOT, "profiles", fname)) as f:
+                tj = json.load(f)
+            if tj.get("cells") == n * n and world == 1:
+                traffic.update({k: tj["kernels"][v]["dram_bytes"] for k, v in kmap.items() if v in tj["kernels"]})
+        except Exception:
+            pass
     for which, name in ((0, "spmv"), (1, "cg_update"), (2, "cg_direction"), (3, "assembly")):
         sec, byt = C.c_double(), C.c_double()
         capi.check(L.hdd_profile_kernel(d._h, which, 20 if which != 3 else 5, C.byref(sec)))
