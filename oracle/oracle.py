@@ -84,6 +84,12 @@ def lib():
     return _LIB
 
 
+def set_threads(n):
+    """host threads of the assembly walk / SpMV / CG (default 1 = the reference's serial walk; more only for the
+    'all cores' CPU baseline of bench.py)"""
+    lib().or_set_threads(int(n))
+
+
 def _p(a, t=C.c_double):
     if a is None:
         return None

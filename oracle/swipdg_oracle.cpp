@@ -24,6 +24,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -358,6 +359,43 @@ double sigma_boundary(int p) { return p <= 1 ? 14.0 : p <= 2 ? 38.0 : p <= 3 ? 7
 // ------------------------------------------------------------------------------------
 // CSR helpers (Stuff::LA container semantics: add_to_entry(row, col, v) into a fixed pattern)
 // ------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------
+// Optional host threading (or_set_threads).  The reference's walk is serial and unthreaded
+// (discretizations/swipdg.hh:485); with one thread - the default - every function below is
+// exactly that serial walk.  More threads exist only so that bench.py can report an
+// "all cores" CPU number next to the faithful one-core one: cells are dealt to the threads
+// in contiguous chunks, matrix entries are added atomically (rows of a cell receive
+// contributions from the walks of its neighbours), reductions are combined in chunk order.
+// ------------------------------------------------------------------------------------
+int g_threads = 1;
+
+template <class F>
+void parallel_chunks(int64_t n, F&& f) {  // f(chunk, begin, end)
+  const int nt = int(std::max<int64_t>(1, std::min<int64_t>(g_threads, n)));
+  if (nt == 1) { f(0, int64_t(0), n); return; }
+  std::vector<std::thread> th;
+  const int64_t chunk = (n + nt - 1) / nt;
+  for (int t = 0; t < nt; ++t) {
+    const int64_t a = t * chunk, b = std::min<int64_t>(a + chunk, n);
+    if (a >= b) break;
+    th.emplace_back([&f, t, a, b] { f(t, a, b); });
+  }
+  for (auto& x : th) x.join();
+}
+
+inline void atomic_add(double* p, double v) {
+  uint64_t* q = reinterpret_cast<uint64_t*>(p);
+  uint64_t old = __atomic_load_n(q, __ATOMIC_RELAXED);
+  for (;;) {
+    double d;
+    std::memcpy(&d, &old, sizeof(d));
+    d += v;
+    uint64_t want;
+    std::memcpy(&want, &d, sizeof(d));
+    if (__atomic_compare_exchange_n(q, &old, want, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) return;
+  }
+}
+
 struct Csr {
   const int64_t* rowptr;
   const int32_t* col;
@@ -366,7 +404,8 @@ struct Csr {
     const int32_t* b = col + rowptr[row];
     const int32_t* e = col + rowptr[row + 1];
     const int32_t* it = std::lower_bound(b, e, c);
-    val[it - col] += v;
+    if (g_threads > 1) atomic_add(val + (it - col), v);
+    else val[it - col] += v;
   }
 };
 
@@ -535,7 +574,8 @@ void or_assemble_lhs(int kind, int polorder, int nc, int nv, const double* xy, c
   const double beta = 1.0;  // default_beta(dimDomain) = 1/(d-1), discretizations/swipdg.hh:168
   const Rule2 vol = kind == SIMPLEX ? triangle_rule(factor->order + 2 * (p - 1)) : square_rule(factor->order + 2 * (p - 1));
   const Rule1 fr = line_rule(factor->order + 2 * p);
-  for (int c = 0; c < nc; ++c) {
+  parallel_chunks(nc, [&](int, int64_t c_begin, int64_t c_end) {
+  for (int c = int(c_begin); c < int(c_end); ++c) {
     const Cell g = load_cell(m, c);
     double K[4];
     tensor_of(tensor, c, K);
@@ -608,6 +648,7 @@ void or_assemble_lhs(int kind, int polorder, int nc, int nv, const double* xy, c
       }
     }
   }
+  });
 }
 
 // ---- a7/a8/a9: rhs ---------------------------------------------------------------------------
@@ -620,7 +661,8 @@ void or_assemble_rhs(int kind, int polorder, int nc, int nv, const double* xy, c
                      const double* tensor, const uint8_t* bnd_type, double* b) {
   Mesh m{kind, nc, nv, xy, cv, nb, polorder};
   const int nl = m.nl(), nf = m.nf(), p = polorder;
-  for (int c = 0; c < nc; ++c) {
+  parallel_chunks(nc, [&](int, int64_t c_begin, int64_t c_end) {
+  for (int c = int(c_begin); c < int(c_end); ++c) {
     const Cell g = load_cell(m, c);
     if (force) {
       const Rule2 vol = kind == SIMPLEX ? triangle_rule(force->order + p) : square_rule(force->order + p);
@@ -670,6 +712,7 @@ void or_assemble_rhs(int kind, int polorder, int nc, int nv, const double* xy, c
       }
     }
   }
+  });
 }
 
 // ---- products (8f rank 1; discretizations/swipdg.hh:359-479, block-swipdg.hh:392-548) ----------------------
@@ -782,12 +825,17 @@ void or_assemble_product(int kind, int polorder, int nc, int nv, const double* x
 // ---- a14: linear solve ---------------------------------------------------------------------
 // Stuff::LA::Solver<Matrix>(A).apply(rhs, x, options) (discretizations/base.hh:344,361-364), with
 // the method fixed to (Jacobi-)preconditioned CG by BASELINE.json north_star.
+void or_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
+int or_get_threads() { return g_threads; }
+
 void or_spmv(int64_t n, const int64_t* rowptr, const int32_t* col, const double* val, const double* x, double* y) {
-  for (int64_t r = 0; r < n; ++r) {
-    double s = 0.0;
-    for (int64_t k = rowptr[r]; k < rowptr[r + 1]; ++k) s += val[k] * x[col[k]];
-    y[r] = s;
-  }
+  parallel_chunks(n, [&](int, int64_t a, int64_t b) {
+    for (int64_t r = a; r < b; ++r) {
+      double s = 0.0;
+      for (int64_t k = rowptr[r]; k < rowptr[r + 1]; ++k) s += val[k] * x[col[k]];
+      y[r] = s;
+    }
+  });
 }
 
 // precond: 0 identity, 1 diagonal.  Stops when ||r||_2 <= rtol * ||b||_2 (recursive residual).
@@ -812,23 +860,40 @@ int or_cg(int64_t n, const int64_t* rowptr, const int32_t* col, const double* va
   if (bb == 0.0) { for (int64_t i = 0; i < n; ++i) x[i] = 0.0; if (relres) *relres = 0.0; return 0; }
   int it = 0;
   if (history) history[0] = std::sqrt(rr / bb);
+  const int nt = std::max(1, g_threads);
+  std::vector<double> part(size_t(2) * nt);
   while (it < maxit && rr > rtol * rtol * bb) {
     or_spmv(n, rowptr, col, val, p.data(), q.data());
+    std::fill(part.begin(), part.end(), 0.0);
+    parallel_chunks(n, [&](int t, int64_t a, int64_t e) {
+      double s = 0.0;
+      for (int64_t i = a; i < e; ++i) s += p[i] * q[i];
+      part[size_t(t)] = s;
+    });
     double pq = 0.0;
-    for (int64_t i = 0; i < n; ++i) pq += p[i] * q[i];
+    for (int t = 0; t < nt; ++t) pq += part[size_t(t)];
     const double alpha = rz / pq;
+    std::fill(part.begin(), part.end(), 0.0);
+    parallel_chunks(n, [&](int t, int64_t a, int64_t e) {
+      double s_rr = 0.0, s_rz = 0.0;
+      for (int64_t i = a; i < e; ++i) {
+        x[i] += alpha * p[i];
+        r[i] -= alpha * q[i];
+        z[i] = dinv[i] * r[i];
+        s_rr += r[i] * r[i];
+        s_rz += r[i] * z[i];
+      }
+      part[size_t(2) * t] = s_rr;
+      part[size_t(2) * t + 1] = s_rz;
+    });
     double rz_new = 0.0;
     rr = 0.0;
-    for (int64_t i = 0; i < n; ++i) {
-      x[i] += alpha * p[i];
-      r[i] -= alpha * q[i];
-      z[i] = dinv[i] * r[i];
-      rr += r[i] * r[i];
-      rz_new += r[i] * z[i];
-    }
+    for (int t = 0; t < nt; ++t) { rr += part[size_t(2) * t]; rz_new += part[size_t(2) * t + 1]; }
     const double beta_cg = rz_new / rz;
     rz = rz_new;
-    for (int64_t i = 0; i < n; ++i) p[i] = z[i] + beta_cg * p[i];
+    parallel_chunks(n, [&](int, int64_t a, int64_t e) {
+      for (int64_t i = a; i < e; ++i) p[i] = z[i] + beta_cg * p[i];
+    });
     ++it;
     if (history) history[it] = std::sqrt(rr / bb);
   }

@@ -90,3 +90,21 @@ def test_neumann_rhs_integrates_the_data_over_the_neumann_faces():
             total += np.linalg.norm(e - a) * (1.0 + 0.5 * (a[1] + e[1]))
         assert abs(b.sum() - total) <= 1e-12
         assert np.all(o.assemble_rhs(m, None, neumann=gn) == 0.0)  # AllDirichlet: no Neumann faces
+
+
+def test_threaded_oracle_equals_the_serial_walk():
+    """or_set_threads only changes who adds which entry (atomically): same matrix, rhs and CG iterates to rounding"""
+    m = o.mesh_cube(48, 48, -1.0, 1.0, -1.0, 1.0)
+    rp, col = o.pattern(m)
+    A1 = o.assemble_lhs(m, o.const(1.0), None, rp, col)
+    b1 = o.assemble_rhs(m, o.esv2007_force())
+    x1, it1, _ = o.cg(rp, col, A1, b1, precond=1, rtol=1e-30, maxit=30)
+    try:
+        o.set_threads(4)
+        A4 = o.assemble_lhs(m, o.const(1.0), None, rp, col)
+        b4 = o.assemble_rhs(m, o.esv2007_force())
+        x4, it4, _ = o.cg(rp, col, A4, b4, precond=1, rtol=1e-30, maxit=30)
+    finally:
+        o.set_threads(1)
+    assert np.abs(A1 - A4).max() <= 1e-14 * np.abs(A1).max() and np.array_equal(b1, b4)
+    assert it1 == it4 and np.abs(x1 - x4).max() <= 1e-11 * np.abs(x1).max()
