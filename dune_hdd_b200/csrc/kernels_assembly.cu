@@ -1107,19 +1107,18 @@ void launch_assemble_lhs(const MeshView& m, const DevFn& factor_dev, int factor_
   const LineRule fr = line_rule(factor_order + 2 * polorder);
   const double si = sigma_inner(polorder), sb = sigma_boundary(polorder);
   const int blocks = grid_for(m.n_own, kThreads);
+  // HDD_ASSEMBLY_GENERIC=1 / HDD_ASM_TENSOR=0: run a cube grid through the generic kernel / without the tensor-grid
+  // tables (kept for A/B measurements and as cross-checks of the specialised variants)
   static const bool generic_cube = [] { const char* e = std::getenv("HDD_ASSEMBLY_GENERIC"); return e && e[0] == '1'; }();
+  static const bool tensor_ok = [] { const char* e = std::getenv("HDD_ASM_TENSOR"); return !(e && e[0] == '0'); }();
   if (polorder != 1) {
-    // p = 2: one thread per row
+    // p = 2: one thread per row, 3 CTAs per SM (168 registers; 2.85 ms vs 3.48 ms with 2 at 1024^2 Q2)
     const int64_t rows = int64_t(m.n_own) * m.nl;
     dispatch_elem(m.kind, polorder, [&](auto kind, auto p) {
-      static const int minb = [] { const char* e = std::getenv("HDD_ASM_ROWS_MINB"); return e ? std::atoi(e) : 3; }();
       if constexpr (decltype(p)::value == 2)
         dispatch_fk(factor_kind, [&](auto k) {
-          constexpr int KD = decltype(kind)::value, FKV = decltype(k)::value;
-          const int g = grid_for(rows, kThreads);
-          if (minb == 3) k_assemble_rows<KD, 2, FKV, 0, 3><<<g, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
-          else if (minb == 4) k_assemble_rows<KD, 2, FKV, 0, 4><<<g, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
-          else k_assemble_rows<KD, 2, FKV, 0, 2><<<g, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+          k_assemble_rows<decltype(kind)::value, 2, decltype(k)::value, 0, 3>
+              <<<grid_for(rows, kThreads), kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
         });
     });
   } else if (m.kind == HDD_SIMPLEX2D) {
@@ -1128,21 +1127,14 @@ void launch_assemble_lhs(const MeshView& m, const DevFn& factor_dev, int factor_
     assemble_dispatch<HDD_CUBE2D>(factor_kind, blocks, s, m, factor_dev, vol, fr, si, sb, values);
   } else {
     // resident CTAs per SM the kernel is compiled for: 3 (160 registers) for the general kernel, 4 (128) for the tensor
-    // grid variant, which keeps no neighbour geometry records alive (measured 2.15 -> 2.03 ms at 4096^2)
-    static const int minb_env = [] { const char* e = std::getenv("HDD_ASM_MINB"); return e ? std::atoi(e) : 0; }();
+    // grid variant, which keeps no neighbour geometry records alive (measured 2.15 -> 2.03 ms at 4096^2; 5 CTAs spill:
+    // 2.81 ms)
     dispatch_fk(factor_kind, [&](auto k) {
       constexpr int FKV = decltype(k)::value;
-      static const bool tensor_ok = [] { const char* e = std::getenv("HDD_ASM_TENSOR"); return !(e && e[0] == '0'); }();
-      const int minb = minb_env ? minb_env : ((m.tgeo && tensor_ok) ? 4 : 3);
-      if (m.tgeo && tensor_ok) {
-        if (minb == 3) k_assemble_lhs_cube<FKV, 3, true><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
-        else if (minb == 5) k_assemble_lhs_cube<FKV, 5, true><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
-        else k_assemble_lhs_cube<FKV, 4, true><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
-      } else if (minb == 4) {
-        k_assemble_lhs_cube<FKV, 4, false><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
-      } else {
+      if (m.tgeo && tensor_ok)
+        k_assemble_lhs_cube<FKV, 4, true><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+      else
         k_assemble_lhs_cube<FKV, 3, false><<<blocks, kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
-      }
     });
   }
   count_launch();
