@@ -1,6 +1,6 @@
 """Scale runs of the BASELINE configs that are not the bench line (one GPU), JSON on stdout:
-    python tests/config_runs.py spe10 [nx ny]     config 2 scaled up: SPE10-shaped Q1 grid, synthetic log-normal permeability
-    python tests/config_runs.py p2 [n] [iters]    config 5, polOrder 2 (Q2) on the n x n grid: assembly + CG per-iteration times
+    python tools/config_runs.py spe10 [nx ny]     config 2 scaled up: SPE10-shaped Q1 grid, synthetic log-normal permeability
+    python tools/config_runs.py p2 [n] [iters]    config 5, polOrder 2 (Q2) on the n x n grid: assembly + CG per-iteration times
 """
 import ctypes as C
 import json

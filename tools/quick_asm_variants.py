@@ -1,4 +1,4 @@
-"""assembly kernel timing for the current HDD_ASM_* environment: python tests/quick_asm_variants.py n polorder kind"""
+"""assembly kernel timing for the current HDD_ASM_* environment: python tools/quick_asm_variants.py n polorder kind"""
 import sys, json, ctypes as C
 sys.path.insert(0, '.')
 import dune_hdd_b200 as hdd

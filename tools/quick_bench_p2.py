@@ -1,4 +1,4 @@
-"""p = 2 timing on one GPU: python tests/quick_bench_p2.py [cells per side] [cube|simplex] [cg iterations]"""
+"""p = 2 timing on one GPU: python tools/quick_bench_p2.py [cells per side] [cube|simplex] [cg iterations]"""
 import sys, time, json
 import numpy as np
 sys.path.insert(0, '.')
