@@ -43,7 +43,7 @@ struct MeshView {
   const int64_t* blk_start; // [n_own+1] number of matrix blocks in front of owned cell k
   const int32_t* cgid;      // [n_loc] global cell id
   // logically structured (tensor-product) cube grid, nullptr / 0 otherwise: vertex 0 of every local cell and the
-  // one-dimensional geometry tables {x0, hx} per column [tnx] followed by {y0, hy} per row [tny]
+  // one-dimensional geometry tables {x0, hx, 1/hx, -} per column [tnx] followed by {y0, hy, 1/hy, -} per row [tny]
   const int32_t* cell_v0;
   const double* tgeo;
   int tnx, tny;

@@ -79,7 +79,7 @@ struct hdd_mesh {
   // vertex 0 of every cell and the map lexicographic cell -> cell; feeds the multigrid preconditioner ("cg.mg")
   int sx = 0, sy = 0;
   hdd::DevBuf<int32_t> cell_v0, lex_cell;
-  hdd::DevBuf<double> tgeo;  // {x0, hx} per column, {y0, hy} per row
+  hdd::DevBuf<double> tgeo;  // {x0, hx, 1/hx, -} per column, {y0, hy, 1/hy, -} per row
   bool purely_neumann = false;  // no Dirichlet face anywhere (DirichletDetector, discretizations/swipdg.hh:219-220,488-489)
 
   // multi GPU

@@ -444,20 +444,20 @@ __device__ __forceinline__ void assemble_cube_cell(const MeshView& m, const DevF
   double nihx[NF], nihy[NF];
   if constexpr (TENSOR) {
     const int cx = v0 % (m.tnx + 1), cy = v0 / (m.tnx + 1);
-    const double2* tx = reinterpret_cast<const double2*>(m.tgeo);
-    const double2* ty = tx + m.tnx;
-    const double2 ox = __ldg(tx + cx), oy = __ldg(ty + cy);
-    g.x0 = ox.x; g.hx = ox.y; g.x1 = ox.x + ox.y;
-    g.y0 = oy.x; g.hy = oy.y; g.y1 = oy.x + oy.y;
-    g.ihx = 1.0 / g.hx; g.ihy = 1.0 / g.hy;
+    const double* tx = m.tgeo;                      // 4 doubles per column: x0, hx, 1/hx, -
+    const double* ty = m.tgeo + 4 * size_t(m.tnx);  // 4 doubles per row:    y0, hy, 1/hy, -
+    const double2 ox = __ldg(reinterpret_cast<const double2*>(tx + 4 * cx));
+    const double2 oy = __ldg(reinterpret_cast<const double2*>(ty + 4 * cy));
+    g.x0 = ox.x; g.hx = ox.y; g.x1 = ox.x + ox.y; g.ihx = __ldg(tx + 4 * cx + 2);
+    g.y0 = oy.x; g.hy = oy.y; g.y1 = oy.x + oy.y; g.ihy = __ldg(ty + 4 * cy + 2);
     g.detj = fabs(g.hx * g.hy);
     // left / right neighbours share the row, bottom / top neighbours the column
-    nihx[0] = 1.0 / __ldg(tx + max(cx - 1, 0)).y;
-    nihx[1] = 1.0 / __ldg(tx + min(cx + 1, m.tnx - 1)).y;
+    nihx[0] = __ldg(tx + 4 * max(cx - 1, 0) + 2);
+    nihx[1] = __ldg(tx + 4 * min(cx + 1, m.tnx - 1) + 2);
     nihx[2] = nihx[3] = g.ihx;
     nihy[0] = nihy[1] = g.ihy;
-    nihy[2] = 1.0 / __ldg(ty + max(cy - 1, 0)).y;
-    nihy[3] = 1.0 / __ldg(ty + min(cy + 1, m.tny - 1)).y;
+    nihy[2] = __ldg(ty + 4 * max(cy - 1, 0) + 2);
+    nihy[3] = __ldg(ty + 4 * min(cy + 1, m.tny - 1) + 2);
   } else {
     g.load(m.cgeo, c);
   }
@@ -820,7 +820,7 @@ __global__ void k_rhs_tensor_moments(const __grid_constant__ DevFn fn, LineRule 
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nx + ny) return;
   const bool is_x = t < nx;
-  const double2 oh = reinterpret_cast<const double2*>(geo)[t];
+  const double2 oh = reinterpret_cast<const double2*>(geo)[2 * size_t(t)];  // {origin, size} of column / row t
   double acc[P + 1];
 #pragma unroll
   for (int a = 0; a <= P; ++a) acc[a] = 0.0;

@@ -76,19 +76,20 @@ __global__ void k_struct_verts(const double* __restrict__ xy, int32_t n_verts, i
   if (p.x != px.x || p.y != py.y) atomicOr(flag, 2);
 }
 
-// one-dimensional geometry of the tensor grid: {x0, hx} per column, {y0, hy} per row, from the vertex coordinates
+// one-dimensional geometry of the tensor grid from the vertex coordinates: {x0, hx, 1/hx, -} per column followed by
+// {y0, hy, 1/hy, -} per row (the reciprocals save the assembly kernel six of its ten fp64 divisions per cell)
 __global__ void k_struct_geo(const double* __restrict__ xy, int nx, int ny, double* __restrict__ tgeo) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nx + ny) return;
   const int nx1 = nx + 1;
-  double2* out = reinterpret_cast<double2*>(tgeo);
+  double4* out = reinterpret_cast<double4*>(tgeo);
   if (t < nx) {
     const double x0 = xy[2 * size_t(t)], x1 = xy[2 * size_t(t + 1)];
-    out[t] = make_double2(x0, x1 - x0);
+    out[t] = make_double4(x0, x1 - x0, 1.0 / (x1 - x0), 0.0);
   } else {
     const int r = t - nx;
     const double y0 = xy[2 * size_t(r) * nx1 + 1], y1 = xy[2 * size_t(r + 1) * nx1 + 1];
-    out[t] = make_double2(y0, y1 - y0);
+    out[t] = make_double4(y0, y1 - y0, 1.0 / (y1 - y0), 0.0);
   }
 }
 
@@ -443,7 +444,7 @@ void mg_detect_structure(hdd_mesh* m, const double* xy_host, const double* xy_de
   flag.zero(s);
   k_struct_cells<<<blocks_for(m->n_loc), kMgThreads, 0, s>>>(cv_dev, m->n_loc, int(nx), int(ny), m->cell_v0.p, m->lex_cell.p, flag.p);
   k_struct_verts<<<blocks_for(n_verts), kMgThreads, 0, s>>>(xy_dev, int32_t(n_verts), int(nx), flag.p);
-  m->tgeo.alloc(2 * size_t(nx + ny));
+  m->tgeo.alloc(4 * size_t(nx + ny));
   k_struct_geo<<<blocks_for(nx + ny), kMgThreads, 0, s>>>(xy_dev, int(nx), int(ny), m->tgeo.p);
   count_launch(3);
   int32_t f = 0;
