@@ -18,16 +18,19 @@
 // structured grids of BASELINE configs 2 and 5.  Everything is additive and symmetric, so CG stays applicable; all
 // reductions are deterministic.
 //
-// Multi GPU: the DG level (SpMV, block Jacobi, restriction, prolongation) is distributed like the rest of the solve; the
-// vertex hierarchy is replicated - every rank assembles the rows of A_c its cells contribute to, one all-reduce makes
-// the level-0 stencil global (once per solve), and per application one all-reduce of the restricted residual (8 B per
-// vertex) feeds identical V-cycles on every rank.  No halo exchange inside the V-cycle; the coarse work does not scale
-// with the GPU count, the 85 % of the iteration that lives on the DG level does.
+// Multi GPU: the DG level (SpMV, block Jacobi, restriction, prolongation) is distributed like the rest of the solve.
+// The vertex-level operators are replicated (one all-reduce per solve makes the level-0 stencil global); when the ranks'
+// cells are full-width bands of rows stacked in rank order (the slabs bench.py deals out), the vectors of the two finest
+// vertex levels are swept in row strips with one halo row exchanged per sweep (grouped ncclSend/ncclRecv with the rank
+// below / above), the level-2 right-hand side is summed over the ranks and levels >= 2 run replicated.  Otherwise the
+// whole V-cycle runs replicated on the all-reduced restricted residual.
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 #include <ctime>
 
 #include "handles.hpp"
@@ -42,6 +45,12 @@ constexpr int kMaxCoarse = 400;   // dense coarsest solve up to this many vertic
 constexpr double kOmega = 0.8;    // Jacobi damping on the vertex levels
 
 inline int blocks_for(int64_t n) { return int((n + kMgThreads - 1) / kMgThreads); }
+
+// The vertices (linear index range = whole grid rows) a kernel launch works on: the whole level, or - for the levels
+// that are distributed over the GPUs - the row strip this rank owns.
+struct Rows {
+  int64_t beg, cnt;
+};
 
 __device__ __forceinline__ void load_neigh4(const int32_t* neigh, int k, int* nb) {
   const int4 v = __ldg(reinterpret_cast<const int4*>(neigh) + k);
@@ -98,10 +107,11 @@ __global__ void k_struct_geo(const double* __restrict__ xy, int nx, int ny, doub
 // index distance 2 cancel analytically (inner-face jumps of continuous functions) and are dropped.
 __global__ void __launch_bounds__(kMgThreads)
     k_vertex_galerkin(MeshView m, const double* __restrict__ vals, const int32_t* __restrict__ cell_v0,
-                      const int32_t* __restrict__ lex_cell, int nx, int ny, double* __restrict__ S) {
+                      const int32_t* __restrict__ lex_cell, int nx, int ny, Rows rg, double* __restrict__ S) {
   const int64_t nv = int64_t(nx + 1) * (ny + 1);
-  const int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (v >= nv) return;
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (tid >= rg.cnt) return;
+  const int64_t v = rg.beg + tid;
   const int nx1 = nx + 1;
   const int ix = int(v % nx1), iy = int(v / nx1);
   double acc[9];
@@ -141,10 +151,11 @@ __global__ void __launch_bounds__(kMgThreads)
 }
 
 // b1 = C b0 after the all-reduce of b0 (multi GPU)
-__global__ void k_twist_vector(const int* done, const double* __restrict__ b0, int nx, int64_t nv, double* __restrict__ b1) {
+__global__ void k_twist_vector(const int* done, const double* __restrict__ b0, int nx, Rows rg, double* __restrict__ b1) {
   if (done && *done) return;
-  const int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (v >= nv) return;
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (tid >= rg.cnt) return;
+  const int64_t v = rg.beg + tid;
   const int nx1 = nx + 1;
   b1[v] = ((int(v % nx1) + int(v / nx1)) & 1) ? -b0[v] : b0[v];
 }
@@ -193,13 +204,14 @@ __global__ void __launch_bounds__(kMgThreads)
 // ---- V-cycle kernels.  done: convergence latch of the CG iteration that owns this application (see k_cg_*) ----------
 // pre-smoothing from a zero guess, x = w D^-1 b, fused with the residual r = b - A x
 __global__ void __launch_bounds__(kMgThreads)
-    k_mg_pre(const int* done, const double* __restrict__ S, const double* __restrict__ dinv, int nx, int ny,
+    k_mg_pre(const int* done, const double* __restrict__ S, const double* __restrict__ dinv, int nx, int ny, Rows rg,
              const double* __restrict__ b, double* __restrict__ x, double* __restrict__ r) {
   if (done && *done) return;
   const int nx1 = nx + 1;
   const int64_t nv = int64_t(nx1) * (ny + 1);
-  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= nv) return;
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (tid >= rg.cnt) return;
+  const int64_t i = rg.beg + tid;
   const int ix = int(i % nx1), iy = int(i / nx1);
   double ax = 0.0;
 #pragma unroll
@@ -218,12 +230,12 @@ __global__ void __launch_bounds__(kMgThreads)
 
 // full weighting: b_H = P^T r
 __global__ void __launch_bounds__(kMgThreads)
-    k_mg_restrict(const int* done, const double* __restrict__ r, int nxf, int nyf, double* __restrict__ bc) {
+    k_mg_restrict(const int* done, const double* __restrict__ r, int nxf, int nyf, Rows rg /* coarse */, double* __restrict__ bc) {
   if (done && *done) return;
-  const int nxc = nxf / 2, nyc = nyf / 2;
-  const int64_t nvc = int64_t(nxc + 1) * (nyc + 1);
-  const int64_t I = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (I >= nvc) return;
+  const int nxc = nxf / 2;
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (tid >= rg.cnt) return;
+  const int64_t I = rg.beg + tid;
   const int IX = int(I % (nxc + 1)), IY = int(I / (nxc + 1));
   double s = 0.0;
 #pragma unroll
@@ -239,12 +251,12 @@ __global__ void __launch_bounds__(kMgThreads)
 
 // x += P x_H (bilinear interpolation)
 __global__ void __launch_bounds__(kMgThreads)
-    k_mg_prolong_add(const int* done, const double* __restrict__ xc, int nxf, int nyf, double* __restrict__ x) {
+    k_mg_prolong_add(const int* done, const double* __restrict__ xc, int nxf, Rows rg /* fine */, double* __restrict__ x) {
   if (done && *done) return;
   const int nxc = nxf / 2;
-  const int64_t nvf = int64_t(nxf + 1) * (nyf + 1);
-  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= nvf) return;
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (tid >= rg.cnt) return;
+  const int64_t i = rg.beg + tid;
   const int fx = int(i % (nxf + 1)), fy = int(i / (nxf + 1));
   const int cx = fx >> 1, cy = fy >> 1;
   const int ox = fx & 1, oy = fy & 1;
@@ -260,13 +272,14 @@ __global__ void __launch_bounds__(kMgThreads)
 
 // post-smoothing: y = x + w D^-1 (b - A x)
 __global__ void __launch_bounds__(kMgThreads)
-    k_mg_post(const int* done, const double* __restrict__ S, const double* __restrict__ dinv, int nx, int ny,
+    k_mg_post(const int* done, const double* __restrict__ S, const double* __restrict__ dinv, int nx, int ny, Rows rg,
               const double* __restrict__ b, const double* __restrict__ x, double* __restrict__ y) {
   if (done && *done) return;
   const int nx1 = nx + 1;
   const int64_t nv = int64_t(nx1) * (ny + 1);
-  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= nv) return;
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (tid >= rg.cnt) return;
+  const int64_t i = rg.beg + tid;
   const int ix = int(i % nx1), iy = int(i / nx1);
   double ax = 0.0;
 #pragma unroll
@@ -284,14 +297,15 @@ __global__ void __launch_bounds__(kMgThreads)
 // (e odd), so the nine coefficient arrays - three quarters of the bytes of a smoothing sweep - are read once for
 // the plain and the twisted hierarchy.
 __global__ void __launch_bounds__(kMgThreads)
-    k_mg_pre2(const int* done, const double* __restrict__ S, const double* __restrict__ dinv, int nx, int ny,
+    k_mg_pre2(const int* done, const double* __restrict__ S, const double* __restrict__ dinv, int nx, int ny, Rows rg,
               const double* __restrict__ b0, const double* __restrict__ b1, double* __restrict__ x0, double* __restrict__ x1,
               double* __restrict__ r0, double* __restrict__ r1) {
   if (done && *done) return;
   const int nx1 = nx + 1;
   const int64_t nv = int64_t(nx1) * (ny + 1);
-  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= nv) return;
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (tid >= rg.cnt) return;
+  const int64_t i = rg.beg + tid;
   const int ix = int(i % nx1), iy = int(i / nx1);
   double a0 = 0.0, a1 = 0.0;
 #pragma unroll
@@ -313,14 +327,15 @@ __global__ void __launch_bounds__(kMgThreads)
 }
 
 __global__ void __launch_bounds__(kMgThreads)
-    k_mg_post2(const int* done, const double* __restrict__ S, const double* __restrict__ dinv, int nx, int ny,
+    k_mg_post2(const int* done, const double* __restrict__ S, const double* __restrict__ dinv, int nx, int ny, Rows rg,
                const double* __restrict__ b0, const double* __restrict__ b1, const double* __restrict__ x0,
                const double* __restrict__ x1, double* __restrict__ y0, double* __restrict__ y1) {
   if (done && *done) return;
   const int nx1 = nx + 1;
   const int64_t nv = int64_t(nx1) * (ny + 1);
-  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= nv) return;
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (tid >= rg.cnt) return;
+  const int64_t i = rg.beg + tid;
   const int ix = int(i % nx1), iy = int(i / nx1);
   double a0 = 0.0, a1 = 0.0;
 #pragma unroll
@@ -360,12 +375,12 @@ __global__ void k_mg_dense(const int* done, const double* __restrict__ Ainv, int
 // rc = P^T r (sum of the DG residual entries sitting on each vertex) and its checkerboard-signed copy
 __global__ void __launch_bounds__(kMgThreads)
     k_dg_restrict(const int* done, const double* __restrict__ r, const int32_t* __restrict__ lex_cell, int own0,
-                  int n_own, int nx, int ny, double* __restrict__ b0, double* __restrict__ b1) {
+                  int n_own, int nx, int ny, Rows rg, double* __restrict__ b0, double* __restrict__ b1) {
   if (done && *done) return;
   const int nx1 = nx + 1;
-  const int64_t nv = int64_t(nx1) * (ny + 1);
-  const int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (v >= nv) return;
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (tid >= rg.cnt) return;
+  const int64_t v = rg.beg + tid;
   const int ix = int(v % nx1), iy = int(v / nx1);
   double s = 0.0;
 #pragma unroll
@@ -380,6 +395,21 @@ __global__ void __launch_bounds__(kMgThreads)
     }
   b0[v] = s;
   if (b1) b1[v] = ((ix + iy) & 1) ? -s : s;
+}
+
+// dst += src over one grid row (the neighbour's share of a vertex row both ranks contribute to); min / max cell row
+__global__ void k_add_row(const int* done, double* __restrict__ dst, const double* __restrict__ src, int n) {
+  if (done && *done) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) dst[t] += src[t];
+}
+
+__global__ void k_cell_row_range(const int32_t* __restrict__ cell_v0_owned, int32_t n_own, int nx, int* __restrict__ minmax) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_own) return;
+  const int cy = __ldg(cell_v0_owned + k) / (nx + 1);
+  atomicMin(minmax, cy);
+  atomicMax(minmax + 1, cy);
 }
 
 // z += P (x0 + C x1), r.z recomputed; optionally p = z (first direction).  One thread per cell, 256-bit accesses.
@@ -422,10 +452,53 @@ struct MgHierarchy {
   DevBuf<double> coarse_inv;
 };
 
+// Multi GPU: the two finest vertex levels are swept in row strips.  The operators (S, dinv) stay replicated - they
+// are static during a solve and one all-reduce per solve makes them global - only the vectors b, x, r of levels 0 and 1
+// are computed strip-wise, on full-size arrays, so a halo row lives at the same index on every rank and an exchange is
+// "send my first / last owned row, receive the neighbour's into the row next to my strip".  Level 2 and below run
+// replicated on the all-reduced level-2 right-hand side.
+struct MgDist {
+  bool on = false;
+  int lower = -1, upper = -1;  // ranks owning the strips below / above (-1: none)
+  int c0 = 0, c1 = 0;          // owned cell rows [c0, c1) of level 0
+  bool last = false;           // the top strip also owns the last vertex row
+  DevBuf<double> tmp;          // one level-0 row
+};
+
 struct MgState {
   MgHierarchy h[2];  // plain and checkerboard-twisted
   int nx = 0, ny = 0;
+  MgDist dist;
 };
+
+static Rows level_rows(const MgState& st, const MgLevel& L, int l) {
+  if (!st.dist.on || l >= 2) return Rows{0, L.nv};
+  const int v0 = st.dist.c0 >> l, v1 = (st.dist.c1 >> l) + (st.dist.last ? 1 : 0);
+  return Rows{int64_t(v0) * (L.nx + 1), int64_t(v1 - v0) * (L.nx + 1)};
+}
+
+enum { EX_UP = 1, EX_DOWN = 2 };
+// EX_UP: my last owned row goes to the rank above, the last row of the rank below arrives in the row under my strip.
+// EX_DOWN: my first owned row goes to the rank below, the first row of the rank above arrives in the row over my strip.
+static void exchange_rows(hdd_mesh* m, const MgState& st, const MgLevel& L, int l, std::initializer_list<double*> arrays, int dirs) {
+  const MgDist& d = st.dist;
+  if (!d.on || (d.lower < 0 && d.upper < 0)) return;
+  const int nx1 = L.nx + 1;
+  const int64_t v0 = d.c0 >> l, v1 = (d.c1 >> l) + (d.last ? 1 : 0);
+  Nccl& nc = Nccl::get();
+  nc.group_start();
+  for (double* a : arrays) {
+    if (dirs & EX_UP) {
+      if (d.upper >= 0) nc.send(a + (v1 - 1) * nx1, size_t(nx1), d.upper, m->comm, m->stream);
+      if (d.lower >= 0) nc.recv(a + (v0 - 1) * nx1, size_t(nx1), d.lower, m->comm, m->stream);
+    }
+    if (dirs & EX_DOWN) {
+      if (d.lower >= 0) nc.send(a + v0 * nx1, size_t(nx1), d.lower, m->comm, m->stream);
+      if (d.upper >= 0) nc.recv(a + v1 * nx1, size_t(nx1), d.upper, m->comm, m->stream);
+    }
+  }
+  nc.group_end();
+}
 
 void mg_detect_structure(hdd_mesh* m, const double* xy_host, const double* xy_dev, const int32_t* cv_dev, int64_t n_verts) {
   m->sx = m->sy = 0;
@@ -519,14 +592,14 @@ static void build_hierarchy(hdd_swipdg* h, MgHierarchy& H, const double* S0, boo
   HDD_CUDA(cudaStreamSynchronize(s));
 }
 
-// levels l0 .. coarsest of one hierarchy: down, dense solve, up; leaves the result in levels[l0]->x
+// levels l0 .. coarsest of one hierarchy, all of them replicated: down, dense solve, up; result in levels[l0]->x
 static void vcycle_from(MgHierarchy& H, int l0, const int* done, cudaStream_t s) {
   const int nl = int(H.levels.size());
   for (int l = l0; l + 1 < nl; ++l) {
     MgLevel& L = *H.levels[size_t(l)];
     MgLevel& Cn = *H.levels[size_t(l) + 1];
-    k_mg_pre<<<blocks_for(L.nv), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, L.b.p, L.x.p, L.r.p);
-    k_mg_restrict<<<blocks_for(Cn.nv), kMgThreads, 0, s>>>(done, L.r.p, L.nx, L.ny, Cn.b.p);
+    k_mg_pre<<<blocks_for(L.nv), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, Rows{0, L.nv}, L.b.p, L.x.p, L.r.p);
+    k_mg_restrict<<<blocks_for(Cn.nv), kMgThreads, 0, s>>>(done, L.r.p, L.nx, L.ny, Rows{0, Cn.nv}, Cn.b.p);
     count_launch(2);
   }
   MgLevel& C = *H.levels.back();
@@ -535,31 +608,110 @@ static void vcycle_from(MgHierarchy& H, int l0, const int* done, cudaStream_t s)
   for (int l = nl - 2; l >= l0; --l) {
     MgLevel& L = *H.levels[size_t(l)];
     MgLevel& Cn = *H.levels[size_t(l) + 1];
-    k_mg_prolong_add<<<blocks_for(L.nv), kMgThreads, 0, s>>>(done, Cn.x.p, L.nx, L.ny, L.x.p);
-    k_mg_post<<<blocks_for(L.nv), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, L.b.p, L.x.p, L.y.p);
+    k_mg_prolong_add<<<blocks_for(L.nv), kMgThreads, 0, s>>>(done, Cn.x.p, L.nx, Rows{0, L.nv}, L.x.p);
+    k_mg_post<<<blocks_for(L.nv), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, Rows{0, L.nv}, L.b.p, L.x.p, L.y.p);
     count_launch(2);
     std::swap(L.x.p, L.y.p);  // the smoothed iterate is the level's x from here on
   }
 }
 
+// Level 1 of one hierarchy and everything below it.  Replicated: plain V-cycle.  Distributed: level 1 in row strips,
+// the level-2 right-hand side is summed over the ranks (every rank restricts its own rows into a zeroed array) and
+// levels >= 2 run replicated.
+static void vcycle_level1(hdd_mesh* m, MgState& st, MgHierarchy& H, const int* done, cudaStream_t s) {
+  if (!st.dist.on) {
+    vcycle_from(H, 1, done, s);
+    return;
+  }
+  MgLevel& L = *H.levels[1];
+  MgLevel& Cn = *H.levels[2];
+  const Rows r1 = level_rows(st, L, 1);
+  const int W0 = st.dist.c0 >> 2, W1 = (st.dist.c1 >> 2) + (st.dist.last ? 1 : 0);
+  const Rows r2own{int64_t(W0) * (Cn.nx + 1), int64_t(W1 - W0) * (Cn.nx + 1)};
+  exchange_rows(m, st, L, 1, {L.b.p}, EX_UP | EX_DOWN);
+  k_mg_pre<<<blocks_for(r1.cnt), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, r1, L.b.p, L.x.p, L.r.p);
+  exchange_rows(m, st, L, 1, {L.r.p}, EX_UP);
+  HDD_CUDA(cudaMemsetAsync(Cn.b.p, 0, size_t(Cn.nv) * sizeof(double), s));
+  k_mg_restrict<<<blocks_for(r2own.cnt), kMgThreads, 0, s>>>(done, L.r.p, L.nx, L.ny, r2own, Cn.b.p);
+  Nccl::get().all_reduce_sum(Cn.b.p, size_t(Cn.nv), m->comm, s);
+  count_launch(2);
+  vcycle_from(H, 2, done, s);
+  k_mg_prolong_add<<<blocks_for(r1.cnt), kMgThreads, 0, s>>>(done, Cn.x.p, L.nx, r1, L.x.p);
+  exchange_rows(m, st, L, 1, {L.x.p}, EX_UP | EX_DOWN);
+  k_mg_post<<<blocks_for(r1.cnt), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, r1, L.b.p, L.x.p, L.y.p);
+  count_launch(2);
+  std::swap(L.x.p, L.y.p);
+}
+
 // one V(1,1)-cycle of both hierarchies; level 0 is swept once for the two of them (k_mg_pre2 / k_mg_post2)
-static void vcycle_pair(MgState& st, const int* done, cudaStream_t s) {
+static void vcycle_pair(hdd_mesh* m, MgState& st, const int* done, cudaStream_t s) {
   MgLevel& a = *st.h[0].levels[0];
   MgLevel& b = *st.h[1].levels[0];
   MgLevel& a1 = *st.h[0].levels[1];
   MgLevel& b1 = *st.h[1].levels[1];
-  k_mg_pre2<<<blocks_for(a.nv), kMgThreads, 0, s>>>(done, a.S.p, a.dinv.p, a.nx, a.ny, a.b.p, b.b.p, a.x.p, b.x.p, a.r.p, b.r.p);
-  k_mg_restrict<<<blocks_for(a1.nv), kMgThreads, 0, s>>>(done, a.r.p, a.nx, a.ny, a1.b.p);
-  k_mg_restrict<<<blocks_for(b1.nv), kMgThreads, 0, s>>>(done, b.r.p, b.nx, b.ny, b1.b.p);
+  const Rows r0 = level_rows(st, a, 0), r1 = level_rows(st, a1, 1);
+  exchange_rows(m, st, a, 0, {a.b.p, b.b.p}, EX_UP | EX_DOWN);
+  k_mg_pre2<<<blocks_for(r0.cnt), kMgThreads, 0, s>>>(done, a.S.p, a.dinv.p, a.nx, a.ny, r0, a.b.p, b.b.p, a.x.p, b.x.p, a.r.p, b.r.p);
+  exchange_rows(m, st, a, 0, {a.r.p, b.r.p}, EX_UP);
+  k_mg_restrict<<<blocks_for(r1.cnt), kMgThreads, 0, s>>>(done, a.r.p, a.nx, a.ny, r1, a1.b.p);
+  k_mg_restrict<<<blocks_for(r1.cnt), kMgThreads, 0, s>>>(done, b.r.p, b.nx, b.ny, r1, b1.b.p);
   count_launch(3);
-  vcycle_from(st.h[0], 1, done, s);
-  vcycle_from(st.h[1], 1, done, s);
-  k_mg_prolong_add<<<blocks_for(a.nv), kMgThreads, 0, s>>>(done, a1.x.p, a.nx, a.ny, a.x.p);
-  k_mg_prolong_add<<<blocks_for(b.nv), kMgThreads, 0, s>>>(done, b1.x.p, b.nx, b.ny, b.x.p);
-  k_mg_post2<<<blocks_for(a.nv), kMgThreads, 0, s>>>(done, a.S.p, a.dinv.p, a.nx, a.ny, a.b.p, b.b.p, a.x.p, b.x.p, a.y.p, b.y.p);
+  vcycle_level1(m, st, st.h[0], done, s);
+  vcycle_level1(m, st, st.h[1], done, s);
+  exchange_rows(m, st, a1, 1, {a1.x.p, b1.x.p}, EX_DOWN);  // fine rows up to v1 - 1 interpolate from coarse row V1
+  k_mg_prolong_add<<<blocks_for(r0.cnt), kMgThreads, 0, s>>>(done, a1.x.p, a.nx, r0, a.x.p);
+  k_mg_prolong_add<<<blocks_for(r0.cnt), kMgThreads, 0, s>>>(done, b1.x.p, b.nx, r0, b.x.p);
+  exchange_rows(m, st, a, 0, {a.x.p, b.x.p}, EX_UP | EX_DOWN);
+  k_mg_post2<<<blocks_for(r0.cnt), kMgThreads, 0, s>>>(done, a.S.p, a.dinv.p, a.nx, a.ny, r0, a.b.p, b.b.p, a.x.p, b.x.p, a.y.p, b.y.p);
   count_launch(3);
   std::swap(a.x.p, a.y.p);
   std::swap(b.x.p, b.y.p);
+}
+
+// Decides, identically on every rank, whether the strips of the ranks are full-width bands of cell rows stacked in rank
+// order with boundaries on multiples of four rows - then levels 0 and 1 are swept in strips.  HDD_MG_DISTRIBUTED=0
+// keeps everything replicated.
+static void detect_strips(hdd_swipdg* h, MgState& st) {
+  hdd_mesh* m = h->mesh;
+  MgDist& d = st.dist;
+  d.on = false;
+  static const bool wanted = [] { const char* e = std::getenv("HDD_MG_DISTRIBUTED"); return !(e && e[0] == '0'); }();
+  if (m->world <= 1) return;
+  cudaStream_t s = m->stream;
+  DevBuf<int> mm;
+  const int init[2] = {INT32_MAX, -1};
+  mm.upload(init, 2, s);
+  if (m->n_own > 0) k_cell_row_range<<<blocks_for(m->n_own), kMgThreads, 0, s>>>(m->cell_v0.p + m->own0, m->n_own, st.nx, mm.p);
+  count_launch();
+  int got[2] = {0, 0};
+  HDD_CUDA(cudaMemcpyAsync(got, mm.p, sizeof(got), cudaMemcpyDeviceToHost, s));
+  HDD_CUDA(cudaStreamSynchronize(s));
+  const int c0 = got[0], c1 = got[1] + 1;
+  const bool mine = wanted && m->n_own > 0 && int64_t(m->n_own) == int64_t(st.nx) * (c1 - c0) && (c0 % 4 == 0) &&
+                    (c1 % 4 == 0 || c1 == st.ny) && st.h[0].levels.size() >= 3;
+  // every rank learns every rank's band: 3 doubles per rank through one all-reduce
+  std::vector<double> all(size_t(3) * m->world, 0.0);
+  all[size_t(3) * m->rank] = c0;
+  all[size_t(3) * m->rank + 1] = c1;
+  all[size_t(3) * m->rank + 2] = mine ? 1.0 : 0.0;
+  DevBuf<double> buf;
+  buf.upload(all.data(), all.size(), s);
+  Nccl::get().all_reduce_sum(buf.p, all.size(), m->comm, s);
+  HDD_CUDA(cudaMemcpyAsync(all.data(), buf.p, all.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+  HDD_CUDA(cudaStreamSynchronize(s));
+  bool ok = all[0] == 0.0 && all[size_t(3) * (m->world - 1) + 1] == double(st.ny);
+  for (int r = 0; r < m->world; ++r) {
+    ok = ok && all[size_t(3) * r + 2] == 1.0;
+    if (r > 0) ok = ok && all[size_t(3) * r] == all[size_t(3) * (r - 1) + 1];
+  }
+  if (!ok) return;
+  d.on = true;
+  d.c0 = c0;
+  d.c1 = c1;
+  d.lower = m->rank > 0 ? m->rank - 1 : -1;
+  d.upper = m->rank + 1 < m->world ? m->rank + 1 : -1;
+  d.last = d.upper < 0;
+  if (d.tmp.n < size_t(st.nx) + 1) d.tmp.alloc(size_t(st.nx) + 1);
 }
 
 void mg_release(MgState* st) { delete st; }
@@ -606,13 +758,14 @@ void mg_setup(hdd_swipdg* h, const double* vals) {
     }
   }
   MgLevel& f0 = *st.h[0].levels[0];
-  k_vertex_galerkin<<<blocks_for(nv), kMgThreads, 0, s>>>(h->view(), vals, m->cell_v0.p, m->lex_cell.p, m->sx, m->sy, f0.S.p);
+  k_vertex_galerkin<<<blocks_for(nv), kMgThreads, 0, s>>>(h->view(), vals, m->cell_v0.p, m->lex_cell.p, m->sx, m->sy, Rows{0, nv}, f0.S.p);
   count_launch();
   if (m->world > 1) Nccl::get().all_reduce_sum(f0.S.p, size_t(9) * nv, m->comm, s);
   HDD_CUDA(cudaGetLastError());
   build_hierarchy(h, st.h[0], f0.S.p, false);
   build_hierarchy(h, st.h[1], f0.S.p, true);
   HDD_CUDA(cudaGetLastError());
+  detect_strips(h, st);
 }
 
 // z += P V(P^T r) + P C V_C(C P^T r), red[1] = r.z; p_init != nullptr also stores z as the first direction
@@ -638,15 +791,37 @@ void mg_apply(hdd_swipdg* h, const int* done, const double* r, double* z, double
   MgLevel& a = *st.h[0].levels[0];
   MgLevel& b = *st.h[1].levels[0];
   const bool multi = m->world > 1;
-  k_dg_restrict<<<blocks_for(a.nv), kMgThreads, 0, s>>>(done, r, m->lex_cell.p, m->own0, m->n_own, st.nx, st.ny, a.b.p,
-                                                         multi ? nullptr : b.b.p);
-  count_launch();
-  lap("restrict");
-  if (multi) {
-    Nccl::get().all_reduce_sum(a.b.p, size_t(a.nv), m->comm, s);
-    lap("all-reduce");
-    k_twist_vector<<<blocks_for(a.nv), kMgThreads, 0, s>>>(done, a.b.p, st.nx, a.nv, b.b.p);
+  const MgDist& d = st.dist;
+  const int nx1 = st.nx + 1;
+  if (d.on) {
+    // vertex rows c0 .. c1 of my cells; row c1 belongs to the rank above (which adds my share), row c0 gets the share
+    // of the rank below
+    const Rows mine{int64_t(d.c0) * nx1, int64_t(d.c1 - d.c0 + 1) * nx1};
+    k_dg_restrict<<<blocks_for(mine.cnt), kMgThreads, 0, s>>>(done, r, m->lex_cell.p, m->own0, m->n_own, st.nx, st.ny, mine, a.b.p, nullptr);
     count_launch();
+    Nccl& nc = Nccl::get();
+    nc.group_start();
+    if (d.upper >= 0) nc.send(a.b.p + int64_t(d.c1) * nx1, size_t(nx1), d.upper, m->comm, s);
+    if (d.lower >= 0) nc.recv(d.tmp.p, size_t(nx1), d.lower, m->comm, s);
+    nc.group_end();
+    if (d.lower >= 0) {
+      k_add_row<<<(nx1 + 255) / 256, 256, 0, s>>>(done, a.b.p + int64_t(d.c0) * nx1, d.tmp.p, nx1);
+      count_launch();
+    }
+    k_twist_vector<<<blocks_for(level_rows(st, a, 0).cnt), kMgThreads, 0, s>>>(done, a.b.p, st.nx, level_rows(st, a, 0), b.b.p);
+    count_launch();
+    lap("restrict");
+  } else {
+    k_dg_restrict<<<blocks_for(a.nv), kMgThreads, 0, s>>>(done, r, m->lex_cell.p, m->own0, m->n_own, st.nx, st.ny, Rows{0, a.nv}, a.b.p,
+                                                           multi ? nullptr : b.b.p);
+    count_launch();
+    lap("restrict");
+    if (multi) {
+      Nccl::get().all_reduce_sum(a.b.p, size_t(a.nv), m->comm, s);
+      lap("all-reduce");
+      k_twist_vector<<<blocks_for(a.nv), kMgThreads, 0, s>>>(done, a.b.p, st.nx, Rows{0, a.nv}, b.b.p);
+      count_launch();
+    }
   }
   if (st.h[0].levels.size() == 1) {
     // the fine vertex grid is already small enough for the dense solve
@@ -654,9 +829,11 @@ void mg_apply(hdd_swipdg* h, const int* done, const double* r, double* z, double
     k_mg_dense<<<(int(b.nv) + 127) / 128, 128, 0, s>>>(done, st.h[1].coarse_inv.p, int(b.nv), b.b.p, b.x.p);
     count_launch(2);
   } else {
-    vcycle_pair(st, done, s);
+    vcycle_pair(m, st, done, s);
     lap("v-cycles");
   }
+  // the cells of my top row read the vertex row above my strip
+  exchange_rows(m, st, a, 0, {a.x.p, b.x.p}, EX_DOWN);
   const int grid = int(std::min<int64_t>((m->n_own + kMgThreads - 1) / kMgThreads, kMaxBlocks));
   k_dg_prolong_dot<<<grid, kMgThreads, 0, s>>>(done, m->n_own, m->cell_v0.p + m->own0, st.nx, a.x.p, b.x.p, r, z, p_init, partial, sc);
   count_launch();
