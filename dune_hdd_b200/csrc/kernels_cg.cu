@@ -387,13 +387,13 @@ __global__ void __launch_bounds__((TmaCfg<NF, NL, TC>::kThreads), 1)
 template <int NF, int NL, int TC>
 void launch_cg_spmv_tma_g(const MeshView& m, const CgBuffers& c, int parity, cudaStream_t s) {
   using Cfg = TmaCfg<NF, NL, TC>;
-  static bool configured = false;
-  if (!configured) {
-    HDD_CUDA(cudaFuncSetAttribute(k_cg_spmv_tma_g<NF, NL, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
-  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
+  static bool configured[64] = {};  // the opt-in to > 48 KB of dynamic shared memory is per device
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    HDD_CUDA(cudaFuncSetAttribute(k_cg_spmv_tma_g<NF, NL, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured[dev] = true;
+  }
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (const char* e = std::getenv("HDD_SPMV_CTAS")) sms = std::max(1, std::atoi(e));  // tests: few CTAs => the ring wraps
   int cells_per_cta = (m.n_own + sms - 1) / sms;
@@ -786,13 +786,13 @@ void launch_cg_init_finish(const MeshView&, const CgBuffers& c, cudaStream_t s) 
 void launch_cg_spmv(const MeshView& m, const CgBuffers& c, int parity, cudaStream_t s, const PeerView* peer) {
   const int64_t rows = int64_t(m.n_own) * m.nl;
   if (cg_spmv_uses_tma(m)) {
-    static bool configured = false;
-    if (!configured) {
-      HDD_CUDA(cudaFuncSetAttribute(k_cg_spmv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes));
-      configured = true;
-    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
+    static bool configured[64] = {};  // the opt-in to > 48 KB of dynamic shared memory is per device
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+      HDD_CUDA(cudaFuncSetAttribute(k_cg_spmv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes));
+      configured[dev] = true;
+    }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (const char* e = std::getenv("HDD_SPMV_CTAS")) sms = std::max(1, std::atoi(e));  // tests: few CTAs => the ring wraps
     int cells_per_cta = (m.n_own + sms - 1) / sms;
