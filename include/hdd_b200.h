@@ -67,7 +67,11 @@ typedef struct hdd_mesh hdd_mesh;
  *                                     numbered subdomain-major so that the global DoF index equals
  *                                     Spaces::Block::mapper().mapToGlobal(ss, i) (discretizations/block-swipdg.hh:1042)
  *   boundary_type  [n_faces*n_cells] or NULL   1 = Dirichlet (default, AllDirichlet), 2 = Neumann
- * The arrays are copied; the caller may free them afterwards.
+ * The arrays are copied; the caller may free them afterwards.  Vertex and neighbour ids are validated (on the device
+ * for a whole mesh): HDD_ERR_INDEX_OUT_OF_RANGE.  A HDD_CUBE2D grid whose vertices are numbered x-fastest over a
+ * tensor-product coordinate grid (Stuff::Grid::Providers::Cube< SGrid >, hdd_grid_cube) is recognised as logically
+ * structured; assembly then reads its cell sizes from per-column / per-row tables and the solver type "cg.mg" is
+ * available.
  * rank / world_size: this process owns the contiguous cell range [cell_begin, cell_end) (whole subdomains);
  * pass 0, 1, 0, n_cells for a single GPU.  device = CUDA ordinal. */
 int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy, const int32_t* cell_verts,
