@@ -662,3 +662,25 @@ def test_alu_error_goldens_on_the_device(gpu, level):
     stem = "linearelliptic-swipdg-expectations_esv2007_2daluconform"
     for key in ("L2", "H1_semi", "energy"):
         assert abs(e[key] - golden(stem, key)[level]) <= 0.006 * golden(stem, key)[level]
+
+
+def test_convergence_studies_reproduce_the_expectation_tables(gpu):
+    """SWIPDGStudy / BlockSWIPDGStudy (test/linearelliptic-swipdg.cc:86-109, test/linearelliptic-block-swipdg.cc) on
+    the first three levels of the ESV2007 ladder: every column of the committed expectations, computed on the device"""
+    from dune_hdd_b200 import studies, testcases
+    t = studies.SWIPDGStudy(testcases.ESV2007("alu", num_refinements=2)).run()
+    stem = "linearelliptic-swipdg-expectations_esv2007_2daluconform"
+    assert t["size"] == [128, 512, 2048]
+    for col in ("L2", "H1_semi", "energy", "eta_NC_ESV2007", "eta_R_ESV2007", "eta_DF_ESV2007", "eta_ESV2007",
+                "eff_ESV2007", "eta_ESV2007_alt", "eff_ESV2007_alt"):
+        tol = 0.01 if col.startswith("eff") else 0.006
+        for level in range(3):
+            assert abs(t[col][level] - golden(stem, col)[level]) <= tol * golden(stem, col)[level], (col, level, t[col])
+    assert all(abs(e - 2.0) < 0.05 for e in t["eoc"]["L2"]) and all(abs(e - 1.0) < 0.05 for e in t["eoc"]["energy"])
+    b = studies.BlockSWIPDGStudy(testcases.ESV2007Multiscale((4, 4), num_refinements=1)).run()
+    stem = "linearelliptic-block-swipdg-expectations_esv2007_2daluconform"
+    for col in ("energy", "eta_NC_OS2014", "eta_R_OS2014", "eta_DF_OS2014", "eta_OS2014", "eff_OS2014"):
+        tol = 0.01 if col.startswith("eff") else 0.006
+        for level in range(2):
+            ref = golden(stem, col, "[4 4 1]")[level]
+            assert abs(b[col][level] - ref) <= tol * ref, (col, level, b[col])
