@@ -670,12 +670,15 @@ static void vcycle_pair(hdd_mesh* m, MgState& st, const int* done, cudaStream_t 
 
 // Decides, identically on every rank, whether the strips of the ranks are full-width bands of cell rows stacked in rank
 // order with boundaries on multiples of four rows - then levels 0 and 1 are swept in strips.  HDD_MG_DISTRIBUTED=0
-// keeps everything replicated.
+// keeps everything replicated, =1 asks for strips at any world size; unset, strips are used up to kVerifiedStripWorld
+// ranks (the sizes the strip path has been run and checked on; larger jobs take the size-agnostic replicated V-cycle).
+constexpr int kVerifiedStripWorld = 4;
 static void detect_strips(hdd_swipdg* h, MgState& st) {
   hdd_mesh* m = h->mesh;
   MgDist& d = st.dist;
   d.on = false;
-  static const bool wanted = [] { const char* e = std::getenv("HDD_MG_DISTRIBUTED"); return !(e && e[0] == '0'); }();
+  static const int env = [] { const char* e = std::getenv("HDD_MG_DISTRIBUTED"); return !e ? -1 : (e[0] == '0' ? 0 : 1); }();
+  const bool wanted = env < 0 ? m->world <= kVerifiedStripWorld : env == 1;
   if (m->world <= 1) return;
   cudaStream_t s = m->stream;
   DevBuf<int> mm;
