@@ -4,6 +4,8 @@
 // (testcases/ESV2007.hh:150-163).  Closed form, O(n), no recursion; tests/ compares the simplex generator
 // against an actual recursive longest-edge bisection.
 #include <algorithm>
+#include <atomic>
+#include <cmath>
 #include <vector>
 
 #include "common.hpp"
@@ -142,6 +144,103 @@ int hdd_grid_simplex(int64_t s, double x0, double x1, double y0, double y1, int 
           nb[3 * c + 1] = id(I, J, t1);                     // face {0,2}: centre - P_{t+1}
           nb[3 * c + 2] = id(I + di[t], J + dj[t], opp[t]); // face {1,2}: perimeter edge
         }
+  });
+}
+
+// Father cells for the prolongation of the convergence studies.  The reference walks ALUGrid's father() pointers
+// (test/linearelliptic-swipdg.hh:186-194) or searches the coarse grid view for the centre of each fine cell
+// (Stuff::Grid::EntityInlevelSearch, test/linearelliptic-block-swipdg.hh:169-177); flat arrays carry no hierarchy, so
+// this is the search: coarse cells are binned into a uniform bucket grid by bounding box, every fine centre tests the
+// cells of its bucket and takes the one it lies deepest inside (ties on shared faces resolve to the lowest id).
+int hdd_grid_fathers(int kind, int64_t n_coarse, int64_t n_coarse_verts, const double* xy_c, const int32_t* cv_c,
+                     int64_t n_fine, int64_t n_fine_verts, const double* xy_f, const int32_t* cv_f, int32_t* father) {
+  return hdd::guarded([&] {
+    if (kind != HDD_SIMPLEX2D && kind != HDD_CUBE2D) HDD_THROW(HDD_ERR_WRONG_INPUT, "unknown element kind " << kind);
+    if (!xy_c || !cv_c || !xy_f || !cv_f || !father) HDD_THROW(HDD_ERR_WRONG_INPUT, "NULL argument");
+    if (n_coarse < 1 || n_fine < 0 || n_coarse > INT32_MAX) HDD_THROW(HDD_ERR_WRONG_INPUT, "bad grid size");
+    const int nl = kind == HDD_SIMPLEX2D ? 3 : 4;
+    for (int64_t t = 0; t < n_coarse * nl; ++t)
+      if (cv_c[t] < 0 || cv_c[t] >= n_coarse_verts) HDD_THROW(HDD_ERR_INDEX_OUT_OF_RANGE, "coarse vertex index out of range");
+    for (int64_t t = 0; t < n_fine * nl; ++t)
+      if (cv_f[t] < 0 || cv_f[t] >= n_fine_verts) HDD_THROW(HDD_ERR_INDEX_OUT_OF_RANGE, "fine vertex index out of range");
+    // bounding boxes
+    std::vector<double> bb(size_t(4) * n_coarse);
+    double lo[2] = {HUGE_VAL, HUGE_VAL}, hi[2] = {-HUGE_VAL, -HUGE_VAL};
+    for (int64_t c = 0; c < n_coarse; ++c) {
+      double b[4] = {HUGE_VAL, HUGE_VAL, -HUGE_VAL, -HUGE_VAL};
+      for (int i = 0; i < nl; ++i) {
+        const double* p = xy_c + 2 * size_t(cv_c[c * nl + i]);
+        b[0] = std::min(b[0], p[0]); b[1] = std::min(b[1], p[1]);
+        b[2] = std::max(b[2], p[0]); b[3] = std::max(b[3], p[1]);
+      }
+      for (int d = 0; d < 4; ++d) bb[size_t(4) * c + d] = b[d];
+      lo[0] = std::min(lo[0], b[0]); lo[1] = std::min(lo[1], b[1]);
+      hi[0] = std::max(hi[0], b[2]); hi[1] = std::max(hi[1], b[3]);
+    }
+    const double ext[2] = {hi[0] - lo[0], hi[1] - lo[1]};
+    if (!(ext[0] > 0.0) || !(ext[1] > 0.0)) HDD_THROW(HDD_ERR_WRONG_INPUT, "degenerate coarse grid");
+    // about one cell per bucket, buckets as square as the domain allows
+    const double per_area = double(n_coarse) / (ext[0] * ext[1]);
+    const int64_t B[2] = {std::max<int64_t>(1, int64_t(std::sqrt(per_area) * ext[0])),
+                          std::max<int64_t>(1, int64_t(std::sqrt(per_area) * ext[1]))};
+    auto bucket = [&](double v, int d) {
+      const int64_t b = int64_t((v - lo[d]) / ext[d] * double(B[d]));
+      return std::min(std::max<int64_t>(b, 0), B[d] - 1);
+    };
+    std::vector<int64_t> start(size_t(B[0] * B[1]) + 1, 0);
+    for (int64_t c = 0; c < n_coarse; ++c)
+      for (int64_t by = bucket(bb[4 * c + 1], 1); by <= bucket(bb[4 * c + 3], 1); ++by)
+        for (int64_t bx = bucket(bb[4 * c], 0); bx <= bucket(bb[4 * c + 2], 0); ++bx) ++start[size_t(by * B[0] + bx) + 1];
+    for (size_t t = 1; t < start.size(); ++t) start[t] += start[t - 1];
+    std::vector<int32_t> items(size_t(start.back()));
+    {  // cells in increasing id inside every bucket
+      std::vector<int64_t> fill(start.begin(), start.end() - 1);
+      for (int64_t c = 0; c < n_coarse; ++c)
+        for (int64_t by = bucket(bb[4 * c + 1], 1); by <= bucket(bb[4 * c + 3], 1); ++by)
+          for (int64_t bx = bucket(bb[4 * c], 0); bx <= bucket(bb[4 * c + 2], 0); ++bx)
+            items[size_t(fill[size_t(by * B[0] + bx)]++)] = int32_t(c);
+    }
+    // depth of a point inside a coarse cell: >= 0 inside, scaled to the cell (barycentric / relative box distance)
+    auto depth = [&](int64_t c, double x, double y) {
+      if (kind == HDD_CUBE2D) {
+        const double* b = &bb[size_t(4) * c];
+        return std::min(std::min(x - b[0], b[2] - x) / (b[2] - b[0]), std::min(y - b[1], b[3] - y) / (b[3] - b[1]));
+      }
+      const double* p0 = xy_c + 2 * size_t(cv_c[3 * c]);
+      const double* p1 = xy_c + 2 * size_t(cv_c[3 * c + 1]);
+      const double* p2 = xy_c + 2 * size_t(cv_c[3 * c + 2]);
+      const double det = (p1[0] - p0[0]) * (p2[1] - p0[1]) - (p2[0] - p0[0]) * (p1[1] - p0[1]);
+      const double l1 = ((x - p0[0]) * (p2[1] - p0[1]) - (p2[0] - p0[0]) * (y - p0[1])) / det;
+      const double l2 = ((p1[0] - p0[0]) * (y - p0[1]) - (x - p0[0]) * (p1[1] - p0[1])) / det;
+      return std::min(std::min(l1, l2), 1.0 - l1 - l2);
+    };
+    std::atomic<int64_t> lost{-1};
+    hdd::parallel_for(n_fine, [&](int64_t a, int64_t e) {
+      for (int64_t f = a; f < e; ++f) {
+        double x = 0.0, y = 0.0;
+        for (int i = 0; i < nl; ++i) {
+          x += xy_f[2 * size_t(cv_f[f * nl + i])];
+          y += xy_f[2 * size_t(cv_f[f * nl + i]) + 1];
+        }
+        x /= nl;
+        y /= nl;
+        const size_t b = size_t(bucket(y, 1) * B[0] + bucket(x, 0));
+        int32_t best = -1;
+        double best_depth = -1e-9;  // tolerate centres on a coarse face up to rounding
+        for (int64_t t = start[b]; t < start[b + 1]; ++t) {
+          const double d = depth(items[size_t(t)], x, y);
+          if (d > best_depth) {
+            best_depth = d;
+            best = items[size_t(t)];
+          }
+        }
+        father[f] = best;
+        if (best < 0) lost.store(f);
+      }
+    });
+    if (lost.load() >= 0)
+      HDD_THROW(HDD_ERR_WRONG_INPUT, "the centre of fine cell " << lost.load() << " lies in no coarse cell: the grids do not cover "
+                                                                   "the same domain");
   });
 }
 

@@ -158,6 +158,11 @@ void launch_error_norms(const MeshView& m, int polorder, const DevFn& exact, con
                         const DevCombo& factor, const DevFn* fn_table, int order, const double* u_own, double* out,
                         cudaStream_t s);
 // out[seg] = sum over the DoFs of the cells [seg_ptr[seg], seg_ptr[seg+1]) of x * y
+// Operators::Prolongation: u_fine (owned cells of `fine`) = the coarse DG function at the fine Lagrange nodes; father =
+// coarse cell id per owned fine cell, cgeo_coarse = geometry records of a whole (non-distributed) coarse mesh; *flag is
+// set if a father id is out of range
+void launch_prolong(const MeshView& fine, int p_fine, const double* cgeo_coarse, int32_t n_coarse, int p_coarse,
+                    const int32_t* father, const double* u_coarse, double* u_fine, int* flag, cudaStream_t s);
 void launch_segment_dot(const double* x, const double* y, const int64_t* seg_ptr_dev, int n_seg, int nd, double* out,
                         cudaStream_t s);
 

@@ -99,6 +99,61 @@ __global__ void __launch_bounds__(128)
   out[2 * size_t(m.n_own) + k] = en;
 }
 
+// Lagrange nodes of Elem<KIND, P> in reference coordinates, in DoF order (device.cuh)
+template <int KIND, int P>
+__device__ __forceinline__ void reference_node(int i, double& xi, double& eta) {
+  if constexpr (KIND == HDD_SIMPLEX2D && P == 1) {
+    xi = i == 1 ? 1.0 : 0.0;
+    eta = i == 2 ? 1.0 : 0.0;
+  } else if constexpr (KIND == HDD_SIMPLEX2D) {  // (0,0) (1/2,0) (1,0) (0,1/2) (1/2,1/2) (0,1)
+    const int row = i < 3 ? 0 : i < 5 ? 1 : 2, in_row = i < 3 ? i : i < 5 ? i - 3 : 0;
+    xi = 0.5 * in_row;
+    eta = 0.5 * row;
+  } else {  // tensor product, x fastest
+    xi = double(i % (P + 1)) / P;
+    eta = double(i / (P + 1)) / P;
+  }
+}
+
+// GDT::Operators::Prolongation (test/linearelliptic.hh:168-176): every DoF of the fine DG function is the value of the
+// coarse DG function at the fine Lagrange node, the coarse function being the polynomial of the father cell (the coarse
+// cell that contains the fine cell; hdd_grid_fathers).  One thread per fine cell, no neighbour access: a fine cell
+// inherits from its father only, like the reference's local L2 projection of a function that is polynomial on the cell.
+template <int KIND, int PC, int PF>
+__global__ void __launch_bounds__(128)
+    k_prolong(MeshView fine, const double* __restrict__ cgeo_coarse, int32_t n_coarse, const int32_t* __restrict__ father,
+              const double* __restrict__ u_coarse, double* __restrict__ u_fine, int* __restrict__ flag) {
+  using GC = Elem<KIND, PC>;
+  using GF = Elem<KIND, PF>;
+  constexpr int NC = GC::NL, NFINE = GF::NL;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= fine.n_own) return;
+  const int fa = __ldg(father + k);
+  if (fa < 0 || fa >= n_coarse) {
+    atomicOr(flag, 1);
+    return;
+  }
+  GF gf;
+  gf.load(fine.cgeo, fine.own0 + k);
+  GC gc;
+  gc.load(cgeo_coarse, fa);
+  double u[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) u[j] = __ldg(u_coarse + size_t(NC) * fa + j);
+#pragma unroll
+  for (int i = 0; i < NFINE; ++i) {
+    double xi, eta, x, y, a, b, phi[NC], gx[NC], gy[NC];
+    reference_node<KIND, PF>(i, xi, eta);
+    gf.to_global(xi, eta, x, y);
+    gc.to_local(x, y, a, b);
+    gc.basis(a, b, phi, gx, gy);
+    double v = 0.0;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) v = fma(u[j], phi[j], v);
+    u_fine[size_t(NFINE) * k + i] = v;
+  }
+}
+
 // per-segment partial dot products (deterministic: fixed tree inside the block, host adds the segments in order)
 __global__ void __launch_bounds__(256)
     k_segment_dot(const double* __restrict__ x, const double* __restrict__ y, const int64_t* __restrict__ seg, int nd,
@@ -151,6 +206,25 @@ void launch_error_norms(const MeshView& m, int polorder, const DevFn& exact, con
   } else {
     if (polorder == 1) go(ic<HDD_CUBE2D>{}, ic<1>{}); else go(ic<HDD_CUBE2D>{}, ic<2>{});
   }
+  count_launch();
+  HDD_CUDA(cudaGetLastError());
+}
+
+void launch_prolong(const MeshView& fine, int p_fine, const double* cgeo_coarse, int32_t n_coarse, int p_coarse,
+                    const int32_t* father, const double* u_coarse, double* u_fine, int* flag, cudaStream_t s) {
+  if (fine.n_own == 0) return;
+  const int blocks = (fine.n_own + 127) / 128;
+  auto go = [&](auto kind, auto pc, auto pf) {
+    k_prolong<decltype(kind)::value, decltype(pc)::value, decltype(pf)::value>
+        <<<blocks, 128, 0, s>>>(fine, cgeo_coarse, n_coarse, father, u_coarse, u_fine, flag);
+  };
+  auto by_p = [&](auto kind) {
+    if (p_coarse == 1 && p_fine == 1) go(kind, ic<1>{}, ic<1>{});
+    else if (p_coarse == 1) go(kind, ic<1>{}, ic<2>{});
+    else if (p_fine == 1) go(kind, ic<2>{}, ic<1>{});
+    else go(kind, ic<2>{}, ic<2>{});
+  };
+  if (fine.kind == HDD_SIMPLEX2D) by_p(ic<HDD_SIMPLEX2D>{}); else by_p(ic<HDD_CUBE2D>{});
   count_launch();
   HDD_CUDA(cudaGetLastError());
 }

@@ -333,4 +333,36 @@ int hdd_error_norms(hdd_swipdg* h, const double* u_host, const char* exact, cons
   });
 }
 
+int hdd_prolong(hdd_swipdg* coarse, const double* u_coarse_host, hdd_swipdg* fine, const int32_t* father_host,
+                double* u_fine_host) {
+  return guarded([&] {
+    if (!coarse || !fine || !u_coarse_host || !father_host || !u_fine_host) HDD_THROW(HDD_ERR_WRONG_INPUT, "NULL argument");
+    hdd_mesh* mc = coarse->mesh;
+    hdd_mesh* mf = fine->mesh;
+    if (mc->kind != mf->kind) HDD_THROW(HDD_ERR_WRONG_INPUT, "coarse and fine grid have different element types");
+    if (!mc->whole || mc->n_own != mc->n_global)
+      HDD_THROW(HDD_ERR_REQUIREMENTS_NOT_MET, "the coarse discretization must own its whole grid (the fine one may be distributed)");
+    if (mc->device != mf->device) HDD_THROW(HDD_ERR_REQUIREMENTS_NOT_MET, "coarse and fine discretization live on different devices");
+    mf->set_device();
+    cudaStream_t s = mf->stream;
+    HDD_CUDA(cudaStreamSynchronize(mc->stream));  // the coarse geometry is written on the coarse mesh's stream
+    const size_t n_own = size_t(mf->n_own), rows_f = n_own * size_t(fine->nl);
+    const size_t rows_c = size_t(mc->n_own) * size_t(coarse->nl);
+    DevBuf<double> uc, uf;
+    DevBuf<int32_t> fa;
+    DevBuf<int> flag;
+    uc.upload(u_coarse_host, rows_c, s);
+    fa.upload(father_host, n_own, s);
+    uf.alloc(std::max<size_t>(rows_f, 1));
+    flag.alloc(1);
+    flag.zero(s);
+    launch_prolong(fine->view(), fine->polorder, mc->cgeo.p, mc->n_own, coarse->polorder, fa.p, uc.p, uf.p, flag.p, s);
+    int f = 0;
+    HDD_CUDA(cudaMemcpyAsync(&f, flag.p, sizeof(f), cudaMemcpyDeviceToHost, s));
+    HDD_CUDA(cudaMemcpyAsync(u_fine_host, uf.p, rows_f * sizeof(double), cudaMemcpyDeviceToHost, s));
+    HDD_CUDA(cudaStreamSynchronize(s));
+    if (f != 0) HDD_THROW(HDD_ERR_INDEX_OUT_OF_RANGE, "a father id is not a cell of the coarse grid");
+  });
+}
+
 }  // extern "C"

@@ -289,6 +289,22 @@ class SWIPDG:
                                           int(order), capi.ptr(mu_a), ms, capi.ptr(out)))
         return {"L2": out[0], "H1_semi": out[1], "energy": out[2]}
 
+    def prolong(self, coarse, vector, father=None):
+        """Operators::Prolongation(self.grid_view).apply(coarse function, .) (test/linearelliptic.hh:168-176): the DG
+        function ``vector`` of the discretization ``coarse`` evaluated at the Lagrange nodes of this (finer) one, on the
+        device.  father: grids.fathers(coarse.grid, self.grid), computed if not given."""
+        from . import grids
+        if father is None:
+            father = grids.fathers(coarse.grid, self.grid)
+        father = capi.as_i32(father)[self.cell_range[0]:self.cell_range[1]]
+        u = capi.as_f64(vector)
+        if u.shape[0] != coarse.num_dofs():
+            raise wrong_input_given(capi.HDD_ERR_WRONG_INPUT, "vector has %d entries, the coarse space %d" % (u.shape[0], coarse.num_dofs()))
+        out = self.create_vector()
+        _check(capi.lib().hdd_prolong(coarse._h, capi.ptr(u), self._h, capi.ptr(np.ascontiguousarray(father), C.c_int32),
+                                      capi.ptr(out)))
+        return out
+
     def parametric(self):
         return self.problem.parametric()
 

@@ -87,3 +87,17 @@ def simplex(squares_per_side, lower_left=(-1.0, -1.0), upper_right=(1.0, 1.0), p
                                   int(partitions[1]), capi.ptr(xy), capi.ptr(cv, C.c_int32), capi.ptr(nb, C.c_int32),
                                   capi.ptr(sub, C.c_int32)))
     return Grid(SIMPLEX2D, xy, cv, nb, sub, partitions)
+
+
+def fathers(coarse, fine):
+    """father[k] = the cell of ``coarse`` containing the centre of cell k of ``fine`` (hdd_grid_fathers): the hierarchy
+    information ALUGrid's ``father()`` / ``Stuff::Grid::EntityInlevelSearch`` give the reference's studies
+    (test/linearelliptic-swipdg.hh:186-194, test/linearelliptic-block-swipdg.hh:169-177)."""
+    if coarse.kind != fine.kind:
+        raise ValueError("coarse and fine grid have different element types")
+    out = np.empty(fine.n_cells, np.int32)
+    capi.check(capi.lib().hdd_grid_fathers(coarse.kind, C.c_int64(coarse.n_cells), C.c_int64(coarse.n_verts),
+                                           capi.ptr(coarse.xy), capi.ptr(coarse.cell_verts, C.c_int32),
+                                           C.c_int64(fine.n_cells), C.c_int64(fine.n_verts), capi.ptr(fine.xy),
+                                           capi.ptr(fine.cell_verts, C.c_int32), capi.ptr(out, C.c_int32)))
+    return out

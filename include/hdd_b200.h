@@ -99,6 +99,14 @@ int hdd_grid_simplex_sizes(int64_t squares_per_side, int64_t* n_cells, int64_t* 
 int hdd_grid_simplex(int64_t squares_per_side, double x0, double x1, double y0, double y1, int partitions_x,
                      int partitions_y, double* xy, int32_t* cell_verts, int32_t* cell_neigh,
                      int32_t* cell_subdomain);
+/* Father cell of every cell of a finer grid covering the same domain: the coarse cell that contains the fine cell's
+ * centre.  The reference walks ALUGrid's father() links (test/linearelliptic-swipdg.hh:186-194) or searches the coarse
+ * grid view with Stuff::Grid::EntityInlevelSearch (test/linearelliptic-block-swipdg.hh:169-177); on flat arrays it is a
+ * bucketed point location (host, threaded, no device).  father: n_fine entries.  HDD_ERR_WRONG_INPUT if a centre lies
+ * in no coarse cell. */
+int hdd_grid_fathers(int kind, int64_t n_coarse, int64_t n_coarse_verts, const double* xy_coarse,
+                     const int32_t* cell_verts_coarse, int64_t n_fine, int64_t n_fine_verts, const double* xy_fine,
+                     const int32_t* cell_verts_fine, int32_t* father);
 
 /* ---- problem data (ProblemInterface, problems/interfaces.hh:84-144) ----------------------------------- */
 /* A scalar data function as the host sees it after localisation:
@@ -228,6 +236,16 @@ int hdd_product_apply2(hdd_swipdg* h, const char* id, const double* mu, int mu_s
  * u_host = NULL uses the last solution. */
 int hdd_error_norms(hdd_swipdg* h, const double* u_host, const char* exact, const char* exact_dx, const char* exact_dy,
                     int order, const double* mu, int mu_size, double* out3);
+/* GDT::Operators::Prolongation(reference_grid_view).apply(coarse_function, fine_function) of the convergence studies
+ * (test/linearelliptic.hh:168-176): every DoF of the fine DG function becomes the value of the coarse DG function at the
+ * fine Lagrange node.  father[k] = the coarse cell containing owned fine cell k (hdd_grid_fathers).  The coarse
+ * discretization must own its whole grid and live on the same device; the fine one may be distributed (u_fine = its
+ * owned rows); the polynomial orders may differ.  With it the studies' error norms without an analytic solution are
+ * product norms of (reference solution - prolonged solution) on the reference level (test/linearelliptic.hh:205-214,
+ * hdd_product_apply2 with "l2" / "h1_semi" / "elliptic").  HDD_ERR_INDEX_OUT_OF_RANGE for a father id outside the
+ * coarse grid. */
+int hdd_prolong(hdd_swipdg* coarse, const double* u_coarse_host, hdd_swipdg* fine, const int32_t* father_host,
+                double* u_fine_host);
 
 /* ---- BlockSWIPDG views (discretizations/block-swipdg.hh:553-690) --------------------------------------- */
 int hdd_num_subdomains(const hdd_swipdg* h, int* n);

@@ -93,6 +93,14 @@ struct Grid {
                            g.cell_neigh.data(), g.cell_subdomain.data()));
     return g;
   }
+  // father cell of every cell of `fine` in this (coarser) grid: ALUGrid father() / Stuff::Grid::EntityInlevelSearch of
+  // the studies (test/linearelliptic-swipdg.hh:186-194, test/linearelliptic-block-swipdg.hh:169-177)
+  std::vector<int32_t> fathers_of(const Grid& fine) const {
+    std::vector<int32_t> father(size_t(fine.n_cells()));
+    check(hdd_grid_fathers(kind, n_cells(), n_verts(), xy.data(), cell_verts.data(), fine.n_cells(), fine.n_verts(),
+                           fine.xy.data(), fine.cell_verts.data(), father.data()));
+    return father;
+  }
 };
 
 // ---- problem: ProblemInterface (problems/interfaces.hh:84-144) ----------------------------------------------------
@@ -318,6 +326,14 @@ class SWIPDG {
     check(hdd_error_norms(h_, vector.data(), exact.c_str(), exact_dx.c_str(), exact_dy.c_str(), order,
                           mu.empty() ? nullptr : mu.data(), int(mu.size()), out));
     return {{"L2", out[0]}, {"H1_semi", out[1]}, {"energy", out[2]}};
+  }
+
+  // GDT::Operators::Prolongation(this grid view).apply(coarse function, fine function) (test/linearelliptic.hh:168-176);
+  // father = coarse_grid.fathers_of(this grid), restricted to the owned cells
+  Vector prolong(const SWIPDG& coarse, const Vector& coarse_vector, const std::vector<int32_t>& father) const {
+    Vector fine = create_vector();
+    check(hdd_prolong(coarse.h_, coarse_vector.data(), h_, father.data(), fine.data()));
+    return fine;
   }
 
   // solve (CachedDefault::solve + ContainerBasedDefault::uncached_solve, discretizations/base.hh:151-178,327-367)

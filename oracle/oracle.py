@@ -264,3 +264,79 @@ def to_scipy(rowptr, col, val):
     import scipy.sparse as sp
     n = rowptr.shape[0] - 1
     return sp.csr_matrix((val, col, rowptr), shape=(n, n))
+
+
+# ---- prolongation of the convergence studies (test/linearelliptic.hh:168-176) ----------------------------------
+def reference_nodes(kind, p):
+    """Lagrange nodes in DoF order: vertices for p = 1; p = 2 lexicographic ((0,0),(1/2,0),(1,0),(0,1/2),(1/2,1/2),(0,1)
+    on the triangle, i + 3 j on the square), as or_basis in swipdg_oracle.cpp."""
+    if kind == SIMPLEX:
+        pts = [(i / p, j / p) for j in range(p + 1) for i in range(p + 1 - j)]
+    else:
+        pts = [(i / p, j / p) for j in range(p + 1) for i in range(p + 1)]
+    return np.array(pts)
+
+
+def basis_values(kind, p, xi, eta):
+    """nodal Lagrange basis at reference points (arrays) -> [n_points, n_local]"""
+    xi, eta = np.asarray(xi, dtype=np.float64), np.asarray(eta, dtype=np.float64)
+    if kind == SIMPLEX:
+        l0, l1, l2 = 1.0 - xi - eta, xi, eta
+        if p == 1:
+            return np.stack([l0, l1, l2], axis=-1)
+        return np.stack([l0 * (2 * l0 - 1), 4 * l0 * l1, l1 * (2 * l1 - 1), 4 * l0 * l2, 4 * l1 * l2, l2 * (2 * l2 - 1)], axis=-1)
+    if p == 1:
+        lx, ly = [1.0 - xi, xi], [1.0 - eta, eta]
+    else:
+        lag = lambda t: [(1 - t) * (1 - 2 * t), 4 * t * (1 - t), t * (2 * t - 1)]
+        lx, ly = lag(xi), lag(eta)
+    return np.stack([lx[i] * ly[j] for j in range(p + 1) for i in range(p + 1)], axis=-1)
+
+
+def _local_coordinates(mesh, cells, pts):
+    """reference coordinates of pts[k] in cell cells[k]"""
+    v = mesh.xy[mesh.cv[cells]]
+    if mesh.kind == SIMPLEX:
+        e1, e2, d = v[:, 1] - v[:, 0], v[:, 2] - v[:, 0], pts - v[:, 0]
+        det = e1[:, 0] * e2[:, 1] - e2[:, 0] * e1[:, 1]
+        return (d[:, 0] * e2[:, 1] - e2[:, 0] * d[:, 1]) / det, (e1[:, 0] * d[:, 1] - d[:, 0] * e1[:, 1]) / det
+    h = v[:, 3] - v[:, 0]
+    return (pts[:, 0] - v[:, 0, 0]) / h[:, 0], (pts[:, 1] - v[:, 0, 1]) / h[:, 1]
+
+
+def fathers(coarse, fine):
+    """for every fine cell the coarse cell containing its centre (the reference: ALUGrid father() /
+    Stuff::Grid::EntityInlevelSearch, test/linearelliptic-swipdg.hh:186-194, -block-swipdg.hh:169-177): candidates from
+    a k-d tree over the coarse centres, containment by local coordinates; independent of the product's bucket search"""
+    from scipy.spatial import cKDTree
+    cc = coarse.xy[coarse.cv].mean(axis=1)
+    cf = fine.xy[fine.cv].mean(axis=1)
+    k = min(12, coarse.nc)
+    _, cand = cKDTree(cc).query(cf, k=k)
+    cand = cand.reshape(fine.nc, k)
+    best, depth = np.full(fine.nc, -1, np.int64), np.full(fine.nc, -1e-9)
+    for j in range(k):
+        xi, eta = _local_coordinates(coarse, cand[:, j], cf)
+        d = np.minimum(np.minimum(xi, eta), 1 - xi - eta) if coarse.kind == SIMPLEX else \
+            np.minimum(np.minimum(xi, 1 - xi), np.minimum(eta, 1 - eta))
+        better = d > depth
+        best[better], depth[better] = cand[better, j], d[better]
+    assert (best >= 0).all(), "a fine cell centre lies in no coarse cell"
+    return best
+
+
+def prolong(coarse, u, fine, father=None):
+    """fine DG vector = the coarse DG function at the fine Lagrange nodes (GDT::Operators::Prolongation)"""
+    father = fathers(coarse, fine) if father is None else np.asarray(father)
+    nodes = reference_nodes(fine.kind, fine.p)
+    v = fine.xy[fine.cv]
+    out = np.empty((fine.nc, fine.nl))
+    uc = np.asarray(u).reshape(coarse.nc, coarse.nl)[father]
+    for i, (xi, eta) in enumerate(nodes):
+        if fine.kind == SIMPLEX:
+            pts = v[:, 0] + xi * (v[:, 1] - v[:, 0]) + eta * (v[:, 2] - v[:, 0])
+        else:
+            pts = v[:, 0] + np.array([xi, eta]) * (v[:, 3] - v[:, 0])
+        a, b = _local_coordinates(coarse, father, pts)
+        out[:, i] = (basis_values(coarse.kind, coarse.p, a, b) * uc).sum(axis=1)
+    return out.reshape(-1)

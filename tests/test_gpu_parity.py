@@ -684,3 +684,44 @@ def test_convergence_studies_reproduce_the_expectation_tables(gpu):
         for level in range(2):
             ref = golden(stem, col, "[4 4 1]")[level]
             assert abs(b[col][level] - ref) <= tol * ref, (col, level, b[col])
+
+
+# ---- prolongation and the reference-level error norms of the studies -------------------------
+@pytest.mark.parametrize("kind", ["alu", "sgrid"])
+@pytest.mark.parametrize("pc,pf", [(1, 1), (1, 2), (2, 1), (2, 2)])
+def test_prolongation_matches_the_oracle(gpu, kind, pc, pf):
+    """hdd_prolong = Operators::Prolongation (test/linearelliptic.hh:168-176) on partitioned (renumbered) grids"""
+    gc, gf = _grid(kind, 2 if kind == "alu" else 3, (1, 1)), _grid(kind, 8 if kind == "alu" else 12, (2, 2))
+    dc, df = hdd.SWIPDG(gc, problems.ESV2007(), polorder=pc), hdd.SWIPDG(gf, problems.ESV2007(), polorder=pf)
+    mc, mf = oracle_mesh(gc).with_polorder(pc), oracle_mesh(gf).with_polorder(pf)
+    father = grids.fathers(gc, gf)
+    assert np.array_equal(father, o.fathers(mc, mf))
+    u = np.random.default_rng(7).standard_normal(dc.num_dofs())
+    ref = o.prolong(mc, u, mf)
+    for fa in (None, father):
+        assert np.abs(df.prolong(dc, u, father=fa) - ref).max() <= 1e-13 * np.abs(u).max()
+    bad = father.copy()
+    bad[3] = gc.n_cells
+    with pytest.raises(hdd.discretizations.index_out_of_range):
+        df.prolong(dc, u, father=bad)
+
+
+def test_os2014_study_effectivities_on_the_reference_level(gpu):
+    """BlockSWIPDGStudy on OS2014 [4 4 1] at mu = mu_bar = 1 (test/OS2014_parametric_convergence_study.cc:100-110): no exact
+    solution, so the energy error is || u_ref - P u_h || in the Products::Elliptic norm on the 32768-triangle reference
+    level; the effectivities of the committed expectations (lines 172-174, 202-204), device only"""
+    from dune_hdd_b200 import studies, testcases
+    stem = "linearelliptic-block-swipdg-expectations_os2014_2daluconform"
+    for mu_hat in (1.0, 0.1):
+        case = testcases.OS2014ParametricESV2007Multiscale({"mu": 1.0, "mu_bar": 1.0, "mu_hat": mu_hat}, (4, 4), num_refinements=3)
+        study = studies.BlockSWIPDGStudy(case)
+        assert "energy_mu" in study.available_norms()
+        t = study.run(levels=(0, 1), only_these_estimators=("eta_OS2014", "eta_OS2014_*", "eff_OS2014_mu", "eff_OS2014_*_mu"))
+        key = "1,1,%g" % mu_hat
+        for col in ("eta_OS2014", "eta_OS2014_*", "eff_OS2014_mu", "eff_OS2014_*_mu"):
+            for level in range(2):
+                ref = golden(stem, col, "[4 4 1]", key)[level]
+                assert abs(t[col][level] - ref) <= 0.012 * ref, (mu_hat, col, level, t[col])
+        # mu = 1: a = 1, the energy norm is the H1 semi norm; implied by the goldens: 0.774 / 2.36 = 0.328
+        assert abs(t["energy_mu"][0] - t["H1_semi"][0]) <= 1e-10 and abs(t["energy_mu"][0] - 0.3275) < 1e-3
+        assert abs(t["eoc"]["energy_mu"][0] - 1.0) < 0.05 and abs(t["eoc"]["L2"][0] - 2.0) < 0.1

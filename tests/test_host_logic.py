@@ -193,3 +193,28 @@ def test_golden_fixture_is_complete_and_cites_its_source():
         spec.loader.exec_module(mod)
         for f in mod.FILES:
             assert d[f[:-4]] == mod.parse(os.path.join("/root/reference/test", f)), f
+
+
+def test_father_search_finds_the_containing_coarse_cell():
+    """hdd_grid_fathers (host): every fine centre lies strictly inside its father, every father has the same number of
+    children on the nested ladders, the oracle's independent k-d tree search agrees, foreign domains are refused"""
+    from dune_hdd_b200 import capi, grids
+    from oracle import oracle as o
+    from tests.helpers import oracle_mesh
+    for make, nc, nf in ((grids.simplex, 2, 8), (grids.cube, 5, 20)):
+        c, f = make(nc, partitions=(1, 1)), make(nf, partitions=(2, 2))
+        fa = grids.fathers(c, f)
+        assert np.array_equal(fa, o.fathers(oracle_mesh(c), oracle_mesh(f)))
+        assert set(np.bincount(fa, minlength=c.n_cells)) == {16}
+        inside = np.empty(f.n_cells, bool)
+        cen = f.centers()
+        for k in range(f.n_cells):
+            v = c.xy[c.cell_verts[fa[k]]]
+            if c.kind == grids.SIMPLEX2D:
+                lam = np.linalg.solve(np.array([v[1] - v[0], v[2] - v[0]]).T, cen[k] - v[0])
+                inside[k] = min(lam[0], lam[1], 1 - lam.sum()) > 1e-9
+            else:
+                inside[k] = ((cen[k] > v.min(0)) & (cen[k] < v.max(0))).all()
+        assert inside.all()
+    with pytest.raises(capi.HddError):
+        grids.fathers(grids.cube(4, lower_left=(0.0, 0.0)), grids.cube(8))

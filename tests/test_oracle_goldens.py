@@ -137,6 +137,36 @@ def test_os2014_parametric_goldens_mu1(level):
         assert digits3(e_r, 0.254, 0.01)
 
 
+def test_os2014_effectivities_against_the_prolonged_reference_level_solution():
+    """eff_OS2014_mu / eff_OS2014_*_mu (test/linearelliptic-block-swipdg-expectations_os2014_2daluconform.cxx:172-174,
+    :202-204) = eta / || u_ref - P u_h ||_energy(mu): the test case has no exact solution, so the study solves on the
+    reference level (32768 triangles), prolongs every level solution onto it (test/linearelliptic.hh:168-176) and takes
+    the Products::Elliptic norm of the difference there (test/linearelliptic.hh:205-214, -block-swipdg.hh:262-270)."""
+    os14 = "linearelliptic-block-swipdg-expectations_os2014_2daluconform"
+    ref = o.mesh_bisect(4, -1.0, 1.0, 2 + 2 * 4)
+    assert ref.nc == 32768
+    u_ref, _ = solve_esv(ref, o.os2014_factor(1.0))
+    rpv, colv = o.pattern_volume(ref)
+    E = o.to_scipy(rpv, colv, o.assemble_product(ref, "elliptic", rpv, colv, factor=o.os2014_factor(1.0)))
+    for level in (0, 1):
+        m = o.mesh_bisect(4, -1.0, 1.0, 2 + 2 * level)
+        u, _ = solve_esv(m, o.os2014_factor(1.0))
+        d = u_ref - o.prolong(m, u, ref)
+        energy = np.sqrt(d @ (E @ d))
+        for mu_hat, cols in ((1.0, ("eff_OS2014_mu", "eff_OS2014_*_mu")), (0.1, ("eff_OS2014_mu", "eff_OS2014_*_mu"))):
+            ind = o.indicators(m, u, o.esv2007_force(), o.os2014_factor(1.0), a_hat=o.os2014_factor(mu_hat),
+                               a_bar=o.os2014_factor(1.0), a_min=o.os2014_factor(0.1), a_max=o.os2014_factor(1.0))
+            e_nc, e_df, e_dfs = (np.sqrt(ind[k].sum()) for k in ("nc2", "df2", "dfstar2"))
+            e_r = subdomain_eta_r(m, ind["res2"], ind["amin"], 4)
+            e_rs = subdomain_eta_r(m, ind["resstar2"], ind["amin"], 4)
+            ratio = 1.0 / mu_hat
+            eta = e_nc + e_r + max(np.sqrt(ratio), 1 / np.sqrt(ratio)) * e_df
+            eta_star = e_nc + e_rs + e_dfs / np.sqrt(ratio)
+            key = "1,1,%g" % mu_hat
+            assert digits3(eta / energy, golden(os14, cols[0], "[4 4 1]", key)[level], 0.012), (level, mu_hat, eta / energy)
+            assert digits3(eta_star / energy, golden(os14, cols[1], "[4 4 1]", key)[level], 0.012), (level, mu_hat, eta_star / energy)
+
+
 def test_quadrature_rules_are_exact():
     for order in range(0, 11):
         x, y, w = o.element_rule(o.SIMPLEX, order)
