@@ -25,6 +25,23 @@ def test_library_exports_every_symbol_the_header_declares():
     assert b"sm_100a" in L.hdd_version()
 
 
+def test_header_is_plain_c_and_matches_the_definitions(tmp_path):
+    """include/hdd_b200.h is the drop-in boundary: it has to compile as C99 (cgo / JNI / ctypes generators read it) and
+    as C++ against the definitions - the csrc files include it, so a drifted prototype would already fail the build;
+    here the C side is checked"""
+    import subprocess
+    header = os.path.join(ROOT, "include", "hdd_b200.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", "-x", "c", header])
+    src = tmp_path / "use.c"
+    src.write_text('#include "hdd_b200.h"\nint main(void) { return hdd_version() == 0; }\n')
+    libdir = os.path.join(ROOT, "dune_hdd_b200")
+    capi.lib()
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), str(src), "-L" + libdir,
+                           "-lhdd_b200", "-Wl,-rpath," + libdir, "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64",
+                           "-o", str(tmp_path / "use")])
+    assert subprocess.run([str(tmp_path / "use")]).returncode == 0
+
+
 def test_no_cpu_fallback_without_a_device():
     try:
         import torch
