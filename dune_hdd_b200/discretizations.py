@@ -305,6 +305,15 @@ class SWIPDG:
                                       capi.ptr(out)))
         return out
 
+    def visualize(self, vector, filename, name="solution", mu=None):
+        """visualize(vector, filename, name[, mu]) (discretizations/base.hh:125-147): <filename>.vtu with the DG function
+        as point data.  SWIPDG has no "dirichlet" shift vector (the boundary values are imposed weakly), so the vector is
+        written as it is.  Needs the whole vector (single process); host code (dune_hdd_b200/vtk.py)."""
+        from . import vtk
+        if self.cell_range != (0, self.grid.n_cells):
+            raise requirements_not_met(capi.HDD_ERR_REQUIREMENTS_NOT_MET, "visualize needs the whole grid on this process")
+        return vtk.write_vtu(filename, self.grid, self.polorder, {name: vector})
+
     def parametric(self):
         return self.problem.parametric()
 

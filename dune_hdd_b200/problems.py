@@ -174,3 +174,33 @@ def Spe10Model1(grid, permeability=None, lower_left=(0.0, 0.0), upper_right=(5.0
                        parameter_name="mu", parameter_size=1, name="Spe10.Model1.parametric")
     return Problem(AffinelyDecomposable(Constant(1.0, "diffusion_factor")), AffinelyDecomposable(Cellwise(f, "force")),
                    diffusion_tensor=tensor, name="Spe10.Model1")
+
+
+def read_spe10_model1(filename, nx=100, ny=20):
+    """The permeability file of SPE10 model 1 (``perm_case1.dat``, looked up outside the reference tree,
+    CMakeLists.txt:76-81): nx * ny whitespace-separated values, x running fastest (upstream
+    Stuff::Functions::Spe10::Model1, model1_x_elements = 100, model1_z_elements = 20; recalled, the file is not shipped).
+    -> array [ny, nx] for Spe10Model1(permeability=...)."""
+    with open(filename) as f:
+        values = np.array(f.read().split(), dtype=np.float64)
+    if values.size != nx * ny:
+        raise ValueError("%s holds %d values, expected %d x %d" % (filename, values.size, nx, ny))
+    return values.reshape(ny, nx)
+
+
+def Thermalblock(grid, num_elements=(2, 2), lower_left=(0.0, 0.0), upper_right=(1.0, 1.0),
+                 parameter_name="diffusion_factor", force=1.0, dirichlet=0.0, neumann=0.0):
+    """problems/thermalblock.hh:44-128: the diffusion factor is a Pymor::Functions::Checkerboard - one indicator
+    function per block of a num_elements[0] x num_elements[1] checkerboard (x fastest), weighted by the parameter
+    component ``parameter_name[k]``; K = I, constant force / Dirichlet / Neumann data.  A handle carries at most
+    7 parametric components (HDD_ERR_NOT_IMPLEMENTED beyond)."""
+    nx, ny = int(num_elements[0]), int(num_elements[1])
+    c = grid.centers()
+    ix = np.clip(((c[:, 0] - lower_left[0]) / (upper_right[0] - lower_left[0]) * nx).astype(int), 0, nx - 1)
+    iy = np.clip(((c[:, 1] - lower_left[1]) / (upper_right[1] - lower_left[1]) * ny).astype(int), 0, ny - 1)
+    block = iy * nx + ix
+    comps = [Cellwise((block == k).astype(np.float64), "component_%d" % k) for k in range(nx * ny)]
+    factor = AffinelyDecomposable(None, comps, ["%s[%d]" % (parameter_name, k) for k in range(nx * ny)])
+    return Problem(factor, AffinelyDecomposable(Constant(force, "force")),
+                   AffinelyDecomposable(Constant(dirichlet, "dirichlet")), AffinelyDecomposable(Constant(neumann, "neumann")),
+                   parameter_name=parameter_name, parameter_size=nx * ny, name="thermalblock")
