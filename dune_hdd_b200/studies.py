@@ -15,6 +15,16 @@ from . import estimators, problems
 from .discretizations import SWIPDG, BlockSWIPDG
 
 
+def localize_energy(blocks, diff, group, n_groups):
+    """blocks [n, nl, nl], diff [n, nl], group [n] -> per group: sum_T d_T^T B_T d_T / (total * cells in the group)
+    (the "average" loop of test/linearelliptic-swipdg.hh:209-211)"""
+    import numpy as np
+    local = np.einsum("ci,cij,cj->c", diff, blocks, diff)
+    sums = np.bincount(group, weights=local, minlength=n_groups)
+    counts = np.bincount(group, minlength=n_groups)
+    return sums / (local.sum() * np.maximum(counts, 1))
+
+
 class _StudyBase:
     disc_class = SWIPDG
     estimator_class = estimators.SWIPDG
@@ -97,6 +107,31 @@ class _StudyBase:
                 out[k] = ref.get_product("elliptic").induced_norm(diff, mu=mu)
         return out
 
+    # ---- localization (compute_reference_indicators / compute_indicators) ----------------------------------------
+    def _groups(self, disc, father):
+        """the coarse entity every reference-level cell is accounted to: its father cell"""
+        return father, disc.grid.n_cells
+
+    def reference_indicators(self, disc, u):
+        """compute_reference_indicators() (test/linearelliptic-swipdg.hh:133-223, test/linearelliptic-block-swipdg.hh:122-199):
+        the elliptic energy of (reference solution - prolonged solution) per reference-level cell, summed over the cells
+        of each coarse entity and divided by (total * number of fine cells of the entity).  Like the reference this
+        exists for test cases without an exact solution only.  The per-cell energies come from the device-assembled
+        "elliptic" product blocks (volume pattern: one dense block per cell)."""
+        if self.test_case.provides_exact_solution():
+            raise NotImplementedError("you_have_to_implement_this (test/linearelliptic-swipdg.hh:157-158)")
+        from . import grids
+        grid_r, ref, u_ref = self.reference()
+        father = grids.fathers(disc.grid, grid_r)
+        diff = (u_ref - ref.prolong(disc, u, father)).reshape(grid_r.n_cells, ref.n_loc)
+        blocks = ref.get_product("elliptic").freeze_parameter(self._mu()).reshape(grid_r.n_cells, ref.n_loc, ref.n_loc)
+        group, n_groups = self._groups(disc, father)
+        return localize_energy(blocks, diff, group, n_groups)
+
+    def indicators(self, disc, u, type):
+        """compute_indicators(type): estimate_local of the estimator class"""
+        return self.estimator_class.estimate_local(disc, u, type, self.test_case.parameters() or None)
+
     # ---- the study ---------------------------------------------------------------------------------------------
     def run(self, only_these_norms=None, only_these_estimators=None, levels=None):
         """-> {"size": [...], "h": [...], "iterations": [...], "<norm>": [...], "<estimator>": [...], "eoc": {column: [...]}}
@@ -147,3 +182,7 @@ class BlockSWIPDGStudy(_StudyBase):
     disc_class = BlockSWIPDG
     estimator_class = estimators.BlockSWIPDG
     effectivity_ids = ("OS2014_*", "OS2014")
+
+    def _groups(self, disc, father):
+        """... its father's subdomain (ms_grid->subdomainOf(father_entity), test/linearelliptic-block-swipdg.hh:178)"""
+        return disc.grid.cell_subdomain[father], disc.grid.n_subdomains

@@ -108,3 +108,28 @@ def test_threaded_oracle_equals_the_serial_walk():
         o.set_threads(1)
     assert np.abs(A1 - A4).max() <= 1e-14 * np.abs(A1).max() and np.array_equal(b1, b4)
     assert it1 == it4 and np.abs(x1 - x4).max() <= 1e-11 * np.abs(x1).max()
+
+
+def test_reference_indicators_localise_the_energy_error():
+    """studies.localize_energy (compute_reference_indicators, test/linearelliptic-swipdg.hh:133-223) on oracle data: the
+    per-cell energies of u_ref - P u_h from the elliptic product blocks add up to the squared energy norm, and the
+    indicators are that energy per coarse cell over (total * children)"""
+    from dune_hdd_b200.studies import localize_energy
+    coarse, fine = o.mesh_bisect(2, -1.0, 1.0, 2), o.mesh_bisect(2, -1.0, 1.0, 6)
+    def solve(m):
+        rp, col = o.pattern(m)
+        import scipy.sparse.linalg as spla
+        return spla.spsolve(o.to_scipy(rp, col, o.assemble_lhs(m, o.os2014_factor(0.5), None, rp, col)).tocsc(),
+                            o.assemble_rhs(m, o.esv2007_force()))
+    father = o.fathers(coarse, fine)
+    d = solve(fine) - o.prolong(coarse, solve(coarse), fine, father)
+    rpv, colv = o.pattern_volume(fine)
+    vals = o.assemble_product(fine, "elliptic", rpv, colv, factor=o.os2014_factor(0.5))
+    total = d @ (o.to_scipy(rpv, colv, vals) @ d)
+    ind = localize_energy(vals.reshape(fine.nc, 3, 3), d.reshape(fine.nc, 3), father, coarse.nc)
+    assert ind.shape == (coarse.nc,) and (ind > 0).all()
+    children = np.bincount(father, minlength=coarse.nc)
+    assert set(children) == {16} and abs((ind * children).sum() - 1.0) < 1e-12
+    local = np.array([d[3 * c:3 * c + 3] @ vals[9 * c:9 * c + 9].reshape(3, 3) @ d[3 * c:3 * c + 3] for c in range(fine.nc)])
+    assert abs(local.sum() - total) <= 1e-12 * total
+    assert np.allclose(ind, np.bincount(father, weights=local) / (total * 16), rtol=1e-12)
