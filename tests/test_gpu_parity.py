@@ -725,3 +725,73 @@ def test_os2014_study_effectivities_on_the_reference_level(gpu):
         # mu = 1: a = 1, the energy norm is the H1 semi norm; implied by the goldens: 0.774 / 2.36 = 0.328
         assert abs(t["energy_mu"][0] - t["H1_semi"][0]) <= 1e-10 and abs(t["energy_mu"][0] - 0.3275) < 1e-3
         assert abs(t["eoc"]["energy_mu"][0] - 1.0) < 0.05 and abs(t["eoc"]["L2"][0] - 2.0) < 0.1
+
+
+# ---- the config-file driver on the device and the localization study --------------------------
+def test_example_driver_and_thermalblock_vector_parameter(gpu, tmp_path):
+    """examples/swipdg_main.py (= examples/linearelliptic/swipdg_main.cc) end to end: default config -> ESV2007 on the 8 x 8
+    SGrid of [0,1]^2 -> .vtu; then the thermalblock problem of the same config with its 4-component parameter
+    diffusion_factor, one solve per [parameter] entry, against the oracle's direct solve"""
+    import subprocess
+    import sys
+    import xml.etree.ElementTree as ET
+    from dune_hdd_b200 import discreteproblem as dp
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, "examples", "swipdg_main.py")
+    cls = dp.LinearellipticExampleSWIPDG
+    for expected in ("Please review the configuration", "discretization is not parametric, solving..."):
+        r = subprocess.run([sys.executable, script, str(tmp_path)], capture_output=True, text=True)
+        assert r.returncode == 0 and expected in r.stdout, r.stdout + r.stderr
+    g = grids.cube(8, 8, (0.0, 0.0), (1.0, 1.0))
+    m, rp, col, A, b = oracle_system(g, o.const(1.0), o.esv2007_force())
+    u_ref = direct_solve(rp, col, A, b)
+    piece = ET.parse(str(tmp_path / "linearelliptic.swipdg.solution.vtu")).getroot().find("UnstructuredGrid/Piece")
+    assert piece.find("PointData/DataArray").attrib["Name"] == "solution"
+    val = np.array(piece.find("PointData/DataArray").text.split(), float).reshape(g.n_cells, 4)[:, [0, 1, 3, 2]]
+    assert rel(val.reshape(-1), u_ref) <= 1e-6  # the driver solves with the default options (1e-10)
+    cfg = tmp_path / (cls.static_id() + ".cfg")
+    cfg.write_text(cfg.read_text().replace("problem = hdd.linearelliptic.problem.ESV2007", "problem = hdd.linearelliptic.problem.thermalblock"))
+    example = cls("sgrid", device=0)
+    example.initialize([str(tmp_path)])
+    d = example.discretization()
+    assert d.parametric() and d.parameter_type() == {"diffusion_factor": 4}
+    ind = np.array([c.cell_values for c in d.problem.diffusion_factor.components])
+    parameters = example.discrete_problem().parameters()
+    assert len(parameters) == 2
+    for parameter in parameters:
+        mu = parameter["diffusion_factor"]
+        u = d.solve({"type": "cg.blockdiagonal", "precision": 1e-13, "max_iter": 20000}, mu=mu)
+        a = (np.array(mu)[:, None] * ind).sum(axis=0)
+        A = o.assemble_lhs(m, o.cellwise(a), None, rp, col)
+        assert rel(u, direct_solve(rp, col, A, o.assemble_rhs(m, o.const(1.0)))) <= SOL_TOL
+    with pytest.raises(hdd.discretizations.wrong_parameter_type):
+        d.solve(mu=[1.0, 2.0])
+
+
+def test_reference_indicators_of_the_localization_study(gpu):
+    """compute_reference_indicators (test/linearelliptic-block-swipdg.hh:122-199, test/linearelliptic-swipdg.hh:133-223):
+    the energy of u_ref - P u_h per subdomain / per coarse cell, against the same quantity from oracle matrices"""
+    from dune_hdd_b200 import studies, testcases
+    case = testcases.OS2014ParametricESV2007Multiscale({"mu": 0.5, "mu_bar": 0.5, "mu_hat": 0.5}, (2, 2), num_refinements=1)
+    grid, grid_r = case.level_grid(0), case.reference_grid()
+    mc, mf = oracle_mesh(grid), oracle_mesh(grid_r)
+
+    def oracle_solution(mesh):
+        rp, col = o.pattern(mesh)
+        return direct_solve(rp, col, o.assemble_lhs(mesh, o.os2014_factor(0.5), None, rp, col), o.assemble_rhs(mesh, o.esv2007_force()))
+
+    father = o.fathers(mc, mf)
+    diff = (oracle_solution(mf) - o.prolong(mc, oracle_solution(mc), mf, father)).reshape(mf.nc, 3)
+    rpv, colv = o.pattern_volume(mf)
+    blocks = o.assemble_product(mf, "elliptic", rpv, colv, factor=o.os2014_factor(0.5)).reshape(mf.nc, 3, 3)
+    for cls, group, n in ((studies.BlockSWIPDGStudy, grid.cell_subdomain[father], 4), (studies.SWIPDGStudy, father, grid.n_cells)):
+        study = cls(case)
+        disc = study._make(grid)
+        disc.init()
+        u = disc.solve(study.solver_options, mu=0.5)
+        ind = study.reference_indicators(disc, u)
+        ref = studies.localize_energy(blocks, diff, group, n)
+        assert ind.shape == (n,) and np.abs(ind - ref).max() <= 1e-7 * ref.max()
+        assert abs((ind * np.bincount(group, minlength=n)).sum() - 1.0) < 1e-12
+        local = study.indicators(disc, u, "eta_OS2014" if cls is studies.BlockSWIPDGStudy else "eta_ESV2007")
+        assert local.shape == (n,)
