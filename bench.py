@@ -113,14 +113,12 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples), "source": "nvml" if self._nvml else "nvidia-smi"}
 
 
-def cpu_baseline(n_cpu, cg_iters, all_cores=True):
-    """oracle (port of the reference's serial walk) on a bounded sample: n_cpu^2 Q1 cells, cg_iters CG iterations.
-    `value` is the faithful one-core number (the reference's walk is serial, discretizations/swipdg.hh:485); all_cores
-    repeats the sample with the oracle's optional host threading (SURVEY 8d asks for both)."""
+def _cpu_sample(n_cpu, cg_iters, threads):
+    """one pass of the oracle over the sample with `threads` host threads -> (pattern s, assembly s, s per CG iteration, iterations, DoFs)"""
     from oracle import oracle as o
     m = o.mesh_cube(n_cpu, n_cpu, -1.0, 1.0, -1.0, 1.0)
-
-    def run():
+    o.set_threads(threads)
+    try:
         t0 = time.perf_counter()
         rp, col = o.pattern(m)
         t_pat = time.perf_counter() - t0
@@ -131,44 +129,55 @@ def cpu_baseline(n_cpu, cg_iters, all_cores=True):
         t0 = time.perf_counter()
         x, it, rr = o.cg(rp, col, A, b, precond=1, rtol=1e-30, maxit=cg_iters)
         t_cg = time.perf_counter() - t0
-        return t_pat, t_asm, t_cg / max(it, 1), it
+    finally:
+        o.set_threads(1)
+    return t_pat, t_asm, t_cg / max(it, 1), it, m.n_dofs
 
-    t_pat, t_asm, t_it, it = run()
-    out = {"value": m.n_dofs / t_asm, "unit": "DoFs/s", "cores": 1, "kind": "port",
-           "sample": "%dx%d Q1 cells (ESV2007 data): serial assembly walk + %d Jacobi-CG iterations" % (n_cpu, n_cpu, it),
-           "assemble_s": t_asm, "pattern_s": t_pat, "cg_s_per_iteration": t_it,
-           "note": "CPU restatement of the reference (oracle/); the reference itself needs un-vendored DUNE modules"}
+
+def _cpu_record(n_cpu, sample, cores):
+    t_pat, t_asm, t_it, it, n_dofs = sample
+    return {"value": n_dofs / t_asm, "unit": "DoFs/s", "cores": cores, "kind": "port",
+            "sample": "%dx%d Q1 cells (ESV2007 data): assembly walk + %d Jacobi-CG iterations, %d host thread%s"
+                      % (n_cpu, n_cpu, it, cores, "" if cores == 1 else "s"),
+            "assemble_s": t_asm, "pattern_s": t_pat, "cg_s_per_iteration": t_it,
+            "note": "CPU restatement of the reference (oracle/); the reference itself needs un-vendored DUNE modules"}
+
+
+def cpu_baseline(n_cpu, cg_iters, all_cores=True):
+    """oracle (port of the reference's serial walk) on a bounded sample: n_cpu^2 Q1 cells, cg_iters CG iterations.
+    `value` is the faithful one-core number (the reference's walk is serial, discretizations/swipdg.hh:485); all_cores
+    repeats the sample with the oracle's optional host threading (SURVEY 8d asks for both)."""
+    out = _cpu_record(n_cpu, _cpu_sample(n_cpu, cg_iters, 1), 1)
     if all_cores:
         cores = os.cpu_count() or 1
-        try:
-            o.set_threads(cores)
-            _, a_asm, a_it, _ = run()
-            out["all_cores"] = {"cores": cores, "value": m.n_dofs / a_asm, "assemble_s": a_asm, "cg_s_per_iteration": a_it,
-                                "note": "same sample with the oracle's own threading (atomic scatter); the reference has none"}
-        finally:
-            o.set_threads(1)
+        rec = _cpu_record(n_cpu, _cpu_sample(n_cpu, cg_iters, cores), cores)
+        out["all_cores"] = {"cores": cores, "value": rec["value"], "assemble_s": rec["assemble_s"],
+                            "cg_s_per_iteration": rec["cg_s_per_iteration"],
+                            "note": "same sample with the oracle's own threading (atomic scatter); the reference has none"}
     return out
 
 
-def cpu_all_cores(n_cpu, cg_iters):
-    return cpu_baseline(n_cpu, cg_iters, all_cores=True).get("all_cores")
-
-
 def run_reference(args):
+    """The CPU arm: the oracle port with all the host threads it can use (its own threading; the reference's walk is
+    serial, the one-core figure is reported next to it)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n_cpu = args.cpu_n
+    cores = os.cpu_count() or 1
     steps = []
     for k in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        cb = cpu_baseline(n_cpu, args.cpu_cg_iters, all_cores=False)
-        steps.append((time.perf_counter() - t0, cb))
+        rec = _cpu_record(n_cpu, _cpu_sample(n_cpu, args.cpu_cg_iters, cores), cores)
+        steps.append((time.perf_counter() - t0, rec))
     timed = steps[args.warmup:]
     cb = timed[-1][1]
     value = float(np.mean([s[1]["value"] for s in timed]))
     cb["value"] = value
-    cb["all_cores"] = cpu_all_cores(n_cpu, args.cpu_cg_iters)  # outside the timed steps
+    one = _cpu_record(n_cpu, _cpu_sample(n_cpu, args.cpu_cg_iters, 1), 1)  # outside the timed steps
+    cb["one_core"] = {"cores": 1, "value": one["value"], "assemble_s": one["assemble_s"],
+                      "cg_s_per_iteration": one["cg_s_per_iteration"],
+                      "note": "the same sample as the reference runs it: serial walk (discretizations/swipdg.hh:485)"}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "DoFs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean([s[0] for s in timed])),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
