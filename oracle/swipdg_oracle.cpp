@@ -369,6 +369,14 @@ double sigma_boundary(int p) { return p <= 1 ? 14.0 : p <= 2 ? 38.0 : p <= 3 ? 7
 // ------------------------------------------------------------------------------------
 int g_threads = 1;
 
+// Variant switches of tools/os2014_mu01_search.py (the search for the arithmetic behind the reference's mu = 0.1
+// OS2014 goldens).  All zero / negative = the restatement every other test pins; nothing else sets them.
+//   g_var_flags bit 0: the penalty takes a_f at the face midpoint instead of the quadrature point
+//               bit 1: harmonic instead of arithmetic mean of a_f(en), a_f(ne) in the inner penalty
+//               bit 2: the weights omega follow a_f K instead of K alone (older dune-gdt, single diffusion function)
+//   g_var_vol_order / g_var_face_order >= 0: quadrature order of the factor in the volume / face terms
+int g_var_flags = 0, g_var_vol_order = -1, g_var_face_order = -1;
+
 template <class F>
 void parallel_chunks(int64_t n, F&& f) {  // f(chunk, begin, end)
   const int nt = int(std::max<int64_t>(1, std::min<int64_t>(g_threads, n)));
@@ -572,8 +580,10 @@ void or_assemble_lhs(int kind, int polorder, int nc, int nv, const double* xy, c
   const int nl = m.nl(), nf = m.nf(), p = polorder;
   Csr A{rowptr, col, val};
   const double beta = 1.0;  // default_beta(dimDomain) = 1/(d-1), discretizations/swipdg.hh:168
-  const Rule2 vol = kind == SIMPLEX ? triangle_rule(factor->order + 2 * (p - 1)) : square_rule(factor->order + 2 * (p - 1));
-  const Rule1 fr = line_rule(factor->order + 2 * p);
+  const int vo = g_var_vol_order >= 0 ? g_var_vol_order : factor->order;
+  const int fo = g_var_face_order >= 0 ? g_var_face_order : factor->order;
+  const Rule2 vol = kind == SIMPLEX ? triangle_rule(vo + 2 * (p - 1)) : square_rule(vo + 2 * (p - 1));
+  const Rule1 fr = line_rule(fo + 2 * p);
   parallel_chunks(nc, [&](int, int64_t c_begin, int64_t c_end) {
   for (int c = int(c_begin); c < int(c_end); ++c) {
     const Cell g = load_cell(m, c);
@@ -605,7 +615,8 @@ void or_assemble_lhs(int kind, int polorder, int nc, int nv, const double* xy, c
           double phi[kMaxLoc], gx[kMaxLoc], gy[kMaxLoc];
           basis_at(g, x, y, phi, gx, gy);
           const double a = fn_eval(*factor, c, x, y);
-          const double pen = sigma_boundary(p) * delta * a / std::pow(e.h, beta);
+          const double a_pen = (g_var_flags & 1) ? fn_eval(*factor, c, 0.5 * (e.ax + e.bx), 0.5 * (e.ay + e.by)) : a;
+          const double pen = sigma_boundary(p) * delta * a_pen / std::pow(e.h, beta);
           const double w = fr.w[q] * e.h;
           double flux[kMaxLoc];
           for (int i = 0; i < nl; ++i)
@@ -620,15 +631,29 @@ void or_assemble_lhs(int kind, int polorder, int nc, int nv, const double* xy, c
         tensor_of(tensor, n, Kn);
         const double dm = e.nx * (K[0] * e.nx + K[1] * e.ny) + e.ny * (K[2] * e.nx + K[3] * e.ny);      // delta^-
         const double dp = e.nx * (Kn[0] * e.nx + Kn[1] * e.ny) + e.ny * (Kn[2] * e.nx + Kn[3] * e.ny);  // delta^+
-        const double gamma = dp * dm / (dp + dm);
-        const double wm = dp / (dp + dm), wp = dm / (dp + dm);
+        double gamma = dp * dm / (dp + dm);
+        double wm = dp / (dp + dm), wp = dm / (dp + dm);
         for (size_t q = 0; q < fr.w.size(); ++q) {
           const double x = e.ax + fr.x[q] * (e.bx - e.ax), y = e.ay + fr.x[q] * (e.by - e.ay);
           double phm[kMaxLoc], gxm[kMaxLoc], gym[kMaxLoc], php[kMaxLoc], gxp[kMaxLoc], gyp[kMaxLoc];
           basis_at(g, x, y, phm, gxm, gym);
           basis_at(gn, x, y, php, gxp, gyp);
           const double am = fn_eval(*factor, c, x, y), ap = fn_eval(*factor, n, x, y);
-          const double pen = sigma_inner(p) * gamma * 0.5 * (am + ap) / std::pow(e.h, beta);
+          double am_pen = am, ap_pen = ap;
+          if (g_var_flags & 1) {
+            am_pen = fn_eval(*factor, c, 0.5 * (e.ax + e.bx), 0.5 * (e.ay + e.by));
+            ap_pen = fn_eval(*factor, n, 0.5 * (e.ax + e.bx), 0.5 * (e.ay + e.by));
+          }
+          double a_mean = 0.5 * (am_pen + ap_pen);
+          if (g_var_flags & 2) a_mean = 2.0 * am_pen * ap_pen / (am_pen + ap_pen);
+          if (g_var_flags & 4) {  // delta^-+ = n . (a_f K) n: weights and gamma see the factor
+            const double em = am_pen * dm, ep = ap_pen * dp;
+            wm = ep / (ep + em);
+            wp = em / (ep + em);
+            gamma = dp * dm / (dp + dm);
+            a_mean = (ep * em / (ep + em)) / gamma;
+          }
+          const double pen = sigma_inner(p) * gamma * a_mean / std::pow(e.h, beta);
           const double w = fr.w[q] * e.h;
           double fm[kMaxLoc], fp[kMaxLoc];
           for (int i = 0; i < nl; ++i) {
@@ -825,6 +850,11 @@ void or_assemble_product(int kind, int polorder, int nc, int nv, const double* x
 // ---- a14: linear solve ---------------------------------------------------------------------
 // Stuff::LA::Solver<Matrix>(A).apply(rhs, x, options) (discretizations/base.hh:344,361-364), with
 // the method fixed to (Jacobi-)preconditioned CG by BASELINE.json north_star.
+void or_set_variant(int flags, int vol_order, int face_order) {
+  g_var_flags = flags;
+  g_var_vol_order = vol_order;
+  g_var_face_order = face_order;
+}
 void or_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
 int or_get_threads() { return g_threads; }
 
