@@ -113,80 +113,300 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples), "source": "nvml" if self._nvml else "nvidia-smi"}
 
 
-def _cpu_sample(n_cpu, cg_iters, threads):
-    """one pass of the oracle over the sample with `threads` host threads -> (pattern s, assembly s, s per CG iteration, iterations, DoFs)"""
+def workload_config(n, solver, world):
+    """the `config` object of both arms (identical for identical arguments)"""
+    return {"workload": "config5: SWIPDG p1 (Q1) on the %dx%d structured grid [-1,1]^2, ESV2007 data, 8x8 BlockSWIPDG "
+                        "partition" % (n, n), "cells": n * n, "dofs": 4 * n * n,
+            "cg": "%s to ||r||/||b|| <= 1e-10" % solver,
+            "l2_flush": "inputs >> L2 (matrix %.1f GB per part)" % (8.0 * 16 * (n * n + 2 * 2 * n * (n - 1)) / 1e9),
+            "parallelism": "subdomain slabs x%d" % world}
+
+
+class CpuWorkload:
+    """the oracle (CPU port of the reference) on an n x n sample of the workload: mesh + pattern once, then per step the
+    assembly walk and `cg_iters` Jacobi-CG iterations"""
+
+    def __init__(self, n):
+        from oracle import oracle as o
+        self.o, self.n = o, n
+        self.m = o.mesh_cube(n, n, -1.0, 1.0, -1.0, 1.0)
+        t0 = time.perf_counter()
+        self.rp, self.col = o.pattern(self.m)
+        self.t_pattern = time.perf_counter() - t0
+
+    def step(self, threads, cg_iters):
+        o = self.o
+        o.set_threads(threads)
+        try:
+            t0 = time.perf_counter()
+            A = o.assemble_lhs(self.m, o.const(1.0), None, self.rp, self.col)
+            b = o.assemble_rhs(self.m, o.esv2007_force())
+            t_asm = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            x, it, rr = o.cg(self.rp, self.col, A, b, precond=1, rtol=1e-30, maxit=cg_iters)
+            t_cg = time.perf_counter() - t0
+        finally:
+            o.set_threads(1)
+        return t_asm, t_cg / max(it, 1), it
+
+    def solve(self, threads, rtol=PRECISION):
+        """Jacobi-CG to the bench's precision (the "CG solve s" half of the metric on this sample)"""
+        o = self.o
+        o.set_threads(threads)
+        try:
+            A = o.assemble_lhs(self.m, o.const(1.0), None, self.rp, self.col)
+            b = o.assemble_rhs(self.m, o.esv2007_force())
+            t0 = time.perf_counter()
+            x, it, rr = o.cg(self.rp, self.col, A, b, precond=1, rtol=rtol, maxit=200000)
+            return time.perf_counter() - t0, it, rr
+        finally:
+            o.set_threads(1)
+
+    def record(self, step, threads, cg_iters):
+        t_asm, t_it, it = step
+        n = self.n
+        return {"value": self.m.n_dofs / t_asm, "unit": "DoFs/s", "cores": threads, "kind": "port",
+                "sample": "%dx%d Q1 cells (ESV2007 data): assembly walk + %d Jacobi-CG iterations, %d host thread%s"
+                          % (n, n, it, threads, "" if threads == 1 else "s"),
+                "assemble_s": t_asm, "pattern_s": self.t_pattern, "cg_s_per_iteration": t_it,
+                "note": "CPU restatement of the reference (oracle/); the reference itself needs un-vendored DUNE modules"}
+
+
+def cpu_estimator_sample(squares=256):
+    """the oracle's four estimator walks (one function) on 8 * squares^2 triangles, one core -> (cells, seconds)"""
     from oracle import oracle as o
-    m = o.mesh_cube(n_cpu, n_cpu, -1.0, 1.0, -1.0, 1.0)
-    o.set_threads(threads)
-    try:
-        t0 = time.perf_counter()
-        rp, col = o.pattern(m)
-        t_pat = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        A = o.assemble_lhs(m, o.const(1.0), None, rp, col)
-        b = o.assemble_rhs(m, o.esv2007_force())
-        t_asm = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        x, it, rr = o.cg(rp, col, A, b, precond=1, rtol=1e-30, maxit=cg_iters)
-        t_cg = time.perf_counter() - t0
-    finally:
-        o.set_threads(1)
-    return t_pat, t_asm, t_cg / max(it, 1), it, m.n_dofs
+    m = o.mesh_bisect(squares, -1.0, 1.0, 2)
+    v = m.xy[m.cv]
+    u = (np.cos(0.5 * np.pi * v[..., 0]) * np.cos(0.5 * np.pi * v[..., 1])).reshape(-1)
+    t0 = time.perf_counter()
+    o.indicators(m, u, o.esv2007_force(), o.const(1.0))
+    return m.nc, time.perf_counter() - t0
 
 
-def _cpu_record(n_cpu, sample, cores):
-    t_pat, t_asm, t_it, it, n_dofs = sample
-    return {"value": n_dofs / t_asm, "unit": "DoFs/s", "cores": cores, "kind": "port",
-            "sample": "%dx%d Q1 cells (ESV2007 data): assembly walk + %d Jacobi-CG iterations, %d host thread%s"
-                      % (n_cpu, n_cpu, it, cores, "" if cores == 1 else "s"),
-            "assemble_s": t_asm, "pattern_s": t_pat, "cg_s_per_iteration": t_it,
-            "note": "CPU restatement of the reference (oracle/); the reference itself needs un-vendored DUNE modules"}
-
-
-def cpu_baseline(n_cpu, cg_iters, all_cores=True):
+def cpu_baseline(n_cpu, cg_iters, solve_n):
     """oracle (port of the reference's serial walk) on a bounded sample: n_cpu^2 Q1 cells, cg_iters CG iterations.
     `value` is the faithful one-core number (the reference's walk is serial, discretizations/swipdg.hh:485); all_cores
-    repeats the sample with the oracle's optional host threading (SURVEY 8d asks for both)."""
-    out = _cpu_record(n_cpu, _cpu_sample(n_cpu, cg_iters, 1), 1)
-    if all_cores:
-        cores = os.cpu_count() or 1
-        rec = _cpu_record(n_cpu, _cpu_sample(n_cpu, cg_iters, cores), cores)
-        out["all_cores"] = {"cores": cores, "value": rec["value"], "assemble_s": rec["assemble_s"],
-                            "cg_s_per_iteration": rec["cg_s_per_iteration"],
-                            "note": "same sample with the oracle's own threading (atomic scatter); the reference has none"}
+    repeats the sample with the oracle's optional host threading (SURVEY 8d asks for both); `solve` is a Jacobi-CG solve
+    to 1e-10 on solve_n^2 cells with all threads, `estimator` the oracle's estimator walks on 524288 triangles."""
+    w = CpuWorkload(n_cpu)
+    out = w.record(w.step(1, cg_iters), 1, cg_iters)
+    cores = os.cpu_count() or 1
+    rec = w.record(w.step(cores, cg_iters), cores, cg_iters)
+    out["all_cores"] = {"cores": cores, "value": rec["value"], "assemble_s": rec["assemble_s"],
+                        "cg_s_per_iteration": rec["cg_s_per_iteration"],
+                        "note": "same sample with the oracle's own threading (atomic scatter); the reference has none"}
+    ws = w if solve_n == n_cpu else CpuWorkload(solve_n)
+    t, it, rr = ws.solve(cores)
+    out["solve"] = {"grid": "%dx%d" % (solve_n, solve_n), "solver": "cg.diagonal", "cores": cores, "seconds": t,
+                    "iterations": it, "relative_residual": rr}
+    cells, te = cpu_estimator_sample()
+    out["estimator"] = {"triangles": cells, "seconds": te, "cells_per_s": cells / te, "cores": 1,
+                        "sample": "ESV2007 indicators (Oswald, P0 f, RT0 flux, eta_NC / eta_R / eta_DF) on %d triangles" % cells}
     return out
+
+
+def default_cpu_n(n):
+    """the CPU arm runs the bench's own grid when the host has the memory for the oracle's CSR arrays (~1.3 KB per cell),
+    else the largest power-of-two fraction of it that fits"""
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 32 << 30
+    m = n
+    while m > 256 and 1400.0 * m * m > 0.6 * avail:
+        m //= 2
+    return m
 
 
 def run_reference(args):
     """The CPU arm: the oracle port with all the host threads it can use (its own threading; the reference's walk is
-    serial, the one-core figure is reported next to it)."""
+    serial, the one-core figure is reported next to it), on the bench's own grid."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_cpu = args.cpu_n
+    n_cpu = args.cpu_n if args.cpu_n > 0 else default_cpu_n(args.n)
     cores = os.cpu_count() or 1
+    w = CpuWorkload(n_cpu)
     steps = []
     for k in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        rec = _cpu_record(n_cpu, _cpu_sample(n_cpu, args.cpu_cg_iters, cores), cores)
+        rec = w.record(w.step(cores, args.cpu_cg_iters), cores, args.cpu_cg_iters)
         steps.append((time.perf_counter() - t0, rec))
     timed = steps[args.warmup:]
     cb = timed[-1][1]
     value = float(np.mean([s[1]["value"] for s in timed]))
     cb["value"] = value
-    one = _cpu_record(n_cpu, _cpu_sample(n_cpu, args.cpu_cg_iters, 1), 1)  # outside the timed steps
-    cb["one_core"] = {"cores": 1, "value": one["value"], "assemble_s": one["assemble_s"],
+    # outside the timed steps: the same walk on one core (bounded: a 1024^2 sample when the grid is larger) and a
+    # Jacobi-CG solve to 1e-10 on a 768^2 sample with all threads
+    n_one = min(n_cpu, 1024)
+    w1 = w if n_one == n_cpu else CpuWorkload(n_one)
+    one = w1.record(w1.step(1, min(args.cpu_cg_iters, 5)), 1, args.cpu_cg_iters)
+    cb["one_core"] = {"cores": 1, "value": one["value"], "assemble_s": one["assemble_s"], "grid": "%dx%d" % (n_one, n_one),
                       "cg_s_per_iteration": one["cg_s_per_iteration"],
-                      "note": "the same sample as the reference runs it: serial walk (discretizations/swipdg.hh:485)"}
+                      "note": "the walk as the reference runs it: serial (discretizations/swipdg.hh:485)"}
+    ws = CpuWorkload(args.cpu_solve_n) if args.cpu_solve_n != n_cpu else w
+    t, it, rr = ws.solve(cores)
+    cb["solve"] = {"grid": "%dx%d" % (args.cpu_solve_n, args.cpu_solve_n), "solver": "cg.diagonal", "cores": cores,
+                   "seconds": t, "iterations": it, "relative_residual": rr}
+    config = workload_config(args.n, args.solver, args.gpus)
+    if n_cpu != args.n:
+        config["cpu_sample"] = "%dx%d cells (host memory)" % (n_cpu, n_cpu)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "DoFs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean([s[0] for s in timed])),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "config5: SWIPDG p1 (Q1), structured [-1,1]^2 grid, ESV2007 data; CPU sample %dx%d cells"
-                       % (n_cpu, n_cpu), "cells": n_cpu * n_cpu},
+            "config": config,
             "cg_s_per_iteration": float(np.mean([s[1]["cg_s_per_iteration"] for s in timed])),
             "cpu_baseline": cb,
             "e2e": {"value": value, "unit": "DoFs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def gather_concat(local, world, torch):
+    """every rank's numpy array, concatenated in rank order, on every rank (NCCL all_gather of padded device tensors)"""
+    if world == 1:
+        return np.asarray(local)
+    import torch.distributed as dist
+    local = np.ascontiguousarray(local)
+    n = torch.tensor([local.shape[0]], dtype=torch.int64, device="cuda")
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(x.item()) for x in sizes]
+    t = torch.zeros(max(sizes), dtype=torch.from_numpy(local[:0]).dtype, device="cuda")
+    t[:local.shape[0]] = torch.from_numpy(local).cuda()
+    parts = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    return np.concatenate([p[:k].cpu().numpy() for p, k in zip(parts, sizes)])
+
+
+def small_grid_parity(hdd, torch, comm, rank, world, local_rank):
+    """In-run parity of what this process group computes, against the CPU oracle (checker only, rank 0): a 256^2 Q1 grid
+    (pattern bit-exact, entries and rhs 1e-12, cg.mg solution 1e-8) and 8192 triangles (block-Jacobi CG solution and every
+    per-cell indicator 1e-8, eta_ESV2007 against the reference's golden 4.85e-02), sharded over the ranks like the
+    timed workload."""
+    from oracle import oracle as o
+    out = {}
+    # ---- Q1, the bench configuration in small -------------------------------------------------------------------
+    n = 256
+    g = hdd.grids.cube(n, partitions=(8, 8))
+    roff = hdd.parallel.rank_cell_offsets(g, world)
+    d = hdd.BlockSWIPDG(g, hdd.problems.ESV2007(), device=local_rank, cell_range=(int(roff[rank]), int(roff[rank + 1])), comm=comm)
+    d.init()
+    rp, col = d.pattern()
+    counts = gather_concat(np.diff(rp), world, torch)
+    col = gather_concat(col, world, torch)
+    A = gather_concat(d.system_matrix().affine_part(), world, torch)
+    b = gather_concat(d.rhs().affine_part(), world, torch)
+    u, info = d.uncached_solve({"type": "cg.mg", "precision": 1e-12, "max_iter": 2000}, return_info=True)
+    res = d.residual()
+    u = gather_concat(u, world, torch)
+    if rank == 0:
+        m = o.Mesh(o.CUBE, g.xy, g.cell_verts, g.cell_neigh)
+        rp_o, col_o = o.pattern(m)
+        A_o = o.assemble_lhs(m, o.const(1.0), None, rp_o, col_o)
+        b_o = o.assemble_rhs(m, o.esv2007_force())
+        rp_g = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        # the oracle's own solution, reached by its CG from the device solution (a wrong one would neither be close nor cheap)
+        u_o, it_o, rr_o = o.cg(rp_o, col_o, A_o, b_o, precond=1, rtol=1e-13, maxit=20000, x0=u)
+        out["q1_256"] = {"pattern_equal": bool(np.array_equal(rp_g, rp_o) and np.array_equal(col, col_o)),
+                         "entries_rel": float(np.abs(A - A_o).max() / np.abs(A_o).max()),
+                         "rhs_rel": float(np.abs(b - b_o).max() / np.abs(b_o).max()),
+                         "solution_rel": float(np.abs(u - u_o).max() / np.abs(u_o).max()),
+                         "oracle_polish_iterations": int(it_o), "cg_mg_iterations": info["iterations"],
+                         "true_residual": res}
+    del d
+    # ---- P1 on 8192 triangles: solve + estimators ------------------------------------------------------------------
+    g = hdd.grids.simplex(32, partitions=(8, 8))
+    roff = hdd.parallel.rank_cell_offsets(g, world)
+    d = hdd.BlockSWIPDG(g, hdd.problems.ESV2007(), device=local_rank, cell_range=(int(roff[rank]), int(roff[rank + 1])), comm=comm)
+    d.init()
+    A = gather_concat(d.system_matrix().affine_part(), world, torch)
+    u_loc = d.uncached_solve({"type": "cg.blockdiagonal", "precision": 1e-13, "max_iter": 20000})
+    ind = d.indicators(u_loc)
+    eta = d.estimate(u_loc, "eta_ESV2007")
+    u = gather_concat(u_loc, world, torch)
+    ind = {k: gather_concat(v, world, torch) for k, v in ind.items()}
+    if rank == 0:
+        m = o.Mesh(o.SIMPLEX, g.xy, g.cell_verts, g.cell_neigh)
+        rp_o, col_o = o.pattern(m)
+        A_o = o.assemble_lhs(m, o.const(1.0), None, rp_o, col_o)
+        b_o = o.assemble_rhs(m, o.esv2007_force())
+        u_o, it_o, rr_o = o.cg(rp_o, col_o, A_o, b_o, precond=1, rtol=1e-14, maxit=20000, x0=u)
+        ind_o = o.indicators(m, u, o.esv2007_force(), o.const(1.0))
+        worst = max(float(np.abs(ind[k] - ind_o[k]).max() / max(np.abs(ind_o[k]).max(), 1e-300))
+                    for k in ("nc2", "res2", "r2", "df2", "dfstar2", "rstar2", "amin", "resstar2"))
+        out["p1_8192"] = {"entries_rel": float(np.abs(A - A_o).max() / np.abs(A_o).max()),
+                          "solution_rel": float(np.abs(u - u_o).max() / np.abs(u_o).max()),
+                          "indicators_rel": worst, "eta_ESV2007": eta, "eta_ESV2007_golden": 4.85e-02}
+    del d
+    ok = True
+    if rank == 0:
+        q, t = out["q1_256"], out["p1_8192"]
+        ok = (q["pattern_equal"] and q["entries_rel"] <= 1e-12 and q["rhs_rel"] <= 1e-12 and q["solution_rel"] <= 1e-8
+              and t["entries_rel"] <= 1e-12 and t["solution_rel"] <= 1e-8 and t["indicators_rel"] <= 1e-8
+              and abs(t["eta_ESV2007"] - 4.85e-02) <= 0.006 * 4.85e-02)
+        out["ok"] = bool(ok)
+    return out, ok
+
+
+def estimator_phase(hdd, torch, capi, comm, rank, world, local_rank, n, peak, peak_kind, barrier):
+    """The a-posteriori estimator (north_star item 3) on BASELINE config 4 at scale: P1 on 8 * s^2 triangles (s = 1448 for
+    the 4096^2-sized job: 16.8 M triangles, 50 M DoFs) with the 8 x 8 subdomain partition sharded over the ranks.
+    Times the assembly of that simplex system, one eta_ESV2007 evaluation through the public API from a host vector
+    (H2D of the vector inside the timed region) and the device part alone (CUDA events)."""
+    import ctypes as C
+    L = capi.lib()
+    s = max(8, int(round(n * 1448 / 4096 / 8.0)) * 8)
+    t0 = time.perf_counter()
+    g = hdd.grids.simplex(s, partitions=(8, 8))
+    t_grid = time.perf_counter() - t0
+    roff = hdd.parallel.rank_cell_offsets(g, world)
+    cr = (int(roff[rank]), int(roff[rank + 1]))
+    d = hdd.BlockSWIPDG(g, hdd.problems.ESV2007(), device=local_rank, cell_range=cr, comm=comm)
+    d.init()
+    t_asm = min(d.assemble() for _ in range(3))
+    # the nodal interpolant of the exact solution as the vector: eta_NC = 0, eta_R and eta_DF have known asymptotics
+    v = g.xy[g.cell_verts[cr[0]:cr[1]]]
+    u = capi.pinned_empty((3 * (cr[1] - cr[0]),), np.float64)
+    u[:] = (np.cos(0.5 * np.pi * v[..., 0]) * np.cos(0.5 * np.pi * v[..., 1])).reshape(-1)
+    eta = d.estimate(u, "eta_ESV2007")  # warm-up (allocations)
+    barrier()
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        eta = d.estimate(u, "eta_ESV2007")
+    barrier()
+    t_e2e = (time.perf_counter() - t0) / reps
+    e_nc, e_r = d.estimate(u, "eta_NC_ESV2007"), d.estimate(u, "eta_R_ESV2007")
+    roofs = {}
+    for which, name in ((4, "estimator_pass"), (5, "indicators"), (3, "assembly_p1")):
+        sec, byt = C.c_double(), C.c_double()
+        capi.check(L.hdd_profile_kernel(d._h, which, 5, C.byref(sec)))
+        capi.check(L.hdd_kernel_bytes(d._h, which, C.byref(byt)))
+        roofs[name] = {"bound": "hbm", "achieved": byt.value / sec.value / 1e9, "peak": peak, "unit": "GB/s",
+                       "frac": byt.value / sec.value / 1e9 / peak, "traffic": None, "ms": sec.value * 1e3,
+                       "algorithmic_bytes": byt.value, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)"}
+    stats = torch.tensor([t_asm, t_e2e, roofs["estimator_pass"]["ms"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        torch.distributed.all_reduce(stats, op=torch.distributed.ReduceOp.MAX)
+    t_asm, t_e2e, ms_dev = [float(x) for x in stats.cpu()]
+    n_cells, n_dofs = g.n_cells, 3 * g.n_cells
+    # asymptotics of the committed ladder (eta_R s^2 = 1.157, 1.165, 1.162, 1.167 on levels 0..3)
+    expect_r = 1.165 / (s * s)
+    ok = (abs(e_nc) <= 1e-10) and (s < 16 or abs(e_r - expect_r) <= 0.02 * expect_r) and np.isfinite(eta)
+    out = {"workload": "config4 at scale: BlockSWIPDG p1 on %d triangles (ALU-ladder grid, %d^2 squares of 8), 8x8 subdomains"
+                       % (n_cells, s), "triangles": n_cells, "dofs": n_dofs,
+           "assemble_ms": 1e3 * t_asm, "assembled_dofs_per_s": n_dofs / t_asm,
+           "estimate_ms": ms_dev, "cells_per_s": n_cells / (1e-3 * ms_dev),
+           "estimate_e2e_ms": 1e3 * t_e2e, "e2e_h2d_bytes": int(8 * n_dofs),
+           "eta_ESV2007": eta, "eta_NC": e_nc, "eta_R": e_r, "eta_R_expected": expect_r, "ok": bool(ok),
+           "roofline_estimator": roofs["estimator_pass"], "roofline_indicators": roofs["indicators"],
+           "roofline_assembly_p1": roofs["assembly_p1"], "grid_generation_s": t_grid,
+           "note": "vector = nodal interpolant of the exact solution (eta_NC = 0 by construction); estimate_ms is the "
+                   "device part (Oswald + indicator kernel + reductions), estimate_e2e_ms the public call from a "
+                   "page-locked host vector"}
+    del d
+    return out, bool(ok)
 
 
 def main():
@@ -196,15 +416,26 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--grid", dest="n", type=int, default=4096, help="cells per side of the structured grid")
-    ap.add_argument("--cpu-n", type=int, default=768)
-    ap.add_argument("--cpu-cg-iters", type=int, default=100)
+    ap.add_argument("--cpu-n", type=int, default=0, help="CPU sample: cells per side (0: reference arm = --grid if the host "
+                                                         "memory allows, cpu_baseline of the GPU arm = 768)")
+    ap.add_argument("--cpu-cg-iters", type=int, default=0, help="0: 100 * (768 / cpu_n)^2, at least 3")
+    ap.add_argument("--cpu-solve-n", type=int, default=768)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-estimator", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the small-grid check against the CPU oracle")
     ap.add_argument("--solver", default="cg.mg", help="cg.mg | cg.blockdiagonal | cg.diagonal | cg.identity")
     ap.add_argument("--no-jacobi", action="store_true", help="skip the extra Jacobi-CG solve reported next to --solver")
     args = ap.parse_args()
     if args.impl == "reference":
+        if args.cpu_cg_iters <= 0:
+            n_cpu = args.cpu_n if args.cpu_n > 0 else default_cpu_n(args.n)
+            args.cpu_cg_iters = max(3, int(100 * (768.0 / n_cpu) ** 2))
         return run_reference(args)
+    if args.cpu_n <= 0:
+        args.cpu_n = 768
+    if args.cpu_cg_iters <= 0:
+        args.cpu_cg_iters = max(3, int(100 * (768.0 / args.cpu_n) ** 2))
 
     import torch
     import dune_hdd_b200 as hdd
@@ -273,6 +504,17 @@ def main():
         torch.distributed.all_reduce(stats, op=torch.distributed.ReduceOp.MAX)
     t_asm, t_cg, wall = [float(v) for v in stats.cpu()]
 
+    # ---- what was timed is checked: true residual recomputed from scratch, error against the exact solution ----------
+    check = {"true_residual": d.residual(), "cg_iterations": iters}
+    norms = d.error_norms(*hdd.problems.ESV2007_EXACT, order=5)
+    # asymptotics of the committed SGrid ladder (test/linearelliptic-swipdg-expectations_esv2007_2dsgrid.cxx:32-36):
+    # L2 n^2 = 0.723, 0.742, 0.759, 0.770 -> 0.78; H1 n = 2.216, 2.224, 2.234, 2.240 -> 2.25
+    check.update({"L2_error": norms["L2"], "H1_semi_error": norms["H1_semi"], "energy_error": norms["energy"],
+                  "H1_semi_expected": 2.25 / n, "L2_expected": 0.78 / (n * n)})
+    check_ok = (check["true_residual"] <= 1e-9 and
+                (n < 64 or (abs(norms["H1_semi"] - 2.25 / n) <= 0.02 * 2.25 / n and
+                            abs(norms["L2"] - 0.78 / (n * n)) <= 0.05 * 0.78 / (n * n))))
+
     # the plain Jacobi-preconditioned CG on the same system, once, outside the timed steps: its SpMV / update / direction
     # kernels are the ones the roofline numbers below are taken from
     jacobi = None
@@ -316,11 +558,24 @@ def main():
                       "frac": byt.value / sec.value / 1e9 / peak, "traffic": traffic.get(name), "ms": sec.value * 1e3,
                       "algorithmic_bytes": byt.value, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)"}
 
+    # the same solver on the CPU baseline's solve sample (cg.diagonal on cpu_solve_n^2 cells): a same-size pair for the
+    # "CG solve s" half of the metric
+    same_size = None
+    if world == 1 and not args.no_cpu_baseline:
+        gs = hdd.grids.cube(args.cpu_solve_n)
+        ds = hdd.SWIPDG(gs, problem, device=local_rank)
+        ds.init()
+        _, si = ds.uncached_solve(dict(options, type="cg.diagonal"), return_info=True, copy_to_host=False)
+        _, sm = ds.uncached_solve(dict(options, type="cg.mg"), return_info=True, copy_to_host=False)
+        same_size = {"grid": "%dx%d" % (args.cpu_solve_n, args.cpu_solve_n), "cg.diagonal_s": si["seconds"],
+                     "cg.diagonal_iterations": si["iterations"], "cg.mg_s": sm["seconds"], "cg.mg_iterations": sm["iterations"]}
+        del ds
+
     # end to end through the public API from host buffers (H2D of the grid + problem, D2H of the solution), every step
     e2e = None
+    del d
+    torch.cuda.empty_cache()
     if not args.no_e2e:
-        del d
-        torch.cuda.empty_cache()
         e_asm, e_cg = [], []
         own_dofs = (cell_range[1] - cell_range[0]) * 4
         x_host = capi.pinned_empty((own_dofs,), np.float64)  # page-locked result buffer, reused by every step
@@ -349,29 +604,40 @@ def main():
                "note": "value = DoFs / (hdd_mesh_create from page-locked host arrays + hdd_swipdg_create + init), incl. "
                        "host-side localisation of the grid; cg_solve_s includes the D2H copy of the solution"}
 
+    est, est_ok = (None, True)
+    if not args.no_estimator:
+        est, est_ok = estimator_phase(hdd, torch, capi, comm, rank, world, local_rank, n, peak, peak_kind, barrier)
+    parity, parity_ok = (None, True)
+    if not args.no_parity:
+        parity, parity_ok = small_grid_parity(hdd, torch, comm, rank, world, local_rank)
+    check["small_grid_parity"] = parity
+    check["ok"] = bool(check_ok and est_ok and parity_ok)
+
     if rank == 0:
+        config = workload_config(n, args.solver, world)
+        config["halo"] = (("peer-memory SpMV (CUDA IPC over NVLink)" if results[-1][1].get("peer_memory") else
+                           "NCCL send/recv of the CG direction" + (", row-strip exchanges of the vertex levels (cg.mg)"
+                                                                  if args.solver == "cg.mg" else ""))
+                          if world > 1 else "none")
         line = {"metric": METRIC, "value": args.steps * n_dofs / t_asm, "unit": "DoFs/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "config5: SWIPDG p1 (Q1) on the %dx%d structured grid [-1,1]^2, ESV2007 data, "
-                                       "8x8 BlockSWIPDG partition" % (n, n), "cells": n * n, "dofs": n_dofs,
-                           "cg": "%s to ||r||/||b|| <= 1e-10" % args.solver, "l2_flush": "inputs >> L2 (matrix "
-                           "%.1f GB per part)" % (8.0 * 16 * (n * n + 2 * 2 * n * (n - 1)) / 1e9),
-                           "parallelism": "subdomain slabs x%d" % world,
-                           "halo": ("peer-memory SpMV (CUDA IPC over NVLink)" if results[-1][1].get("peer_memory") else
-                                    "NCCL send/recv of the CG direction" + (", all-reduce of the restricted residual (cg.mg)"
-                                                                           if args.solver == "cg.mg" else ""))
-                           if world > 1 else "none"},
+                "config": config,
                 "assemble_ms": 1e3 * t_asm / args.steps, "cg_solve_s": t_cg / args.steps, "cg_iterations": iters,
                 "cg_s_per_iteration": t_cg / args.steps / max(iters, 1), "cg_diagonal": jacobi,
+                "time_to_solution_dofs_per_s": n_dofs / (wall / args.steps),
+                "check": check,
                 "roofline": roof["spmv"], "roofline_assembly": roof["assembly"], "roofline_cg_update": roof["cg_update"],
-                "roofline_cg_direction": roof["cg_direction"],
+                "roofline_cg_direction": roof["cg_direction"], "estimator": est, "same_size_solve": same_size,
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "grid_generation_s": t_grid}
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args.cpu_n, args.cpu_cg_iters)
+            line["cpu_baseline"] = cpu_baseline(args.cpu_n, args.cpu_cg_iters, args.cpu_solve_n)
         print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
+    if not check["ok"]:
+        sys.stderr.write("bench.py: the in-run check failed: %s\n" % json.dumps(check))
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -177,6 +177,7 @@ struct Parser {
     p.n_ops = 0;
     int n_consts = 0, depth = 0, max_depth = 0;
     emit(root, p, n_consts, depth, max_depth);
+    p.depth = max_depth;
     return p;
   }
   // constant folding, bottom-up; returns the (possibly new) node

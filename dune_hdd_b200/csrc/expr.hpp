@@ -45,15 +45,19 @@ constexpr int kMaxOps = 48;
 constexpr int kMaxConsts = 16;
 constexpr int kMaxStack = 16;
 
+constexpr int kRegStack = 6;  // programs at most this deep run on a register stack (no local memory on the device)
+
 struct Program {
   int n_ops;
+  int depth;  // maximal stack depth of the program
   unsigned char op[kMaxOps];
   unsigned char cidx[kMaxOps];  // constant slot for OP_CONST
   double cst[kMaxConsts];
 };
 
 // Evaluates a compiled program.  vars: x[0], x[1] (functions) or mu[0..3] (parameter functionals).
-HDD_HD HDD_FORCEINLINE double eval_program(const Program& p, const double* vars) {
+// Generic version: value stack in an indexed array (local memory on the device).
+HDD_HD HDD_FORCEINLINE double eval_program_generic(const Program& p, const double* vars) {
   double st[kMaxStack];
   int sp = 0;
   for (int k = 0; k < p.n_ops; ++k) {
@@ -83,6 +87,45 @@ HDD_HD HDD_FORCEINLINE double eval_program(const Program& p, const double* vars)
     }
   }
   return sp > 0 ? st[0] : 0.0;
+}
+
+// The same program on a stack of kRegStack named values (s0 = top): every access is statically indexed, so on the
+// device the stack lives in registers - the array version spills every push and pop to local memory, which showed up as
+// 9x the algorithmic DRAM writes in the estimator kernel.  Identical arithmetic, identical results.
+HDD_HD HDD_FORCEINLINE double eval_program(const Program& p, const double* vars) {
+  if (p.depth > kRegStack) return eval_program_generic(p, vars);
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, s5 = 0.0;
+#define HDD_PUSH(v) { const double t_ = (v); s5 = s4; s4 = s3; s3 = s2; s2 = s1; s1 = s0; s0 = t_; }
+#define HDD_BIN(e) { const double a_ = s1, b_ = s0; s0 = (e); s1 = s2; s2 = s3; s3 = s4; s4 = s5; }
+  for (int k = 0; k < p.n_ops; ++k) {
+    switch (p.op[k]) {
+      case OP_CONST: HDD_PUSH(p.cst[p.cidx[k]]); break;
+      case OP_VAR0: HDD_PUSH(vars[0]); break;
+      case OP_VAR1: HDD_PUSH(vars[1]); break;
+      case OP_VAR2: HDD_PUSH(vars[2]); break;
+      case OP_VAR3: HDD_PUSH(vars[3]); break;
+      case OP_ADD: HDD_BIN(a_ + b_); break;
+      case OP_SUB: HDD_BIN(a_ - b_); break;
+      case OP_MUL: HDD_BIN(a_ * b_); break;
+      case OP_DIV: HDD_BIN(a_ / b_); break;
+      case OP_POW: HDD_BIN(pow(a_, b_)); break;
+      case OP_MIN: HDD_BIN(fmin(a_, b_)); break;
+      case OP_MAX: HDD_BIN(fmax(a_, b_)); break;
+      case OP_NEG: s0 = -s0; break;
+      case OP_SIN: s0 = sin(s0); break;
+      case OP_COS: s0 = cos(s0); break;
+      case OP_TAN: s0 = tan(s0); break;
+      case OP_EXP: s0 = exp(s0); break;
+      case OP_LOG: s0 = log(s0); break;
+      case OP_SQRT: s0 = sqrt(s0); break;
+      case OP_ABS: s0 = fabs(s0); break;
+      case OP_ATAN: s0 = atan(s0); break;
+      default: break;
+    }
+  }
+#undef HDD_PUSH
+#undef HDD_BIN
+  return p.n_ops > 0 ? s0 : 0.0;
 }
 
 // Compiles `text` with the (vector) variable called `var` ("x" or "mu"): var[k], and bare `var` for var[0].

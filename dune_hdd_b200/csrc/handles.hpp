@@ -230,6 +230,8 @@ struct hdd_swipdg {
 
   // estimator workspace
   hdd::DevBuf<double> vertex_mean, ind_out, seg_out;
+  bool estimator_vector_resident = false;        // tmp_local holds the vector of the last hdd_estimate (halo included)
+  const hdd_parameters* profile_prm = nullptr;   // parameters hdd_profile_kernel(4/5) evaluates the estimator at
 
   hdd::MeshView view() const {
     hdd::MeshView v = mesh->view(has_tensor ? tensor.p : nullptr);

@@ -126,6 +126,9 @@ void launch_cg_spmv(const MeshView& m, const CgBuffers& c, int parity, cudaStrea
 void launch_cg_update(const MeshView& m, const CgBuffers& c, int parity, cudaStream_t s);
 void launch_cg_direction(const MeshView& m, const CgBuffers& c, int parity, cudaStream_t s);
 
+// sc->red[0] = sum (b - q)^2, sc->red[1] = sum b^2 over n entries (true residual check, hdd_residual)
+void launch_residual_norms(const double* b, const double* q, int64_t n, double* partial, CgScalars* sc, cudaStream_t s);
+
 // a15 (pure Neumann): symmetric unit row/column 0 + rhs[0] = 0, and x -= mean(x) after the solve
 void launch_unit_row_col0(const MeshView& m, double* values, double* b, cudaStream_t s);
 void launch_subtract_mean(double* x, int64_t n, double* partial, CgScalars* sc, cudaStream_t s);
@@ -144,8 +147,12 @@ struct IndicatorArgs {
 };
 void launch_oswald_vertex_means(const int64_t* vptr, const int32_t* vdof, const uint8_t* vboundary, int32_t n_verts,
                                 const double* u_local, double* vertex_mean, cudaStream_t s);
-void launch_indicators(const MeshView& m, const IndicatorArgs& a, int polorder, cudaStream_t s);
-// deterministic segmented sums: out[seg] = sum_{k in [seg_ptr[seg], seg_ptr[seg+1])} in[k]
+// fn_table_host: the host copy of a.fn_table (decides whether any diffusion-factor part is an expression)
+void launch_indicators(const MeshView& m, const IndicatorArgs& a, const DevFn* fn_table_host, int polorder, cudaStream_t s);
+// deterministic segmented reductions (fixed trees): out[r * n_seg + seg] = sum (or min, if bit r of min_mask is set)
+// over k in [seg_ptr[seg], seg_ptr[seg+1]) of in[r * row_stride + k], all rows in one launch
+void launch_segment_reduce(const double* in, int64_t row_stride, int n_rows, unsigned min_mask, const int64_t* seg_ptr_dev,
+                           int n_seg, double* out, cudaStream_t s);
 void launch_segment_sums(const double* in, const int64_t* seg_ptr_dev, int n_seg, double* out, cudaStream_t s);
 void launch_segment_min(const double* in, const int64_t* seg_ptr_dev, int n_seg, double* out, cudaStream_t s);
 

@@ -682,6 +682,18 @@ __global__ void __launch_bounds__(kCgThreads) k_sum(const double* __restrict__ x
   grid_sum<1>(v, partial, ticket, [out](const double(&w)[1]) { *out = w[0]; });
 }
 
+__global__ void __launch_bounds__(kCgThreads) k_residual_norms(const double* __restrict__ b, const double* __restrict__ q, int64_t n,
+                                                              double* partial, CgScalars* sc) {
+  double v[2] = {0.0, 0.0};
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double bi = b[i], d = bi - q[i];
+    v[0] = fma(d, d, v[0]);
+    v[1] = fma(bi, bi, v[1]);
+  }
+  grid_sum<2>(v, partial, &sc->ticket_a, [sc](const double(&w)[2]) { sc->red[0] = w[0]; sc->red[1] = w[1]; });
+}
+
 __global__ void k_shift(double* __restrict__ x, int64_t n, const double* __restrict__ sum, double inv_count) {
   const double mean = *sum * inv_count;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
@@ -849,6 +861,11 @@ void launch_subtract_mean(double* x, int64_t n, double* partial, CgScalars* sc, 
   k_shift<<<cg_grid(n), kCgThreads, 0, s>>>(x, n, &sc->red[3], 1.0 / double(n));
   count_launch(2);
   HDD_CUDA(cudaGetLastError());
+}
+
+void launch_residual_norms(const double* b, const double* q, int64_t n, double* partial, CgScalars* sc, cudaStream_t s) {
+  k_residual_norms<<<cg_grid(n), kCgThreads, 0, s>>>(b, q, n, partial, sc);
+  count_launch();
 }
 
 void launch_pack(const double* v_local, const int32_t* cells, int64_t n_cells, int nd, double* out, cudaStream_t s) {

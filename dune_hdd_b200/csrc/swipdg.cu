@@ -353,26 +353,16 @@ struct IndicatorSums {           // per subdomain (global numbering)
   std::vector<double> s[9];      // sums of rows 0..8 (row 6: minimum)
 };
 
-// runs the two estimator passes and reduces the per-cell rows per subdomain
-void run_indicators(hdd_swipdg* h, const double* u_host, const hdd_parameters* prm, IndicatorSums& sums) {
+// device part of an estimator evaluation: Oswald vertex means, the per-cell indicator pass and the segmented reductions
+// of its nine rows.  Stream ordered, no host synchronisation; u is expected in h->tmp_local (owned part filled in).
+void indicators_device(hdd_swipdg* h, const hdd_parameters* prm, bool exchange_halo, int parts = 7) {
   hdd_mesh* m = h->mesh;
   cudaStream_t s = m->stream;
-  if (m->kind != HDD_SIMPLEX2D)
-    HDD_THROW(HDD_ERR_USING_THIS_WRONG, "the estimators are only available on 2d simplex grids (estimators/swipdg.hh:71)");
-  if (h->polorder != 1)
-    HDD_THROW(HDD_ERR_NOT_IMPLEMENTED, "the estimators need polOrder 1 (Oswald interpolation and RT0 reconstruction, estimators/swipdg.hh:149,359)");
   const int nl = h->nl;
-  const size_t loc = size_t(m->n_loc) * nl, rows = size_t(h->n_rows);
-  if (!h->tmp_local.p) { h->tmp_local.alloc(loc); h->tmp_local.zero(s); }
-  if (u_host) {
-    HDD_CUDA(cudaMemcpyAsync(h->tmp_local.p + size_t(m->own0) * nl, u_host, rows * sizeof(double), cudaMemcpyHostToDevice, s));
-  } else {
-    if (!h->have_solution) HDD_THROW(HDD_ERR_USING_THIS_WRONG, "no vector given and no solution available");
-    HDD_CUDA(cudaMemcpyAsync(h->tmp_local.p + size_t(m->own0) * nl, h->x.p, rows * sizeof(double), cudaMemcpyDeviceToDevice, s));
-  }
-  m->halo_exchange(h->tmp_local.p, nl);
+  if (exchange_halo) m->halo_exchange(h->tmp_local.p, nl);
   if (!h->vertex_mean.p) h->vertex_mean.alloc(size_t(m->n_verts_loc));
-  launch_oswald_vertex_means(m->vptr.p, m->vdof.p, m->vboundary.p, m->n_verts_loc, h->tmp_local.p, h->vertex_mean.p, s);
+  if (parts & 1)
+    launch_oswald_vertex_means(m->vptr.p, m->vdof.p, m->vboundary.p, m->n_verts_loc, h->tmp_local.p, h->vertex_mean.p, s);
 
   const int ms = prm ? prm->mu_size : 0;
   const double* mu = prm ? prm->mu : nullptr;
@@ -397,16 +387,38 @@ void run_indicators(hdd_swipdg* h, const double* u_host, const hdd_parameters* p
   a.cell_verts = m->cell_verts.p;
   if (!h->ind_out.p) h->ind_out.alloc(size_t(9) * m->n_own);
   a.out = h->ind_out.p;
-  launch_indicators(h->view(), a, h->polorder, s);
+  if (parts & 2) launch_indicators(h->view(), a, h->fn_host.data(), h->polorder, s);
 
   const int n_seg = int(m->seg_sub.size());
   if (!h->seg_out.p) h->seg_out.alloc(size_t(9) * std::max(n_seg, 1));
-  for (int r = 0; r < 9; ++r) {
-    if (r == 6)
-      launch_segment_min(h->ind_out.p + size_t(r) * m->n_own, m->d_seg_ptr.p, n_seg, h->seg_out.p + size_t(r) * n_seg, s);
-    else
-      launch_segment_sums(h->ind_out.p + size_t(r) * m->n_own, m->d_seg_ptr.p, n_seg, h->seg_out.p + size_t(r) * n_seg, s);
+  if (parts & 4)
+    launch_segment_reduce(h->ind_out.p, int64_t(m->n_own), 9, 1u << 6, m->d_seg_ptr.p, n_seg, h->seg_out.p, s);  // row 6: minimum
+}
+
+void check_estimator_space(const hdd_swipdg* h) {
+  if (h->mesh->kind != HDD_SIMPLEX2D)
+    HDD_THROW(HDD_ERR_USING_THIS_WRONG, "the estimators are only available on 2d simplex grids (estimators/swipdg.hh:71)");
+  if (h->polorder != 1)
+    HDD_THROW(HDD_ERR_NOT_IMPLEMENTED, "the estimators need polOrder 1 (Oswald interpolation and RT0 reconstruction, estimators/swipdg.hh:149,359)");
+}
+
+// runs the two estimator passes and reduces the per-cell rows per subdomain
+void run_indicators(hdd_swipdg* h, const double* u_host, const hdd_parameters* prm, IndicatorSums& sums) {
+  hdd_mesh* m = h->mesh;
+  cudaStream_t s = m->stream;
+  check_estimator_space(h);
+  const int nl = h->nl;
+  const size_t loc = size_t(m->n_loc) * nl, rows = size_t(h->n_rows);
+  if (!h->tmp_local.p) { h->tmp_local.alloc(loc); h->tmp_local.zero(s); }
+  if (u_host) {
+    HDD_CUDA(cudaMemcpyAsync(h->tmp_local.p + size_t(m->own0) * nl, u_host, rows * sizeof(double), cudaMemcpyHostToDevice, s));
+  } else {
+    if (!h->have_solution) HDD_THROW(HDD_ERR_USING_THIS_WRONG, "no vector given and no solution available");
+    HDD_CUDA(cudaMemcpyAsync(h->tmp_local.p + size_t(m->own0) * nl, h->x.p, rows * sizeof(double), cudaMemcpyDeviceToDevice, s));
   }
+  indicators_device(h, prm, true);
+  h->estimator_vector_resident = true;
+  const int n_seg = int(m->seg_sub.size());
   std::vector<double> seg(size_t(9) * std::max(n_seg, 1));
   HDD_CUDA(cudaMemcpyAsync(seg.data(), h->seg_out.p, seg.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
   HDD_CUDA(cudaStreamSynchronize(s));
@@ -730,6 +742,31 @@ int hdd_apply(hdd_swipdg* h, const double* mu, int mu_size, const double* x_host
     launch_spmv(h->view(), vals, h->tmp_local.p, y.p, s);
     HDD_CUDA(cudaMemcpyAsync(y_host, y.p, rows * sizeof(double), cudaMemcpyDeviceToHost, s));
     HDD_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int hdd_residual(hdd_swipdg* h, const double* mu, int mu_size, double* relative_residual) {
+  return guarded([&] {
+    require_init(h);
+    check_mu(h, mu, mu_size, "mu");
+    if (!h->have_solution) HDD_THROW(HDD_ERR_USING_THIS_WRONG, "no solution available, call hdd_solve first");
+    hdd_mesh* m = h->mesh;
+    if (m->purely_neumann) HDD_THROW(HDD_ERR_NOT_IMPLEMENTED, "hdd_residual for the modified pure-Neumann system");
+    m->set_device();
+    cudaStream_t s = m->stream;
+    const double* vals = freeze_lhs(h, mu, mu_size);
+    freeze_rhs(h, mu, mu_size);
+    const size_t loc = size_t(m->n_loc) * h->nl, rows = size_t(h->n_rows);
+    if (!h->tmp_local.p) { h->tmp_local.alloc(loc); h->tmp_local.zero(s); }
+    HDD_CUDA(cudaMemcpyAsync(h->tmp_local.p + size_t(m->own0) * h->nl, h->x.p, rows * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    m->halo_exchange(h->tmp_local.p, h->nl);
+    launch_spmv(h->view(), vals, h->tmp_local.p, h->q.p, s);
+    launch_residual_norms(h->b.p, h->q.p, int64_t(rows), h->partial.p, h->sc.p, s);
+    if (m->world > 1) Nccl::get().all_reduce_sum(&h->sc.p->red[0], 2, m->comm, s);
+    double red[2] = {0.0, 0.0};
+    HDD_CUDA(cudaMemcpyAsync(red, &h->sc.p->red[0], sizeof(red), cudaMemcpyDeviceToHost, s));
+    HDD_CUDA(cudaStreamSynchronize(s));
+    if (relative_residual) *relative_residual = red[1] > 0.0 ? std::sqrt(red[0] / red[1]) : std::sqrt(red[0]);
   });
 }
 
@@ -1203,7 +1240,17 @@ int hdd_kernel_bytes(hdd_swipdg* h, int which, double* bytes) {
       case 2:  // diagonal: read r,dinv,p, write p; block: read z,p, write p
         b = h->last_precond >= 2 ? 3.0 * 8.0 * rows : 4.0 * 8.0 * rows;
         break;
-      case 3: b = 8.0 * nnz + (geo + rec) * cells; break;
+      case 3:  // the tensor-grid Q1 kernel reads the neighbour record, the block offset and vertex 0 (28 B), no geometry
+        b = 8.0 * nnz + ((m->kind == HDD_CUBE2D && h->polorder == 1 && m->sx > 0) ? 28.0 : geo + rec) * cells;
+        break;
+      case 4:  // whole estimator pass: Oswald (u 8 B/DoF + incidence 4 B/DoF + 8 B/vertex written and read back) + case 5
+      case 5: {  // k_indicators, compulsory traffic: own u, geometry, neighbour ids, vertex ids, 9 rows written
+        const double verts = double(m->n_verts_loc);
+        const double ind = (8.0 * nl + geo + 4.0 * m->nf + 4.0 * nl + 72.0) * cells + 8.0 * verts;
+        const double osw = (8.0 * nl + 4.0 * nl) * cells + (8.0 + 8.0 + 1.0) * verts;
+        b = which == 5 ? ind : ind + osw + 72.0 * cells /* rows read by the segmented reduction */;
+        break;
+      }
       default: HDD_THROW(HDD_ERR_WRONG_INPUT, "unknown kernel id " << which);
     }
     if (bytes) *bytes = b;
@@ -1217,14 +1264,20 @@ int hdd_profile_kernel(hdd_swipdg* h, int which, int reps, double* avg_seconds) 
     hdd_mesh* m = h->mesh;
     m->set_device();
     cudaStream_t s = m->stream;
-    if (which != 3 && !h->x.p) HDD_THROW(HDD_ERR_USING_THIS_WRONG, "call hdd_solve once before profiling the CG kernels");
+    if (which >= 4) {
+      check_estimator_space(h);
+      if (!h->estimator_vector_resident)
+        HDD_THROW(HDD_ERR_USING_THIS_WRONG, "call hdd_estimate once before profiling the estimator kernels");
+    } else if (which != 3 && !h->x.p) {
+      HDD_THROW(HDD_ERR_USING_THIS_WRONG, "call hdd_solve once before profiling the CG kernels");
+    }
     const MeshView v = h->view();
     CgBuffers c{};
     c.values = h->lhs_comps.empty() ? h->lhs_affine->values.p : h->frozen.p;
     c.dinv = h->dinv.p; c.b = h->b.p; c.x = h->x.p; c.r = h->r.p; c.p = h->p.p; c.q = h->q.p;
     c.partial = h->partial.p; c.sc = h->sc.p;
     if (h->last_precond >= 2) { c.dinv_block = h->dinv_block.p; c.z = h->z.p; }
-    if (which != 3) {
+    if (which < 3) {
       // un-latch the convergence flag of parity 0 so that the kernels do their work; the vectors are scratch now
       CgScalars sc = *h->sc_host;
       sc.done[0] = 0; sc.done[1] = 0; sc.rz[0] = 1.0; sc.red[0] = 1.0; sc.red[1] = 1.0; sc.max_it = 1 << 30;
@@ -1241,6 +1294,8 @@ int hdd_profile_kernel(hdd_swipdg* h, int which, int reps, double* avg_seconds) 
           launch_assemble_lhs(v, h->fn_h(part.factor), part.factor.kind, part.factor.order, h->polorder, part.values.p, s);
           break;
         }
+        case 4: indicators_device(h, h->profile_prm, false, 7); break;  // the vector of the last hdd_estimate
+        case 5: indicators_device(h, h->profile_prm, false, 2); break;  // k_indicators alone
         default: HDD_THROW(HDD_ERR_WRONG_INPUT, "unknown kernel id " << which);
       }
       if (which == 2) {  // the direction kernel flips the parity state; keep parity 0 alive

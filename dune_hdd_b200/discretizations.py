@@ -328,6 +328,14 @@ class SWIPDG:
         _check(capi.lib().hdd_apply(self._h, capi.ptr(mu_a), ms, capi.ptr(x), capi.ptr(y)))
         return y
 
+    def residual(self, mu=None):
+        """||rhs(mu) - system_matrix(mu) x|| / ||rhs(mu)|| of the solution the last solve left on the device, recomputed
+        there with one SpMV (global over all ranks; collective)"""
+        mu_a, ms = _mu_array(mu)
+        r = C.c_double()
+        _check(capi.lib().hdd_residual(self._h, capi.ptr(mu_a), ms, C.byref(r)))
+        return r.value
+
     # ---- solve --------------------------------------------------------------------------------------------
     def solver_types(self):
         t, n = C.POINTER(C.c_char_p)(), C.c_int()

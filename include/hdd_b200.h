@@ -180,6 +180,10 @@ int hdd_sync(hdd_swipdg* h);
 
 /* get_operator().freeze_parameter(mu).apply(x, y) - one SpMV with the frozen operator (block-swipdg.hh:741). */
 int hdd_apply(hdd_swipdg* h, const double* mu, int mu_size, const double* x_host, double* y_host);
+/* True relative residual ||b(mu) - A(mu) x||_2 / ||b(mu)||_2 of the solution the last hdd_solve left on the device,
+ * recomputed from scratch (one SpMV with the frozen operator, global over all ranks): what a caller of the reference would
+ * get from rhs - system_matrix.mv(solution) after solve() (discretizations/base.hh:361-364).  Collective on N GPUs. */
+int hdd_residual(hdd_swipdg* h, const double* mu, int mu_size, double* relative_residual);
 
 typedef struct hdd_solve_info {
   int iterations;
@@ -310,7 +314,10 @@ int hdd_free(void* p);
 /* Times `reps` back-to-back launches of one hot kernel on the handle's stream with CUDA events (after 3 warm-up
  * launches) and returns the average launch duration: which = 0 the CG SpMV kernel (q = A p with the fused p.Ap
  * partial dot), 1 the fused CG update kernel, 2 the CG direction kernel, 3 the system-matrix assembly kernel of the
- * first affine part.  Needs a previous hdd_solve (CG workspace).  Used by bench.py for the roofline numbers. */
+ * first affine part; 4 the device part of one estimator evaluation (Oswald vertex means, the per-cell indicator kernel
+ * and the segmented reduction of its nine rows: the reference's four walks, estimators/swipdg.hh:668-687) on the vector
+ * of the last hdd_estimate / hdd_indicators with default parameters; 5 the indicator kernel alone.  0-2 need a previous
+ * hdd_solve (CG workspace), 4-5 a previous hdd_estimate.  Used by bench.py for the roofline numbers. */
 int hdd_profile_kernel(hdd_swipdg* h, int which, int reps, double* avg_seconds);
 /* algorithmic HBM bytes of one launch of that kernel (DESIGN.md "Kernels and rooflines") */
 int hdd_kernel_bytes(hdd_swipdg* h, int which, double* bytes);

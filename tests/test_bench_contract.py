@@ -6,7 +6,8 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-ARGS = ["--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-n", "48", "--cpu-cg-iters", "5"]
+ARGS = ["--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-n", "48", "--cpu-cg-iters", "5", "--cpu-solve-n", "32",
+        "--grid", "48"]
 KEYS = {"impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
         "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"}
 
@@ -26,7 +27,9 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == (os.cpu_count() or 1) and "sample" in d["cpu_baseline"]
     assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["one_core"]["cores"] == 1
     assert d["e2e"] == {"value": d["value"], "unit": "DoFs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"] and "model" not in d["config"]
+    assert "workload" in d["config"] and "model" not in d["config"] and d["config"]["cells"] == 48 * 48
+    # the "CG solve s" half of the metric: a Jacobi-CG solve to 1e-10 on a bounded sample
+    assert d["cpu_baseline"]["solve"]["relative_residual"] <= 1e-10 and d["cpu_baseline"]["solve"]["iterations"] > 0
 
 
 def test_reference_arm_under_torchrun_prints_on_rank_zero_only():
