@@ -300,6 +300,9 @@ def small_grid_parity(hdd, torch, comm, rank, world, local_rank):
     u, info = d.uncached_solve({"type": "cg.mg", "precision": 1e-12, "max_iter": 2000}, return_info=True)
     res = d.residual()
     u = gather_concat(u, world, torch)
+    # the Jacobi solve takes the peer-memory SpMV on N > 1 ranks (halo read over NVLink inside the kernel)
+    uj, info_j = d.uncached_solve({"type": "cg.diagonal", "precision": 1e-12, "max_iter": 20000}, return_info=True)
+    uj = gather_concat(uj, world, torch)
     if rank == 0:
         m = o.Mesh(o.CUBE, g.xy, g.cell_verts, g.cell_neigh)
         rp_o, col_o = o.pattern(m)
@@ -313,7 +316,8 @@ def small_grid_parity(hdd, torch, comm, rank, world, local_rank):
                          "rhs_rel": float(np.abs(b - b_o).max() / np.abs(b_o).max()),
                          "solution_rel": float(np.abs(u - u_o).max() / np.abs(u_o).max()),
                          "oracle_polish_iterations": int(it_o), "cg_mg_iterations": info["iterations"],
-                         "true_residual": res}
+                         "true_residual": res, "jacobi_solution_rel": float(np.abs(uj - u_o).max() / np.abs(u_o).max()),
+                         "jacobi_iterations": info_j["iterations"], "jacobi_peer_memory": bool(info_j.get("peer_memory"))}
     del d
     # ---- P1 on 8192 triangles: solve + estimators ------------------------------------------------------------------
     g = hdd.grids.simplex(32, partitions=(8, 8))
@@ -343,7 +347,7 @@ def small_grid_parity(hdd, torch, comm, rank, world, local_rank):
     if rank == 0:
         q, t = out["q1_256"], out["p1_8192"]
         ok = (q["pattern_equal"] and q["entries_rel"] <= 1e-12 and q["rhs_rel"] <= 1e-12 and q["solution_rel"] <= 1e-8
-              and t["entries_rel"] <= 1e-12 and t["solution_rel"] <= 1e-8 and t["indicators_rel"] <= 1e-8
+              and q["jacobi_solution_rel"] <= 1e-8 and t["entries_rel"] <= 1e-12 and t["solution_rel"] <= 1e-8 and t["indicators_rel"] <= 1e-8
               and abs(t["eta_ESV2007"] - 4.85e-02) <= 0.006 * 4.85e-02)
         out["ok"] = bool(ok)
     return out, ok
@@ -505,13 +509,17 @@ def main():
     t_asm, t_cg, wall = [float(v) for v in stats.cpu()]
 
     # ---- what was timed is checked: true residual recomputed from scratch, error against the exact solution ----------
-    check = {"true_residual": d.residual(), "cg_iterations": iters}
+    res, floor = d.residual(with_floor=True)
+    # b scales with h^2 against O(1) matrix entries: recomputing b - A x in fp64 has a rounding level of its own (`floor`,
+    # an upper estimate), below which no solver can push it; the solve itself is judged by the error norms below
+    check = {"true_residual": res, "true_residual_fp64_floor": floor, "true_residual_bound": max(1e-9, 0.25 * floor),
+             "cg_iterations": iters}
     norms = d.error_norms(*hdd.problems.ESV2007_EXACT, order=5)
     # asymptotics of the committed SGrid ladder (test/linearelliptic-swipdg-expectations_esv2007_2dsgrid.cxx:32-36):
     # L2 n^2 = 0.723, 0.742, 0.759, 0.770 -> 0.78; H1 n = 2.216, 2.224, 2.234, 2.240 -> 2.25
     check.update({"L2_error": norms["L2"], "H1_semi_error": norms["H1_semi"], "energy_error": norms["energy"],
                   "H1_semi_expected": 2.25 / n, "L2_expected": 0.78 / (n * n)})
-    check_ok = (check["true_residual"] <= 1e-9 and
+    check_ok = (check["true_residual"] <= check["true_residual_bound"] and
                 (n < 64 or (abs(norms["H1_semi"] - 2.25 / n) <= 0.02 * 2.25 / n and
                             abs(norms["L2"] - 0.78 / (n * n)) <= 0.05 * 0.78 / (n * n))))
 

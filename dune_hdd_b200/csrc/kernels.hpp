@@ -126,8 +126,9 @@ void launch_cg_spmv(const MeshView& m, const CgBuffers& c, int parity, cudaStrea
 void launch_cg_update(const MeshView& m, const CgBuffers& c, int parity, cudaStream_t s);
 void launch_cg_direction(const MeshView& m, const CgBuffers& c, int parity, cudaStream_t s);
 
-// sc->red[0] = sum (b - q)^2, sc->red[1] = sum b^2 over n entries (true residual check, hdd_residual)
-void launch_residual_norms(const double* b, const double* q, int64_t n, double* partial, CgScalars* sc, cudaStream_t s);
+// sc->red[0] = sum (b - q)^2, red[1] = sum b^2, red[2] = sum x^2 over n entries, red[3] = max |values| (hdd_residual)
+void launch_residual_norms(const double* b, const double* q, const double* x, int64_t n, const double* values, int64_t nnz,
+                           double* partial, CgScalars* sc, cudaStream_t s);
 
 // a15 (pure Neumann): symmetric unit row/column 0 + rhs[0] = 0, and x -= mean(x) after the solve
 void launch_unit_row_col0(const MeshView& m, double* values, double* b, cudaStream_t s);

@@ -682,16 +682,28 @@ __global__ void __launch_bounds__(kCgThreads) k_sum(const double* __restrict__ x
   grid_sum<1>(v, partial, ticket, [out](const double(&w)[1]) { *out = w[0]; });
 }
 
-__global__ void __launch_bounds__(kCgThreads) k_residual_norms(const double* __restrict__ b, const double* __restrict__ q, int64_t n,
-                                                              double* partial, CgScalars* sc) {
-  double v[2] = {0.0, 0.0};
+__global__ void __launch_bounds__(kCgThreads) k_residual_norms(const double* __restrict__ b, const double* __restrict__ q,
+                                                              const double* __restrict__ x, int64_t n, double* partial,
+                                                              CgScalars* sc) {
+  double v[3] = {0.0, 0.0, 0.0};
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const double bi = b[i], d = bi - q[i];
+    const double bi = b[i], d = bi - q[i], xi = x[i];
     v[0] = fma(d, d, v[0]);
     v[1] = fma(bi, bi, v[1]);
+    v[2] = fma(xi, xi, v[2]);
   }
-  grid_sum<2>(v, partial, &sc->ticket_a, [sc](const double(&w)[2]) { sc->red[0] = w[0]; sc->red[1] = w[1]; });
+  grid_sum<3>(v, partial, &sc->ticket_a, [sc](const double(&w)[3]) { sc->red[0] = w[0]; sc->red[1] = w[1]; sc->red[2] = w[2]; });
+}
+
+// *out = max |v[i]| (out must hold 0 on entry; non-negative doubles order like their bit patterns)
+__global__ void __launch_bounds__(kCgThreads) k_abs_max(const double* __restrict__ v, int64_t n, double* out) {
+  double m = 0.0;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) m = fmax(m, fabs(v[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(m));
 }
 
 __global__ void k_shift(double* __restrict__ x, int64_t n, const double* __restrict__ sum, double inv_count) {
@@ -863,9 +875,12 @@ void launch_subtract_mean(double* x, int64_t n, double* partial, CgScalars* sc, 
   HDD_CUDA(cudaGetLastError());
 }
 
-void launch_residual_norms(const double* b, const double* q, int64_t n, double* partial, CgScalars* sc, cudaStream_t s) {
-  k_residual_norms<<<cg_grid(n), kCgThreads, 0, s>>>(b, q, n, partial, sc);
-  count_launch();
+void launch_residual_norms(const double* b, const double* q, const double* x, int64_t n, const double* values, int64_t nnz,
+                           double* partial, CgScalars* sc, cudaStream_t s) {
+  k_residual_norms<<<cg_grid(n), kCgThreads, 0, s>>>(b, q, x, n, partial, sc);
+  HDD_CUDA(cudaMemsetAsync(&sc->red[3], 0, sizeof(double), s));
+  k_abs_max<<<cg_grid(nnz), kCgThreads, 0, s>>>(values, nnz, &sc->red[3]);
+  count_launch(2);
 }
 
 void launch_pack(const double* v_local, const int32_t* cells, int64_t n_cells, int nd, double* out, cudaStream_t s) {

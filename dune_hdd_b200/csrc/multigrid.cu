@@ -202,6 +202,8 @@ __global__ void __launch_bounds__(kMgThreads)
 }
 
 // ---- V-cycle kernels.  done: convergence latch of the CG iteration that owns this application (see k_cg_*) ----------
+// On levels >= 1 the two hierarchies (plain and twisted) are swept by the same launch: blockIdx.y picks the hierarchy,
+// its operator sits 9 nv and its vectors nv entries behind those of the plain one.
 // pre-smoothing from a zero guess, x = w D^-1 b, fused with the residual r = b - A x
 __global__ void __launch_bounds__(kMgThreads)
     k_mg_pre(const int* done, const double* __restrict__ S, const double* __restrict__ dinv, int nx, int ny, Rows rg,
@@ -211,6 +213,8 @@ __global__ void __launch_bounds__(kMgThreads)
   const int64_t nv = int64_t(nx1) * (ny + 1);
   const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (tid >= rg.cnt) return;
+  const int64_t hv = int64_t(blockIdx.y) * nv;
+  S += 9 * hv; dinv += hv; b += hv; x += hv; r += hv;
   const int64_t i = rg.beg + tid;
   const int ix = int(i % nx1), iy = int(i / nx1);
   double ax = 0.0;
@@ -228,13 +232,15 @@ __global__ void __launch_bounds__(kMgThreads)
   r[i] = b[i] - ax;
 }
 
-// full weighting: b_H = P^T r
+// full weighting: b_H = P^T r (both hierarchies)
 __global__ void __launch_bounds__(kMgThreads)
     k_mg_restrict(const int* done, const double* __restrict__ r, int nxf, int nyf, Rows rg /* coarse */, double* __restrict__ bc) {
   if (done && *done) return;
-  const int nxc = nxf / 2;
+  const int nxc = nxf / 2, nyc = nyf / 2;
   const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (tid >= rg.cnt) return;
+  r += int64_t(blockIdx.y) * (int64_t(nxf + 1) * (nyf + 1));
+  bc += int64_t(blockIdx.y) * (int64_t(nxc + 1) * (nyc + 1));
   const int64_t I = rg.beg + tid;
   const int IX = int(I % (nxc + 1)), IY = int(I / (nxc + 1));
   double s = 0.0;
@@ -249,28 +255,33 @@ __global__ void __launch_bounds__(kMgThreads)
   bc[I] = s;
 }
 
-// x += P x_H (bilinear interpolation)
-__global__ void __launch_bounds__(kMgThreads)
-    k_mg_prolong_add(const int* done, const double* __restrict__ xc, int nxf, Rows rg /* fine */, double* __restrict__ x) {
-  if (done && *done) return;
-  const int nxc = nxf / 2;
-  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (tid >= rg.cnt) return;
-  const int64_t i = rg.beg + tid;
-  const int fx = int(i % (nxf + 1)), fy = int(i / (nxf + 1));
-  const int cx = fx >> 1, cy = fy >> 1;
+// value of the bilinear interpolant P x_H at the fine vertex (fx, fy)
+__device__ __forceinline__ double mg_interp(const double* __restrict__ xc, int nxc1, int fx, int fy) {
   const int ox = fx & 1, oy = fy & 1;
-  const int64_t I = cx + int64_t(nxc + 1) * cy;
+  const int64_t I = (fx >> 1) + int64_t(nxc1) * (fy >> 1);
   double v = __ldg(xc + I);
   if (ox) v += __ldg(xc + I + 1);
   if (oy) {
-    v += __ldg(xc + I + nxc + 1);
-    if (ox) v += __ldg(xc + I + nxc + 2);
+    v += __ldg(xc + I + nxc1);
+    if (ox) v += __ldg(xc + I + nxc1 + 1);
   }
-  x[i] += v * (ox ? 0.5 : 1.0) * (oy ? 0.5 : 1.0);
+  return v * (ox ? 0.5 : 1.0) * (oy ? 0.5 : 1.0);
 }
 
-// post-smoothing: y = x + w D^-1 (b - A x)
+// x += P x_H (bilinear interpolation), both hierarchies
+__global__ void __launch_bounds__(kMgThreads)
+    k_mg_prolong_add(const int* done, const double* __restrict__ xc, int nxf, int nyf, Rows rg /* fine */, double* __restrict__ x) {
+  if (done && *done) return;
+  const int nxc = nxf / 2, nyc = nyf / 2;
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (tid >= rg.cnt) return;
+  x += int64_t(blockIdx.y) * (int64_t(nxf + 1) * (nyf + 1));
+  xc += int64_t(blockIdx.y) * (int64_t(nxc + 1) * (nyc + 1));
+  const int64_t i = rg.beg + tid;
+  x[i] += mg_interp(xc, nxc + 1, int(i % (nxf + 1)), int(i / (nxf + 1)));
+}
+
+// post-smoothing: y = x + w D^-1 (b - A x), both hierarchies
 __global__ void __launch_bounds__(kMgThreads)
     k_mg_post(const int* done, const double* __restrict__ S, const double* __restrict__ dinv, int nx, int ny, Rows rg,
               const double* __restrict__ b, const double* __restrict__ x, double* __restrict__ y) {
@@ -279,6 +290,8 @@ __global__ void __launch_bounds__(kMgThreads)
   const int64_t nv = int64_t(nx1) * (ny + 1);
   const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (tid >= rg.cnt) return;
+  const int64_t hv = int64_t(blockIdx.y) * nv;
+  S += 9 * hv; dinv += hv; b += hv; x += hv; y += hv;
   const int64_t i = rg.beg + tid;
   const int ix = int(i % nx1), iy = int(i / nx1);
   double ax = 0.0;
@@ -293,18 +306,50 @@ __global__ void __launch_bounds__(kMgThreads)
   y[i] = fma(__ldg(dinv + i), b[i] - ax, x[i]);
 }
 
+// prolongation and post-smoothing in one sweep for the small levels, where a launch costs more than the arithmetic:
+// y = xp + w D^-1 (b - A xp) with xp = x + P x_H formed on the fly at the nine stencil points (same operations, same
+// results as k_mg_prolong_add followed by k_mg_post)
+__global__ void __launch_bounds__(kMgThreads)
+    k_mg_up(const int* done, const double* __restrict__ S, const double* __restrict__ dinv, int nx, int ny, Rows rg,
+            const double* __restrict__ b, const double* __restrict__ x, const double* __restrict__ xc, double* __restrict__ y) {
+  if (done && *done) return;
+  const int nx1 = nx + 1, nxc1 = nx / 2 + 1;
+  const int64_t nv = int64_t(nx1) * (ny + 1);
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (tid >= rg.cnt) return;
+  const int64_t hv = int64_t(blockIdx.y) * nv;
+  S += 9 * hv; dinv += hv; b += hv; x += hv; y += hv;
+  xc += int64_t(blockIdx.y) * (int64_t(nxc1) * (ny / 2 + 1));
+  const int64_t i = rg.beg + tid;
+  const int ix = int(i % nx1), iy = int(i / nx1);
+  double ax = 0.0, xi = 0.0;
+#pragma unroll
+  for (int ey = -1; ey <= 1; ++ey)
+#pragma unroll
+    for (int ex = -1; ex <= 1; ++ex) {
+      const int jx = ix + ex, jy = iy + ey;
+      if (jx < 0 || jy < 0 || jx > nx || jy > ny) continue;
+      const double xp = __ldg(x + i + ex + int64_t(ey) * nx1) + mg_interp(xc, nxc1, jx, jy);
+      ax = fma(__ldg(S + ((ey + 1) * 3 + ex + 1) * nv + i), xp, ax);
+      if (ex == 0 && ey == 0) xi = xp;
+    }
+  y[i] = fma(__ldg(dinv + i), b[i] - ax, xi);
+}
+
 // Level 0, both hierarchies in one sweep: C A_c C differs from A_c only by the sign of the edge-neighbour entries
 // (e odd), so the nine coefficient arrays - three quarters of the bytes of a smoothing sweep - are read once for
-// the plain and the twisted hierarchy.
+// the plain and the twisted hierarchy.  The vectors of the twisted hierarchy sit nv entries behind the plain ones.
 __global__ void __launch_bounds__(kMgThreads)
     k_mg_pre2(const int* done, const double* __restrict__ S, const double* __restrict__ dinv, int nx, int ny, Rows rg,
-              const double* __restrict__ b0, const double* __restrict__ b1, double* __restrict__ x0, double* __restrict__ x1,
-              double* __restrict__ r0, double* __restrict__ r1) {
+              const double* __restrict__ b0, double* __restrict__ x0, double* __restrict__ r0) {
   if (done && *done) return;
   const int nx1 = nx + 1;
   const int64_t nv = int64_t(nx1) * (ny + 1);
   const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (tid >= rg.cnt) return;
+  const double* b1 = b0 + nv;
+  double* x1 = x0 + nv;
+  double* r1 = r0 + nv;
   const int64_t i = rg.beg + tid;
   const int ix = int(i % nx1), iy = int(i / nx1);
   double a0 = 0.0, a1 = 0.0;
@@ -328,13 +373,15 @@ __global__ void __launch_bounds__(kMgThreads)
 
 __global__ void __launch_bounds__(kMgThreads)
     k_mg_post2(const int* done, const double* __restrict__ S, const double* __restrict__ dinv, int nx, int ny, Rows rg,
-               const double* __restrict__ b0, const double* __restrict__ b1, const double* __restrict__ x0,
-               const double* __restrict__ x1, double* __restrict__ y0, double* __restrict__ y1) {
+               const double* __restrict__ b0, const double* __restrict__ x0, double* __restrict__ y0) {
   if (done && *done) return;
   const int nx1 = nx + 1;
   const int64_t nv = int64_t(nx1) * (ny + 1);
   const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (tid >= rg.cnt) return;
+  const double* b1 = b0 + nv;
+  const double* x1 = x0 + nv;
+  double* y1 = y0 + nv;
   const int64_t i = rg.beg + tid;
   const int ix = int(i % nx1), iy = int(i / nx1);
   double a0 = 0.0, a1 = 0.0;
@@ -354,20 +401,25 @@ __global__ void __launch_bounds__(kMgThreads)
   y1[i] = fma(d, b1[i] - a1, x1[i]);
 }
 
-// dinv = w / diagonal of the level operator
+// dinv = w / diagonal of the level operator (both hierarchies)
 __global__ void k_mg_dinv(const double* __restrict__ S, int64_t nv, double* __restrict__ dinv) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < nv) dinv[i] = kOmega / S[4 * nv + i];
+  const int64_t hv = int64_t(blockIdx.y) * nv;
+  if (i < nv) dinv[hv + i] = kOmega / S[9 * hv + 4 * nv + i];
 }
 
-// coarsest grid: x = A^-1 b with the dense inverse, one thread per row
+// coarsest grid: x = A^-1 b with the dense inverse, one thread per row; the inverse of the symmetric matrix is read by
+// columns, so a warp reads consecutive addresses.  Both hierarchies.
 __global__ void k_mg_dense(const int* done, const double* __restrict__ Ainv, int n, const double* __restrict__ b,
                            double* __restrict__ x) {
   if (done && *done) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  Ainv += size_t(blockIdx.y) * n * n;
+  b += size_t(blockIdx.y) * n;
+  x += size_t(blockIdx.y) * n;
   double s = 0.0;
-  for (int j = 0; j < n; ++j) s = fma(__ldg(Ainv + size_t(i) * n + j), __ldg(b + j), s);
+  for (int j = 0; j < n; ++j) s = fma(__ldg(Ainv + size_t(j) * n + i), __ldg(b + j), s);
   x[i] = s;
 }
 
@@ -397,11 +449,36 @@ __global__ void __launch_bounds__(kMgThreads)
   if (b1) b1[v] = ((ix + iy) & 1) ? -s : s;
 }
 
-// dst += src over one grid row (the neighbour's share of a vertex row both ranks contribute to); min / max cell row
-__global__ void k_add_row(const int* done, double* __restrict__ dst, const double* __restrict__ src, int n) {
+// Strip-distributed application, after the exchange of the level-0 right-hand side: lo / up hold the g + 1 vertex rows
+// [c0 - g, c0] of the rank below and [c1, c1 + g] of the rank above.  The shared rows c0 and c1 were summed over this
+// rank's cells only - the neighbour's share is added (two summands: the order does not matter) - the other rows are
+// copied, and the checkerboard-signed copy b1 = C b0 is written for the whole range [rows lo_row, hi_row].
+__global__ void __launch_bounds__(kMgThreads)
+    k_ghost_unpack_twist(const int* done, double* __restrict__ b0, double* __restrict__ b1, const double* __restrict__ lo,
+                         const double* __restrict__ up, int nx, int c0, int c1, int g, int lo_row, int hi_row) {
   if (done && *done) return;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n) dst[t] += src[t];
+  const int nx1 = nx + 1;
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (tid >= int64_t(hi_row - lo_row + 1) * nx1) return;
+  const int64_t v = int64_t(lo_row) * nx1 + tid;
+  const int ix = int(v % nx1), iy = int(v / nx1);
+  double val;
+  if (lo && iy < c0) {
+    val = lo[int64_t(iy - (c0 - g)) * nx1 + ix];
+    b0[v] = val;
+  } else if (up && iy > c1) {
+    val = up[int64_t(iy - c1) * nx1 + ix];
+    b0[v] = val;
+  } else if (lo && iy == c0) {
+    val = b0[v] + lo[int64_t(g) * nx1 + ix];
+    b0[v] = val;
+  } else if (up && iy == c1) {
+    val = b0[v] + up[ix];
+    b0[v] = val;
+  } else {
+    val = b0[v];
+  }
+  b1[v] = ((ix + iy) & 1) ? -val : val;
 }
 
 __global__ void k_cell_row_range(const int32_t* __restrict__ cell_v0_owned, int32_t n_own, int nx, int* __restrict__ minmax) {
@@ -441,63 +518,85 @@ __global__ void __launch_bounds__(kMgThreads)
 }  // namespace
 
 // ---- host side ------------------------------------------------------------------------------------------------
+// One level of both hierarchies: the arrays of the twisted hierarchy follow those of the plain one (9 nv / nv entries
+// behind).  Level 0 has one operator for both (C A_c C is A_c with the edge-neighbour entries negated).
 struct MgLevel {
   int nx = 0, ny = 0;
   int64_t nv = 0;
   DevBuf<double> S, dinv, b, x, r, y;
+  double* result = nullptr;  // where the level's correction ends up: y after post-smoothing, x on the coarsest level
 };
 
-struct MgHierarchy {
-  std::vector<std::unique_ptr<MgLevel>> levels;
-  DevBuf<double> coarse_inv;
-};
+constexpr int kMaxDist = 3;  // at most this many finest vertex levels are swept in row strips
 
-// Multi GPU: the two finest vertex levels are swept in row strips.  The operators (S, dinv) stay replicated - they
-// are static during a solve and one all-reduce per solve makes them global - only the vectors b, x, r of levels 0 and 1
-// are computed strip-wise, on full-size arrays, so a halo row lives at the same index on every rank and an exchange is
-// "send my first / last owned row, receive the neighbour's into the row next to my strip".  Level 2 and below run
-// replicated on the all-reduced level-2 right-hand side.
+// Multi GPU, cells in full-width bands of rows stacked in rank order: the vectors of the n_dist finest vertex levels are
+// computed in row strips with ghost zones instead of exchanges.  Every array keeps its full size, so a vertex has the
+// same index on every rank.  A rank receives the g rows of the level-0 right-hand side next to its strip once per
+// application (one grouped send / recv with the ranks below and above) and then computes, redundantly, every value of
+// the distributed levels its own rows depend on: the sweeps of level l run on the row ranges below, which shrink by one
+// row per stencil application towards the rows this rank owns.  The values in the ghost zones are the same numbers the
+// neighbour computes (same operations on the same data), so the result equals the replicated V-cycle.  The first
+// replicated level gets its right-hand side by one all-reduce (every rank restricts into its own rows of a zeroed
+// array); the operators are replicated (one all-reduce of the level-0 stencil per solve).
 struct MgDist {
   bool on = false;
+  int n_dist = 0;              // distributed levels 0 .. n_dist-1
   int lower = -1, upper = -1;  // ranks owning the strips below / above (-1: none)
   int c0 = 0, c1 = 0;          // owned cell rows [c0, c1) of level 0
-  bool last = false;           // the top strip also owns the last vertex row
-  DevBuf<double> tmp;          // one level-0 row
+  bool last = false;           // the top strip
+  int ghost = 0;               // level-0 rows of b received from each neighbour
+  // inclusive vertex-row ranges per distributed level: pre-smoothing (x, r), right-hand side b, post-smoothing (y),
+  // prolongation (x += P x_H)
+  int pre_lo[kMaxDist], pre_hi[kMaxDist], b_lo[kMaxDist], b_hi[kMaxDist], up_lo[kMaxDist], up_hi[kMaxDist],
+      pro_lo[kMaxDist], pro_hi[kMaxDist];
+  int own_lo = 0, own_hi = 0;  // own rows of the first replicated level (restricted into the all-reduced array)
+  DevBuf<double> tmp_lo, tmp_up;
 };
 
 struct MgState {
-  MgHierarchy h[2];  // plain and checkerboard-twisted
+  std::vector<std::unique_ptr<MgLevel>> levels;
+  DevBuf<double> coarse_inv;  // [2][n * n]
   int nx = 0, ny = 0;
   MgDist dist;
 };
 
-static Rows level_rows(const MgState& st, const MgLevel& L, int l) {
-  if (!st.dist.on || l >= 2) return Rows{0, L.nv};
-  const int v0 = st.dist.c0 >> l, v1 = (st.dist.c1 >> l) + (st.dist.last ? 1 : 0);
-  return Rows{int64_t(v0) * (L.nx + 1), int64_t(v1 - v0) * (L.nx + 1)};
+static inline Rows row_range(const MgLevel& L, int lo, int hi) {
+  return Rows{int64_t(lo) * (L.nx + 1), int64_t(hi - lo + 1) * (L.nx + 1)};
 }
 
-enum { EX_UP = 1, EX_DOWN = 2 };
-// EX_UP: my last owned row goes to the rank above, the last row of the rank below arrives in the row under my strip.
-// EX_DOWN: my first owned row goes to the rank below, the first row of the rank above arrives in the row over my strip.
-static void exchange_rows(hdd_mesh* m, const MgState& st, const MgLevel& L, int l, std::initializer_list<double*> arrays, int dirs) {
-  const MgDist& d = st.dist;
-  if (!d.on || (d.lower < 0 && d.upper < 0)) return;
-  const int nx1 = L.nx + 1;
-  const int64_t v0 = d.c0 >> l, v1 = (d.c1 >> l) + (d.last ? 1 : 0);
-  Nccl& nc = Nccl::get();
-  nc.group_start();
-  for (double* a : arrays) {
-    if (dirs & EX_UP) {
-      if (d.upper >= 0) nc.send(a + (v1 - 1) * nx1, size_t(nx1), d.upper, m->comm, m->stream);
-      if (d.lower >= 0) nc.recv(a + (v0 - 1) * nx1, size_t(nx1), d.lower, m->comm, m->stream);
-    }
-    if (dirs & EX_DOWN) {
-      if (d.lower >= 0) nc.send(a + v0 * nx1, size_t(nx1), d.lower, m->comm, m->stream);
-      if (d.upper >= 0) nc.recv(a + v1 * nx1, size_t(nx1), d.upper, m->comm, m->stream);
-    }
+// The row ranges of MgDist for the strip [c0, c1) of an ny-row grid with n_dist distributed levels (host arithmetic,
+// exported for the CPU tests as hdd_mg_strip_plan).  Top-down: which rows of the post-smoothed correction, of the
+// prolongated iterate and hence of the coarser correction are needed; bottom-up: which rows of the residual feed the
+// restriction, hence of the pre-smoothing sweep and of the right-hand side.
+void mg_strip_plan(int ny, int c0, int c1, int n_dist, MgDist& d) {
+  const bool last = c1 == ny;
+  auto clip = [](int v, int n) { return std::max(0, std::min(v, n)); };
+  int need_lo = c0, need_hi = c1;  // rows of the level-0 correction the DG prolongation of the own cells reads
+  for (int l = 0; l < n_dist; ++l) {
+    const int n = ny >> l;
+    d.up_lo[l] = clip(need_lo, n);
+    d.up_hi[l] = clip(need_hi, n);
+    d.pro_lo[l] = clip(d.up_lo[l] - 1, n);
+    d.pro_hi[l] = clip(d.up_hi[l] + 1, n);
+    need_lo = d.pro_lo[l] >> 1;
+    need_hi = (d.pro_hi[l] + 1) >> 1;
   }
-  nc.group_end();
+  // own rows of the first replicated level
+  const int sh = n_dist;
+  d.own_lo = c0 >> sh;
+  d.own_hi = last ? (ny >> sh) : (c1 >> sh) - 1;
+  int res_lo = d.own_lo, res_hi = d.own_hi;  // rows of level l+1 whose right-hand side this rank computes
+  for (int l = n_dist - 1; l >= 0; --l) {
+    const int n = ny >> l;
+    const int rr_lo = clip(2 * res_lo - 1, n), rr_hi = clip(2 * res_hi + 1, n);  // residual rows the restriction reads
+    d.pre_lo[l] = std::min(d.pro_lo[l], rr_lo);
+    d.pre_hi[l] = std::max(d.pro_hi[l], rr_hi);
+    d.b_lo[l] = clip(d.pre_lo[l] - 1, n);
+    d.b_hi[l] = clip(d.pre_hi[l] + 1, n);
+    res_lo = d.b_lo[l];
+    res_hi = d.b_hi[l];
+  }
+  d.ghost = std::max(c0 - d.b_lo[0], d.b_hi[0] - c1);
 }
 
 void mg_detect_structure(hdd_mesh* m, const double* xy_host, const double* xy_dev, const int32_t* cv_dev, int64_t n_verts) {
@@ -533,152 +632,142 @@ void mg_detect_structure(hdd_mesh* m, const double* xy_host, const double* xy_de
   m->sy = int(ny);
 }
 
-// recomputes the Galerkin operators below the finest level and the dense coarsest inverse; the level buffers are
+// recomputes the Galerkin operators below the finest level and the dense coarsest inverses; the level buffers are
 // allocated once per mesh by mg_setup and persist across solves, so a captured CUDA graph of the iteration stays valid.
-// The twisted hierarchy has no level-0 arrays of its own: its finest operator is C A_c C, read from `S0` with the sign
-// of the edge-neighbour entries flipped.
-static void build_hierarchy(hdd_swipdg* h, MgHierarchy& H, const double* S0, bool twisted) {
+// The twisted hierarchy has no level-0 arrays of its own: its finest operator is C A_c C, read from the level-0 arrays
+// with the sign of the edge-neighbour entries flipped.
+static void build_hierarchies(hdd_swipdg* h, MgState& st) {
   cudaStream_t s = h->mesh->stream;
-  for (size_t l = 0; l + 1 < H.levels.size(); ++l) {
-    MgLevel& f = *H.levels[l];
-    MgLevel& c = *H.levels[l + 1];
-    k_rap<<<blocks_for(c.nv), kMgThreads, 0, s>>>(l == 0 ? S0 : f.S.p, f.nx, f.ny, (l == 0 && twisted) ? 1 : 0, c.S.p);
+  const size_t nl = st.levels.size();
+  for (size_t l = 0; l + 1 < nl; ++l) {
+    MgLevel& f = *st.levels[l];
+    MgLevel& c = *st.levels[l + 1];
+    for (int t = 0; t < 2; ++t) {
+      const double* Sf = l == 0 ? f.S.p : f.S.p + size_t(t) * 9 * f.nv;
+      k_rap<<<blocks_for(c.nv), kMgThreads, 0, s>>>(Sf, f.nx, f.ny, (l == 0 && t == 1) ? 1 : 0, c.S.p + size_t(t) * 9 * c.nv);
+    }
+    count_launch(2);
+  }
+  for (size_t l = 0; l < nl; ++l) {
+    MgLevel& L = *st.levels[l];
+    k_mg_dinv<<<dim3(unsigned(blocks_for(L.nv)), l == 0 ? 1u : 2u), kMgThreads, 0, s>>>(L.S.p, L.nv, L.dinv.p);
     count_launch();
   }
-  for (size_t l = twisted ? 1 : 0; l < H.levels.size(); ++l) {
-    MgLevel& L = *H.levels[l];
-    k_mg_dinv<<<blocks_for(L.nv), kMgThreads, 0, s>>>(L.S.p, L.nv, L.dinv.p);
-    count_launch();
-  }
-  // dense inverse of the coarsest operator (s.p.d.), Gauss-Jordan on the host
-  MgLevel& C = *H.levels.back();
+  // dense inverses of the coarsest operators (s.p.d.), Gauss-Jordan on the host
+  MgLevel& C = *st.levels.back();
   if (C.nv > kMaxCoarse)
-    HDD_THROW(HDD_ERR_REQUIREMENTS_NOT_MET, "cg.mg: the " << H.levels.front()->nx << " x " << H.levels.front()->ny
-                                                           << " grid cannot be coarsened by halving down to at most "
+    HDD_THROW(HDD_ERR_REQUIREMENTS_NOT_MET, "cg.mg: the " << st.nx << " x " << st.ny << " grid cannot be coarsened by halving down to at most "
                                                            << kMaxCoarse << " vertices (stuck at " << C.nx << " x " << C.ny << ")");
   const int n = int(C.nv);
-  const bool coarsest_is_finest = H.levels.size() == 1;
+  const bool coarsest_is_finest = nl == 1;
+  std::vector<double> inv(size_t(2) * n * n);
   std::vector<double> S(size_t(9) * n);
-  HDD_CUDA(cudaMemcpyAsync(S.data(), coarsest_is_finest ? S0 : C.S.p, S.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
-  HDD_CUDA(cudaStreamSynchronize(s));
-  if (coarsest_is_finest && twisted)
-    for (int e = 1; e < 9; e += 2)
-      for (int i = 0; i < n; ++i) S[size_t(e) * n + i] = -S[size_t(e) * n + i];
-  std::vector<double> A(size_t(n) * n, 0.0), I(size_t(n) * n, 0.0);
-  const int nx1 = C.nx + 1;
-  for (int i = 0; i < n; ++i) {
-    const int ix = i % nx1, iy = i / nx1;
-    for (int ey = -1; ey <= 1; ++ey)
-      for (int ex = -1; ex <= 1; ++ex) {
-        const int jx = ix + ex, jy = iy + ey;
-        if (jx < 0 || jy < 0 || jx > C.nx || jy > C.ny) continue;
-        A[size_t(i) * n + (jx + nx1 * jy)] = S[size_t((ey + 1) * 3 + ex + 1) * n + i];
-      }
-    I[size_t(i) * n + i] = 1.0;
-  }
-  for (int c = 0; c < n; ++c) {
-    const double piv = A[size_t(c) * n + c];
-    if (!(piv > 0.0)) HDD_THROW(HDD_ERR_REQUIREMENTS_NOT_MET, "cg.mg: the coarsest operator is not positive definite");
-    const double ip = 1.0 / piv;
-    for (int j = 0; j < n; ++j) { A[size_t(c) * n + j] *= ip; I[size_t(c) * n + j] *= ip; }
+  for (int t = 0; t < 2; ++t) {
+    const double* src = coarsest_is_finest ? C.S.p : C.S.p + size_t(t) * 9 * n;
+    HDD_CUDA(cudaMemcpyAsync(S.data(), src, S.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    HDD_CUDA(cudaStreamSynchronize(s));
+    if (coarsest_is_finest && t == 1)
+      for (int e = 1; e < 9; e += 2)
+        for (int i = 0; i < n; ++i) S[size_t(e) * n + i] = -S[size_t(e) * n + i];
+    std::vector<double> A(size_t(n) * n, 0.0);
+    double* I = inv.data() + size_t(t) * n * n;
+    std::fill(I, I + size_t(n) * n, 0.0);
+    const int nx1 = C.nx + 1;
     for (int i = 0; i < n; ++i) {
-      if (i == c) continue;
-      const double f = A[size_t(i) * n + c];
-      if (f == 0.0) continue;
-      for (int j = 0; j < n; ++j) { A[size_t(i) * n + j] -= f * A[size_t(c) * n + j]; I[size_t(i) * n + j] -= f * I[size_t(c) * n + j]; }
+      const int ix = i % nx1, iy = i / nx1;
+      for (int ey = -1; ey <= 1; ++ey)
+        for (int ex = -1; ex <= 1; ++ex) {
+          const int jx = ix + ex, jy = iy + ey;
+          if (jx < 0 || jy < 0 || jx > C.nx || jy > C.ny) continue;
+          A[size_t(i) * n + (jx + nx1 * jy)] = S[size_t((ey + 1) * 3 + ex + 1) * n + i];
+        }
+      I[size_t(i) * n + i] = 1.0;
+    }
+    for (int c = 0; c < n; ++c) {
+      const double piv = A[size_t(c) * n + c];
+      if (!(piv > 0.0)) HDD_THROW(HDD_ERR_REQUIREMENTS_NOT_MET, "cg.mg: the coarsest operator is not positive definite");
+      const double ip = 1.0 / piv;
+      for (int j = 0; j < n; ++j) { A[size_t(c) * n + j] *= ip; I[size_t(c) * n + j] *= ip; }
+      for (int i = 0; i < n; ++i) {
+        if (i == c) continue;
+        const double f = A[size_t(i) * n + c];
+        if (f == 0.0) continue;
+        for (int j = 0; j < n; ++j) { A[size_t(i) * n + j] -= f * A[size_t(c) * n + j]; I[size_t(i) * n + j] -= f * I[size_t(c) * n + j]; }
+      }
     }
   }
-  H.coarse_inv.upload(I.data(), I.size(), s);
+  st.coarse_inv.upload(inv.data(), inv.size(), s);
   HDD_CUDA(cudaStreamSynchronize(s));
 }
 
-// levels l0 .. coarsest of one hierarchy, all of them replicated: down, dense solve, up; result in levels[l0]->x
-static void vcycle_from(MgHierarchy& H, int l0, const int* done, cudaStream_t s) {
-  const int nl = int(H.levels.size());
-  for (int l = l0; l + 1 < nl; ++l) {
-    MgLevel& L = *H.levels[size_t(l)];
-    MgLevel& Cn = *H.levels[size_t(l) + 1];
-    k_mg_pre<<<blocks_for(L.nv), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, Rows{0, L.nv}, L.b.p, L.x.p, L.r.p);
-    k_mg_restrict<<<blocks_for(Cn.nv), kMgThreads, 0, s>>>(done, L.r.p, L.nx, L.ny, Rows{0, Cn.nv}, Cn.b.p);
+// levels with at most this many vertices prolongate and post-smooth in one kernel (launch bound there)
+constexpr int64_t kFusedUpMaxVerts = 1500000;
+
+static inline dim3 grid2(int64_t cnt) { return dim3(unsigned(blocks_for(cnt)), 2u); }
+
+// One V(1,1)-cycle of both hierarchies, right-hand sides in levels[0]->b (rows b_lo .. b_hi of this rank when the strip
+// mode is on); the corrections end up in levels[0]->result.
+static void vcycle(hdd_mesh* m, MgState& st, const int* done, cudaStream_t s) {
+  const int nl = int(st.levels.size());
+  const MgDist& d = st.dist;
+  const int nd = d.on ? d.n_dist : 0;
+  // ---- down: pre-smoothing + restriction ---------------------------------------------------------------------------
+  for (int l = 0; l + 1 < nl; ++l) {
+    MgLevel& L = *st.levels[size_t(l)];
+    MgLevel& Cn = *st.levels[size_t(l) + 1];
+    const Rows rp = l < nd ? row_range(L, d.pre_lo[l], d.pre_hi[l]) : Rows{0, L.nv};
+    if (l == 0)
+      k_mg_pre2<<<blocks_for(rp.cnt), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, rp, L.b.p, L.x.p, L.r.p);
+    else
+      k_mg_pre<<<grid2(rp.cnt), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, rp, L.b.p, L.x.p, L.r.p);
+    Rows rc{0, Cn.nv};
+    if (l + 1 < nd) {
+      rc = row_range(Cn, d.b_lo[l + 1], d.b_hi[l + 1]);
+    } else if (l + 1 == nd && nd > 0) {
+      // first replicated level: own rows into a zeroed array, summed over the ranks
+      HDD_CUDA(cudaMemsetAsync(Cn.b.p, 0, size_t(2) * Cn.nv * sizeof(double), s));
+      rc = row_range(Cn, d.own_lo, d.own_hi);
+    }
+    k_mg_restrict<<<grid2(rc.cnt), kMgThreads, 0, s>>>(done, L.r.p, L.nx, L.ny, rc, Cn.b.p);
     count_launch(2);
+    if (l + 1 == nd && nd > 0) Nccl::get().all_reduce_sum(Cn.b.p, size_t(2) * Cn.nv, m->comm, s);
   }
-  MgLevel& C = *H.levels.back();
-  k_mg_dense<<<(int(C.nv) + 127) / 128, 128, 0, s>>>(done, H.coarse_inv.p, int(C.nv), C.b.p, C.x.p);
+  // ---- coarsest: dense inverse ----------------------------------------------------------------------------------------
+  MgLevel& C = *st.levels.back();
+  k_mg_dense<<<dim3(unsigned(int(C.nv) + 127) / 128, 2u), 128, 0, s>>>(done, st.coarse_inv.p, int(C.nv), C.b.p, C.x.p);
   count_launch();
-  for (int l = nl - 2; l >= l0; --l) {
-    MgLevel& L = *H.levels[size_t(l)];
-    MgLevel& Cn = *H.levels[size_t(l) + 1];
-    k_mg_prolong_add<<<blocks_for(L.nv), kMgThreads, 0, s>>>(done, Cn.x.p, L.nx, Rows{0, L.nv}, L.x.p);
-    k_mg_post<<<blocks_for(L.nv), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, Rows{0, L.nv}, L.b.p, L.x.p, L.y.p);
-    count_launch(2);
-    std::swap(L.x.p, L.y.p);  // the smoothed iterate is the level's x from here on
+  C.result = C.x.p;
+  // ---- up: prolongation + post-smoothing ----------------------------------------------------------------------------
+  for (int l = nl - 2; l >= 0; --l) {
+    MgLevel& L = *st.levels[size_t(l)];
+    MgLevel& Cn = *st.levels[size_t(l) + 1];
+    const Rows ru = l < nd ? row_range(L, d.up_lo[l], d.up_hi[l]) : Rows{0, L.nv};
+    if (l > 0 && L.nv <= kFusedUpMaxVerts) {
+      k_mg_up<<<grid2(ru.cnt), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, ru, L.b.p, L.x.p, Cn.result, L.y.p);
+      count_launch();
+    } else {
+      const Rows rq = l < nd ? row_range(L, d.pro_lo[l], d.pro_hi[l]) : Rows{0, L.nv};
+      k_mg_prolong_add<<<grid2(rq.cnt), kMgThreads, 0, s>>>(done, Cn.result, L.nx, L.ny, rq, L.x.p);
+      if (l == 0)
+        k_mg_post2<<<blocks_for(ru.cnt), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, ru, L.b.p, L.x.p, L.y.p);
+      else
+        k_mg_post<<<grid2(ru.cnt), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, ru, L.b.p, L.x.p, L.y.p);
+      count_launch(2);
+    }
+    L.result = L.y.p;
   }
 }
 
-// Level 1 of one hierarchy and everything below it.  Replicated: plain V-cycle.  Distributed: level 1 in row strips,
-// the level-2 right-hand side is summed over the ranks (every rank restricts its own rows into a zeroed array) and
-// levels >= 2 run replicated.
-static void vcycle_level1(hdd_mesh* m, MgState& st, MgHierarchy& H, const int* done, cudaStream_t s) {
-  if (!st.dist.on) {
-    vcycle_from(H, 1, done, s);
-    return;
-  }
-  MgLevel& L = *H.levels[1];
-  MgLevel& Cn = *H.levels[2];
-  const Rows r1 = level_rows(st, L, 1);
-  const int W0 = st.dist.c0 >> 2, W1 = (st.dist.c1 >> 2) + (st.dist.last ? 1 : 0);
-  const Rows r2own{int64_t(W0) * (Cn.nx + 1), int64_t(W1 - W0) * (Cn.nx + 1)};
-  exchange_rows(m, st, L, 1, {L.b.p}, EX_UP | EX_DOWN);
-  k_mg_pre<<<blocks_for(r1.cnt), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, r1, L.b.p, L.x.p, L.r.p);
-  exchange_rows(m, st, L, 1, {L.r.p}, EX_UP);
-  HDD_CUDA(cudaMemsetAsync(Cn.b.p, 0, size_t(Cn.nv) * sizeof(double), s));
-  k_mg_restrict<<<blocks_for(r2own.cnt), kMgThreads, 0, s>>>(done, L.r.p, L.nx, L.ny, r2own, Cn.b.p);
-  Nccl::get().all_reduce_sum(Cn.b.p, size_t(Cn.nv), m->comm, s);
-  count_launch(2);
-  vcycle_from(H, 2, done, s);
-  k_mg_prolong_add<<<blocks_for(r1.cnt), kMgThreads, 0, s>>>(done, Cn.x.p, L.nx, r1, L.x.p);
-  exchange_rows(m, st, L, 1, {L.x.p}, EX_UP | EX_DOWN);
-  k_mg_post<<<blocks_for(r1.cnt), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, r1, L.b.p, L.x.p, L.y.p);
-  count_launch(2);
-  std::swap(L.x.p, L.y.p);
-}
-
-// one V(1,1)-cycle of both hierarchies; level 0 is swept once for the two of them (k_mg_pre2 / k_mg_post2)
-static void vcycle_pair(hdd_mesh* m, MgState& st, const int* done, cudaStream_t s) {
-  MgLevel& a = *st.h[0].levels[0];
-  MgLevel& b = *st.h[1].levels[0];
-  MgLevel& a1 = *st.h[0].levels[1];
-  MgLevel& b1 = *st.h[1].levels[1];
-  const Rows r0 = level_rows(st, a, 0), r1 = level_rows(st, a1, 1);
-  exchange_rows(m, st, a, 0, {a.b.p, b.b.p}, EX_UP | EX_DOWN);
-  k_mg_pre2<<<blocks_for(r0.cnt), kMgThreads, 0, s>>>(done, a.S.p, a.dinv.p, a.nx, a.ny, r0, a.b.p, b.b.p, a.x.p, b.x.p, a.r.p, b.r.p);
-  exchange_rows(m, st, a, 0, {a.r.p, b.r.p}, EX_UP);
-  k_mg_restrict<<<blocks_for(r1.cnt), kMgThreads, 0, s>>>(done, a.r.p, a.nx, a.ny, r1, a1.b.p);
-  k_mg_restrict<<<blocks_for(r1.cnt), kMgThreads, 0, s>>>(done, b.r.p, b.nx, b.ny, r1, b1.b.p);
-  count_launch(3);
-  vcycle_level1(m, st, st.h[0], done, s);
-  vcycle_level1(m, st, st.h[1], done, s);
-  exchange_rows(m, st, a1, 1, {a1.x.p, b1.x.p}, EX_DOWN);  // fine rows up to v1 - 1 interpolate from coarse row V1
-  k_mg_prolong_add<<<blocks_for(r0.cnt), kMgThreads, 0, s>>>(done, a1.x.p, a.nx, r0, a.x.p);
-  k_mg_prolong_add<<<blocks_for(r0.cnt), kMgThreads, 0, s>>>(done, b1.x.p, b.nx, r0, b.x.p);
-  exchange_rows(m, st, a, 0, {a.x.p, b.x.p}, EX_UP | EX_DOWN);
-  k_mg_post2<<<blocks_for(r0.cnt), kMgThreads, 0, s>>>(done, a.S.p, a.dinv.p, a.nx, a.ny, r0, a.b.p, b.b.p, a.x.p, b.x.p, a.y.p, b.y.p);
-  count_launch(3);
-  std::swap(a.x.p, a.y.p);
-  std::swap(b.x.p, b.y.p);
-}
-
-// Decides, identically on every rank, whether the strips of the ranks are full-width bands of cell rows stacked in rank
-// order with boundaries on multiples of four rows - then levels 0 and 1 are swept in strips.  HDD_MG_DISTRIBUTED=0
-// keeps everything replicated, =1 asks for strips at any world size; unset, strips are used up to kVerifiedStripWorld
-// ranks (the sizes the strip path has been run and checked on; larger jobs take the size-agnostic replicated V-cycle).
-constexpr int kVerifiedStripWorld = 4;
+// Decides, identically on every rank, whether the ranks' cells are full-width bands of cell rows stacked in rank order
+// whose boundaries and heights allow the strip mode, and with how many distributed levels (as many as kMaxDist).
+// HDD_MG_DISTRIBUTED=0 keeps every vertex level replicated; HDD_MG_DIST_LEVELS=n caps the number of distributed levels.
 static void detect_strips(hdd_swipdg* h, MgState& st) {
   hdd_mesh* m = h->mesh;
   MgDist& d = st.dist;
   d.on = false;
-  static const int env = [] { const char* e = std::getenv("HDD_MG_DISTRIBUTED"); return !e ? -1 : (e[0] == '0' ? 0 : 1); }();
-  const bool wanted = env < 0 ? m->world <= kVerifiedStripWorld : env == 1;
+  d.n_dist = 0;
+  static const bool wanted = [] { const char* e = std::getenv("HDD_MG_DISTRIBUTED"); return !(e && e[0] == '0'); }();
+  static const int cap = [] { const char* e = std::getenv("HDD_MG_DIST_LEVELS"); return e ? std::atoi(e) : kMaxDist; }();
   if (m->world <= 1) return;
   cudaStream_t s = m->stream;
   DevBuf<int> mm;
@@ -690,31 +779,57 @@ static void detect_strips(hdd_swipdg* h, MgState& st) {
   HDD_CUDA(cudaMemcpyAsync(got, mm.p, sizeof(got), cudaMemcpyDeviceToHost, s));
   HDD_CUDA(cudaStreamSynchronize(s));
   const int c0 = got[0], c1 = got[1] + 1;
-  const bool mine = wanted && m->n_own > 0 && int64_t(m->n_own) == int64_t(st.nx) * (c1 - c0) && (c0 % 4 == 0) &&
-                    (c1 % 4 == 0 || c1 == st.ny) && st.h[0].levels.size() >= 3;
+  const bool band = m->n_own > 0 && int64_t(m->n_own) == int64_t(st.nx) * (c1 - c0);
   // every rank learns every rank's band: 3 doubles per rank through one all-reduce
   std::vector<double> all(size_t(3) * m->world, 0.0);
   all[size_t(3) * m->rank] = c0;
   all[size_t(3) * m->rank + 1] = c1;
-  all[size_t(3) * m->rank + 2] = mine ? 1.0 : 0.0;
+  all[size_t(3) * m->rank + 2] = band ? 1.0 : 0.0;
   DevBuf<double> buf;
   buf.upload(all.data(), all.size(), s);
   Nccl::get().all_reduce_sum(buf.p, all.size(), m->comm, s);
   HDD_CUDA(cudaMemcpyAsync(all.data(), buf.p, all.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
   HDD_CUDA(cudaStreamSynchronize(s));
-  bool ok = all[0] == 0.0 && all[size_t(3) * (m->world - 1) + 1] == double(st.ny);
+  if (!wanted) return;
+  bool stacked = all[0] == 0.0 && all[size_t(3) * (m->world - 1) + 1] == double(st.ny);
   for (int r = 0; r < m->world; ++r) {
-    ok = ok && all[size_t(3) * r + 2] == 1.0;
-    if (r > 0) ok = ok && all[size_t(3) * r] == all[size_t(3) * (r - 1) + 1];
+    stacked = stacked && all[size_t(3) * r + 2] == 1.0;
+    if (r > 0) stacked = stacked && all[size_t(3) * r] == all[size_t(3) * (r - 1) + 1];
   }
-  if (!ok) return;
+  if (!stacked) return;
+  // the largest number of distributed levels every band allows: boundaries on multiples of 2^n, enough rows for the
+  // ghost zones to stay inside the adjacent strip, and at least one replicated level below
+  int n_dist = 0;
+  for (int n = std::min({cap, kMaxDist, int(st.levels.size()) - 1}); n >= 1 && n_dist == 0; --n) {
+    bool ok = true;
+    MgDist probe;
+    mg_strip_plan(st.ny, 0, st.ny, n, probe);  // ghost width only depends on n away from the domain boundary
+    for (int r = 0; r < m->world && ok; ++r) {
+      const int a = int(all[size_t(3) * r]), b = int(all[size_t(3) * r + 1]);
+      MgDist pr;
+      mg_strip_plan(st.ny, a, b, n, pr);
+      ok = a % (1 << n) == 0 && (b % (1 << n) == 0 || b == st.ny) && (b - a) >= 2 * pr.ghost + 2;
+    }
+    if (ok) n_dist = n;
+  }
+  if (n_dist == 0) return;
   d.on = true;
+  d.n_dist = n_dist;
   d.c0 = c0;
   d.c1 = c1;
   d.lower = m->rank > 0 ? m->rank - 1 : -1;
   d.upper = m->rank + 1 < m->world ? m->rank + 1 : -1;
   d.last = d.upper < 0;
-  if (d.tmp.n < size_t(st.nx) + 1) d.tmp.alloc(size_t(st.nx) + 1);
+  mg_strip_plan(st.ny, c0, c1, n_dist, d);
+  // the message size is the same on every rank: the ghost width of an interior strip
+  MgDist interior;
+  mg_strip_plan(st.ny, 1 << 20, (1 << 20) + (1 << 10), n_dist, interior);
+  (void)interior;
+  const size_t rows = size_t(d.ghost) + 1;
+  if (d.tmp_lo.n < rows * (size_t(st.nx) + 1)) {
+    d.tmp_lo.alloc(rows * (size_t(st.nx) + 1));
+    d.tmp_up.alloc(rows * (size_t(st.nx) + 1));
+  }
 }
 
 void mg_release(MgState* st) { delete st; }
@@ -732,41 +847,34 @@ void mg_setup(hdd_swipdg* h, const double* vals) {
   st.nx = m->sx;
   st.ny = m->sy;
   const int64_t nv = int64_t(m->sx + 1) * (m->sy + 1);
-  if (!st.h[0].levels.empty() && (st.h[0].levels[0]->nx != m->sx || st.h[0].levels[0]->ny != m->sy)) {
-    st.h[0].levels.clear();
-    st.h[1].levels.clear();
-  }
-  if (st.h[0].levels.empty()) {  // level structure, allocation only
-    for (int t = 0; t < 2; ++t) {
-      int lx = m->sx, ly = m->sy;
-      for (int l = 0;; ++l) {
-        std::unique_ptr<MgLevel> L(new MgLevel);
-        L->nx = lx;
-        L->ny = ly;
-        L->nv = int64_t(lx + 1) * (ly + 1);
-        if (!(t == 1 && l == 0)) {  // the twisted hierarchy shares the level-0 operator of the plain one
-          L->S.alloc(size_t(9) * L->nv);
-          L->dinv.alloc(size_t(L->nv));
-        }
-        L->b.alloc(size_t(L->nv));
-        L->x.alloc(size_t(L->nv));
-        L->r.alloc(size_t(L->nv));
-        L->y.alloc(size_t(L->nv));
-        const bool last = L->nv <= kMaxCoarse || (lx & 1) || (ly & 1) || lx < 2 || ly < 2;
-        st.h[t].levels.push_back(std::move(L));
-        if (last) break;
-        lx /= 2;
-        ly /= 2;
-      }
+  if (!st.levels.empty() && (st.levels[0]->nx != m->sx || st.levels[0]->ny != m->sy)) st.levels.clear();
+  if (st.levels.empty()) {  // level structure, allocation only
+    int lx = m->sx, ly = m->sy;
+    for (int l = 0;; ++l) {
+      std::unique_ptr<MgLevel> L(new MgLevel);
+      L->nx = lx;
+      L->ny = ly;
+      L->nv = int64_t(lx + 1) * (ly + 1);
+      const size_t ops = l == 0 ? 1 : 2;  // the twisted hierarchy shares the level-0 operator of the plain one
+      L->S.alloc(ops * 9 * size_t(L->nv));
+      L->dinv.alloc(ops * size_t(L->nv));
+      L->b.alloc(2 * size_t(L->nv));
+      L->x.alloc(2 * size_t(L->nv));
+      L->r.alloc(2 * size_t(L->nv));
+      L->y.alloc(2 * size_t(L->nv));
+      const bool last = L->nv <= kMaxCoarse || (lx & 1) || (ly & 1) || lx < 2 || ly < 2;
+      st.levels.push_back(std::move(L));
+      if (last) break;
+      lx /= 2;
+      ly /= 2;
     }
   }
-  MgLevel& f0 = *st.h[0].levels[0];
+  MgLevel& f0 = *st.levels[0];
   k_vertex_galerkin<<<blocks_for(nv), kMgThreads, 0, s>>>(h->view(), vals, m->cell_v0.p, m->lex_cell.p, m->sx, m->sy, Rows{0, nv}, f0.S.p);
   count_launch();
   if (m->world > 1) Nccl::get().all_reduce_sum(f0.S.p, size_t(9) * nv, m->comm, s);
   HDD_CUDA(cudaGetLastError());
-  build_hierarchy(h, st.h[0], f0.S.p, false);
-  build_hierarchy(h, st.h[1], f0.S.p, true);
+  build_hierarchies(h, st);
   HDD_CUDA(cudaGetLastError());
   detect_strips(h, st);
 }
@@ -776,75 +884,75 @@ void mg_apply(hdd_swipdg* h, const int* done, const double* r, double* z, double
   hdd_mesh* m = h->mesh;
   MgState& st = *h->mg;
   cudaStream_t s = m->stream;
-  // HDD_MG_TIMING=1: wall-clock phases of the first applications (synchronising; diagnostics only)
-  static const bool timing = [] { const char* e = std::getenv("HDD_MG_TIMING"); return e && e[0] == '1'; }();
-  static int timed_calls = 0;
-  const bool tt = timing && timed_calls < 6;
-  double t_mark = 0.0;
-  auto lap = [&](const char* what) {
-    if (!tt) return;
-    cudaStreamSynchronize(s);
-    timespec ts;
-    clock_gettime(CLOCK_MONOTONIC, &ts);
-    const double now = ts.tv_sec + 1e-9 * ts.tv_nsec;
-    if (what) std::fprintf(stderr, "[hdd mg rank %d call %d] %-12s %.3f ms\n", m->rank, timed_calls, what, 1e3 * (now - t_mark));
-    t_mark = now;
-  };
-  lap(nullptr);
-  MgLevel& a = *st.h[0].levels[0];
-  MgLevel& b = *st.h[1].levels[0];
+  MgLevel& a = *st.levels[0];
   const bool multi = m->world > 1;
   const MgDist& d = st.dist;
   const int nx1 = st.nx + 1;
+  double* b0 = a.b.p;
+  double* b1 = a.b.p + a.nv;
   if (d.on) {
-    // vertex rows c0 .. c1 of my cells; row c1 belongs to the rank above (which adds my share), row c0 gets the share
-    // of the rank below
+    // vertex rows c0 .. c1 of my cells; rows c0 and c1 are shared with the ranks below / above
     const Rows mine{int64_t(d.c0) * nx1, int64_t(d.c1 - d.c0 + 1) * nx1};
-    k_dg_restrict<<<blocks_for(mine.cnt), kMgThreads, 0, s>>>(done, r, m->lex_cell.p, m->own0, m->n_own, st.nx, st.ny, mine, a.b.p, nullptr);
+    k_dg_restrict<<<blocks_for(mine.cnt), kMgThreads, 0, s>>>(done, r, m->lex_cell.p, m->own0, m->n_own, st.nx, st.ny, mine, b0, nullptr);
     count_launch();
+    const int g = d.ghost;
+    const size_t cnt = size_t(g + 1) * nx1;
     Nccl& nc = Nccl::get();
     nc.group_start();
-    if (d.upper >= 0) nc.send(a.b.p + int64_t(d.c1) * nx1, size_t(nx1), d.upper, m->comm, s);
-    if (d.lower >= 0) nc.recv(d.tmp.p, size_t(nx1), d.lower, m->comm, s);
-    nc.group_end();
+    if (d.upper >= 0) {
+      nc.send(b0 + int64_t(d.c1 - g) * nx1, cnt, d.upper, m->comm, s);  // my rows [c1 - g, c1]
+      nc.recv(d.tmp_up.p, cnt, d.upper, m->comm, s);                    // its rows [c1, c1 + g]
+    }
     if (d.lower >= 0) {
-      k_add_row<<<(nx1 + 255) / 256, 256, 0, s>>>(done, a.b.p + int64_t(d.c0) * nx1, d.tmp.p, nx1);
-      count_launch();
+      nc.send(b0 + int64_t(d.c0) * nx1, cnt, d.lower, m->comm, s);      // my rows [c0, c0 + g]
+      nc.recv(d.tmp_lo.p, cnt, d.lower, m->comm, s);                    // its rows [c0 - g, c0]
     }
-    k_twist_vector<<<blocks_for(level_rows(st, a, 0).cnt), kMgThreads, 0, s>>>(done, a.b.p, st.nx, level_rows(st, a, 0), b.b.p);
+    nc.group_end();
+    const int lo_row = d.b_lo[0], hi_row = d.b_hi[0];
+    k_ghost_unpack_twist<<<blocks_for(int64_t(hi_row - lo_row + 1) * nx1), kMgThreads, 0, s>>>(
+        done, b0, b1, d.lower >= 0 ? d.tmp_lo.p : nullptr, d.upper >= 0 ? d.tmp_up.p : nullptr, st.nx, d.c0, d.c1, g, lo_row, hi_row);
     count_launch();
-    lap("restrict");
   } else {
-    k_dg_restrict<<<blocks_for(a.nv), kMgThreads, 0, s>>>(done, r, m->lex_cell.p, m->own0, m->n_own, st.nx, st.ny, Rows{0, a.nv}, a.b.p,
-                                                           multi ? nullptr : b.b.p);
+    k_dg_restrict<<<blocks_for(a.nv), kMgThreads, 0, s>>>(done, r, m->lex_cell.p, m->own0, m->n_own, st.nx, st.ny, Rows{0, a.nv}, b0,
+                                                           multi ? nullptr : b1);
     count_launch();
-    lap("restrict");
     if (multi) {
-      Nccl::get().all_reduce_sum(a.b.p, size_t(a.nv), m->comm, s);
-      lap("all-reduce");
-      k_twist_vector<<<blocks_for(a.nv), kMgThreads, 0, s>>>(done, a.b.p, st.nx, Rows{0, a.nv}, b.b.p);
+      Nccl::get().all_reduce_sum(b0, size_t(a.nv), m->comm, s);
+      k_twist_vector<<<blocks_for(a.nv), kMgThreads, 0, s>>>(done, b0, st.nx, Rows{0, a.nv}, b1);
       count_launch();
     }
   }
-  if (st.h[0].levels.size() == 1) {
+  if (st.levels.size() == 1) {
     // the fine vertex grid is already small enough for the dense solve
-    k_mg_dense<<<(int(a.nv) + 127) / 128, 128, 0, s>>>(done, st.h[0].coarse_inv.p, int(a.nv), a.b.p, a.x.p);
-    k_mg_dense<<<(int(b.nv) + 127) / 128, 128, 0, s>>>(done, st.h[1].coarse_inv.p, int(b.nv), b.b.p, b.x.p);
-    count_launch(2);
+    k_mg_dense<<<dim3(unsigned(int(a.nv) + 127) / 128, 2u), 128, 0, s>>>(done, st.coarse_inv.p, int(a.nv), a.b.p, a.x.p);
+    count_launch();
+    a.result = a.x.p;
   } else {
-    vcycle_pair(m, st, done, s);
-    lap("v-cycles");
+    vcycle(m, st, done, s);
   }
-  // the cells of my top row read the vertex row above my strip
-  exchange_rows(m, st, a, 0, {a.x.p, b.x.p}, EX_DOWN);
   const int grid = int(std::min<int64_t>((m->n_own + kMgThreads - 1) / kMgThreads, kMaxBlocks));
-  k_dg_prolong_dot<<<grid, kMgThreads, 0, s>>>(done, m->n_own, m->cell_v0.p + m->own0, st.nx, a.x.p, b.x.p, r, z, p_init, partial, sc);
+  k_dg_prolong_dot<<<grid, kMgThreads, 0, s>>>(done, m->n_own, m->cell_v0.p + m->own0, st.nx, a.result, a.result + a.nv, r, z, p_init,
+                                               partial, sc);
   count_launch();
   HDD_CUDA(cudaGetLastError());
-  lap("prolong+dot");
-  if (tt) ++timed_calls;
 }
 
-int mg_num_levels(const hdd_swipdg* h) { return h->mg ? int(h->mg->h[0].levels.size()) : 0; }
+int mg_num_levels(const hdd_swipdg* h) { return h->mg ? int(h->mg->levels.size()) : 0; }
 
 }  // namespace hdd
+
+// host-only view of the strip plan for the CPU tests: out[8 * l + {0..7}] = pre_lo, pre_hi, b_lo, b_hi, up_lo, up_hi,
+// pro_lo, pro_hi of level l; out[8 * n_dist + {0, 1, 2}] = own_lo, own_hi, ghost
+extern "C" int hdd_mg_strip_plan(int ny, int c0, int c1, int n_dist, int* out) {
+  if (!out || n_dist < 1 || n_dist > hdd::kMaxDist || c0 < 0 || c1 <= c0 || c1 > ny) return HDD_ERR_WRONG_INPUT;
+  hdd::MgDist d;
+  hdd::mg_strip_plan(ny, c0, c1, n_dist, d);
+  for (int l = 0; l < n_dist; ++l) {
+    const int v[8] = {d.pre_lo[l], d.pre_hi[l], d.b_lo[l], d.b_hi[l], d.up_lo[l], d.up_hi[l], d.pro_lo[l], d.pro_hi[l]};
+    for (int k = 0; k < 8; ++k) out[8 * l + k] = v[k];
+  }
+  out[8 * n_dist] = d.own_lo;
+  out[8 * n_dist + 1] = d.own_hi;
+  out[8 * n_dist + 2] = d.ghost;
+  return HDD_OK;
+}

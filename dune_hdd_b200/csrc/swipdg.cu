@@ -12,6 +12,21 @@
 using namespace hdd;
 
 hdd_swipdg::~hdd_swipdg() {
+  if (p2p_ready && mesh) {
+    // The neighbours read r / p / p_alt of this rank through their own IPC mappings.  Nobody frees an exported buffer
+    // before every rank has finished its kernels and closed its mappings: drain the stream, close, then meet the other
+    // ranks in one all-reduce (destruction of a distributed discretization is collective, like its construction).
+    cudaStreamSynchronize(mesh->stream);
+    for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
+    ipc_opened.clear();
+    if (mesh->world > 1 && mesh->comm && sc.p) {
+      try {
+        hdd::Nccl::get().all_reduce_sum(&sc.p->red[0], 1, mesh->comm, mesh->stream);
+        cudaStreamSynchronize(mesh->stream);
+      } catch (...) {
+      }
+    }
+  }
   for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
   if (sc_host) cudaFreeHost(sc_host);
   if (mg) hdd::mg_release(mg);
@@ -251,6 +266,21 @@ bool p2p_wanted() {
   return on;
 }
 
+// collective yes / no: true iff every rank passes ok = true (one all-reduce, one host synchronisation)
+static bool all_ranks_ok(hdd_mesh* m, bool ok) {
+  cudaStream_t s = m->stream;
+  DevBuf<double> flag;
+  double f = ok ? 0.0 : 1.0;
+  flag.upload(&f, 1, s);
+  Nccl::get().all_reduce_sum(flag.p, 1, m->comm, s);
+  HDD_CUDA(cudaMemcpyAsync(&f, flag.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+  HDD_CUDA(cudaStreamSynchronize(s));
+  return f == 0.0;
+}
+
+// Every step that can fail on one rank alone is followed by a collective agreement before the next collective, so the
+// ranks always issue the same sequence of NCCL calls: (1) local allocations and IPC export, agree; (2) all-gather of the
+// handles, open the neighbours' handles, agree.  A failure anywhere makes every rank fall back to the NCCL halo exchange.
 bool setup_p2p(hdd_swipdg* h) {
   hdd_mesh* m = h->mesh;
   if (h->p2p_ready) return true;
@@ -258,62 +288,67 @@ bool setup_p2p(hdd_swipdg* h) {
   cudaStream_t s = m->stream;
   Nccl& nc = Nccl::get();
   const size_t loc = size_t(m->n_loc) * h->nl;
-  int ok = 1;
-  std::vector<IpcRecord> all(size_t(m->world));
+  // (1) local work only
+  bool ok = true;
+  IpcRecord mine{};
   try {
     if (m->world > kMaxPeers) HDD_THROW(HDD_ERR_NOT_IMPLEMENTED, "peer-memory SpMV supports at most " << kMaxPeers << " ranks");
     h->p_alt.alloc(loc);
     h->p_alt.zero(s);
     h->dinv_local.alloc(loc);
     h->dinv_local.zero(s);
-    IpcRecord mine{};
     const void* ptrs[3] = {h->r.p, h->p.p, h->p_alt.p};
     for (int k = 0; k < 3; ++k) {
       HDD_CUDA(cudaIpcGetMemHandle(&mine.handle[k], const_cast<void*>(ptrs[k])));
       mine.offset[k] = allocation_offset(ptrs[k]);
     }
+  } catch (const Error& e) {
+    set_last_error(e.what());
+    cudaGetLastError();
+    ok = false;
+  }
+  if (!all_ranks_ok(m, ok)) {
+    h->p2p_failed = true;
+    h->p_alt.release();
+    return false;
+  }
+  // (2) every rank takes part in the all-gather; opening a handle can fail locally again
+  std::vector<IpcRecord> all(size_t(m->world));
+  {
     DevBuf<unsigned char> send, recv;
     send.upload(reinterpret_cast<const unsigned char*>(&mine), sizeof(mine), s);
     recv.alloc(sizeof(IpcRecord) * size_t(m->world));
     nc.all_gather_bytes(send.p, recv.p, sizeof(IpcRecord), m->comm, s);
     HDD_CUDA(cudaMemcpyAsync(all.data(), recv.p, sizeof(IpcRecord) * size_t(m->world), cudaMemcpyDeviceToHost, s));
     HDD_CUDA(cudaStreamSynchronize(s));
-  } catch (const Error& e) {
-    set_last_error(e.what());
-    ok = 0;
   }
   PeerView pv{};
-  if (ok) {
-    pv.own0 = m->own0;
-    pv.n_own = m->n_own;
-    pv.halo_peer = m->halo_peer.p;
-    pv.halo_rcell = m->halo_rcell.p;
-    pv.dinv_local = h->dinv_local.p;
-    for (const HaloPeer& peer : m->peers) {
-      void* opened[3] = {nullptr, nullptr, nullptr};
-      for (int k = 0; k < 3 && ok; ++k) {
-        if (cudaIpcOpenMemHandle(&opened[k], all[size_t(peer.rank)].handle[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-          cudaGetLastError();
-          ok = 0;
-          break;
-        }
-        h->ipc_opened.push_back(opened[k]);
+  pv.own0 = m->own0;
+  pv.n_own = m->n_own;
+  pv.halo_peer = m->halo_peer.p;
+  pv.halo_rcell = m->halo_rcell.p;
+  pv.dinv_local = h->dinv_local.p;
+  for (const HaloPeer& peer : m->peers) {
+    void* opened[3] = {nullptr, nullptr, nullptr};
+    for (int k = 0; k < 3 && ok; ++k) {
+      if (cudaIpcOpenMemHandle(&opened[k], all[size_t(peer.rank)].handle[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ok = false;
+        break;
       }
-      if (!ok) break;
-      pv.r[peer.rank] = reinterpret_cast<const double*>(static_cast<char*>(opened[0]) + all[size_t(peer.rank)].offset[0]);
-      pv.p[0][peer.rank] = reinterpret_cast<const double*>(static_cast<char*>(opened[1]) + all[size_t(peer.rank)].offset[1]);
-      pv.p[1][peer.rank] = reinterpret_cast<const double*>(static_cast<char*>(opened[2]) + all[size_t(peer.rank)].offset[2]);
-      pv.own0_of[peer.rank] = m->rank_own0[size_t(peer.rank)];
+      h->ipc_opened.push_back(opened[k]);
     }
+    if (!ok) break;
+    pv.r[peer.rank] = reinterpret_cast<const double*>(static_cast<char*>(opened[0]) + all[size_t(peer.rank)].offset[0]);
+    pv.p[0][peer.rank] = reinterpret_cast<const double*>(static_cast<char*>(opened[1]) + all[size_t(peer.rank)].offset[1]);
+    pv.p[1][peer.rank] = reinterpret_cast<const double*>(static_cast<char*>(opened[2]) + all[size_t(peer.rank)].offset[2]);
+    pv.own0_of[peer.rank] = m->rank_own0[size_t(peer.rank)];
   }
-  // agree on the outcome
-  DevBuf<double> flag;
-  double f = ok ? 0.0 : 1.0;
-  flag.upload(&f, 1, s);
-  nc.all_reduce_sum(flag.p, 1, m->comm, s);
-  HDD_CUDA(cudaMemcpyAsync(&f, flag.p, sizeof(double), cudaMemcpyDeviceToHost, s));
-  HDD_CUDA(cudaStreamSynchronize(s));
-  if (f != 0.0) {
+  if (!all_ranks_ok(m, ok)) {
+    // nobody uses the mappings: close what was opened; the exported buffers stay allocated until every rank has passed
+    // the agreement above, which it has
+    for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+    h->ipc_opened.clear();
     h->p2p_failed = true;
     h->p_alt.release();
     return false;
@@ -745,7 +780,7 @@ int hdd_apply(hdd_swipdg* h, const double* mu, int mu_size, const double* x_host
   });
 }
 
-int hdd_residual(hdd_swipdg* h, const double* mu, int mu_size, double* relative_residual) {
+int hdd_residual(hdd_swipdg* h, const double* mu, int mu_size, double* relative_residual, double* fp64_floor) {
   return guarded([&] {
     require_init(h);
     check_mu(h, mu, mu_size, "mu");
@@ -761,12 +796,30 @@ int hdd_residual(hdd_swipdg* h, const double* mu, int mu_size, double* relative_
     HDD_CUDA(cudaMemcpyAsync(h->tmp_local.p + size_t(m->own0) * h->nl, h->x.p, rows * sizeof(double), cudaMemcpyDeviceToDevice, s));
     m->halo_exchange(h->tmp_local.p, h->nl);
     launch_spmv(h->view(), vals, h->tmp_local.p, h->q.p, s);
-    launch_residual_norms(h->b.p, h->q.p, int64_t(rows), h->partial.p, h->sc.p, s);
-    if (m->world > 1) Nccl::get().all_reduce_sum(&h->sc.p->red[0], 2, m->comm, s);
-    double red[2] = {0.0, 0.0};
+    launch_residual_norms(h->b.p, h->q.p, h->x.p, int64_t(rows), vals, h->nnz, h->partial.p, h->sc.p, s);
+    if (m->world > 1) {
+      Nccl::get().all_reduce_sum(&h->sc.p->red[0], 3, m->comm, s);
+      // max |A_ij| over the ranks: -min(-v)
+      DevBuf<double> neg;
+      double amax_local = 0.0;
+      HDD_CUDA(cudaMemcpyAsync(&amax_local, &h->sc.p->red[3], sizeof(double), cudaMemcpyDeviceToHost, s));
+      HDD_CUDA(cudaStreamSynchronize(s));
+      amax_local = -amax_local;
+      neg.upload(&amax_local, 1, s);
+      Nccl::get().all_reduce_min(neg.p, 1, m->comm, s);
+      HDD_CUDA(cudaMemcpyAsync(&amax_local, neg.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+      HDD_CUDA(cudaStreamSynchronize(s));
+      amax_local = -amax_local;
+      HDD_CUDA(cudaMemcpyAsync(&h->sc.p->red[3], &amax_local, sizeof(double), cudaMemcpyHostToDevice, s));
+      HDD_CUDA(cudaStreamSynchronize(s));
+    }
+    double red[4] = {0.0, 0.0, 0.0, 0.0};
     HDD_CUDA(cudaMemcpyAsync(red, &h->sc.p->red[0], sizeof(red), cudaMemcpyDeviceToHost, s));
     HDD_CUDA(cudaStreamSynchronize(s));
     if (relative_residual) *relative_residual = red[1] > 0.0 ? std::sqrt(red[0] / red[1]) : std::sqrt(red[0]);
+    // what b - A x can resolve in fp64: one SpMV row sums (1 + n_faces) n_loc products of size <= max|A| |x|
+    if (fp64_floor)
+      *fp64_floor = red[1] > 0.0 ? 1.1102230246251565e-16 * double((m->nf + 1) * h->nl) * red[3] * std::sqrt(red[2] / red[1]) : 0.0;
   });
 }
 

@@ -36,6 +36,21 @@ def _check(status):
         raise _EXC.get(status, HddError)(status, capi.lib().hdd_last_error().decode())
 
 
+def _owned_vector(disc, v, what="vector", writable=False):
+    """the reference throws shapes_do_not_match for a vector of the wrong size (wrong_input_given here); the C-ABI copies
+    num_owned_dofs() doubles from / to the pointer, so the check has to happen before the call"""
+    n = disc.num_owned_dofs()
+    if writable:
+        if not (isinstance(v, np.ndarray) and v.dtype == np.float64 and v.flags.c_contiguous and v.flags.writeable):
+            raise wrong_input_given(capi.HDD_ERR_WRONG_INPUT, "%s has to be a writable C-contiguous float64 array" % what)
+        a = v
+    else:
+        a = capi.as_f64(v)
+    if a.ndim != 1 or a.shape[0] != n:
+        raise wrong_input_given(capi.HDD_ERR_WRONG_INPUT, "%s has shape %s, the space has %d (owned) DoFs" % (what, a.shape, n))
+    return a
+
+
 def _mu_array(mu):
     if mu is None:
         return None, 0
@@ -155,8 +170,8 @@ class _ProductParts(_Parts):
         """u^T P(mu) v on the device"""
         mu_a, ms = _mu_array(mu)
         r = C.c_double()
-        _check(capi.lib().hdd_product_apply2(self._d._h, self._id, capi.ptr(mu_a), ms, capi.ptr(capi.as_f64(u)),
-                                             capi.ptr(capi.as_f64(v)), C.byref(r)))
+        u, v = _owned_vector(self._d, u, "u"), _owned_vector(self._d, v, "v")
+        _check(capi.lib().hdd_product_apply2(self._d._h, self._id, capi.ptr(mu_a), ms, capi.ptr(u), capi.ptr(v), C.byref(r)))
         return r.value
 
     def induced_norm(self, u, mu=None):
@@ -284,7 +299,7 @@ class SWIPDG:
         """{L2, H1_semi, energy} norms of vector - exact (test/linearelliptic-swipdg.hh:267-290), on the device"""
         mu_a, ms = _mu_array(mu)
         out = np.zeros(3)
-        v = None if vector is None else capi.as_f64(vector)
+        v = None if vector is None else _owned_vector(self, vector)
         _check(capi.lib().hdd_error_norms(self._h, capi.ptr(v), exact.encode(), exact_dx.encode(), exact_dy.encode(),
                                           int(order), capi.ptr(mu_a), ms, capi.ptr(out)))
         return {"L2": out[0], "H1_semi": out[1], "energy": out[2]}
@@ -323,18 +338,19 @@ class SWIPDG:
     def apply(self, x, mu=None):
         """get_operator().freeze_parameter(mu).apply(x)"""
         mu_a, ms = _mu_array(mu)
-        x = capi.as_f64(x)
+        x = _owned_vector(self, x, "x")
         y = np.empty_like(x)
         _check(capi.lib().hdd_apply(self._h, capi.ptr(mu_a), ms, capi.ptr(x), capi.ptr(y)))
         return y
 
-    def residual(self, mu=None):
+    def residual(self, mu=None, with_floor=False):
         """||rhs(mu) - system_matrix(mu) x|| / ||rhs(mu)|| of the solution the last solve left on the device, recomputed
-        there with one SpMV (global over all ranks; collective)"""
+        there with one SpMV (global over all ranks; collective).  with_floor: also the fp64 rounding level of that
+        quantity, 2^-53 (1 + n_faces) n_loc max|A| ||x|| / ||b||"""
         mu_a, ms = _mu_array(mu)
-        r = C.c_double()
-        _check(capi.lib().hdd_residual(self._h, capi.ptr(mu_a), ms, C.byref(r)))
-        return r.value
+        r, f = C.c_double(), C.c_double()
+        _check(capi.lib().hdd_residual(self._h, capi.ptr(mu_a), ms, C.byref(r), C.byref(f)))
+        return (r.value, f.value) if with_floor else r.value
 
     # ---- solve --------------------------------------------------------------------------------------------
     def solver_types(self):
@@ -364,7 +380,7 @@ class SWIPDG:
         """out: optional preallocated float64 array of num_owned_dofs() entries (e.g. page-locked, capi.pinned_empty)"""
         options = dict(self.solver_options() if options is None else options)
         mu_a, ms = _mu_array(mu)
-        x = (self.create_vector() if out is None else out) if copy_to_host else None
+        x = (self.create_vector() if out is None else _owned_vector(self, out, "out", writable=True)) if copy_to_host else None
         info = capi.hdd_solve_info()
         _check(capi.lib().hdd_solve(self._h, options.get("type", "").encode(), C.c_double(options.get("precision", 1e-10)),
                                     int(options.get("max_iter", 100000)), capi.ptr(mu_a), ms, capi.ptr(x),
@@ -397,14 +413,14 @@ class SWIPDG:
     def estimate(self, vector, type, parameters=None):
         p = self._parameters(parameters)
         eta = C.c_double()
-        v = None if vector is None else capi.as_f64(vector)
+        v = None if vector is None else _owned_vector(self, vector)
         _check(capi.lib().hdd_estimate(self._h, type.encode(), capi.ptr(v), C.byref(p), C.byref(eta), None))
         return eta.value
 
     def estimate_local(self, vector, type, parameters=None):
         p = self._parameters(parameters)
         eta = C.c_double()
-        v = None if vector is None else capi.as_f64(vector)
+        v = None if vector is None else _owned_vector(self, vector)
         n = self.num_subdomains() if "OS2014" in type else self.num_owned_dofs() // self.n_loc
         out = np.zeros(n)
         _check(capi.lib().hdd_estimate(self._h, type.encode(), capi.ptr(v), C.byref(p), C.byref(eta), capi.ptr(out)))
@@ -413,7 +429,7 @@ class SWIPDG:
     def indicators(self, vector, parameters=None):
         """all squared per-cell indicators of one device pass (dict of arrays), for parity tests"""
         p = self._parameters(parameters)
-        v = None if vector is None else capi.as_f64(vector)
+        v = None if vector is None else _owned_vector(self, vector)
         n = self.num_owned_dofs() // self.n_loc
         out = np.zeros((8, n))
         _check(capi.lib().hdd_indicators(self._h, capi.ptr(v), C.byref(p), capi.ptr(out)))

@@ -182,8 +182,11 @@ int hdd_sync(hdd_swipdg* h);
 int hdd_apply(hdd_swipdg* h, const double* mu, int mu_size, const double* x_host, double* y_host);
 /* True relative residual ||b(mu) - A(mu) x||_2 / ||b(mu)||_2 of the solution the last hdd_solve left on the device,
  * recomputed from scratch (one SpMV with the frozen operator, global over all ranks): what a caller of the reference would
- * get from rhs - system_matrix.mv(solution) after solve() (discretizations/base.hh:361-364).  Collective on N GPUs. */
-int hdd_residual(hdd_swipdg* h, const double* mu, int mu_size, double* relative_residual);
+ * get from rhs - system_matrix.mv(solution) after solve() (discretizations/base.hh:361-364).  Collective on N GPUs.
+ * fp64_floor (nullable): the size of that quantity's own rounding error, 2^-53 (1 + n_faces) n_loc max|A_ij| ||x|| / ||b||
+ * - the right-hand side of the SWIPDG system scales with h^2 against O(1) matrix entries, so on fine grids a recomputed
+ * residual cannot fall below it however long the solver iterates (4096^2 Q1: a few 1e-9). */
+int hdd_residual(hdd_swipdg* h, const double* mu, int mu_size, double* relative_residual, double* fp64_floor);
 
 typedef struct hdd_solve_info {
   int iterations;
@@ -309,6 +312,13 @@ int hdd_partition_plan(int kind, int64_t n_cells, int64_t n_verts, const int32_t
                        const int64_t* rank_cell_offsets, int rank, int32_t** halo_cells, int64_t* n_halo,
                        int32_t** send_cells, int64_t* send_offsets);
 int hdd_free(void* p);
+/* Host arithmetic of the strip-distributed multigrid preconditioner ("cg.mg" on N GPUs), exported for the CPU
+ * tests: the inclusive vertex-row ranges the sweeps of the n_dist finest vertex levels run on for the rank owning the cell
+ * rows [c0, c1) of an ny-row structured grid.  out[8 l + k], k = 0..7: pre_lo, pre_hi (pre-smoothing), b_lo, b_hi
+ * (right-hand side), up_lo, up_hi (post-smoothing), pro_lo, pro_hi (prolongation) of level l; out[8 n_dist + {0,1,2}]:
+ * first and last own row of the first replicated level, and the number of level-0 rows received from each neighbour.
+ * No device needed. */
+int hdd_mg_strip_plan(int ny, int c0, int c1, int n_dist, int* out);
 
 /* ---- measurement ------------------------------------------------------------------------------------------------ */
 /* Times `reps` back-to-back launches of one hot kernel on the handle's stream with CUDA events (after 3 warm-up

@@ -226,6 +226,10 @@ class Product {
   // freeze_parameter(mu).apply2(u, v) = u^T P(mu) v, evaluated on the device
   double apply2(const Vector& u, const Vector& v, const Parameter& mu = Parameter()) const {
     double r = 0.0;
+    int64_t g = 0, o = 0;
+    check(hdd_num_dofs(h_, &g, &o));
+    if (int64_t(u.size()) != o || int64_t(v.size()) != o)
+      throw Exceptions::wrong_input_given("apply2: the vectors must have num_owned_dofs() entries");  // shapes_do_not_match
     check(hdd_product_apply2(h_, id_.c_str(), mu.empty() ? nullptr : mu.data(), int(mu.size()), u.data(), v.data(), &r));
     return r;
   }
@@ -298,7 +302,15 @@ class SWIPDG {
   AffinelyDecomposedContainer rhs() const { return AffinelyDecomposedContainer(h_, HDD_RHS); }
   AffinelyDecomposedContainer get_operator() const { return system_matrix(); }
   AffinelyDecomposedContainer get_rhs() const { return rhs(); }
+  // the C-ABI copies num_owned_dofs() doubles from / to the pointers it gets: a vector of another size is refused here,
+  // where the reference throws Stuff::Exceptions::shapes_do_not_match
+  void require_owned_size(const Vector& v, const char* what) const {
+    if (int64_t(v.size()) != num_owned_dofs())
+      throw Exceptions::wrong_input_given(std::string(what) + ": the vector has " + std::to_string(v.size()) + " entries, the space " +
+                                          std::to_string(num_owned_dofs()) + " (owned) DoFs");
+  }
   Vector apply(const Vector& x, const Parameter& mu = Parameter()) const {
+    require_owned_size(x, "apply");
     Vector y(x.size());
     check(hdd_apply(h_, mu.empty() ? nullptr : mu.data(), int(mu.size()), x.data(), y.data()));
     return y;
@@ -323,6 +335,7 @@ class SWIPDG {
                                             const std::string& exact_dy, int order = 5,
                                             const Parameter& mu = Parameter()) const {
     double out[3] = {0.0, 0.0, 0.0};
+    require_owned_size(vector, "error_norms");
     check(hdd_error_norms(h_, vector.data(), exact.c_str(), exact_dx.c_str(), exact_dy.c_str(), order,
                           mu.empty() ? nullptr : mu.data(), int(mu.size()), out));
     return {{"L2", out[0]}, {"H1_semi", out[1]}, {"energy", out[2]}};
@@ -399,6 +412,7 @@ class SWIPDG {
     set("mu", p.mu); set("mu_hat", p.mu_hat); set("mu_bar", p.mu_bar);
     set("parameter_range_min", p.parameter_range_min); set("parameter_range_max", p.parameter_range_max);
     double eta = 0.0;
+    require_owned_size(vector, "estimate");
     if (local) local->assign(size_t(type.find("OS2014") != std::string::npos ? num_subdomains() : num_owned_dofs() / n_loc_), 0.0);
     check(hdd_estimate(h_, type.c_str(), vector.data(), &p, &eta, local ? local->data() : nullptr));
     return eta;

@@ -795,3 +795,56 @@ def test_reference_indicators_of_the_localization_study(gpu):
         assert abs((ind * np.bincount(group, minlength=n)).sum() - 1.0) < 1e-12
         local = study.indicators(disc, u, "eta_OS2014" if cls is studies.BlockSWIPDGStudy else "eta_ESV2007")
         assert local.shape == (n,)
+
+
+def test_true_residual_and_vector_shape_checks(gpu):
+    """hdd_residual recomputes ||b - A x|| / ||b|| of the device solution from scratch; the façade refuses vectors of
+    the wrong size (shapes_do_not_match in the reference) before the C-ABI would copy num_owned_dofs() doubles."""
+    g = grids.cube(24)
+    d = hdd.SWIPDG(g, problems.ESV2007())
+    d.init()
+    with pytest.raises(hdd.discretizations.you_are_using_this_wrong):
+        d.residual()  # no solution yet
+    u, info = d.solve({"type": "cg.mg", "precision": 1e-12, "max_iter": 500}, return_info=True)
+    m, rp, col, A, b = oracle_system(g, o.const(1.0), o.esv2007_force())
+    res_ref = np.linalg.norm(b - o.spmv(rp, col, A, u)) / np.linalg.norm(b)
+    res, floor = d.residual(with_floor=True)
+    assert res <= 1e-11 and abs(res - res_ref) <= 0.5 * max(res, res_ref) + 1e-14
+    assert 0.0 < floor < 1e-9
+    # a solve that stops early leaves a large true residual
+    with pytest.raises(hdd.discretizations.linear_solver_failed):
+        d.uncached_solve({"type": "cg.diagonal", "precision": 1e-12, "max_iter": 3})
+    assert d.residual() > 1e-3
+    bad = np.zeros(g.n_dofs + 1)
+    for call in (lambda: d.apply(bad), lambda: d.error_norms(*problems.ESV2007_EXACT, vector=bad),
+                 lambda: d.uncached_solve(out=bad), lambda: d.uncached_solve(out=np.zeros(g.n_dofs, np.float32))):
+        with pytest.raises(hdd.discretizations.wrong_input_given):
+            call()
+    gs = grids.simplex(4)
+    ds = hdd.SWIPDG(gs, problems.ESV2007(), only_these_products=("l2",))
+    ds.init()
+    bad = np.zeros(gs.n_dofs - 3)
+    for call in (lambda: ds.estimate(bad, "eta_ESV2007"), lambda: ds.estimate_local(bad, "eta_ESV2007"),
+                 lambda: ds.indicators(bad), lambda: ds.get_product("l2").apply2(bad, bad)):
+        with pytest.raises(hdd.discretizations.wrong_input_given):
+            call()
+
+
+def test_estimator_with_expression_factor_and_many_segments(gpu):
+    """the expression branch of the indicator kernel (OS2014 factor at mu_hat != mu) on a grid whose subdomains span
+    several reduction segments (> 8192 cells per subdomain), against the oracle"""
+    g = grids.simplex(64, partitions=(1, 1))  # 32768 triangles in one subdomain: four segments
+    prob = problems.OS2014ParametricESV2007()
+    d = hdd.BlockSWIPDG(g, prob)
+    d.init()
+    mu = 0.3
+    u = d.solve({"type": "cg.blockdiagonal", "precision": 1e-12, "max_iter": 20000}, mu=mu)
+    prm = {"mu": mu, "mu_bar": mu, "mu_hat": 0.7, "parameter_range_min": 0.1, "parameter_range_max": 1.0}
+    m = oracle_mesh(g)
+    ind_ref = o.indicators(m, u, o.esv2007_force(), o.os2014_factor(mu), a_hat=o.os2014_factor(0.7),
+                           a_bar=o.os2014_factor(mu), a_min=o.os2014_factor(0.1), a_max=o.os2014_factor(1.0))
+    ind = d.indicators(u, prm)
+    for k in ("nc2", "res2", "r2", "df2", "dfstar2", "rstar2", "amin", "resstar2"):
+        assert np.abs(ind[k] - ind_ref[k]).max() <= SOL_TOL * np.abs(ind_ref[k]).max(), k
+    assert abs(d.estimate(u, "eta_NC_OS2014", prm) - np.sqrt(ind_ref["nc2"].sum())) <= SOL_TOL
+    assert abs(d.estimate(u, "eta_DF_OS2014", prm) - np.sqrt(ind_ref["df2"].sum())) <= SOL_TOL * np.sqrt(ind_ref["df2"].sum())
