@@ -64,7 +64,7 @@ SYMBOLS = [
     "hdd_kernel_bytes", "hdd_expression_evaluate", "hdd_partition_plan", "hdd_free",
     "hdd_swipdg_only_these_products", "hdd_products_available", "hdd_product_num_components", "hdd_product_values",
     "hdd_product_coefficient", "hdd_pattern_volume", "hdd_product_apply2", "hdd_error_norms",
-    "hdd_host_alloc", "hdd_host_free", "hdd_grid_fathers", "hdd_prolong", "hdd_residual", "hdd_mg_strip_plan",
+    "hdd_host_alloc", "hdd_host_free", "hdd_grid_fathers", "hdd_prolong", "hdd_residual", "hdd_mg_strip_plan", "hdd_partition_plan_local", "hdd_mesh_create_cube", "hdd_h2d_bytes",
 ]
 
 _lib = None
@@ -87,6 +87,7 @@ def lib():
         _lib.hdd_last_error.restype = C.c_char_p
         _lib.hdd_version.restype = C.c_char_p
         _lib.hdd_kernel_launches.restype = C.c_int64
+        _lib.hdd_h2d_bytes.restype = C.c_int64
     return _lib
 
 
@@ -143,6 +144,10 @@ def pinned_empty(shape, dtype):
     buf = (C.c_char * blk.nbytes).from_address(blk.ptr.value)
     buf._hdd_owner = blk  # the ctypes buffer is the array's base object: the block lives as long as any view
     return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+
+def h2d_bytes():
+    return int(lib().hdd_h2d_bytes())
 
 
 def kernel_launches():

@@ -117,6 +117,13 @@ void parallel_for(int64_t n, F&& f) {  // f(begin, end)
   parallel_for_indexed(n, worker_count(n), [&f](int, int64_t a, int64_t b) { f(a, b); });
 }
 
+// bytes this library copied host -> device / device -> host since process start (bench.py's e2e.h2d_bytes_per_step)
+extern std::atomic<int64_t> g_h2d_bytes, g_d2h_bytes;
+inline cudaError_t h2d_async(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  g_h2d_bytes.fetch_add(int64_t(bytes));
+  return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s);
+}
+
 // RAII device buffer
 template <class T>
 struct DevBuf {
@@ -145,7 +152,7 @@ struct DevBuf {
   }
   void upload(const T* host, size_t count, cudaStream_t s) {
     if (n < count || !p) alloc(count);
-    if (count) HDD_CUDA(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    if (count) HDD_CUDA(h2d_async(p, host, count * sizeof(T), s));
   }
   void zero(cudaStream_t s) {
     if (p) HDD_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));

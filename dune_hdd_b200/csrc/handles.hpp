@@ -93,7 +93,10 @@ struct hdd_mesh {
   hdd::DevBuf<int32_t> halo_peer, halo_rcell;  // per halo cell: owner rank, cell offset inside the owner's owned range
   std::vector<int32_t> rank_own0;              // own0 of every rank
   // host scratch used while the halo plan is built
-  std::vector<int32_t> h_cell_verts_loc;  // [n_loc*nl] local vertex ids of all local cells
+  // for the halo plan of hdd_mesh_attach_comm (the caller's arrays are gone by then): global vertex ids of the halo cells
+  // [n_halo*nl] (halo order), the owned cells along the partition boundary (local ids, sorted) and their vertex ids
+  std::vector<int32_t> h_halo_verts, h_bowned, h_bowned_verts;
+  int64_t v_begin = 0, v_end = 0;  // vertex id range the local cells touch
 
   hdd::MeshView view(const double* tensor) const {
     hdd::MeshView v{};
@@ -250,7 +253,8 @@ void check_mu(const hdd_swipdg* h, const double* mu, int mu_size, const char* na
 double eval_coef(const Program& p, const double* mu, int mu_size);
 void assemble_products(hdd_swipdg* h);
 // multigrid.cu ("cg.mg")
-void mg_detect_structure(hdd_mesh* m, const double* xy_host, const double* xy_dev, const int32_t* cv_dev, int64_t n_verts);
+void mg_detect_structure(hdd_mesh* m, const double* xy_host, const double* xy_dev, int64_t v_begin, int64_t v_end,
+                         const int32_t* cv_dev, int64_t n_verts);
 void mg_setup(hdd_swipdg* h, const double* frozen_values);
 void mg_apply(hdd_swipdg* h, const int* done, const double* r, double* z, double* p_init, double* partial, CgScalars* sc);
 void mg_release(MgState* st);

@@ -7,10 +7,25 @@
 namespace hdd {
 
 // ---- K0: device-side localisation of the host grid -------------------------------------------------------------------
-// cgeo[c] from (xy, cell_verts); flag |= 1 if a cube cell is not an axis-parallel rectangle
-// (also validates the vertex ids: flag |= 4 if one is out of range)
-void launch_build_geometry(int kind, int32_t n_loc, int32_t n_verts, const double* xy, const int32_t* cell_verts_local,
+// cgeo[c] from (xy, cell_verts); xy is addressed by global vertex id and valid in [v_begin, v_end); flag |= 1 if a cube
+// cell is not an axis-parallel rectangle (also validates the vertex ids: flag |= 4 if one is outside that range)
+void launch_build_geometry(int kind, int32_t n_loc, int32_t v_begin, int32_t v_end, const double* xy, const int32_t* cell_verts_local,
                            double* cgeo, int32_t* flag, cudaStream_t s);
+// A structured nx x ny grid on [x0,x1] x [y0,y1] with px x py boxes as subdomains, cells numbered subdomain-major (boxes x
+// fastest, cells inside a box x fastest): X[px+1] / Y[py+1] first cell column / row of every box, off[px*py+1] first cell id
+// of every box (device arrays).
+struct CubeGridDesc {
+  int nx, ny, px, py;
+  double x0, x1, y0, y1;
+  const int32_t* X;
+  const int32_t* Y;
+  const int64_t* off;
+};
+// fills cgeo / cell_v0 / lex_cell / cgid for the local cells [lower halo | owned | upper halo] and the global face-neighbour
+// ids of the owned cells, plus the one-dimensional geometry tables
+void launch_cube_fill(const CubeGridDesc& g, int32_t n_loc, int32_t own0, int32_t n_own, int32_t cell_begin, const int32_t* halo,
+                      double* cgeo, int32_t* cell_v0, int32_t* lex_cell, int32_t* cgid, int32_t* neigh, double* tgeo,
+                      cudaStream_t s);
 // whole mesh on one GPU: flag |= 8 if a neighbour id is out of range; out[i] = i
 void launch_validate_neighbours(const int32_t* neigh, int64_t count, int32_t n_cells, int32_t* flag, cudaStream_t s);
 void launch_iota(int32_t* out, int32_t n, cudaStream_t s);

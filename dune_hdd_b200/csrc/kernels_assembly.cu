@@ -34,7 +34,8 @@ __device__ __forceinline__ void load_neigh(const int32_t* neigh, int k, int* nb)
   }
 }
 
-__global__ void k_build_geometry(int kind, int32_t n_loc, int32_t n_verts, const double* __restrict__ xy,
+// xy is addressed by global vertex id and holds the vertices [v_begin, v_end) only
+__global__ void k_build_geometry(int kind, int32_t n_loc, int32_t v_begin, int32_t v_end, const double* __restrict__ xy,
                                  const int32_t* __restrict__ cv, double* __restrict__ cgeo, int32_t* flag) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_loc) return;
@@ -44,12 +45,13 @@ __global__ void k_build_geometry(int kind, int32_t n_loc, int32_t n_verts, const
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       const int v = cv[size_t(3) * c + i];
-      if (v < 0 || v >= n_verts) { atomicOr(flag, 4); return; }  // index validation happens here, not on the host
+      if (v < v_begin || v >= v_end) { atomicOr(flag, 4); return; }  // index validation happens here, not on the host
       out[i] = __ldg(p + v);
     }
   } else {
     const int4 v = __ldg(reinterpret_cast<const int4*>(cv) + c);
-    if (v.x < 0 || v.y < 0 || v.z < 0 || v.w < 0 || v.x >= n_verts || v.y >= n_verts || v.z >= n_verts || v.w >= n_verts) {
+    if (v.x < v_begin || v.y < v_begin || v.z < v_begin || v.w < v_begin || v.x >= v_end || v.y >= v_end || v.z >= v_end ||
+        v.w >= v_end) {
       atomicOr(flag, 4);
       return;
     }
@@ -58,6 +60,68 @@ __global__ void k_build_geometry(int kind, int32_t n_loc, int32_t n_verts, const
     double2* out = reinterpret_cast<double2*>(cgeo + size_t(4) * c);
     out[0] = a;
     out[1] = e;
+  }
+}
+
+// Structured cube grid with a px x py box partition, built on the device from closed forms (hdd_mesh_create_cube): one
+// thread per local cell writes its geometry record, vertex 0, global id, the lexicographic -> local map and, for an
+// owned cell, the global ids of its four face neighbours (translated to local ids by k_localize_neighbours afterwards).
+// Coordinates are the expressions of the host generator (grids.cpp), so both paths give bit-identical geometry.
+__device__ __forceinline__ int cube_cell_id(const CubeGridDesc& g, int i, int j) {
+  if (i < 0 || j < 0 || i >= g.nx || j >= g.ny) return -1;
+  int bx = 0, by = 0;
+  while (bx + 1 < g.px && i >= g.X[bx + 1]) ++bx;
+  while (by + 1 < g.py && j >= g.Y[by + 1]) ++by;
+  const int w = g.X[bx + 1] - g.X[bx];
+  return int(g.off[by * g.px + bx]) + (j - g.Y[by]) * w + (i - g.X[bx]);
+}
+
+__global__ void k_cube_fill(CubeGridDesc g, int32_t n_loc, int32_t own0, int32_t n_own, int32_t cell_begin,
+                            const int32_t* __restrict__ halo /* sorted global ids: lower part, then upper part */,
+                            double* __restrict__ cgeo, int32_t* __restrict__ cell_v0, int32_t* __restrict__ lex_cell,
+                            int32_t* __restrict__ cgid, int32_t* __restrict__ neigh) {
+  const int lc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lc >= n_loc) return;
+  const bool own = lc >= own0 && lc < own0 + n_own;
+  const int gid = own ? cell_begin + (lc - own0) : halo[lc < own0 ? lc : lc - n_own];
+  // subdomain of gid: binary search in the offsets, then the position inside the box
+  int lo = 0, hi = g.px * g.py;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (g.off[mid] <= gid) lo = mid; else hi = mid;
+  }
+  const int bx = lo % g.px, by = lo / g.px;
+  const int w = g.X[bx + 1] - g.X[bx];
+  const int r = gid - int(g.off[lo]);
+  const int i = g.X[bx] + r % w, j = g.Y[by] + r / w;
+  double2* geo = reinterpret_cast<double2*>(cgeo + size_t(4) * lc);
+  geo[0] = make_double2(g.x0 + (g.x1 - g.x0) * double(i) / double(g.nx), g.y0 + (g.y1 - g.y0) * double(j) / double(g.ny));
+  geo[1] = make_double2(g.x0 + (g.x1 - g.x0) * double(i + 1) / double(g.nx), g.y0 + (g.y1 - g.y0) * double(j + 1) / double(g.ny));
+  cell_v0[lc] = j * (g.nx + 1) + i;
+  lex_cell[size_t(j) * g.nx + i] = lc;
+  cgid[lc] = gid;
+  if (own) {
+    int4 nb;
+    nb.x = cube_cell_id(g, i - 1, j);
+    nb.y = cube_cell_id(g, i + 1, j);
+    nb.z = cube_cell_id(g, i, j - 1);
+    nb.w = cube_cell_id(g, i, j + 1);
+    reinterpret_cast<int4*>(neigh)[lc - own0] = nb;
+  }
+}
+
+// {x0, hx, 1/hx, -} per column followed by {y0, hy, 1/hy, -} per row, from the closed-form coordinates
+__global__ void k_cube_tgeo(CubeGridDesc g, double* __restrict__ tgeo) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= g.nx + g.ny) return;
+  double4* out = reinterpret_cast<double4*>(tgeo);
+  if (t < g.nx) {
+    const double a = g.x0 + (g.x1 - g.x0) * double(t) / double(g.nx), b = g.x0 + (g.x1 - g.x0) * double(t + 1) / double(g.nx);
+    out[t] = make_double4(a, b - a, 1.0 / (b - a), 0.0);
+  } else {
+    const int r = t - g.nx;
+    const double a = g.y0 + (g.y1 - g.y0) * double(r) / double(g.ny), b = g.y0 + (g.y1 - g.y0) * double(r + 1) / double(g.ny);
+    out[t] = make_double4(a, b - a, 1.0 / (b - a), 0.0);
   }
 }
 
@@ -998,11 +1062,21 @@ __global__ void k_extract_dinv(MeshView m, const double* __restrict__ values, in
 
 }  // namespace
 
-void launch_build_geometry(int kind, int32_t n_loc, int32_t n_verts, const double* xy, const int32_t* cell_verts_local,
+void launch_build_geometry(int kind, int32_t n_loc, int32_t v_begin, int32_t v_end, const double* xy, const int32_t* cell_verts_local,
                            double* cgeo, int32_t* flag, cudaStream_t s) {
   if (n_loc == 0) return;
-  k_build_geometry<<<grid_for(n_loc, 256), 256, 0, s>>>(kind, n_loc, n_verts, xy, cell_verts_local, cgeo, flag);
+  k_build_geometry<<<grid_for(n_loc, 256), 256, 0, s>>>(kind, n_loc, v_begin, v_end, xy, cell_verts_local, cgeo, flag);
   count_launch();
+  HDD_CUDA(cudaGetLastError());
+}
+
+void launch_cube_fill(const CubeGridDesc& g, int32_t n_loc, int32_t own0, int32_t n_own, int32_t cell_begin, const int32_t* halo,
+                      double* cgeo, int32_t* cell_v0, int32_t* lex_cell, int32_t* cgid, int32_t* neigh, double* tgeo,
+                      cudaStream_t s) {
+  if (n_loc > 0)
+    k_cube_fill<<<grid_for(n_loc, 256), 256, 0, s>>>(g, n_loc, own0, n_own, cell_begin, halo, cgeo, cell_v0, lex_cell, cgid, neigh);
+  k_cube_tgeo<<<grid_for(g.nx + g.ny, 256), 256, 0, s>>>(g, tgeo);
+  count_launch(2);
   HDD_CUDA(cudaGetLastError());
 }
 

@@ -13,6 +13,7 @@
 namespace hdd {
 
 std::atomic<int64_t> g_kernel_launches{0};
+std::atomic<int64_t> g_h2d_bytes{0}, g_d2h_bytes{0};
 static thread_local std::string t_last_error;
 void set_last_error(const std::string& msg) { t_last_error = msg; }
 
@@ -146,11 +147,82 @@ void hdd_mesh::halo_exchange(double* v_local, int nd) {
   nc.group_end();
 }
 
+// Shared end of hdd_mesh_create / hdd_mesh_create_cube, once n_subdomains / sub_cell_offsets / sub_neighbours are known:
+// owned subdomains, their diameters (simplex grids; needs the caller's arrays), the reduction segments and the block
+// offsets of the matrix rows (K1 part 1).
+static void finish_mesh(hdd_mesh* m, const double* xy, const int32_t* cell_verts, const int32_t* cell_neigh,
+                        const int32_t* cell_subdomain, PhaseTimer& pt) {
+  const int kind = m->kind, nl = m->nl, nf = m->nf;
+  const int64_t cell_begin = m->cell_begin, cell_end = m->cell_end, n_own = cell_end - cell_begin;
+  cudaStream_t s = m->stream;
+  m->sub_dof_offsets.resize(m->sub_cell_offsets.size());
+  for (size_t k = 0; k < m->sub_cell_offsets.size(); ++k) m->sub_dof_offsets[k] = nl * m->sub_cell_offsets[k];
+  // owned subdomains: the owned range must consist of whole subdomains
+  m->sub_first = int(std::lower_bound(m->sub_cell_offsets.begin(), m->sub_cell_offsets.end(), cell_begin) -
+                     m->sub_cell_offsets.begin());
+  m->sub_last = int(std::lower_bound(m->sub_cell_offsets.begin(), m->sub_cell_offsets.end(), cell_end) -
+                    m->sub_cell_offsets.begin());
+  if (n_own > 0 && (m->sub_cell_offsets[size_t(m->sub_first)] != cell_begin ||
+                    m->sub_cell_offsets[size_t(m->sub_last)] != cell_end))
+    HDD_THROW(HDD_ERR_WRONG_INPUT, "the owned cell range must consist of whole subdomains");
+  if (n_own == 0) m->sub_last = m->sub_first;
+  m->sub_diameter.assign(size_t(m->n_subdomains), 0.0);
+  if (kind == HDD_SIMPLEX2D) {  // only the OS2014 estimators (simplex grids) use the diameters
+    for (int sd = m->sub_first; sd < m->sub_last; ++sd) {
+      std::vector<std::pair<double, double>> pts;
+      // the farthest pair lies on the hull, whose vertices sit on faces leaving the subdomain
+      for (int64_t c = m->sub_cell_offsets[size_t(sd)]; c < m->sub_cell_offsets[size_t(sd) + 1]; ++c)
+        for (int f = 0; f < nf; ++f) {
+          const int32_t g = cell_neigh[c * nf + f];
+          if (g >= 0 && cell_subdomain && cell_subdomain[g] == sd) continue;
+          if (g >= 0 && !cell_subdomain) continue;
+          const int* fv = kFaceVertsSimplex[f];
+          for (int e = 0; e < 2; ++e) {
+            const int32_t v = cell_verts[c * nl + fv[e]];
+            pts.emplace_back(xy[2 * v], xy[2 * v + 1]);
+          }
+        }
+      m->sub_diameter[size_t(sd)] = point_set_diameter(pts);
+    }
+  }
+  // chunked segments of the owned cells for deterministic two-level sums
+  {
+    const int64_t chunk = 8192;
+    m->seg_ptr.clear();
+    m->seg_sub.clear();
+    for (int sd = m->sub_first; sd < m->sub_last; ++sd) {
+      const int64_t b = m->sub_cell_offsets[size_t(sd)] - cell_begin, e = m->sub_cell_offsets[size_t(sd) + 1] - cell_begin;
+      for (int64_t k = b; k < e; k += chunk) {
+        m->seg_ptr.push_back(k);
+        m->seg_sub.push_back(sd);
+      }
+    }
+    m->seg_ptr.push_back(n_own);
+    m->d_seg_ptr.upload(m->seg_ptr.data(), m->seg_ptr.size(), s);
+  }
+
+  pt.lap("subdomains");
+  // ---- K1 part 1: number of blocks per owned cell and their exclusive prefix sum
+  {
+    DevBuf<int64_t> nblk;
+    nblk.alloc(size_t(n_own) + 1);
+    nblk.zero(s);
+    m->blk_start.alloc(size_t(n_own) + 1);
+    const MeshView v = m->view(nullptr);
+    launch_count_blocks(v, nblk.p, s);
+    exclusive_scan_i64(nblk.p, m->blk_start.p, n_own + 1, s);  // nblk[n_own] = 0 => total in blk_start[n_own]
+    HDD_CUDA(cudaMemcpyAsync(&m->n_blocks, m->blk_start.p + n_own, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    HDD_CUDA(cudaStreamSynchronize(s));
+  }
+  pt.lap("block offsets");
+}
+
 extern "C" {
 
 const char* hdd_last_error(void) { return t_last_error.c_str(); }
 const char* hdd_version(void) { return "hdd_b200 0.1 (sm_100a)"; }
 int64_t hdd_kernel_launches(void) { return g_kernel_launches.load(); }
+int64_t hdd_h2d_bytes(void) { return g_h2d_bytes.load(); }
 
 int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy, const int32_t* cell_verts,
                     const int32_t* cell_neigh, const int32_t* cell_subdomain, const uint8_t* boundary_type,
@@ -184,12 +256,13 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
     cudaStream_t s = m->stream;
     PhaseTimer pt("hdd_mesh_create", s);
 
-    // ---- index validation: on the device for a whole mesh (inside the geometry / neighbour kernels); a distributed
-    // mesh walks the caller's arrays on the host below (halo search), so those are checked here first
+    // ---- index validation: on the device (inside the geometry / neighbour kernels) for the cells this rank keeps.  A
+    // distributed mesh walks the host arrays of its owned cells and of the cells across the partition boundary below, so
+    // the ids of the owned cells are checked here first - every rank checks its own, together they check all
     if (!whole) {
       std::atomic<int64_t> bad_vertex{-1}, bad_neigh{-1};
-      parallel_for(n_cells, [&](int64_t c0, int64_t c1) {
-        for (int64_t c = c0; c < c1; ++c)
+      parallel_for(n_own, [&](int64_t c0, int64_t c1) {
+        for (int64_t c = cell_begin + c0; c < cell_begin + c1; ++c)
           for (int i = 0; i < nl; ++i) {
             const int32_t v = cell_verts[c * nl + i], g = cell_neigh[c * nf + i];
             if (v < 0 || v >= n_verts) bad_vertex = c;
@@ -201,9 +274,16 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
     }
     pt.lap("validate indices");
     // ---- halo: every non-owned cell sharing a vertex with an owned cell (superset of the face neighbours the
-    // SpMV needs; the Oswald interpolation needs all cells around a vertex)
-    std::vector<int32_t> halo_lo, halo_hi;
-    compute_halo(nl, n_cells, n_verts, cell_verts, cell_begin, cell_end, halo_lo, halo_hi);
+    // SpMV needs; the Oswald interpolation needs all cells around a vertex), found from the owned side: work
+    // proportional to the partition boundary, no sweep over the other ranks' cells
+    std::vector<int32_t> halo_lo, halo_hi, bowned;
+    compute_halo_local(nl, cell_verts, cell_neigh, n_cells, cell_begin, cell_end, halo_lo, halo_hi, bowned);
+    for (const std::vector<int32_t>* hv : {&halo_lo, &halo_hi})
+      for (int32_t g : *hv)
+        for (int i = 0; i < nl; ++i) {
+          const int32_t v = cell_verts[int64_t(g) * nl + i];
+          if (v < 0 || v >= n_verts) HDD_THROW(HDD_ERR_INDEX_OUT_OF_RANGE, "vertex id out of range in cell " << g);
+        }
     m->own0 = int32_t(halo_lo.size());
     m->n_own = int32_t(n_own);
     m->n_loc = int32_t(halo_lo.size() + n_own + halo_hi.size());
@@ -216,39 +296,78 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
         for (int64_t k = a; k < b; ++k) own[k] = int32_t(cell_begin + k);
       });
       std::copy(halo_hi.begin(), halo_hi.end(), m->cgid.begin() + halo_lo.size() + n_own);
+      // what the halo plan of hdd_mesh_attach_comm needs later (the caller's arrays are gone by then): the vertex ids of
+      // the halo cells and of the owned cells along the partition boundary
+      m->h_halo_verts.resize((halo_lo.size() + halo_hi.size()) * size_t(nl));
+      size_t k = 0;
+      for (const std::vector<int32_t>* hv : {&halo_lo, &halo_hi})
+        for (int32_t g : *hv) {
+          std::memcpy(&m->h_halo_verts[k * nl], cell_verts + int64_t(g) * nl, nl * sizeof(int32_t));
+          ++k;
+        }
+      m->h_bowned.resize(bowned.size());
+      m->h_bowned_verts.resize(bowned.size() * size_t(nl));
+      for (size_t q = 0; q < bowned.size(); ++q) {
+        m->h_bowned[q] = int32_t(bowned[q] - cell_begin) + m->own0;  // local id
+        std::memcpy(&m->h_bowned_verts[q * nl], cell_verts + int64_t(bowned[q]) * nl, nl * sizeof(int32_t));
+      }
     }
 
     pt.lap("halo + cell ids");
+    // ---- the vertices the local cells touch: only the id range [v_begin, v_end) is uploaded (the whole array for a whole
+    // mesh; the rows of a strip for the slabs of a structured grid)
+    int64_t v_begin = 0, v_end = n_verts;
+    if (!whole) {
+      const int nt = worker_count(n_own);
+      std::vector<int32_t> mn(size_t(nt), INT32_MAX), mx(size_t(nt), -1);
+      parallel_for_indexed(n_own, nt, [&](int t, int64_t a, int64_t b) {
+        int32_t lo = INT32_MAX, hi = -1;
+        for (int64_t e = (cell_begin + a) * nl; e < (cell_begin + b) * nl; ++e) {
+          lo = std::min(lo, cell_verts[e]);
+          hi = std::max(hi, cell_verts[e]);
+        }
+        mn[size_t(t)] = lo;
+        mx[size_t(t)] = hi;
+      });
+      int32_t lo = *std::min_element(mn.begin(), mn.end()), hi = *std::max_element(mx.begin(), mx.end());
+      for (int32_t v : m->h_halo_verts) {
+        lo = std::min(lo, v);
+        hi = std::max(hi, v);
+      }
+      if (hi >= lo) {
+        v_begin = lo;
+        v_end = int64_t(hi) + 1;
+      } else {
+        v_begin = 0;
+        v_end = 1;
+      }
+    }
+    m->v_begin = v_begin;
+    m->v_end = v_end;
     // ---- device-side localisation: the owned slices of the host arrays are uploaded as they are (no host copy);
     // kernels build the per-cell geometry records and translate neighbour ids to local numbering
     {
-      DevBuf<double> d_xy;
-      d_xy.upload(xy, size_t(2) * n_verts, s);
+      DevBuf<double> d_xy_slice;
+      d_xy_slice.upload(xy + 2 * v_begin, size_t(2) * (v_end - v_begin), s);
+      const double* d_xy = d_xy_slice.p - 2 * v_begin;  // addressed by global vertex id, valid in [v_begin, v_end)
       DevBuf<int32_t> d_cv;
       d_cv.alloc(size_t(m->n_loc) * nl);
-      std::vector<int32_t> halo_cv((halo_lo.size() + halo_hi.size()) * nl);
-      for (size_t h = 0; h < halo_lo.size(); ++h)
-        std::memcpy(&halo_cv[h * nl], cell_verts + int64_t(halo_lo[h]) * nl, nl * sizeof(int32_t));
-      for (size_t h = 0; h < halo_hi.size(); ++h)
-        std::memcpy(&halo_cv[(halo_lo.size() + h) * nl], cell_verts + int64_t(halo_hi[h]) * nl, nl * sizeof(int32_t));
       if (!halo_lo.empty())
-        HDD_CUDA(cudaMemcpyAsync(d_cv.p, halo_cv.data(), halo_lo.size() * nl * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        HDD_CUDA(h2d_async(d_cv.p, m->h_halo_verts.data(), halo_lo.size() * nl * sizeof(int32_t), s));
       if (n_own)
-        HDD_CUDA(cudaMemcpyAsync(d_cv.p + halo_lo.size() * nl, cell_verts + cell_begin * nl, size_t(n_own) * nl * sizeof(int32_t),
-                                 cudaMemcpyHostToDevice, s));
+        HDD_CUDA(h2d_async(d_cv.p + halo_lo.size() * nl, cell_verts + cell_begin * nl, size_t(n_own) * nl * sizeof(int32_t), s));
       if (!halo_hi.empty())
-        HDD_CUDA(cudaMemcpyAsync(d_cv.p + (halo_lo.size() + n_own) * nl, halo_cv.data() + halo_lo.size() * nl,
-                                 halo_hi.size() * nl * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        HDD_CUDA(h2d_async(d_cv.p + (halo_lo.size() + n_own) * nl, m->h_halo_verts.data() + halo_lo.size() * nl,
+                                 halo_hi.size() * nl * sizeof(int32_t), s));
       const int ngeo = kind == HDD_SIMPLEX2D ? 6 : 4;
       m->cgeo.alloc(size_t(m->n_loc) * ngeo);
       DevBuf<int32_t> d_flag;
       d_flag.alloc(1);
       d_flag.zero(s);
-      launch_build_geometry(kind, m->n_loc, int32_t(n_verts), d_xy.p, d_cv.p, m->cgeo.p, d_flag.p, s);
+      launch_build_geometry(kind, m->n_loc, int32_t(v_begin), int32_t(v_end), d_xy, d_cv.p, m->cgeo.p, d_flag.p, s);
       m->neigh.alloc(size_t(n_own) * nf);
       if (n_own)
-        HDD_CUDA(cudaMemcpyAsync(m->neigh.p, cell_neigh + cell_begin * nf, size_t(n_own) * nf * sizeof(int32_t),
-                                 cudaMemcpyHostToDevice, s));
+        HDD_CUDA(h2d_async(m->neigh.p, cell_neigh + cell_begin * nf, size_t(n_own) * nf * sizeof(int32_t), s));
       DevBuf<int32_t> d_halo;
       if (!whole) {
         std::vector<int32_t> halo(halo_lo);
@@ -262,7 +381,7 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
         m->d_cgid.alloc(size_t(m->n_loc));
         launch_iota(m->d_cgid.p, m->n_loc, s);
       }
-      mg_detect_structure(m.get(), xy, d_xy.p, d_cv.p, n_verts);
+      mg_detect_structure(m.get(), xy, d_xy, v_begin, v_end, d_cv.p, n_verts);
       if (boundary_type) {
         m->has_btype = true;
         m->btype.upload(boundary_type + cell_begin * nf, size_t(n_own) * nf, s);
@@ -287,29 +406,22 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
     // ---- local vertices + incidence (vertex -> local DoFs), boundary flags
     // (the incidence feeds the Oswald pass, which exists on simplices only; the local vertex ids also drive the
     // halo plan of a distributed mesh)
-    const bool need_verts = !whole || kind == HDD_SIMPLEX2D;
+    const bool need_verts = kind == HDD_SIMPLEX2D;
     std::vector<int32_t> cvl(need_verts ? size_t(m->n_loc) * nl : 0);
-    if (need_verts && kind == HDD_CUBE2D) {
-      // cubes have no vertex incidence (the Oswald pass exists on simplices only): the halo plan works on the global
-      // vertex ids of the local cells directly
-      parallel_for(m->n_loc, [&](int64_t a, int64_t b) {
-        for (int64_t lc = a; lc < b; ++lc)
-          std::memcpy(&cvl[size_t(lc) * nl], cell_verts + int64_t(m->gid(int32_t(lc))) * nl, nl * sizeof(int32_t));
-      });
-      m->n_verts_loc = int32_t(n_verts);
-    } else if (need_verts) {
-      // global vertex -> local vertex: ascending global id over the vertices the local cells touch (threaded mark,
-      // serial prefix sum over the vertices, threaded map)
-      std::vector<int32_t> dense(size_t(n_verts), 0);
-      int32_t* dn = dense.data();
+    m->n_verts_loc = int32_t(v_end - v_begin);
+    if (need_verts) {
+      // global vertex -> local vertex: ascending global id over the vertices of [v_begin, v_end) the local cells touch
+      // (threaded mark, serial prefix sum over that range, threaded map)
+      std::vector<int32_t> dense(size_t(v_end - v_begin), 0);
+      int32_t* dn = dense.data() - v_begin;
       parallel_for(m->n_loc, [&](int64_t a, int64_t b) {
         for (int64_t lc = a; lc < b; ++lc) {
           const int32_t* gv = cell_verts + int64_t(m->gid(int32_t(lc))) * nl;
-          for (int i = 0; i < nl; ++i) dn[size_t(gv[i])] = 1;  // same value from every thread
+          for (int i = 0; i < nl; ++i) dn[gv[i]] = 1;  // same value from every thread
         }
       });
       int32_t nvl = 0;
-      for (int64_t v = 0; v < n_verts; ++v) {
+      for (int64_t v = v_begin; v < v_end; ++v) {
         const int32_t touched = dn[v];
         dn[v] = touched ? nvl : -1;
         nvl += touched;
@@ -317,7 +429,7 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
       parallel_for(m->n_loc, [&](int64_t a, int64_t b) {
         for (int64_t lc = a; lc < b; ++lc) {
           const int32_t* gv = cell_verts + int64_t(m->gid(int32_t(lc))) * nl;
-          for (int i = 0; i < nl; ++i) cvl[size_t(lc) * nl + i] = dn[size_t(gv[i])];
+          for (int i = 0; i < nl; ++i) cvl[size_t(lc) * nl + i] = dn[gv[i]];
         }
       });
       m->n_verts_loc = nvl;
@@ -347,7 +459,6 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
       m->cell_verts.upload(cvl.data() + size_t(m->own0) * nl, size_t(n_own) * nl, s);
       HDD_CUDA(cudaStreamSynchronize(s));
     }
-    m->h_cell_verts_loc.swap(cvl);
 
     pt.lap("vertex incidence");
     // ---- subdomains (grid::Multiscale view): contiguous, subdomain-major cell ranges
@@ -385,10 +496,14 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
         for (int b = 0; b < ns; ++b)
           if (adj[size_t(a) * ns + b]) m->sub_neighbours[size_t(a)].push_back(b);
     } else if (cell_subdomain) {
+      // A rank that owns a part of the cells looks at its own part only: the subdomain-major order is checked over
+      // [cell_begin - 1, cell_end] (all ranks together check everything), the offsets of all subdomains come from binary
+      // searches in the (monotone) array, the neighbouring-subdomain relation is known for the owned subdomains.
       if (cell_subdomain[0] != 0) HDD_THROW(HDD_ERR_WRONG_INPUT, "subdomain numbering must start at 0");
       std::atomic<int64_t> bad{-1};
-      parallel_for(n_cells - 1, [&](int64_t a, int64_t b) {
-        for (int64_t c = a; c < b; ++c) {
+      const int64_t lo = std::max<int64_t>(cell_begin - 1, 0), hi = std::min<int64_t>(cell_end, n_cells - 1);
+      parallel_for(hi - lo, [&](int64_t a, int64_t b) {
+        for (int64_t c = lo + a; c < lo + b; ++c) {
           const int32_t d = cell_subdomain[c + 1] - cell_subdomain[c];
           if (d < 0 || d > 1) bad = c + 1;
         }
@@ -396,19 +511,22 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
       if (bad >= 0)
         HDD_THROW(HDD_ERR_WRONG_INPUT, "cells must be numbered subdomain-major without empty subdomains (cell " << bad.load() << ")");
       m->n_subdomains = cell_subdomain[n_cells - 1] + 1;
+      if (m->n_subdomains < 1) HDD_THROW(HDD_ERR_WRONG_INPUT, "bad subdomain numbering");
       m->sub_cell_offsets.assign(size_t(m->n_subdomains) + 1, 0);
       m->sub_cell_offsets[size_t(m->n_subdomains)] = n_cells;
-      parallel_for(n_cells - 1, [&](int64_t a, int64_t b) {
-        for (int64_t c = a; c < b; ++c)
-          if (cell_subdomain[c + 1] != cell_subdomain[c]) m->sub_cell_offsets[size_t(cell_subdomain[c + 1])] = c + 1;
-      });
-      // neighbouring subdomains: per-thread pair lists, merged
-      const int nt = hdd::worker_count(n_cells);
+      for (int sd = 1; sd < m->n_subdomains; ++sd) {
+        const int32_t* it = std::lower_bound(cell_subdomain, cell_subdomain + n_cells, int32_t(sd));
+        if (it == cell_subdomain + n_cells || *it != sd)
+          HDD_THROW(HDD_ERR_WRONG_INPUT, "cells must be numbered subdomain-major without empty subdomains (subdomain " << sd << ")");
+        m->sub_cell_offsets[size_t(sd)] = it - cell_subdomain;
+      }
+      // neighbouring subdomains of the owned ones: per-thread pair lists over the owned cells, merged
+      const int nt = hdd::worker_count(n_own);
       std::vector<std::vector<std::pair<int32_t, int32_t>>> pairs;
       pairs.resize(size_t(nt));
-      parallel_for_indexed(n_cells, nt, [&](int t, int64_t a, int64_t b) {
+      parallel_for_indexed(n_own, nt, [&](int t, int64_t a, int64_t b) {
         auto& out = pairs[size_t(t)];
-        for (int64_t c = a; c < b; ++c)
+        for (int64_t c = cell_begin + a; c < cell_begin + b; ++c)
           for (int f = 0; f < nf; ++f) {
             const int32_t g = cell_neigh[c * nf + f];
             if (g >= 0 && g < n_cells && cell_subdomain[g] != cell_subdomain[c]) {
@@ -429,66 +547,167 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
       m->sub_cell_offsets = {0, n_cells};
       m->sub_neighbours.assign(1, {});
     }
-    m->sub_dof_offsets.resize(m->sub_cell_offsets.size());
-    for (size_t k = 0; k < m->sub_cell_offsets.size(); ++k) m->sub_dof_offsets[k] = nl * m->sub_cell_offsets[k];
-    // owned subdomains: the owned range must consist of whole subdomains
-    m->sub_first = int(std::lower_bound(m->sub_cell_offsets.begin(), m->sub_cell_offsets.end(), cell_begin) -
-                       m->sub_cell_offsets.begin());
-    m->sub_last = int(std::lower_bound(m->sub_cell_offsets.begin(), m->sub_cell_offsets.end(), cell_end) -
-                      m->sub_cell_offsets.begin());
-    if (n_own > 0 && (m->sub_cell_offsets[size_t(m->sub_first)] != cell_begin ||
-                      m->sub_cell_offsets[size_t(m->sub_last)] != cell_end))
-      HDD_THROW(HDD_ERR_WRONG_INPUT, "the owned cell range must consist of whole subdomains");
-    if (n_own == 0) m->sub_last = m->sub_first;
-    m->sub_diameter.assign(size_t(m->n_subdomains), 0.0);
-    if (kind == HDD_SIMPLEX2D) {  // only the OS2014 estimators (simplex grids) use the diameters
-      for (int sd = m->sub_first; sd < m->sub_last; ++sd) {
-        std::vector<std::pair<double, double>> pts;
-        // the farthest pair lies on the hull, whose vertices sit on faces leaving the subdomain
-        for (int64_t c = m->sub_cell_offsets[size_t(sd)]; c < m->sub_cell_offsets[size_t(sd) + 1]; ++c)
-          for (int f = 0; f < nf; ++f) {
-            const int32_t g = cell_neigh[c * nf + f];
-            if (g >= 0 && cell_subdomain && cell_subdomain[g] == sd) continue;
-            if (g >= 0 && !cell_subdomain) continue;
-            const int* fv = kFaceVertsSimplex[f];
-            for (int e = 0; e < 2; ++e) {
-              const int32_t v = cell_verts[c * nl + fv[e]];
-              pts.emplace_back(xy[2 * v], xy[2 * v + 1]);
-            }
-          }
-        m->sub_diameter[size_t(sd)] = point_set_diameter(pts);
-      }
-    }
-    // chunked segments of the owned cells for deterministic two-level sums
-    {
-      const int64_t chunk = 8192;
-      m->seg_ptr.clear();
-      m->seg_sub.clear();
-      for (int sd = m->sub_first; sd < m->sub_last; ++sd) {
-        const int64_t b = m->sub_cell_offsets[size_t(sd)] - cell_begin, e = m->sub_cell_offsets[size_t(sd) + 1] - cell_begin;
-        for (int64_t k = b; k < e; k += chunk) {
-          m->seg_ptr.push_back(k);
-          m->seg_sub.push_back(sd);
-        }
-      }
-      m->seg_ptr.push_back(n_own);
-      m->d_seg_ptr.upload(m->seg_ptr.data(), m->seg_ptr.size(), s);
-    }
+    finish_mesh(m.get(), xy, cell_verts, cell_neigh, cell_subdomain, pt);
+    *out = m.release();
+  });
+}
 
-    pt.lap("subdomains");
-    // ---- K1 part 1: number of blocks per owned cell and their exclusive prefix sum
-    {
-      DevBuf<int64_t> nblk;
-      nblk.alloc(size_t(n_own) + 1);
-      nblk.zero(s);
-      m->blk_start.alloc(size_t(n_own) + 1);
-      const MeshView v = m->view(nullptr);
-      launch_count_blocks(v, nblk.p, s);
-      exclusive_scan_i64(nblk.p, m->blk_start.p, n_own + 1, s);  // nblk[n_own] = 0 => total in blk_start[n_own]
-      HDD_CUDA(cudaMemcpyAsync(&m->n_blocks, m->blk_start.p + n_own, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-      HDD_CUDA(cudaStreamSynchronize(s));
+int hdd_mesh_create_cube(int64_t nx, int64_t ny, double x0, double x1, double y0, double y1, int px, int py,
+                         int64_t cell_begin, int64_t cell_end, int device, hdd_mesh** out) {
+  return guarded([&] {
+    if (!out) HDD_THROW(HDD_ERR_WRONG_INPUT, "out is NULL");
+    *out = nullptr;
+    if (nx < 1 || ny < 1 || px < 1 || py < 1 || px > nx || py > ny || px * py > 4096)
+      HDD_THROW(HDD_ERR_WRONG_INPUT, "bad grid size " << nx << " x " << ny << " or partition " << px << " x " << py);
+    if (!(x1 > x0) || !(y1 > y0)) HDD_THROW(HDD_ERR_WRONG_INPUT, "upper_right must exceed lower_left");
+    const int64_t n_cells = nx * ny;
+    if (n_cells > INT32_MAX / 8) HDD_THROW(HDD_ERR_WRONG_INPUT, "too many cells for 32-bit DoF indices");
+    if (cell_end < 0) cell_end = n_cells;
+    if (cell_begin < 0 || cell_end > n_cells || cell_begin > cell_end)
+      HDD_THROW(HDD_ERR_WRONG_INPUT, "bad owned cell range [" << cell_begin << ", " << cell_end << ")");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+      HDD_THROW(HDD_ERR_DEVICE, "no CUDA device available (libhdd_b200 has no CPU fallback)");
+    if (device < 0 || device >= n_dev) HDD_THROW(HDD_ERR_DEVICE, "CUDA device " << device << " out of range");
+
+    std::unique_ptr<hdd_mesh> m(new hdd_mesh);
+    m->kind = HDD_CUBE2D;
+    m->nl = m->nf = 4;
+    m->device = device;
+    m->n_global = n_cells;
+    m->cell_begin = cell_begin;
+    m->cell_end = cell_end;
+    m->set_device();
+    HDD_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    cudaStream_t s = m->stream;
+    PhaseTimer pt("hdd_mesh_create_cube", s);
+    const bool whole = (cell_begin == 0 && cell_end == n_cells);
+    const int64_t n_own = cell_end - cell_begin;
+    // boxes: the column / row a box starts at, exactly as the host generator assigns cells to boxes (grids.cpp: box_of)
+    auto starts = [](int64_t n, int parts) {
+      std::vector<int32_t> st(size_t(parts) + 1, int32_t(n));
+      st[0] = 0;
+      for (int64_t i = 0; i < n; ++i) {
+        int b = int((double(i) + 0.5) / double(n) * parts);
+        b = std::min(std::max(b, 0), parts - 1);
+        if (int32_t(i) < st[size_t(b)]) st[size_t(b)] = int32_t(i);
+      }
+      return st;
+    };
+    const std::vector<int32_t> X = starts(nx, px), Y = starts(ny, py);
+    const int ns = px * py;
+    std::vector<int64_t> off(size_t(ns) + 1, 0);
+    for (int b = 0; b < ns; ++b)
+      off[size_t(b) + 1] = off[size_t(b)] + int64_t(X[size_t(b % px) + 1] - X[size_t(b % px)]) * (Y[size_t(b / px) + 1] - Y[size_t(b / px)]);
+    for (int b = 0; b < ns; ++b)
+      if (off[size_t(b) + 1] == off[size_t(b)]) HDD_THROW(HDD_ERR_WRONG_INPUT, "the partition has an empty box");
+    auto box_at = [&](const std::vector<int32_t>& st, int64_t i) { return int(std::upper_bound(st.begin(), st.end(), int32_t(i)) - st.begin()) - 1; };
+    auto cell_id = [&](int64_t i, int64_t j) -> int64_t {
+      if (i < 0 || j < 0 || i >= nx || j >= ny) return -1;
+      const int bx = box_at(X, i), by = box_at(Y, j);
+      return off[size_t(by * px + bx)] + (j - Y[size_t(by)]) * int64_t(X[size_t(bx) + 1] - X[size_t(bx)]) + (i - X[size_t(bx)]);
+    };
+    m->n_subdomains = ns;
+    m->sub_cell_offsets = off;
+    m->sub_neighbours.assign(size_t(ns), {});
+    for (int b = 0; b < ns; ++b) {
+      const int bx = b % px, by = b / px;
+      if (by > 0) m->sub_neighbours[size_t(b)].push_back(b - px);
+      if (bx > 0) m->sub_neighbours[size_t(b)].push_back(b - 1);
+      if (bx + 1 < px) m->sub_neighbours[size_t(b)].push_back(b + 1);
+      if (by + 1 < py) m->sub_neighbours[size_t(b)].push_back(b + px);
     }
-    pt.lap("block offsets");
+    const int sub_first = int(std::lower_bound(off.begin(), off.end(), cell_begin) - off.begin());
+    const int sub_last = int(std::lower_bound(off.begin(), off.end(), cell_end) - off.begin());
+    if (n_own > 0 && (off[size_t(sub_first)] != cell_begin || off[size_t(sub_last)] != cell_end))
+      HDD_THROW(HDD_ERR_WRONG_INPUT, "the owned cell range must consist of whole subdomains");
+    // halo (cells of other ranks sharing a vertex with an owned cell) and the owned cells along the partition boundary:
+    // the one-cell rings outside / inside the owned boxes, in closed form - work proportional to the boundary
+    std::vector<int32_t> halo, bowned;
+    if (!whole) {
+      auto owned = [&](int64_t g) { return g >= cell_begin && g < cell_end; };
+      for (int b = sub_first; b < sub_last; ++b) {
+        const int bx = b % px, by = b / px;
+        const int64_t i0 = X[size_t(bx)], i1 = X[size_t(bx) + 1], j0 = Y[size_t(by)], j1 = Y[size_t(by) + 1];
+        auto visit = [&](int64_t i, int64_t j) {  // a cell of the outer ring and its inner neighbours
+          const int64_t g = cell_id(i, j);
+          if (g < 0 || owned(g)) return;
+          halo.push_back(int32_t(g));
+          for (int dj = -1; dj <= 1; ++dj)
+            for (int di = -1; di <= 1; ++di) {
+              const int64_t q = cell_id(i + di, j + dj);
+              if (q >= 0 && owned(q)) bowned.push_back(int32_t(q));
+            }
+        };
+        for (int64_t i = i0 - 1; i <= i1; ++i) { visit(i, j0 - 1); visit(i, j1); }
+        for (int64_t j = j0; j < j1; ++j) { visit(i0 - 1, j); visit(i1, j); }
+      }
+      std::sort(halo.begin(), halo.end());
+      halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
+      std::sort(bowned.begin(), bowned.end());
+      bowned.erase(std::unique(bowned.begin(), bowned.end()), bowned.end());
+    }
+    const size_t n_lo = size_t(std::lower_bound(halo.begin(), halo.end(), int32_t(cell_begin)) - halo.begin());
+    m->own0 = int32_t(n_lo);
+    m->n_own = int32_t(n_own);
+    m->n_loc = int32_t(halo.size() + n_own);
+    m->whole = whole;
+    m->n_verts_loc = int32_t((nx + 1) * (ny + 1));
+    if (!whole) {
+      m->cgid.resize(size_t(m->n_loc));
+      std::copy(halo.begin(), halo.begin() + n_lo, m->cgid.begin());
+      for (int64_t k = 0; k < n_own; ++k) m->cgid[n_lo + size_t(k)] = int32_t(cell_begin + k);
+      std::copy(halo.begin() + n_lo, halo.end(), m->cgid.begin() + n_lo + n_own);
+      auto verts_of = [&](int64_t g, int32_t* v4) {  // inverse of cell_id, then the vertex ids of hdd_grid_cube
+        const int b = int(std::upper_bound(off.begin(), off.end(), g) - off.begin()) - 1;
+        const int bx = b % px, by = b / px;
+        const int64_t w = X[size_t(bx) + 1] - X[size_t(bx)], r = g - off[size_t(b)];
+        const int64_t i = X[size_t(bx)] + r % w, j = Y[size_t(by)] + r / w;
+        v4[0] = int32_t(j * (nx + 1) + i);
+        v4[1] = v4[0] + 1;
+        v4[2] = int32_t((j + 1) * (nx + 1) + i);
+        v4[3] = v4[2] + 1;
+      };
+      m->h_halo_verts.resize(halo.size() * 4);
+      for (size_t k = 0; k < halo.size(); ++k) verts_of(halo[k], &m->h_halo_verts[4 * k]);
+      m->h_bowned.resize(bowned.size());
+      m->h_bowned_verts.resize(bowned.size() * 4);
+      for (size_t k = 0; k < bowned.size(); ++k) {
+        m->h_bowned[k] = int32_t(bowned[k] - cell_begin) + m->own0;
+        verts_of(bowned[k], &m->h_bowned_verts[4 * k]);
+      }
+    }
+    pt.lap("boxes + halo");
+    // ---- everything per cell is written by one kernel
+    DevBuf<int32_t> d_X, d_Y, d_halo, d_flag;
+    DevBuf<int64_t> d_off;
+    d_X.upload(X.data(), X.size(), s);
+    d_Y.upload(Y.data(), Y.size(), s);
+    d_off.upload(off.data(), off.size(), s);
+    d_halo.upload(halo.data(), halo.size(), s);
+    d_flag.alloc(1);
+    d_flag.zero(s);
+    m->cgeo.alloc(size_t(m->n_loc) * 4);
+    m->neigh.alloc(size_t(n_own) * 4);
+    m->d_cgid.alloc(size_t(m->n_loc));
+    m->cell_v0.alloc(size_t(m->n_loc));
+    m->lex_cell.alloc(size_t(n_cells));
+    HDD_CUDA(cudaMemsetAsync(m->lex_cell.p, 0xFF, size_t(n_cells) * sizeof(int32_t), s));  // -1: not on this rank
+    m->tgeo.alloc(4 * size_t(nx + ny));
+    CubeGridDesc g{int(nx), int(ny), px, py, x0, x1, y0, y1, d_X.p, d_Y.p, d_off.p};
+    launch_cube_fill(g, m->n_loc, m->own0, m->n_own, int32_t(cell_begin), d_halo.p, m->cgeo.p, m->cell_v0.p, m->lex_cell.p,
+                     m->d_cgid.p, m->neigh.p, m->tgeo.p, s);
+    if (!whole)
+      launch_localize_neighbours(m->neigh.p, int64_t(n_own) * 4, int32_t(cell_begin), int32_t(cell_end), d_halo.p, int32_t(n_lo),
+                                 int32_t(halo.size() - n_lo), d_flag.p, s);
+    m->sx = int(nx);
+    m->sy = int(ny);
+    int32_t flag = 0;
+    HDD_CUDA(cudaMemcpyAsync(&flag, d_flag.p, sizeof(flag), cudaMemcpyDeviceToHost, s));
+    HDD_CUDA(cudaStreamSynchronize(s));
+    if (flag & 2) HDD_THROW(HDD_ERR_INTERNAL, "a neighbour of an owned cell is missing from the halo");
+    pt.lap("fill kernels");
+    finish_mesh(m.get(), nullptr, nullptr, nullptr, nullptr, pt);
     *out = m.release();
   });
 }
@@ -586,6 +805,20 @@ int hdd_mesh_attach_comm(hdd_mesh* m, hdd_comm* c) {
       HDD_CUDA(cudaMemcpyAsync(m->sub_diameter.data(), dia.p, m->sub_diameter.size() * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
       HDD_CUDA(cudaStreamSynchronize(m->stream));
     }
+    {  // logically structured grid: every rank checked its own cells and vertices; the verdict has to be the same everywhere
+      DevBuf<double> bad;
+      double f = m->sx > 0 ? 0.0 : 1.0;
+      bad.upload(&f, 1, m->stream);
+      nc.all_reduce_sum(bad.p, 1, m->comm, m->stream);
+      HDD_CUDA(cudaMemcpyAsync(&f, bad.p, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+      HDD_CUDA(cudaStreamSynchronize(m->stream));
+      if (f != 0.0 && m->sx > 0) {
+        m->sx = m->sy = 0;
+        m->cell_v0.release();
+        m->lex_cell.release();
+        m->tgeo.release();
+      }
+    }
     pt.lap("ranges + diameters");
     // halo plan.  Receive: halo cells sorted by global id are grouped by owner => contiguous ranges of the local
     // vector.  Send: owned cells sharing a vertex with a halo cell owned by that peer, sorted by global id - this is
@@ -609,8 +842,7 @@ int hdd_mesh_attach_comm(hdd_mesh* m, hdd_comm* c) {
       it->second.recv_count += 1;
     }
     std::map<int, std::vector<int32_t>> send_cells;
-    compute_send_cells(nl, m->n_verts_loc, m->h_cell_verts_loc.data(), m->own0, int64_t(m->own0) + m->n_own, halo_cells,
-                       halo_owner, send_cells);
+    compute_send_cells_local(nl, m->h_bowned, m->h_bowned_verts.data(), halo_cells, m->h_halo_verts.data(), halo_owner, send_cells);
     std::vector<int32_t> idx;
     m->peers.clear();
     for (auto& kv : peers) {

@@ -74,30 +74,29 @@ __global__ void k_struct_cells(const int32_t* __restrict__ cv, int32_t n_cells, 
   lex_cell[cx + nx * cy] = c;
 }
 
-// vertices: tensor-product coordinates
-__global__ void k_struct_verts(const double* __restrict__ xy, int32_t n_verts, int nx, int32_t* flag) {
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= n_verts) return;
+// vertices [v0, v0 + count): tensor-product coordinates, checked against the one-dimensional coordinate tables
+__global__ void k_struct_verts(const double* __restrict__ xy /* indexed by global vertex id */, int64_t v0, int64_t count, int nx,
+                               const double* __restrict__ xs, const double* __restrict__ ys, int32_t* flag) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const int64_t v = v0 + t;
   const int nx1 = nx + 1;
   const double2 p = __ldg(reinterpret_cast<const double2*>(xy) + v);
-  const double2 px = __ldg(reinterpret_cast<const double2*>(xy) + v % nx1);
-  const double2 py = __ldg(reinterpret_cast<const double2*>(xy) + (v / nx1) * nx1);
-  if (p.x != px.x || p.y != py.y) atomicOr(flag, 2);
+  if (p.x != __ldg(xs + v % nx1) || p.y != __ldg(ys + v / nx1)) atomicOr(flag, 2);
 }
 
-// one-dimensional geometry of the tensor grid from the vertex coordinates: {x0, hx, 1/hx, -} per column followed by
-// {y0, hy, 1/hy, -} per row (the reciprocals save the assembly kernel six of its ten fp64 divisions per cell)
-__global__ void k_struct_geo(const double* __restrict__ xy, int nx, int ny, double* __restrict__ tgeo) {
+// one-dimensional geometry of the tensor grid: {x0, hx, 1/hx, -} per column followed by {y0, hy, 1/hy, -} per row
+// (the reciprocals save the assembly kernel six of its ten fp64 divisions per cell)
+__global__ void k_struct_geo(const double* __restrict__ xs, const double* __restrict__ ys, int nx, int ny, double* __restrict__ tgeo) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nx + ny) return;
-  const int nx1 = nx + 1;
   double4* out = reinterpret_cast<double4*>(tgeo);
   if (t < nx) {
-    const double x0 = xy[2 * size_t(t)], x1 = xy[2 * size_t(t + 1)];
+    const double x0 = xs[t], x1 = xs[t + 1];
     out[t] = make_double4(x0, x1 - x0, 1.0 / (x1 - x0), 0.0);
   } else {
     const int r = t - nx;
-    const double y0 = xy[2 * size_t(r) * nx1 + 1], y1 = xy[2 * size_t(r + 1) * nx1 + 1];
+    const double y0 = ys[r], y1 = ys[r + 1];
     out[t] = make_double4(y0, y1 - y0, 1.0 / (y1 - y0), 0.0);
   }
 }
@@ -599,7 +598,10 @@ void mg_strip_plan(int ny, int c0, int c1, int n_dist, MgDist& d) {
   d.ghost = std::max(c0 - d.b_lo[0], d.b_hi[0] - c1);
 }
 
-void mg_detect_structure(hdd_mesh* m, const double* xy_host, const double* xy_dev, const int32_t* cv_dev, int64_t n_verts) {
+// xy_dev is addressed by global vertex id and holds the vertices [v_begin, v_end) only (the ones the local cells touch):
+// every rank checks its own cells and vertices; hdd_mesh_attach_comm makes the verdict collective.
+void mg_detect_structure(hdd_mesh* m, const double* xy_host, const double* xy_dev, int64_t v_begin, int64_t v_end,
+                         const int32_t* cv_dev, int64_t n_verts) {
   m->sx = m->sy = 0;
   if (m->kind != HDD_CUBE2D) return;
   int64_t nx1 = 1;
@@ -608,6 +610,15 @@ void mg_detect_structure(hdd_mesh* m, const double* xy_host, const double* xy_de
   const int64_t nx = nx1 - 1, ny = n_verts / nx1 - 1;
   if (ny < 1 || nx * ny != m->n_global) return;
   cudaStream_t s = m->stream;
+  // column / row coordinates from the first grid row and the first grid column of the caller's array
+  std::vector<double> xs, ys;
+  xs.resize(size_t(nx1));
+  ys.resize(size_t(ny) + 1);
+  for (int64_t i = 0; i < nx1; ++i) xs[size_t(i)] = xy_host[2 * i];
+  for (int64_t j = 0; j <= ny; ++j) ys[size_t(j)] = xy_host[2 * j * nx1 + 1];
+  DevBuf<double> d_xs, d_ys;
+  d_xs.upload(xs.data(), xs.size(), s);
+  d_ys.upload(ys.data(), ys.size(), s);
   m->cell_v0.alloc(size_t(m->n_loc));
   m->lex_cell.alloc(size_t(m->n_global));
   HDD_CUDA(cudaMemsetAsync(m->lex_cell.p, 0xFF, size_t(m->n_global) * sizeof(int32_t), s));  // -1: not on this rank
@@ -615,9 +626,9 @@ void mg_detect_structure(hdd_mesh* m, const double* xy_host, const double* xy_de
   flag.alloc(1);
   flag.zero(s);
   k_struct_cells<<<blocks_for(m->n_loc), kMgThreads, 0, s>>>(cv_dev, m->n_loc, int(nx), int(ny), m->cell_v0.p, m->lex_cell.p, flag.p);
-  k_struct_verts<<<blocks_for(n_verts), kMgThreads, 0, s>>>(xy_dev, int32_t(n_verts), int(nx), flag.p);
+  k_struct_verts<<<blocks_for(v_end - v_begin), kMgThreads, 0, s>>>(xy_dev, v_begin, v_end - v_begin, int(nx), d_xs.p, d_ys.p, flag.p);
   m->tgeo.alloc(4 * size_t(nx + ny));
-  k_struct_geo<<<blocks_for(nx + ny), kMgThreads, 0, s>>>(xy_dev, int(nx), int(ny), m->tgeo.p);
+  k_struct_geo<<<blocks_for(nx + ny), kMgThreads, 0, s>>>(d_xs.p, d_ys.p, int(nx), int(ny), m->tgeo.p);
   count_launch(3);
   int32_t f = 0;
   HDD_CUDA(cudaMemcpyAsync(&f, flag.p, sizeof(f), cudaMemcpyDeviceToHost, s));

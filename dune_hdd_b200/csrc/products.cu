@@ -253,8 +253,8 @@ int hdd_product_apply2(hdd_swipdg* h, const char* id, const double* mu, int mu_s
     if (h->prod_tmp.n < 2 * rows) h->prod_tmp.alloc(2 * rows);
     double* y = h->prod_tmp.p;          // P v
     double* u = h->prod_tmp.p + rows;   // u
-    HDD_CUDA(cudaMemcpyAsync(h->tmp_local.p + size_t(m->own0) * nl, v_host, rows * sizeof(double), cudaMemcpyHostToDevice, s));
-    HDD_CUDA(cudaMemcpyAsync(u, u_host, rows * sizeof(double), cudaMemcpyHostToDevice, s));
+    HDD_CUDA(h2d_async(h->tmp_local.p + size_t(m->own0) * nl, v_host, rows * sizeof(double), s));
+    HDD_CUDA(h2d_async(u, u_host, rows * sizeof(double), s));
     if (P->volume_pattern) {
       launch_block_spmv(h->view(), vals, h->tmp_local.p + size_t(m->own0) * nl, y, s);
     } else {

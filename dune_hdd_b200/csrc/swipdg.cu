@@ -446,7 +446,7 @@ void run_indicators(hdd_swipdg* h, const double* u_host, const hdd_parameters* p
   const size_t loc = size_t(m->n_loc) * nl, rows = size_t(h->n_rows);
   if (!h->tmp_local.p) { h->tmp_local.alloc(loc); h->tmp_local.zero(s); }
   if (u_host) {
-    HDD_CUDA(cudaMemcpyAsync(h->tmp_local.p + size_t(m->own0) * nl, u_host, rows * sizeof(double), cudaMemcpyHostToDevice, s));
+    HDD_CUDA(h2d_async(h->tmp_local.p + size_t(m->own0) * nl, u_host, rows * sizeof(double), s));
   } else {
     if (!h->have_solution) HDD_THROW(HDD_ERR_USING_THIS_WRONG, "no vector given and no solution available");
     HDD_CUDA(cudaMemcpyAsync(h->tmp_local.p + size_t(m->own0) * nl, h->x.p, rows * sizeof(double), cudaMemcpyDeviceToDevice, s));
@@ -772,7 +772,7 @@ int hdd_apply(hdd_swipdg* h, const double* mu, int mu_size, const double* x_host
     if (!h->tmp_local.p) { h->tmp_local.alloc(loc); h->tmp_local.zero(s); }
     DevBuf<double> y;
     y.alloc(rows);
-    HDD_CUDA(cudaMemcpyAsync(h->tmp_local.p + size_t(m->own0) * h->nl, x_host, rows * sizeof(double), cudaMemcpyHostToDevice, s));
+    HDD_CUDA(h2d_async(h->tmp_local.p + size_t(m->own0) * h->nl, x_host, rows * sizeof(double), s));
     m->halo_exchange(h->tmp_local.p, h->nl);
     launch_spmv(h->view(), vals, h->tmp_local.p, y.p, s);
     HDD_CUDA(cudaMemcpyAsync(y_host, y.p, rows * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -810,7 +810,7 @@ int hdd_residual(hdd_swipdg* h, const double* mu, int mu_size, double* relative_
       HDD_CUDA(cudaMemcpyAsync(&amax_local, neg.p, sizeof(double), cudaMemcpyDeviceToHost, s));
       HDD_CUDA(cudaStreamSynchronize(s));
       amax_local = -amax_local;
-      HDD_CUDA(cudaMemcpyAsync(&h->sc.p->red[3], &amax_local, sizeof(double), cudaMemcpyHostToDevice, s));
+      HDD_CUDA(h2d_async(&h->sc.p->red[3], &amax_local, sizeof(double), s));
       HDD_CUDA(cudaStreamSynchronize(s));
     }
     double red[4] = {0.0, 0.0, 0.0, 0.0};
@@ -1334,7 +1334,7 @@ int hdd_profile_kernel(hdd_swipdg* h, int which, int reps, double* avg_seconds) 
       // un-latch the convergence flag of parity 0 so that the kernels do their work; the vectors are scratch now
       CgScalars sc = *h->sc_host;
       sc.done[0] = 0; sc.done[1] = 0; sc.rz[0] = 1.0; sc.red[0] = 1.0; sc.red[1] = 1.0; sc.max_it = 1 << 30;
-      HDD_CUDA(cudaMemcpyAsync(h->sc.p, &sc, sizeof(sc), cudaMemcpyHostToDevice, s));
+      HDD_CUDA(h2d_async(h->sc.p, &sc, sizeof(sc), s));
       h->have_solution = false;
     }
     auto launch = [&]() {

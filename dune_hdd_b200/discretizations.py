@@ -192,10 +192,20 @@ class SWIPDG:
         self._cache = {}
         cb, ce = (0, grid.n_cells) if cell_range is None else cell_range
         bt = None if boundary_info is None else np.ascontiguousarray(boundary_info, dtype=np.uint8)
-        _check(L.hdd_mesh_create(grid.kind, C.c_int64(grid.n_cells), C.c_int64(grid.n_verts), capi.ptr(grid.xy),
-                                 capi.ptr(grid.cell_verts, C.c_int32), capi.ptr(grid.cell_neigh, C.c_int32),
-                                 capi.ptr(grid.cell_subdomain, C.c_int32), capi.ptr(bt, C.c_uint8), C.c_int64(cb),
-                                 C.c_int64(ce), device, C.byref(self._mesh)))
+        from .grids import CubeProvider
+        if isinstance(grid, CubeProvider) and bt is None:
+            # the grid provider's three vectors go to the device, the grid tables are written there
+            _check(L.hdd_mesh_create_cube(C.c_int64(grid.nx), C.c_int64(grid.ny), C.c_double(grid.lower_left[0]),
+                                          C.c_double(grid.upper_right[0]), C.c_double(grid.lower_left[1]),
+                                          C.c_double(grid.upper_right[1]), grid.partitions[0], grid.partitions[1],
+                                          C.c_int64(cb), C.c_int64(ce), device, C.byref(self._mesh)))
+        else:
+            if isinstance(grid, CubeProvider):
+                grid = self.grid = grid.materialize()
+            _check(L.hdd_mesh_create(grid.kind, C.c_int64(grid.n_cells), C.c_int64(grid.n_verts), capi.ptr(grid.xy),
+                                     capi.ptr(grid.cell_verts, C.c_int32), capi.ptr(grid.cell_neigh, C.c_int32),
+                                     capi.ptr(grid.cell_subdomain, C.c_int32), capi.ptr(bt, C.c_uint8), C.c_int64(cb),
+                                     C.c_int64(ce), device, C.byref(self._mesh)))
         self._comm = comm  # keep the communicator alive as long as the mesh
         if comm is not None:
             _check(L.hdd_mesh_attach_comm(self._mesh, comm.handle))
@@ -327,7 +337,8 @@ class SWIPDG:
         from . import vtk
         if self.cell_range != (0, self.grid.n_cells):
             raise requirements_not_met(capi.HDD_ERR_REQUIREMENTS_NOT_MET, "visualize needs the whole grid on this process")
-        return vtk.write_vtu(filename, self.grid, self.polorder, {name: vector})
+        grid = self.grid.materialize() if hasattr(self.grid, "materialize") else self.grid
+        return vtk.write_vtu(filename, grid, self.polorder, {name: vector})
 
     def parametric(self):
         return self.problem.parametric()

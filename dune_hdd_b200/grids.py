@@ -49,6 +49,42 @@ class Grid:
         return np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
 
 
+class CubeProvider:
+    """``Stuff::Grid::Providers::Cube(lower_left, upper_right, num_elements)`` + the ``[px py 1]`` multiscale partition as a
+    description only (testcases/ESV2007.hh:123-127, :150-163): the discretization hands the three vectors to
+    ``hdd_mesh_create_cube`` and the grid tables are written on the device.  Same grid and numbering as ``cube(...)``;
+    ``materialize()`` gives the flat host arrays (for VTK output or the oracle)."""
+    kind = CUBE2D
+    n_loc = 4
+
+    def __init__(self, nx, ny=None, lower_left=(-1.0, -1.0), upper_right=(1.0, 1.0), partitions=(1, 1)):
+        self.nx, self.ny = int(nx), int(nx if ny is None else ny)
+        self.lower_left, self.upper_right = tuple(map(float, lower_left)), tuple(map(float, upper_right))
+        self.partitions = (int(partitions[0]), int(partitions[1]))
+        self._grid = None
+
+    n_cells = property(lambda self: self.nx * self.ny)
+    n_verts = property(lambda self: (self.nx + 1) * (self.ny + 1))
+    n_dofs = property(lambda self: 4 * self.nx * self.ny)
+    n_subdomains = property(lambda self: self.partitions[0] * self.partitions[1])
+    cell_subdomain = property(lambda self: True)  # "has subdomains" for BlockSWIPDG; the array lives in materialize()
+
+    @staticmethod
+    def _starts(n, parts):
+        b = np.clip(((np.arange(n) + 0.5) / n * parts).astype(np.int64), 0, parts - 1)
+        return np.concatenate([np.searchsorted(b, np.arange(parts)), [n]]).astype(np.int64)
+
+    def subdomain_cell_offsets(self):
+        X, Y = self._starts(self.nx, self.partitions[0]), self._starts(self.ny, self.partitions[1])
+        sizes = (np.diff(Y)[:, None] * np.diff(X)[None, :]).ravel()
+        return np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+
+    def materialize(self):
+        if self._grid is None:
+            self._grid = cube(self.nx, self.ny, self.lower_left, self.upper_right, self.partitions)
+        return self._grid
+
+
 def cube(nx, ny=None, lower_left=(-1.0, -1.0), upper_right=(1.0, 1.0), partitions=(1, 1), pinned=False):
     """SGrid<2,2> via Providers::Cube(lower_left, upper_right, num_elements): nx*ny axis-parallel cells, x fastest.
     pinned: allocate the arrays in page-locked host memory (hdd_host_alloc) so that the upload runs at link speed."""

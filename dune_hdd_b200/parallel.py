@@ -22,16 +22,23 @@ def rank_cell_offsets(grid, world_size):
     return np.array([off[s] for s in slabs], dtype=np.int64)
 
 
-def partition_plan(grid, world_size, rank, offsets=None):
-    """host-side halo / send plan of `rank` (hdd_partition_plan): (halo_cells, {peer: send_cells})"""
+def partition_plan(grid, world_size, rank, offsets=None, local=False):
+    """host-side halo / send plan of `rank` (hdd_partition_plan): (halo_cells, {peer: send_cells}).
+    local: the owned-side walk hdd_mesh_create uses on N > 1 ranks (hdd_partition_plan_local) - same result"""
     L = capi.lib()
     off = rank_cell_offsets(grid, world_size) if offsets is None else np.ascontiguousarray(offsets, dtype=np.int64)
     halo_p, send_p = C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)()
     n_halo = C.c_int64()
     send_off = np.zeros(world_size + 1, np.int64)
-    capi.check(L.hdd_partition_plan(grid.kind, C.c_int64(grid.n_cells), C.c_int64(grid.n_verts),
-                                    capi.ptr(grid.cell_verts, C.c_int32), world_size, capi.ptr(off, C.c_int64), rank,
-                                    C.byref(halo_p), C.byref(n_halo), C.byref(send_p), capi.ptr(send_off, C.c_int64)))
+    if local:
+        capi.check(L.hdd_partition_plan_local(grid.kind, C.c_int64(grid.n_cells), capi.ptr(grid.cell_verts, C.c_int32),
+                                              capi.ptr(grid.cell_neigh, C.c_int32), world_size, capi.ptr(off, C.c_int64),
+                                              rank, C.byref(halo_p), C.byref(n_halo), C.byref(send_p),
+                                              capi.ptr(send_off, C.c_int64)))
+    else:
+        capi.check(L.hdd_partition_plan(grid.kind, C.c_int64(grid.n_cells), C.c_int64(grid.n_verts),
+                                        capi.ptr(grid.cell_verts, C.c_int32), world_size, capi.ptr(off, C.c_int64), rank,
+                                        C.byref(halo_p), C.byref(n_halo), C.byref(send_p), capi.ptr(send_off, C.c_int64)))
     try:
         halo = np.array([halo_p[i] for i in range(n_halo.value)], dtype=np.int32)
         flat = np.array([send_p[i] for i in range(send_off[-1])], dtype=np.int32)

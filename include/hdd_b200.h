@@ -77,6 +77,14 @@ typedef struct hdd_mesh hdd_mesh;
 int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy, const int32_t* cell_verts,
                     const int32_t* cell_neigh, const int32_t* cell_subdomain, const uint8_t* boundary_type,
                     int64_t cell_begin, int64_t cell_end, int device, hdd_mesh** out);
+/* Stuff::Grid::Providers::Cube< SGrid<2,2> >(lower_left, upper_right, num_elements) with the [px py 1] partition of
+ * grid::Multiscale, the way the reference's structured test cases get their grids (testcases/ESV2007.hh:123-127, :150-163;
+ * testcases/spe10.hh:262-268, :301-307): nothing but these numbers travels to the device, where one kernel writes the
+ * geometry, neighbour and numbering tables of the cells this rank keeps.  Same grid, same subdomain-major cell numbering,
+ * bit-identical coordinates as hdd_grid_cube + hdd_mesh_create (tests compare the assembled matrices).  cell_end < 0 means
+ * "all cells"; the owned range must consist of whole subdomains. */
+int hdd_mesh_create_cube(int64_t nx, int64_t ny, double x0, double x1, double y0, double y1, int px, int py,
+                         int64_t cell_begin, int64_t cell_end, int device, hdd_mesh** out);
 int hdd_mesh_destroy(hdd_mesh* mesh);
 /* Page-locked host memory for the grid / solution arrays handed to this library: copies from and to it run at PCIe /
  * NVLink-C2C speed instead of being staged through the driver's bounce buffers (4096^2 grid: 0.87 GB of arrays).
@@ -311,6 +319,12 @@ int hdd_mesh_attach_comm(hdd_mesh* mesh, hdd_comm* comm);
 int hdd_partition_plan(int kind, int64_t n_cells, int64_t n_verts, const int32_t* cell_verts, int world_size,
                        const int64_t* rank_cell_offsets, int rank, int32_t** halo_cells, int64_t* n_halo,
                        int32_t** send_cells, int64_t* send_offsets);
+/* The same plan computed the way hdd_mesh_create does it on N > 1 ranks: from the owned side only, walking face neighbours
+ * across the partition faces (work proportional to the partition boundary, no sweep over the other ranks' cells); needs
+ * the cell -> neighbour array.  Must equal hdd_partition_plan (tests/test_multi_gloo.py). */
+int hdd_partition_plan_local(int kind, int64_t n_cells, const int32_t* cell_verts, const int32_t* cell_neigh, int world_size,
+                             const int64_t* rank_cell_offsets, int rank, int32_t** halo_cells, int64_t* n_halo,
+                             int32_t** send_cells, int64_t* send_offsets);
 int hdd_free(void* p);
 /* Host arithmetic of the strip-distributed multigrid preconditioner ("cg.mg" on N GPUs), exported for the CPU
  * tests: the inclusive vertex-row ranges the sweeps of the n_dist finest vertex levels run on for the rank owning the cell
@@ -339,6 +353,8 @@ int hdd_expression_evaluate(const char* expression, const char* variable, const 
 /* ---- counters --------------------------------------------------------------------------------------------------- */
 /* number of kernels this library launched since process start (bench.py's gpu_launches) */
 int64_t hdd_kernel_launches(void);
+/* bytes this library copied from host to device memory since process start (bench.py's e2e.h2d_bytes_per_step) */
+int64_t hdd_h2d_bytes(void);
 
 #ifdef __cplusplus
 }

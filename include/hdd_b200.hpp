@@ -258,6 +258,11 @@ class SWIPDG {
                           grid.cell_neigh.data(), grid.cell_subdomain.empty() ? nullptr : grid.cell_subdomain.data(),
                           grid.boundary_type.empty() ? nullptr : grid.boundary_type.data(), cell_begin, cell_end, device,
                           &mesh_));
+    finish_construction(problem, polorder, comm, only_these_products);
+  }
+
+ private:
+  void finish_construction(const Problem& problem, int polorder, hdd_comm* comm, const std::vector<std::string>& only_these_products) {
     try {
       if (comm) check(hdd_mesh_attach_comm(mesh_, comm));
       internal::CAffine fac(problem.diffusion_factor), frc(problem.force), dir(problem.dirichlet), neu(problem.neumann);
@@ -277,6 +282,22 @@ class SWIPDG {
       hdd_mesh_destroy(mesh_);
       throw;
     }
+  }
+
+ public:
+  // Stuff::Grid::Providers::Cube(lower_left, upper_right, num_elements) with a [px py 1] multiscale partition
+  // (testcases/ESV2007.hh:123-127, :150-163): the grid tables are written on the device (hdd_mesh_create_cube)
+  struct CubeProvider {
+    int64_t nx = 1, ny = 1;
+    double lower_left[2] = {-1.0, -1.0}, upper_right[2] = {1.0, 1.0};
+    int px = 1, py = 1;
+  };
+  SWIPDG(const CubeProvider& grid, const Problem& problem, int polorder = 1, int device = 0, hdd_comm* comm = nullptr,
+         int64_t cell_begin = 0, int64_t cell_end = -1, const std::vector<std::string>& only_these_products = {})
+      : n_loc_((polorder + 1) * (polorder + 1)) {
+    check(hdd_mesh_create_cube(grid.nx, grid.ny, grid.lower_left[0], grid.upper_right[0], grid.lower_left[1], grid.upper_right[1],
+                               grid.px, grid.py, cell_begin, cell_end, device, &mesh_));
+    finish_construction(problem, polorder, comm, only_these_products);
   }
   SWIPDG(const SWIPDG&) = delete;
   SWIPDG& operator=(const SWIPDG&) = delete;

@@ -96,6 +96,20 @@ def main():
             assert loc.shape == (16,) and np.all(loc > 0)
             if rank == 0:
                 print("estimates", etas)
+        if kind == "sgrid" and n == 256:
+            # the same grid from the cube provider (tables written on the device, rank-local closed forms)
+            pr = hdd.grids.CubeProvider(n, partitions=(8, 8))
+            dp = hdd.BlockSWIPDG(pr, prob, device=lr, cell_range=rng, comm=comm)
+            dp.init()
+            rp_p, col_p = dp.pattern()
+            assert np.array_equal(rp_p, rp_l) and np.array_equal(col_p, col_l), "cube provider pattern"
+            assert np.array_equal(dp.system_matrix().affine_part(), Al), "cube provider entries"
+            up, ip = dp.solve({"type": "cg.mg", "precision": 1e-13, "max_iter": 500}, return_info=True)
+            assert np.abs(up - u_ref[r0:r1]).max() <= 1e-8 * np.abs(u_ref).max(), "cube provider cg.mg solution"
+            assert ip["iterations"] == im["iterations"], "cube provider cg.mg iterations"
+            uq = dp.solve({"type": "cg.diagonal", "precision": 1e-13, "max_iter": 50000})
+            assert np.abs(uq - u_ref[r0:r1]).max() <= 1e-8 * np.abs(u_ref).max(), "cube provider Jacobi solution"
+            del dp
         if rank == 0:
             print("multi-GPU check ok:", kind, n, "world", world, "iterations", info["iterations"])
         del d

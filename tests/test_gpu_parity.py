@@ -848,3 +848,25 @@ def test_estimator_with_expression_factor_and_many_segments(gpu):
         assert np.abs(ind[k] - ind_ref[k]).max() <= SOL_TOL * np.abs(ind_ref[k]).max(), k
     assert abs(d.estimate(u, "eta_NC_OS2014", prm) - np.sqrt(ind_ref["nc2"].sum())) <= SOL_TOL
     assert abs(d.estimate(u, "eta_DF_OS2014", prm) - np.sqrt(ind_ref["df2"].sum())) <= SOL_TOL * np.sqrt(ind_ref["df2"].sum())
+
+
+@pytest.mark.parametrize("nx,ny,parts", [(16, 16, (1, 1)), (24, 16, (4, 2)), (10, 7, (3, 2)), (64, 64, (8, 8))])
+def test_cube_provider_on_the_device_equals_the_flat_array_path(gpu, nx, ny, parts):
+    """hdd_mesh_create_cube (Stuff::Grid::Providers::Cube: three vectors, tables written on the device) against
+    hdd_mesh_create from the host arrays of the same grid: identical pattern, bit-identical entries, same solution"""
+    ll, ur = (-1.0, 0.0), (1.0, 2.0 * ny / nx)
+    p = grids.CubeProvider(nx, ny, ll, ur, parts)
+    g = grids.cube(nx, ny, ll, ur, parts)
+    da, db = hdd.BlockSWIPDG(p, problems.ESV2007()), hdd.BlockSWIPDG(g, problems.ESV2007())
+    da.init()
+    db.init()
+    (rpa, cola), (rpb, colb) = da.pattern(), db.pattern()
+    assert np.array_equal(rpa, rpb) and np.array_equal(cola, colb)
+    assert np.array_equal(da.system_matrix().affine_part(), db.system_matrix().affine_part())
+    assert np.array_equal(da.rhs().affine_part(), db.rhs().affine_part())
+    assert np.array_equal(da.subdomain_offsets(), db.subdomain_offsets())
+    for ss in range(da.num_subdomains()):
+        assert da.neighbouring_subdomains(ss) == db.neighbouring_subdomains(ss)
+    opts = {"type": "cg.mg" if min(nx, ny) >= 16 else "cg.blockdiagonal", "precision": 1e-12, "max_iter": 5000}
+    ua, ub = da.solve(opts), db.solve(opts)
+    assert rel(ua, ub) <= 1e-12

@@ -235,3 +235,15 @@ def test_father_search_finds_the_containing_coarse_cell():
         assert inside.all()
     with pytest.raises(capi.HddError):
         grids.fathers(grids.cube(4, lower_left=(0.0, 0.0)), grids.cube(8))
+
+
+@pytest.mark.parametrize("nx,ny,parts", [(8, 8, (1, 1)), (16, 12, (4, 3)), (10, 7, (3, 2)), (64, 64, (8, 8)), (5, 9, (5, 3))])
+def test_cube_provider_describes_the_same_partition_as_the_flat_arrays(nx, ny, parts):
+    """grids.CubeProvider (three vectors + partition, hdd_mesh_create_cube) against grids.cube (flat host arrays)"""
+    from dune_hdd_b200 import grids
+    p = grids.CubeProvider(nx, ny, partitions=parts)
+    g = grids.cube(nx, ny, partitions=parts)
+    assert (p.n_cells, p.n_verts, p.n_dofs, p.n_subdomains) == (g.n_cells, g.n_verts, g.n_dofs, g.n_subdomains)
+    assert np.array_equal(p.subdomain_cell_offsets(), g.subdomain_cell_offsets())
+    m = p.materialize()
+    assert np.array_equal(m.cell_verts, g.cell_verts) and np.array_equal(m.cell_subdomain, g.cell_subdomain)

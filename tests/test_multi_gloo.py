@@ -88,3 +88,25 @@ def test_partition_and_halo_exchange_over_gloo(kind, n, world):
     out = mp.Manager().dict()
     mp.spawn(_worker, args=(world, port, kind, n, out), nprocs=world, join=True)
     assert sorted(out.keys()) == list(range(world))
+
+
+@pytest.mark.parametrize("kind,n,parts", [("alu", 8, (4, 4)), ("alu", 16, (8, 8)), ("sgrid", 32, (8, 8)), ("sgrid", 24, (4, 4)),
+                                          ("sgrid", 12, (1, 1)), ("alu", 6, (3, 2))])
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_owned_side_halo_walk_equals_the_full_sweep(kind, n, parts, world):
+    """hdd_mesh_create on N > 1 ranks finds halo and send lists from the owned side (walk over the partition boundary);
+    the device-free full sweep of hdd_partition_plan is the specification"""
+    from dune_hdd_b200 import grids, parallel
+    g = (grids.simplex if kind == "alu" else grids.cube)(n, partitions=parts)
+    if g.n_subdomains < world:
+        # uneven hand-made ranges (any contiguous split is allowed by the plan functions)
+        off = np.linspace(0, g.n_cells, world + 1).astype(np.int64)
+    else:
+        off = parallel.rank_cell_offsets(g, world)
+    for rank in range(world):
+        halo, send = parallel.partition_plan(g, world, rank, offsets=off)
+        halo_l, send_l = parallel.partition_plan(g, world, rank, offsets=off, local=True)
+        assert np.array_equal(halo, halo_l), (rank, len(halo), len(halo_l))
+        assert sorted(send) == sorted(send_l)
+        for peer in send:
+            assert np.array_equal(send[peer], send_l[peer]), (rank, peer)
