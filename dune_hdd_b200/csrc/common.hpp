@@ -124,6 +124,16 @@ inline cudaError_t h2d_async(void* dst, const void* src, size_t bytes, cudaStrea
   return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s);
 }
 
+// Device memory of the library comes from a small caching allocator (mesh.cu): a freed block is kept and handed to the next
+// request of the same size on the same device.  Discretizations are created and destroyed per solve in the reference's
+// studies (test/linearelliptic.hh:150-160) with the same sizes every time, and cudaMalloc / cudaFree synchronise the device
+// and - once peer access is enabled by NCCL or CUDA IPC - map / unmap the block on every peer, which costs milliseconds per
+// call.  The cache holds at most kDevCacheFraction of the device memory (least recently freed blocks are released first) and
+// is emptied when an allocation fails.  HDD_DEV_CACHE=0 turns it off.
+void* dev_alloc(size_t bytes);
+void dev_free(void* p, size_t bytes);
+void dev_cache_release_all();
+
 // RAII device buffer
 template <class T>
 struct DevBuf {
@@ -139,7 +149,7 @@ struct DevBuf {
   }
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) dev_free(p, n * sizeof(T) + 32);
     p = nullptr;
     n = 0;
   }
@@ -147,7 +157,7 @@ struct DevBuf {
     release();
     if (count == 0) count = 1;
     // 32 bytes of slack: the bulk-copy SpMV rounds its 8-byte aligned row blocks out to 16-byte boundaries
-    HDD_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T) + 32));
+    p = static_cast<T*>(dev_alloc(count * sizeof(T) + 32));
     n = count;
   }
   void upload(const T* host, size_t count, cudaStream_t s) {

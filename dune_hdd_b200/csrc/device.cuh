@@ -18,6 +18,7 @@ struct DevFn {
   Program prog;
   int separable;       // expression == px(x[0]) * py(x[1])
   Program px, py;
+  FastFn fast;         // the expression as a sum of products of elementary functions of affine arguments, if it fits
 };
 
 // sum_k theta[k] * fn[k]: a frozen affinely decomposed function (problem.with_mu(mu), estimators/swipdg.hh:134).
@@ -52,6 +53,7 @@ struct MeshView {
 __device__ __forceinline__ double fn_eval(const DevFn& f, int cell, double x, double y) {
   if (f.kind == HDD_FN_CONSTANT) return f.value;
   if (f.kind == HDD_FN_CELLWISE) return __ldg(f.cell + cell);
+  if (f.fast.n_terms > 0) return eval_fast(f.fast, x, y);
   const double v[2] = {x, y};
   return eval_program(f.prog, v);
 }

@@ -194,6 +194,93 @@ struct Parser {
     }
     return m;
   }
+  // ---- fast form (see expr.hpp): normal form = list of terms, term = coefficient * list of (kind, a, b, d) factors
+  struct NfFactor { int kind; double a, b, d; };
+  struct NfTerm { double c; std::vector<NfFactor> f; };
+  typedef std::vector<NfTerm> Nf;
+  static bool nf_affine(const Nf& n, double& a, double& b, double& d) {
+    a = b = d = 0.0;
+    for (const NfTerm& t : n) {
+      if (t.f.empty()) { d += t.c; continue; }
+      if (t.f.size() != 1 || t.f[0].kind != FAST_ID) return false;
+      a += t.c * t.f[0].a;
+      b += t.c * t.f[0].b;
+      d += t.c * t.f[0].d;
+    }
+    return true;
+  }
+  bool to_nf(int n, Nf& out) const {
+    const Node& x = nodes[size_t(n)];
+    out.clear();
+    switch (x.op) {
+      case OP_CONST: out.push_back({x.value, {}}); return true;
+      case OP_VAR0: out.push_back({1.0, {{FAST_ID, 1.0, 0.0, 0.0}}}); return true;
+      case OP_VAR1: out.push_back({1.0, {{FAST_ID, 0.0, 1.0, 0.0}}}); return true;
+      case OP_ADD: case OP_SUB: {
+        Nf a, b;
+        if (!to_nf(x.a, a) || !to_nf(x.b, b)) return false;
+        out = a;
+        for (NfTerm t : b) { if (x.op == OP_SUB) t.c = -t.c; out.push_back(t); }
+        return out.size() <= size_t(kFastTerms);
+      }
+      case OP_NEG: {
+        if (!to_nf(x.a, out)) return false;
+        for (NfTerm& t : out) t.c = -t.c;
+        return true;
+      }
+      case OP_MUL: {
+        Nf a, b;
+        if (!to_nf(x.a, a) || !to_nf(x.b, b)) return false;
+        for (const NfTerm& ta : a)
+          for (const NfTerm& tb : b) {
+            NfTerm t{ta.c * tb.c, ta.f};
+            t.f.insert(t.f.end(), tb.f.begin(), tb.f.end());
+            if (t.f.size() > size_t(kFastFactors)) return false;
+            out.push_back(t);
+          }
+        return out.size() <= size_t(kFastTerms);
+      }
+      case OP_DIV: {
+        Nf a, b;
+        if (!to_nf(x.a, a) || !to_nf(x.b, b)) return false;
+        if (b.size() != 1 || !b[0].f.empty() || b[0].c == 0.0) return false;  // division by a constant only
+        out = a;
+        for (NfTerm& t : out) t.c /= b[0].c;
+        return true;
+      }
+      case OP_POW: {
+        Nf a, b;
+        if (!to_nf(x.a, a) || !to_nf(x.b, b)) return false;
+        if (b.size() != 1 || !b[0].f.empty()) return false;
+        const double e = b[0].c;
+        if (e != 2.0 && e != 3.0 && e != 1.0) return false;
+        out = a;
+        for (int k = 1; k < int(e); ++k) {
+          Nf prod;
+          for (const NfTerm& ta : out)
+            for (const NfTerm& tb : a) {
+              NfTerm t{ta.c * tb.c, ta.f};
+              t.f.insert(t.f.end(), tb.f.begin(), tb.f.end());
+              if (t.f.size() > size_t(kFastFactors)) return false;
+              prod.push_back(t);
+            }
+          if (prod.size() > size_t(kFastTerms)) return false;
+          out.swap(prod);
+        }
+        return true;
+      }
+      case OP_COS: case OP_SIN: case OP_EXP: {
+        Nf a;
+        if (!to_nf(x.a, a)) return false;
+        double A, B, D;
+        if (!nf_affine(a, A, B, D)) return false;
+        out.push_back({1.0, {{x.op == OP_COS ? FAST_COS : x.op == OP_SIN ? FAST_SIN : FAST_EXP, A, B, D}}});
+        return true;
+      }
+      default: return false;
+    }
+  }
+
   // flattens a top-level product into factors (handles unary minus and division)
   void factors(int n, std::vector<int>& out) {
     const Node x = nodes[size_t(n)];
@@ -222,6 +309,37 @@ Program compile_expression(const std::string& text, const std::string& var) {
   p.skip();
   if (p.pos != text.size()) p.fail("trailing characters");
   return p.program_of(p.fold(root));
+}
+
+bool compile_fast(const std::string& text, const std::string& var, FastFn& out) {
+  std::memset(&out, 0, sizeof(out));
+  Parser p(text, var);
+  const int root = p.expr();
+  p.skip();
+  if (p.pos != text.size()) p.fail("trailing characters");
+  Parser::Nf nf;
+  if (!p.to_nf(p.fold(root), nf) || nf.empty() || nf.size() > size_t(kFastTerms)) return false;
+  // constant terms first merged into one, identity factors with zero slope folded into the coefficient
+  for (Parser::NfTerm& t : nf)
+    for (size_t k = 0; k < t.f.size();)
+      if (t.f[k].kind == FAST_ID && t.f[k].a == 0.0 && t.f[k].b == 0.0) {
+        t.c *= t.f[k].d;
+        t.f.erase(t.f.begin() + long(k));
+      } else {
+        ++k;
+      }
+  out.n_terms = int(nf.size());
+  for (int t = 0; t < out.n_terms; ++t) {
+    out.t[t].c = nf[size_t(t)].c;
+    out.t[t].n_fac = int(nf[size_t(t)].f.size());
+    for (int k = 0; k < out.t[t].n_fac; ++k) {
+      out.t[t].kind[k] = nf[size_t(t)].f[size_t(k)].kind;
+      out.t[t].a[k] = nf[size_t(t)].f[size_t(k)].a;
+      out.t[t].b[k] = nf[size_t(t)].f[size_t(k)].b;
+      out.t[t].d[k] = nf[size_t(t)].f[size_t(k)].d;
+    }
+  }
+  return true;
 }
 
 bool compile_separable(const std::string& text, const std::string& var, Program& fx, Program& fy) {

@@ -128,6 +128,49 @@ HDD_HD HDD_FORCEINLINE double eval_program(const Program& p, const double* vars)
   return p.n_ops > 0 ? s0 : 0.0;
 }
 
+// ---- fast form: sum of products of elementary functions of affine arguments ---------------------------------------------
+//   f(x) = sum_t c_t prod_k g_tk(a_tk x[0] + b_tk x[1] + d_tk),   g in {identity, cos, sin, exp}
+// Every data function of the reference's test cases has this shape - the ESV2007 force and exact solution
+// (problems/ESV2007.hh:78, testcases/ESV2007.hh:41), the OS2014 diffusion factor (problems/OS2014.hh:63-74) - and evaluating
+// it costs two fused multiply-adds and one elementary function per factor, against ~25 instructions of dispatch per
+// postfix operation in the interpreter.  Expressions that do not fit (abs, min, max, division by a variable, ...) keep
+// n_terms = 0 and run through the interpreter.
+constexpr int kFastTerms = 4;
+constexpr int kFastFactors = 4;
+enum FastKind : int { FAST_ID = 0, FAST_COS, FAST_SIN, FAST_EXP };
+
+struct FastFn {
+  int n_terms;  // 0: not available
+  struct Term {
+    double c;
+    int n_fac;
+    int kind[kFastFactors];
+    double a[kFastFactors], b[kFastFactors], d[kFastFactors];
+  } t[kFastTerms];
+};
+
+HDD_HD HDD_FORCEINLINE double eval_fast(const FastFn& f, double x, double y) {
+  double s = 0.0;
+  for (int t = 0; t < f.n_terms; ++t) {
+    const FastFn::Term& T = f.t[t];
+    double v = T.c;
+    for (int k = 0; k < T.n_fac; ++k) {
+      const double arg = fma(T.a[k], x, fma(T.b[k], y, T.d[k]));
+      switch (T.kind[k]) {
+        case FAST_COS: v *= cos(arg); break;
+        case FAST_SIN: v *= sin(arg); break;
+        case FAST_EXP: v *= exp(arg); break;
+        default: v *= arg; break;
+      }
+    }
+    s += v;
+  }
+  return s;
+}
+
+// Tries to bring `text` (a function of var[0], var[1]) into the fast form; false (and out.n_terms = 0) if it does not fit.
+bool compile_fast(const std::string& text, const std::string& var, FastFn& out);
+
 // Compiles `text` with the (vector) variable called `var` ("x" or "mu"): var[k], and bare `var` for var[0].
 // Throws hdd::Error(HDD_ERR_WRONG_INPUT) on syntax errors or programs that are too long.
 Program compile_expression(const std::string& text, const std::string& var);

@@ -55,9 +55,15 @@ struct hdd_mesh {
   int32_t n_verts_loc = 0;
 
   // host copies needed after creation
-  std::vector<int32_t> cgid;       // [n_loc] global id of every local cell; empty for a whole mesh (identity)
+  std::vector<int32_t> cgid;       // global ids of the halo cells, sorted (lower halo, then upper halo); empty for a whole mesh
   bool whole = true;               // this rank owns every cell
-  int32_t gid(int32_t lc) const { return whole ? lc : cgid[size_t(lc)]; }
+  // global id of a local cell: [lower halo | owned | upper halo]; `cgid` holds the halo cells only (sorted)
+  int32_t gid(int32_t lc) const {
+    if (whole) return lc;
+    if (lc < own0) return cgid[size_t(lc)];
+    if (lc < own0 + n_own) return int32_t(cell_begin) + (lc - own0);
+    return cgid[size_t(lc - n_own)];
+  }
   int n_subdomains = 1;
   std::vector<int64_t> sub_cell_offsets;             // [n_subdomains+1] global cell offsets
   std::vector<int64_t> sub_dof_offsets;              // nl * sub_cell_offsets

@@ -29,6 +29,7 @@ void launch_cube_fill(const CubeGridDesc& g, int32_t n_loc, int32_t own0, int32_
 // whole mesh on one GPU: flag |= 8 if a neighbour id is out of range; out[i] = i
 void launch_validate_neighbours(const int32_t* neigh, int64_t count, int32_t n_cells, int32_t* flag, cudaStream_t s);
 void launch_iota(int32_t* out, int32_t n, cudaStream_t s);
+void launch_iota_from(int32_t* out, int32_t n, int32_t first, cudaStream_t s);  // out[i] = first + i
 // subdomain offsets and neighbouring-subdomain byte matrix of a whole mesh; flag |= 16 if not subdomain-major
 void launch_subdomain_structure(const int32_t* sub, const int32_t* neigh, int nf, int32_t n_cells, int n_sub,
                                 int64_t* offsets, uint8_t* adj, int32_t* flag, cudaStream_t s);

@@ -133,9 +133,9 @@ __global__ void k_validate_neighbours(const int32_t* __restrict__ neigh, int64_t
   if (g < -1 || g >= n_cells) atomicOr(flag, 8);
 }
 
-__global__ void k_iota(int32_t* __restrict__ out, int32_t n) {
+__global__ void k_iota(int32_t* __restrict__ out, int32_t n, int32_t first) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n) out[t] = t;
+  if (t < n) out[t] = first + t;
 }
 
 // subdomain structure of a whole mesh (grid::Multiscale view): offsets of the subdomain-major cell ranges, the
@@ -1089,7 +1089,14 @@ void launch_validate_neighbours(const int32_t* neigh, int64_t count, int32_t n_c
 
 void launch_iota(int32_t* out, int32_t n, cudaStream_t s) {
   if (n == 0) return;
-  k_iota<<<grid_for(n, 256), 256, 0, s>>>(out, n);
+  k_iota<<<grid_for(n, 256), 256, 0, s>>>(out, n, 0);
+  count_launch();
+  HDD_CUDA(cudaGetLastError());
+}
+
+void launch_iota_from(int32_t* out, int32_t n, int32_t first, cudaStream_t s) {
+  if (n == 0) return;
+  k_iota<<<grid_for(n, 256), 256, 0, s>>>(out, n, first);
   count_launch();
   HDD_CUDA(cudaGetLastError());
 }

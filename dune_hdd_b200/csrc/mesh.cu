@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 
 #include "handles.hpp"
 #include "partition.hpp"
@@ -16,6 +17,97 @@ std::atomic<int64_t> g_kernel_launches{0};
 std::atomic<int64_t> g_h2d_bytes{0}, g_d2h_bytes{0};
 static thread_local std::string t_last_error;
 void set_last_error(const std::string& msg) { t_last_error = msg; }
+
+// ---- caching device allocator (see common.hpp) ---------------------------------------------------------------------------
+namespace {
+constexpr double kDevCacheFraction = 0.45;
+struct DevCache {
+  struct Block { void* p; size_t bytes; int device; uint64_t stamp; };
+  std::mutex mu;
+  std::vector<Block> free_blocks;
+  size_t cached_bytes = 0;
+  uint64_t clock = 0;
+  bool enabled = [] { const char* e = std::getenv("HDD_DEV_CACHE"); return !(e && e[0] == '0'); }();
+};
+DevCache& dev_cache() {
+  static DevCache* c = new DevCache;  // never destroyed: blocks may be freed during static destruction
+  return *c;
+}
+}  // namespace
+
+void dev_cache_release_all() {
+  DevCache& c = dev_cache();
+  std::lock_guard<std::mutex> lock(c.mu);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (const auto& b : c.free_blocks) {
+    cudaSetDevice(b.device);
+    cudaFree(b.p);
+  }
+  cudaSetDevice(cur);
+  c.free_blocks.clear();
+  c.cached_bytes = 0;
+}
+
+void* dev_alloc(size_t bytes) {
+  DevCache& c = dev_cache();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (c.enabled) {
+    std::lock_guard<std::mutex> lock(c.mu);
+    for (size_t k = 0; k < c.free_blocks.size(); ++k)
+      if (c.free_blocks[k].bytes == bytes && c.free_blocks[k].device == dev) {
+        void* p = c.free_blocks[k].p;
+        c.cached_bytes -= bytes;
+        c.free_blocks.erase(c.free_blocks.begin() + long(k));
+        return p;
+      }
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {  // make room: give everything cached back to the driver and try once more
+    cudaGetLastError();
+    dev_cache_release_all();
+    e = cudaMalloc(&p, bytes);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    HDD_THROW(HDD_ERR_DEVICE, "cudaMalloc of " << bytes << " bytes failed: " << cudaGetErrorString(e));
+  }
+  return p;
+}
+
+void dev_free(void* p, size_t bytes) {
+  if (!p) return;
+  DevCache& c = dev_cache();
+  if (!c.enabled) {
+    cudaFree(p);
+    return;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  // The block may be handed to another stream next: what cudaFree does implicitly - wait until nothing on the device uses
+  // it any more - is done here explicitly for large blocks (small ones are scratch of calls that synchronise themselves)
+  if (bytes >= (size_t(1) << 20)) cudaDeviceSynchronize();
+  size_t total = 0, avail = 0;
+  cudaMemGetInfo(&avail, &total);
+  std::lock_guard<std::mutex> lock(c.mu);
+  c.free_blocks.push_back({p, bytes, dev, ++c.clock});
+  c.cached_bytes += bytes;
+  const size_t cap = size_t(kDevCacheFraction * double(total));
+  while (c.cached_bytes > cap && !c.free_blocks.empty()) {
+    size_t oldest = 0;
+    for (size_t k = 1; k < c.free_blocks.size(); ++k)
+      if (c.free_blocks[k].stamp < c.free_blocks[oldest].stamp) oldest = k;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(c.free_blocks[oldest].device);
+    cudaFree(c.free_blocks[oldest].p);
+    cudaSetDevice(cur);
+    c.cached_bytes -= c.free_blocks[oldest].bytes;
+    c.free_blocks.erase(c.free_blocks.begin() + long(oldest));
+  }
+}
 
 // ---- NCCL, resolved at run time ----------------------------------------------------------------------------
 enum { F_UID, F_INIT, F_DESTROY, F_ALLREDUCE, F_GSTART, F_GEND, F_SEND, F_RECV, F_ERRSTR, F_ALLGATHER };
@@ -259,18 +351,28 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
     // ---- index validation: on the device (inside the geometry / neighbour kernels) for the cells this rank keeps.  A
     // distributed mesh walks the host arrays of its owned cells and of the cells across the partition boundary below, so
     // the ids of the owned cells are checked here first - every rank checks its own, together they check all
+    int32_t own_vmin = INT32_MAX, own_vmax = -1;
     if (!whole) {
       std::atomic<int64_t> bad_vertex{-1}, bad_neigh{-1};
-      parallel_for(n_own, [&](int64_t c0, int64_t c1) {
+      const int nt = worker_count(n_own);
+      std::vector<int32_t> mn(size_t(nt), INT32_MAX), mx(size_t(nt), -1);
+      parallel_for_indexed(n_own, nt, [&](int t, int64_t c0, int64_t c1) {
+        int32_t lo = INT32_MAX, hi = -1;
         for (int64_t c = cell_begin + c0; c < cell_begin + c1; ++c)
           for (int i = 0; i < nl; ++i) {
             const int32_t v = cell_verts[c * nl + i], g = cell_neigh[c * nf + i];
             if (v < 0 || v >= n_verts) bad_vertex = c;
             if (g >= n_cells) bad_neigh = c;
+            lo = std::min(lo, v);
+            hi = std::max(hi, v);
           }
+        mn[size_t(t)] = lo;
+        mx[size_t(t)] = hi;
       });
       if (bad_vertex >= 0) HDD_THROW(HDD_ERR_INDEX_OUT_OF_RANGE, "vertex id out of range in cell " << bad_vertex.load());
       if (bad_neigh >= 0) HDD_THROW(HDD_ERR_INDEX_OUT_OF_RANGE, "neighbour id out of range in cell " << bad_neigh.load());
+      own_vmin = *std::min_element(mn.begin(), mn.end());
+      own_vmax = *std::max_element(mx.begin(), mx.end());
     }
     pt.lap("validate indices");
     // ---- halo: every non-owned cell sharing a vertex with an owned cell (superset of the face neighbours the
@@ -289,13 +391,8 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
     m->n_loc = int32_t(halo_lo.size() + n_own + halo_hi.size());
     m->whole = whole;
     if (!whole) {
-      m->cgid.resize(size_t(m->n_loc));
-      std::copy(halo_lo.begin(), halo_lo.end(), m->cgid.begin());
-      int32_t* own = m->cgid.data() + halo_lo.size();
-      parallel_for(n_own, [&](int64_t a, int64_t b) {
-        for (int64_t k = a; k < b; ++k) own[k] = int32_t(cell_begin + k);
-      });
-      std::copy(halo_hi.begin(), halo_hi.end(), m->cgid.begin() + halo_lo.size() + n_own);
+      m->cgid = halo_lo;
+      m->cgid.insert(m->cgid.end(), halo_hi.begin(), halo_hi.end());
       // what the halo plan of hdd_mesh_attach_comm needs later (the caller's arrays are gone by then): the vertex ids of
       // the halo cells and of the owned cells along the partition boundary
       m->h_halo_verts.resize((halo_lo.size() + halo_hi.size()) * size_t(nl));
@@ -318,18 +415,7 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
     // mesh; the rows of a strip for the slabs of a structured grid)
     int64_t v_begin = 0, v_end = n_verts;
     if (!whole) {
-      const int nt = worker_count(n_own);
-      std::vector<int32_t> mn(size_t(nt), INT32_MAX), mx(size_t(nt), -1);
-      parallel_for_indexed(n_own, nt, [&](int t, int64_t a, int64_t b) {
-        int32_t lo = INT32_MAX, hi = -1;
-        for (int64_t e = (cell_begin + a) * nl; e < (cell_begin + b) * nl; ++e) {
-          lo = std::min(lo, cell_verts[e]);
-          hi = std::max(hi, cell_verts[e]);
-        }
-        mn[size_t(t)] = lo;
-        mx[size_t(t)] = hi;
-      });
-      int32_t lo = *std::min_element(mn.begin(), mn.end()), hi = *std::max_element(mx.begin(), mx.end());
+      int32_t lo = own_vmin, hi = own_vmax;
       for (int32_t v : m->h_halo_verts) {
         lo = std::min(lo, v);
         hi = std::max(hi, v);
@@ -375,7 +461,11 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
         d_halo.upload(halo.data(), halo.size(), s);
         launch_localize_neighbours(m->neigh.p, int64_t(n_own) * nf, int32_t(cell_begin), int32_t(cell_end), d_halo.p,
                                    int32_t(halo_lo.size()), int32_t(halo_hi.size()), d_flag.p, s);
-        m->d_cgid.upload(m->cgid.data(), m->cgid.size(), s);
+        m->d_cgid.alloc(size_t(m->n_loc));
+        launch_iota_from(m->d_cgid.p + halo_lo.size(), int32_t(n_own), int32_t(cell_begin), s);
+        if (!halo_lo.empty()) HDD_CUDA(h2d_async(m->d_cgid.p, halo_lo.data(), halo_lo.size() * sizeof(int32_t), s));
+        if (!halo_hi.empty())
+          HDD_CUDA(h2d_async(m->d_cgid.p + halo_lo.size() + n_own, halo_hi.data(), halo_hi.size() * sizeof(int32_t), s));
       } else {
         launch_validate_neighbours(m->neigh.p, int64_t(n_own) * nf, int32_t(n_cells), d_flag.p, s);
         m->d_cgid.alloc(size_t(m->n_loc));
@@ -654,10 +744,7 @@ int hdd_mesh_create_cube(int64_t nx, int64_t ny, double x0, double x1, double y0
     m->whole = whole;
     m->n_verts_loc = int32_t((nx + 1) * (ny + 1));
     if (!whole) {
-      m->cgid.resize(size_t(m->n_loc));
-      std::copy(halo.begin(), halo.begin() + n_lo, m->cgid.begin());
-      for (int64_t k = 0; k < n_own; ++k) m->cgid[n_lo + size_t(k)] = int32_t(cell_begin + k);
-      std::copy(halo.begin() + n_lo, halo.end(), m->cgid.begin() + n_lo + n_own);
+      m->cgid = halo;
       auto verts_of = [&](int64_t g, int32_t* v4) {  // inverse of cell_id, then the vertex ids of hdd_grid_cube
         const int b = int(std::upper_bound(off.begin(), off.end(), g) - off.begin()) - 1;
         const int bx = b % px, by = b / px;
@@ -827,8 +914,8 @@ int hdd_mesh_attach_comm(hdd_mesh* m, hdd_comm* c) {
     std::map<int, HaloPeer> peers;
     std::vector<int32_t> halo_cells;
     std::vector<int> halo_owner;
-    for (int32_t lc = 0; lc < m->n_loc; ++lc) {
-      if (lc >= m->own0 && lc < m->own0 + m->n_own) continue;
+    for (int32_t hk = 0; hk < m->n_loc - m->n_own; ++hk) {
+      const int32_t lc = hk < m->own0 ? hk : hk + m->n_own;
       const int r = owner_of(m->rank_cell_offsets, m->gid(lc));
       halo_cells.push_back(lc);
       halo_owner.push_back(r);

@@ -160,12 +160,19 @@ __global__ void k_twist_vector(const int* done, const double* __restrict__ b0, i
 }
 
 // ---- Galerkin coarse operator with bilinear interpolation: 9-point -> 9-point ---------------------------------
+// Coarse vertices of the row range rg (reads the fine operator on the fine rows 2 I - 1 .. 2 I + 1 only).  blockIdx.y
+// picks the hierarchy: fine / coarse operators hf / hc entries apart; twist_h1: the fine operator of hierarchy 1 is
+// C A C, read from the arrays of A (level 0 -> 1).
 __global__ void __launch_bounds__(kMgThreads)
-    k_rap(const double* __restrict__ Sf, int nxf, int nyf, int twist, double* __restrict__ Sc) {
+    k_rap(const double* __restrict__ Sf, int64_t hf, int nxf, int nyf, int twist_h1, Rows rg, double* __restrict__ Sc, int64_t hc) {
   const int nxc = nxf / 2, nyc = nyf / 2;
   const int64_t nvc = int64_t(nxc + 1) * (nyc + 1), nvf = int64_t(nxf + 1) * (nyf + 1);
-  const int64_t I = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (I >= nvc) return;
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (tid >= rg.cnt) return;
+  const int twist = twist_h1 && blockIdx.y == 1;
+  Sf += int64_t(blockIdx.y) * hf;
+  Sc += int64_t(blockIdx.y) * hc;
+  const int64_t I = rg.beg + tid;
   const int IX = int(I % (nxc + 1)), IY = int(I / (nxc + 1));
   double acc[9];
 #pragma unroll
@@ -401,10 +408,10 @@ __global__ void __launch_bounds__(kMgThreads)
 }
 
 // dinv = w / diagonal of the level operator (both hierarchies)
-__global__ void k_mg_dinv(const double* __restrict__ S, int64_t nv, double* __restrict__ dinv) {
-  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+__global__ void k_mg_dinv(const double* __restrict__ S, int64_t nv, Rows rg, double* __restrict__ dinv) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t hv = int64_t(blockIdx.y) * nv;
-  if (i < nv) dinv[hv + i] = kOmega / S[9 * hv + 4 * nv + i];
+  if (t < rg.cnt) dinv[hv + rg.beg + t] = kOmega / S[9 * hv + 4 * nv + rg.beg + t];
 }
 
 // coarsest grid: x = A^-1 b with the dense inverse, one thread per row; the inverse of the symmetric matrix is read by
@@ -478,6 +485,25 @@ __global__ void __launch_bounds__(kMgThreads)
     val = b0[v];
   }
   b1[v] = ((ix + iy) & 1) ? -val : val;
+}
+
+// The same for the nine coefficient arrays of the level-0 operator (once per solve): array e of lo / up starts at
+// e (g + 1) nx1
+__global__ void __launch_bounds__(kMgThreads)
+    k_ghost_unpack_S(double* __restrict__ S, int64_t nv, const double* __restrict__ lo, const double* __restrict__ up, int nx, int c0,
+                     int c1, int g, int lo_row, int hi_row) {
+  const int nx1 = nx + 1;
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (tid >= int64_t(hi_row - lo_row + 1) * nx1) return;
+  const int e = blockIdx.y;
+  const int64_t v = int64_t(lo_row) * nx1 + tid;
+  const int ix = int(v % nx1), iy = int(v / nx1);
+  double* Se = S + int64_t(e) * nv;
+  const int64_t chunk = int64_t(g + 1) * nx1;
+  if (lo && iy < c0) Se[v] = lo[e * chunk + int64_t(iy - (c0 - g)) * nx1 + ix];
+  else if (up && iy > c1) Se[v] = up[e * chunk + int64_t(iy - c1) * nx1 + ix];
+  else if (lo && iy == c0) Se[v] += lo[e * chunk + int64_t(g) * nx1 + ix];
+  else if (up && iy == c1) Se[v] += up[e * chunk + ix];
 }
 
 __global__ void k_cell_row_range(const int32_t* __restrict__ cell_v0_owned, int32_t n_own, int nx, int* __restrict__ minmax) {
@@ -558,6 +584,8 @@ struct MgState {
   int nx = 0, ny = 0;
   MgDist dist;
 };
+
+static inline dim3 grid2(int64_t cnt) { return dim3(unsigned(blocks_for(cnt)), 2u); }
 
 static inline Rows row_range(const MgLevel& L, int lo, int hi) {
   return Rows{int64_t(lo) * (L.nx + 1), int64_t(hi - lo + 1) * (L.nx + 1)};
@@ -648,20 +676,32 @@ void mg_detect_structure(hdd_mesh* m, const double* xy_host, const double* xy_de
 // The twisted hierarchy has no level-0 arrays of its own: its finest operator is C A_c C, read from the level-0 arrays
 // with the sign of the edge-neighbour entries flipped.
 static void build_hierarchies(hdd_swipdg* h, MgState& st) {
-  cudaStream_t s = h->mesh->stream;
+  hdd_mesh* m = h->mesh;
+  cudaStream_t s = m->stream;
   const size_t nl = st.levels.size();
+  const MgDist& d = st.dist;
+  const int nd = d.on ? d.n_dist : 0;
+  // Strip mode: the operator of a distributed level is needed (and valid) on the rows of its right-hand side, b_lo .. b_hi;
+  // the first replicated level is computed on the own rows and summed over the ranks, the levels below it are replicated.
   for (size_t l = 0; l + 1 < nl; ++l) {
     MgLevel& f = *st.levels[l];
     MgLevel& c = *st.levels[l + 1];
-    for (int t = 0; t < 2; ++t) {
-      const double* Sf = l == 0 ? f.S.p : f.S.p + size_t(t) * 9 * f.nv;
-      k_rap<<<blocks_for(c.nv), kMgThreads, 0, s>>>(Sf, f.nx, f.ny, (l == 0 && t == 1) ? 1 : 0, c.S.p + size_t(t) * 9 * c.nv);
+    Rows rc{0, c.nv};
+    const int lc = int(l) + 1;
+    if (lc < nd) {
+      rc = row_range(c, d.b_lo[lc], d.b_hi[lc]);
+    } else if (lc == nd && nd > 0) {
+      HDD_CUDA(cudaMemsetAsync(c.S.p, 0, size_t(2) * 9 * c.nv * sizeof(double), s));
+      rc = row_range(c, d.own_lo, d.own_hi);
     }
-    count_launch(2);
+    k_rap<<<grid2(rc.cnt), kMgThreads, 0, s>>>(f.S.p, l == 0 ? 0 : 9 * f.nv, f.nx, f.ny, l == 0 ? 1 : 0, rc, c.S.p, 9 * c.nv);
+    count_launch();
+    if (lc == nd && nd > 0) Nccl::get().all_reduce_sum(c.S.p, size_t(2) * 9 * c.nv, m->comm, s);
   }
   for (size_t l = 0; l < nl; ++l) {
     MgLevel& L = *st.levels[l];
-    k_mg_dinv<<<dim3(unsigned(blocks_for(L.nv)), l == 0 ? 1u : 2u), kMgThreads, 0, s>>>(L.S.p, L.nv, L.dinv.p);
+    const Rows r = int(l) < nd ? row_range(L, d.b_lo[l], d.b_hi[l]) : Rows{0, L.nv};
+    k_mg_dinv<<<dim3(unsigned(blocks_for(r.cnt)), l == 0 ? 1u : 2u), kMgThreads, 0, s>>>(L.S.p, L.nv, r, L.dinv.p);
     count_launch();
   }
   // dense inverses of the coarsest operators (s.p.d.), Gauss-Jordan on the host
@@ -713,8 +753,6 @@ static void build_hierarchies(hdd_swipdg* h, MgState& st) {
 
 // levels with at most this many vertices prolongate and post-smooth in one kernel (launch bound there)
 constexpr int64_t kFusedUpMaxVerts = 1500000;
-
-static inline dim3 grid2(int64_t cnt) { return dim3(unsigned(blocks_for(cnt)), 2u); }
 
 // One V(1,1)-cycle of both hierarchies, right-hand sides in levels[0]->b (rows b_lo .. b_hi of this rank when the strip
 // mode is on); the corrections end up in levels[0]->result.
@@ -880,14 +918,48 @@ void mg_setup(hdd_swipdg* h, const double* vals) {
       ly /= 2;
     }
   }
+  detect_strips(h, st);
   MgLevel& f0 = *st.levels[0];
-  k_vertex_galerkin<<<blocks_for(nv), kMgThreads, 0, s>>>(h->view(), vals, m->cell_v0.p, m->lex_cell.p, m->sx, m->sy, Rows{0, nv}, f0.S.p);
-  count_launch();
-  if (m->world > 1) Nccl::get().all_reduce_sum(f0.S.p, size_t(9) * nv, m->comm, s);
+  const MgDist& d = st.dist;
+  if (d.on) {
+    // level-0 operator on the vertex rows of my cells (rows c0 and c1 are shared with the ranks below / above), then the
+    // g rows next to the strip from the neighbours - instead of an all-reduce of the whole operator
+    const int nx1 = st.nx + 1;
+    const Rows mine{int64_t(d.c0) * nx1, int64_t(d.c1 - d.c0 + 1) * nx1};
+    k_vertex_galerkin<<<blocks_for(mine.cnt), kMgThreads, 0, s>>>(h->view(), vals, m->cell_v0.p, m->lex_cell.p, m->sx, m->sy, mine, f0.S.p);
+    count_launch();
+    const int g = d.ghost;
+    const size_t chunk = size_t(g + 1) * nx1;
+    DevBuf<double> lo, up;
+    lo.alloc(9 * chunk);
+    up.alloc(9 * chunk);
+    Nccl& nc = Nccl::get();
+    nc.group_start();
+    for (int e = 0; e < 9; ++e) {
+      double* Se = f0.S.p + int64_t(e) * nv;
+      if (d.upper >= 0) {
+        nc.send(Se + int64_t(d.c1 - g) * nx1, chunk, d.upper, m->comm, s);
+        nc.recv(up.p + e * chunk, chunk, d.upper, m->comm, s);
+      }
+      if (d.lower >= 0) {
+        nc.send(Se + int64_t(d.c0) * nx1, chunk, d.lower, m->comm, s);
+        nc.recv(lo.p + e * chunk, chunk, d.lower, m->comm, s);
+      }
+    }
+    nc.group_end();
+    const int lo_row = d.b_lo[0], hi_row = d.b_hi[0];
+    k_ghost_unpack_S<<<dim3(unsigned(blocks_for(int64_t(hi_row - lo_row + 1) * nx1)), 9u), kMgThreads, 0, s>>>(
+        f0.S.p, nv, d.lower >= 0 ? lo.p : nullptr, d.upper >= 0 ? up.p : nullptr, st.nx, d.c0, d.c1, g, lo_row, hi_row);
+    count_launch();
+    HDD_CUDA(cudaStreamSynchronize(s));  // lo / up are freed at the end of this scope
+  } else {
+    k_vertex_galerkin<<<blocks_for(nv), kMgThreads, 0, s>>>(h->view(), vals, m->cell_v0.p, m->lex_cell.p, m->sx, m->sy, Rows{0, nv}, f0.S.p);
+    count_launch();
+    if (m->world > 1) Nccl::get().all_reduce_sum(f0.S.p, size_t(9) * nv, m->comm, s);
+  }
   HDD_CUDA(cudaGetLastError());
   build_hierarchies(h, st);
   HDD_CUDA(cudaGetLastError());
-  detect_strips(h, st);
 }
 
 // z += P V(P^T r) + P C V_C(C P^T r), red[1] = r.z; p_init != nullptr also stores z as the first direction

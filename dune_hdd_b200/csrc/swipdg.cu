@@ -120,6 +120,10 @@ FnRef add_function(hdd_swipdg* h, const hdd_function& f, const char* what) {
       if (!f.expression) HDD_THROW(HDD_ERR_WRONG_INPUT, what << ": expression is NULL");
       d.prog = compile_expression(f.expression, "x");
       d.separable = compile_separable(f.expression, "x", d.px, d.py) ? 1 : 0;
+      {
+        static const bool fast_on = [] { const char* e = std::getenv("HDD_EXPR_FAST"); return !(e && e[0] == '0'); }();
+        if (fast_on) compile_fast(f.expression, "x", d.fast);
+      }
       break;
     default:
       HDD_THROW(HDD_ERR_WRONG_INPUT, what << ": unknown function kind " << f.kind);
