@@ -118,9 +118,13 @@ struct Geo<HDD_SIMPLEX2D> {
     cx = (vx[0] + vx[1] + vx[2]) / 3.0;
     cy = (vy[0] + vy[1] + vy[2]) / 3.0;
   }
+  // faces {0,1}, {0,2}, {1,2}; written with selects so that a face index known only at run time does not turn vx / vy
+  // into dynamically indexed (local-memory) arrays
   __device__ __forceinline__ void face_ends(int f, double& ax, double& ay, double& bx, double& by) const {
-    const int a = f == 2 ? 1 : 0, b = f == 0 ? 1 : 2;
-    ax = vx[a]; ay = vy[a]; bx = vx[b]; by = vy[b];
+    ax = f == 2 ? vx[1] : vx[0];
+    ay = f == 2 ? vy[1] : vy[0];
+    bx = f == 0 ? vx[1] : vx[2];
+    by = f == 0 ? vy[1] : vy[2];
   }
   __device__ __forceinline__ double diameter() const {
     double h = 0.0;

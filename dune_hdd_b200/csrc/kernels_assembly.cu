@@ -245,8 +245,8 @@ __device__ __forceinline__ double factor_at(const DevFn& fn, double a_cell, doub
   }
 }
 
-template <int KIND, int FK>
-__global__ void __launch_bounds__(kThreads)
+template <int KIND, int FK, int OCC = 1>
+__global__ void __launch_bounds__(kThreads, OCC)
     k_assemble_lhs(MeshView m, const __grid_constant__ DevFn fn, ElemRule vol, LineRule fr, double s_in, double s_bnd,
                    double* __restrict__ vals) {
   using G = Geo<KIND>;
@@ -1176,8 +1176,14 @@ void launch_fill_csr(const MeshView& m, int64_t* rowptr, int32_t* col, cudaStrea
 template <int KIND>
 static void assemble_dispatch(int fk, int blocks, cudaStream_t s, const MeshView& m, const DevFn& fn, const ElemRule& vol,
                               const LineRule& fr, double si, double sb, double* values) {
+  // P1: 4 resident CTAs per SM (128 registers, a few spilled values) against 3 (144-148 registers); HDD_ASM_P1_OCC=3 picks
+  // the latter for A/B measurements
+  static const bool occ4 = [] { const char* e = std::getenv("HDD_ASM_P1_OCC"); return !(e && e[0] == '3'); }();
   dispatch_fk(fk, [&](auto k) {
-    k_assemble_lhs<KIND, decltype(k)::value><<<blocks, kThreads, 0, s>>>(m, fn, vol, fr, si, sb, values);
+    if (KIND == HDD_SIMPLEX2D && occ4)
+      k_assemble_lhs<KIND, decltype(k)::value, 4><<<blocks, kThreads, 0, s>>>(m, fn, vol, fr, si, sb, values);
+    else
+      k_assemble_lhs<KIND, decltype(k)::value><<<blocks, kThreads, 0, s>>>(m, fn, vol, fr, si, sb, values);
   });
 }
 
