@@ -757,6 +757,176 @@ __global__ void __launch_bounds__(kThreads, MINB)
   for (int64_t q = threadIdx.x; q < total; q += blockDim.x) out[q] = stage[q];
 }
 
+// K2 for Q2 on axis-parallel rectangles (BASELINE config 5 at p = 2).  One thread per matrix row, 32 cells per CTA.
+// What makes the generic row kernel fp64-bound is that the nine row threads of a cell each re-evaluate the nine basis
+// functions and their fluxes at every face point.  Here (a) the basis is the tensor product l_a(xi) l_b(eta) of the
+// quadratic Lagrange polynomials, so everything needed on a face follows from three values l(t_q) and three derivatives
+// along the face plus the constants l(0), l(1), l'(0), l'(1) across it, and only the three functions of the face's own
+// nodes are non-zero on it; (b) the two vectors that couple all nine columns,
+//     A_j = w pen phi_j - w omega^- (A^- grad phi_j . n)        (en/en)
+//     C_j = -w omega^+ (A^+ grad phi^+_j . n) - w pen phi^+_j     (en/ne)
+// do not depend on the row: thread j of a cell computes A_j, C_j for the three face points once and the nine row threads
+// read them from shared memory.  A row then costs 24 fused multiply-adds per face point instead of ~350 fp64 operations.
+constexpr int kQ2Cells = 32;
+constexpr int kQ2Threads = kQ2Cells * 9;
+constexpr int kQ2MaxFacePts = 4;
+
+__device__ __forceinline__ void lagrange2(double t, double* l, double* d) {
+  l[0] = (1.0 - t) * (1.0 - 2.0 * t); l[1] = 4.0 * t * (1.0 - t); l[2] = t * (2.0 * t - 1.0);
+  d[0] = 4.0 * t - 3.0;               d[1] = 4.0 - 8.0 * t;       d[2] = 4.0 * t - 1.0;
+}
+
+template <int F, int FK>
+__device__ __forceinline__ void q2_face(const MeshView& m, const DevFn& fn, const Geo<HDD_CUBE2D>& g, const double* K, int k,
+                                        int c, int n, int i, double a_self, const LineRule& fr, double s_in, double s_bnd,
+                                        double* tab /* this cell's [q][2][9] */, double* D, double* row, const int* nb, bool live) {
+  constexpr bool vertical = F < 2;                      // faces 0,1: x = const; faces 2,3: y = const
+  constexpr double sgn = (F == 0 || F == 2) ? -1.0 : 1.0;
+  constexpr int side = (F == 1 || F == 3) ? 2 : 0;      // index of the 1-d node on the face: own side, neighbour's 2 - side
+  const int ai = i % 3, bi = i / 3;
+  const int across = vertical ? ai : bi, along = vertical ? bi : ai;
+  // l and l' across the face at the face coordinate (0 or 1): l = unit vector, l' = (-3, 4, -1) or (1, -4, 3)
+  const double dl_own = side == 0 ? (across == 0 ? -3.0 : across == 1 ? 4.0 : -1.0) : (across == 0 ? 1.0 : across == 1 ? -4.0 : 3.0);
+  const double dl_nb = side == 0 ? (across == 0 ? 1.0 : across == 1 ? -4.0 : 3.0) : (across == 0 ? -3.0 : across == 1 ? 4.0 : -1.0);
+  const double l_own = across == side ? 1.0 : 0.0, l_nb = across == 2 - side ? 1.0 : 0.0;
+  const double h = vertical ? fabs(g.hy) : fabs(g.hx);
+  const double ih = vertical ? fabs(g.ihy) : fabs(g.ihx);
+  const double i_across = vertical ? g.ihx : g.ihy, i_along = vertical ? g.ihy : g.ihx;
+  // (K^T n) split into the across / along components of the face
+  const double kn_ac = sgn * (vertical ? K[0] : K[3]), kn_al = sgn * (vertical ? K[1] : K[2]);
+  const double dm = vertical ? K[0] : K[3];
+  const bool inner = n >= 0;
+  const bool dirichlet = !inner && !(m.btype && __ldg(m.btype + size_t(4) * k + F) != 1);
+  double wm = 1.0, wp = 0.0, pen0 = s_bnd * dm * ih, a_nb = a_self, kn_ac_p = 0.0, kn_al_p = 0.0, i_across_p = 0.0;
+  if (inner) {
+    double Kn[4];
+    load_tensor(m.tensor, n, Kn);
+    const double dp = vertical ? Kn[0] : Kn[3];
+    const double isum = 1.0 / (dp + dm);
+    wm = dp * isum;
+    wp = dm * isum;
+    pen0 = s_in * dp * dm * isum * 0.5 * ih;
+    kn_ac_p = sgn * (vertical ? Kn[0] : Kn[3]);
+    kn_al_p = sgn * (vertical ? Kn[1] : Kn[2]);
+    if constexpr (FK == HDD_FN_CELLWISE) a_nb = __ldg(fn.cell + n);
+    Geo<HDD_CUBE2D> gn;
+    gn.load(m.cgeo, n);
+    i_across_p = vertical ? gn.ihx : gn.ihy;
+  }
+  // ---- phase 1: this thread's column j = i of A and C at every face point; its own B_i and phi_i stay in registers
+  double Bi[kQ2MaxFacePts], phi_i[kQ2MaxFacePts];
+  for (int q = 0; q < fr.n; ++q) {
+    double lt[3], dt[3];
+    lagrange2(fr.x[q], lt, dt);
+    double am = a_self;
+    if constexpr (FK == HDD_FN_EXPRESSION) {
+      const double xi = vertical ? (side == 0 ? 0.0 : 1.0) : fr.x[q], eta = vertical ? fr.x[q] : (side == 0 ? 0.0 : 1.0);
+      am = factor_at<FK>(fn, a_self, g.x0 + g.hx * xi, g.y0 + g.hy * eta);
+    }
+    const double ap = (FK == HDD_FN_EXPRESSION) ? am : a_nb;
+    const double w = fr.w[q] * h;
+    const double wpen = inner ? w * pen0 * (am + ap) : w * pen0 * am;
+    const double wwm = w * wm * am, wwp = w * wp * ap;
+    const double la = pick<3>(lt, along), da = pick<3>(dt, along);
+    const double phi = l_own * la;
+    // grad phi . K^T n = d/d(across) * kn_ac + d/d(along) * kn_al
+    const double B = wwm * (dl_own * la * i_across * kn_ac + l_own * da * i_along * kn_al);
+    double A = wpen * phi - B, C = 0.0;
+    if (!inner && !dirichlet) A = 0.0;
+    if (inner) {
+      const double phip = l_nb * la;
+      C = -wwp * (dl_nb * la * i_across_p * kn_ac_p + l_nb * da * i_along * kn_al_p) - wpen * phip;
+    }
+    tab[(q * 2 + 0) * 9 + i] = A;
+    tab[(q * 2 + 1) * 9 + i] = C;
+    Bi[q] = (inner || dirichlet) ? B : 0.0;
+    phi_i[q] = (inner || dirichlet) ? phi : 0.0;
+  }
+  __syncthreads();
+  // ---- phase 2: row i.  D[j] += phi_i A_j - B_i phi_j ; E[j] = phi_i C_j + B_i phi^+_j ; phi_j, phi^+_j are non-zero for the
+  // three nodes on the face only (values l(t_q))
+  double E[9];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) E[j] = 0.0;
+  for (int q = 0; q < fr.n; ++q) {
+    double lt[3], dt[3];
+    lagrange2(fr.x[q], lt, dt);
+    const double* A = tab + (q * 2 + 0) * 9;
+    const double* C = tab + (q * 2 + 1) * 9;
+    const double p = phi_i[q], B = Bi[q];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      D[j] = fma(p, A[j], D[j]);
+      E[j] = fma(p, C[j], E[j]);
+    }
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const int j_own = vertical ? side + 3 * t : t + 3 * side;
+      const int j_nb = vertical ? (2 - side) + 3 * t : t + 3 * (2 - side);
+      D[j_own] = fma(-B, lt[t], D[j_own]);
+      E[j_nb] = fma(B, lt[t], E[j_nb]);
+    }
+  }
+  if (inner && live) {
+    double* dst = row + block_slot<4>(c, nb, n) * 9;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) dst[j] = E[j];
+  }
+}
+
+template <int FK>
+__global__ void __launch_bounds__(kQ2Threads, 2)
+    k_assemble_q2_cube(MeshView m, const __grid_constant__ DevFn fn, ElemRule vol, LineRule fr, double s_in, double s_bnd,
+                       double* __restrict__ vals) {
+  // A_j, C_j of the current face: [parity][cell][q][2][9]; two buffers, so that one barrier per face is enough
+  __shared__ double tabs[2][kQ2Cells][kQ2MaxFacePts * 2 * 9];
+  const int cs = threadIdx.x / 9, i = threadIdx.x % 9;
+  const int k_raw = blockIdx.x * kQ2Cells + cs;
+  const bool live = k_raw < m.n_own;
+  const int k = live ? k_raw : m.n_own - 1;  // idle threads of the last CTA recompute its last cell (they take part in the barriers)
+  const int c = m.own0 + k;
+  Geo<HDD_CUBE2D> g;
+  g.load(m.cgeo, c);
+  double K[4];
+  load_tensor(m.tensor, c, K);
+  int nb[4];
+  load_neigh<4>(m.neigh, k, nb);
+  const int nblk = block_count<4>(nb);
+  double* row = vals + __ldg(m.blk_start + k) * 81 + int64_t(i) * nblk * 9;
+  double a_self = 0.0;
+  if constexpr (FK == HDD_FN_CONSTANT) a_self = fn.value;
+  if constexpr (FK == HDD_FN_CELLWISE) a_self = __ldg(fn.cell + c);
+  const int ai = i % 3, bi = i / 3;
+  double D[9];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) D[j] = 0.0;
+  // volume: sum_q w (a K grad phi_j) . grad phi_i with the tensor-product basis
+  for (int q = 0; q < vol.n; ++q) {
+    double lx[3], dx[3], ly[3], dy[3];
+    lagrange2(vol.x[q], lx, dx);
+    lagrange2(vol.y[q], ly, dy);
+    double a = a_self;
+    if constexpr (FK == HDD_FN_EXPRESSION) a = factor_at<FK>(fn, a_self, g.x0 + g.hx * vol.x[q], g.y0 + g.hy * vol.y[q]);
+    const double wa = vol.w[q] * g.detj * a;
+    const double gxi = wa * pick<3>(dx, ai) * pick<3>(ly, bi) * g.ihx, gyi = wa * pick<3>(lx, ai) * pick<3>(dy, bi) * g.ihy;
+    const double cx = K[0] * gxi + K[2] * gyi, cy = K[1] * gxi + K[3] * gyi;  // (K grad phi_j) . grad phi_i = grad phi_j . K^T grad phi_i
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+#pragma unroll
+      for (int a2 = 0; a2 < 3; ++a2)
+        D[a2 + 3 * b] = fma(dx[a2] * ly[b] * g.ihx, cx, fma(lx[a2] * dy[b] * g.ihy, cy, D[a2 + 3 * b]));
+  }
+  q2_face<0, FK>(m, fn, g, K, k, c, nb[0], i, a_self, fr, s_in, s_bnd, tabs[0][cs], D, row, nb, live);
+  q2_face<1, FK>(m, fn, g, K, k, c, nb[1], i, a_self, fr, s_in, s_bnd, tabs[1][cs], D, row, nb, live);
+  q2_face<2, FK>(m, fn, g, K, k, c, nb[2], i, a_self, fr, s_in, s_bnd, tabs[0][cs], D, row, nb, live);
+  q2_face<3, FK>(m, fn, g, K, k, c, nb[3], i, a_self, fr, s_in, s_bnd, tabs[1][cs], D, row, nb, live);
+  if (live) {
+    double* dst = row + block_slot<4>(c, nb, c) * 9;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) dst[j] = D[j];
+  }
+}
+
 // Volume-pattern products (discretizations/swipdg.hh:359-443): one dense n_loc x n_loc block per cell, one thread per
 // row.  WHICH 0 "l2" int phi_i phi_j, 1 "h1_semi" int grad phi_j . grad phi_i, 2 "elliptic" int a K grad phi_j . grad
 // phi_i, 3 "boundary_l2" int_{dT on dOmega} phi_i phi_j.  over_integrate = 2 is folded into the rules by the launcher.
@@ -1198,7 +1368,13 @@ void launch_assemble_lhs(const MeshView& m, const DevFn& factor_dev, int factor_
   // tables (kept for A/B measurements and as cross-checks of the specialised variants)
   static const bool generic_cube = [] { const char* e = std::getenv("HDD_ASSEMBLY_GENERIC"); return e && e[0] == '1'; }();
   static const bool tensor_ok = [] { const char* e = std::getenv("HDD_ASM_TENSOR"); return !(e && e[0] == '0'); }();
-  if (polorder != 1) {
+  static const bool q2_fast = [] { const char* e = std::getenv("HDD_ASM_Q2_CUBE"); return !(e && e[0] == '0'); }();
+  if (polorder == 2 && m.kind == HDD_CUBE2D && q2_fast && fr.n <= kQ2MaxFacePts) {
+    // Q2 on axis-parallel rectangles: tensor-product basis, per-cell flux vectors shared through shared memory
+    dispatch_fk(factor_kind, [&](auto k) {
+      k_assemble_q2_cube<decltype(k)::value><<<(m.n_own + kQ2Cells - 1) / kQ2Cells, kQ2Threads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+    });
+  } else if (polorder != 1) {
     // p = 2: one thread per row, 3 CTAs per SM (168 registers; 2.85 ms vs 3.48 ms with 2 at 1024^2 Q2)
     const int64_t rows = int64_t(m.n_own) * m.nl;
     dispatch_elem(m.kind, polorder, [&](auto kind, auto p) {
