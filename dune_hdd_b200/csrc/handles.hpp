@@ -84,6 +84,11 @@ struct hdd_mesh {
   // logically structured cube grid (vertices x-fastest): cells per direction (0 = not structured / not one GPU), the
   // vertex 0 of every cell and the map lexicographic cell -> cell; feeds the multigrid preconditioner ("cg.mg")
   int sx = 0, sy = 0;
+  // simplex grid whose vertices form a tensor-product lattice numbered x-fastest and whose triangles join lattice neighbours
+  // (the ALU ladder of the test cases): lattice cells per direction, global (= lattice) vertex ids of the local cells and of
+  // the local vertices - what cg.mg needs for its conforming P1 auxiliary space
+  int lx = 0, ly = 0;
+  hdd::DevBuf<int32_t> cell_gv, lvert_gid;
   hdd::DevBuf<int32_t> cell_v0, lex_cell;
   hdd::DevBuf<double> tgeo;  // {x0, hx, 1/hx, -} per column, {y0, hy, 1/hy, -} per row
   bool purely_neumann = false;  // no Dirichlet face anywhere (DirichletDetector, discretizations/swipdg.hh:219-220,488-489)

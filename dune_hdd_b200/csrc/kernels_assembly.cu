@@ -767,9 +767,15 @@ __global__ void __launch_bounds__(kThreads, MINB)
 //     C_j = -w omega^+ (A^+ grad phi^+_j . n) - w pen phi^+_j     (en/ne)
 // do not depend on the row: thread j of a cell computes A_j, C_j for the three face points once and the nine row threads
 // read them from shared memory.  A row then costs 24 fused multiply-adds per face point instead of ~350 fp64 operations.
-constexpr int kQ2Cells = 32;
+// The rows of a CTA's cells are one contiguous range of the value array: they are staged in shared memory and written out
+// coalesced (written straight from the registers every store instruction touches 32 sectors for 8 bytes each, and the L2
+// request rate - 1.7 G partial-sector writes for 13.6 GB at 2048^2 - bounds the kernel: measured 12.7 ms).
+constexpr int kQ2Cells = 16;
 constexpr int kQ2Threads = kQ2Cells * 9;
 constexpr int kQ2MaxFacePts = 4;
+constexpr int kQ2TabDoubles = 2 * kQ2Cells * kQ2MaxFacePts * 2 * 9;  // A_j, C_j of two faces in flight
+constexpr int kQ2StageDoubles = kQ2Cells * 5 * 81;                    // every block of every cell of the CTA
+constexpr int kQ2SmemBytes = (kQ2TabDoubles + kQ2StageDoubles) * 8;
 
 __device__ __forceinline__ void lagrange2(double t, double* l, double* d) {
   l[0] = (1.0 - t) * (1.0 - 2.0 * t); l[1] = 4.0 * t * (1.0 - t); l[2] = t * (2.0 * t - 1.0);
@@ -875,11 +881,13 @@ __device__ __forceinline__ void q2_face(const MeshView& m, const DevFn& fn, cons
 }
 
 template <int FK>
-__global__ void __launch_bounds__(kQ2Threads, 2)
+__global__ void __launch_bounds__(kQ2Threads, 3)
     k_assemble_q2_cube(MeshView m, const __grid_constant__ DevFn fn, ElemRule vol, LineRule fr, double s_in, double s_bnd,
                        double* __restrict__ vals) {
   // A_j, C_j of the current face: [parity][cell][q][2][9]; two buffers, so that one barrier per face is enough
-  __shared__ double tabs[2][kQ2Cells][kQ2MaxFacePts * 2 * 9];
+  extern __shared__ __align__(16) double q2_smem[];
+  double (*tabs)[kQ2Cells][kQ2MaxFacePts * 2 * 9] = reinterpret_cast<double (*)[kQ2Cells][kQ2MaxFacePts * 2 * 9]>(q2_smem);
+  double* stage = q2_smem + kQ2TabDoubles;
   const int cs = threadIdx.x / 9, i = threadIdx.x % 9;
   const int k_raw = blockIdx.x * kQ2Cells + cs;
   const bool live = k_raw < m.n_own;
@@ -892,7 +900,9 @@ __global__ void __launch_bounds__(kQ2Threads, 2)
   int nb[4];
   load_neigh<4>(m.neigh, k, nb);
   const int nblk = block_count<4>(nb);
-  double* row = vals + __ldg(m.blk_start + k) * 81 + int64_t(i) * nblk * 9;
+  const int k_first = blockIdx.x * kQ2Cells;
+  const int64_t base_blk = __ldg(m.blk_start + k_first);
+  double* row = stage + (__ldg(m.blk_start + k) - base_blk) * 81 + int64_t(i) * nblk * 9;
   double a_self = 0.0;
   if constexpr (FK == HDD_FN_CONSTANT) a_self = fn.value;
   if constexpr (FK == HDD_FN_CELLWISE) a_self = __ldg(fn.cell + c);
@@ -925,6 +935,11 @@ __global__ void __launch_bounds__(kQ2Threads, 2)
 #pragma unroll
     for (int j = 0; j < 9; ++j) dst[j] = D[j];
   }
+  __syncthreads();
+  const int k_end = min(k_first + kQ2Cells, m.n_own);
+  const int64_t total = (__ldg(m.blk_start + k_end) - base_blk) * 81;
+  double* out = vals + base_blk * 81;
+  for (int64_t t = threadIdx.x; t < total; t += blockDim.x) out[t] = stage[t];
 }
 
 // Volume-pattern products (discretizations/swipdg.hh:359-443): one dense n_loc x n_loc block per cell, one thread per
@@ -1372,7 +1387,9 @@ void launch_assemble_lhs(const MeshView& m, const DevFn& factor_dev, int factor_
   if (polorder == 2 && m.kind == HDD_CUBE2D && q2_fast && fr.n <= kQ2MaxFacePts) {
     // Q2 on axis-parallel rectangles: tensor-product basis, per-cell flux vectors shared through shared memory
     dispatch_fk(factor_kind, [&](auto k) {
-      k_assemble_q2_cube<decltype(k)::value><<<(m.n_own + kQ2Cells - 1) / kQ2Cells, kQ2Threads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+      auto kern = k_assemble_q2_cube<decltype(k)::value>;
+      HDD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kQ2SmemBytes));
+      kern<<<(m.n_own + kQ2Cells - 1) / kQ2Cells, kQ2Threads, kQ2SmemBytes, s>>>(m, factor_dev, vol, fr, si, sb, values);
     });
   } else if (polorder != 1) {
     // p = 2: one thread per row, 3 CTAs per SM (168 registers; 2.85 ms vs 3.48 ms with 2 at 1024^2 Q2)

@@ -472,6 +472,7 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
         launch_iota(m->d_cgid.p, m->n_loc, s);
       }
       mg_detect_structure(m.get(), xy, d_xy, v_begin, v_end, d_cv.p, n_verts);
+      if (kind == HDD_SIMPLEX2D && m->lx > 0) m->cell_gv = std::move(d_cv);  // lattice ids of the local cells' vertices
       if (boundary_type) {
         m->has_btype = true;
         m->btype.upload(boundary_type + cell_begin * nf, size_t(n_own) * nf, s);
@@ -523,6 +524,14 @@ int hdd_mesh_create(int kind, int64_t n_cells, int64_t n_verts, const double* xy
         }
       });
       m->n_verts_loc = nvl;
+      if (m->lx > 0) {  // local vertex -> lattice vertex
+        std::vector<int32_t> gidv;
+        gidv.resize(size_t(nvl));
+        for (int64_t v = v_begin; v < v_end; ++v)
+          if (dn[v] >= 0) gidv[size_t(dn[v])] = int32_t(v);
+        m->lvert_gid.upload(gidv.data(), gidv.size(), s);
+        HDD_CUDA(cudaStreamSynchronize(s));
+      }
     }
     if (kind == HDD_SIMPLEX2D) {
       const int32_t nvl = m->n_verts_loc;
@@ -894,11 +903,16 @@ int hdd_mesh_attach_comm(hdd_mesh* m, hdd_comm* c) {
     }
     {  // logically structured grid: every rank checked its own cells and vertices; the verdict has to be the same everywhere
       DevBuf<double> bad;
-      double f = m->sx > 0 ? 0.0 : 1.0;
+      double f = (m->sx > 0 || m->lx > 0) ? 0.0 : 1.0;
       bad.upload(&f, 1, m->stream);
       nc.all_reduce_sum(bad.p, 1, m->comm, m->stream);
       HDD_CUDA(cudaMemcpyAsync(&f, bad.p, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
       HDD_CUDA(cudaStreamSynchronize(m->stream));
+      if (f != 0.0 && m->lx > 0) {
+        m->lx = m->ly = 0;
+        m->cell_gv.release();
+        m->lvert_gid.release();
+      }
       if (f != 0.0 && m->sx > 0) {
         m->sx = m->sy = 0;
         m->cell_v0.release();

@@ -74,6 +74,23 @@ __global__ void k_struct_cells(const int32_t* __restrict__ cv, int32_t n_cells, 
   lex_cell[cx + nx * cy] = c;
 }
 
+// triangles: the three vertices must be pairwise lattice neighbours (index distance <= 1 in both directions)
+__global__ void k_struct_triangles(const int32_t* __restrict__ cv, int32_t n_cells, int nx1, int64_t n_verts, int32_t* flag) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cells) return;
+  int vx[3], vy[3];
+  for (int i = 0; i < 3; ++i) {
+    const int v = cv[size_t(3) * c + i];
+    if (v < 0 || v >= n_verts) { atomicOr(flag, 1); return; }
+    vx[i] = v % nx1;
+    vy[i] = v / nx1;
+  }
+  for (int i = 0; i < 3; ++i) {
+    const int j = (i + 1) % 3;
+    if (abs(vx[i] - vx[j]) > 1 || abs(vy[i] - vy[j]) > 1) atomicOr(flag, 1);
+  }
+}
+
 // vertices [v0, v0 + count): tensor-product coordinates, checked against the one-dimensional coordinate tables
 __global__ void k_struct_verts(const double* __restrict__ xy /* indexed by global vertex id */, int64_t v0, int64_t count, int nx,
                                const double* __restrict__ xs, const double* __restrict__ ys, int32_t* flag) {
@@ -506,6 +523,92 @@ __global__ void __launch_bounds__(kMgThreads)
   else if (up && iy == c1) Se[v] += up[e * chunk + ix];
 }
 
+// ---- DG level on lattice-structured simplex grids: P = injection of the conforming P1 space (one hierarchy: the P1
+// volume term is integrated exactly, there is no hourglass family) --------------------------------------------------------
+// A_c = P^T A P per local vertex through the vertex -> DoF incidence of the Oswald pass; rows of cells owned elsewhere
+// are added by the all-reduce
+__global__ void __launch_bounds__(kMgThreads)
+    k_vertex_galerkin_p1(MeshView m, const double* __restrict__ vals, const int64_t* __restrict__ vptr,
+                         const int32_t* __restrict__ vdof, const int32_t* __restrict__ lvert_gid,
+                         const int32_t* __restrict__ cell_gv, int32_t n_verts_loc, int nx, int ny, double* __restrict__ S) {
+  const int lv = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lv >= n_verts_loc) return;
+  const int nx1 = nx + 1;
+  const int64_t nv = int64_t(nx1) * (ny + 1);
+  const int v = __ldg(lvert_gid + lv);
+  const int ix = v % nx1, iy = v / nx1;
+  double acc[9];
+#pragma unroll
+  for (int e = 0; e < 9; ++e) acc[e] = 0.0;
+  bool any = false;
+  for (int64_t q = __ldg(vptr + lv); q < __ldg(vptr + lv + 1); ++q) {
+    const int dof = __ldg(vdof + q);
+    const int c = dof / 3, i = dof - 3 * c, k = c - m.own0;
+    if (k < 0 || k >= m.n_own) continue;
+    any = true;
+    int nb[3];
+    nb[0] = __ldg(m.neigh + size_t(3) * k);
+    nb[1] = __ldg(m.neigh + size_t(3) * k + 1);
+    nb[2] = __ldg(m.neigh + size_t(3) * k + 2);
+    const int nblk = block_count<3>(nb);
+    const double* row = vals + __ldg(m.blk_start + k) * 9 + int64_t(i) * nblk * 3;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int cell = t == 0 ? c : nb[t - 1];
+      if (cell < 0) continue;
+      const int slot = block_slot<3>(c, nb, cell);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int w = __ldg(cell_gv + size_t(3) * cell + j);
+        const int dx = w % nx1 - ix, dy = w / nx1 - iy;
+        if (dx < -1 || dx > 1 || dy < -1 || dy > 1) continue;  // cancels analytically (jumps of continuous functions)
+        acc[(dy + 1) * 3 + dx + 1] += __ldg(row + slot * 3 + j);
+      }
+    }
+  }
+  if (!any) return;  // no owned cell at this vertex: its row comes from the owners
+#pragma unroll
+  for (int e = 0; e < 9; ++e) S[e * nv + v] = acc[e];
+}
+
+// b0 = P^T r: per local vertex the sum of the owned DG residual entries sitting on it
+__global__ void __launch_bounds__(kMgThreads)
+    k_dg_restrict_p1(const int* done, const double* __restrict__ r, const int64_t* __restrict__ vptr,
+                     const int32_t* __restrict__ vdof, const int32_t* __restrict__ lvert_gid, int32_t n_verts_loc, int own0,
+                     int n_own, double* __restrict__ b0) {
+  if (done && *done) return;
+  const int lv = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lv >= n_verts_loc) return;
+  double s = 0.0;
+  for (int64_t q = __ldg(vptr + lv); q < __ldg(vptr + lv + 1); ++q) {
+    const int dof = __ldg(vdof + q);
+    const int k = dof / 3 - own0;
+    if (k < 0 || k >= n_own) continue;
+    s += __ldg(r + size_t(dof) - size_t(3) * own0);
+  }
+  b0[__ldg(lvert_gid + lv)] = s;
+}
+
+// z += P x, r.z recomputed; optionally p = z (first direction).  One thread per owned triangle.
+__global__ void __launch_bounds__(kMgThreads)
+    k_dg_prolong_dot_p1(const int* done, int32_t n_cells, const int32_t* __restrict__ cell_gv /* of the owned cells */,
+                        const double* __restrict__ x0, const double* __restrict__ r, double* __restrict__ z,
+                        double* __restrict__ p_init, double* partial, CgScalars* sc) {
+  if (done && *done) return;
+  double v[1] = {0.0};
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; c < n_cells; c += stride) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double o = z[3 * c + i] + __ldg(x0 + __ldg(cell_gv + 3 * c + i));
+      z[3 * c + i] = o;
+      if (p_init) p_init[3 * c + i] = o;
+      v[0] = fma(r[3 * c + i], o, v[0]);
+    }
+  }
+  grid_sum<1>(v, partial, &sc->ticket_a, [sc](const double(&w)[1]) { sc->red[1] = w[0]; });
+}
+
 __global__ void k_cell_row_range(const int32_t* __restrict__ cell_v0_owned, int32_t n_own, int nx, int* __restrict__ minmax) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_own) return;
@@ -580,12 +683,13 @@ struct MgDist {
 
 struct MgState {
   std::vector<std::unique_ptr<MgLevel>> levels;
-  DevBuf<double> coarse_inv;  // [2][n * n]
+  DevBuf<double> coarse_inv;  // [n_hier][n * n]
   int nx = 0, ny = 0;
+  int n_hier = 2;  // Q1 on cubes: plain + checkerboard-twisted hierarchy; P1 on lattice-structured simplex grids: one
   MgDist dist;
 };
 
-static inline dim3 grid2(int64_t cnt) { return dim3(unsigned(blocks_for(cnt)), 2u); }
+static inline dim3 grid2(int64_t cnt, int n_hier = 2) { return dim3(unsigned(blocks_for(cnt)), unsigned(n_hier)); }
 
 static inline Rows row_range(const MgLevel& L, int lo, int hi) {
   return Rows{int64_t(lo) * (L.nx + 1), int64_t(hi - lo + 1) * (L.nx + 1)};
@@ -631,13 +735,40 @@ void mg_strip_plan(int ny, int c0, int c1, int n_dist, MgDist& d) {
 void mg_detect_structure(hdd_mesh* m, const double* xy_host, const double* xy_dev, int64_t v_begin, int64_t v_end,
                          const int32_t* cv_dev, int64_t n_verts) {
   m->sx = m->sy = 0;
-  if (m->kind != HDD_CUBE2D) return;
+  m->lx = m->ly = 0;
   int64_t nx1 = 1;
   while (nx1 < n_verts && xy_host[2 * nx1 + 1] == xy_host[1]) ++nx1;
   if (nx1 < 2 || n_verts % nx1 != 0) return;
   const int64_t nx = nx1 - 1, ny = n_verts / nx1 - 1;
-  if (ny < 1 || nx * ny != m->n_global) return;
   cudaStream_t s = m->stream;
+  if (m->kind == HDD_SIMPLEX2D) {
+    // lattice-structured triangulation (two triangles per lattice cell, e.g. the ALU ladder): vertex coordinates are a
+    // tensor product, every triangle joins lattice neighbours
+    if (ny < 1 || 2 * nx * ny != m->n_global) return;
+    std::vector<double> xs, ys;
+    xs.resize(size_t(nx1));
+    ys.resize(size_t(ny) + 1);
+    for (int64_t i = 0; i < nx1; ++i) xs[size_t(i)] = xy_host[2 * i];
+    for (int64_t j = 0; j <= ny; ++j) ys[size_t(j)] = xy_host[2 * j * nx1 + 1];
+    DevBuf<double> d_xs, d_ys;
+    d_xs.upload(xs.data(), xs.size(), s);
+    d_ys.upload(ys.data(), ys.size(), s);
+    DevBuf<int32_t> flag;
+    flag.alloc(1);
+    flag.zero(s);
+    k_struct_triangles<<<blocks_for(m->n_loc), kMgThreads, 0, s>>>(cv_dev, m->n_loc, int(nx1), n_verts, flag.p);
+    k_struct_verts<<<blocks_for(v_end - v_begin), kMgThreads, 0, s>>>(xy_dev, v_begin, v_end - v_begin, int(nx), d_xs.p, d_ys.p, flag.p);
+    count_launch(2);
+    int32_t f = 0;
+    HDD_CUDA(cudaMemcpyAsync(&f, flag.p, sizeof(f), cudaMemcpyDeviceToHost, s));
+    HDD_CUDA(cudaStreamSynchronize(s));
+    if (f == 0) {
+      m->lx = int(nx);
+      m->ly = int(ny);
+    }
+    return;
+  }
+  if (ny < 1 || nx * ny != m->n_global) return;
   // column / row coordinates from the first grid row and the first grid column of the caller's array
   std::vector<double> xs, ys;
   xs.resize(size_t(nx1));
@@ -688,20 +819,22 @@ static void build_hierarchies(hdd_swipdg* h, MgState& st) {
     MgLevel& c = *st.levels[l + 1];
     Rows rc{0, c.nv};
     const int lc = int(l) + 1;
+    const int nh = st.n_hier;
     if (lc < nd) {
       rc = row_range(c, d.b_lo[lc], d.b_hi[lc]);
     } else if (lc == nd && nd > 0) {
-      HDD_CUDA(cudaMemsetAsync(c.S.p, 0, size_t(2) * 9 * c.nv * sizeof(double), s));
+      HDD_CUDA(cudaMemsetAsync(c.S.p, 0, size_t(nh) * 9 * c.nv * sizeof(double), s));
       rc = row_range(c, d.own_lo, d.own_hi);
     }
-    k_rap<<<grid2(rc.cnt), kMgThreads, 0, s>>>(f.S.p, l == 0 ? 0 : 9 * f.nv, f.nx, f.ny, l == 0 ? 1 : 0, rc, c.S.p, 9 * c.nv);
+    k_rap<<<grid2(rc.cnt, nh), kMgThreads, 0, s>>>(f.S.p, l == 0 ? 0 : 9 * f.nv, f.nx, f.ny, (l == 0 && nh == 2) ? 1 : 0, rc, c.S.p,
+                                                  9 * c.nv);
     count_launch();
-    if (lc == nd && nd > 0) Nccl::get().all_reduce_sum(c.S.p, size_t(2) * 9 * c.nv, m->comm, s);
+    if (lc == nd && nd > 0) Nccl::get().all_reduce_sum(c.S.p, size_t(nh) * 9 * c.nv, m->comm, s);
   }
   for (size_t l = 0; l < nl; ++l) {
     MgLevel& L = *st.levels[l];
     const Rows r = int(l) < nd ? row_range(L, d.b_lo[l], d.b_hi[l]) : Rows{0, L.nv};
-    k_mg_dinv<<<dim3(unsigned(blocks_for(r.cnt)), l == 0 ? 1u : 2u), kMgThreads, 0, s>>>(L.S.p, L.nv, r, L.dinv.p);
+    k_mg_dinv<<<dim3(unsigned(blocks_for(r.cnt)), l == 0 ? 1u : unsigned(st.n_hier)), kMgThreads, 0, s>>>(L.S.p, L.nv, r, L.dinv.p);
     count_launch();
   }
   // dense inverses of the coarsest operators (s.p.d.), Gauss-Jordan on the host
@@ -711,9 +844,9 @@ static void build_hierarchies(hdd_swipdg* h, MgState& st) {
                                                            << kMaxCoarse << " vertices (stuck at " << C.nx << " x " << C.ny << ")");
   const int n = int(C.nv);
   const bool coarsest_is_finest = nl == 1;
-  std::vector<double> inv(size_t(2) * n * n);
+  std::vector<double> inv(size_t(st.n_hier) * n * n);
   std::vector<double> S(size_t(9) * n);
-  for (int t = 0; t < 2; ++t) {
+  for (int t = 0; t < st.n_hier; ++t) {
     const double* src = coarsest_is_finest ? C.S.p : C.S.p + size_t(t) * 9 * n;
     HDD_CUDA(cudaMemcpyAsync(S.data(), src, S.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
     HDD_CUDA(cudaStreamSynchronize(s));
@@ -760,30 +893,31 @@ static void vcycle(hdd_mesh* m, MgState& st, const int* done, cudaStream_t s) {
   const int nl = int(st.levels.size());
   const MgDist& d = st.dist;
   const int nd = d.on ? d.n_dist : 0;
+  const int nh = st.n_hier;
   // ---- down: pre-smoothing + restriction ---------------------------------------------------------------------------
   for (int l = 0; l + 1 < nl; ++l) {
     MgLevel& L = *st.levels[size_t(l)];
     MgLevel& Cn = *st.levels[size_t(l) + 1];
     const Rows rp = l < nd ? row_range(L, d.pre_lo[l], d.pre_hi[l]) : Rows{0, L.nv};
-    if (l == 0)
+    if (l == 0 && nh == 2)
       k_mg_pre2<<<blocks_for(rp.cnt), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, rp, L.b.p, L.x.p, L.r.p);
     else
-      k_mg_pre<<<grid2(rp.cnt), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, rp, L.b.p, L.x.p, L.r.p);
+      k_mg_pre<<<grid2(rp.cnt, nh), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, rp, L.b.p, L.x.p, L.r.p);
     Rows rc{0, Cn.nv};
     if (l + 1 < nd) {
       rc = row_range(Cn, d.b_lo[l + 1], d.b_hi[l + 1]);
     } else if (l + 1 == nd && nd > 0) {
       // first replicated level: own rows into a zeroed array, summed over the ranks
-      HDD_CUDA(cudaMemsetAsync(Cn.b.p, 0, size_t(2) * Cn.nv * sizeof(double), s));
+      HDD_CUDA(cudaMemsetAsync(Cn.b.p, 0, size_t(nh) * Cn.nv * sizeof(double), s));
       rc = row_range(Cn, d.own_lo, d.own_hi);
     }
-    k_mg_restrict<<<grid2(rc.cnt), kMgThreads, 0, s>>>(done, L.r.p, L.nx, L.ny, rc, Cn.b.p);
+    k_mg_restrict<<<grid2(rc.cnt, nh), kMgThreads, 0, s>>>(done, L.r.p, L.nx, L.ny, rc, Cn.b.p);
     count_launch(2);
-    if (l + 1 == nd && nd > 0) Nccl::get().all_reduce_sum(Cn.b.p, size_t(2) * Cn.nv, m->comm, s);
+    if (l + 1 == nd && nd > 0) Nccl::get().all_reduce_sum(Cn.b.p, size_t(nh) * Cn.nv, m->comm, s);
   }
   // ---- coarsest: dense inverse ----------------------------------------------------------------------------------------
   MgLevel& C = *st.levels.back();
-  k_mg_dense<<<dim3(unsigned(int(C.nv) + 127) / 128, 2u), 128, 0, s>>>(done, st.coarse_inv.p, int(C.nv), C.b.p, C.x.p);
+  k_mg_dense<<<dim3(unsigned(int(C.nv) + 127) / 128, unsigned(nh)), 128, 0, s>>>(done, st.coarse_inv.p, int(C.nv), C.b.p, C.x.p);
   count_launch();
   C.result = C.x.p;
   // ---- up: prolongation + post-smoothing ----------------------------------------------------------------------------
@@ -792,15 +926,15 @@ static void vcycle(hdd_mesh* m, MgState& st, const int* done, cudaStream_t s) {
     MgLevel& Cn = *st.levels[size_t(l) + 1];
     const Rows ru = l < nd ? row_range(L, d.up_lo[l], d.up_hi[l]) : Rows{0, L.nv};
     if (l > 0 && L.nv <= kFusedUpMaxVerts) {
-      k_mg_up<<<grid2(ru.cnt), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, ru, L.b.p, L.x.p, Cn.result, L.y.p);
+      k_mg_up<<<grid2(ru.cnt, nh), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, ru, L.b.p, L.x.p, Cn.result, L.y.p);
       count_launch();
     } else {
       const Rows rq = l < nd ? row_range(L, d.pro_lo[l], d.pro_hi[l]) : Rows{0, L.nv};
-      k_mg_prolong_add<<<grid2(rq.cnt), kMgThreads, 0, s>>>(done, Cn.result, L.nx, L.ny, rq, L.x.p);
-      if (l == 0)
+      k_mg_prolong_add<<<grid2(rq.cnt, nh), kMgThreads, 0, s>>>(done, Cn.result, L.nx, L.ny, rq, L.x.p);
+      if (l == 0 && nh == 2)
         k_mg_post2<<<blocks_for(ru.cnt), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, ru, L.b.p, L.x.p, L.y.p);
       else
-        k_mg_post<<<grid2(ru.cnt), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, ru, L.b.p, L.x.p, L.y.p);
+        k_mg_post<<<grid2(ru.cnt, nh), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, ru, L.b.p, L.x.p, L.y.p);
       count_launch(2);
     }
     L.result = L.y.p;
@@ -817,7 +951,7 @@ static void detect_strips(hdd_swipdg* h, MgState& st) {
   d.n_dist = 0;
   static const bool wanted = [] { const char* e = std::getenv("HDD_MG_DISTRIBUTED"); return !(e && e[0] == '0'); }();
   static const int cap = [] { const char* e = std::getenv("HDD_MG_DIST_LEVELS"); return e ? std::atoi(e) : kMaxDist; }();
-  if (m->world <= 1) return;
+  if (m->world <= 1 || m->kind != HDD_CUBE2D) return;  // simplex grids: replicated vertex levels
   cudaStream_t s = m->stream;
   DevBuf<int> mm;
   const int init[2] = {INT32_MAX, -1};
@@ -886,19 +1020,22 @@ void mg_release(MgState* st) { delete st; }
 // (re)builds both hierarchies for the frozen operator `vals`
 void mg_setup(hdd_swipdg* h, const double* vals) {
   hdd_mesh* m = h->mesh;
-  if (m->sx == 0 || h->polorder != 1)
+  const bool cube = m->kind == HDD_CUBE2D && m->sx > 0, lattice = m->kind == HDD_SIMPLEX2D && m->lx > 0;
+  if ((!cube && !lattice) || h->polorder != 1)
     HDD_THROW(HDD_ERR_REQUIREMENTS_NOT_MET,
-              "solver type 'cg.mg' needs polOrder 1 on a logically structured HDD_CUBE2D grid (vertices numbered x-fastest as by "
-              "Stuff::Grid::Providers::Cube / hdd_grid_cube); use 'cg.diagonal' or 'cg.blockdiagonal'");
+              "solver type 'cg.mg' needs polOrder 1 on a logically structured grid: HDD_CUBE2D with the vertices numbered x-fastest "
+              "(Stuff::Grid::Providers::Cube / hdd_grid_cube) or a simplex grid whose vertices form such a lattice and whose "
+              "triangles join lattice neighbours (the ALU ladder, hdd_grid_simplex); use 'cg.diagonal' or 'cg.blockdiagonal'");
   cudaStream_t s = m->stream;
   if (!h->mg) h->mg = new MgState;
   MgState& st = *h->mg;
-  st.nx = m->sx;
-  st.ny = m->sy;
-  const int64_t nv = int64_t(m->sx + 1) * (m->sy + 1);
-  if (!st.levels.empty() && (st.levels[0]->nx != m->sx || st.levels[0]->ny != m->sy)) st.levels.clear();
+  st.nx = cube ? m->sx : m->lx;
+  st.ny = cube ? m->sy : m->ly;
+  st.n_hier = cube ? 2 : 1;
+  const int64_t nv = int64_t(st.nx + 1) * (st.ny + 1);
+  if (!st.levels.empty() && (st.levels[0]->nx != st.nx || st.levels[0]->ny != st.ny)) st.levels.clear();
   if (st.levels.empty()) {  // level structure, allocation only
-    int lx = m->sx, ly = m->sy;
+    int lx = st.nx, ly = st.ny;
     for (int l = 0;; ++l) {
       std::unique_ptr<MgLevel> L(new MgLevel);
       L->nx = lx;
@@ -952,6 +1089,12 @@ void mg_setup(hdd_swipdg* h, const double* vals) {
         f0.S.p, nv, d.lower >= 0 ? lo.p : nullptr, d.upper >= 0 ? up.p : nullptr, st.nx, d.c0, d.c1, g, lo_row, hi_row);
     count_launch();
     HDD_CUDA(cudaStreamSynchronize(s));  // lo / up are freed at the end of this scope
+  } else if (lattice) {
+    if (m->world > 1) HDD_CUDA(cudaMemsetAsync(f0.S.p, 0, size_t(9) * nv * sizeof(double), s));
+    k_vertex_galerkin_p1<<<blocks_for(m->n_verts_loc), kMgThreads, 0, s>>>(h->view(), vals, m->vptr.p, m->vdof.p, m->lvert_gid.p,
+                                                                          m->cell_gv.p, m->n_verts_loc, st.nx, st.ny, f0.S.p);
+    count_launch();
+    if (m->world > 1) Nccl::get().all_reduce_sum(f0.S.p, size_t(9) * nv, m->comm, s);
   } else {
     k_vertex_galerkin<<<blocks_for(nv), kMgThreads, 0, s>>>(h->view(), vals, m->cell_v0.p, m->lex_cell.p, m->sx, m->sy, Rows{0, nv}, f0.S.p);
     count_launch();
@@ -995,6 +1138,13 @@ void mg_apply(hdd_swipdg* h, const int* done, const double* r, double* z, double
     k_ghost_unpack_twist<<<blocks_for(int64_t(hi_row - lo_row + 1) * nx1), kMgThreads, 0, s>>>(
         done, b0, b1, d.lower >= 0 ? d.tmp_lo.p : nullptr, d.upper >= 0 ? d.tmp_up.p : nullptr, st.nx, d.c0, d.c1, g, lo_row, hi_row);
     count_launch();
+  } else if (st.n_hier == 1) {
+    // lattice-structured simplex grid: conforming P1 auxiliary space, one hierarchy
+    if (multi) HDD_CUDA(cudaMemsetAsync(b0, 0, size_t(a.nv) * sizeof(double), s));
+    k_dg_restrict_p1<<<blocks_for(m->n_verts_loc), kMgThreads, 0, s>>>(done, r, m->vptr.p, m->vdof.p, m->lvert_gid.p, m->n_verts_loc,
+                                                                      m->own0, m->n_own, b0);
+    count_launch();
+    if (multi) Nccl::get().all_reduce_sum(b0, size_t(a.nv), m->comm, s);
   } else {
     k_dg_restrict<<<blocks_for(a.nv), kMgThreads, 0, s>>>(done, r, m->lex_cell.p, m->own0, m->n_own, st.nx, st.ny, Rows{0, a.nv}, b0,
                                                            multi ? nullptr : b1);
@@ -1007,15 +1157,18 @@ void mg_apply(hdd_swipdg* h, const int* done, const double* r, double* z, double
   }
   if (st.levels.size() == 1) {
     // the fine vertex grid is already small enough for the dense solve
-    k_mg_dense<<<dim3(unsigned(int(a.nv) + 127) / 128, 2u), 128, 0, s>>>(done, st.coarse_inv.p, int(a.nv), a.b.p, a.x.p);
+    k_mg_dense<<<dim3(unsigned(int(a.nv) + 127) / 128, unsigned(st.n_hier)), 128, 0, s>>>(done, st.coarse_inv.p, int(a.nv), a.b.p, a.x.p);
     count_launch();
     a.result = a.x.p;
   } else {
     vcycle(m, st, done, s);
   }
   const int grid = int(std::min<int64_t>((m->n_own + kMgThreads - 1) / kMgThreads, kMaxBlocks));
-  k_dg_prolong_dot<<<grid, kMgThreads, 0, s>>>(done, m->n_own, m->cell_v0.p + m->own0, st.nx, a.result, a.result + a.nv, r, z, p_init,
-                                               partial, sc);
+  if (st.n_hier == 1)
+    k_dg_prolong_dot_p1<<<grid, kMgThreads, 0, s>>>(done, m->n_own, m->cell_gv.p + size_t(3) * m->own0, a.result, r, z, p_init, partial, sc);
+  else
+    k_dg_prolong_dot<<<grid, kMgThreads, 0, s>>>(done, m->n_own, m->cell_v0.p + m->own0, st.nx, a.result, a.result + a.nv, r, z, p_init,
+                                                 partial, sc);
   count_launch();
   HDD_CUDA(cudaGetLastError());
 }

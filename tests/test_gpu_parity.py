@@ -588,11 +588,19 @@ def test_cg_mg_spe10_shape_parametric_and_requirements(gpu):
         um = d2.solve({"type": "cg.mg", "precision": 1e-13, "max_iter": 1000}, mu=mu)
         ud = d2.solve({"type": "cg.diagonal", "precision": 1e-13, "max_iter": 100000}, mu=mu)
         assert rel(um, ud) <= SOL_TOL
-    # needs a structured cube grid with p = 1
-    ds = hdd.SWIPDG(grids.simplex(4), problems.ESV2007())
+    # needs a logically structured grid with p = 1: a simplex grid whose vertices are not numbered as a lattice is refused
+    gs = grids.simplex(4)
+    perm = np.random.default_rng(3).permutation(gs.n_verts).astype(np.int32)
+    xy = np.empty_like(gs.xy)
+    xy[perm] = gs.xy
+    ds = hdd.SWIPDG(grids.Grid(gs.kind, xy, perm[gs.cell_verts], gs.cell_neigh), problems.ESV2007())
     ds.init()
     with pytest.raises(hdd.discretizations.requirements_not_met):
         ds.solve({"type": "cg.mg", "precision": 1e-10, "max_iter": 100})
+    dp2 = hdd.SWIPDG(grids.simplex(4), problems.ESV2007(), polorder=2)
+    dp2.init()
+    with pytest.raises(hdd.discretizations.requirements_not_met):
+        dp2.solve({"type": "cg.mg", "precision": 1e-10, "max_iter": 100})
     dq = hdd.SWIPDG(grids.cube(8), problems.ESV2007(), polorder=2)
     dq.init()
     with pytest.raises(hdd.discretizations.requirements_not_met):
@@ -870,3 +878,30 @@ def test_cube_provider_on_the_device_equals_the_flat_array_path(gpu, nx, ny, par
     opts = {"type": "cg.mg" if min(nx, ny) >= 16 else "cg.blockdiagonal", "precision": 1e-12, "max_iter": 5000}
     ua, ub = da.solve(opts), db.solve(opts)
     assert rel(ua, ub) <= 1e-12
+
+
+@pytest.mark.parametrize("s,parts", [(4, (1, 1)), (8, (4, 4)), (16, (8, 8)), (24, (2, 3))])
+def test_cg_mg_on_the_alu_ladder(gpu, s, parts):
+    """cg.mg on lattice-structured simplex grids (BASELINE configs 1, 3, 4): conforming P1 auxiliary space on the vertex
+    lattice, one hierarchy.  Against the direct solve, iteration counts flat in h (scipy prototype: 24-25, 28 for OS2014 at
+    mu = 0.1), for ESV2007 and for the parametric OS2014 operator."""
+    g = grids.simplex(s, partitions=parts)
+    d = hdd.BlockSWIPDG(g, problems.ESV2007())
+    d.init()
+    m, rp, col, A, b = oracle_system(g, o.const(1.0), o.esv2007_force())
+    u_ref = direct_solve(rp, col, A, b)
+    u, info = d.solve({"type": "cg.mg", "precision": 1e-13, "max_iter": 500}, return_info=True)
+    assert info["converged"] and rel(u, u_ref) <= SOL_TOL
+    assert info["iterations"] <= 40, info["iterations"]
+    _, ib = d.solve({"type": "cg.blockdiagonal", "precision": 1e-13, "max_iter": 50000}, return_info=True)
+    assert s < 8 or info["iterations"] < ib["iterations"] / 2
+    dp = hdd.BlockSWIPDG(g, problems.OS2014ParametricESV2007())
+    dp.init()
+    for mu in (0.1, 1.0):
+        A_mu = o.assemble_lhs(m, o.os2014_factor(mu), None, rp, col)
+        um, im = dp.solve({"type": "cg.mg", "precision": 1e-13, "max_iter": 500}, mu=mu, return_info=True)
+        assert rel(um, direct_solve(rp, col, A_mu, b)) <= SOL_TOL and im["iterations"] <= 45, (mu, im["iterations"])
+    # goldens of the ladder through the multigrid solve: eta_ESV2007 on 128 / 512 triangles
+    if s in (4, 8) and parts == (1, 1):
+        eta = d.estimate(u, "eta_ESV2007")
+        assert abs(eta - golden("linearelliptic-swipdg-expectations_esv2007_2daluconform", "eta_ESV2007")[0 if s == 4 else 1]) < 0.006 * eta
