@@ -380,6 +380,130 @@ __global__ void __launch_bounds__(kThreads, OCC)
   }
 }
 
+// K2 for P1 on triangles with a diffusion factor that is constant per cell (Constant / per-cell data: ESV2007, SPE10,
+// thermalblock).  Every integrand is then a polynomial of degree <= 2 along a face and constant in the cell, so the
+// quadrature loops of k_assemble_lhs collapse into closed forms: with I_i = int_e phi_i = h/2 and M_ij = int_e phi_i phi_j
+// = h/3, h/6 for the two nodes of the face (0 for the opposite one), b_i = omega a (grad phi_i . K^T n) constant,
+//     en/en += pen M - I b^T - b I^T,      en/ne = -I b+^T - pen M+ + b I+^T
+// (M+, I+ with the neighbour's basis: its node sitting on the same vertex).  Outward normal and face length come from the
+// gradient of the opposite node's basis function: n = -grad phi_o / |grad phi_o|, h = 2 |T| |grad phi_o|.  Same integrals
+// as the quadrature version to rounding; a third of the instructions and half the registers, so twice as many warps are
+// resident to hide the neighbour gathers.
+template <int FK, int P, int Q, int O>
+__device__ __forceinline__ void p1_face(const MeshView& m, const DevFn& fn, const Geo<HDD_SIMPLEX2D>& g, const double* gx,
+                                        const double* gy, const double* K, double area, double a_self, int k, int c, int n, int f,
+                                        double s_in, double s_bnd, double* D, double* row0, int rs, const int* nb, bool live) {
+  const double glen = sqrt(gx[O] * gx[O] + gy[O] * gy[O]);
+  const double iglen = 1.0 / glen;
+  const double nx = -gx[O] * iglen, ny = -gy[O] * iglen;
+  const double h = 2.0 * area * glen;
+  const double ktx = K[0] * nx + K[2] * ny, kty = K[1] * nx + K[3] * ny;  // K^T n
+  const double dm = nx * (K[0] * nx + K[1] * ny) + ny * (K[2] * nx + K[3] * ny);
+  const double h2 = 0.5 * h, h3 = h * (1.0 / 3.0), h6 = h * (1.0 / 6.0);
+  if (n < 0) {
+    if (m.btype && __ldg(m.btype + size_t(3) * k + f) != 1) return;
+    const double pen = s_bnd * dm * a_self / h;
+    double B[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) B[i] = a_self * (gx[i] * ktx + gy[i] * kty);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      D[P * 3 + j] -= h2 * B[j];
+      D[Q * 3 + j] -= h2 * B[j];
+      D[j * 3 + P] -= h2 * B[j];
+      D[j * 3 + Q] -= h2 * B[j];
+    }
+    D[P * 3 + P] = fma(pen, h3, D[P * 3 + P]);
+    D[Q * 3 + Q] = fma(pen, h3, D[Q * 3 + Q]);
+    D[P * 3 + Q] = fma(pen, h6, D[P * 3 + Q]);
+    D[Q * 3 + P] = fma(pen, h6, D[Q * 3 + P]);
+    return;
+  }
+  Geo<HDD_SIMPLEX2D> gn;
+  gn.load(m.cgeo, n);
+  double Kn[4];
+  load_tensor(m.tensor, n, Kn);
+  double a_nb = a_self;
+  if constexpr (FK == HDD_FN_CELLWISE) a_nb = __ldg(fn.cell + n);
+  const double ktxp = Kn[0] * nx + Kn[2] * ny, ktyp = Kn[1] * nx + Kn[3] * ny;
+  const double dp = nx * (Kn[0] * nx + Kn[1] * ny) + ny * (Kn[2] * nx + Kn[3] * ny);
+  const double isum = 1.0 / (dp + dm);
+  const double wm = dp * isum, wp = dm * isum;
+  const double pen = s_in * dp * dm * isum * 0.5 * (a_self + a_nb) / h;
+  double Bm[3], Bp[3];
+  const double hx[3] = {-gn.i00 - gn.i10, gn.i00, gn.i10}, hy[3] = {-gn.i01 - gn.i11, gn.i01, gn.i11};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    Bm[i] = wm * a_self * (gx[i] * ktx + gy[i] * kty);
+    Bp[i] = wp * a_nb * (hx[i] * ktxp + hy[i] * ktyp);
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    D[P * 3 + j] -= h2 * Bm[j];
+    D[Q * 3 + j] -= h2 * Bm[j];
+    D[j * 3 + P] -= h2 * Bm[j];
+    D[j * 3 + Q] -= h2 * Bm[j];
+  }
+  D[P * 3 + P] = fma(pen, h3, D[P * 3 + P]);
+  D[Q * 3 + Q] = fma(pen, h3, D[Q * 3 + Q]);
+  D[P * 3 + Q] = fma(pen, h6, D[P * 3 + Q]);
+  D[Q * 3 + P] = fma(pen, h6, D[Q * 3 + P]);
+  // en/ne: rows P and Q see -h/2 b+_j - pen M+ + b_i I+_j, row O only b_O I+_j
+  double E[9];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const bool onp = gn.vx[j] == g.vx[P] && gn.vy[j] == g.vy[P];
+    const bool onq = gn.vx[j] == g.vx[Q] && gn.vy[j] == g.vy[Q];
+    const double Ip = (onp || onq) ? h2 : 0.0;
+    const double mp = onp ? h3 : onq ? h6 : 0.0, mq = onq ? h3 : onp ? h6 : 0.0;
+    E[P * 3 + j] = -h2 * Bp[j] - pen * mp + Bm[P] * Ip;
+    E[Q * 3 + j] = -h2 * Bp[j] - pen * mq + Bm[Q] * Ip;
+    E[O * 3 + j] = Bm[O] * Ip;
+  }
+  if (live) store_block<3>(row0, rs, block_slot<3>(c, nb, n), E);
+}
+
+template <int FK, int OCC>
+__global__ void __launch_bounds__(kThreads, OCC)
+    k_assemble_p1_closed(MeshView m, const __grid_constant__ DevFn fn, double s_in, double s_bnd, double* __restrict__ vals) {
+  using G = Geo<HDD_SIMPLEX2D>;
+  // row blocks are 3 doubles wide: staged in shared memory and written out coalesced (see k_assemble_lhs)
+  __shared__ double stage[kThreads * 4 * 9];
+  const int k_first = blockIdx.x * blockDim.x;
+  const bool live = k_first + int(threadIdx.x) < m.n_own;
+  const int k = live ? k_first + threadIdx.x : m.n_own - 1;
+  const int c = m.own0 + k;
+  G g;
+  g.load(m.cgeo, c);
+  double K[4];
+  load_tensor(m.tensor, c, K);
+  int nb[3];
+  load_neigh<3>(m.neigh, k, nb);
+  const int rs = block_count<3>(nb) * 3;
+  const int64_t base_blk = __ldg(m.blk_start + k_first);
+  double* row0 = stage + (m.blk_start[k] - base_blk) * 9;
+  double a_self = fn.value;
+  if constexpr (FK == HDD_FN_CELLWISE) a_self = __ldg(fn.cell + c);
+  const double gx[3] = {-g.i00 - g.i10, g.i00, g.i10}, gy[3] = {-g.i01 - g.i11, g.i01, g.i11};
+  const double area = 0.5 * g.detj;
+  double D[9];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const double fx = a_self * area * (K[0] * gx[j] + K[1] * gy[j]), fy = a_self * area * (K[2] * gx[j] + K[3] * gy[j]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) D[i * 3 + j] = fx * gx[i] + fy * gy[i];
+  }
+  p1_face<FK, 0, 1, 2>(m, fn, g, gx, gy, K, area, a_self, k, c, nb[0], 0, s_in, s_bnd, D, row0, rs, nb, live);
+  p1_face<FK, 0, 2, 1>(m, fn, g, gx, gy, K, area, a_self, k, c, nb[1], 1, s_in, s_bnd, D, row0, rs, nb, live);
+  p1_face<FK, 1, 2, 0>(m, fn, g, gx, gy, K, area, a_self, k, c, nb[2], 2, s_in, s_bnd, D, row0, rs, nb, live);
+  if (live) store_block<3>(row0, rs, block_slot<3>(c, nb, c), D);
+  __syncthreads();
+  const int k_end = min(k_first + int(blockDim.x), m.n_own);
+  const int64_t total = (__ldg(m.blk_start + k_end) - base_blk) * 9;
+  double* dst = vals + base_blk * 9;
+  for (int64_t t = threadIdx.x; t < total; t += blockDim.x) dst[t] = stage[t];
+}
+
 // K2 for Q1 on axis-parallel rectangles.  Same integrals as k_assemble_lhs, with two structural facts used at compile
 // time per face F: only the two basis functions of the face's own nodes are non-zero on it (and only the two nodes of
 // the neighbour's opposite face), and normals are +-e_x / +-e_y.  That halves the fp64 work (16 instead of 32 fused
@@ -1361,9 +1485,9 @@ void launch_fill_csr(const MeshView& m, int64_t* rowptr, int32_t* col, cudaStrea
 template <int KIND>
 static void assemble_dispatch(int fk, int blocks, cudaStream_t s, const MeshView& m, const DevFn& fn, const ElemRule& vol,
                               const LineRule& fr, double si, double sb, double* values) {
-  // P1: 4 resident CTAs per SM (128 registers, a few spilled values) against 3 (144-148 registers); HDD_ASM_P1_OCC=3 picks
-  // the latter for A/B measurements
-  static const bool occ4 = [] { const char* e = std::getenv("HDD_ASM_P1_OCC"); return !(e && e[0] == '3'); }();
+  // P1 quadrature kernel (Expression factors): 3 resident CTAs per SM (144-148 registers); HDD_ASM_P1_OCC=4 squeezes it to
+  // 128 registers with a few spilled values (measured slower: 1.99 vs 1.92 ms on 16.8 M triangles)
+  static const bool occ4 = [] { const char* e = std::getenv("HDD_ASM_P1_OCC"); return e && e[0] == '4'; }();
   dispatch_fk(fk, [&](auto k) {
     if (KIND == HDD_SIMPLEX2D && occ4)
       k_assemble_lhs<KIND, decltype(k)::value, 4><<<blocks, kThreads, 0, s>>>(m, fn, vol, fr, si, sb, values);
@@ -1402,7 +1526,18 @@ void launch_assemble_lhs(const MeshView& m, const DevFn& factor_dev, int factor_
         });
     });
   } else if (m.kind == HDD_SIMPLEX2D) {
-    assemble_dispatch<HDD_SIMPLEX2D>(factor_kind, blocks, s, m, factor_dev, vol, fr, si, sb, values);
+    // HDD_ASM_P1_CLOSED=0: quadrature kernel; HDD_ASM_P1_OCC=5: 5 resident CTAs per SM (96 registers, a few spills) instead of
+    // 4 (126 registers, none) - kept for A/B measurements
+    static const bool closed = [] { const char* e = std::getenv("HDD_ASM_P1_CLOSED"); return !(e && e[0] == '0'); }();
+    static const bool occ5 = [] { const char* e = std::getenv("HDD_ASM_P1_OCC"); return e && e[0] == '5'; }();
+    if (closed && factor_kind == HDD_FN_CONSTANT && occ5)
+      k_assemble_p1_closed<HDD_FN_CONSTANT, 5><<<blocks, kThreads, 0, s>>>(m, factor_dev, si, sb, values);
+    else if (closed && factor_kind == HDD_FN_CONSTANT)
+      k_assemble_p1_closed<HDD_FN_CONSTANT, 4><<<blocks, kThreads, 0, s>>>(m, factor_dev, si, sb, values);
+    else if (closed && factor_kind == HDD_FN_CELLWISE)
+      k_assemble_p1_closed<HDD_FN_CELLWISE, 4><<<blocks, kThreads, 0, s>>>(m, factor_dev, si, sb, values);
+    else
+      assemble_dispatch<HDD_SIMPLEX2D>(factor_kind, blocks, s, m, factor_dev, vol, fr, si, sb, values);
   } else if (generic_cube) {
     assemble_dispatch<HDD_CUBE2D>(factor_kind, blocks, s, m, factor_dev, vol, fr, si, sb, values);
   } else {

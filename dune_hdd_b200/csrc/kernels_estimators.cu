@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(128, 4)
   // P0 projection of f, then int_T (f - P0 f)^2 and int_T (f - div t_h)^2 in one sweep over the residual rule: the force
   // (the expensive part: an interpreted expression per point) is evaluated once per point and never stored
   double f0 = 0.0;
+#pragma unroll 4
   for (int q = 0; q < R.p0.n; ++q) {
     double x, y;
     g.to_global(R.p0.x[q], R.p0.y[q], x, y);
@@ -206,6 +207,7 @@ __global__ void __launch_bounds__(128, 4)
   double v_r;
   {
     double rs = 0.0, rstar = 0.0;
+#pragma unroll 4
     for (int q = 0; q < R.res.n; ++q) {
       double x, y;
       g.to_global(R.res.x[q], R.res.y[q], x, y);

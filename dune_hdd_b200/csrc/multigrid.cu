@@ -609,6 +609,15 @@ __global__ void __launch_bounds__(kMgThreads)
   grid_sum<1>(v, partial, &sc->ticket_a, [sc](const double(&w)[1]) { sc->red[1] = w[0]; });
 }
 
+// lattice rows touched by the owned triangles: min / max of (vertex id / nx1) over their vertices
+__global__ void k_vertex_row_range(const int32_t* __restrict__ gv_owned, int64_t n_entries, int nx1, int* __restrict__ minmax) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n_entries) return;
+  const int row = __ldg(gv_owned + t) / nx1;
+  atomicMin(minmax, row);
+  atomicMax(minmax + 1, row);
+}
+
 __global__ void k_cell_row_range(const int32_t* __restrict__ cell_v0_owned, int32_t n_own, int nx, int* __restrict__ minmax) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_own) return;
@@ -951,18 +960,26 @@ static void detect_strips(hdd_swipdg* h, MgState& st) {
   d.n_dist = 0;
   static const bool wanted = [] { const char* e = std::getenv("HDD_MG_DISTRIBUTED"); return !(e && e[0] == '0'); }();
   static const int cap = [] { const char* e = std::getenv("HDD_MG_DIST_LEVELS"); return e ? std::atoi(e) : kMaxDist; }();
-  if (m->world <= 1 || m->kind != HDD_CUBE2D) return;  // simplex grids: replicated vertex levels
+  if (m->world <= 1) return;
   cudaStream_t s = m->stream;
   DevBuf<int> mm;
   const int init[2] = {INT32_MAX, -1};
   mm.upload(init, 2, s);
-  if (m->n_own > 0) k_cell_row_range<<<blocks_for(m->n_own), kMgThreads, 0, s>>>(m->cell_v0.p + m->own0, m->n_own, st.nx, mm.p);
+  const bool cube = m->kind == HDD_CUBE2D;
+  if (m->n_own > 0) {
+    if (cube)
+      k_cell_row_range<<<blocks_for(m->n_own), kMgThreads, 0, s>>>(m->cell_v0.p + m->own0, m->n_own, st.nx, mm.p);
+    else
+      k_vertex_row_range<<<blocks_for(int64_t(3) * m->n_own), kMgThreads, 0, s>>>(m->cell_gv.p + size_t(3) * m->own0,
+                                                                                 int64_t(3) * m->n_own, st.nx + 1, mm.p);
+  }
   count_launch();
   int got[2] = {0, 0};
   HDD_CUDA(cudaMemcpyAsync(got, mm.p, sizeof(got), cudaMemcpyDeviceToHost, s));
   HDD_CUDA(cudaStreamSynchronize(s));
-  const int c0 = got[0], c1 = got[1] + 1;
-  const bool band = m->n_own > 0 && int64_t(m->n_own) == int64_t(st.nx) * (c1 - c0);
+  // cubes: cell rows [c0, c1); triangles: the lattice rows of their vertices are [c0, c1] - two triangles per lattice cell
+  const int c0 = got[0], c1 = cube ? got[1] + 1 : got[1];
+  const bool band = m->n_own > 0 && int64_t(m->n_own) == int64_t(cube ? 1 : 2) * st.nx * (c1 - c0);
   // every rank learns every rank's band: 3 doubles per rank through one all-reduce
   std::vector<double> all(size_t(3) * m->world, 0.0);
   all[size_t(3) * m->rank] = c0;
@@ -1063,7 +1080,11 @@ void mg_setup(hdd_swipdg* h, const double* vals) {
     // g rows next to the strip from the neighbours - instead of an all-reduce of the whole operator
     const int nx1 = st.nx + 1;
     const Rows mine{int64_t(d.c0) * nx1, int64_t(d.c1 - d.c0 + 1) * nx1};
-    k_vertex_galerkin<<<blocks_for(mine.cnt), kMgThreads, 0, s>>>(h->view(), vals, m->cell_v0.p, m->lex_cell.p, m->sx, m->sy, mine, f0.S.p);
+    if (lattice)  // writes the rows of the vertices with an owned triangle: c0 .. c1
+      k_vertex_galerkin_p1<<<blocks_for(m->n_verts_loc), kMgThreads, 0, s>>>(h->view(), vals, m->vptr.p, m->vdof.p, m->lvert_gid.p,
+                                                                            m->cell_gv.p, m->n_verts_loc, st.nx, st.ny, f0.S.p);
+    else
+      k_vertex_galerkin<<<blocks_for(mine.cnt), kMgThreads, 0, s>>>(h->view(), vals, m->cell_v0.p, m->lex_cell.p, m->sx, m->sy, mine, f0.S.p);
     count_launch();
     const int g = d.ghost;
     const size_t chunk = size_t(g + 1) * nx1;
@@ -1119,7 +1140,11 @@ void mg_apply(hdd_swipdg* h, const int* done, const double* r, double* z, double
   if (d.on) {
     // vertex rows c0 .. c1 of my cells; rows c0 and c1 are shared with the ranks below / above
     const Rows mine{int64_t(d.c0) * nx1, int64_t(d.c1 - d.c0 + 1) * nx1};
-    k_dg_restrict<<<blocks_for(mine.cnt), kMgThreads, 0, s>>>(done, r, m->lex_cell.p, m->own0, m->n_own, st.nx, st.ny, mine, b0, nullptr);
+    if (st.n_hier == 1)  // triangles: every local vertex (rows c0 - 1 .. c1 + 1; the outer two receive zeros and are ghost rows)
+      k_dg_restrict_p1<<<blocks_for(m->n_verts_loc), kMgThreads, 0, s>>>(done, r, m->vptr.p, m->vdof.p, m->lvert_gid.p, m->n_verts_loc,
+                                                                        m->own0, m->n_own, b0);
+    else
+      k_dg_restrict<<<blocks_for(mine.cnt), kMgThreads, 0, s>>>(done, r, m->lex_cell.p, m->own0, m->n_own, st.nx, st.ny, mine, b0, nullptr);
     count_launch();
     const int g = d.ghost;
     const size_t cnt = size_t(g + 1) * nx1;

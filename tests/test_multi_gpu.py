@@ -18,7 +18,7 @@ def _run(env_extra):
     env.update(env_extra)
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    assert r.stdout.count("multi-GPU check ok") == 3
+    assert r.stdout.count("multi-GPU check ok") == 4
     return [line for line in r.stdout.splitlines() if line.startswith("cg.mg iterations")]
 
 
