@@ -87,6 +87,8 @@ def main():
             ua, ia = d.solve({"type": "cg.mg", "precision": 1e-13, "max_iter": 500}, mu=mu, return_info=True)
             assert np.abs(ua - u_ref[r0:r1]).max() <= 1e-8 * np.abs(u_ref).max(), "cg.mg solution on simplices"
             assert ia["iterations"] <= 45, "cg.mg iterations on simplices"
+            if rank == 0:
+                print("cg.mg iterations on triangles", n, ia["iterations"])
             prm = {"mu": 0.5, "mu_bar": 0.5, "mu_hat": 1.0, "parameter_range_min": 0.1, "parameter_range_max": 1.0}
             ind_ref = o.indicators(m, u_ref, o.esv2007_force(), o.os2014_factor(0.5), a_hat=o.os2014_factor(1.0),
                                    a_bar=o.os2014_factor(0.5), a_min=o.os2014_factor(0.1), a_max=o.os2014_factor(1.0))
