@@ -431,19 +431,20 @@ __global__ void k_mg_dinv(const double* __restrict__ S, int64_t nv, Rows rg, dou
   if (t < rg.cnt) dinv[hv + rg.beg + t] = kOmega / S[9 * hv + 4 * nv + rg.beg + t];
 }
 
-// coarsest grid: x = A^-1 b with the dense inverse, one thread per row; the inverse of the symmetric matrix is read by
-// columns, so a warp reads consecutive addresses.  Both hierarchies.
+// coarsest grid: x = A^-1 b with the dense inverse, one warp per row (lanes along the row: coalesced, 9 products per lane
+// at n = 289, then a shuffle reduction - one thread per row was a chain of n dependent loads, 50 us).  Both hierarchies.
 __global__ void k_mg_dense(const int* done, const double* __restrict__ Ainv, int n, const double* __restrict__ b,
                            double* __restrict__ x) {
   if (done && *done) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (i >= n) return;
   Ainv += size_t(blockIdx.y) * n * n;
   b += size_t(blockIdx.y) * n;
   x += size_t(blockIdx.y) * n;
   double s = 0.0;
-  for (int j = 0; j < n; ++j) s = fma(__ldg(Ainv + size_t(j) * n + i), __ldg(b + j), s);
-  x[i] = s;
+  for (int j = lane; j < n; j += 32) s = fma(__ldg(Ainv + size_t(i) * n + j), __ldg(b + j), s);
+  s = warp_sum(s);
+  if (lane == 0) x[i] = s;
 }
 
 // ---- DG level ---------------------------------------------------------------------------------------------------
@@ -926,7 +927,7 @@ static void vcycle(hdd_mesh* m, MgState& st, const int* done, cudaStream_t s) {
   }
   // ---- coarsest: dense inverse ----------------------------------------------------------------------------------------
   MgLevel& C = *st.levels.back();
-  k_mg_dense<<<dim3(unsigned(int(C.nv) + 127) / 128, unsigned(nh)), 128, 0, s>>>(done, st.coarse_inv.p, int(C.nv), C.b.p, C.x.p);
+  k_mg_dense<<<dim3(unsigned(int(C.nv) + 3) / 4, unsigned(nh)), 128, 0, s>>>(done, st.coarse_inv.p, int(C.nv), C.b.p, C.x.p);
   count_launch();
   C.result = C.x.p;
   // ---- up: prolongation + post-smoothing ----------------------------------------------------------------------------
@@ -1182,7 +1183,7 @@ void mg_apply(hdd_swipdg* h, const int* done, const double* r, double* z, double
   }
   if (st.levels.size() == 1) {
     // the fine vertex grid is already small enough for the dense solve
-    k_mg_dense<<<dim3(unsigned(int(a.nv) + 127) / 128, unsigned(st.n_hier)), 128, 0, s>>>(done, st.coarse_inv.p, int(a.nv), a.b.p, a.x.p);
+    k_mg_dense<<<dim3(unsigned(int(a.nv) + 3) / 4, unsigned(st.n_hier)), 128, 0, s>>>(done, st.coarse_inv.p, int(a.nv), a.b.p, a.x.p);
     count_launch();
     a.result = a.x.p;
   } else {
