@@ -447,6 +447,62 @@ __global__ void k_mg_dense(const int* done, const double* __restrict__ Ainv, int
   if (lane == 0) x[i] = s;
 }
 
+// Dense inverse of the coarsest operator (s.p.d., n <= kMaxCoarse) on the device: Gauss-Jordan without pivoting, one CTA per
+// hierarchy, [A | inv] in global memory (L2 resident).  Per pivot: the pivot column is saved in shared memory, then every
+// warp updates the rows that have a non-zero there (a 9-point operator: ~2 (nx + 2) rows) with its lanes along the row.
+// The host version of this loop took 7-15 ms per hierarchy and solve - at 8 GPUs a quarter of the whole solve.
+// flag |= 1 if a pivot is not positive.  twist: hierarchy 1 reads C A C from the arrays of A (single-level case).
+__global__ void __launch_bounds__(1024)
+    k_dense_inverse(const double* __restrict__ S, int64_t hs /* operator stride between the hierarchies */, int nx, int ny,
+                    int twist_h1, double* __restrict__ work, double* __restrict__ inv, int* flag) {
+  __shared__ double col[kMaxCoarse];
+  __shared__ double pivot_inv;
+  const int nx1 = nx + 1, n = nx1 * (ny + 1);
+  const int h = blockIdx.x;
+  const bool twist = twist_h1 && h == 1;
+  S += int64_t(h) * hs;
+  double* A = work + size_t(h) * n * n;
+  double* I = inv + size_t(h) * n * n;
+  for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
+    const int i = t / n, j = t - i * n;
+    const int ix = i % nx1, iy = i / nx1, jx = j % nx1, jy = j / nx1;
+    const int ex = jx - ix, ey = jy - iy;
+    double a = 0.0;
+    if (ex >= -1 && ex <= 1 && ey >= -1 && ey <= 1) {
+      a = S[int64_t((ey + 1) * 3 + ex + 1) * n + i];
+      if (twist && ((ex + ey) & 1)) a = -a;
+    }
+    A[t] = a;
+    I[t] = i == j ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+  for (int c = 0; c < n; ++c) {
+    if (threadIdx.x == 0) {
+      const double piv = A[size_t(c) * n + c];
+      if (!(piv > 0.0)) atomicOr(flag, 1);
+      pivot_inv = 1.0 / piv;
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) col[i] = i == c ? 0.0 : A[size_t(i) * n + c];
+    __syncthreads();
+    const double ip = pivot_inv;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      A[size_t(c) * n + j] *= ip;
+      I[size_t(c) * n + j] *= ip;
+    }
+    __syncthreads();
+    for (int i = warp; i < n; i += n_warps) {
+      const double f = col[i];
+      if (f == 0.0) continue;
+      for (int j = lane; j < n; j += 32) {
+        A[size_t(i) * n + j] = fma(-f, A[size_t(c) * n + j], A[size_t(i) * n + j]);
+        I[size_t(i) * n + j] = fma(-f, I[size_t(c) * n + j], I[size_t(i) * n + j]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ---- DG level ---------------------------------------------------------------------------------------------------
 // rc = P^T r (sum of the DG residual entries sitting on each vertex) and its checkerboard-signed copy
 __global__ void __launch_bounds__(kMgThreads)
@@ -693,7 +749,8 @@ struct MgDist {
 
 struct MgState {
   std::vector<std::unique_ptr<MgLevel>> levels;
-  DevBuf<double> coarse_inv;  // [n_hier][n * n]
+  DevBuf<double> coarse_inv, coarse_work;  // [n_hier][n * n]: inverse of the coarsest operators, scratch of its computation
+  DevBuf<int> coarse_flag;
   int nx = 0, ny = 0;
   int n_hier = 2;  // Q1 on cubes: plain + checkerboard-twisted hierarchy; P1 on lattice-structured simplex grids: one
   MgDist dist;
@@ -847,51 +904,26 @@ static void build_hierarchies(hdd_swipdg* h, MgState& st) {
     k_mg_dinv<<<dim3(unsigned(blocks_for(r.cnt)), l == 0 ? 1u : unsigned(st.n_hier)), kMgThreads, 0, s>>>(L.S.p, L.nv, r, L.dinv.p);
     count_launch();
   }
-  // dense inverses of the coarsest operators (s.p.d.), Gauss-Jordan on the host
+  // dense inverses of the coarsest operators (s.p.d.): Gauss-Jordan on the device, one CTA per hierarchy
   MgLevel& C = *st.levels.back();
   if (C.nv > kMaxCoarse)
     HDD_THROW(HDD_ERR_REQUIREMENTS_NOT_MET, "cg.mg: the " << st.nx << " x " << st.ny << " grid cannot be coarsened by halving down to at most "
                                                            << kMaxCoarse << " vertices (stuck at " << C.nx << " x " << C.ny << ")");
   const int n = int(C.nv);
   const bool coarsest_is_finest = nl == 1;
-  std::vector<double> inv(size_t(st.n_hier) * n * n);
-  std::vector<double> S(size_t(9) * n);
-  for (int t = 0; t < st.n_hier; ++t) {
-    const double* src = coarsest_is_finest ? C.S.p : C.S.p + size_t(t) * 9 * n;
-    HDD_CUDA(cudaMemcpyAsync(S.data(), src, S.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
-    HDD_CUDA(cudaStreamSynchronize(s));
-    if (coarsest_is_finest && t == 1)
-      for (int e = 1; e < 9; e += 2)
-        for (int i = 0; i < n; ++i) S[size_t(e) * n + i] = -S[size_t(e) * n + i];
-    std::vector<double> A(size_t(n) * n, 0.0);
-    double* I = inv.data() + size_t(t) * n * n;
-    std::fill(I, I + size_t(n) * n, 0.0);
-    const int nx1 = C.nx + 1;
-    for (int i = 0; i < n; ++i) {
-      const int ix = i % nx1, iy = i / nx1;
-      for (int ey = -1; ey <= 1; ++ey)
-        for (int ex = -1; ex <= 1; ++ex) {
-          const int jx = ix + ex, jy = iy + ey;
-          if (jx < 0 || jy < 0 || jx > C.nx || jy > C.ny) continue;
-          A[size_t(i) * n + (jx + nx1 * jy)] = S[size_t((ey + 1) * 3 + ex + 1) * n + i];
-        }
-      I[size_t(i) * n + i] = 1.0;
-    }
-    for (int c = 0; c < n; ++c) {
-      const double piv = A[size_t(c) * n + c];
-      if (!(piv > 0.0)) HDD_THROW(HDD_ERR_REQUIREMENTS_NOT_MET, "cg.mg: the coarsest operator is not positive definite");
-      const double ip = 1.0 / piv;
-      for (int j = 0; j < n; ++j) { A[size_t(c) * n + j] *= ip; I[size_t(c) * n + j] *= ip; }
-      for (int i = 0; i < n; ++i) {
-        if (i == c) continue;
-        const double f = A[size_t(i) * n + c];
-        if (f == 0.0) continue;
-        for (int j = 0; j < n; ++j) { A[size_t(i) * n + j] -= f * A[size_t(c) * n + j]; I[size_t(i) * n + j] -= f * I[size_t(c) * n + j]; }
-      }
-    }
-  }
-  st.coarse_inv.upload(inv.data(), inv.size(), s);
+  const size_t need = size_t(st.n_hier) * n * n;
+  if (st.coarse_inv.n < need) st.coarse_inv.alloc(need);
+  if (st.coarse_work.n < need) st.coarse_work.alloc(need);
+  if (!st.coarse_flag.p) st.coarse_flag.alloc(1);
+  st.coarse_flag.zero(s);
+  k_dense_inverse<<<st.n_hier, 1024, 0, s>>>(C.S.p, coarsest_is_finest ? 0 : int64_t(9) * n, C.nx, C.ny,
+                                             (coarsest_is_finest && st.n_hier == 2) ? 1 : 0, st.coarse_work.p, st.coarse_inv.p,
+                                             st.coarse_flag.p);
+  count_launch();
+  int bad = 0;
+  HDD_CUDA(cudaMemcpyAsync(&bad, st.coarse_flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   HDD_CUDA(cudaStreamSynchronize(s));
+  if (bad) HDD_THROW(HDD_ERR_REQUIREMENTS_NOT_MET, "cg.mg: the coarsest operator is not positive definite");
 }
 
 // levels with at most this many vertices prolongate and post-smooth in one kernel (launch bound there)
