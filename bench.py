@@ -531,10 +531,11 @@ def main():
     t_asm = sum(r[0] for r in results)
     t_cg = sum(r[1]["seconds"] for r in results)
     iters = results[-1][1]["iterations"]
-    stats = torch.tensor([t_asm, t_cg, wall], dtype=torch.float64, device="cuda")
+    stats = torch.tensor([t_asm, t_cg, wall] + [r[0] + r[1]["seconds"] for r in results], dtype=torch.float64, device="cuda")
     if world > 1:
         torch.distributed.all_reduce(stats, op=torch.distributed.ReduceOp.MAX)
-    t_asm, t_cg, wall = [float(v) for v in stats.cpu()]
+    t_asm, t_cg, wall = [float(v) for v in stats.cpu()[:3]]
+    step_ms = [1e3 * float(v) for v in stats.cpu()[3:]]  # per step, max over ranks: shows an outlier step for what it is
 
     # ---- what was timed is checked: true residual recomputed from scratch, error against the exact solution ----------
     res, floor = d.residual(with_floor=True)
@@ -696,7 +697,7 @@ def main():
                                                                   if args.solver == "cg.mg" else ""))
                           if world > 1 else "none")
         line = {"metric": METRIC, "value": args.steps * n_dofs / t_asm, "unit": "DoFs/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "step_ms": step_ms,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config,
                 "assemble_ms": 1e3 * t_asm / args.steps, "cg_solve_s": t_cg / args.steps, "cg_iterations": iters,

@@ -231,6 +231,37 @@ __device__ __forceinline__ void store_block(double* __restrict__ row0, int row_s
   }
 }
 
+// Write-out of rows staged in shared memory: `total` doubles, element t of the CTA's contiguous range sits at stage[t] and
+// goes to dst[t].  One elected thread hands the 16-byte aligned middle of the range to the bulk-copy engine
+// (cp.async.bulk.global.shared::cta, SASS UBLKCP) instead of every thread looping over LDS + STG; the staging buffer is laid
+// out so that shared and global addresses agree modulo 16 (the caller offsets its rows by `stage_pad(dst)` doubles).
+// Must be called by every thread of the CTA after the rows have been written; returns when the shared memory may be reused.
+__device__ __forceinline__ int stage_pad(const double* dst) { return int((reinterpret_cast<uintptr_t>(dst) >> 3) & 1); }
+
+__device__ __forceinline__ void bulk_write_out(double* __restrict__ dst, const double* stage /* = stage0 + stage_pad(dst) */,
+                                               int64_t total, bool bulk) {
+  if (!bulk) {
+    __syncthreads();
+    for (int64_t t = threadIdx.x; t < total; t += blockDim.x) dst[t] = stage[t];
+    return;
+  }
+  // make the generic-proxy writes to shared memory visible to the async proxy, then meet
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  const int head = stage_pad(dst);                       // elements in front of the first 16-byte boundary
+  const int64_t body = total > head ? ((total - head) >> 1) << 1 : 0;
+  if (threadIdx.x == 0 && body > 0) {
+    const uint32_t src = uint32_t(__cvta_generic_to_shared(stage + head));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + head), "r"(src),
+                 "r"(uint32_t(body * 8))
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+  if (threadIdx.x == 32 && head == 1 && total > 0) dst[0] = stage[0];
+  if (threadIdx.x == 64 && head + body < total) dst[head + body] = stage[head + body];
+}
+
 // K2.  SURVEY 8a rows a4 (GDT::LocalEvaluation::Elliptic), a5 (SWIPDG::Inner), a6 (SWIPDG::BoundaryLHS).
 // FK = kind of the diffusion-factor part (HDD_FN_*), resolved at compile time so that constant and cell-wise data
 // cost no function evaluation per quadrature point.  An Expression is one global function: both sides of a face
@@ -465,10 +496,11 @@ __device__ __forceinline__ void p1_face(const MeshView& m, const DevFn& fn, cons
 
 template <int FK, int OCC>
 __global__ void __launch_bounds__(kThreads, OCC)
-    k_assemble_p1_closed(MeshView m, const __grid_constant__ DevFn fn, double s_in, double s_bnd, double* __restrict__ vals) {
+    k_assemble_p1_closed(MeshView m, const __grid_constant__ DevFn fn, double s_in, double s_bnd, double* __restrict__ vals,
+                         int bulk) {
   using G = Geo<HDD_SIMPLEX2D>;
-  // row blocks are 3 doubles wide: staged in shared memory and written out coalesced (see k_assemble_lhs)
-  __shared__ double stage[kThreads * 4 * 9];
+  // row blocks are 3 doubles wide: staged in shared memory and written out as one bulk copy (see bulk_write_out)
+  __shared__ __align__(16) double stage0[kThreads * 4 * 9 + 2];
   const int k_first = blockIdx.x * blockDim.x;
   const bool live = k_first + int(threadIdx.x) < m.n_own;
   const int k = live ? k_first + threadIdx.x : m.n_own - 1;
@@ -481,6 +513,8 @@ __global__ void __launch_bounds__(kThreads, OCC)
   load_neigh<3>(m.neigh, k, nb);
   const int rs = block_count<3>(nb) * 3;
   const int64_t base_blk = __ldg(m.blk_start + k_first);
+  double* dst = vals + base_blk * 9;
+  double* stage = stage0 + stage_pad(dst);
   double* row0 = stage + (m.blk_start[k] - base_blk) * 9;
   double a_self = fn.value;
   if constexpr (FK == HDD_FN_CELLWISE) a_self = __ldg(fn.cell + c);
@@ -497,11 +531,8 @@ __global__ void __launch_bounds__(kThreads, OCC)
   p1_face<FK, 0, 2, 1>(m, fn, g, gx, gy, K, area, a_self, k, c, nb[1], 1, s_in, s_bnd, D, row0, rs, nb, live);
   p1_face<FK, 1, 2, 0>(m, fn, g, gx, gy, K, area, a_self, k, c, nb[2], 2, s_in, s_bnd, D, row0, rs, nb, live);
   if (live) store_block<3>(row0, rs, block_slot<3>(c, nb, c), D);
-  __syncthreads();
   const int k_end = min(k_first + int(blockDim.x), m.n_own);
-  const int64_t total = (__ldg(m.blk_start + k_end) - base_blk) * 9;
-  double* dst = vals + base_blk * 9;
-  for (int64_t t = threadIdx.x; t < total; t += blockDim.x) dst[t] = stage[t];
+  bulk_write_out(dst, stage, (__ldg(m.blk_start + k_end) - base_blk) * 9, bulk != 0);
 }
 
 // K2 for Q1 on axis-parallel rectangles.  Same integrals as k_assemble_lhs, with two structural facts used at compile
@@ -899,7 +930,7 @@ constexpr int kQ2Threads = kQ2Cells * 9;
 constexpr int kQ2MaxFacePts = 4;
 constexpr int kQ2TabDoubles = 2 * kQ2Cells * kQ2MaxFacePts * 2 * 9;  // A_j, C_j of two faces in flight
 constexpr int kQ2StageDoubles = kQ2Cells * 5 * 81;                    // every block of every cell of the CTA
-constexpr int kQ2SmemBytes = (kQ2TabDoubles + kQ2StageDoubles) * 8;
+constexpr int kQ2SmemBytes = (kQ2TabDoubles + kQ2StageDoubles + 2) * 8;
 
 __device__ __forceinline__ void lagrange2(double t, double* l, double* d) {
   l[0] = (1.0 - t) * (1.0 - 2.0 * t); l[1] = 4.0 * t * (1.0 - t); l[2] = t * (2.0 * t - 1.0);
@@ -1007,11 +1038,11 @@ __device__ __forceinline__ void q2_face(const MeshView& m, const DevFn& fn, cons
 template <int FK>
 __global__ void __launch_bounds__(kQ2Threads, 3)
     k_assemble_q2_cube(MeshView m, const __grid_constant__ DevFn fn, ElemRule vol, LineRule fr, double s_in, double s_bnd,
-                       double* __restrict__ vals) {
+                       double* __restrict__ vals, int bulk) {
   // A_j, C_j of the current face: [parity][cell][q][2][9]; two buffers, so that one barrier per face is enough
   extern __shared__ __align__(16) double q2_smem[];
   double (*tabs)[kQ2Cells][kQ2MaxFacePts * 2 * 9] = reinterpret_cast<double (*)[kQ2Cells][kQ2MaxFacePts * 2 * 9]>(q2_smem);
-  double* stage = q2_smem + kQ2TabDoubles;
+  double* stage0 = q2_smem + kQ2TabDoubles;
   const int cs = threadIdx.x / 9, i = threadIdx.x % 9;
   const int k_raw = blockIdx.x * kQ2Cells + cs;
   const bool live = k_raw < m.n_own;
@@ -1026,6 +1057,8 @@ __global__ void __launch_bounds__(kQ2Threads, 3)
   const int nblk = block_count<4>(nb);
   const int k_first = blockIdx.x * kQ2Cells;
   const int64_t base_blk = __ldg(m.blk_start + k_first);
+  double* out = vals + base_blk * 81;
+  double* stage = stage0 + stage_pad(out);
   double* row = stage + (__ldg(m.blk_start + k) - base_blk) * 81 + int64_t(i) * nblk * 9;
   double a_self = 0.0;
   if constexpr (FK == HDD_FN_CONSTANT) a_self = fn.value;
@@ -1059,11 +1092,8 @@ __global__ void __launch_bounds__(kQ2Threads, 3)
 #pragma unroll
     for (int j = 0; j < 9; ++j) dst[j] = D[j];
   }
-  __syncthreads();
   const int k_end = min(k_first + kQ2Cells, m.n_own);
-  const int64_t total = (__ldg(m.blk_start + k_end) - base_blk) * 81;
-  double* out = vals + base_blk * 81;
-  for (int64_t t = threadIdx.x; t < total; t += blockDim.x) out[t] = stage[t];
+  bulk_write_out(out, stage, (__ldg(m.blk_start + k_end) - base_blk) * 81, bulk != 0);
 }
 
 // Volume-pattern products (discretizations/swipdg.hh:359-443): one dense n_loc x n_loc block per cell, one thread per
@@ -1508,12 +1538,14 @@ void launch_assemble_lhs(const MeshView& m, const DevFn& factor_dev, int factor_
   static const bool generic_cube = [] { const char* e = std::getenv("HDD_ASSEMBLY_GENERIC"); return e && e[0] == '1'; }();
   static const bool tensor_ok = [] { const char* e = std::getenv("HDD_ASM_TENSOR"); return !(e && e[0] == '0'); }();
   static const bool q2_fast = [] { const char* e = std::getenv("HDD_ASM_Q2_CUBE"); return !(e && e[0] == '0'); }();
+  // HDD_ASM_BULK_STORE=0: staged rows are written out by a store loop of all threads instead of one bulk copy
+  static const int bulk_store = [] { const char* e = std::getenv("HDD_ASM_BULK_STORE"); return (e && e[0] == '0') ? 0 : 1; }();
   if (polorder == 2 && m.kind == HDD_CUBE2D && q2_fast && fr.n <= kQ2MaxFacePts) {
     // Q2 on axis-parallel rectangles: tensor-product basis, per-cell flux vectors shared through shared memory
     dispatch_fk(factor_kind, [&](auto k) {
       auto kern = k_assemble_q2_cube<decltype(k)::value>;
       HDD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kQ2SmemBytes));
-      kern<<<(m.n_own + kQ2Cells - 1) / kQ2Cells, kQ2Threads, kQ2SmemBytes, s>>>(m, factor_dev, vol, fr, si, sb, values);
+      kern<<<(m.n_own + kQ2Cells - 1) / kQ2Cells, kQ2Threads, kQ2SmemBytes, s>>>(m, factor_dev, vol, fr, si, sb, values, bulk_store);
     });
   } else if (polorder != 1) {
     // p = 2: one thread per row, 3 CTAs per SM (168 registers; 2.85 ms vs 3.48 ms with 2 at 1024^2 Q2)
@@ -1531,11 +1563,11 @@ void launch_assemble_lhs(const MeshView& m, const DevFn& factor_dev, int factor_
     static const bool closed = [] { const char* e = std::getenv("HDD_ASM_P1_CLOSED"); return !(e && e[0] == '0'); }();
     static const bool occ5 = [] { const char* e = std::getenv("HDD_ASM_P1_OCC"); return e && e[0] == '5'; }();
     if (closed && factor_kind == HDD_FN_CONSTANT && occ5)
-      k_assemble_p1_closed<HDD_FN_CONSTANT, 5><<<blocks, kThreads, 0, s>>>(m, factor_dev, si, sb, values);
+      k_assemble_p1_closed<HDD_FN_CONSTANT, 5><<<blocks, kThreads, 0, s>>>(m, factor_dev, si, sb, values, bulk_store);
     else if (closed && factor_kind == HDD_FN_CONSTANT)
-      k_assemble_p1_closed<HDD_FN_CONSTANT, 4><<<blocks, kThreads, 0, s>>>(m, factor_dev, si, sb, values);
+      k_assemble_p1_closed<HDD_FN_CONSTANT, 4><<<blocks, kThreads, 0, s>>>(m, factor_dev, si, sb, values, bulk_store);
     else if (closed && factor_kind == HDD_FN_CELLWISE)
-      k_assemble_p1_closed<HDD_FN_CELLWISE, 4><<<blocks, kThreads, 0, s>>>(m, factor_dev, si, sb, values);
+      k_assemble_p1_closed<HDD_FN_CELLWISE, 4><<<blocks, kThreads, 0, s>>>(m, factor_dev, si, sb, values, bulk_store);
     else
       assemble_dispatch<HDD_SIMPLEX2D>(factor_kind, blocks, s, m, factor_dev, vol, fr, si, sb, values);
   } else if (generic_cube) {
