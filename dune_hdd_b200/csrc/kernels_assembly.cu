@@ -236,6 +236,11 @@ __device__ __forceinline__ void store_block(double* __restrict__ row0, int row_s
 // (cp.async.bulk.global.shared::cta, SASS UBLKCP) instead of every thread looping over LDS + STG; the staging buffer is laid
 // out so that shared and global addresses agree modulo 16 (the caller offsets its rows by `stage_pad(dst)` doubles).
 // Must be called by every thread of the CTA after the rows have been written; returns when the shared memory may be reused.
+// HDD_ASM_BULK_STORE=0: staged rows are written out by a store loop of all threads instead of one bulk copy (A/B switch)
+static int bulk_store_on() {
+  static const int on = [] { const char* e = std::getenv("HDD_ASM_BULK_STORE"); return (e && e[0] == '0') ? 0 : 1; }();
+  return on;
+}
 __device__ __forceinline__ int stage_pad(const double* dst) { return int((reinterpret_cast<uintptr_t>(dst) >> 3) & 1); }
 
 __device__ __forceinline__ void bulk_write_out(double* __restrict__ dst, const double* stage /* = stage0 + stage_pad(dst) */,
@@ -279,14 +284,14 @@ __device__ __forceinline__ double factor_at(const DevFn& fn, double a_cell, doub
 template <int KIND, int FK, int OCC = 1>
 __global__ void __launch_bounds__(kThreads, OCC)
     k_assemble_lhs(MeshView m, const __grid_constant__ DevFn fn, ElemRule vol, LineRule fr, double s_in, double s_bnd,
-                   double* __restrict__ vals) {
+                   double* __restrict__ vals, int bulk) {
   using G = Geo<KIND>;
   constexpr int NL = G::NL, NF = G::NF;
   // P1 row blocks are 3 doubles wide: written straight from the registers every store instruction would touch 32
   // different sectors for 24 bytes each.  The row blocks of the CTA's cells are one contiguous range of the value array,
-  // so they are staged in shared memory and written out fully coalesced.
+  // so they are staged in shared memory and written out as one bulk copy (see bulk_write_out).
   constexpr bool kStaged = (NL == 3);
-  __shared__ double stage[kStaged ? kThreads * (NF + 1) * NL * NL : 1];
+  __shared__ __align__(16) double stage0[kStaged ? kThreads * (NF + 1) * NL * NL + 2 : 2];
   const int k_first = blockIdx.x * blockDim.x;
   const bool live = k_first + int(threadIdx.x) < m.n_own;
   if (!kStaged && !live) return;
@@ -301,6 +306,7 @@ __global__ void __launch_bounds__(kThreads, OCC)
   const int nblk = block_count<NF>(nb);
   const int rs = nblk * NL;
   const int64_t base_blk = kStaged ? __ldg(m.blk_start + k_first) : 0;
+  double* stage = stage0 + (kStaged ? stage_pad(vals + base_blk * (NL * NL)) : 0);
   double* row0 = kStaged ? stage + (m.blk_start[k] - base_blk) * (NL * NL) : vals + m.blk_start[k] * (NL * NL);
   double a_self = 0.0;
   if constexpr (FK == HDD_FN_CONSTANT) a_self = fn.value;
@@ -403,11 +409,8 @@ __global__ void __launch_bounds__(kThreads, OCC)
   }
   if (live) store_block<NL>(row0, rs, block_slot<NF>(c, nb, c), D);
   if constexpr (kStaged) {
-    __syncthreads();
     const int k_end = min(k_first + int(blockDim.x), m.n_own);
-    const int64_t total = (__ldg(m.blk_start + k_end) - base_blk) * (NL * NL);
-    double* dst = vals + base_blk * (NL * NL);
-    for (int64_t t = threadIdx.x; t < total; t += blockDim.x) dst[t] = stage[t];
+    bulk_write_out(vals + base_blk * (NL * NL), stage, (__ldg(m.blk_start + k_end) - base_blk) * (NL * NL), bulk != 0);
   }
 }
 
@@ -756,13 +759,13 @@ __device__ __forceinline__ double pick(const double* v, int i) {
 template <int KIND, int P, int FK, int MODE, int MINB = 2>
 __global__ void __launch_bounds__(kThreads, MINB)
     k_assemble_rows(MeshView m, const __grid_constant__ DevFn fn, ElemRule vol, LineRule fr, double s_in, double s_bnd,
-                    double* __restrict__ vals) {
+                    double* __restrict__ vals, int bulk) {
   using G = Elem<KIND, P>;
   constexpr int NL = G::NL, NF = G::NF;
   // The rows of the CTA are one contiguous range of the value array.  Written straight from the registers every store
   // instruction would touch 32 sectors for 8 bytes each (four partial writes per sector: the L2 request rate, not the
-  // fp64 pipe, bounded the first version); the rows are staged in shared memory and written out coalesced instead.
-  __shared__ double stage[kThreads * (NF + 1) * NL];
+  // fp64 pipe, bounded the first version); the rows are staged in shared memory and written out as one bulk copy instead.
+  __shared__ __align__(16) double stage0[kThreads * (NF + 1) * NL + 2];
   const int64_t n_rows = int64_t(m.n_own) * NL;
   const int64_t t_first = int64_t(blockIdx.x) * blockDim.x;
   const bool live = t_first + threadIdx.x < n_rows;
@@ -784,6 +787,7 @@ __global__ void __launch_bounds__(kThreads, MINB)
     base = __ldg(m.blk_start + kf) * (NL * NL) + int64_t(jf) * block_count<NF>(nbf) * NL;
   }
   const int64_t row_off = m.blk_start[k] * (NL * NL) + int64_t(i) * nblk * NL;
+  double* stage = stage0 + stage_pad(vals + base);
   double* row = stage + (row_off - base);
   double a_self = 0.0;
   if constexpr (FK == HDD_FN_CONSTANT) a_self = fn.value;
@@ -900,7 +904,6 @@ __global__ void __launch_bounds__(kThreads, MINB)
 #pragma unroll
     for (int j = 0; j < NL; ++j) dst[j] = D[j];
   }
-  __syncthreads();
   // end of the CTA's last row
   const int64_t t_last = min(t_first + int64_t(blockDim.x), n_rows) - 1;
   const int kl = int(t_last / NL), il = int(t_last % NL);
@@ -908,8 +911,7 @@ __global__ void __launch_bounds__(kThreads, MINB)
   load_neigh<NF>(m.neigh, kl, nbl);
   const int nblkl = block_count<NF>(nbl);
   const int64_t total = __ldg(m.blk_start + kl) * (NL * NL) + int64_t(il + 1) * nblkl * NL - base;
-  double* out = vals + base;
-  for (int64_t q = threadIdx.x; q < total; q += blockDim.x) out[q] = stage[q];
+  bulk_write_out(vals + base, stage, total, bulk != 0);
 }
 
 // K2 for Q2 on axis-parallel rectangles (BASELINE config 5 at p = 2).  One thread per matrix row, 32 cells per CTA.
@@ -932,7 +934,7 @@ constexpr int kQ2TabDoubles = 2 * kQ2Cells * kQ2MaxFacePts * 2 * 9;  // A_j, C_j
 constexpr int kQ2StageDoubles = kQ2Cells * 5 * 81;                    // every block of every cell of the CTA
 constexpr int kQ2SmemBytes = (kQ2TabDoubles + kQ2StageDoubles + 2) * 8;
 
-__device__ __forceinline__ void lagrange2(double t, double* l, double* d) {
+__host__ __device__ __forceinline__ void lagrange2(double t, double* l, double* d) {
   l[0] = (1.0 - t) * (1.0 - 2.0 * t); l[1] = 4.0 * t * (1.0 - t); l[2] = t * (2.0 * t - 1.0);
   d[0] = 4.0 * t - 3.0;               d[1] = 4.0 - 8.0 * t;       d[2] = 4.0 * t - 1.0;
 }
@@ -1087,6 +1089,182 @@ __global__ void __launch_bounds__(kQ2Threads, 3)
   q2_face<1, FK>(m, fn, g, K, k, c, nb[1], i, a_self, fr, s_in, s_bnd, tabs[1][cs], D, row, nb, live);
   q2_face<2, FK>(m, fn, g, K, k, c, nb[2], i, a_self, fr, s_in, s_bnd, tabs[0][cs], D, row, nb, live);
   q2_face<3, FK>(m, fn, g, K, k, c, nb[3], i, a_self, fr, s_in, s_bnd, tabs[1][cs], D, row, nb, live);
+  if (live) {
+    double* dst = row + block_slot<4>(c, nb, c) * 9;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) dst[j] = D[j];
+  }
+  const int k_end = min(k_first + kQ2Cells, m.n_own);
+  bulk_write_out(out, stage, (__ldg(m.blk_start + k_end) - base_blk) * 81, bulk != 0);
+}
+
+// K2 for Q2 on axis-parallel rectangles with a constant or cellwise factor: no quadrature loop at all.  On such a cell every
+// integrand of the SWIPDG form is a product of a function of xi and a function of eta, and the quadrature the reference
+// prescribes (tensor Gauss rule in the cell, Gauss rule on the faces) sums the two directions independently - so every
+// entry is a combination of the entries of five 3 x 3 matrices of the quadratic Lagrange basis on [0,1],
+//     M[a][b] = sum_q w_q l_a(t_q) l_b(t_q),   G[a][b] = sum_q w_q l_a(t_q) l_b'(t_q),   S[a][b] = sum_q w_q l_a'(t_q) l_b'(t_q),
+// taken with the cell rule's 1-d points (Mv, Gv, Sv: the reference's order-2 rule does not integrate these exactly, which is
+// why they are built from the rule and not from the exact integrals) and with the face rule's (Mf, Gf).  With
+// phi_j = l_aj(xi) l_bj(eta), j = aj + 3 bj, and for a face: across / along = the 1-d index across / along it,
+// u = l_across(face) in {0,1}, v = l_across'(face) / h_across, P = |e| pen (a^- + a^+), Ta = |e| omega^- a^- K^-_nn / h_across,
+// Tl = |e| omega^- a^- K^-_nt / h_along (and Ta+, Tl+ with the neighbour's data),
+//     en/en  D_ij += Mf[al_i][al_j] (P u_i u_j - Ta (u_i v_j + u_j v_i)) - Tl u_i u_j (Gf[al_i][al_j] + Gf[al_j][al_i])
+//     en/ne  E_ij  = Mf[al_i][al_j] (-P u_i u+_j - Ta+ u_i v+_j + Ta v_i u+_j) + u_i u+_j (Tl Gf[al_j][al_i] - Tl+ Gf[al_i][al_j])
+// - the sums over the face points of k_assemble_q2_cube's A_j, B_i, C_j carried out by hand.  A row costs ~300 fp64
+// operations instead of ~1400, needs no shared-memory tables and no barriers; what is left is the write-out.
+struct Q2Tables {
+  double Mf[9], Gf[9], Mv[9], Gv[9], Sv[9];
+};
+
+static Q2Tables make_q2_tables(const LineRule& vol1d, const LineRule& fr) {
+  Q2Tables T{};
+  auto fill = [](const LineRule& r, double* M, double* G, double* S) {
+    for (int q = 0; q < r.n; ++q) {
+      double l[3], d[3];
+      lagrange2(r.x[q], l, d);
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+          M[3 * a + b] += r.w[q] * l[a] * l[b];
+          G[3 * a + b] += r.w[q] * l[a] * d[b];
+          if (S) S[3 * a + b] += r.w[q] * d[a] * d[b];
+        }
+    }
+  };
+  fill(fr, T.Mf, T.Gf, nullptr);
+  fill(vol1d, T.Mv, T.Gv, T.Sv);
+  return T;
+}
+
+template <int F, int FK>
+__device__ __forceinline__ void q2_face_closed(const MeshView& m, const DevFn& fn, const Geo<HDD_CUBE2D>& g, const double* K, int k,
+                                               int c, int n, int ai, int bi, double a_self, const Q2Tables& T, double s_in,
+                                               double s_bnd, double* D, double* row, const int* nb, bool live) {
+  constexpr bool vertical = F < 2;                      // faces 0,1: x = const; faces 2,3: y = const
+  constexpr double sgn = (F == 0 || F == 2) ? -1.0 : 1.0;
+  constexpr int side = (F == 1 || F == 3) ? 2 : 0;      // 1-d node on the face: own side, the neighbour's is 2 - side
+  // l' across the face at the face coordinate (0 or 1) for the own cell and for the neighbour: (-3, 4, -1) or (1, -4, 3)
+  constexpr double dl0[3] = {-3.0, 4.0, -1.0}, dl1[3] = {1.0, -4.0, 3.0};
+  const bool inner = n >= 0;
+  if (!inner && m.btype && __ldg(m.btype + size_t(4) * k + F) != 1) return;  // Neumann face: nothing on the left-hand side
+  const int across = vertical ? ai : bi, along = vertical ? bi : ai;
+  const double u_i = across == side ? 1.0 : 0.0;
+  const double v_i = side == 0 ? pick<3>(dl0, across) : pick<3>(dl1, across);
+  const double h = vertical ? fabs(g.hy) : fabs(g.hx);
+  const double ih = vertical ? fabs(g.ihy) : fabs(g.ihx);
+  const double i_across = vertical ? g.ihx : g.ihy, i_along = vertical ? g.ihy : g.ihx;
+  const double kn_ac = sgn * (vertical ? K[0] : K[3]), kn_al = sgn * (vertical ? K[1] : K[2]);
+  const double dm = vertical ? K[0] : K[3];
+  double wm = 1.0, wp = 0.0, pen0 = s_bnd * dm * ih, a_nb = 0.0, kn_ac_p = 0.0, kn_al_p = 0.0, i_across_p = 0.0;
+  if (inner) {
+    double Kn[4];
+    load_tensor(m.tensor, n, Kn);
+    const double dp = vertical ? Kn[0] : Kn[3];
+    const double isum = 1.0 / (dp + dm);
+    wm = dp * isum;
+    wp = dm * isum;
+    pen0 = s_in * dp * dm * isum * 0.5 * ih;
+    kn_ac_p = sgn * (vertical ? Kn[0] : Kn[3]);
+    kn_al_p = sgn * (vertical ? Kn[1] : Kn[2]);
+    a_nb = a_self;
+    if constexpr (FK == HDD_FN_CELLWISE) a_nb = __ldg(fn.cell + n);
+    Geo<HDD_CUBE2D> gn;
+    gn.load(m.cgeo, n);
+    i_across_p = vertical ? gn.ihx : gn.ihy;
+  }
+  const double P = h * pen0 * (a_self + a_nb);
+  const double cm = h * wm * a_self, cp = h * wp * a_nb;
+  const double Ta = cm * i_across * kn_ac, Tl = cm * i_along * kn_al;
+  double Mi[3], Gij[3], Gji[3];
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    Mi[b] = T.Mf[along * 3 + b];
+    Gij[b] = T.Gf[along * 3 + b];
+    Gji[b] = T.Gf[b * 3 + along];
+  }
+#pragma unroll
+  for (int acj = 0; acj < 3; ++acj) {
+    const double u_j = acj == side ? 1.0 : 0.0;
+    const double v_j = side == 0 ? dl0[acj] : dl1[acj];
+    const double cD = P * u_i * u_j - Ta * (u_i * v_j + u_j * v_i);
+#pragma unroll
+    for (int alj = 0; alj < 3; ++alj) {
+      const int j = vertical ? acj + 3 * alj : alj + 3 * acj;
+      D[j] = fma(Mi[alj], cD, D[j]);
+      if (acj == side) D[j] = fma(-Tl * u_i, Gij[alj] + Gji[alj], D[j]);
+    }
+  }
+  if (!inner) return;
+  const double Tap = cp * i_across_p * kn_ac_p, Tlp = cp * i_along * kn_al_p;
+  double* dst = row + block_slot<4>(c, nb, n) * 9;
+#pragma unroll
+  for (int acj = 0; acj < 3; ++acj) {
+    const double un_j = acj == 2 - side ? 1.0 : 0.0;
+    const double vn_j = side == 0 ? dl1[acj] : dl0[acj];
+    const double cE = -P * u_i * un_j - Tap * u_i * vn_j + Ta * v_i * un_j;
+#pragma unroll
+    for (int alj = 0; alj < 3; ++alj) {
+      const int j = vertical ? acj + 3 * alj : alj + 3 * acj;
+      double e = Mi[alj] * cE;
+      if (acj == 2 - side) e = fma(u_i, Tl * Gji[alj] - Tlp * Gij[alj], e);
+      if (live) dst[j] = e;
+    }
+  }
+}
+
+constexpr int kQ2ClosedSmemBytes = (kQ2StageDoubles + 2) * 8;
+
+template <int FK>
+__global__ void __launch_bounds__(kQ2Threads, 4)
+    k_assemble_q2_closed(MeshView m, const __grid_constant__ DevFn fn, const __grid_constant__ Q2Tables T, double s_in, double s_bnd,
+                         double* __restrict__ vals, int bulk) {
+  extern __shared__ __align__(16) double q2_smem[];
+  const int cs = threadIdx.x / 9, i = threadIdx.x % 9;
+  const int k_raw = blockIdx.x * kQ2Cells + cs;
+  const bool live = k_raw < m.n_own;
+  const int k = live ? k_raw : m.n_own - 1;  // idle threads of the last CTA recompute its last cell
+  const int c = m.own0 + k;
+  Geo<HDD_CUBE2D> g;
+  g.load(m.cgeo, c);
+  double K[4];
+  load_tensor(m.tensor, c, K);
+  int nb[4];
+  load_neigh<4>(m.neigh, k, nb);
+  const int nblk = block_count<4>(nb);
+  const int k_first = blockIdx.x * kQ2Cells;
+  const int64_t base_blk = __ldg(m.blk_start + k_first);
+  double* out = vals + base_blk * 81;
+  double* stage = q2_smem + stage_pad(out);
+  double* row = stage + (__ldg(m.blk_start + k) - base_blk) * 81 + int64_t(i) * nblk * 9;
+  double a_self = fn.value;
+  if constexpr (FK == HDD_FN_CELLWISE) a_self = __ldg(fn.cell + c);
+  const int ai = i % 3, bi = i / 3;
+  // volume: a |T| sum over the four gradient pairings of (1-d matrix in x) x (1-d matrix in y)
+  double D[9];
+  {
+    const double ad = a_self * g.detj;
+    const double c0 = ad * K[0] * g.ihx * g.ihx, c1 = ad * K[2] * g.ihx * g.ihy, c2 = ad * K[1] * g.ihx * g.ihy, c3 = ad * K[3] * g.ihy * g.ihy;
+    double xS[3], xM[3], xG[3], xGt[3], yS[3], yM[3], yG[3], yGt[3];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      xS[b] = c0 * T.Sv[ai * 3 + b];
+      xM[b] = c3 * T.Mv[ai * 3 + b];
+      xG[b] = c1 * T.Gv[ai * 3 + b];   // sum w l_ai l_aj'
+      xGt[b] = c2 * T.Gv[b * 3 + ai];  // sum w l_aj l_ai'
+      yS[b] = T.Sv[bi * 3 + b];
+      yM[b] = T.Mv[bi * 3 + b];
+      yG[b] = T.Gv[bi * 3 + b];        // sum w l_bi l_bj'
+      yGt[b] = T.Gv[b * 3 + bi];       // sum w l_bj l_bi'
+    }
+#pragma unroll
+    for (int bj = 0; bj < 3; ++bj)
+#pragma unroll
+      for (int aj = 0; aj < 3; ++aj)
+        D[aj + 3 * bj] = fma(xS[aj], yM[bj], fma(xG[aj], yGt[bj], fma(xGt[aj], yG[bj], xM[aj] * yS[bj])));
+  }
+  q2_face_closed<0, FK>(m, fn, g, K, k, c, nb[0], ai, bi, a_self, T, s_in, s_bnd, D, row, nb, live);
+  q2_face_closed<1, FK>(m, fn, g, K, k, c, nb[1], ai, bi, a_self, T, s_in, s_bnd, D, row, nb, live);
+  q2_face_closed<2, FK>(m, fn, g, K, k, c, nb[2], ai, bi, a_self, T, s_in, s_bnd, D, row, nb, live);
+  q2_face_closed<3, FK>(m, fn, g, K, k, c, nb[3], ai, bi, a_self, T, s_in, s_bnd, D, row, nb, live);
   if (live) {
     double* dst = row + block_slot<4>(c, nb, c) * 9;
 #pragma unroll
@@ -1520,9 +1698,9 @@ static void assemble_dispatch(int fk, int blocks, cudaStream_t s, const MeshView
   static const bool occ4 = [] { const char* e = std::getenv("HDD_ASM_P1_OCC"); return e && e[0] == '4'; }();
   dispatch_fk(fk, [&](auto k) {
     if (KIND == HDD_SIMPLEX2D && occ4)
-      k_assemble_lhs<KIND, decltype(k)::value, 4><<<blocks, kThreads, 0, s>>>(m, fn, vol, fr, si, sb, values);
+      k_assemble_lhs<KIND, decltype(k)::value, 4><<<blocks, kThreads, 0, s>>>(m, fn, vol, fr, si, sb, values, bulk_store_on());
     else
-      k_assemble_lhs<KIND, decltype(k)::value><<<blocks, kThreads, 0, s>>>(m, fn, vol, fr, si, sb, values);
+      k_assemble_lhs<KIND, decltype(k)::value><<<blocks, kThreads, 0, s>>>(m, fn, vol, fr, si, sb, values, bulk_store_on());
   });
 }
 
@@ -1538,14 +1716,22 @@ void launch_assemble_lhs(const MeshView& m, const DevFn& factor_dev, int factor_
   static const bool generic_cube = [] { const char* e = std::getenv("HDD_ASSEMBLY_GENERIC"); return e && e[0] == '1'; }();
   static const bool tensor_ok = [] { const char* e = std::getenv("HDD_ASM_TENSOR"); return !(e && e[0] == '0'); }();
   static const bool q2_fast = [] { const char* e = std::getenv("HDD_ASM_Q2_CUBE"); return !(e && e[0] == '0'); }();
-  // HDD_ASM_BULK_STORE=0: staged rows are written out by a store loop of all threads instead of one bulk copy
-  static const int bulk_store = [] { const char* e = std::getenv("HDD_ASM_BULK_STORE"); return (e && e[0] == '0') ? 0 : 1; }();
-  if (polorder == 2 && m.kind == HDD_CUBE2D && q2_fast && fr.n <= kQ2MaxFacePts) {
+  // HDD_ASM_Q2_CLOSED=0: Q2 with a constant / cellwise factor through the quadrature kernel (A/B switch, cross-check)
+  static const bool q2_closed = [] { const char* e = std::getenv("HDD_ASM_Q2_CLOSED"); return !(e && e[0] == '0'); }();
+  if (polorder == 2 && m.kind == HDD_CUBE2D && q2_fast && q2_closed && factor_kind != HDD_FN_EXPRESSION) {
+    const Q2Tables T = make_q2_tables(line_rule(factor_order + 2 * (polorder - 1)), fr);
+    auto launch = [&](auto kern) {
+      HDD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kQ2ClosedSmemBytes));
+      kern<<<(m.n_own + kQ2Cells - 1) / kQ2Cells, kQ2Threads, kQ2ClosedSmemBytes, s>>>(m, factor_dev, T, si, sb, values, bulk_store_on());
+    };
+    if (factor_kind == HDD_FN_CONSTANT) launch(k_assemble_q2_closed<HDD_FN_CONSTANT>);
+    else launch(k_assemble_q2_closed<HDD_FN_CELLWISE>);
+  } else if (polorder == 2 && m.kind == HDD_CUBE2D && q2_fast && fr.n <= kQ2MaxFacePts) {
     // Q2 on axis-parallel rectangles: tensor-product basis, per-cell flux vectors shared through shared memory
     dispatch_fk(factor_kind, [&](auto k) {
       auto kern = k_assemble_q2_cube<decltype(k)::value>;
       HDD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kQ2SmemBytes));
-      kern<<<(m.n_own + kQ2Cells - 1) / kQ2Cells, kQ2Threads, kQ2SmemBytes, s>>>(m, factor_dev, vol, fr, si, sb, values, bulk_store);
+      kern<<<(m.n_own + kQ2Cells - 1) / kQ2Cells, kQ2Threads, kQ2SmemBytes, s>>>(m, factor_dev, vol, fr, si, sb, values, bulk_store_on());
     });
   } else if (polorder != 1) {
     // p = 2: one thread per row, 3 CTAs per SM (168 registers; 2.85 ms vs 3.48 ms with 2 at 1024^2 Q2)
@@ -1554,7 +1740,7 @@ void launch_assemble_lhs(const MeshView& m, const DevFn& factor_dev, int factor_
       if constexpr (decltype(p)::value == 2)
         dispatch_fk(factor_kind, [&](auto k) {
           k_assemble_rows<decltype(kind)::value, 2, decltype(k)::value, 0, 3>
-              <<<grid_for(rows, kThreads), kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+              <<<grid_for(rows, kThreads), kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values, bulk_store_on());
         });
     });
   } else if (m.kind == HDD_SIMPLEX2D) {
@@ -1563,11 +1749,11 @@ void launch_assemble_lhs(const MeshView& m, const DevFn& factor_dev, int factor_
     static const bool closed = [] { const char* e = std::getenv("HDD_ASM_P1_CLOSED"); return !(e && e[0] == '0'); }();
     static const bool occ5 = [] { const char* e = std::getenv("HDD_ASM_P1_OCC"); return e && e[0] == '5'; }();
     if (closed && factor_kind == HDD_FN_CONSTANT && occ5)
-      k_assemble_p1_closed<HDD_FN_CONSTANT, 5><<<blocks, kThreads, 0, s>>>(m, factor_dev, si, sb, values, bulk_store);
+      k_assemble_p1_closed<HDD_FN_CONSTANT, 5><<<blocks, kThreads, 0, s>>>(m, factor_dev, si, sb, values, bulk_store_on());
     else if (closed && factor_kind == HDD_FN_CONSTANT)
-      k_assemble_p1_closed<HDD_FN_CONSTANT, 4><<<blocks, kThreads, 0, s>>>(m, factor_dev, si, sb, values, bulk_store);
+      k_assemble_p1_closed<HDD_FN_CONSTANT, 4><<<blocks, kThreads, 0, s>>>(m, factor_dev, si, sb, values, bulk_store_on());
     else if (closed && factor_kind == HDD_FN_CELLWISE)
-      k_assemble_p1_closed<HDD_FN_CELLWISE, 4><<<blocks, kThreads, 0, s>>>(m, factor_dev, si, sb, values, bulk_store);
+      k_assemble_p1_closed<HDD_FN_CELLWISE, 4><<<blocks, kThreads, 0, s>>>(m, factor_dev, si, sb, values, bulk_store_on());
     else
       assemble_dispatch<HDD_SIMPLEX2D>(factor_kind, blocks, s, m, factor_dev, vol, fr, si, sb, values);
   } else if (generic_cube) {
@@ -1601,7 +1787,7 @@ void launch_assemble_penalty(const MeshView& m, const DevFn& factor_dev, int fac
   dispatch_elem(m.kind, polorder, [&](auto kind, auto p) {
     dispatch_fk(factor_kind, [&](auto k) {
       k_assemble_rows<decltype(kind)::value, decltype(p)::value, decltype(k)::value, 1>
-          <<<grid_for(rows, kThreads), kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values);
+          <<<grid_for(rows, kThreads), kThreads, 0, s>>>(m, factor_dev, vol, fr, si, sb, values, bulk_store_on());
     });
   });
   count_launch();
