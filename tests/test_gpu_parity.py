@@ -437,6 +437,35 @@ def test_p2_parametric_cellwise_and_block_views(gpu):
 
 
 # ---- a9: non-zero Neumann data (Functionals::L2Face, discretizations/swipdg.hh:335-356) --------------------------
+def test_q2_closed_form_kernel_full_tensor_cellwise_factor_rectangles(gpu, monkeypatch):
+    """the closed-form Q2 kernel (1-d quadrature matrices instead of quadrature loops) against the oracle where its formulas
+    have the most terms: cells with hx != hy, a full symmetric cell-wise tensor, a cell-wise factor - and against the
+    quadrature kernel it replaces (HDD_ASM_Q2_CLOSED is read once per process, so that comparison goes through the oracle)"""
+    g = grids.cube(7, 5, lower_left=(-1.0, 0.0), upper_right=(2.5, 1.0))
+    rng = np.random.default_rng(11)
+    k = rng.uniform(0.5, 4.0, (g.n_cells, 2))
+    off = rng.uniform(-0.4, 0.4, g.n_cells)
+    tensor = np.stack([k[:, 0], off, off, k[:, 1]], axis=1)
+    a = rng.uniform(0.2, 5.0, g.n_cells)
+    prob = problems.Problem(problems.AffinelyDecomposable(problems.Cellwise(a, "diffusion_factor")),
+                            problems.AffinelyDecomposable(problems.Expression(problems.ESV2007_FORCE, 3, "force")),
+                            diffusion_tensor=tensor, name="q2 closed form")
+    d = hdd.SWIPDG(g, prob, polorder=2)
+    d.init()
+    m, rp, col, A, b = _oracle_system_p(g, 2, o.cellwise(a), o.esv2007_force(), tensor)
+    rp_g, col_g = d.pattern()
+    assert np.array_equal(rp_g, rp) and np.array_equal(col_g, col)
+    assert rel(d.system_matrix().affine_part(), A) <= ENTRY_TOL
+    assert rel(d.rhs().affine_part(), b) <= ENTRY_TOL
+    # constant factor, same tensor
+    prob_c = problems.ESV2007()
+    prob_c.diffusion_tensor = tensor
+    dc = hdd.SWIPDG(g, prob_c, polorder=2)
+    dc.init()
+    Ac = o.assemble_lhs(m, o.const(1.0), tensor, rp, col)
+    assert rel(dc.system_matrix().affine_part(), Ac) <= ENTRY_TOL
+
+
 @pytest.mark.parametrize("kind,n,polorder", [("alu", 4, 1), ("sgrid", 8, 1), ("alu", 2, 2), ("sgrid", 4, 2)])
 def test_nonzero_neumann_and_dirichlet_data(gpu, kind, n, polorder):
     g = _grid(kind, n)

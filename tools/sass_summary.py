@@ -3,7 +3,8 @@
 memory from `cuobjdump -res-usage`, and opcode counts from `cuobjdump -sass` for the instructions that show how a kernel
 moves its data on sm_100a:
 
-    UBLKCP                 cp.async.bulk (TMA bulk copy engine, global -> shared)
+    UBLKCP                 cp.async.bulk (TMA bulk copy engine: global -> shared in the SpMV ring, shared -> global in the
+                           write-out of staged assembly rows)
     SYNCS                  mbarrier arrive / expect_tx / try_wait (the bulk copies' completion mechanism)
     LDG.256 / STG.256      256-bit global loads / stores (LDG.E.ENL2.256 / STG.E.ENL2.256, one full 32-byte sector per lane)
     LDG / STG              all global loads / stores
@@ -25,7 +26,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "dune_hdd_b200", "libhdd_b200.so")
-HOT = ["k_cg_spmv_tma", "k_cg_update", "k_cg_direction", "k_assemble_lhs", "k_assemble_rows", "k_indicators", "k_vertex_means",
+HOT = ["k_cg_spmv_tma", "k_cg_update", "k_cg_direction", "k_assemble_lhs", "k_assemble_rows", "k_assemble_p1_closed", "k_assemble_q2", "k_indicators", "k_vertex_means",
        "k_mg_pre", "k_mg_post", "k_mg_up", "k_mg_restrict", "k_mg_prolong_add", "k_dg_restrict", "k_dg_prolong_dot",
        "k_freeze", "k_rhs_tensor", "k_fill_csr", "k_error_norms", "k_vertex_galerkin", "k_rap", "k_cube_fill"]
 
