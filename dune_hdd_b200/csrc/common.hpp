@@ -124,6 +124,25 @@ inline cudaError_t h2d_async(void* dst, const void* src, size_t bytes, cudaStrea
   return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s);
 }
 
+// HDD_CG_PHASES=1: the solver records a CUDA event after every phase of every iteration (halo exchange, SpMV, all-reduces,
+// update, the multigrid stages, direction) - launched directly, not as a graph - and prints, at the end of the solve, the
+// time per phase summed over the iterations (this rank's device timeline).  A diagnostic: the numbers of a normal run are
+// taken without it.
+struct SolvePhases {
+  bool on = false;
+  std::vector<std::pair<const char*, cudaEvent_t>> marks;
+  void begin(cudaStream_t s) { if (on) mark("(start)", s); }
+  void mark(const char* name, cudaStream_t s) {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    marks.emplace_back(name, e);
+  }
+  void report(int rank, int iterations);  // mesh.cu
+};
+SolvePhases& phase_timer();
+
 // Device memory of the library comes from a small caching allocator (mesh.cu): a freed block is kept and handed to the next
 // request of the same size on the same device.  Discretizations are created and destroyed per solve in the reference's
 // studies (test/linearelliptic.hh:150-160) with the same sizes every time, and cudaMalloc / cudaFree synchronise the device

@@ -15,6 +15,38 @@ namespace hdd {
 
 std::atomic<int64_t> g_kernel_launches{0};
 std::atomic<int64_t> g_h2d_bytes{0}, g_d2h_bytes{0};
+
+SolvePhases& phase_timer() {
+  static SolvePhases t = [] {
+    SolvePhases x;
+    const char* e = std::getenv("HDD_CG_PHASES");
+    x.on = e && e[0] == '1';
+    return x;
+  }();
+  return t;
+}
+
+void SolvePhases::report(int rank, int iterations) {
+  if (!on || marks.size() < 2) return;
+  cudaEventSynchronize(marks.back().second);
+  std::vector<std::pair<const char*, double>> sums;
+  double total = 0.0;
+  for (size_t i = 1; i < marks.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+    total += ms;
+    bool found = false;
+    for (auto& kv : sums)
+      if (std::strcmp(kv.first, marks[i].first) == 0) { kv.second += ms; found = true; break; }
+    if (!found) sums.emplace_back(marks[i].first, double(ms));
+  }
+  std::fprintf(stderr, "[hdd phases] rank %d: %d iterations, %.3f ms\n", rank, iterations, total);
+  for (auto& kv : sums)
+    std::fprintf(stderr, "[hdd phases] rank %d   %-28s %9.3f ms  %7.1f us/iteration  %5.1f %%\n", rank, kv.first, kv.second,
+                 1e3 * kv.second / std::max(iterations, 1), 100.0 * kv.second / total);
+  for (auto& m : marks) cudaEventDestroy(m.second);
+  marks.clear();
+}
 static thread_local std::string t_last_error;
 void set_last_error(const std::string& msg) { t_last_error = msg; }
 

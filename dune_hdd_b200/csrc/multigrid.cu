@@ -503,6 +503,75 @@ __global__ void __launch_bounds__(1024)
   }
 }
 
+// The same inverse through a banded Cholesky factorisation (the 9-point operator on an nx1-wide lattice has half bandwidth
+// w = nx1 + 1): A = L L^T with L kept as a band in shared memory (n (w + 1) doubles: 44 KB for 17 x 17), then thread k solves
+// L y = e_k, L^T x = y for column k of the inverse - n independent substitutions running in lockstep, the L entries broadcast
+// from shared memory, y and x in the (L2-resident) work / inv arrays with coalesced rows.  O(n w^2 + n^2 w) operations instead
+// of the O(n^3) of Gauss-Jordan, and two barriers per column instead of three plus a sweep over every row: ~0.2 ms instead of
+// ~9 ms for the two 289 x 289 operators of the 4096^2 hierarchy (a fifth of the whole solve at 8 GPUs).
+// One CTA per hierarchy, blockDim.x >= n.  flag |= 1 if a pivot is not positive.
+__global__ void __launch_bounds__(512)
+    k_dense_inverse_banded(const double* __restrict__ S, int64_t hs, int nx, int ny, int twist_h1, double* __restrict__ work,
+                           double* __restrict__ inv, int* flag) {
+  extern __shared__ __align__(16) double Lb[];  // Lb[i * (w + 1) + d] = L[i][i - d]
+  __shared__ double piv;
+  const int nx1 = nx + 1, n = nx1 * (ny + 1), w = nx1 + 1, ld = w + 1;
+  const int h = blockIdx.x;
+  const bool twist = twist_h1 && h == 1;
+  S += int64_t(h) * hs;
+  double* Y = work + size_t(h) * n * n;
+  double* X = inv + size_t(h) * n * n;
+  for (int t = threadIdx.x; t < n * ld; t += blockDim.x) {
+    const int i = t / ld, d = t - i * ld, j = i - d;
+    double a = 0.0;
+    if (j >= 0) {
+      const int ix = i % nx1, iy = i / nx1, jx = j % nx1, jy = j / nx1;
+      const int ex = jx - ix, ey = jy - iy;
+      if (ex >= -1 && ex <= 1 && ey >= -1 && ey <= 1) {
+        a = S[int64_t((ey + 1) * 3 + ex + 1) * n + i];
+        if (twist && ((ex + ey) & 1)) a = -a;
+      }
+    }
+    Lb[t] = a;
+  }
+  __syncthreads();
+  // left-looking banded Cholesky: thread t of the first w + 1 computes L[j + t][j]
+  for (int j = 0; j < n; ++j) {
+    const int t = threadIdx.x, i = j + t;
+    double v = 0.0;
+    if (t <= w && i < n) {
+      v = Lb[i * ld + t];                          // A[i][j]
+      for (int d = 1; d + t <= w && d <= j; ++d)   // k = j - d: L[i][k] = Lb[i][t + d], L[j][k] = Lb[j][d]
+        v = fma(-Lb[i * ld + t + d], Lb[j * ld + d], v);
+      if (t == 0) {
+        if (!(v > 0.0)) atomicOr(flag, 1);
+        piv = sqrt(v);
+      }
+    }
+    __syncthreads();
+    if (t <= w && i < n) Lb[i * ld + t] = t == 0 ? piv : v / piv;
+    __syncthreads();
+  }
+  const int k = threadIdx.x;
+  if (k >= n) return;
+  // forward: L y = e_k (y_i = 0 for i < k)
+  for (int i = 0; i < n; ++i) {
+    double sacc = i == k ? 1.0 : 0.0;
+    if (i > k) {
+      const int dmax = min(w, i - k);
+      for (int d = 1; d <= dmax; ++d) sacc = fma(-Lb[i * ld + d], Y[size_t(i - d) * n + k], sacc);
+    }
+    Y[size_t(i) * n + k] = i < k ? 0.0 : sacc / Lb[i * ld];
+  }
+  // backward: L^T x = y
+  for (int i = n - 1; i >= 0; --i) {
+    double sacc = Y[size_t(i) * n + k];
+    const int dmax = min(w, n - 1 - i);
+    for (int d = 1; d <= dmax; ++d) sacc = fma(-Lb[(i + d) * ld + d], X[size_t(i + d) * n + k], sacc);
+    X[size_t(i) * n + k] = sacc / Lb[i * ld];
+  }
+}
+
 // ---- DG level ---------------------------------------------------------------------------------------------------
 // rc = P^T r (sum of the DG residual entries sitting on each vertex) and its checkerboard-signed copy
 __global__ void __launch_bounds__(kMgThreads)
@@ -751,6 +820,7 @@ struct MgState {
   std::vector<std::unique_ptr<MgLevel>> levels;
   DevBuf<double> coarse_inv, coarse_work;  // [n_hier][n * n]: inverse of the coarsest operators, scratch of its computation
   DevBuf<int> coarse_flag;
+  bool strips_known = false;
   int nx = 0, ny = 0;
   int n_hier = 2;  // Q1 on cubes: plain + checkerboard-twisted hierarchy; P1 on lattice-structured simplex grids: one
   MgDist dist;
@@ -916,9 +986,20 @@ static void build_hierarchies(hdd_swipdg* h, MgState& st) {
   if (st.coarse_work.n < need) st.coarse_work.alloc(need);
   if (!st.coarse_flag.p) st.coarse_flag.alloc(1);
   st.coarse_flag.zero(s);
-  k_dense_inverse<<<st.n_hier, 1024, 0, s>>>(C.S.p, coarsest_is_finest ? 0 : int64_t(9) * n, C.nx, C.ny,
-                                             (coarsest_is_finest && st.n_hier == 2) ? 1 : 0, st.coarse_work.p, st.coarse_inv.p,
-                                             st.coarse_flag.p);
+  // HDD_MG_COARSE_GJ=1: Gauss-Jordan instead of the banded Cholesky (A/B switch; also the fall-back for a band that does not
+  // fit into shared memory - a long thin coarsest grid)
+  static const bool gauss_jordan = [] { const char* e = std::getenv("HDD_MG_COARSE_GJ"); return e && e[0] == '1'; }();
+  const size_t band_bytes = size_t(n) * size_t(C.nx + 3) * sizeof(double);
+  if (!gauss_jordan && band_bytes <= 200 * 1024 && n <= 512) {
+    HDD_CUDA(cudaFuncSetAttribute(k_dense_inverse_banded, cudaFuncAttributeMaxDynamicSharedMemorySize, int(band_bytes)));
+    k_dense_inverse_banded<<<st.n_hier, 512, band_bytes, s>>>(C.S.p, coarsest_is_finest ? 0 : int64_t(9) * n, C.nx, C.ny,
+                                                              (coarsest_is_finest && st.n_hier == 2) ? 1 : 0, st.coarse_work.p,
+                                                              st.coarse_inv.p, st.coarse_flag.p);
+  } else {
+    k_dense_inverse<<<st.n_hier, 1024, 0, s>>>(C.S.p, coarsest_is_finest ? 0 : int64_t(9) * n, C.nx, C.ny,
+                                               (coarsest_is_finest && st.n_hier == 2) ? 1 : 0, st.coarse_work.p, st.coarse_inv.p,
+                                               st.coarse_flag.p);
+  }
   count_launch();
   int bad = 0;
   HDD_CUDA(cudaMemcpyAsync(&bad, st.coarse_flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -936,6 +1017,7 @@ static void vcycle(hdd_mesh* m, MgState& st, const int* done, cudaStream_t s) {
   const MgDist& d = st.dist;
   const int nd = d.on ? d.n_dist : 0;
   const int nh = st.n_hier;
+  SolvePhases& pt = phase_timer();
   // ---- down: pre-smoothing + restriction ---------------------------------------------------------------------------
   for (int l = 0; l + 1 < nl; ++l) {
     MgLevel& L = *st.levels[size_t(l)];
@@ -955,12 +1037,17 @@ static void vcycle(hdd_mesh* m, MgState& st, const int* done, cudaStream_t s) {
     }
     k_mg_restrict<<<grid2(rc.cnt, nh), kMgThreads, 0, s>>>(done, L.r.p, L.nx, L.ny, rc, Cn.b.p);
     count_launch(2);
-    if (l + 1 == nd && nd > 0) Nccl::get().all_reduce_sum(Cn.b.p, size_t(nh) * Cn.nv, m->comm, s);
+    pt.mark(l == 0 ? "mg down level 0" : l < nd ? "mg down distributed 1.." : "mg down replicated", s);
+    if (l + 1 == nd && nd > 0) {
+      Nccl::get().all_reduce_sum(Cn.b.p, size_t(nh) * Cn.nv, m->comm, s);
+      pt.mark("mg all-reduce coarse rhs", s);
+    }
   }
   // ---- coarsest: dense inverse ----------------------------------------------------------------------------------------
   MgLevel& C = *st.levels.back();
   k_mg_dense<<<dim3(unsigned(int(C.nv) + 3) / 4, unsigned(nh)), 128, 0, s>>>(done, st.coarse_inv.p, int(C.nv), C.b.p, C.x.p);
   count_launch();
+  pt.mark("mg dense", s);
   C.result = C.x.p;
   // ---- up: prolongation + post-smoothing ----------------------------------------------------------------------------
   for (int l = nl - 2; l >= 0; --l) {
@@ -979,6 +1066,7 @@ static void vcycle(hdd_mesh* m, MgState& st, const int* done, cudaStream_t s) {
         k_mg_post<<<grid2(ru.cnt, nh), kMgThreads, 0, s>>>(done, L.S.p, L.dinv.p, L.nx, L.ny, ru, L.b.p, L.x.p, L.y.p);
       count_launch(2);
     }
+    pt.mark(l == 0 ? "mg up level 0" : l < nd ? "mg up distributed 1.." : "mg up replicated", s);
     L.result = L.y.p;
   }
 }
@@ -1083,7 +1171,10 @@ void mg_setup(hdd_swipdg* h, const double* vals) {
   st.ny = cube ? m->sy : m->ly;
   st.n_hier = cube ? 2 : 1;
   const int64_t nv = int64_t(st.nx + 1) * (st.ny + 1);
-  if (!st.levels.empty() && (st.levels[0]->nx != st.nx || st.levels[0]->ny != st.ny)) st.levels.clear();
+  if (!st.levels.empty() && (st.levels[0]->nx != st.nx || st.levels[0]->ny != st.ny)) {
+    st.levels.clear();
+    st.strips_known = false;
+  }
   if (st.levels.empty()) {  // level structure, allocation only
     int lx = st.nx, ly = st.ny;
     for (int l = 0;; ++l) {
@@ -1105,7 +1196,14 @@ void mg_setup(hdd_swipdg* h, const double* vals) {
       ly /= 2;
     }
   }
-  detect_strips(h, st);
+  phase_timer().mark("setup mg: allocation", s);
+  // the strip layout depends on the mesh and the communicator only: decided at the first solve of this discretization
+  // (two stream synchronisations and a collective - 3 ms per solve at 2 and 8 ranks when repeated)
+  if (!st.strips_known) {
+    detect_strips(h, st);
+    st.strips_known = true;
+  }
+  phase_timer().mark("setup mg: strip detection", s);
   MgLevel& f0 = *st.levels[0];
   const MgDist& d = st.dist;
   if (d.on) {
@@ -1155,7 +1253,9 @@ void mg_setup(hdd_swipdg* h, const double* vals) {
     if (m->world > 1) Nccl::get().all_reduce_sum(f0.S.p, size_t(9) * nv, m->comm, s);
   }
   HDD_CUDA(cudaGetLastError());
+  phase_timer().mark("setup mg: level-0 operator", s);
   build_hierarchies(h, st);
+  phase_timer().mark("setup mg: coarse operators", s);
   HDD_CUDA(cudaGetLastError());
 }
 
@@ -1179,6 +1279,7 @@ void mg_apply(hdd_swipdg* h, const int* done, const double* r, double* z, double
     else
       k_dg_restrict<<<blocks_for(mine.cnt), kMgThreads, 0, s>>>(done, r, m->lex_cell.p, m->own0, m->n_own, st.nx, st.ny, mine, b0, nullptr);
     count_launch();
+    phase_timer().mark("mg dg-restrict", s);
     const int g = d.ghost;
     const size_t cnt = size_t(g + 1) * nx1;
     Nccl& nc = Nccl::get();
@@ -1192,6 +1293,7 @@ void mg_apply(hdd_swipdg* h, const int* done, const double* r, double* z, double
       nc.recv(d.tmp_lo.p, cnt, d.lower, m->comm, s);                    // its rows [c0 - g, c0]
     }
     nc.group_end();
+    phase_timer().mark("mg ghost rows send/recv", s);
     const int lo_row = d.b_lo[0], hi_row = d.b_hi[0];
     k_ghost_unpack_twist<<<blocks_for(int64_t(hi_row - lo_row + 1) * nx1), kMgThreads, 0, s>>>(
         done, b0, b1, d.lower >= 0 ? d.tmp_lo.p : nullptr, d.upper >= 0 ? d.tmp_up.p : nullptr, st.nx, d.c0, d.c1, g, lo_row, hi_row);
@@ -1213,6 +1315,7 @@ void mg_apply(hdd_swipdg* h, const int* done, const double* r, double* z, double
       count_launch();
     }
   }
+  phase_timer().mark(d.on ? "mg ghost unpack" : "mg dg-restrict", s);
   if (st.levels.size() == 1) {
     // the fine vertex grid is already small enough for the dense solve
     k_mg_dense<<<dim3(unsigned(int(a.nv) + 3) / 4, unsigned(st.n_hier)), 128, 0, s>>>(done, st.coarse_inv.p, int(a.nv), a.b.p, a.x.p);
@@ -1228,6 +1331,7 @@ void mg_apply(hdd_swipdg* h, const int* done, const double* r, double* z, double
     k_dg_prolong_dot<<<grid, kMgThreads, 0, s>>>(done, m->n_own, m->cell_v0.p + m->own0, st.nx, a.result, a.result + a.nv, r, z, p_init,
                                                  partial, sc);
   count_launch();
+  phase_timer().mark("mg dg-prolong + r.z", s);
   HDD_CUDA(cudaGetLastError());
 }
 

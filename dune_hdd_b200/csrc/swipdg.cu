@@ -849,8 +849,11 @@ int hdd_solve(hdd_swipdg* h, const char* type, double precision, int max_iter, c
     HDD_CUDA(cudaEventCreate(&e0));
     HDD_CUDA(cudaEventCreate(&e1));
     HDD_CUDA(cudaEventRecord(e0, s));
+    SolvePhases& pt = phase_timer();
+    pt.begin(s);
     const double* vals = freeze_lhs(h, mu, mu_size);
     freeze_rhs(h, mu, mu_size);
+    pt.mark("setup: freeze", s);
     const MeshView v = h->view();
     if (m->purely_neumann) {
       // discretizations/base.hh:337-345: unit_row(0), rhs[0] = 0, solve, subtract the mean
@@ -871,6 +874,7 @@ int hdd_solve(hdd_swipdg* h, const char* type, double precision, int max_iter, c
         h->z.alloc(size_t(h->n_rows));
       }
       launch_invert_diag_blocks(v, vals, h->dinv_block.p, s);
+      pt.mark("setup: block inverses", s);
       c.dinv_block = h->dinv_block.p;
       c.z = h->z.p;
       if (use_diag == 3) mg_setup(h, vals);
@@ -888,7 +892,7 @@ int hdd_solve(hdd_swipdg* h, const char* type, double precision, int max_iter, c
     const bool multi = m->world > 1;
     // multi GPU, Q1, Jacobi / identity: fused SpMV + halo read over peer memory instead of pack + send/recv
     bool p2p = multi && p2p_wanted() && use_diag < 2 && cg_spmv_uses_tma(v);
-    if (multi) {  // the decision must be collective: a rank without owned cells large enough would disagree
+    if (multi && use_diag < 2) {  // the decision must be collective: a rank without owned cells large enough would disagree
       DevBuf<double> vote;
       double want = p2p ? 0.0 : 1.0;
       vote.upload(&want, 1, s);
@@ -898,6 +902,7 @@ int hdd_solve(hdd_swipdg* h, const char* type, double precision, int max_iter, c
       p2p = (want == 0.0);
     }
     if (p2p) p2p = setup_p2p(h);
+    pt.mark("setup: solver vote", s);
     const PeerView* peer = nullptr;
     if (p2p) {
       // Jacobi diagonal including the halo (static during the solve): owned part computed here, halo exchanged once
@@ -911,23 +916,26 @@ int hdd_solve(hdd_swipdg* h, const char* type, double precision, int max_iter, c
     if (use_diag == 3) mg_apply(h, nullptr, c.r, c.z, c.p + size_t(m->own0) * h->nl, c.partial, c.sc);
     if (multi) nc.all_reduce_sum(&c.sc->red[1], 2, m->comm, s);
     launch_cg_init_finish(v, c, s);
+    pt.mark("setup: cg init", s);
     // One CG iteration = 3 kernels (+ 2 all-reduces, + ~100 small multigrid kernels for cg.mg).  The first batch is
     // launched directly (one-time attribute / buffer set-up happens there); after that two iterations (parity 0 and 1)
     // are captured into a CUDA graph and replayed, so a launch-bound iteration costs one graph launch instead of up to
     // a hundred kernel launches and does not stall the GPU when the host thread is delayed.  HDD_CG_GRAPH=0 disables it.
     auto iteration = [&](int parity) {
-      if (multi && !p2p) m->halo_exchange(c.p, h->nl);
+      if (multi && !p2p) { m->halo_exchange(c.p, h->nl); pt.mark("halo exchange (p)", s); }
       launch_cg_spmv(v, c, parity, s, peer);
-      if (multi) nc.all_reduce_sum(&c.sc->red[0], 1, m->comm, s);
+      pt.mark("spmv", s);
+      if (multi) { nc.all_reduce_sum(&c.sc->red[0], 1, m->comm, s); pt.mark("all-reduce p.q", s); }
       launch_cg_update(v, c, parity, s);
+      pt.mark("update", s);
       if (use_diag == 3) mg_apply(h, &c.sc->done[parity], c.r, c.z, nullptr, c.partial, c.sc);
-      if (multi) nc.all_reduce_sum(&c.sc->red[1], 2, m->comm, s);
+      if (multi) { nc.all_reduce_sum(&c.sc->red[1], 2, m->comm, s); pt.mark("all-reduce r.z", s); }
       launch_cg_direction(v, c, parity, s);
+      pt.mark("direction", s);
     };
     static const bool graphs_wanted = [] {
       const char* e = std::getenv("HDD_CG_GRAPH");
-      const char* t = std::getenv("HDD_MG_TIMING");
-      return !(e && e[0] == '0') && !(t && t[0] == '1');
+      return !(e && e[0] == '0') && !phase_timer().on;
     }();
     hdd_swipdg::CgGraph& cached = h->cg_graph[use_diag];
     const void* key[5] = {vals, c.p_alt, peer, c.dinv_block, m->send_buf.p};
@@ -997,6 +1005,7 @@ int hdd_solve(hdd_swipdg* h, const char* type, double precision, int max_iter, c
       }
     }
     if (m->purely_neumann) launch_subtract_mean(h->x.p, h->n_rows, h->partial.p, h->sc.p, s);
+    pt.report(m->rank, launched);
     HDD_CUDA(cudaEventRecord(e1, s));
     HDD_CUDA(cudaEventSynchronize(e1));
     float ms = 0.f;
