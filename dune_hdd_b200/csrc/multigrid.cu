@@ -790,7 +790,7 @@ struct MgLevel {
   double* result = nullptr;  // where the level's correction ends up: y after post-smoothing, x on the coarsest level
 };
 
-constexpr int kMaxDist = 3;  // at most this many finest vertex levels are swept in row strips
+constexpr int kMaxDist = 4;  // at most this many finest vertex levels are swept in row strips (ghost zones of 2, 8, 18, 38 rows)
 
 // Multi GPU, cells in full-width bands of rows stacked in rank order: the vectors of the n_dist finest vertex levels are
 // computed in row strips with ghost zones instead of exchanges.  Every array keeps its full size, so a vertex has the

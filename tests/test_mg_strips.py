@@ -146,7 +146,7 @@ def vcycle(Ss, b0, n_levels, ranges=None, reduce_coarse=None):
     return result[0]
 
 
-@pytest.mark.parametrize("world,n_dist", [(2, 1), (2, 2), (3, 2), (2, 3), (4, 3), (8, 3)])
+@pytest.mark.parametrize("world,n_dist", [(2, 1), (2, 2), (3, 2), (2, 3), (4, 3), (8, 3), (2, 4), (3, 4)])
 def test_strip_plan_reproduces_the_replicated_vcycle(world, n_dist):
     g_probe = plan(1 << 12, 1 << 10, 1 << 11, n_dist)[3]
     rows_per_rank = ((2 * g_probe + 2 + (1 << n_dist) - 1) >> n_dist) << n_dist
@@ -154,7 +154,7 @@ def test_strip_plan_reproduces_the_replicated_vcycle(world, n_dist):
     while (ny >> n_dist) % 2 == 1 and (ny >> n_dist) > 1:  # one more level below the distributed ones
         rows_per_rank += 1 << n_dist
         ny = rows_per_rank * world
-    nx = 16
+    nx = max(16, 1 << (n_dist + 2))  # at least two cells per row on the coarsest level
     n_levels = n_dist + 2
     assert ny % (1 << (n_levels - 1)) == 0
     Ss = [stencil(nx >> l, ny >> l, 100 + l) for l in range(n_levels)]
@@ -198,8 +198,8 @@ def test_strip_plan_reproduces_the_replicated_vcycle(world, n_dist):
 
 
 def test_ghost_widths():
-    """2 rows for one distributed level, 8 for two, 18 for three, symmetric for an interior strip"""
-    for n_dist, g in ((1, 2), (2, 8), (3, 18)):
+    """2 rows for one distributed level, 8 for two, 18 for three, 38 for four, symmetric for an interior strip"""
+    for n_dist, g in ((1, 2), (2, 8), (3, 18), (4, 38)):
         lv, own_lo, own_hi, ghost = plan(4096, 1024, 1536, n_dist)
         assert ghost == g
         assert lv[0]["b_lo"] == 1024 - g and lv[0]["b_hi"] == 1536 + g
