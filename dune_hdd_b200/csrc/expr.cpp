@@ -365,3 +365,10 @@ bool compile_separable(const std::string& text, const std::string& var, Program&
 }
 
 }  // namespace hdd
+
+// host view of fast_cos for the CPU tests (include/hdd_b200.h)
+extern "C" int hdd_fast_cos(const double* x, int64_t n, double* out) {
+  if (!x || !out || n < 0) return HDD_ERR_WRONG_INPUT;
+  for (int64_t i = 0; i < n; ++i) out[i] = hdd::fast_cos(x[i]);
+  return HDD_OK;
+}

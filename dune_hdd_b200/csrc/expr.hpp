@@ -168,6 +168,62 @@ HDD_HD HDD_FORCEINLINE double eval_fast(const FastFn& f, double x, double y) {
   return s;
 }
 
+// ---- branch-free cosine + the "product of cosines" form --------------------------------------------------------------------
+// cos(x) for |x| <= kFastCosMax without a branch: three-constant Cody-Waite reduction by pi/2 with fused multiply-adds
+// (exact product, one rounding per step: the reduced argument is good to the last bit in that range), then ONE polynomial
+// in r^2 whose coefficients are selected by the quadrant's parity - the fdlibm kernels: sin r = r + r^3 S(r^2),
+// cos r = 1 - r^2/2 + r^4 C(r^2) on |r| <= pi/4, both below one ulp.  The library cos() carries a slow path for huge arguments
+// behind a branch, which keeps the compiler from interleaving the evaluations at neighbouring quadrature points; this one is
+// ~16 fp64 operations of straight-line code.  Differs from cos() in the last bit at most (tests/test_host_logic.py).
+constexpr double kFastCosMax = 1.0e5;
+
+HDD_HD HDD_FORCEINLINE double fast_cos(double x) {
+  const double q = rint(x * 0.63661977236758138);  // x * 2 / pi
+  double r = fma(-q, 1.5707963267948966e+00, x);
+  r = fma(-q, 6.1232339957367574e-17, r);
+  r = fma(-q, 8.4784276603688985e-32, r);
+  const int j = int(q) + 1;  // cos x = sin(x + pi/2): quadrant of the sine
+  const bool use_cos = j & 1;
+  const double z = r * r;
+  // coefficients of the selected kernel, highest order first
+  double p = use_cos ? -1.13596475577881948265e-11 : 1.58969099521155010221e-10;
+  p = fma(p, z, use_cos ? 2.08757232129817482790e-09 : -2.50507602534068634195e-08);
+  p = fma(p, z, use_cos ? -2.75573143513906633035e-07 : 2.75573137070700676789e-06);
+  p = fma(p, z, use_cos ? 2.48015872894767294178e-05 : -1.98412698298579493134e-04);
+  p = fma(p, z, use_cos ? -1.38888888888741095749e-03 : 8.33333333332248946124e-03);
+  p = fma(p, z, use_cos ? 4.16666666666666019037e-02 : -1.66666666666666324348e-01);
+  const double base = use_cos ? fma(-0.5, z, 1.0) : r;      // 1 - r^2/2   |  r
+  const double mult = use_cos ? z * z : r * z;              // r^4         |  r^3
+  const double v = fma(mult, p, base);
+  return (j & 2) ? -v : v;
+}
+
+// f(x) = c * prod_{k < 2} cos(a_k x[0] + b_k x[1] + d_k): the shape of the ESV2007 force and exact solution and of every
+// other product of at most two sines / cosines of affine arguments (sin t = cos(t - pi/2); a missing second factor is
+// cos(0)).  Kernels that evaluate one function at many points per cell (the estimator's residual sweeps) take it as plain
+// scalars in registers: per cell the arguments become affine functions of the reference coordinates, per point the value
+// costs two fused multiply-adds and one fast_cos per factor.
+struct TrigProduct {
+  int valid;
+  double c, a[2], b[2], d[2];
+};
+
+inline TrigProduct as_trig_product(const FastFn& f) {
+  TrigProduct t{};
+  if (f.n_terms != 1 || f.t[0].n_fac < 1 || f.t[0].n_fac > 2) return t;
+  const FastFn::Term& T = f.t[0];
+  for (int k = 0; k < 2; ++k) {
+    if (k >= T.n_fac) { t.a[k] = t.b[k] = t.d[k] = 0.0; continue; }
+    if (T.kind[k] != FAST_COS && T.kind[k] != FAST_SIN) return t;
+    t.a[k] = T.a[k];
+    t.b[k] = T.b[k];
+    t.d[k] = T.kind[k] == FAST_SIN ? T.d[k] - 1.5707963267948966 : T.d[k];
+  }
+  t.c = T.c;
+  t.valid = 1;
+  return t;
+}
+
 // Tries to bring `text` (a function of var[0], var[1]) into the fast form; false (and out.n_terms = 0) if it does not fit.
 bool compile_fast(const std::string& text, const std::string& var, FastFn& out);
 

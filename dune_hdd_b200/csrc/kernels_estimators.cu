@@ -51,10 +51,15 @@ __device__ __forceinline__ double combo_cell(const DevCombo& c, const DevFn* tab
 // spills to local memory.  EXPR = false: every diffusion-factor combination is constant per cell (Constant / per-cell
 // data: ESV2007, SPE10) and is evaluated once per cell instead of once per quadrature point.
 // The P1 functions are evaluated as u(x) = u_0 + grad u . (x - v_0) instead of through the basis at mapped-back points.
-template <bool EXPR>
+// TRIG: the force is c cos(..) cos(..) of affine arguments (TrigProduct, expr.hpp; the ESV2007 force) and travels as plain
+// scalars: per cell the arguments become affine in the reference coordinates, per point the force is two fused
+// multiply-adds and one branch-free fast_cos per factor - straight-line code the compiler interleaves over the unrolled
+// points, instead of the table-driven FastFn loop around the library cos() (ncu, round 2: 8900 instructions per cell, 29 %
+// of them fp64, half of the stall samples waiting on fixed-latency dependencies).
+template <bool EXPR, bool TRIG>
 __global__ void __launch_bounds__(128, 4)
     k_indicators(const __grid_constant__ MeshView m, const __grid_constant__ IndicatorArgs a,
-                 const __grid_constant__ IndicatorRules R, double s_in, double s_bnd) {
+                 const __grid_constant__ IndicatorRules R, const __grid_constant__ TrigProduct tp, double s_in, double s_bnd) {
   using G = Geo<HDD_SIMPLEX2D>;
   constexpr int NL = 3;
   // the data functions (expression programs included) are staged in shared memory once per block
@@ -196,25 +201,58 @@ __global__ void __launch_bounds__(128, 4)
   const double div = (G0 + G1 + G2) / area;
   // P0 projection of f, then int_T (f - P0 f)^2 and int_T (f - div t_h)^2 in one sweep over the residual rule: the force
   // (the expensive part: an interpreted expression per point) is evaluated once per point and never stored
+  // TRIG: theta_k(xi, eta) = t0_k + tx_k xi + ty_k eta, the affine argument of factor k in the reference coordinates
+  double t00 = 0.0, t0x = 0.0, t0y = 0.0, t10 = 0.0, t1x = 0.0, t1y = 0.0;
+  bool trig = false;
+  if (TRIG) {
+    const double e1x = g.vx[1] - g.vx[0], e1y = g.vy[1] - g.vy[0], e2x = g.vx[2] - g.vx[0], e2y = g.vy[2] - g.vy[0];
+    t00 = fma(tp.a[0], g.vx[0], fma(tp.b[0], g.vy[0], tp.d[0]));
+    t0x = tp.a[0] * e1x + tp.b[0] * e1y;
+    t0y = tp.a[0] * e2x + tp.b[0] * e2y;
+    t10 = fma(tp.a[1], g.vx[0], fma(tp.b[1], g.vy[0], tp.d[1]));
+    t1x = tp.a[1] * e1x + tp.b[1] * e1y;
+    t1y = tp.a[1] * e2x + tp.b[1] * e2y;
+    // the whole cell inside the range of fast_cos (always, for any sensible domain); otherwise the general evaluation
+    trig = fabs(t00) + fabs(t0x) + fabs(t0y) < kFastCosMax && fabs(t10) + fabs(t1x) + fabs(t1y) < kFastCosMax;
+  }
+  auto force_at = [&](const double xi, const double eta) -> double {
+    return tp.c * fast_cos(fma(t0x, xi, fma(t0y, eta, t00))) * fast_cos(fma(t1x, xi, fma(t1y, eta, t10)));
+  };
   double f0 = 0.0;
+  if (TRIG && trig) {
+#pragma unroll 7
+    for (int q = 0; q < R.p0.n; ++q) f0 = fma(R.p0.w[q], force_at(R.p0.x[q], R.p0.y[q]), f0);
+  } else {
 #pragma unroll 4
-  for (int q = 0; q < R.p0.n; ++q) {
-    double x, y;
-    g.to_global(R.p0.x[q], R.p0.y[q], x, y);
-    f0 += R.p0.w[q] * fn_eval(force, c, x, y);
+    for (int q = 0; q < R.p0.n; ++q) {
+      double x, y;
+      g.to_global(R.p0.x[q], R.p0.y[q], x, y);
+      f0 += R.p0.w[q] * fn_eval(force, c, x, y);
+    }
   }
   f0 /= 0.5;
   double v_r;
   {
     double rs = 0.0, rstar = 0.0;
+    if (TRIG && trig) {
+#pragma unroll 5
+      for (int q = 0; q < R.res.n; ++q) {
+        const double fv = force_at(R.res.x[q], R.res.y[q]);
+        const double d = fv - f0, ds = fv - div;
+        const double w = R.res.w[q] * g.detj;
+        rs = fma(w * d, d, rs);
+        rstar = fma(w * ds, ds, rstar);
+      }
+    } else {
 #pragma unroll 4
-    for (int q = 0; q < R.res.n; ++q) {
-      double x, y;
-      g.to_global(R.res.x[q], R.res.y[q], x, y);
-      const double fv = fn_eval(force, c, x, y);
-      const double d = fv - f0, ds = fv - div;
-      rs += R.res.w[q] * g.detj * d * d;
-      rstar += R.res.w[q] * g.detj * ds * ds;
+      for (int q = 0; q < R.res.n; ++q) {
+        double x, y;
+        g.to_global(R.res.x[q], R.res.y[q], x, y);
+        const double fv = fn_eval(force, c, x, y);
+        const double d = fv - f0, ds = fv - div;
+        rs += R.res.w[q] * g.detj * d * d;
+        rstar += R.res.w[q] * g.detj * ds * ds;
+      }
     }
     a.out[1 * n + k] = rs;
     a.out[2 * n + k] = cutoff * rs;
@@ -310,10 +348,20 @@ void launch_indicators(const MeshView& m, const IndicatorArgs& a, const DevFn* f
                       combo_is_cellwise(a.a_bar, fn_table_host) && combo_is_cellwise(a.a_cut, fn_table_host) &&
                       combo_is_cellwise(a.a_min, fn_table_host) && combo_is_cellwise(a.a_max, fn_table_host));
   const int grid = (m.n_own + 127) / 128;
-  if (expr)
-    k_indicators<true><<<grid, 128, fn_bytes, s>>>(m, a, R, sigma_inner(p), sigma_boundary(p));
+  // HDD_EST_TRIG=0: the force always through the general function evaluation (A/B switch, cross-check)
+  static const bool trig_on = [] { const char* e = std::getenv("HDD_EST_TRIG"); return !(e && e[0] == '0'); }();
+  const DevFn& force = fn_table_host[a.force_idx];
+  TrigProduct tp{};
+  if (trig_on && force.kind == HDD_FN_EXPRESSION && force.fast.n_terms > 0) tp = as_trig_product(force.fast);
+  const double si = sigma_inner(p), sb = sigma_boundary(p);
+  if (expr && tp.valid)
+    k_indicators<true, true><<<grid, 128, fn_bytes, s>>>(m, a, R, tp, si, sb);
+  else if (expr)
+    k_indicators<true, false><<<grid, 128, fn_bytes, s>>>(m, a, R, tp, si, sb);
+  else if (tp.valid)
+    k_indicators<false, true><<<grid, 128, fn_bytes, s>>>(m, a, R, tp, si, sb);
   else
-    k_indicators<false><<<grid, 128, fn_bytes, s>>>(m, a, R, sigma_inner(p), sigma_boundary(p));
+    k_indicators<false, false><<<grid, 128, fn_bytes, s>>>(m, a, R, tp, si, sb);
   count_launch();
   HDD_CUDA(cudaGetLastError());
 }

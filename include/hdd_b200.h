@@ -333,6 +333,9 @@ int hdd_free(void* p);
  * first and last own row of the first replicated level, and the number of level-0 rows received from each neighbour.
  * No device needed. */
 int hdd_mg_strip_plan(int ny, int c0, int c1, int n_dist, int* out);
+/* The branch-free cosine the estimator kernel evaluates trigonometric data functions with (csrc/expr.hpp: fast_cos, valid
+ * for |x| <= 1e5), run on the host for the CPU tests: out[i] = fast_cos(x[i]).  No device needed. */
+int hdd_fast_cos(const double* x, int64_t n, double* out);
 
 /* ---- measurement ------------------------------------------------------------------------------------------------ */
 /* Times `reps` back-to-back launches of one hot kernel on the handle's stream with CUDA events (after 3 warm-up
