@@ -1336,9 +1336,13 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // K3a.  Functionals::L2Volume(force) (discretizations/swipdg.hh:253-271): rule of order(f) + p.
-template <int KIND, int P>
+// TRIG: the force is c cos(..) cos(..) of affine arguments (TrigProduct, expr.hpp): the reference-to-cell map of both cell
+// types is affine, so per cell the arguments are affine in (xi, eta) and a point costs two fast_cos instead of the general
+// function evaluation (see k_indicators).
+template <int KIND, int P, bool TRIG>
 __global__ void __launch_bounds__(kThreads)
-    k_rhs_volume(MeshView m, const __grid_constant__ DevFn fn, ElemRule vol, int accumulate, double* __restrict__ b) {
+    k_rhs_volume(MeshView m, const __grid_constant__ DevFn fn, const __grid_constant__ TrigProduct tp, ElemRule vol, int accumulate,
+                 double* __restrict__ b) {
   using G = Elem<KIND, P>;
   constexpr int NL = G::NL;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1349,11 +1353,32 @@ __global__ void __launch_bounds__(kThreads)
   double acc[NL];
 #pragma unroll
   for (int i = 0; i < NL; ++i) acc[i] = 0.0;
+  double t00 = 0.0, t0x = 0.0, t0y = 0.0, t10 = 0.0, t1x = 0.0, t1y = 0.0;
+  bool trig = false;
+  if (TRIG) {
+    double ox, oy, px, py, qx, qy;
+    g.to_global(0.0, 0.0, ox, oy);
+    g.to_global(1.0, 0.0, px, py);
+    g.to_global(0.0, 1.0, qx, qy);
+    t00 = fma(tp.a[0], ox, fma(tp.b[0], oy, tp.d[0]));
+    t0x = tp.a[0] * (px - ox) + tp.b[0] * (py - oy);
+    t0y = tp.a[0] * (qx - ox) + tp.b[0] * (qy - oy);
+    t10 = fma(tp.a[1], ox, fma(tp.b[1], oy, tp.d[1]));
+    t1x = tp.a[1] * (px - ox) + tp.b[1] * (py - oy);
+    t1y = tp.a[1] * (qx - ox) + tp.b[1] * (qy - oy);
+    trig = fabs(t00) + fabs(t0x) + fabs(t0y) < kFastCosMax && fabs(t10) + fabs(t1x) + fabs(t1y) < kFastCosMax;
+  }
   for (int q = 0; q < vol.n; ++q) {
     double phi[NL], gx[NL], gy[NL], x, y;
     g.basis(vol.x[q], vol.y[q], phi, gx, gy);
-    g.to_global(vol.x[q], vol.y[q], x, y);
-    const double fv = fn_eval(fn, c, x, y) * vol.w[q] * g.detj;
+    double fv;
+    if (TRIG && trig) {
+      fv = tp.c * fast_cos(fma(t0x, vol.x[q], fma(t0y, vol.y[q], t00))) * fast_cos(fma(t1x, vol.x[q], fma(t1y, vol.y[q], t10)));
+    } else {
+      g.to_global(vol.x[q], vol.y[q], x, y);
+      fv = fn_eval(fn, c, x, y);
+    }
+    fv *= vol.w[q] * g.detj;
 #pragma unroll
     for (int i = 0; i < NL; ++i) acc[i] += fv * phi[i];
   }
@@ -1847,8 +1872,15 @@ void launch_rhs_volume(const MeshView& m, const DevFn& force_dev, int force_orde
     return;
   }
   const ElemRule vol = element_rule(m.kind, force_order + polorder);
+  // HDD_EST_TRIG=0 also switches this kernel back to the general function evaluation
+  static const bool trig_on = [] { const char* e = std::getenv("HDD_EST_TRIG"); return !(e && e[0] == '0'); }();
+  TrigProduct tp{};
+  if (trig_on && force_dev.kind == HDD_FN_EXPRESSION && force_dev.fast.n_terms > 0) tp = as_trig_product(force_dev.fast);
   dispatch_elem(m.kind, polorder, [&](auto kind, auto p) {
-    k_rhs_volume<decltype(kind)::value, decltype(p)::value><<<grid_for(m.n_own, kThreads), kThreads, 0, s>>>(m, force_dev, vol, acc, b);
+    if (tp.valid)
+      k_rhs_volume<decltype(kind)::value, decltype(p)::value, true><<<grid_for(m.n_own, kThreads), kThreads, 0, s>>>(m, force_dev, tp, vol, acc, b);
+    else
+      k_rhs_volume<decltype(kind)::value, decltype(p)::value, false><<<grid_for(m.n_own, kThreads), kThreads, 0, s>>>(m, force_dev, tp, vol, acc, b);
   });
   count_launch();
   HDD_CUDA(cudaGetLastError());
