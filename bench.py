@@ -643,7 +643,7 @@ def main():
         h2d = float(hb.cpu()[0])
         e2e = {"value": args.steps * n_dofs / ea, "unit": "DoFs/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(n_dofs * 8), "cg_solve_s": ec / args.steps,
-               "setup_s": ea / args.steps,
+               "setup_s": ea / args.steps, "setup_steps_s": [round(v, 5) for v in e_asm],
                "note": "value = DoFs / (hdd_mesh_create from page-locked host arrays + hdd_swipdg_create + init), incl. "
                        "host-side localisation of the grid; cg_solve_s includes the D2H copy of the solution"}
 
