@@ -1787,6 +1787,9 @@ void launch_assemble_lhs(const MeshView& m, const DevFn& factor_dev, int factor_
     // resident CTAs per SM the kernel is compiled for: 3 (160 registers) for the general kernel, 4 (128) for the tensor
     // grid variant, which keeps no neighbour geometry records alive (measured 2.15 -> 2.03 ms at 4096^2; 5 CTAs spill:
     // 2.81 ms)
+    // (closed-form entries as in the P1 / Q2 kernels were tried here as well - half the fp64 work, 40 % fewer instructions,
+    // 5 resident CTAs: 2.07 ms against 2.05-2.09 ms, and 2.37 ms when a thread stores row after row instead of block after
+    // block - this kernel is limited by its scattered 32-byte-sector store stream, not by instruction issue)
     dispatch_fk(factor_kind, [&](auto k) {
       constexpr int FKV = decltype(k)::value;
       if (m.tgeo && tensor_ok)
