@@ -645,7 +645,8 @@ def main():
                "d2h_bytes_per_step": int(n_dofs * 8), "cg_solve_s": ec / args.steps,
                "setup_s": ea / args.steps, "setup_steps_s": [round(v, 5) for v in e_asm],
                "note": "value = DoFs / (hdd_mesh_create from page-locked host arrays + hdd_swipdg_create + init), incl. "
-                       "host-side localisation of the grid; cg_solve_s includes the D2H copy of the solution"}
+                       "host-side localisation of the grid; cg_solve_s includes the D2H copy of the solution; the expanded CSR "
+                       "index arrays (a consumer view no kernel reads, 3.1 ms to write) are built at the first hdd_pattern call"}
 
     # the same end to end with the grid provider's three vectors instead of flat arrays (hdd_mesh_create_cube: what the
     # reference's own test case hands over, testcases/ESV2007.hh:123-127); reported next to `e2e`, which keeps the host arrays

@@ -167,14 +167,17 @@ enum { HDD_LHS = 0, HDD_RHS = 1 };
 int hdd_swipdg_create(hdd_mesh* mesh, int polorder, const hdd_problem* problem, hdd_swipdg** out);
 int hdd_swipdg_destroy(hdd_swipdg* h);
 
-/* SWIPDG::init() (discretizations/swipdg.hh:206-512): pattern + all affine parts of the system matrix and of
- * the rhs, assembled on the GPU in one pass per part set.  Idempotent (container_based_initialized_, :208,:510). */
+/* SWIPDG::init() (discretizations/swipdg.hh:206-512): all affine parts of the system matrix (on the block-compressed
+ * pattern, see hdd_pattern) and of the rhs, assembled on the GPU in one pass per part set.  Idempotent
+ * (container_based_initialized_, :208,:510). */
 int hdd_swipdg_init(hdd_swipdg* h);
 /* Re-runs only system_assembler.walk() (:485) on an initialised handle; used by the benchmark. seconds may be NULL. */
 int hdd_swipdg_assemble(hdd_swipdg* h, double* seconds);
 
 int hdd_num_dofs(const hdd_swipdg* h, int64_t* n_global, int64_t* n_owned);   /* space.mapper().size() */
-/* pattern() (discretizations/swipdg.hh:201-204) as CSR of the owned rows; col holds global DoF indices. */
+/* pattern() (discretizations/swipdg.hh:201-204) as CSR of the owned rows; col holds global DoF indices.  The library keeps
+ * the pattern in block-compressed form (block offsets per cell + the neighbour table, built with the mesh); the expanded
+ * index arrays are written on the device at the first call that asks for rowptr_dev or col_dev and kept from then on. */
 int hdd_pattern(hdd_swipdg* h, int64_t* n_rows, int64_t* nnz, const int64_t** rowptr_dev, const int32_t** col_dev);
 /* system_matrix()/rhs() parts (discretizations/base.hh:240-270): num_components(), component(q), coefficient(q),
  * has_affine_part(), affine_part().  q = -1 addresses the affine part. */
