@@ -1668,10 +1668,13 @@ void launch_count_blocks(const MeshView& m, int64_t* nblk, cudaStream_t s) {
 void exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, cudaStream_t s) {
   size_t bytes = 0;
   HDD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, int(n), s));
-  void* tmp = nullptr;
-  HDD_CUDA(cudaMallocAsync(&tmp, bytes, s));
-  HDD_CUDA(cub::DeviceScan::ExclusiveSum(tmp, bytes, in, out, int(n), s));
-  HDD_CUDA(cudaFreeAsync(tmp, s));
+  // scratch from the library's caching allocator: the stream-ordered allocator (cudaMallocAsync) grows and trims its pool
+  // at synchronisation points, and with peer access enabled a fresh block is mapped on every peer - measured as sporadic
+  // 10-190 ms stalls of this call on 2 ranks
+  DevBuf<unsigned char> tmp;
+  tmp.alloc(bytes > 0 ? bytes : 1);
+  HDD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, in, out, int(n), s));
+  HDD_CUDA(cudaStreamSynchronize(s));  // the scratch goes back to the cache when tmp leaves scope
   count_launch(2);
 }
 
