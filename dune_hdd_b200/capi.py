@@ -64,7 +64,7 @@ SYMBOLS = [
     "hdd_kernel_bytes", "hdd_expression_evaluate", "hdd_partition_plan", "hdd_free",
     "hdd_swipdg_only_these_products", "hdd_products_available", "hdd_product_num_components", "hdd_product_values",
     "hdd_product_coefficient", "hdd_pattern_volume", "hdd_product_apply2", "hdd_error_norms",
-    "hdd_host_alloc", "hdd_host_free", "hdd_grid_fathers", "hdd_prolong", "hdd_residual", "hdd_mg_strip_plan", "hdd_fast_cos", "hdd_partition_plan_local", "hdd_mesh_create_cube", "hdd_h2d_bytes",
+    "hdd_host_alloc", "hdd_host_free", "hdd_grid_fathers", "hdd_prolong", "hdd_residual", "hdd_mg_strip_plan", "hdd_fast_cos", "hdd_trig_product", "hdd_partition_plan_local", "hdd_mesh_create_cube", "hdd_h2d_bytes",
 ]
 
 _lib = None

@@ -372,3 +372,19 @@ extern "C" int hdd_fast_cos(const double* x, int64_t n, double* out) {
   for (int64_t i = 0; i < n; ++i) out[i] = hdd::fast_cos(x[i]);
   return HDD_OK;
 }
+
+// host view of the TrigProduct recognition for the CPU tests (include/hdd_b200.h): out[7] = c, a0, b0, d0, a1, b1, d1
+extern "C" int hdd_trig_product(const char* expression, double* out, int* valid) {
+  if (!expression || !out || !valid) return HDD_ERR_WRONG_INPUT;
+  try {
+    hdd::FastFn f;
+    hdd::TrigProduct t{};
+    if (hdd::compile_fast(expression, "x", f)) t = hdd::as_trig_product(f);
+    *valid = t.valid;
+    const double v[7] = {t.c, t.a[0], t.b[0], t.d[0], t.a[1], t.b[1], t.d[1]};
+    for (int k = 0; k < 7; ++k) out[k] = v[k];
+    return HDD_OK;
+  } catch (const hdd::Error& e) {
+    return e.status;
+  }
+}

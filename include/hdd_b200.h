@@ -339,6 +339,11 @@ int hdd_mg_strip_plan(int ny, int c0, int c1, int n_dist, int* out);
 /* The branch-free cosine the estimator kernel evaluates trigonometric data functions with (csrc/expr.hpp: fast_cos, valid
  * for |x| <= 1e5), run on the host for the CPU tests: out[i] = fast_cos(x[i]).  No device needed. */
 int hdd_fast_cos(const double* x, int64_t n, double* out);
+/* Whether the kernels would evaluate the Expression `expression` (variable "x") as a product of at most two cosines of
+ * affine arguments (csrc/expr.hpp: TrigProduct), and with which numbers: out[7] = c, a0, b0, d0, a1, b1, d1 of
+ * c cos(a0 x[0] + b0 x[1] + d0) cos(a1 x[0] + b1 x[1] + d1); *valid = 0 if the expression has another shape (it is then
+ * evaluated by the general path).  For the CPU tests; no device needed. */
+int hdd_trig_product(const char* expression, double* out, int* valid);
 
 /* ---- measurement ------------------------------------------------------------------------------------------------ */
 /* Times `reps` back-to-back launches of one hot kernel on the handle's stream with CUDA events (after 3 warm-up

@@ -263,3 +263,36 @@ def test_fast_cos_is_within_two_ulp_of_cos():
     one = np.zeros(1)
     capi.check(L.hdd_fast_cos(capi.ptr(np.zeros(1)), C.c_int64(1), capi.ptr(one)))
     assert one[0] == 1.0  # a missing second factor of a TrigProduct is cos(0)
+
+
+def test_trig_product_recognition_and_values():
+    """csrc/expr.hpp as_trig_product through hdd_trig_product: products of at most two sines / cosines of affine arguments
+    are recognised (sines become cosines with a phase shift), everything else is left to the general evaluation; the
+    recognised form, evaluated with fast_cos, reproduces the expression"""
+    L = capi.lib()
+    rng = np.random.default_rng(3)
+    x, y = rng.uniform(-2, 2, 200), rng.uniform(-2, 2, 200)
+    pi = np.pi
+    cases = {
+        problems.ESV2007_FORCE: 0.5 * pi * pi * np.cos(0.5 * pi * x) * np.cos(0.5 * pi * y),
+        "cos(0.5*pi*x[0])*cos(0.5*pi*x[1])": np.cos(0.5 * pi * x) * np.cos(0.5 * pi * y),
+        "-0.5*pi*sin(0.5*pi*x[0])*cos(0.5*pi*x[1])": -0.5 * pi * np.sin(0.5 * pi * x) * np.cos(0.5 * pi * y),
+        "sin(2*x[0]+1)*sin(x[1]-0.25)": np.sin(2 * x + 1) * np.sin(y - 0.25),
+        "-3*sin(x[0]-x[1])": -3 * np.sin(x - y),
+        "cos(4*pi*(x[0]+0.5*x[1]))": np.cos(4 * pi * (x + 0.5 * y)),
+    }
+    for expr, want in cases.items():
+        out, valid = np.zeros(7), C.c_int()
+        capi.check(L.hdd_trig_product(expr.encode(), capi.ptr(out), C.byref(valid)))
+        assert valid.value == 1, expr
+        c, a0, b0, d0, a1, b1, d1 = out
+        args = np.concatenate([a0 * x + b0 * y + d0, a1 * x + b1 * y + d1])
+        cosv = np.empty_like(args)
+        capi.check(L.hdd_fast_cos(capi.ptr(args), C.c_int64(args.size), capi.ptr(cosv)))
+        got = c * cosv[:x.size] * cosv[x.size:]
+        assert np.abs(got - want).max() <= 1e-14 * max(1.0, np.abs(want).max()), expr
+    for expr in ("x[0]*cos(x[1])", "cos(x[0])+1", "exp(x[0])*cos(x[1])", "cos(x[0])*cos(x[1])*cos(x[0]+x[1])",
+                 "1+0.75*(sin(4*pi*(x[0]+0.5*x[1])))", "abs(x[0])"):
+        out, valid = np.zeros(7), C.c_int()
+        capi.check(L.hdd_trig_product(expr.encode(), capi.ptr(out), C.byref(valid)))
+        assert valid.value == 0, expr
