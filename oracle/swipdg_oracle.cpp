@@ -149,6 +149,11 @@ Rule2 triangle_rule(int order) {
 // ESV2007::Testcase1Force, Spe10::Model1, Indicator} objects through virtual
 // local_function(entity)->evaluate(x); here a function is sum_k coef[k] * basic_k(cell, x).
 // ------------------------------------------------------------------------------------
+// search tool only: the direction (alpha, beta) of the OS2014 factor sin(4 pi (alpha x + beta y)); the reference has (1, 1/2).
+// The ESV2007 data and the domain are invariant under the symmetries of the square, this factor is not: a grid that is the
+// mirror image of the reference's shows up for mu != 1 only (tools/os2014_mu01_search.py --symmetries).
+double g_os_dir[2] = {1.0, 0.5};
+
 enum FnKind {
   FN_ONE = 0,        // 1                                  (Constant, problems/ESV2007.hh:76-80)
   FN_CELLWISE = 1,   // value[cell]                        (Spe10::Model1 / Indicator, problems/spe10.hh:74-80,154-157)
@@ -176,7 +181,7 @@ double fn_eval(const ofn_t& f, int cell, double x, double y) {
       case FN_ONE: v = 1.0; break;
       case FN_CELLWISE: v = f.cell[k][cell]; break;
       case FN_ESV_FORCE: v = 0.5 * kPi * kPi * std::cos(0.5 * kPi * x) * std::cos(0.5 * kPi * y); break;
-      case FN_OS_SIN: v = std::sin(4.0 * kPi * (x + 0.5 * y)); break;
+      case FN_OS_SIN: v = std::sin(4.0 * kPi * (g_os_dir[0] * x + g_os_dir[1] * y)); break;
       case FN_ESV_EXACT: v = std::cos(0.5 * kPi * x) * std::cos(0.5 * kPi * y); break;
       case FN_X: v = x; break;
       case FN_Y: v = y; break;
@@ -854,6 +859,10 @@ void or_set_variant(int flags, int vol_order, int face_order) {
   g_var_flags = flags;
   g_var_vol_order = vol_order;
   g_var_face_order = face_order;
+}
+void or_set_os_direction(double alpha, double beta) {
+  g_os_dir[0] = alpha;
+  g_os_dir[1] = beta;
 }
 void or_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
 int or_get_threads() { return g_threads; }

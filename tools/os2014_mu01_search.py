@@ -199,7 +199,8 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden", "os2014_mu01_search.txt"))
     ap.add_argument("--quick", action="store_true", help="restatement only")
     ap.add_argument("--amplitudes", action="store_true",
-                    help="also scan the amplitude of the problem's factor (is it the data, not the arithmetic, that differs?)")
+                    help="also scan the amplitude and the direction of the problem's factor (is it the data or the grid's orientation, "
+                         "not the arithmetic, that differs?)")
     args = ap.parse_args()
     results = []
     for name, v in variants():
@@ -228,6 +229,24 @@ def main():
                 A, 100 * deviation(res, args.levels), " ".join("%.3e" % x for x in res["energy"]),
                 " ".join("%.3e" % x for x in res[(0.1, "eta_DF_OS2014")]), " ".join("%.3e" % x for x in res[(0.1, "eta_OS2014")])))
             print(lines[-1], flush=True)
+        lines += ["", "# the eight images of the factor's direction (1, 1/2) under the symmetries of the square (equivalently: the grid",
+                  "# mirrored or rotated against the data; the ESV2007 force and the bisection grids are invariant, so the mu = 1 rows",
+                  "# could not tell): identical to three digits, the grid's orientation is not it either.", ""]
+        import ctypes as C
+        L = o.lib()
+        L.or_set_os_direction.argtypes = [C.c_double, C.c_double]
+        L.or_set_os_direction.restype = None
+        base = dict(solve_factor="exact", est_factor="exact", flags=0, vol_order=-1, face_order=-1, est_order=3)
+        try:
+            for a, b in ((1, .5), (-1, .5), (1, -.5), (-1, -.5), (.5, 1), (-.5, 1), (.5, -1), (-.5, -1)):
+                L.or_set_os_direction(a, b)
+                res = run_variant(base, args.levels)
+                lines.append("direction (%4g, %4g)  deviation %5.1f %%  energy %s  eta_DF(0.1) %s" % (
+                    a, b, 100 * deviation(res, args.levels), " ".join("%.3e" % x for x in res["energy"]),
+                    " ".join("%.3e" % x for x in res[(0.1, "eta_DF_OS2014")])))
+                print(lines[-1], flush=True)
+        finally:
+            L.or_set_os_direction(1.0, 0.5)
         lines.append("")
     text = "\n".join(lines)
     if args.out:
